@@ -1,0 +1,171 @@
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Each fixture is one trajectory of the reference (``/root/reference/demo1``) driven by injected
+Philox draws through ``oracle/ref_oracle.RefStepper`` -- i.e. the reference's own counts,
+``weighted_choice``, ``perform_given_move`` and incremental move caches -- plus the reference's
+view of the lattice at the end (status plane, full slot table from its move caches, class
+counts) and a ``sim.validate()`` pass.  State-generator fixtures come from the reference's
+``gen_random_state`` under ``random.Random(seed)``.
+
+The fixtures pin (a) the CPU restatement oracle/kmc_oracle.c and (b) the CUDA engine, both of
+which must reproduce every event (class, site, slot), the fsum total rate, and the final lattice
+bit for bit.
+"""
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import canon  # noqa: E402
+import philox  # noqa: E402
+import ref_oracle  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+TEST_CFG_RULES = {          # /root/reference/test-cfg.yaml:11-29 with the stale 'Rule' prefix removed
+    "CreateMonovacancy": {"rate": {"from-double": 10, "make-empty": 300}},
+    "FillMonovacancy": {"rate": {"make-double": 100, "from-empty": 100}},
+    "CreateDivacancy": {"rate": 10},
+    "MoveDivacancy": {"rate": {"natural": 12.0, "missing-metal": 3.0, "missing-comb": 7.0,
+                               "missing-both": 7.0}},
+    "CreateTrefoil": {"rate": 5000},
+    "DestroyTrefoil": {"rate": 400},
+}
+ALL_RULES = dict(TEST_CFG_RULES, FlipMonovacancy={"rate": 55.0}, FillDivacancy={"rate": 20.0})
+WSE2_RULES = {              # /root/reference/config/WSe2.yaml:2-24 minus the stub MoveMonovacancy
+    "CreateMonovacancy": {"barrier": {"from-double": 6.72584072, "make-empty": 6.72584072}},
+    "FlipMonovacancy": {"barrier": 3.41217502},
+    "MoveDivacancy": {"barrier": {"natural": 2.25, "missing-metal": 2.11199155,
+                                  "missing-comb": 2.52009312, "missing-both": 2.25}},
+    "CreateTrefoil": {"barrier": 3.12293677},
+    "DestroyTrefoil": {"barrier": 4.43051273},
+}
+# equal weights on a pristine lattice: 10*N == 5*(2N) == 10*N -> exercises the stable tie-break
+TIE_RULES = {
+    "CreateMonovacancy": {"rate": {"from-double": 5, "make-empty": 40}},
+    "CreateDivacancy": {"rate": 10},
+    "FillDivacancy": {"rate": 40},
+    "FillMonovacancy": {"rate": {"make-double": 40, "from-empty": 20}},
+    "FlipMonovacancy": {"rate": 40},
+    "MoveDivacancy": {"rate": {"natural": 10, "missing-metal": 10, "missing-comb": 10, "missing-both": 10}},
+    "CreateTrefoil": {"rate": 40},
+    "DestroyTrefoil": {"rate": 40},
+}
+
+
+def exact_state(dim, frac_div, frac_mono, seed):
+    """Our canonical 'exact' initial state recipe (host-side): shuffle the node
+    list with random.Random(seed), first round(fd*N) nodes -> divacancy, next -> monovacancy with
+    layer rng.choice([1, 2])."""
+    rng = random.Random(seed)
+    n = dim[0] * dim[1]
+    nodes = list(range(n))
+    rng.shuffle(nodes)
+    nd = round(frac_div * n)
+    nm = round((frac_div + frac_mono) * n)
+    st = np.zeros(n, dtype=np.uint8)
+    for i in nodes[:nd]:
+        st[i] = 3
+    for i in nodes[nd:nm]:
+        st[i] = rng.choice([1, 2])
+    return st
+
+
+def trajectory(name, dim, rules, status0, seed, nsteps, temperature=None, rule_order=None, replica=0):
+    st = ref_oracle.RefStepper(list(map(int, status0)), dim, rules, temperature=temperature,
+                               rule_order=rule_order)
+    d = philox.draws(seed, replica, 0, nsteps)
+    ev = np.zeros(nsteps, dtype=[("cls", "u1"), ("slot", "u1"), ("site", "<u4"), ("total_rate", "<f8")])
+    infos = []
+    counts0 = st.counts()
+    for t in range(nsteps):
+        r = st.step(float(d[t, 0]), float(d[t, 1]))
+        ev[t] = (r["class"], r["slot"], r["site"], r["total_rate"])
+        if t < 64:
+            infos.append({"rule": r["rule"], "kind": r["kind"],
+                          "move": json.loads(json.dumps(r["info"], default=list))})
+    with ref_oracle.ref_modules():
+        st.validate()
+    meta = {
+        "name": name, "dim": list(dim), "seed": seed, "replica": replica, "nsteps": nsteps,
+        "temperature": temperature, "rules": rules,
+        "rule_order": rule_order or list(rules), "class_order": st.class_order(),
+        "n_ties": st.n_ties, "infos": infos,
+        "source": "unmodified /root/reference/demo1 driven by oracle/ref_oracle.py",
+    }
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(
+        path, meta=json.dumps(meta), rates=np.array(st.rates(), dtype=np.float64),
+        status0=np.asarray(status0, dtype=np.uint8), events=ev, counts0=np.array(counts0, dtype=np.int64),
+        status1=np.array(st.status(), dtype=np.uint8), counts1=np.array(st.counts(), dtype=np.int64),
+        slots1=np.array(st.slot_table(), dtype=np.uint8))
+    hist = np.bincount(ev["cls"], minlength=canon.N_CLASSES)
+    print("%-28s dim=%s steps=%d ties=%d hist=%s (%d bytes)" % (
+        name, dim, nsteps, st.n_ties, hist.tolist(), os.path.getsize(path)))
+
+
+def state_gen_fixtures():
+    """gen_random_state of the reference under random.Random(seed) (state.py:329-378)."""
+    stmod = ref_oracle.ref()["state"]
+    out = {}
+    cases = [
+        ("exact", (12, 9), {"divacancy": 0.05, "monovacancy": 0.10}, 11),
+        ("exact", (64, 64), {"divacancy": 0.07, "monovacancy": 0.03}, 20261019),
+        ("exact", (7, 5), {"divacancy": 0.0, "monovacancy": 0.5}, 3),
+        ("approx", (12, 9), {"divacancy": 0.05, "monovacancy": 0.10}, 11),
+        ("approx", (16, 16), {"divacancy": 0.2, "monovacancy": 0.3}, 5),
+        ("approx", (8, 8), {"divacancy": 0.0, "monovacancy": 0.0}, 1),
+    ]
+    metas = []
+    for i, (mode, dim, params, seed) in enumerate(cases):
+        # the reference iterates RANDOM_PARAMS (a list built from a set); only the *values* sorted by
+        # rate matter in 'exact', and 'approx' sorts by weight inside weighted_choice -- with the
+        # distinct fractions used here neither depends on hash order.
+        state = stmod.gen_random_state(dim, mode, dict(params), rng=random.Random(seed))
+        status = np.array(ref_oracle.status_from_state(state), dtype=np.uint8)
+        out["status_%d" % i] = status
+        metas.append({"mode": mode, "dim": list(dim), "params": params, "seed": seed})
+    path = os.path.join(OUT, "state_gen.npz")
+    np.savez_compressed(path, meta=json.dumps(metas), **out)
+    print("state_gen.npz: %d cases (%d bytes)" % (len(cases), os.path.getsize(path)))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # 1. all eight rules, pristine start: trefoils are created and destroyed along the way
+    trajectory("allrules_8x8", (8, 8), ALL_RULES, np.zeros(64, np.uint8), seed=7, nsteps=3000)
+    # 2. the reference's own test-cfg.yaml rule set, ragged odd dims
+    trajectory("testcfg_5x7", (5, 7), TEST_CFG_RULES, np.zeros(35, np.uint8), seed=11, nsteps=2000)
+    trajectory("testcfg_9x5", (9, 5), TEST_CFG_RULES, exact_state((9, 5), 0.2, 0.2, 5), seed=12, nsteps=2000)
+    # 3. WSe2 barriers at 1500 K on a seeded-defect lattice (BASELINE config 2 recipe, smaller)
+    trajectory("wse2_16x16", (16, 16), WSE2_RULES, exact_state((16, 16), 0.05, 0.05, 20261019),
+               seed=20261019, nsteps=3000, temperature=1500.0)
+    trajectory("wse2_64x64", (64, 64), WSE2_RULES, exact_state((64, 64), 0.05, 0.05, 20261019),
+               seed=20261019, nsteps=2000, temperature=1500.0)
+    # hotter, denser: trefoil create/destroy and all four MoveDivacancy kinds are live
+    trajectory("wse2_hot_24x24", (24, 24), WSE2_RULES, exact_state((24, 24), 0.30, 0.05, 9),
+               seed=99, nsteps=3000, temperature=4000.0)
+    # 4. equal class weights -> stable tie-break by canonical class order; two rule orders
+    trajectory("ties_7x11", (7, 11), TIE_RULES, np.zeros(77, np.uint8), seed=3, nsteps=2500)
+    trajectory("ties_reordered_7x11", (7, 11), TIE_RULES, np.zeros(77, np.uint8), seed=3, nsteps=2500,
+               rule_order=["DestroyTrefoil", "FlipMonovacancy", "CreateDivacancy", "MoveDivacancy",
+                           "FillMonovacancy", "CreateMonovacancy", "CreateTrefoil", "FillDivacancy"])
+    # 5. mixed rules at the headline lattice size
+    trajectory("allrules_64x64", (64, 64), ALL_RULES, exact_state((64, 64), 0.05, 0.05, 1), seed=5,
+               nsteps=2000)
+    # 6. non-square, larger than a warp's row span
+    trajectory("allrules_40x70", (40, 70), ALL_RULES, exact_state((40, 70), 0.1, 0.1, 2), seed=6,
+               nsteps=1500, replica=3)
+    state_gen_fixtures()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""CPU oracle (oracle/kmc_oracle.c) pinned against fixtures produced by the unmodified reference.
+
+Bar: bit-exact for class / site / slot / lattice / counts; total_rate is the exactly rounded
+math.fsum (sim.py:138), also compared bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+import kmc_oracle as ko  # noqa: E402
+import philox  # noqa: E402
+from util_golden import load, trajectory_names, enabled_classes  # noqa: E402
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox.philox4x32_10(*[[c] for c in ctr], [key[0]], [key[1]])
+        assert tuple(int(x[0]) for x in got) == want
+
+
+def test_c_draws_match_numpy_philox():
+    for seed, rep, step0 in [(0, 0, 0), (20261019, 5, 0), ((1 << 40) + 17, 123456, (1 << 33) + 5)]:
+        d = philox.draws(seed, rep, step0, 64)
+        for t in range(64):
+            assert ko.draw(seed, rep, step0 + t) == (d[t, 0], d[t, 1])
+    assert ((d >= 0) & (d < 1)).all()
+
+
+@pytest.mark.parametrize("name", trajectory_names())
+def test_trajectory_matches_reference(name):
+    g = load(name)
+    m = g["meta"]
+    o = ko.Oracle(m["dim"], g["rates"], m["class_order"], g["status0"])
+    en = enabled_classes(m)
+    assert (o.counts()[en] == g["counts0"][en]).all()
+    done, ev = o.run_philox(m["seed"], m["replica"], 0, m["nsteps"])
+    assert done == m["nsteps"]
+    want = g["events"]
+    for f in ("cls", "site", "slot"):
+        bad = np.nonzero(ev[f] != want[f])[0]
+        assert bad.size == 0, "%s: first %s mismatch at step %d" % (name, f, bad[0])
+    assert (ev["total_rate"].view(np.uint64) == want["total_rate"].view(np.uint64)).all()
+    assert (o.status() == g["status1"]).all()
+    assert (o.counts()[en] == g["counts1"][en]).all()
+    # slot table: the reference only holds slots of enabled rules
+    slots = o.slots()
+    mask = np.isin(slots, en)
+    assert (np.where(mask, slots, 0xFF) == g["slots1"]).all()
+    assert o.validate() == 0
+    assert o.ties() == m["n_ties"]
+    # naive prefix-sum total stays within the north-star tolerance of fsum
+    rel = np.abs(ev["total_naive"] - ev["total_rate"]) / ev["total_rate"]
+    assert rel.max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["allrules_8x8", "wse2_hot_24x24", "allrules_40x70"])
+def test_incremental_equals_full_sweep(name):
+    """kmco_validate restates KmcSim.validate (sim.py:159-168)."""
+    g = load(name)
+    m = g["meta"]
+    o = ko.Oracle(m["dim"], g["rates"], m["class_order"], g["status0"])
+    for chunk in range(10):
+        o.run_philox(m["seed"] + 1, 0, chunk * 200, 200, log=False)
+        assert o.validate() == 0
+        slots, counts, rowcnt = ko.sweep(o.status(), m["dim"])
+        assert (slots == o.slots()).all() and (counts == o.counts()).all()
+        assert (rowcnt.sum(axis=0) == counts).all()
+
+
+def test_rank_search_equals_linear_scan():
+    g = load("allrules_64x64")
+    m = g["meta"]
+    o = ko.Oracle(m["dim"], g["rates"], m["class_order"], g["status1"])
+    counts = o.counts()
+    slots = o.slots()
+    rng = np.random.default_rng(0)
+    for c in range(13):
+        if counts[c] == 0:
+            continue
+        flat = np.argwhere(slots == c)       # already (site, slot) lexicographic
+        for r in rng.integers(0, counts[c], size=20):
+            rc, site, slot = o.rank_to_move_scan(c, int(r))
+            assert rc == 0 and (site, slot) == tuple(flat[r])
+
+
+def test_zero_total_weight_is_reported():
+    # only FillDivacancy enabled on a pristine lattice: nothing can happen (kmc.py:31-32)
+    rates = [0.0] * 13
+    rates[1] = 5.0
+    o = ko.Oracle((5, 5), rates, [1], np.zeros(25, np.uint8))
+    rc, ev = o.step(0.3, 0.3)
+    assert rc == 1 and ev["cls"] == 0xFF
+    assert (o.status() == 0).all()
+
+
+def test_known_answer_first_total_rate():
+    # pristine 8x8 with test-cfg rates -> first total_rate = 64*(2*10 + 10) = 1920
+    g = load("allrules_8x8")
+    rates = np.array(g["rates"])
+    rates[1] = 0.0
+    rates[12] = 0.0
+    o = ko.Oracle((8, 8), rates, g["meta"]["class_order"], np.zeros(64, np.uint8))
+    rc, ev = o.step(0.5, 0.5)
+    assert ev["total_rate"] == 1920.0
+
+
+def test_batch_runner_matches_single():
+    g = load("wse2_16x16")
+    m = g["meta"]
+    st = np.stack([g["status0"]] * 6)
+    done, hist, st = ko.run_replicas(m["dim"], g["rates"], m["class_order"], st, seed=m["seed"],
+                                     nsteps=500, threads=3)
+    assert done == 6 * 500
+    for r in range(6):
+        o = ko.Oracle(m["dim"], g["rates"], m["class_order"], g["status0"])
+        o.run_philox(m["seed"], r, 0, 500, log=False)
+        assert (o.status() == st[r]).all()
+    assert hist.sum() == done
