@@ -1,0 +1,171 @@
+/*
+ * kmc_b200.h -- C ABI of the B200-native KMC engine for the kmc-dichalcogen hot path.
+ *
+ * The reference (ExpHP/kmc-dichalcogen) is pure Python and has NO plugin / FFI interface: the seam
+ * this library replaces is the Python object `KmcSim` as driven by `demo1/__main__.py:run`
+ * (reference demo1/__main__.py:123,129,141,148) and the callbacks it fans out to.  Every entry
+ * point below names the reference interface it stands in for (paths relative to the reference
+ * root).  The Python host in kmc-dichalcogen_b200/demo1/ binds these with ctypes; INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns 0 on success and a
+ *     negative kmc_status on failure; kmc_last_error() gives the message (thread-local).
+ *   - host buffers belong to the caller; device memory belongs to the handle.
+ *   - one host thread per handle; work is ordered on the handle's own CUDA stream.
+ *   - lattice: axial hex coordinates (a, b), 0 <= a < dim0, 0 <= b < dim1, periodic; site index
+ *     i = a*dim1 + b (reference demo1/state.py:388-390,461-464).  dim0, dim1 >= 5 and != 6
+ *     (smaller lattices alias the trefoil geometry under PBC; 6 makes collinear "triangles").
+ *   - site status byte: 0 pristine, 1 / 2 monovacancy in layer 1 / 2, 3 divacancy (these equal the
+ *     reference's vacant layer set, demo1/state.py:22-23,171-177), 4 + 3*orientation + role for a
+ *     trefoil member (orientation 0: {p, p+(2,0), p+(0,2)}, 1: {p, p+(2,0), p+(2,-2)}; role = index
+ *     in that list; role 0 is the anchor p).
+ *   - event classes (rule:kind) 0..12 and per-site move slots 0..16: see the tables at the end.
+ */
+#ifndef KMC_B200_H
+#define KMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_N_CLASSES 13
+#define KMC_N_SLOTS   17
+#define KMC_SLOT_NONE 0xFF
+#define KMC_CLASS_NONE 0xFF      /* event.cls when the total rate is zero (reference kmc.py:31-32) */
+
+typedef enum {
+    KMC_OK = 0,
+    KMC_ERR_ARG = -1,            /* bad argument (RuntimeError('config: ...') territory)              */
+    KMC_ERR_CUDA = -2,           /* CUDA runtime failure (message carries cudaGetErrorString)         */
+    KMC_ERR_STATE = -3,          /* invalid lattice (bad status byte / broken trefoil)                */
+    KMC_ERR_VALIDATE = -4,       /* incremental tables != from-scratch sweep (AssertionError)         */
+    KMC_ERR_NO_DEVICE = -5,      /* no usable CUDA device: there is NO CPU fallback                   */
+    KMC_ERR_ZERO_RATE = -6       /* some replica reached total rate 0 (ValueError, kmc.py:32)         */
+} kmc_status;
+
+/* Event log records.  total_rate is the sequential fp64 prefix-sum total the selection used
+ * (reference kmc.py:41-42); the reference *logs* math.fsum of the same weights (sim.py:138), which
+ * the host recomputes exactly from `counts` (full records) -- the two agree to <= 1e-12 relative. */
+typedef struct {
+    uint32_t site;               /* anchor site of the move                                          */
+    uint8_t  cls;                /* event class 0..12, or KMC_CLASS_NONE                             */
+    uint8_t  slot;               /* move slot 0..16                                                  */
+    uint16_t flags;              /* bit0: the class draw landed exactly on a cumulative boundary     */
+    double   total_rate;
+} kmc_event_compact;             /* 16 bytes */
+
+typedef struct {
+    uint32_t site;
+    uint8_t  cls;
+    uint8_t  slot;
+    uint16_t flags;
+    double   total_rate;
+    uint32_t counts[KMC_N_CLASSES];   /* moves per class BEFORE the event (sim.py:90-104)          */
+    uint32_t pad;
+} kmc_event_full;                /* 72 bytes */
+
+enum { KMC_LOG_NONE = 0, KMC_LOG_COMPACT = 1, KMC_LOG_FULL = 2 };
+
+typedef struct kmc_engine kmc_engine;
+
+const char *kmc_last_error(void);
+int kmc_device_count(void);
+
+/* KmcSim.__init__ (reference demo1/sim.py:39-44) for `n_replicas` independent trajectories on
+ * CUDA device `device`.  class_rate[c] is the fp64 rate of class c (the host computes Arrhenius
+ * rates with math.exp exactly as sim.py:179-181 so bits match); classes of disabled rules get 0.
+ * class_order lists the enabled class ids in weighted_choice input order (rules in config order,
+ * kinds in Rule.kinds() order): it is the tie-break among equal weights (kmc.py:35 is a stable
+ * sort).  The lattice starts pristine. */
+int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int n_replicas,
+               const double *class_rate /*[13]*/, const int *class_order, int n_order);
+int kmc_destroy(kmc_engine *h);
+
+/* KmcSim.initialize(state) (sim.py:46-54): replace the lattices.  host: [n_replicas][dim0*dim1]. */
+int kmc_upload_state(kmc_engine *h, const uint8_t *host_status);
+int kmc_download_state(kmc_engine *h, uint8_t *host_status);
+/* same, but the source/destination is a device pointer on the handle's device */
+int kmc_set_state_device(kmc_engine *h, const void *dev_status);
+int kmc_get_state_device(kmc_engine *h, void *dev_status);
+
+/* Full enumeration = Rule.initialize_moves for all rules (sim.py:204-206, rules.py:19-21,43-45), the
+ * `--no-incremental` sweep (sim.py:114-115): status planes -> 17 slot planes (class id or 0xFF per
+ * site), per-row and per-replica class counts.  Everything stays on the device. */
+int kmc_sweep(kmc_engine *h);
+/* IncrementalMoveCache.undecided_counts for every rule (incremental.py:103-110): [n_replicas][13],
+ * from the last kmc_sweep(). */
+int kmc_get_counts(kmc_engine *h, int64_t *out);
+/* IncrementalMoveCache.undecided_sets (incremental.py:112-123) as a table: [n_replicas][n][17]
+ * class id or 0xFF, from the last kmc_sweep().  Parity / debug. */
+int kmc_get_slots(kmc_engine *h, uint8_t *out);
+/* per-row class counts of the last kmc_sweep(): [n_replicas][dim0][13] */
+int kmc_get_row_counts(kmc_engine *h, uint32_t *out);
+
+/* KmcSim.perform_random_move x nsteps (sim.py:106-143) for every replica, incremental tables held
+ * in shared memory, many events per launch.  Draws: Philox4x32-10, key = (seed lo32, replica0 + r),
+ * counter = (step lo32, step hi32, seed hi32, 0); u1 = class draw, u2 = in-class draw (53-bit).
+ * Step numbering continues across calls.  events: host buffer [n_replicas][nsteps] of
+ * kmc_event_compact / kmc_event_full according to log_mode, or NULL with KMC_LOG_NONE.
+ * validate != 0 re-enumerates every lattice at the end of the launch and compares with the
+ * incrementally maintained tables (KmcSim.validate, sim.py:159-168) -> KMC_ERR_VALIDATE.
+ * Returns KMC_ERR_ZERO_RATE if a replica stopped early (see kmc_get_steps_done). */
+int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
+            void *events, int validate);
+/* Same, with the caller's uniform draws u[n_replicas][nsteps][2] (host buffer): the seam the
+ * reference offers through weighted_choice(..., rng=) (kmc.py:21) and get_random_key(..., rng=)
+ * (incremental.py:283). */
+int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events,
+                   int validate);
+/* KmcSim.perform_given_move (sim.py:145-157) on one replica: apply move (site, slot). */
+int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot);
+
+/* The `--no-incremental` event (sim.py:114-143) on a lattice of any size held in HBM: full sweep,
+ * class selection + hierarchical in-class rank search, apply.  Same draws and records as kmc_run. */
+int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
+                  void *events);
+
+/* statistics: events per class summed over replicas [13]; per replica [n_replicas][13];
+ * events done per replica [n_replicas]; boundary ties summed over replicas. */
+int kmc_get_histogram(kmc_engine *h, int64_t *out);
+int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out);
+int kmc_get_steps_done(kmc_engine *h, int64_t *out);
+int kmc_get_ties(kmc_engine *h, int64_t *out);
+int kmc_reset_stats(kmc_engine *h);
+
+/* measurement helpers: CUDA events recorded on the handle's stream */
+int kmc_sync(kmc_engine *h);
+int kmc_timer_start(kmc_engine *h);
+int kmc_timer_stop(kmc_engine *h, float *elapsed_ms);   /* synchronises */
+/* number of kernels this library has launched on the handle so far */
+int kmc_get_launch_count(kmc_engine *h, int64_t *out);
+/* raw device pointers (for callers that share device memory, e.g. torch tensors / NCCL) */
+int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **row_counts,
+                            void **histogram);
+/* tuning knob: warps (replicas) per CTA of the replica kernel; 0 = automatic */
+int kmc_set_warps_per_block(kmc_engine *h, int warps);
+
+/*
+ * Event classes (reference demo1/rules.py):           Move slots per site (move key in the reference):
+ *   0  CreateDivacancy:natural      (:60-75)            0      CreateDivacancy        node
+ *   1  FillDivacancy:natural        (:77-92)            1      FillDivacancy          node
+ *   2  MoveDivacancy:natural        (:94-136)           2,3    CreateMonovacancy      (node, layer 1/2, old|layer)
+ *   3  MoveDivacancy:missing-metal                      4,5    FillMonovacancy        (node, layer 1/2, old&~layer)
+ *   4  MoveDivacancy:missing-comb                       6      FlipMonovacancy        node
+ *   5  MoveDivacancy:missing-both                       7..12  MoveDivacancy          (node, nbr_k), k = slot-7, in
+ *   6  CreateTrefoil:natural        (:141-174)                                        neighbors_and_mutuals order
+ *   7  DestroyTrefoil:natural       (:176-198)                                        (state.py:443-459)
+ *   8  CreateMonovacancy:from-double(:238-255)          13,14  CreateTrefoil          {p,p+(2,0),p+(0,2)} / {p,p+(2,0),p+(2,-2)}
+ *   9  CreateMonovacancy:make-empty                     15,16  DestroyTrefoil         same two triangles
+ *   10 FillMonovacancy:make-double  (:257-274)
+ *   11 FillMonovacancy:from-empty
+ *   12 FlipMonovacancy:natural      (:277-293)
+ * In-class order (the rank the in-class draw indexes): site ascending, then slot ascending.
+ */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMC_B200_H */

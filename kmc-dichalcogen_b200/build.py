@@ -1,0 +1,41 @@
+"""Build libkmc_b200.so (the CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+The library is plain CUDA runtime code (no torch dependency) so that any host language can bind it.
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with gpurun.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libkmc_b200.so")
+SOURCES = ["capi.cu"]       # single translation unit; the .cuh files are included
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",              # fp64 class weights / prefix sums must not be contracted
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+]
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps.append(os.path.join(os.path.dirname(HERE), "include", "kmc_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not _stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

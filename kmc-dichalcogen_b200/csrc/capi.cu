@@ -1,0 +1,516 @@
+// capi.cu -- the C ABI (include/kmc_b200.h) over the CUDA kernels.  No torch, no C++ types in the
+// signatures; errors become status codes + a thread-local message.  There is NO CPU fallback: without
+// a CUDA device every entry point that computes fails with KMC_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kmc_b200.h"
+#include "kmc_common.cuh"
+#include "noinc_kernel.cuh"
+#include "replica_kernel.cuh"
+#include "sweep_kernel.cuh"
+
+using namespace kmc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                     __FILE__, __LINE__);                                                      \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver           \
+                            ? KMC_ERR_NO_DEVICE : KMC_ERR_CUDA, b_);                           \
+        }                                                                                      \
+    } while (0)
+
+struct kmc_engine {
+    int device = 0, d0 = 0, d1 = 0, n = 0, R = 0;
+    double rate[NC];
+    int order_pos[NC];
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t *d_status = nullptr;
+    uint8_t *d_slots = nullptr;              // [R][17][n], allocated on first sweep
+    uint32_t *d_rowcnt = nullptr;            // [R][d0][16]
+    unsigned long long *d_counts = nullptr;  // [R][13]
+    unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr;
+    uint32_t *d_flags = nullptr;
+    void *d_events = nullptr; size_t events_cap = 0;
+    double *d_draws = nullptr; size_t draws_cap = 0;
+    int *d_result = nullptr;
+    int warps_per_block = 0;
+    long long launches = 0;
+    bool swept = false;
+    int max_smem_optin = 0;
+};
+
+extern "C" const char *kmc_last_error(void) { return g_err.c_str(); }
+
+extern "C" int kmc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+static int bind(kmc_engine *h) {
+    if (!h) return fail(KMC_ERR_ARG, "null engine handle");
+    CU(cudaSetDevice(h->device));
+    return KMC_OK;
+}
+
+extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int n_replicas,
+                          const double *class_rate, const int *class_order, int n_order)
+{
+    if (!out) return fail(KMC_ERR_ARG, "kmc_create: out is null");
+    *out = nullptr;
+    if (dim0 < 5 || dim1 < 5 || dim0 == 6 || dim1 == 6)
+        return fail(KMC_ERR_ARG, "kmc_create: lattice dimensions must be >= 5 and != 6 "
+                                 "(smaller lattices alias the trefoil geometry under periodic boundaries)");
+    if ((long long)dim0 * dim1 > 0x7FFFFFFFLL / 32) return fail(KMC_ERR_ARG, "kmc_create: lattice too large");
+    if (n_replicas < 1) return fail(KMC_ERR_ARG, "kmc_create: n_replicas must be >= 1");
+    if (!class_rate || (n_order > 0 && !class_order) || n_order < 0 || n_order > NC)
+        return fail(KMC_ERR_ARG, "kmc_create: bad class_rate / class_order");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(KMC_ERR_NO_DEVICE, "kmc_create: no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(KMC_ERR_ARG, "kmc_create: bad device index");
+    kmc_engine *h = new kmc_engine();
+    h->device = device; h->d0 = dim0; h->d1 = dim1; h->n = dim0 * dim1; h->R = n_replicas;
+    for (int c = 0; c < NC; c++) { h->rate[c] = 0.0; h->order_pos[c] = -1; }
+    for (int i = 0; i < n_order; i++) {
+        int c = class_order[i];
+        if (c < 0 || c >= NC || h->order_pos[c] >= 0) { delete h; return fail(KMC_ERR_ARG, "kmc_create: class_order must list distinct class ids 0..12"); }
+        if (!(class_rate[c] >= 0.0)) { delete h; return fail(KMC_ERR_ARG, "kmc_create: negative or NaN rate"); }   // kmc.py:37-39
+        h->order_pos[c] = i; h->rate[c] = class_rate[c];
+    }
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&h->ev0));
+    CU(cudaEventCreate(&h->ev1));
+    const size_t R = (size_t)n_replicas;
+    CU(cudaMalloc(&h->d_status, R * h->n));
+    CU(cudaMalloc(&h->d_counts, R * NC * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_steps, R * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_hist, R * NC * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_ties, R * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_flags, R * sizeof(uint32_t)));
+    CU(cudaMalloc(&h->d_result, sizeof(int)));
+    CU(cudaMemsetAsync(h->d_status, 0, R * h->n, h->stream));
+    CU(cudaMemsetAsync(h->d_counts, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return KMC_OK;
+}
+
+extern "C" int kmc_destroy(kmc_engine *h)
+{
+    if (!h) return KMC_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
+    cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
+    cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return KMC_OK;
+}
+
+// ---- lattice transfer ---------------------------------------------------------------------------
+static int check_state_host(const kmc_engine *h, const uint8_t *s)
+{
+    // State invariants (reference demo1/state.py:102-149): known status codes, complete trefoils
+    static const int TM[2][3][2] = {{{0, 0}, {2, 0}, {0, 2}}, {{0, 0}, {2, 0}, {2, -2}}};
+    for (int r = 0; r < h->R; r++) {
+        const uint8_t *st = s + (size_t)r * h->n;
+        for (int i = 0; i < h->n; i++) {
+            int v = st[i];
+            if (v > 9) return fail(KMC_ERR_STATE, "invalid status byte (> 9)");
+            if (v >= 4) {
+                int o = (v - 4) / 3, role = (v - 4) % 3;
+                int a = i / h->d1 - TM[o][role][0], b = i % h->d1 - TM[o][role][1];
+                for (int q = 0; q < 3; q++) {
+                    int aa = ((a + TM[o][q][0]) % h->d0 + h->d0) % h->d0;
+                    int bb = ((b + TM[o][q][1]) % h->d1 + h->d1) % h->d1;
+                    if (st[aa * h->d1 + bb] != 4 + 3 * o + q)
+                        return fail(KMC_ERR_STATE, "incomplete trefoil in the uploaded lattice");
+                }
+            }
+        }
+    }
+    return KMC_OK;
+}
+
+extern "C" int kmc_upload_state(kmc_engine *h, const uint8_t *host_status)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!host_status) return fail(KMC_ERR_ARG, "kmc_upload_state: null buffer");
+    rc = check_state_host(h, host_status); if (rc) return rc;
+    CU(cudaMemcpyAsync(h->d_status, host_status, (size_t)h->R * h->n, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->swept = false;
+    return KMC_OK;
+}
+
+extern "C" int kmc_download_state(kmc_engine *h, uint8_t *host_status)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!host_status) return fail(KMC_ERR_ARG, "kmc_download_state: null buffer");
+    CU(cudaMemcpyAsync(host_status, h->d_status, (size_t)h->R * h->n, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!dev_status) return fail(KMC_ERR_ARG, "kmc_set_state_device: null pointer");
+    CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    h->swept = false;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!dev_status) return fail(KMC_ERR_ARG, "kmc_get_state_device: null pointer");
+    CU(cudaMemcpyAsync(dev_status, h->d_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+// ---- K1/K2 sweep ---------------------------------------------------------------------------------
+static int sweep_launch(kmc_engine *h, bool with_slots)
+{
+    const size_t R = (size_t)h->R;
+    if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * RCG_STRIDE * sizeof(uint32_t)));
+    if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * NS * h->n));
+    CU(cudaMemsetAsync(h->d_rowcnt, 0, R * h->d0 * RCG_STRIDE * sizeof(uint32_t), h->stream));
+    SweepParams p;
+    p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
+    p.status = h->d_status; p.slots = with_slots ? h->d_slots : nullptr; p.rowcnt = h->d_rowcnt;
+    if ((h->d1 & 3) == 0) {
+        p.total_words = (long long)R * (h->n >> 2);
+        const long long blocks = (p.total_words + 255) / 256;
+        kmc_sweep_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    } else {
+        p.total_words = 0;
+        const long long blocks = ((long long)R * h->n + 255) / 256;
+        kmc_sweep_kernel_generic<<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    kmc_reduce_counts_kernel<<<h->R, 256, 0, h->stream>>>(h->d_rowcnt, h->d0, h->R, h->d_counts);
+    CU(cudaGetLastError());
+    h->launches += 2;
+    return KMC_OK;
+}
+
+extern "C" int kmc_sweep(kmc_engine *h)
+{
+    int rc = bind(h); if (rc) return rc;
+    rc = sweep_launch(h, true); if (rc) return rc;
+    h->swept = true;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_counts(kmc_engine *h, int64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_counts: call kmc_sweep first");
+    CU(cudaMemcpyAsync(out, h->d_counts, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_slots(kmc_engine *h, uint8_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!h->swept || !h->d_slots) return fail(KMC_ERR_ARG, "kmc_get_slots: call kmc_sweep first");
+    std::vector<uint8_t> planes((size_t)NS * h->n);
+    for (int r = 0; r < h->R; r++) {
+        CU(cudaMemcpyAsync(planes.data(), h->d_slots + (size_t)r * NS * h->n, planes.size(),
+                           cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        uint8_t *o = out + (size_t)r * h->n * NS;
+        for (int j = 0; j < NS; j++)
+            for (int i = 0; i < h->n; i++) o[(size_t)i * NS + j] = planes[(size_t)j * h->n + i];
+    }
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_row_counts(kmc_engine *h, uint32_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_row_counts: call kmc_sweep first");
+    std::vector<uint32_t> tmp((size_t)h->R * h->d0 * RCG_STRIDE);
+    CU(cudaMemcpyAsync(tmp.data(), h->d_rowcnt, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < (size_t)h->R * h->d0; i++)
+        for (int c = 0; c < NC; c++) out[i * NC + c] = tmp[i * RCG_STRIDE + c];
+    return KMC_OK;
+}
+
+// ---- K3/K4 replica kernel ------------------------------------------------------------------------
+static size_t record_size(int log_mode) {
+    return log_mode == KMC_LOG_FULL ? sizeof(kmc_event_full) : log_mode == KMC_LOG_COMPACT ? sizeof(kmc_event_compact) : 0;
+}
+
+static int ensure_events(kmc_engine *h, size_t bytes) {
+    if (bytes > h->events_cap) {
+        if (h->d_events) CU(cudaFree(h->d_events));
+        h->d_events = nullptr; h->events_cap = 0;
+        CU(cudaMalloc(&h->d_events, bytes));
+        h->events_cap = bytes;
+    }
+    return KMC_OK;
+}
+
+static int check_flags(kmc_engine *h, bool check_validate)
+{
+    std::vector<uint32_t> fl(h->R);
+    CU(cudaMemcpyAsync(fl.data(), h->d_flags, fl.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    int zero = -1, bad = -1;
+    for (int r = 0; r < h->R; r++) {
+        if ((fl[r] & FLAG_VALIDATE) && bad < 0) bad = r;
+        if ((fl[r] & FLAG_ZERO_RATE) && zero < 0) zero = r;
+    }
+    char b[256];
+    if (check_validate && bad >= 0) {
+        snprintf(b, sizeof b, "validation failed: incremental move tables of replica %d differ from a "
+                              "from-scratch enumeration", bad);
+        return fail(KMC_ERR_VALIDATE, b);
+    }
+    if (zero >= 0) {
+        snprintf(b, sizeof b, "Cannot choose from total weight of zero! (replica %d)", zero);
+        return fail(KMC_ERR_ZERO_RATE, b);
+    }
+    return KMC_OK;
+}
+
+static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32_t replica0,
+                          const double *d_draws, int log_mode, void *host_events, int validate)
+{
+    if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
+    if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
+    if (log_mode != KMC_LOG_NONE && !host_events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
+    const size_t wbytes = replica_warp_bytes(h->d0, h->d1);
+    if (wbytes > (size_t)h->max_smem_optin) {
+        char b[256];
+        snprintf(b, sizeof b, "lattice %dx%d needs %zu B of shared memory per replica (limit %d): use kmc_run_noinc",
+                 h->d0, h->d1, wbytes, h->max_smem_optin);
+        return fail(KMC_ERR_ARG, b);
+    }
+    int W = h->warps_per_block > 0 ? h->warps_per_block : 8;
+    while (W > 1 && W * wbytes > (size_t)h->max_smem_optin) W--;
+    if (W > 32) W = 32;
+    const size_t smem = W * wbytes;
+    const size_t rs = record_size(log_mode);
+    if (rs) { int rc = ensure_events(h, rs * (size_t)h->R * (size_t)nsteps); if (rc) return rc; }
+
+    ReplicaParams p;
+    p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
+    p.status = h->d_status;
+    for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+    p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
+    p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
+    p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+    p.validate = validate;
+    const unsigned blocks = (unsigned)((h->R + W - 1) / W);
+    if (h->d0 == 64 && h->d1 == 64) {
+        CU(cudaFuncSetAttribute(kmc_replica_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmc_replica_kernel<64, 64><<<blocks, W * 32, smem, h->stream>>>(p);
+    } else {
+        CU(cudaFuncSetAttribute(kmc_replica_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmc_replica_kernel<0, 0><<<blocks, W * 32, smem, h->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->swept = false;
+    if (rs) {
+        CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return KMC_OK;
+}
+
+extern "C" int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
+                       void *events, int validate)
+{
+    int rc = bind(h); if (rc) return rc;
+    rc = replica_launch(h, nsteps, seed, replica0, nullptr, log_mode, events, validate); if (rc) return rc;
+    if (log_mode != KMC_LOG_NONE || validate) return check_flags(h, validate != 0);
+    return KMC_OK;       // asynchronous: statistics getters / kmc_sync order after the launch
+}
+
+extern "C" int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events,
+                              int validate)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!u) return fail(KMC_ERR_ARG, "kmc_step_draws: null draws");
+    const size_t bytes = (size_t)h->R * (size_t)nsteps * 2 * sizeof(double);
+    if (bytes > h->draws_cap) {
+        if (h->d_draws) CU(cudaFree(h->d_draws));
+        h->d_draws = nullptr; h->draws_cap = 0;
+        CU(cudaMalloc(&h->d_draws, bytes ? bytes : 16));
+        h->draws_cap = bytes;
+    }
+    CU(cudaMemcpyAsync(h->d_draws, u, bytes, cudaMemcpyHostToDevice, h->stream));
+    rc = replica_launch(h, nsteps, 0, 0, h->d_draws, log_mode, events, validate); if (rc) return rc;
+    return check_flags(h, validate != 0);
+}
+
+extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (replica < 0 || replica >= h->R || site >= (uint32_t)h->n || slot < 0 || slot >= NS)
+        return fail(KMC_ERR_ARG, "kmc_perform_given: bad replica / site / slot");
+    kmc_apply_given_kernel<<<1, 1, 0, h->stream>>>(h->d_status + (size_t)replica * h->n, h->d0, h->d1,
+                                                   (int)site, slot, h->d_result);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    int res = 0;
+    CU(cudaMemcpyAsync(&res, h->d_result, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->swept = false;
+    if (res) return fail(KMC_ERR_ARG, "kmc_perform_given: that move does not exist on the current lattice");
+    return KMC_OK;
+}
+
+// ---- the --no-incremental event on HBM-resident lattices ---------------------------------------
+extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
+                             void *events)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
+    if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
+    if (log_mode != KMC_LOG_NONE && !events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
+    const size_t rs = record_size(log_mode);
+    if (rs) { rc = ensure_events(h, rs * (size_t)h->R * (size_t)nsteps); if (rc) return rc; }
+    NoincParams p;
+    p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
+    p.status = h->d_status;
+    for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+    p.seed = seed; p.replica0 = replica0; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
+    p.nsteps = nsteps;
+    p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+    for (long long t = 0; t < nsteps; t++) {
+        rc = sweep_launch(h, false); if (rc) return rc;        // sim.py:114-115: initialize() every step
+        p.rowcnt = h->d_rowcnt; p.counts = h->d_counts; p.t = t;
+        kmc_noinc_select_apply_kernel<<<h->R, 32, 0, h->stream>>>(p);
+        CU(cudaGetLastError());
+        h->launches += 1;
+    }
+    h->swept = false;
+    if (rs) CU(cudaMemcpyAsync(events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
+    return check_flags(h, false);
+}
+
+// ---- statistics -------------------------------------------------------------------------------------
+extern "C" int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_histogram(kmc_engine *h, int64_t *out)
+{
+    std::vector<int64_t> tmp((size_t)(h ? h->R : 0) * NC);
+    int rc = kmc_get_histogram_per_replica(h, tmp.data()); if (rc) return rc;
+    for (int c = 0; c < NC; c++) out[c] = 0;
+    for (int r = 0; r < h->R; r++) for (int c = 0; c < NC; c++) out[c] += tmp[(size_t)r * NC + c];
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_steps_done(kmc_engine *h, int64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    CU(cudaMemcpyAsync(out, h->d_steps, (size_t)h->R * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_ties(kmc_engine *h, int64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    std::vector<int64_t> tmp(h->R);
+    CU(cudaMemcpyAsync(tmp.data(), h->d_ties, tmp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = 0;
+    for (int r = 0; r < h->R; r++) *out += tmp[r];
+    return KMC_OK;
+}
+
+extern "C" int kmc_reset_stats(kmc_engine *h)
+{
+    int rc = bind(h); if (rc) return rc;
+    const size_t R = (size_t)h->R;
+    CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
+    return KMC_OK;
+}
+
+// ---- measurement helpers -----------------------------------------------------------------------------
+extern "C" int kmc_sync(kmc_engine *h)
+{
+    int rc = bind(h); if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+extern "C" int kmc_timer_start(kmc_engine *h)
+{
+    int rc = bind(h); if (rc) return rc;
+    CU(cudaEventRecord(h->ev0, h->stream));
+    return KMC_OK;
+}
+extern "C" int kmc_timer_stop(kmc_engine *h, float *elapsed_ms)
+{
+    int rc = bind(h); if (rc) return rc;
+    CU(cudaEventRecord(h->ev1, h->stream));
+    CU(cudaEventSynchronize(h->ev1));
+    CU(cudaEventElapsedTime(elapsed_ms, h->ev0, h->ev1));
+    return KMC_OK;
+}
+extern "C" int kmc_get_launch_count(kmc_engine *h, int64_t *out)
+{
+    if (!h || !out) return fail(KMC_ERR_ARG, "null argument");
+    *out = h->launches;
+    return KMC_OK;
+}
+extern "C" int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **row_counts, void **histogram)
+{
+    if (!h) return fail(KMC_ERR_ARG, "null engine handle");
+    if (status) *status = h->d_status;
+    if (slots) *slots = h->d_slots;
+    if (row_counts) *row_counts = h->d_rowcnt;
+    if (histogram) *histogram = h->d_hist;
+    return KMC_OK;
+}
+extern "C" int kmc_set_warps_per_block(kmc_engine *h, int warps)
+{
+    if (!h || warps < 0 || warps > 32) return fail(KMC_ERR_ARG, "warps per block must be 0..32");
+    h->warps_per_block = warps;
+    return KMC_OK;
+}
+
+#include "hostcheck.cuh"

@@ -1,0 +1,542 @@
+// replica_kernel.cuh -- K3 + K4: fused select -> apply -> neighbourhood-refresh kernel.
+//
+// One warp owns one replica (an independent trajectory, i.e. what the reference runs as one
+// process: demo1/__main__.py:148).  The lattice (one status byte per site) and the Fenwick-style
+// hierarchy used for the in-class rank search (per-row x per-class move counts, uint16) live in
+// shared memory for the whole launch; the 13 per-class totals live in registers (lane c holds class
+// c).  Many events run per launch; HBM is touched only to load/store the lattice once per launch, to
+// fetch 16 B of draws per event in draw-injection mode, and to write event records when logging.
+//
+// One event = KmcSim.perform_random_move (reference demo1/sim.py:106-143):
+//   1. weights w_c = count_c * rate_c                       (sim.py:120-121)
+//   2. class choice: weighted_choice bit for bit            (kmc.py:21-54, util.py:32-46,65-68):
+//      drop zeros, stable ascending sort, sequential fp64 prefix sums, x = total*u1, bisect_left
+//   3. in-class pick: rank floor(u2*count) in (site, slot) order -- hierarchical search
+//      rows -> sites of the row -> slots of the site   (replaces get_random_key, incremental.py:283)
+//   4. apply the move                                        (rules.py perform())
+//   5. refresh the neighbourhood: every site whose moves can depend on the touched nodes has its
+//      13 class counts re-derived before and after the mutation; the difference goes to the row
+//      counts and class totals   (pre/post_status_change, rules.py:22-27,46-51; sim.py:149-157)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <initializer_list>
+#include "kmc_common.cuh"
+#include "../../include/kmc_b200.h"
+
+namespace kmc {
+
+struct ReplicaParams {
+    int d0, d1, n;
+    int n_replicas;
+    uint8_t *status;                 // [R][n]
+    double rate[NC];                 // per-class rate (0 for disabled)
+    int order_pos[NC];               // position in weighted_choice input order, or -1
+    long long nsteps;
+    unsigned long long seed;
+    uint32_t replica0;
+    const double *draws;             // [R][nsteps][2] or nullptr (Philox)
+    int log_mode;
+    void *events;                    // [R][nsteps] records or nullptr
+    unsigned long long *steps_done;  // [R] in: step offset; out: += events done
+    unsigned long long *hist;        // [R][NC]
+    unsigned long long *ties;        // [R]
+    uint32_t *flags;                 // [R] bit0 zero-rate stop, bit1 validate mismatch
+    int validate;
+};
+
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// small offset tables packed as nibbles (value + 2), entry 0 in the lowest nibble
+constexpr unsigned long long pack_nibbles(std::initializer_list<int> v) {
+    unsigned long long r = 0; int i = 0;
+    for (int x : v) { r |= (unsigned long long)(x + 2) << (4 * i); i++; }
+    return r;
+}
+// ring neighbours R0..R5 (state.py:392-394)
+constexpr unsigned long long RING_DA = pack_nibbles({-1, 0, 1, 1, 0, -1});
+constexpr unsigned long long RING_DB = pack_nibbles({0, -1, -1, 0, 1, 1});
+// sites whose move counts can depend on a touched node p: p, its six neighbours (MoveDivacancy,
+// rules.py:115-117), and the anchors of the triangles containing p (p-(2,0), p-(0,2), p-(2,-2))
+constexpr unsigned long long REFRESH_DA = pack_nibbles({0, -1, 0, 1, 1, 0, -1, -2, 0, -2});
+constexpr unsigned long long REFRESH_DB = pack_nibbles({0, 0, -1, -1, 0, 1, 1, 0, -2, 2});
+constexpr uint32_t FLAG_ZERO_RATE = 1u, FLAG_VALIDATE = 2u;
+
+struct SmemStatus {
+    const uint8_t *p;
+    __device__ __forceinline__ int operator()(int i) const { return p[i]; }
+};
+
+__host__ __device__ inline size_t replica_warp_bytes(int d0, int d1) {
+    size_t n = (size_t)d0 * d1;
+    size_t a = (n + 15) & ~(size_t)15;
+    size_t b = ((size_t)d0 * RC_WORDS * 4 + 15) & ~(size_t)15;
+    return a + b;
+}
+
+// find the lane whose inclusive prefix first exceeds r; v = per-lane count.
+// returns false (and r -= warp total) when r is beyond this chunk.
+__device__ __forceinline__ bool warp_rank_search(uint32_t v, uint32_t &r, int &L, int lane) {
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    uint32_t tot = __shfl_sync(FULL, inc, 31);
+    if (r >= tot) { r -= tot; return false; }
+    uint32_t m = __ballot_sync(FULL, inc > r);
+    L = __ffs(m) - 1;
+    r -= __shfl_sync(FULL, inc - v, L);
+    return true;
+}
+
+// weighted_choice (reference demo1/kmc.py:21-54) over 16 lanes holding (weight, input position).
+// `sc` (lanes 0..15) is the class held at each sorted position; it persists between events and is
+// re-derived only when the (weight, position) order actually changed.
+struct ClassPick { int csel; double total; uint32_t tie; bool zero; };
+__device__ __forceinline__ ClassPick pick_class(double w, int pos, int &sc, bool &need_sort, double u1, int lane)
+{
+    double ws = __shfl_sync(FULL, w, sc);
+    int ps = __shfl_sync(FULL, pos, sc);
+    {
+        // is the previous order still (w, pos)-sorted?  (almost always)
+        const double wp = __shfl_up_sync(FULL, ws, 1);
+        const int pp = __shfl_up_sync(FULL, ps, 1);
+        const bool ok = (lane == 0) || (lane > 15) || (wp < ws) || (wp == ws && pp < ps);
+        if (need_sort || !__all_sync(FULL, ok)) {
+            // stable ascending sort (kmc.py:35) as a rank sort of the 16 unique (w, pos) keys
+            int rank = 0;
+            for (int j = 0; j < 16; j++) {
+                const double wj = __shfl_sync(FULL, w, j);
+                const int pj = __shfl_sync(FULL, pos, j);
+                rank += (wj < w) || (wj == w && pj < pos);
+            }
+            for (int j = 0; j < 16; j++) {
+                const int rj = __shfl_sync(FULL, rank, j);
+                if (rj == lane) sc = j;
+            }
+            need_sort = false;
+            ws = __shfl_sync(FULL, w, sc);
+        }
+    }
+    ClassPick out;
+    // zero weights are dropped (kmc.py:30); they sort first and adding them is exact, so the
+    // sequential sum simply starts after them
+    const int z = __popc(__ballot_sync(FULL, ws == 0.0) & 0xFFFFu);
+    out.zero = (z == 16);
+    double acc = 0.0, cum = 0.0;
+    for (int k = z; k < 16; k++) {
+        const double wk = __shfl_sync(FULL, ws, k);
+        acc = __dadd_rn(acc, wk);                              // util.py:65-68: sequential sums
+        if (lane == k) cum = acc;
+    }
+    out.total = acc;
+    const double x = __dmul_rn(acc, u1);                       // random.uniform(0, total), kmc.py:49
+    const bool live = (lane >= z) && (lane < 16);
+    const uint32_t ge = __ballot_sync(FULL, live && cum >= x); // bisect_left, kmc.py:50
+    const int isel = ge ? (__ffs(ge) - 1) : 15;
+    out.tie = __ballot_sync(FULL, live && cum == x);
+    out.csel = __shfl_sync(FULL, sc, isel);
+    return out;
+}
+
+// class count of the (uniform) class `c` at one site, specialised per class group
+template <int GROUP>   // 0: own-status classes, 1: MoveDivacancy kinds, 2: CreateTrefoil
+__device__ __forceinline__ uint32_t site_class_count(const uint8_t *st, int a, int b, int d0, int d1, int c,
+                                                    uint32_t g1const) {
+    const int s0 = st[a * d1 + b];
+    if (GROUP == 0) return (g1const >> (2 * s0)) & 3u;
+    if (s0 != S_DIVAC) return 0u;
+    if (GROUP == 1) {
+        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
+        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
+        RingMasks m = ring_masks(st[am * d1 + b], st[a * d1 + bm], st[ap * d1 + bm], st[ap * d1 + b],
+                                 st[a * d1 + bp], st[am * d1 + bp]);
+        return __popc(kind_mask(m, c - C_MOVE_DIV));
+    }
+    const int ap2 = wrap_inc(a + 2, d0), bp2 = wrap_inc(b + 2, d1), bm2 = wrap_dec(b - 2, d1);
+    uint32_t t20 = st[ap2 * d1 + b] == S_DIVAC;
+    return (t20 & (uint32_t)(st[a * d1 + bp2] == S_DIVAC)) + (t20 & (uint32_t)(st[ap2 * d1 + bm2] == S_DIVAC));
+}
+
+// 2 bits per status: number of class-c moves a site of that status carries (own-status classes)
+__device__ __forceinline__ uint32_t g1_const(int c) {
+    switch (c) {
+        case C_CREATE_DIV: return 0x1u;
+        case C_FILL_DIV: return 0x40u;
+        case C_DESTROY_TREF: return 0x4100u;
+        case C_CMONO_FROM_DOUBLE: return 0x2u;
+        case C_FMONO_FROM_EMPTY: return 0x80u;
+        default: return 0x14u;        // classes 9, 10, 12: monovacancy sites
+    }
+}
+
+// Rule.perform + nodes_affected_by (reference demo1/rules.py:62-65,79-82,96-101,143-148,178-183,
+// 204-214,279-283): the nodes a move touches and the status each one gets.
+struct MoveNodes { int na, a1, b1, a2, b2, ns0, ns1, ns2; };
+__device__ __forceinline__ MoveNodes move_nodes(int row, int col, int slot, int s0, int d0, int d1)
+{
+    MoveNodes m;
+    m.na = 1; m.a1 = row; m.b1 = col; m.a2 = row; m.b2 = col; m.ns1 = 0; m.ns2 = 0;
+    if (slot < 7) {
+        m.ns0 = slot == 0 ? S_DIVAC : slot == 1 ? S_PRISTINE : slot <= 3 ? (s0 | (slot - 1))
+                : slot <= 5 ? (s0 & ~(slot - 3)) : (s0 ^ 3);
+    } else if (slot < 13) {
+        const int ri = kring(slot - 7);     // ring position of the target
+        const int da = (int)((RING_DA >> (4 * ri)) & 0xF) - 2;
+        const int db = (int)((RING_DB >> (4 * ri)) & 0xF) - 2;
+        m.a1 = wrap_inc(wrap_dec(row + da, d0), d0);
+        m.b1 = wrap_inc(wrap_dec(col + db, d1), d1);
+        m.na = 2; m.ns0 = S_PRISTINE; m.ns1 = S_DIVAC;
+    } else {
+        const int o = (slot - 13) & 1;
+        const bool create = slot < 15;
+        m.a1 = wrap_inc(row + 2, d0); m.b1 = col;                          // role 1: p + (2, 0)
+        m.a2 = o ? m.a1 : row;                                              // role 2: p+(0,2) | p+(2,-2)
+        m.b2 = o ? wrap_dec(col - 2, d1) : wrap_inc(col + 2, d1);
+        m.na = 3;
+        m.ns0 = create ? S_TREF + 3 * o : S_DIVAC;
+        m.ns1 = create ? S_TREF + 3 * o + 1 : S_DIVAC;
+        m.ns2 = create ? S_TREF + 3 * o + 2 : S_DIVAC;
+    }
+    return m;
+}
+__device__ __forceinline__ void apply_move(uint8_t *st, int d0, int d1, int row, int col, int slot, int s0)
+{
+    const MoveNodes m = move_nodes(row, col, slot, s0, d0, d1);
+    st[row * d1 + col] = (uint8_t)m.ns0;
+    if (m.na > 1) st[m.a1 * d1 + m.b1] = (uint8_t)m.ns1;
+    if (m.na > 2) st[m.a2 * d1 + m.b2] = (uint8_t)m.ns2;
+}
+
+// per-row class counts of row `a`, as 7 pair-words (two uint16 fields each)
+__device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int d1, uint32_t out[RC_WORDS]) {
+    SmemStatus S{st};
+    uint32_t A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0, A3 = 0;
+    for (int b = 0; b < d1; b++) {
+        F4 f = eval_site(S, a, b, d0, d1);
+        A0 += f.w0 & 0x00FF00FFu; B0 += (f.w0 >> 8) & 0x00FF00FFu;
+        A1 += f.w1 & 0x00FF00FFu; B1 += (f.w1 >> 8) & 0x00FF00FFu;
+        A2 += f.w2 & 0x00FF00FFu; B2 += (f.w2 >> 8) & 0x00FF00FFu;
+        A3 += f.w3 & 0x00FF00FFu;
+    }
+    out[0] = A0; out[1] = B0; out[2] = A1; out[3] = B1; out[4] = A2; out[5] = B2; out[6] = A3;
+}
+
+template <int TD0, int TD1>
+__global__ void __launch_bounds__(1024, 1) kmc_replica_kernel(const ReplicaParams p)
+{
+    const int d0 = TD0 ? TD0 : p.d0;
+    const int d1 = TD1 ? TD1 : p.d1;
+    const int n = d0 * d1;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int rep = blockIdx.x * warps_per_block + warp;
+    if (rep >= p.n_replicas) return;       // whole warp exits together; no block barriers are used
+
+    extern __shared__ uint4 smem_raw[];
+    const size_t wbytes = replica_warp_bytes(d0, d1);
+    uint8_t *st = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * wbytes;
+    uint32_t *rc = reinterpret_cast<uint32_t *>(st + (((size_t)n + 15) & ~(size_t)15));
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(rc);
+
+    // ---- load the lattice ------------------------------------------------------------------
+    uint8_t *gst = p.status + (size_t)rep * n;
+    if ((n & 15) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gst);
+        uint4 *dst = reinterpret_cast<uint4 *>(st);
+        for (int i = lane; i < (n >> 4); i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < n; i += 32) st[i] = gst[i];
+    }
+    __syncwarp();
+
+    // ---- build the row hierarchy (a full enumeration, as Rule.initialize_moves does) --------
+    for (int a = lane; a < d0; a += 32) {
+        uint32_t w[RC_WORDS];
+        row_counts(st, a, d0, d1, w);
+#pragma unroll
+        for (int j = 0; j < RC_WORDS; j++) rc[a * RC_WORDS + j] = w[j];
+    }
+    __syncwarp();
+
+    // per-lane class state: lane c < 13 owns class c; lanes 13..15 are permanent zero weights
+    const int myc = lane < NC ? lane : 0;
+    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    int tot = 0;
+    if (lane < NC) {
+        const int f = rc_field(lane);
+        for (int a = 0; a < d0; a++) tot += rc16[a * (2 * RC_WORDS) + f];
+    }
+    unsigned long long hist = 0;
+    unsigned long long n_ties = 0;
+    int sc = lane & 15;                    // class held at sorted position `lane` (lanes 0..15)
+    bool need_sort = true;
+
+    // per-lane role in the refresh: node index and one of 10 offsets
+    const int my_i = lane / 10, my_o = lane % 10;
+    //            o:   0   1   2   3   4   5   6   7   8   9
+    // da              0  -1   0   1   1   0  -1  -2   0  -2
+    // db              0   0  -1  -1   0   1   1   0  -2   2
+    const int my_da = (int)((REFRESH_DA >> (4 * my_o)) & 0xF) - 2;
+    const int my_db = (int)((REFRESH_DB >> (4 * my_o)) & 0xF) - 2;
+
+    const unsigned long long step_base = p.steps_done[rep];
+    double mu1 = 0.0, mu2 = 0.0;           // this lane's prefetched draws
+    long long t = 0;
+    uint32_t flag = 0;
+
+    for (; t < p.nsteps; t++) {
+        // ---- draws: a block of 32 events at a time, one event per lane ----------------------
+        if ((t & 31) == 0) {
+            long long tt = t + lane;
+            if (tt < p.nsteps) {
+                if (p.draws) {
+                    const double2 u = *reinterpret_cast<const double2 *>(
+                        p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)tt) * 2);
+                    mu1 = u.x; mu2 = u.y;
+                } else {
+                    kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step_base + (unsigned long long)tt, mu1, mu2);
+                }
+            }
+        }
+        const double u1 = __shfl_sync(FULL, mu1, (int)(t & 31));
+        const double u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
+
+        // ---- 1. weights ------------------------------------------------------------------------
+        const double w = __dmul_rn((double)tot, rate);       // lanes >= 13: tot = 0, rate = 0
+
+        // ---- 2. class choice -------------------------------------------------------------------
+        const ClassPick pick = pick_class(w, pos, sc, need_sort, u1, lane);
+        if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
+            flag |= FLAG_ZERO_RATE;
+            if (p.log_mode != KMC_LOG_NONE && lane == 0) {
+                const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
+                if (p.log_mode == KMC_LOG_FULL) {
+                    kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+                    rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
+                    rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
+                } else {
+                    kmc_event_compact e;
+                    e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE; e.flags = 0;
+                    e.total_rate = 0.0;
+                    reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
+                }
+            }
+            break;
+        }
+        const int csel = pick.csel;
+        const double total = pick.total;
+        const uint32_t tie = pick.tie;
+
+        // ---- event record, part 1 (counts before the event) -------------------------------------
+        if (p.log_mode == KMC_LOG_FULL) {
+            kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
+                                  ((size_t)rep * (size_t)p.nsteps + (size_t)t);
+            if (lane < NC) rec->counts[lane] = (uint32_t)tot;
+        }
+
+        // ---- 3. in-class pick --------------------------------------------------------------------
+        const int cnt = __shfl_sync(FULL, tot, csel);
+        uint32_t r;
+        {
+            long long rr = (long long)__dmul_rn(u2, (double)cnt);
+            if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
+            r = (uint32_t)rr;
+        }
+        // 3a. row: two rows per lane per pass
+        int row = 0;
+        {
+            const int f = rc_field(csel);
+            for (int base = 0; base < d0; base += 64) {
+                const int r0 = base + 2 * lane;
+                const uint32_t v0 = (r0 < d0) ? rc16[r0 * (2 * RC_WORDS) + f] : 0u;
+                const uint32_t v1 = (r0 + 1 < d0) ? rc16[(r0 + 1) * (2 * RC_WORDS) + f] : 0u;
+                int L;
+                if (warp_rank_search(v0 + v1, r, L, lane)) {
+                    const uint32_t v0L = __shfl_sync(FULL, v0, L);
+                    row = base + 2 * L;
+                    if (r >= v0L) { r -= v0L; row++; }
+                    break;
+                }
+            }
+        }
+        // 3b. site within the row: two sites per lane per pass
+        int col = 0;
+        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
+        {
+            const uint32_t g1c = g1_const(csel);
+            for (int base = 0; base < d1; base += 64) {
+                const int b0 = base + 2 * lane;
+                uint32_t v0 = 0, v1 = 0;
+                if (group == 0) {
+                    if (b0 < d1) v0 = site_class_count<0>(st, row, b0, d0, d1, csel, g1c);
+                    if (b0 + 1 < d1) v1 = site_class_count<0>(st, row, b0 + 1, d0, d1, csel, g1c);
+                } else if (group == 1) {
+                    if (b0 < d1) v0 = site_class_count<1>(st, row, b0, d0, d1, csel, g1c);
+                    if (b0 + 1 < d1) v1 = site_class_count<1>(st, row, b0 + 1, d0, d1, csel, g1c);
+                } else {
+                    if (b0 < d1) v0 = site_class_count<2>(st, row, b0, d0, d1, csel, g1c);
+                    if (b0 + 1 < d1) v1 = site_class_count<2>(st, row, b0 + 1, d0, d1, csel, g1c);
+                }
+                int L;
+                if (warp_rank_search(v0 + v1, r, L, lane)) {
+                    const uint32_t v0L = __shfl_sync(FULL, v0, L);
+                    col = base + 2 * L;
+                    if (r >= v0L) { r -= v0L; col++; }
+                    break;
+                }
+            }
+        }
+        // 3c. slot within the site (uniform across the warp)
+        const int site = row * d1 + col;
+        const int s0 = st[site];
+        int slot;
+        if (group == 0) {
+            switch (csel) {
+                case C_CREATE_DIV: slot = 0; break;
+                case C_FILL_DIV: slot = 1; break;
+                case C_DESTROY_TREF: slot = (s0 == S_TREF) ? 15 : 16; break;
+                case C_CMONO_FROM_DOUBLE: slot = 2 + (int)r; break;
+                case C_CMONO_MAKE_EMPTY: slot = 1 + (3 & ~s0); break;
+                case C_FMONO_MAKE_DOUBLE: slot = 3 + s0; break;
+                case C_FMONO_FROM_EMPTY: slot = 4 + (int)r; break;
+                default: slot = 6; break;
+            }
+        } else if (group == 1) {
+            const int am = wrap_dec(row - 1, d0), ap = wrap_inc(row + 1, d0);
+            const int bm = wrap_dec(col - 1, d1), bp = wrap_inc(col + 1, d1);
+            RingMasks m = ring_masks(st[am * d1 + col], st[row * d1 + bm], st[ap * d1 + bm], st[ap * d1 + col],
+                                     st[row * d1 + bp], st[am * d1 + bp]);
+            const uint32_t km = kind_mask(m, csel - C_MOVE_DIV);
+            slot = 7;
+            int rr = (int)r;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const int bit = (km >> kring(k)) & 1;
+                if (bit && rr == 0) slot = 7 + k;
+                rr -= bit;
+            }
+        } else {
+            const int ap2 = wrap_inc(row + 2, d0), bp2 = wrap_inc(col + 2, d1);
+            const bool up = (st[ap2 * d1 + col] == S_DIVAC) && (st[row * d1 + bp2] == S_DIVAC);
+            slot = (up && r == 0) ? 13 : 14;
+        }
+
+        // ---- event record, part 2 ------------------------------------------------------------------
+        if (p.log_mode != KMC_LOG_NONE && lane == 0) {
+            const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
+            if (p.log_mode == KMC_LOG_FULL) {
+                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+                rec->site = (uint32_t)site; rec->cls = (uint8_t)csel; rec->slot = (uint8_t)slot;
+                rec->flags = tie ? 1 : 0; rec->total_rate = total; rec->pad = 0;
+            } else {
+                kmc_event_compact *rec = reinterpret_cast<kmc_event_compact *>(p.events) + idx;
+                kmc_event_compact e;
+                e.site = (uint32_t)site; e.cls = (uint8_t)csel; e.slot = (uint8_t)slot;
+                e.flags = tie ? 1 : 0; e.total_rate = total;
+                *rec = e;
+            }
+        }
+        if (lane == csel) hist++;
+        if (tie && lane == 0) n_ties++;
+
+        // ---- 4. the move: touched nodes and their new status (uniform) --------------------------------
+        const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
+        const int na = mv.na, a1 = mv.a1, b1 = mv.b1, a2 = mv.a2, b2 = mv.b2;
+        const int ns0 = mv.ns0, ns1 = mv.ns1, ns2 = mv.ns2;
+
+        // ---- 5. neighbourhood refresh -----------------------------------------------------------------
+        const bool act = my_i < na;
+        const int ba = my_i == 0 ? row : my_i == 1 ? a1 : a2;
+        const int bb = my_i == 0 ? col : my_i == 1 ? b1 : b2;
+        int xa = ba + my_da; xa = xa < 0 ? xa + d0 : (xa >= d0 ? xa - d0 : xa);
+        int xb = bb + my_db; xb = xb < 0 ? xb + d1 : (xb >= d1 ? xb - d1 : xb);
+        const int xsite = xa * d1 + xb;
+        // the same site can be reached from two touched nodes: keep one lane per distinct site
+        const uint32_t same = __match_any_sync(FULL, act ? xsite : (int)(0x40000000 | lane));
+        const bool leader = act && ((__ffs(same) - 1) == lane);
+
+        SmemStatus S{st};
+        F4 fb = {0u, 0u, 0u, 0u};
+        if (leader) fb = eval_site(S, xa, xb, d0, d1);
+        __syncwarp();
+        if (lane == 0) {
+            st[site] = (uint8_t)ns0;
+            if (na > 1) st[a1 * d1 + b1] = (uint8_t)ns1;
+            if (na > 2) st[a2 * d1 + b2] = (uint8_t)ns2;
+        }
+        __syncwarp();
+        F4 fa = {0u, 0u, 0u, 0u};
+        if (leader) fa = eval_site(S, xa, xb, d0, d1);
+
+        // per-byte (after - before), biased by 0x80 so no borrow crosses bytes; then spread to
+        // 16-bit pair-words whose integer value is hi*65536 + lo with signed lo, hi
+        uint32_t dw[RC_WORDS];
+        {
+            const uint32_t e0 = (fa.w0 | 0x80808080u) - fb.w0, e1 = (fa.w1 | 0x80808080u) - fb.w1;
+            const uint32_t e2 = (fa.w2 | 0x80808080u) - fb.w2, e3 = (fa.w3 | 0x80808080u) - fb.w3;
+            dw[0] = (e0 & 0x00FF00FFu) - 0x00800080u; dw[1] = ((e0 >> 8) & 0x00FF00FFu) - 0x00800080u;
+            dw[2] = (e1 & 0x00FF00FFu) - 0x00800080u; dw[3] = ((e1 >> 8) & 0x00FF00FFu) - 0x00800080u;
+            dw[4] = (e2 & 0x00FF00FFu) - 0x00800080u; dw[5] = ((e2 >> 8) & 0x00FF00FFu) - 0x00800080u;
+            dw[6] = (e3 & 0x00FF00FFu) - 0x00800080u;
+        }
+        // row counts: the few lanes with a change add their packed deltas
+#pragma unroll
+        for (int j = 0; j < RC_WORDS; j++)
+            if (dw[j] != 0u) atomicAdd(&rc[xa * RC_WORDS + j], dw[j]);
+        // class totals: warp-sum of the packed deltas, then lane c unpacks its own field
+        int keep = 0;
+#pragma unroll
+        for (int j = 0; j < RC_WORDS; j++) {
+            const int sj = (int)__reduce_add_sync(FULL, dw[j]);
+            if (lane == j) keep = sj;
+        }
+        if (true) {
+            const int fld = rc_field(myc);                         // 2*pairword + half
+            const int v = __shfl_sync(FULL, keep, fld >> 1);
+            const int lo = (int)(short)(v & 0xFFFF);
+            const int hi = (v - lo) >> 16;
+            if (lane < NC) tot += (fld & 1) ? hi : lo;
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------------
+    const long long done = t;
+    if (p.validate) {
+        // KmcSim.validate (sim.py:159-168): incremental tables vs a fresh enumeration
+        bool bad = false;
+        for (int a = lane; a < d0; a += 32) {
+            uint32_t w[RC_WORDS];
+            row_counts(st, a, d0, d1, w);
+#pragma unroll
+            for (int j = 0; j < RC_WORDS; j++) bad |= (rc[a * RC_WORDS + j] != w[j]);
+        }
+        if (lane < NC) {
+            const int f = rc_field(lane);
+            int fresh = 0;
+            for (int a = 0; a < d0; a++) fresh += rc16[a * (2 * RC_WORDS) + f];
+            bad |= (fresh != tot);
+        }
+        if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
+    }
+    if ((n & 15) == 0) {
+        uint4 *dst = reinterpret_cast<uint4 *>(gst);
+        const uint4 *src = reinterpret_cast<const uint4 *>(st);
+        for (int i = lane; i < (n >> 4); i += 32) dst[i] = src[i];
+    } else {
+        for (int i = lane; i < n; i += 32) gst[i] = st[i];
+    }
+    if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane == 0) {
+        p.steps_done[rep] = step_base + (unsigned long long)done;
+        p.ties[rep] += n_ties;
+        if (flag) p.flags[rep] |= flag;
+    }
+}
+
+}  // namespace kmc

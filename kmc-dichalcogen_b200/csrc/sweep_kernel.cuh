@@ -1,0 +1,243 @@
+// sweep_kernel.cuh -- K1 + K2: full-lattice enumerate + classify sweep (the `--no-incremental` path).
+//
+// Replaces Rule.initialize_moves x 8 rules (reference demo1/sim.py:204-206, rules.py:19-21,43-45 and
+// each rule's all_moves) and ReverseDict.value_counts (incremental.py:287-294).
+//
+// in : status planes   uint8  [R][d0][d1]            (1 B/site read)
+// out: slot planes     uint8  [R][17][d0*d1]         (17 B/site written; class id or 0xFF)
+//      row counts      uint32 [R][d0][16]            (13 used)
+//
+// HBM-bound by construction: 18 algorithmic bytes per site.  The arithmetic is byte-parallel: one
+// thread owns 4 consecutive sites of a row as one 32-bit word and evaluates all predicates with
+// per-byte 0/1 flag words, so the instruction count per site stays far below the memory time.
+// Neighbour rows come from L1/L2 (the status plane is 1/18 of the traffic and every word is re-read by
+// a handful of neighbouring threads).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kmc_common.cuh"
+
+namespace kmc {
+
+constexpr int RCG_STRIDE = 16;            // uint32 per row in the global row-count table
+constexpr uint32_t ONES = 0x01010101u;
+
+// per-byte flags (0x01 / 0x00) of a word of four status bytes (status < 16)
+struct ByteFlags { uint32_t zero, div, mono, up_anchor, dn_anchor; };
+__host__ __device__ __forceinline__ ByteFlags byte_flags(uint32_t w) {
+    const uint32_t e0 = w & ONES, e1 = (w >> 1) & ONES, e2 = (w >> 2) & ONES, e3 = (w >> 3) & ONES;
+    ByteFlags f;
+    const uint32_t hi = e2 | e3;
+    f.zero = (e0 | e1 | hi) ^ ONES;
+    f.div = e0 & e1 & ~hi;
+    f.mono = (e0 ^ e1) & ~hi;
+    f.up_anchor = e2 & ~(e0 | e1 | e3);          // status 4
+    f.dn_anchor = e0 & e1 & e2 & ~e3;            // status 7
+    return f;
+}
+// flags of the sites one / two to the right (+) or left (-) of each byte's site
+__host__ __device__ __forceinline__ uint32_t shr_sites(uint32_t cur, uint32_t next, int k) {
+    return k == 0 ? cur : (cur >> (8 * k)) | (next << (32 - 8 * k));
+}
+__host__ __device__ __forceinline__ uint32_t shl_sites(uint32_t prev, uint32_t cur, int k) {
+    return k == 0 ? cur : (cur << (8 * k)) | (prev >> (32 - 8 * k));
+}
+// code plane word: class id where flag set, 0xFF elsewhere
+__host__ __device__ __forceinline__ uint32_t code(uint32_t flag, uint32_t cls_bytes) {
+    const uint32_t m = flag * 0xFFu;
+    return (cls_bytes & m) | ~m;
+}
+__host__ __device__ __forceinline__ uint32_t hsum(uint32_t bytes) { return (bytes * ONES) >> 24; }
+
+// All 17 slot words + 13 class counts of one word of 4 sites.
+// Inputs: status words of rows a-1 (cur,next), a (prev,cur,next), a+1 (prev,cur), a+2 (prev,cur).
+struct WordIn { uint32_t m_cur, m_next, c_prev, c_cur, c_next, p_prev, p_cur, q_prev, q_cur; };
+
+__host__ __device__ __forceinline__ void sweep_word(const WordIn &in, uint32_t out[NS], uint32_t cnt[NC]) {
+    const ByteFlags c = byte_flags(in.c_cur);
+    const ByteFlags cp = byte_flags(in.c_prev), cn = byte_flags(in.c_next);
+    const ByteFlags m0 = byte_flags(in.m_cur), m1 = byte_flags(in.m_next);
+    const ByteFlags p0 = byte_flags(in.p_cur), pm = byte_flags(in.p_prev);
+    const ByteFlags q0 = byte_flags(in.q_cur), qm = byte_flags(in.q_prev);
+
+    // own-status slots (rules.py:71,88,220-227,289; trefoil anchors for DestroyTrefoil :189)
+    out[0] = code(c.zero, C_CREATE_DIV * ONES);
+    out[1] = code(c.div, C_FILL_DIV * ONES);
+    // CreateMonovacancy layer 1 (slot 2): status 0 -> from-double, status 2 -> make-empty
+    const uint32_t e0 = in.c_cur & ONES, e1 = (in.c_cur >> 1) & ONES;
+    const uint32_t s1 = c.mono & e0, s2 = c.mono & e1;          // status == 1 / == 2
+    out[2] = code(c.zero | s2, (C_CMONO_FROM_DOUBLE * ONES) + s2);
+    out[3] = code(c.zero | s1, (C_CMONO_FROM_DOUBLE * ONES) + s1);
+    // FillMonovacancy layer 1 (slot 4): status 1 -> make-double, status 3 -> from-empty
+    out[4] = code(c.div | s1, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    out[5] = code(c.div | s2, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    out[6] = code(c.mono, C_FLIP * ONES);
+    cnt[C_CREATE_DIV] = hsum(c.zero);
+    cnt[C_FILL_DIV] = hsum(c.div);
+    cnt[C_CMONO_FROM_DOUBLE] = 2 * hsum(c.zero);
+    cnt[C_CMONO_MAKE_EMPTY] = hsum(c.mono);
+    cnt[C_FMONO_MAKE_DOUBLE] = hsum(c.mono);
+    cnt[C_FMONO_FROM_EMPTY] = 2 * hsum(c.div);
+    cnt[C_FLIP] = hsum(c.mono);
+
+    // ring neighbours R0..R5 = (-1,0) (0,-1) (1,-1) (1,0) (0,1) (-1,1): pristine / divacancy flags
+    uint32_t P[6], D[6];
+    P[0] = m0.zero;                              D[0] = m0.div;
+    P[1] = shl_sites(cp.zero, c.zero, 1);        D[1] = shl_sites(cp.div, c.div, 1);
+    P[2] = shl_sites(pm.zero, p0.zero, 1);       D[2] = shl_sites(pm.div, p0.div, 1);
+    P[3] = p0.zero;                              D[3] = p0.div;
+    P[4] = shr_sites(c.zero, cn.zero, 1);        D[4] = shr_sites(c.div, cn.div, 1);
+    P[5] = shr_sites(m0.zero, m1.zero, 1);       D[5] = shr_sites(m0.div, m1.div, 1);
+    uint32_t k_nat = 0, k_met = 0, k_cmb = 0, k_bth = 0;      // per-byte counts (<= 6)
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int i = kring(k);
+        const uint32_t near = (i & 1) ? D[(i + 5) % 6] : D[(i + 1) % 6];
+        const uint32_t far = (i & 1) ? D[(i + 1) % 6] : D[(i + 5) % 6];
+        const uint32_t present = c.div & P[i];
+        out[7 + k] = code(present, (C_MOVE_DIV * ONES) + near + (far << 1));
+        k_nat += present & ~near & ~far;
+        k_met += present & near & ~far;
+        k_cmb += present & ~near & far;
+        k_bth += present & near & far;
+    }
+    cnt[C_MOVE_DIV + 0] = hsum(k_nat); cnt[C_MOVE_DIV + 1] = hsum(k_met);
+    cnt[C_MOVE_DIV + 2] = hsum(k_cmb); cnt[C_MOVE_DIV + 3] = hsum(k_bth);
+
+    // trefoils: Up(p) = {p, p+(2,0), p+(0,2)}, Down(p) = {p, p+(2,0), p+(2,-2)} (rules.py:159-174)
+    const uint32_t t20 = q0.div;
+    const uint32_t t02 = shr_sites(c.div, cn.div, 2);
+    const uint32_t t2m2 = shl_sites(qm.div, q0.div, 2);
+    const uint32_t up = c.div & t20 & t02, dn = c.div & t20 & t2m2;
+    out[13] = code(up, C_CREATE_TREF * ONES);
+    out[14] = code(dn, C_CREATE_TREF * ONES);
+    out[15] = code(c.up_anchor, C_DESTROY_TREF * ONES);
+    out[16] = code(c.dn_anchor, C_DESTROY_TREF * ONES);
+    cnt[C_CREATE_TREF] = hsum(up) + hsum(dn);
+    cnt[C_DESTROY_TREF] = hsum(c.up_anchor) + hsum(c.dn_anchor);
+}
+
+struct SweepParams {
+    int d0, d1, n, n_replicas;
+    const uint8_t *status;       // [R][n]
+    uint8_t *slots;              // [R][17][n] or nullptr (count-only sweep)
+    uint32_t *rowcnt;            // [R][d0][16], zeroed by the caller
+    long long total_words;       // R * n / 4
+};
+
+// Fast path: d1 % 4 == 0.  One thread = one 32-bit word = 4 consecutive sites of a row.
+__global__ void __launch_bounds__(256) kmc_sweep_kernel(const SweepParams p)
+{
+    const long long gw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gw < p.total_words;
+    const int wpr = p.d1 >> 2;                              // words per row
+    const int wpl = p.n >> 2;                               // words per lattice
+    long long seg = -1 - (long long)(threadIdx.x & 31);     // row id for the count reduction
+    uint32_t cnt[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) cnt[c] = 0;
+
+    if (active) {
+        const int rep = (int)(gw / wpl);
+        const int wl = (int)(gw - (long long)rep * wpl);
+        const int a = wl / wpr;
+        const int wi = wl - a * wpr;
+        const uint32_t *S = reinterpret_cast<const uint32_t *>(p.status + (size_t)rep * p.n);
+        const int am = a == 0 ? p.d0 - 1 : a - 1;
+        const int ap = a + 1 == p.d0 ? 0 : a + 1;
+        const int ap2 = ap + 1 == p.d0 ? 0 : ap + 1;
+        const int wm = wi == 0 ? wpr - 1 : wi - 1;
+        const int wn = wi + 1 == wpr ? 0 : wi + 1;
+        WordIn in;
+        in.m_cur = __ldg(S + am * wpr + wi);  in.m_next = __ldg(S + am * wpr + wn);
+        in.c_prev = __ldg(S + a * wpr + wm);  in.c_cur = __ldg(S + a * wpr + wi);  in.c_next = __ldg(S + a * wpr + wn);
+        in.p_prev = __ldg(S + ap * wpr + wm); in.p_cur = __ldg(S + ap * wpr + wi);
+        in.q_prev = __ldg(S + ap2 * wpr + wm); in.q_cur = __ldg(S + ap2 * wpr + wi);
+        uint32_t out[NS];
+        sweep_word(in, out, cnt);
+        if (p.slots) {
+            uint32_t *O = reinterpret_cast<uint32_t *>(p.slots + (size_t)rep * NS * p.n) + wl;
+#pragma unroll
+            for (int j = 0; j < NS; j++) __stcs(O + (size_t)j * wpl, out[j]);   // streaming stores
+        }
+        seg = (long long)rep * p.d0 + a;
+    }
+    // K2: per-row class counts.  Lanes of the same row pool their counts (16-bit pairs), the
+    // lowest lane of each row adds them to the table.
+    const uint32_t mask = __match_any_sync(0xFFFFFFFFu, seg);
+    uint32_t pk[7];
+#pragma unroll
+    for (int j = 0; j < 6; j++) pk[j] = cnt[2 * j] | (cnt[2 * j + 1] << 16);
+    pk[6] = cnt[12];
+#pragma unroll
+    for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+    if (active && (__ffs(mask) - 1) == (int)(threadIdx.x & 31)) {
+        uint32_t *R = p.rowcnt + (size_t)seg * RCG_STRIDE;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
+            if (lo) atomicAdd(R + 2 * j, lo);
+            if (hi) atomicAdd(R + 2 * j + 1, hi);
+        }
+    }
+}
+
+// Generic path (any d1 >= 5): one thread per site, scalar evaluation.
+__global__ void __launch_bounds__(256) kmc_sweep_kernel_generic(const SweepParams p)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)p.n_replicas * p.n) return;
+    const int rep = (int)(g / p.n);
+    const int i = (int)(g - (long long)rep * p.n);
+    const int a = i / p.d1, b = i - a * p.d1;
+    const uint8_t *st = p.status + (size_t)rep * p.n;
+    struct G { const uint8_t *p; __device__ int operator()(int k) const { return __ldg(p + k); } } S{st};
+    const int d0 = p.d0, d1 = p.d1;
+    const int s0 = st[i];
+    uint8_t out[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) out[j] = 0xFF;
+    if (s0 == 0) { out[0] = C_CREATE_DIV; out[2] = out[3] = C_CMONO_FROM_DOUBLE; }
+    if (s0 == 1) { out[3] = C_CMONO_MAKE_EMPTY; out[4] = C_FMONO_MAKE_DOUBLE; out[6] = C_FLIP; }
+    if (s0 == 2) { out[2] = C_CMONO_MAKE_EMPTY; out[5] = C_FMONO_MAKE_DOUBLE; out[6] = C_FLIP; }
+    if (s0 == 3) {
+        out[1] = C_FILL_DIV; out[4] = out[5] = C_FMONO_FROM_EMPTY;
+        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
+        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
+        RingMasks m = ring_masks(S(am * d1 + b), S(a * d1 + bm), S(ap * d1 + bm), S(ap * d1 + b),
+                                 S(a * d1 + bp), S(am * d1 + bp));
+        for (int k = 0; k < 6; k++) {
+            const int ri = kring(k);
+            if ((m.P >> ri) & 1) out[7 + k] = (uint8_t)(C_MOVE_DIV + ((m.N >> ri) & 1) + 2 * ((m.F >> ri) & 1));
+        }
+        const int ap2 = wrap_inc(a + 2, d0), bp2 = wrap_inc(b + 2, d1), bm2 = wrap_dec(b - 2, d1);
+        const bool t20 = S(ap2 * d1 + b) == 3;
+        if (t20 && S(a * d1 + bp2) == 3) out[13] = C_CREATE_TREF;
+        if (t20 && S(ap2 * d1 + bm2) == 3) out[14] = C_CREATE_TREF;
+    }
+    if (s0 == 4) out[15] = C_DESTROY_TREF;
+    if (s0 == 7) out[16] = C_DESTROY_TREF;
+    uint32_t *R = p.rowcnt + ((size_t)rep * d0 + a) * RCG_STRIDE;
+    for (int j = 0; j < NS; j++) {
+        if (p.slots) p.slots[((size_t)rep * NS + j) * p.n + i] = out[j];
+        if (out[j] != 0xFF) atomicAdd(R + out[j], 1u);
+    }
+}
+
+// class totals per replica from the row counts: counts[R][13]
+__global__ void kmc_reduce_counts_kernel(const uint32_t *rowcnt, int d0, int n_replicas,
+                                         unsigned long long *counts)
+{
+    const int rep = blockIdx.x;
+    const int c = threadIdx.x & 15, part = threadIdx.x >> 4, nparts = blockDim.x >> 4;
+    __shared__ unsigned long long acc[16];
+    if (threadIdx.x < 16) acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long s = 0;
+    for (int a = part; a < d0; a += nparts) s += rowcnt[((size_t)rep * d0 + a) * RCG_STRIDE + c];
+    atomicAdd(&acc[c], s);
+    __syncthreads();
+    if (threadIdx.x < NC) counts[(size_t)rep * NC + threadIdx.x] = acc[threadIdx.x];
+}
+
+}  // namespace kmc

@@ -1,0 +1,153 @@
+"""Thin object wrapper over the C ABI: one `Engine` = `n_replicas` independent trajectories on one GPU.
+
+This is the device-side half of `KmcSim` (reference demo1/sim.py:31-168); `demo1/sim.py` in this
+package is the reference-facing half (rule specs, rates, log dicts).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+
+class Engine:
+    def __init__(self, dim, class_rates, class_order, n_replicas=1, device=0):
+        self.dim = (int(dim[0]), int(dim[1]))
+        self.n = self.dim[0] * self.dim[1]
+        self.n_replicas = int(n_replicas)
+        self.device = int(device)
+        self._lib = nat.load()
+        self._h = C.c_void_p()
+        rates = (C.c_double * nat.N_CLASSES)(*[float(x) for x in class_rates])
+        order = (C.c_int * max(1, len(class_order)))(*[int(c) for c in class_order])
+        nat.check(self._lib.kmc_create(C.byref(self._h), self.device, self.dim[0], self.dim[1],
+                                       self.n_replicas, rates, order, len(class_order)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.kmc_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- lattice ------------------------------------------------------------------------
+    def upload_state(self, status):
+        status = np.ascontiguousarray(status, dtype=np.uint8).reshape(self.n_replicas, self.n)
+        nat.check(self._lib.kmc_upload_state(self._h, status.ctypes.data))
+
+    def download_state(self):
+        out = np.empty((self.n_replicas, self.n), dtype=np.uint8)
+        nat.check(self._lib.kmc_download_state(self._h, out.ctypes.data))
+        return out
+
+    def set_state_device(self, dev_ptr):
+        nat.check(self._lib.kmc_set_state_device(self._h, C.c_void_p(int(dev_ptr))))
+
+    # -- full enumeration ---------------------------------------------------------------
+    def sweep(self):
+        nat.check(self._lib.kmc_sweep(self._h))
+
+    def counts(self):
+        out = np.empty((self.n_replicas, nat.N_CLASSES), dtype=np.int64)
+        nat.check(self._lib.kmc_get_counts(self._h, out.ctypes.data))
+        return out
+
+    def slots(self):
+        out = np.empty((self.n_replicas, self.n, nat.N_SLOTS), dtype=np.uint8)
+        nat.check(self._lib.kmc_get_slots(self._h, out.ctypes.data))
+        return out
+
+    def row_counts(self):
+        out = np.empty((self.n_replicas, self.dim[0], nat.N_CLASSES), dtype=np.uint32)
+        nat.check(self._lib.kmc_get_row_counts(self._h, out.ctypes.data))
+        return out
+
+    # -- events -------------------------------------------------------------------------
+    def _events_buffer(self, nsteps, log_mode):
+        if log_mode == nat.LOG_NONE:
+            return None
+        dt = nat.EVENT_FULL if log_mode == nat.LOG_FULL else nat.EVENT_COMPACT
+        return np.zeros((self.n_replicas, int(nsteps)), dtype=dt)
+
+    def run(self, nsteps, seed, replica0=0, log_mode=nat.LOG_NONE, validate=False):
+        ev = self._events_buffer(nsteps, log_mode)
+        rc = self._lib.kmc_run(self._h, int(nsteps), int(seed), int(replica0), log_mode,
+                               ev.ctypes.data if ev is not None else None, int(bool(validate)))
+        self._last_events = ev
+        nat.check(rc)
+        return ev
+
+    def step_draws(self, draws, log_mode=nat.LOG_FULL, validate=False):
+        draws = np.ascontiguousarray(draws, dtype=np.float64)
+        draws = draws.reshape(self.n_replicas, -1, 2)
+        nsteps = draws.shape[1]
+        ev = self._events_buffer(nsteps, log_mode)
+        rc = self._lib.kmc_step_draws(self._h, draws.ctypes.data, nsteps, log_mode,
+                                      ev.ctypes.data if ev is not None else None, int(bool(validate)))
+        self._last_events = ev
+        nat.check(rc)
+        return ev
+
+    def run_noinc(self, nsteps, seed, replica0=0, log_mode=nat.LOG_NONE):
+        ev = self._events_buffer(nsteps, log_mode)
+        rc = self._lib.kmc_run_noinc(self._h, int(nsteps), int(seed), int(replica0), log_mode,
+                                     ev.ctypes.data if ev is not None else None)
+        self._last_events = ev
+        nat.check(rc)
+        return ev
+
+    def perform_given(self, replica, site, slot):
+        nat.check(self._lib.kmc_perform_given(self._h, int(replica), int(site), int(slot)))
+
+    # -- statistics ---------------------------------------------------------------------
+    def histogram(self):
+        out = np.empty(nat.N_CLASSES, dtype=np.int64)
+        nat.check(self._lib.kmc_get_histogram(self._h, out.ctypes.data))
+        return out
+
+    def histogram_per_replica(self):
+        out = np.empty((self.n_replicas, nat.N_CLASSES), dtype=np.int64)
+        nat.check(self._lib.kmc_get_histogram_per_replica(self._h, out.ctypes.data))
+        return out
+
+    def steps_done(self):
+        out = np.empty(self.n_replicas, dtype=np.int64)
+        nat.check(self._lib.kmc_get_steps_done(self._h, out.ctypes.data))
+        return out
+
+    def ties(self):
+        v = C.c_int64()
+        nat.check(self._lib.kmc_get_ties(self._h, C.byref(v)))
+        return v.value
+
+    def reset_stats(self):
+        nat.check(self._lib.kmc_reset_stats(self._h))
+
+    # -- measurement --------------------------------------------------------------------
+    def sync(self):
+        nat.check(self._lib.kmc_sync(self._h))
+
+    def timer_start(self):
+        nat.check(self._lib.kmc_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        nat.check(self._lib.kmc_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        v = C.c_int64()
+        nat.check(self._lib.kmc_get_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def device_pointers(self):
+        ptrs = [C.c_void_p() for _ in range(4)]
+        nat.check(self._lib.kmc_get_device_pointers(self._h, *[C.byref(p) for p in ptrs]))
+        return {k: p.value for k, p in zip(("status", "slots", "row_counts", "histogram"), ptrs)}
+
+    def set_warps_per_block(self, warps):
+        nat.check(self._lib.kmc_set_warps_per_block(self._h, int(warps)))

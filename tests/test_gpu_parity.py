@@ -1,0 +1,256 @@
+"""Parity of the CUDA engine (through the C ABI) with the CPU oracle and the golden fixtures.
+
+Bar: bit-exact event sequences (class, site, slot), lattices, slot tables and counts; the logged
+total rate (sequential fp64 sum) bit-equal to the oracle's, and the reference's math.fsum total
+recomputed from the logged counts bit-equal to the fixture's (1e-12 relative is the north-star
+tolerance for rates; we hold 0)."""
+import math
+
+import numpy as np
+import pytest
+
+from util_cases import (ko, philox, ALL_ORDER, TEST_RATES, WSE2_ORDER, wse2_rates, exact_state,
+                        evolved_state, iid_state)
+from util_golden import load, trajectory_names, enabled_classes
+from demo1 import _native as nat
+from demo1.engine import Engine
+
+pytestmark = pytest.mark.gpu
+
+
+def fsum_totals(ev, rates, order):
+    rates = np.asarray(rates, dtype=np.float64)
+    return np.array([math.fsum(float(int(c[k])) * float(rates[k]) for k in order) for c in ev["counts"]])
+
+
+def assert_events_equal(dev, want, what):
+    for f in ("cls", "site", "slot"):
+        bad = np.nonzero(dev[f] != want[f])[0]
+        assert bad.size == 0, "%s: first %s mismatch at step %d: got %r want %r" % (
+            what, f, bad[0], dev[bad[0]], want[bad[0]])
+
+
+@pytest.mark.parametrize("name", trajectory_names())
+def test_golden_trajectory_philox(name):
+    g = load(name)
+    m = g["meta"]
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.upload_state(g["status0"])
+    # replica0 = fixture's replica id: the Philox key is (seed, replica0 + r)
+    ev = eng.run(m["nsteps"], m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL, validate=True)[0]
+    assert_events_equal(ev, g["events"], name)
+    got = fsum_totals(ev, g["rates"], m["class_order"])
+    assert (got.view(np.uint64) == g["events"]["total_rate"].view(np.uint64)).all()
+    rel = np.abs(ev["total_rate"] - g["events"]["total_rate"]) / g["events"]["total_rate"]
+    assert rel.max() < 1e-12
+    assert (eng.download_state()[0] == g["status1"]).all()
+    en = enabled_classes(m)
+    eng.sweep()
+    assert (eng.counts()[0][en] == g["counts1"][en]).all()
+    slots = eng.slots()[0]
+    mask = np.isin(slots, en)
+    assert (np.where(mask, slots, 0xFF) == g["slots1"]).all()
+    assert (eng.histogram() == np.bincount(g["events"]["cls"], minlength=13)).all()
+    assert eng.steps_done()[0] == m["nsteps"]
+    assert eng.ties() == m["n_ties"]
+    eng.close()
+
+
+@pytest.mark.parametrize("name", ["allrules_8x8", "ties_7x11", "wse2_hot_24x24"])
+def test_golden_trajectory_injected_draws(name):
+    """Same trajectories through the draw-injection seam (kmc_step_draws), in two chunks."""
+    g = load(name)
+    m = g["meta"]
+    d = philox.draws(m["seed"], m["replica"], 0, m["nsteps"])
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.upload_state(g["status0"])
+    half = m["nsteps"] // 2 + 7
+    ev1 = eng.step_draws(d[:half], log_mode=nat.LOG_COMPACT, validate=True)[0]
+    ev2 = eng.step_draws(d[half:], log_mode=nat.LOG_COMPACT, validate=True)[0]
+    ev = np.concatenate([ev1, ev2])
+    assert_events_equal(ev, g["events"], name)
+    assert (eng.download_state()[0] == g["status1"]).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,rates,order,nrep,nsteps", [
+    ((64, 64), TEST_RATES, ALL_ORDER, 6, 20000),
+    ((64, 64), wse2_rates(1500.0), WSE2_ORDER, 5, 20000),
+    ((33, 47), TEST_RATES, ALL_ORDER, 3, 8000),
+    ((5, 5), TEST_RATES, ALL_ORDER, 4, 5000),
+    ((96, 80), TEST_RATES, ALL_ORDER, 2, 8000),
+    ((7, 130), TEST_RATES, ALL_ORDER, 2, 5000),
+])
+def test_replicas_match_oracle(dim, rates, order, nrep, nsteps):
+    """Several replicas, long runs, two launches (step counter continuity), vs the C oracle."""
+    seed = 424242
+    st0 = np.stack([exact_state(dim, 0.05 + 0.02 * r, 0.05, 100 + r) for r in range(nrep)])
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    eng.upload_state(st0)
+    n1 = nsteps // 3
+    ev1 = eng.run(n1, seed, replica0=10, log_mode=nat.LOG_FULL, validate=True)
+    ev2 = eng.run(nsteps - n1, seed, replica0=10, log_mode=nat.LOG_FULL, validate=True)
+    ev = np.concatenate([ev1, ev2], axis=1)
+    final = eng.download_state()
+    hist = eng.histogram_per_replica()
+    for r in range(nrep):
+        o = ko.Oracle(dim, rates, order, st0[r])
+        done, want = o.run_philox(seed, 10 + r, 0, nsteps)
+        assert done == nsteps
+        assert_events_equal(ev[r], want, "replica %d" % r)
+        assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["flags"] == want["flags"]).all()
+        assert (final[r] == o.status()).all()
+        assert (hist[r] == o.hist()).all()
+    eng.close()
+
+
+def test_stats_only_mode_equals_logged_mode():
+    dim, nrep, nsteps = (64, 64), 40, 3000
+    st0 = np.stack([exact_state(dim, 0.05, 0.05, r) for r in range(nrep)])
+    a = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    b = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    a.upload_state(st0)
+    b.upload_state(st0)
+    a.run(nsteps, 5, log_mode=nat.LOG_NONE)
+    b.run(nsteps, 5, log_mode=nat.LOG_COMPACT, validate=True)
+    assert (a.download_state() == b.download_state()).all()
+    assert (a.histogram() == b.histogram()).all()
+    assert a.histogram().sum() == nrep * nsteps
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (256, 256), (7, 130)])
+def test_sweep_matches_oracle(dim):
+    sts = [evolved_state(dim, 3) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3), iid_state(dim, 4)]
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
+    eng.upload_state(np.stack(sts))
+    eng.sweep()
+    slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
+    for r in range(2):
+        ws, wc, wr = ko.sweep(sts[r], dim)
+        assert (slots[r] == ws).all()
+        assert (counts[r] == wc).all()
+        assert (rows[r] == wr).all()
+    eng.close()
+
+
+def test_sweep_full_size_4096():
+    """BASELINE config 4 (4096x4096): counts equal the oracle's; checksum of the slot planes agrees."""
+    dim = (4096, 4096)
+    st = iid_state(dim, 20261019)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=1)
+    eng.upload_state(st)
+    eng.sweep()
+    ws, wc, wr = ko.sweep(st, dim)
+    assert (eng.counts()[0] == wc).all()
+    assert (eng.row_counts()[0] == wr).all()
+    slots = eng.slots()[0]
+    assert (slots == ws).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 60)])
+def test_no_incremental_path_matches_oracle(dim, nsteps):
+    st0 = exact_state(dim, 0.1, 0.1, 77)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
+    eng.upload_state(np.stack([st0, st0]))
+    ev = eng.run_noinc(nsteps, 9, replica0=0, log_mode=nat.LOG_FULL)
+    final = eng.download_state()
+    for r in range(2):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0)
+        _, want = o.run_philox(9, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "noinc replica %d" % r)
+        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (final[r] == o.status()).all()
+    eng.close()
+
+
+def test_incremental_and_no_incremental_agree():
+    """The reference's A/B check (--no-incremental, sim.py:114-115): same draws, same trajectory."""
+    dim = (64, 64)
+    st0 = exact_state(dim, 0.05, 0.05, 1)
+    a = Engine(dim, TEST_RATES, ALL_ORDER)
+    b = Engine(dim, TEST_RATES, ALL_ORDER)
+    a.upload_state(st0)
+    b.upload_state(st0)
+    ea = a.run(400, 31, log_mode=nat.LOG_COMPACT)
+    eb = b.run_noinc(400, 31, log_mode=nat.LOG_COMPACT)
+    assert (ea == eb).all()
+    assert (a.download_state() == b.download_state()).all()
+    a.close()
+    b.close()
+
+
+def test_zero_total_rate_raises_value_error():
+    rates = [0.0] * 13
+    rates[1] = 5.0        # only FillDivacancy, on a lattice with two divacancies
+    st = np.zeros(25, np.uint8)
+    st[3] = st[17] = 3
+    eng = Engine((5, 5), rates, [1])
+    eng.upload_state(st)
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.run(10, 1, log_mode=nat.LOG_COMPACT)
+    ev = eng._last_events[0]
+    assert list(ev["cls"][:3]) == [1, 1, 0xFF]
+    assert eng.steps_done()[0] == 2
+    assert (eng.download_state() == 0).all()
+    eng.close()
+
+
+def test_perform_given_move():
+    dim = (8, 8)
+    st = evolved_state(dim, 5)
+    o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER)
+    eng.upload_state(st)
+    slots = o.slots()
+    done = set()
+    for site, slot in np.argwhere(slots != 0xFF):
+        if slot in done:
+            continue
+        if o.slots()[site, slot] == 0xFF:
+            continue
+        done.add(slot)
+        assert o.perform_given(site, slot) == 0
+        eng.perform_given(0, site, slot)
+        assert (eng.download_state()[0] == o.status()).all()
+    assert len(done) >= 12
+    with pytest.raises(RuntimeError, match="does not exist"):
+        site = int(np.argwhere(o.status() == 0)[0][0])
+        eng.perform_given(0, site, 1)
+    eng.close()
+
+
+def test_invalid_lattice_is_rejected():
+    eng = Engine((8, 8), TEST_RATES, ALL_ORDER)
+    st = np.zeros(64, np.uint8)
+    st[10] = 5                    # trefoil member without its partners
+    with pytest.raises(AssertionError, match="trefoil"):
+        eng.upload_state(st)
+    st[10] = 11
+    with pytest.raises(AssertionError, match="status"):
+        eng.upload_state(st)
+    eng.close()
+
+
+def test_full_size_replica_batch_properties():
+    """BASELINE config 3 shape (64x64, many replicas): size-independent properties at scale --
+    histogram total = replicas x steps, incremental tables == fresh enumeration on every replica
+    (validate), and a sample of replicas bit-equal to the oracle."""
+    dim, nrep, nsteps = (64, 64), 2048, 2000
+    rates, order = wse2_rates(1500.0), WSE2_ORDER
+    base = [exact_state(dim, 0.05, 0.05, 20261019 + r) for r in range(16)]
+    st0 = np.stack([base[r % 16] for r in range(nrep)])
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    eng.upload_state(st0)
+    eng.run(nsteps, 20261019, log_mode=nat.LOG_NONE, validate=True)
+    assert eng.histogram().sum() == nrep * nsteps
+    final = eng.download_state()
+    for r in [0, 1, 17, 1000, 2047]:
+        o = ko.Oracle(dim, rates, order, st0[r])
+        o.run_philox(20261019, r, 0, nsteps, log=False)
+        assert (final[r] == o.status()).all()
+    eng.close()
