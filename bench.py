@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the B200 KMC engine (contract: see the task's bench section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[2]): config/WSe2.yaml barriers at T = 1500 K (stub rule
+MoveMonovacancy disabled), 64x64 lattice with 5 % divacancies + 5 % monovacancies, 16384 independent
+replicas PER GPU (one warp per replica; weak scaling), Philox draws keyed by (seed, global replica).
+One "step" = one launch of the fused replica kernel = `--events` KMC events on every replica.
+
+One JSON line on stdout (rank 0):
+  value      whole-job events/s, lattices resident in HBM, CUDA-event timed on the engine's stream
+  e2e        same metric through the C ABI with HOST buffers: per step H2D of all lattices from
+             pinned memory, the events, D2H of the final lattices + per-replica event histograms
+  roofline   the HBM-bound kernel of the path: the 4096x4096 full rate sweep (BASELINE configs[3]),
+             18 algorithmic bytes per site, timed live here with CUDA events, L2 flushed
+  replica_kernel   SM-bound figures for the fused kernel (events/s per SM, SM cycles per event)
+  cpu_baseline     the CPU oracle port (oracle/kmc_oracle.c) on the host cores, bounded sample
+`--impl reference` times that CPU port alone (the reference itself is pure Python that cannot travel
+to the GPU box) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "kmc-dichalcogen_b200"))
+
+SEED = 20261019
+DIM = (64, 64)
+TEMPERATURE = 1500.0
+KB_EV = 1.38064852e-23 * 6.24150913e18            # reference demo1/sim.py:27-29
+WSE2_BARRIERS = {2: 2.25, 3: 2.11199155, 4: 2.52009312, 5: 2.25, 6: 3.12293677, 7: 4.43051273,
+                 8: 6.72584072, 9: 6.72584072, 12: 3.41217502}      # config/WSe2.yaml
+WSE2_ORDER = [8, 9, 12, 2, 3, 4, 5, 6, 7]
+SWEEP_DIM = (4096, 4096)
+SWEEP_BYTES_PER_SITE = 18                         # 1 B status read + 17 B slot codes written
+
+
+def wse2_rates():
+    import math
+    r = [0.0] * 13
+    for c, e in WSE2_BARRIERS.items():
+        r[c] = math.exp(-e / (TEMPERATURE * KB_EV))
+    return r
+
+
+def synthetic_lattices(n_replicas, replica0, dim=DIM, frac_div=0.05, frac_mono=0.05):
+    """'exact'-mode lattices (reference demo1/state.py:360-378 semantics: exact defect counts at
+    shuffled positions), vectorised: one independent permutation per replica."""
+    n = dim[0] * dim[1]
+    nd, nm = round(frac_div * n), round((frac_div + frac_mono) * n)
+    rng = np.random.Generator(np.random.Philox(key=SEED + 7919 * replica0))
+    base = np.zeros((n_replicas, n), dtype=np.uint8)
+    base[:, :nd] = 3
+    base[:, nd:nm] = rng.integers(1, 3, size=(n_replicas, nm - nd), dtype=np.uint8)
+    return rng.permuted(base, axis=1)
+
+
+def iid_lattice(dim, seed):
+    rng = np.random.Generator(np.random.Philox(seed))
+    return rng.choice(np.arange(4, dtype=np.uint8), size=dim[0] * dim[1],
+                      p=(0.90, 0.025, 0.025, 0.05)).astype(np.uint8)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+# -------------------------------------------------------------------------------------------------
+def cpu_port_events_per_sec(n_threads, target_seconds, rates, order):
+    """The CPU oracle port on the host cores: one independent trajectory per thread at a time
+    (the reference runs one trajectory per process).  bench.py may execute oracle/ only here."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kmc_oracle as ko
+    probe_r, probe_e = n_threads, 20000
+    st = synthetic_lattices(probe_r, 0)
+    t0 = time.perf_counter()
+    ko.run_replicas(DIM, rates, order, st, seed=SEED, nsteps=probe_e, threads=n_threads)
+    rate = probe_r * probe_e / (time.perf_counter() - t0)
+    n_rep = 4 * n_threads
+    n_ev = int(max(20000, min(5_000_000, rate * target_seconds / n_rep)))
+    st = synthetic_lattices(n_rep, 0)
+    t0 = time.perf_counter()
+    done, hist, _ = ko.run_replicas(DIM, rates, order, st, seed=SEED, nsteps=n_ev, threads=n_threads)
+    dt = time.perf_counter() - t0
+    return done / dt, "%d replicas x %d events, %d threads, %.1f s" % (n_rep, n_ev, n_threads, dt), dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path, as its C port (the Python
+    reference cannot travel to the GPU box), on all host threads, same workload/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rates, order = wse2_rates(), WSE2_ORDER
+    n_threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import kmc_oracle as ko
+    n_rep = 4 * n_threads
+    # calibrate one step to ~ (120 s / (steps + warmup)), capped at 10 s
+    st = synthetic_lattices(n_threads, 0)
+    t0 = time.perf_counter()
+    ko.run_replicas(DIM, rates, order, st, seed=SEED, nsteps=20000, threads=n_threads)
+    rate = n_threads * 20000 / (time.perf_counter() - t0)
+    per_step_s = min(10.0, 120.0 / (args.steps + args.warmup))
+    n_ev = int(max(5000, rate * per_step_s / n_rep))
+    st = synthetic_lattices(n_rep, 0)
+    for w in range(args.warmup):
+        ko.run_replicas(DIM, rates, order, st, seed=SEED, nsteps=n_ev, step0=w * n_ev, threads=n_threads)
+    t0 = time.perf_counter()
+    total = 0
+    for k in range(args.steps):
+        done, _, _ = ko.run_replicas(DIM, rates, order, st, seed=SEED, nsteps=n_ev,
+                                     step0=(args.warmup + k) * n_ev, threads=n_threads)
+        total += done
+    dt = time.perf_counter() - t0
+    value = total / dt
+    sample = "%d replicas x %d events per step (64x64 WSe2, 1500 K), %d host threads" % (n_rep, n_ev, n_threads)
+    line = {
+        "impl": "reference", "metric": "kmc_events_per_sec", "value": value, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 lattice / f64 rates",
+        "data": "synthetic",
+        "config": {"workload": "config/WSe2.yaml 64x64 lattice, independent replicas, CPU port of the "
+                               "reference hot path (oracle/kmc_oracle.c), bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": n_threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--replicas", type=int, default=16384, help="replicas per GPU")
+    ap.add_argument("--events", type=int, default=10000, help="events per replica per step (launch)")
+    ap.add_argument("--warps-per-block", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sweep-iters", type=int, default=20)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from demo1 import _native as nat
+    from demo1.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    rates, order = wse2_rates(), WSE2_ORDER
+    R, E = args.replicas, args.events
+    replica0 = rank * R                     # global replica index -> results independent of GPU count
+    lattices = synthetic_lattices(R, replica0)
+    host = torch.from_numpy(lattices).pin_memory()
+    host_out = torch.empty_like(host).pin_memory()
+    eng = Engine(DIM, rates, order, n_replicas=R, device=local)
+    if args.warps_per_block:
+        eng.set_warps_per_block(args.warps_per_block)
+    eng.upload_state(host.numpy())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")        # > 126 MB L2
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    for _ in range(args.warmup):
+        eng.run(E, SEED, replica0=replica0)
+    eng.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = eng.launch_count()
+    total_ms = 0.0
+    for _ in range(args.steps):
+        flush_l2()
+        eng.timer_start()
+        eng.run(E, SEED, replica0=replica0)
+        total_ms += eng.timer_stop()
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * R * E * args.steps / (max_ms * 1e-3)
+    steps_done = eng.steps_done()
+    assert int(steps_done.min()) == (args.warmup + args.steps) * E, "a replica stopped early"
+
+    # the one collective of the path: event histogram summed over GPUs (NCCL over NVLink)
+    hist = torch.from_numpy(eng.histogram()).to("cuda")
+    if world > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+    hist = hist.cpu().numpy()
+    assert int(hist.sum()) == world * R * E * (args.warmup + args.steps)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------------
+    def e2e_step():
+        eng.upload_state(host.numpy())                     # H2D from pinned memory (+ device-side validation)
+        eng.run(E, SEED, replica0=replica0)
+        out = eng.download_state_into(host_out.numpy())    # D2H final lattices
+        h = eng.histogram_per_replica()                    # D2H statistics
+        return out, h
+
+    eng.reset_stats()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * R * E * args.steps / float(t.item())
+    h2d = R * DIM[0] * DIM[1]
+    d2h = R * DIM[0] * DIM[1] + R * 13 * 8
+    eng.close()
+
+    # ---- HBM roofline: 4096^2 full rate sweep (rank 0 of each GPU does it; reported from rank 0) -----
+    roofline = None
+    if not args.no_sweep:
+        peak, peak_src = measured_peaks()
+        sw = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
+        sw.upload_state(iid_lattice(SWEEP_DIM, SEED))
+        for _ in range(3):
+            sw.sweep()
+        sw.sync()
+        l0 = sw.launch_count()
+        ms = []
+        for _ in range(args.sweep_iters):
+            flush_l2()
+            sw.timer_start()
+            sw.sweep()
+            ms.append(sw.timer_stop())
+        sweep_launches = sw.launch_count() - l0
+        sw.close()
+        avg_ms = float(np.mean(ms))
+        nsites = SWEEP_DIM[0] * SWEEP_DIM[1]
+        achieved = nsites * SWEEP_BYTES_PER_SITE / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": "kmc_sweep_kernel (K1+K2, 4096x4096 full rate sweep)", "bound": "hbm",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "bytes_per_site": SWEEP_BYTES_PER_SITE,
+                    "ms_per_sweep": avg_ms, "ms_min": float(np.min(ms)), "sites_per_s": nsites / (avg_ms * 1e-3),
+                    "note": "timed region = memset of row counts + sweep kernel + count reduction kernel"}
+        launches += sweep_launches
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_threads = os.cpu_count() or 1
+        v, sample, _ = cpu_port_events_per_sec(n_threads, 12.0, rates, order)
+        cpu = {"value": v, "unit": "events/s", "cores": n_threads, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        per_sm = value / world / 148.0
+        line = {
+            "metric": "kmc_events_per_sec", "value": value, "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 lattice / f64 rates", "data": "synthetic",
+            "config": {"workload": "config/WSe2.yaml (MoveMonovacancy stub disabled) T=1500K, 64x64 lattice, "
+                                   "5%% divacancy + 5%% monovacancy, %d independent replicas per GPU, "
+                                   "one warp per replica" % R,
+                       "replicas_per_gpu": R, "events_per_replica_per_step": E,
+                       "l2": "flushed (256 MiB write) between timed iterations", "seed": SEED,
+                       "parallelism": "replicas sharded by contiguous global index; one NCCL all-reduce of "
+                                      "the event histogram at the end"},
+            "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "replica_kernel": {"bound": "sm-issue / shared-memory (lattice resident in smem, ~0 HBM bytes per event)",
+                               "events_per_s_per_sm": per_sm, "sm_cycles_per_event": sm_clock / per_sm,
+                               "hbm_bytes_per_event_algorithmic": 2.0 * DIM[0] * DIM[1] / E},
+            "cpu_baseline": cpu,
+            "event_histogram": [int(x) for x in hist],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

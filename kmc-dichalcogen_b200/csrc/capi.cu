@@ -134,27 +134,42 @@ extern "C" int kmc_destroy(kmc_engine *h)
 }
 
 // ---- lattice transfer ---------------------------------------------------------------------------
-static int check_state_host(const kmc_engine *h, const uint8_t *s)
+// State invariants (reference demo1/state.py:102-149): known status codes, complete trefoils.
+// Checked on the device after the copy so that a 64 MiB batch upload is not CPU-bound.
+__global__ void kmc_check_state_kernel(const uint8_t *status, long long total, int d0, int d1, int *result)
 {
-    // State invariants (reference demo1/state.py:102-149): known status codes, complete trefoils
-    static const int TM[2][3][2] = {{{0, 0}, {2, 0}, {0, 2}}, {{0, 0}, {2, 0}, {2, -2}}};
-    for (int r = 0; r < h->R; r++) {
-        const uint8_t *st = s + (size_t)r * h->n;
-        for (int i = 0; i < h->n; i++) {
-            int v = st[i];
-            if (v > 9) return fail(KMC_ERR_STATE, "invalid status byte (> 9)");
-            if (v >= 4) {
-                int o = (v - 4) / 3, role = (v - 4) % 3;
-                int a = i / h->d1 - TM[o][role][0], b = i % h->d1 - TM[o][role][1];
-                for (int q = 0; q < 3; q++) {
-                    int aa = ((a + TM[o][q][0]) % h->d0 + h->d0) % h->d0;
-                    int bb = ((b + TM[o][q][1]) % h->d1 + h->d1) % h->d1;
-                    if (st[aa * h->d1 + bb] != 4 + 3 * o + q)
-                        return fail(KMC_ERR_STATE, "incomplete trefoil in the uploaded lattice");
-                }
-            }
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total) return;
+    const int n = d0 * d1;
+    const long long rep = g / n;
+    const int i = (int)(g - rep * n);
+    const uint8_t *st = status + rep * n;
+    const int v = st[i];
+    if (v > 9) { atomicOr(result, 1); return; }
+    if (v >= 4) {
+        const int o = (v - 4) / 3, role = (v - 4) % 3;
+        // member offsets: Up {0,0},{2,0},{0,2}; Down {0,0},{2,0},{2,-2}
+        const int ma[3] = {0, 2, o ? 2 : 0}, mb[3] = {0, 0, o ? -2 : 2};
+        const int a = i / d1 - ma[role], b = i % d1 - mb[role];
+        for (int q = 0; q < 3; q++) {
+            const int aa = ((a + ma[q]) % d0 + d0) % d0, bb = ((b + mb[q]) % d1 + d1) % d1;
+            if (st[aa * d1 + bb] != 4 + 3 * o + q) atomicOr(result, 2);
         }
     }
+}
+
+static int check_state_device(kmc_engine *h)
+{
+    CU(cudaMemsetAsync(h->d_result, 0, sizeof(int), h->stream));
+    const long long total = (long long)h->R * h->n;
+    kmc_check_state_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(h->d_status, total, h->d0, h->d1, h->d_result);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    int res = 0;
+    CU(cudaMemcpyAsync(&res, h->d_result, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (res & 1) return fail(KMC_ERR_STATE, "invalid status byte (> 9) in the lattice");
+    if (res & 2) return fail(KMC_ERR_STATE, "incomplete trefoil in the lattice");
     return KMC_OK;
 }
 
@@ -162,11 +177,9 @@ extern "C" int kmc_upload_state(kmc_engine *h, const uint8_t *host_status)
 {
     int rc = bind(h); if (rc) return rc;
     if (!host_status) return fail(KMC_ERR_ARG, "kmc_upload_state: null buffer");
-    rc = check_state_host(h, host_status); if (rc) return rc;
     CU(cudaMemcpyAsync(h->d_status, host_status, (size_t)h->R * h->n, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
     h->swept = false;
-    return KMC_OK;
+    return check_state_device(h);
 }
 
 extern "C" int kmc_download_state(kmc_engine *h, uint8_t *host_status)
@@ -184,7 +197,7 @@ extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
     if (!dev_status) return fail(KMC_ERR_ARG, "kmc_set_state_device: null pointer");
     CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
     h->swept = false;
-    return KMC_OK;
+    return check_state_device(h);
 }
 
 extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)

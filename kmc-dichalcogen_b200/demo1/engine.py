@@ -44,6 +44,11 @@ class Engine:
         nat.check(self._lib.kmc_download_state(self._h, out.ctypes.data))
         return out
 
+    def download_state_into(self, out):
+        assert out.dtype == np.uint8 and out.size == self.n_replicas * self.n and out.flags.c_contiguous
+        nat.check(self._lib.kmc_download_state(self._h, out.ctypes.data))
+        return out
+
     def set_state_device(self, dev_ptr):
         nat.check(self._lib.kmc_set_state_device(self._h, C.c_void_p(int(dev_ptr))))
 
