@@ -144,8 +144,11 @@ int kmc_get_launch_count(kmc_engine *h, int64_t *out);
 /* raw device pointers (for callers that share device memory, e.g. torch tensors / NCCL) */
 int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **row_counts,
                             void **histogram);
-/* tuning knob: warps (replicas) per CTA of the replica kernel; 0 = automatic */
+/* tuning knobs: warps (replicas) per CTA of the replica kernel, 0 = automatic (max 8); and which
+ * replica kernel runs: 0 = automatic (bit-sliced lattice when dim1 <= 64, byte lattice otherwise),
+ * 1 = byte lattice, 2 = bit-sliced.  Both produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
+int kmc_set_replica_kernel(kmc_engine *h, int variant);
 
 /*
  * Event classes (reference demo1/rules.py):           Move slots per site (move key in the reference):

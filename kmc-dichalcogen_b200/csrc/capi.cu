@@ -12,6 +12,7 @@
 #include "kmc_common.cuh"
 #include "noinc_kernel.cuh"
 #include "replica_kernel.cuh"
+#include "replica_bp_kernel.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace kmc;
@@ -41,12 +42,15 @@ struct kmc_engine {
     uint8_t *d_slots = nullptr;              // [R][17][n], allocated on first sweep
     uint32_t *d_rowcnt = nullptr;            // [R][d0][16]
     unsigned long long *d_counts = nullptr;  // [R][13]
+    unsigned long long *d_acc = nullptr;     // [R][16] running totals of the aligned sweep (zero between launches)
+    unsigned int *d_ticket = nullptr;        // [R]
     unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr;
     uint32_t *d_flags = nullptr;
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
     int *d_result = nullptr;
     int warps_per_block = 0;
+    int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes
     long long launches = 0;
     bool swept = false;
     int max_smem_optin = 0;
@@ -124,6 +128,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
+    cudaFree(h->d_acc); cudaFree(h->d_ticket);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -215,6 +220,27 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     const size_t R = (size_t)h->R;
     if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * RCG_STRIDE * sizeof(uint32_t)));
     if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * NS * h->n));
+    // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas, one launch in total
+    const int cpr = h->d1 >> 4;
+    const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
+    if (aligned) {
+        if (!h->d_acc) {
+            CU(cudaMalloc(&h->d_acc, R * 16 * sizeof(unsigned long long)));
+            CU(cudaMalloc(&h->d_ticket, R * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(h->d_acc, 0, R * 16 * sizeof(unsigned long long), h->stream));
+            CU(cudaMemsetAsync(h->d_ticket, 0, R * sizeof(unsigned int), h->stream));
+        }
+        Sweep16Params q;
+        q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
+        q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
+        q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
+        q.ctas_per_replica = (h->n >> 4) / 256;
+        const long long blocks = (long long)R * q.ctas_per_replica;
+        kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        return KMC_OK;
+    }
     CU(cudaMemsetAsync(h->d_rowcnt, 0, R * h->d0 * RCG_STRIDE * sizeof(uint32_t), h->stream));
     SweepParams p;
     p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
@@ -324,7 +350,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
     if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
     if (log_mode != KMC_LOG_NONE && !host_events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
-    const size_t wbytes = replica_warp_bytes(h->d0, h->d1);
+    // rows of <= 64 sites run on the bit-sliced kernel, wider rows on the byte-lattice kernel
+    const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64);
+    if (bitplanes && h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernel needs dim1 <= 64");
+    const size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1);
     if (wbytes > (size_t)h->max_smem_optin) {
         char b[256];
         snprintf(b, sizeof b, "lattice %dx%d needs %zu B of shared memory per replica (limit %d): use kmc_run_noinc",
@@ -332,8 +361,8 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         return fail(KMC_ERR_ARG, b);
     }
     int W = h->warps_per_block > 0 ? h->warps_per_block : 8;
+    if (W > 8) W = 8;
     while (W > 1 && W * wbytes > (size_t)h->max_smem_optin) W--;
-    if (W > 32) W = 32;
     const size_t smem = W * wbytes;
     const size_t rs = record_size(log_mode);
     if (rs) { int rc = ensure_events(h, rs * (size_t)h->R * (size_t)nsteps); if (rc) return rc; }
@@ -347,13 +376,20 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
     p.validate = validate;
     const unsigned blocks = (unsigned)((h->R + W - 1) / W);
-    if (h->d0 == 64 && h->d1 == 64) {
-        CU(cudaFuncSetAttribute(kmc_replica_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kmc_replica_kernel<64, 64><<<blocks, W * 32, smem, h->stream>>>(p);
+#define KMC_LAUNCH(KERNEL)                                                                               \
+    do {                                                                                                 \
+        CU(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        CU(cudaFuncSetAttribute(KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, 100));            \
+        KERNEL<<<blocks, W * 32, smem, h->stream>>>(p);                                                   \
+    } while (0)
+    if (bitplanes) {
+        if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>));
+        else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0>));
     } else {
-        CU(cudaFuncSetAttribute(kmc_replica_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kmc_replica_kernel<0, 0><<<blocks, W * 32, smem, h->stream>>>(p);
+        if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_kernel<64, 64>));
+        else KMC_LAUNCH((kmc_replica_kernel<0, 0>));
     }
+#undef KMC_LAUNCH
     CU(cudaGetLastError());
     h->launches += 1;
     h->swept = false;
@@ -521,8 +557,14 @@ extern "C" int kmc_get_device_pointers(kmc_engine *h, void **status, void **slot
 }
 extern "C" int kmc_set_warps_per_block(kmc_engine *h, int warps)
 {
-    if (!h || warps < 0 || warps > 32) return fail(KMC_ERR_ARG, "warps per block must be 0..32");
+    if (!h || warps < 0 || warps > 8) return fail(KMC_ERR_ARG, "warps per block must be 0..8");
     h->warps_per_block = warps;
+    return KMC_OK;
+}
+extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)
+{
+    if (!h || variant < 0 || variant > 2) return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice) or 2 (bit planes)");
+    h->variant = variant;
     return KMC_OK;
 }
 

@@ -33,6 +33,43 @@ extern "C" int kmc_hostcheck_sweep_words(const uint8_t *status, int d0, int d1, 
     return 0;
 }
 
+// Emulates kmc_sweep16_kernel's chunk gathering (16 sites per thread) on the host.
+extern "C" int kmc_hostcheck_sweep_words16(const uint8_t *status, int d0, int d1, uint8_t *slots, int64_t *counts)
+{
+    if (d1 & 15) return -1;
+    const int n = d0 * d1, cpr = d1 >> 4, wpr = d1 >> 2;
+    const uint32_t *S = reinterpret_cast<const uint32_t *>(status);
+    for (int c = 0; c < NC; c++) counts[c] = 0;
+    for (int a = 0; a < d0; a++)
+        for (int ci = 0; ci < cpr; ci++) {
+            const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+            const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+            const uint32_t *r0 = S + a * wpr, *rm = S + am * wpr, *rp = S + ap * wpr, *rq = S + ap2 * wpr;
+            ZD cf[6], mf[5], pf[5];
+            uint32_t qd[5], cw[4];
+            cf[0] = zd_flags(r0[4 * cim + 3]); cf[5] = zd_flags(r0[4 * cin]);
+            pf[0] = zd_flags(rp[4 * cim + 3]); qd[0] = zd_flags(rq[4 * cim + 3]).div;
+            mf[4] = zd_flags(rm[4 * cin]);
+            for (int j = 0; j < 4; j++) {
+                cw[j] = r0[4 * ci + j];
+                cf[1 + j] = zd_flags(cw[j]); mf[j] = zd_flags(rm[4 * ci + j]);
+                pf[1 + j] = zd_flags(rp[4 * ci + j]); qd[1 + j] = zd_flags(rq[4 * ci + j]).div;
+            }
+            ByteAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < 4; j++) {
+                uint32_t out[NS];
+                sweep_word16(cw[j], cf[j], cf[j + 1], cf[j + 2], mf[j], mf[j + 1], pf[j], pf[j + 1], qd[j], qd[j + 1], out, acc);
+                for (int q = 0; q < NS; q++) memcpy(slots + (size_t)q * n + (size_t)a * d1 + 16 * ci + 4 * j, &out[q], 4);
+            }
+            const uint32_t z = hsum(acc.zero), dv = hsum(acc.div), mo = hsum(acc.mono);
+            counts[0] += z; counts[1] += dv; counts[2] += hsum(acc.nat); counts[3] += hsum(acc.met);
+            counts[4] += hsum(acc.cmb); counts[5] += hsum(acc.bth); counts[6] += hsum(acc.tref);
+            counts[7] += hsum(acc.anch); counts[8] += 2 * z; counts[9] += mo; counts[10] += mo;
+            counts[11] += 2 * dv; counts[12] += mo;
+        }
+    return 0;
+}
+
 // eval_site over the whole lattice: out [n][13] class counts per site
 extern "C" int kmc_hostcheck_eval_sites(const uint8_t *status, int d0, int d1, uint8_t *out)
 {

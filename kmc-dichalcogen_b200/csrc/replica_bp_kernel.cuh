@@ -1,0 +1,526 @@
+// replica_bp_kernel.cuh -- K3 + K4 for lattices with rows of <= 64 sites: the fused
+// select -> apply -> refresh kernel on a BIT-SLICED lattice.
+//
+// One warp owns one replica.  The lattice is held in shared memory as six predicate bit-planes, one
+// 64-bit word per lattice row per plane:
+//     Z  pristine          D  divacancy         M1 / M2  monovacancy in layer 1 / 2
+//     A4 / A7  anchor (role 0) of an Up / Down trefoil          (no bit set = other trefoil member)
+// so that every neighbourhood predicate of the reference's rules (demo1/rules.py) becomes a handful
+// of 64-site-wide Boolean operations on rotated row words (periodic wrap = bit rotation):
+//     MoveDivacancy direction k, kind q :  D[a] & rot(Z[a+da_n]) & (+/-)rot(D[near]) & (+/-)rot(D[far])
+//     CreateTrefoil Up / Down           :  D[a] & D[a+2] & rot(D[a], +2)   /   D[a] & D[a+2] & rot(D[a+2], -2)
+// The Fenwick-style hierarchy for the in-class rank search is the per-row x per-class move count table
+// (uint16, class-major) next to the planes; class totals live in registers (lane c owns class c).
+//
+// Neighbourhood refresh after an event (reference sim.py:149-157, rules.py pre/post_status_change) is
+// "recompute and replace": the <= 5 rows whose MoveDivacancy counts can change are re-derived by
+// 30 lanes (row x direction) with popcounts, the <= 6 anchor rows of CreateTrefoil by 6 lanes, and the
+// own-status classes by their owner lanes from (old status, new status) of the <= 3 touched nodes.
+// No per-site re-enumeration, no atomics.
+//
+// Results are bit-identical to replica_kernel.cuh (the byte-lattice kernel used for wider rows) and to
+// the CPU oracle; the tests run both.
+#pragma once
+#include "replica_kernel.cuh"
+
+namespace kmc {
+
+typedef unsigned long long u64;
+enum { PL_Z = 0, PL_D = 1, PL_M1 = 2, PL_M2 = 3, PL_A4 = 4, PL_A7 = 5, N_PLANES = 6 };
+
+__host__ __device__ inline size_t replica_bp_warp_bytes(int d0) {
+    const size_t d0e = ((size_t)d0 + 1) & ~(size_t)1;
+    const size_t planes = (size_t)N_PLANES * d0 * 8;
+    const size_t rc = (NC * d0e * 2 + 15) & ~(size_t)15;
+    return planes + rc;
+}
+
+// neighbors_and_mutuals (reference state.py:443-459), direction k: (da, db) of nbr / near / far
+constexpr u64 NBR_DA = pack_nibbles({-1, 0, 1, 0, -1, 1}),  NBR_DB = pack_nibbles({1, -1, 0, 1, 0, -1});
+constexpr u64 NEAR_DA = pack_nibbles({0, -1, 1, -1, 0, 1}), NEAR_DB = pack_nibbles({1, 0, -1, 1, -1, 0});
+constexpr u64 FAR_DA = pack_nibbles({-1, 1, 0, 1, -1, 0}),  FAR_DB = pack_nibbles({0, -1, 1, 0, 1, -1});
+__host__ __device__ __forceinline__ int nib(u64 t, int k) { return (int)((t >> (4 * k)) & 0xF) - 2; }
+
+// status -> plane index + 1 (0 = no plane: non-anchor trefoil member)
+//   s:      0     1      2      3     4      5  6  7      8  9
+//   plane:  Z(1)  M1(3)  M2(4)  D(2)  A4(5)  0  0  A7(6)  0  0
+constexpr u64 STATUS_PLANE = 0x0060052431ull;
+__host__ __device__ __forceinline__ int status_plane(int s) { return (int)((STATUS_PLANE >> (4 * s)) & 0xF) - 1; }
+
+template <int TD1>
+struct RowBits {
+    int d1; u64 mask;
+    __device__ __forceinline__ RowBits(int d1_) : d1(TD1 ? TD1 : d1_), mask(d1 >= 64 ? ~0ull : ((1ull << d1) - 1)) {}
+    // word whose bit b is x's bit (b + db), periodic in d1;  s = (-db) mod d1 is the left-rotate amount
+    __device__ __forceinline__ u64 rotl(u64 x, int s) const {
+        if (TD1 == 64) return (x << s) | (x >> ((64 - s) & 63));
+        return s ? (((x << s) | (x >> (d1 - s))) & mask) : x;
+    }
+    __device__ __forceinline__ int amount(int db) const { return db > 0 ? d1 - db : -db; }
+    // bits [0, n) set, n in 0..64
+    __device__ __forceinline__ static u64 low(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1); }
+};
+
+struct DirConst { int da_n, s_n, da_e, s_e, da_f, s_f; };
+template <int TD1>
+__device__ __forceinline__ DirConst dir_const(int k, const RowBits<TD1> &rb) {
+    DirConst c;
+    c.da_n = nib(NBR_DA, k);  c.s_n = rb.amount(nib(NBR_DB, k));
+    c.da_e = nib(NEAR_DA, k); c.s_e = rb.amount(nib(NEAR_DB, k));
+    c.da_f = nib(FAR_DA, k);  c.s_f = rb.amount(nib(FAR_DB, k));
+    return c;
+}
+__device__ __forceinline__ int wrap1(int x, int d) { return x < 0 ? x + d : (x >= d ? x - d : x); }
+
+// MoveDivacancy of row `a`, direction constants `c`: present / near / far masks over the row's sites
+template <int TD1>
+__device__ __forceinline__ void dir_masks(const u64 *PL, int d0, int a, const DirConst &c, const RowBits<TD1> &rb,
+                                          u64 &present, u64 &near, u64 &far) {
+    const u64 Da = PL[PL_D * d0 + a];
+    present = Da & rb.rotl(PL[PL_Z * d0 + wrap1(a + c.da_n, d0)], c.s_n);
+    near = rb.rotl(PL[PL_D * d0 + wrap1(a + c.da_e, d0)], c.s_e);
+    far = rb.rotl(PL[PL_D * d0 + wrap1(a + c.da_f, d0)], c.s_f);
+}
+// counts of the four kinds (natural, missing-metal, missing-comb, missing-both), 16 bits each
+__device__ __forceinline__ void kind_counts(u64 present, u64 near, u64 far, uint32_t &pk01, uint32_t &pk23) {
+    const u64 pn = present & near, pf = present & far;
+    const uint32_t n3 = __popcll(pn & far), n1 = __popcll(pn) - n3, n2 = __popcll(pf) - n3;
+    const uint32_t n0 = __popcll(present) - n1 - n2 - n3;
+    pk01 = n0 | (n1 << 16);
+    pk23 = n2 | (n3 << 16);
+}
+__device__ __forceinline__ u64 kind_select(u64 present, u64 near, u64 far, int q) {
+    return present & ((q & 1) ? near : ~near) & ((q & 2) ? far : ~far);
+}
+// CreateTrefoil anchored in row `a`: Up / Down masks
+template <int TD1>
+__device__ __forceinline__ void trefoil_masks(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, u64 &up, u64 &dn) {
+    const u64 Da = PL[PL_D * d0 + a];
+    const u64 Db = PL[PL_D * d0 + wrap1(a + 2, d0)];
+    const u64 both = Da & Db;
+    up = both & rb.rotl(Da, rb.amount(2));
+    dn = both & rb.rotl(Db, rb.amount(-2));
+}
+
+// all 13 class counts of row `a` (full enumeration of one row; used at launch start and by validate)
+template <int TD1>
+__device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
+    const uint32_t pz = __popcll(PL[PL_Z * d0 + a]), pd = __popcll(PL[PL_D * d0 + a]);
+    const uint32_t pm = __popcll(PL[PL_M1 * d0 + a] | PL[PL_M2 * d0 + a]);
+    const uint32_t pa = __popcll(PL[PL_A4 * d0 + a] | PL[PL_A7 * d0 + a]);
+    out[C_CREATE_DIV] = pz; out[C_FILL_DIV] = pd; out[C_DESTROY_TREF] = pa;
+    out[C_CMONO_FROM_DOUBLE] = 2 * pz; out[C_CMONO_MAKE_EMPTY] = pm; out[C_FMONO_MAKE_DOUBLE] = pm;
+    out[C_FMONO_FROM_EMPTY] = 2 * pd; out[C_FLIP] = pm;
+    uint32_t k01 = 0, k23 = 0;
+    for (int k = 0; k < 6; k++) {
+        const DirConst c = dir_const(k, rb);
+        u64 p, n, f; dir_masks(PL, d0, a, c, rb, p, n, f);
+        uint32_t a01, a23; kind_counts(p, n, f, a01, a23);
+        k01 += a01; k23 += a23;
+    }
+    out[C_MOVE_DIV] = k01 & 0xFFFF; out[C_MOVE_DIV + 1] = k01 >> 16;
+    out[C_MOVE_DIV + 2] = k23 & 0xFFFF; out[C_MOVE_DIV + 3] = k23 >> 16;
+    u64 up, dn; trefoil_masks(PL, d0, a, rb, up, dn);
+    out[C_CREATE_TREF] = __popcll(up) + __popcll(dn);
+}
+
+// position of the (idx)-th set bit (0-based) of a row mask, found by 32 lanes in parallel:
+// lane l counts the set bits below site 2l+2.  Returns the column; *before = set bits below it.
+__device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane) {
+    const uint32_t c = __popcll(m & RowBits<64>::low(2 * lane + 2));
+    const uint32_t ball = __ballot_sync(FULL, c > idx);
+    const int L = __ffs(ball) - 1;
+    const uint32_t below = __popcll(m & RowBits<64>::low(2 * L));
+    return 2 * L + (int)!(((m >> (2 * L)) & 1ull) && idx == below);
+}
+
+template <int TD0, int TD1>
+__global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaParams p)
+{
+    const int d0 = TD0 ? TD0 : p.d0;
+    const int d1 = TD1 ? TD1 : p.d1;
+    const int n = d0 * d1;
+    const int d0e = (d0 + 1) & ~1;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int rep = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (rep >= p.n_replicas) return;       // whole warp exits together; no block barriers are used
+    const RowBits<TD1> rb(d1);
+
+    extern __shared__ uint4 smem_raw[];
+    u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_bp_warp_bytes(d0));
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + N_PLANES * d0);      // [NC][d0e]
+    const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(rc16);
+
+    // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
+    uint8_t *gst = p.status + (size_t)rep * n;
+    for (int a = lane; a < d0; a += 32) {
+        u64 w[N_PLANES] = {0, 0, 0, 0, 0, 0};
+        if ((d1 & 3) == 0) {
+            const uint32_t *g32 = reinterpret_cast<const uint32_t *>(gst + a * d1);
+            for (int b4 = 0; b4 < (d1 >> 2); b4++) {
+                const uint32_t v = g32[b4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int pl = status_plane((v >> (8 * i)) & 0xF);
+#pragma unroll
+                    for (int q = 0; q < N_PLANES; q++) w[q] |= (u64)(pl == q) << (4 * b4 + i);
+                }
+            }
+        } else {
+            for (int b = 0; b < d1; b++) {
+                const int pl = status_plane(gst[a * d1 + b]);
+#pragma unroll
+                for (int q = 0; q < N_PLANES; q++) w[q] |= (u64)(pl == q) << b;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < N_PLANES; q++) PL[q * d0 + a] = w[q];
+    }
+    __syncwarp();
+    // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
+    for (int a = lane; a < d0e; a += 32) {
+        uint32_t cnt[NC];
+        if (a < d0) bp_row_counts(PL, d0, a, rb, cnt);
+#pragma unroll
+        for (int c = 0; c < NC; c++) rc16[c * d0e + a] = a < d0 ? (uint16_t)cnt[c] : (uint16_t)0;
+    }
+    __syncwarp();
+
+    // per-lane class state: lane c < 13 owns class c; lanes 13..15 are permanent zero weights
+    const int myc = lane < NC ? lane : 0;
+    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    int tot = 0;
+    if (lane < NC)
+        for (int a = 0; a < d0; a++) tot += rc16[lane * d0e + a];
+    // own-status classes: 2 bits per status = moves of my class a site of that status carries
+    const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
+    unsigned long long hist = 0, n_ties = 0;
+    int sc = lane & 15;
+    bool need_sort = true;
+    // refresh roles: lane = 6*j + k -> (row slot j, direction k)
+    const int my_j = lane / 6, my_k = lane % 6;
+    const DirConst my_dir = dir_const(my_k, rb);
+
+    const unsigned long long step_base = p.steps_done[rep];
+    double mu1 = 0.0, mu2 = 0.0;
+    long long t = 0;
+    uint32_t flag = 0;
+
+    for (; t < p.nsteps; t++) {
+        // ---- draws: a block of 32 events at a time, one event per lane ----------------------
+        if ((t & 31) == 0) {
+            const long long tt = t + lane;
+            if (tt < p.nsteps) {
+                if (p.draws) {
+                    const double2 u = *reinterpret_cast<const double2 *>(
+                        p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)tt) * 2);
+                    mu1 = u.x; mu2 = u.y;
+                } else {
+                    kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step_base + (unsigned long long)tt, mu1, mu2);
+                }
+            }
+        }
+        const double u1 = __shfl_sync(FULL, mu1, (int)(t & 31));
+        const double u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
+
+        // ---- 1./2. weights and class choice (sim.py:120-122, kmc.py:21-54) ----------------------
+        const double w = __dmul_rn((double)tot, rate);
+        const ClassPick pick = pick_class(w, pos, sc, need_sort, u1, lane);
+        if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
+            flag |= FLAG_ZERO_RATE;
+            if (p.log_mode != KMC_LOG_NONE && lane == 0) {
+                const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
+                if (p.log_mode == KMC_LOG_FULL) {
+                    kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+                    rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
+                    rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
+                } else {
+                    kmc_event_compact e;
+                    e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE; e.flags = 0;
+                    e.total_rate = 0.0;
+                    reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
+                }
+            }
+            break;
+        }
+        const int csel = pick.csel;
+        if (p.log_mode == KMC_LOG_FULL) {
+            kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
+                                  ((size_t)rep * (size_t)p.nsteps + (size_t)t);
+            if (lane < NC) rec->counts[lane] = (uint32_t)tot;
+        }
+
+        // ---- 3. in-class pick: rank in (site, slot) order ------------------------------------------
+        const int cnt = __shfl_sync(FULL, tot, csel);
+        uint32_t r;
+        {
+            long long rr = (long long)__dmul_rn(u2, (double)cnt);
+            if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
+            r = (uint32_t)rr;
+        }
+        // 3a. row: two rows per lane per pass (one 32-bit load of two uint16 counts)
+        int row = 0;
+        for (int base = 0; base < d0; base += 64) {
+            const int r0 = base + 2 * lane;
+            const uint32_t v01 = (r0 < d0) ? rc32[(csel * d0e + r0) >> 1] : 0u;
+            const uint32_t v0 = v01 & 0xFFFFu, v1 = v01 >> 16;
+            int L;
+            if (warp_rank_search(v0 + v1, r, L, lane)) {
+                const uint32_t v0L = __shfl_sync(FULL, v0, L);
+                row = base + 2 * L;
+                if (r >= v0L) { r -= v0L; row++; }
+                break;
+            }
+        }
+        // 3b/3c. site within the row and slot within the site
+        int col, slot, s0;
+        if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
+            // lanes 0..5 derive their direction's kind mask for this row, everyone gets all six
+            u64 pr, ne, fa;
+            dir_masks(PL, d0, row, my_dir, rb, pr, ne, fa);
+            const u64 mine = lane < 6 ? kind_select(pr, ne, fa, csel - C_MOVE_DIV) : 0ull;
+            const u64 lowm = RowBits<64>::low(2 * lane + 2);
+            uint32_t c = 0;
+#pragma unroll
+            for (int k = 0; k < 6; k++) c += __popcll(__shfl_sync(FULL, mine, k) & lowm);
+            const uint32_t ball = __ballot_sync(FULL, c > r);
+            const int L = __ffs(ball) - 1;
+            const uint32_t cprev = __shfl_sync(FULL, c, (L + 31) & 31);
+            uint32_t rem = r - (L ? cprev : 0u);
+            // directions present at sites 2L and 2L+1, as 6-bit masks in k order
+            const uint32_t m0 = __ballot_sync(FULL, (mine >> (2 * L)) & 1ull) & 0x3Fu;
+            const uint32_t m1 = __ballot_sync(FULL, (mine >> (2 * L + 1)) & 1ull) & 0x3Fu;
+            const uint32_t n0 = __popc(m0);
+            uint32_t km = m0;
+            col = 2 * L;
+            if (rem >= n0) { rem -= n0; km = m1; col++; }
+            slot = 7 + (__fns(km, 0, (int)rem + 1) & 7);
+            s0 = S_DIVAC;
+        } else if (csel == C_CREATE_TREF) {
+            u64 up, dn;
+            trefoil_masks(PL, d0, row, rb, up, dn);
+            const u64 lowm = RowBits<64>::low(2 * lane + 2);
+            const uint32_t c = __popcll(up & lowm) + __popcll(dn & lowm);
+            const uint32_t ball = __ballot_sync(FULL, c > r);
+            const int L = __ffs(ball) - 1;
+            const u64 lowL = RowBits<64>::low(2 * L);
+            uint32_t rem = r - (__popcll(up & lowL) + __popcll(dn & lowL));
+            const uint32_t u0 = (uint32_t)(up >> (2 * L)) & 1u, w0 = (uint32_t)(dn >> (2 * L)) & 1u;
+            const uint32_t u1b = (uint32_t)(up >> (2 * L + 1)) & 1u;
+            col = 2 * L;
+            if (rem >= u0 + w0) { rem -= u0 + w0; col++; slot = (u1b && rem == 0) ? 13 : 14; }
+            else slot = (u0 && rem == 0) ? 13 : 14;
+            s0 = S_DIVAC;
+        } else {
+            // own-status classes: the sites are one plane (or the union of two), 1 or 2 moves per site
+            const bool two = (csel == C_CMONO_FROM_DOUBLE) || (csel == C_FMONO_FROM_EMPTY);
+            const int pa = (csel == C_CREATE_DIV || csel == C_CMONO_FROM_DOUBLE) ? PL_Z
+                         : (csel == C_FILL_DIV || csel == C_FMONO_FROM_EMPTY) ? PL_D
+                         : (csel == C_DESTROY_TREF) ? PL_A4 : PL_M1;
+            const u64 first = PL[pa * d0 + row];
+            const u64 m = (pa == PL_A4 || pa == PL_M1) ? (first | PL[(pa + 1) * d0 + row]) : first;
+            col = nth_set_bit(m, two ? (r >> 1) : r, lane);
+            const bool in_first = (first >> col) & 1ull;
+            switch (csel) {
+                case C_CREATE_DIV: slot = 0; s0 = 0; break;
+                case C_FILL_DIV: slot = 1; s0 = 3; break;
+                case C_DESTROY_TREF: s0 = in_first ? 4 : 7; slot = in_first ? 15 : 16; break;
+                case C_CMONO_FROM_DOUBLE: slot = 2 + (int)(r & 1); s0 = 0; break;
+                case C_CMONO_MAKE_EMPTY: s0 = in_first ? 1 : 2; slot = 1 + (3 & ~s0); break;
+                case C_FMONO_MAKE_DOUBLE: s0 = in_first ? 1 : 2; slot = 3 + s0; break;
+                case C_FMONO_FROM_EMPTY: slot = 4 + (int)(r & 1); s0 = 3; break;
+                default: s0 = in_first ? 1 : 2; slot = 6; break;
+            }
+        }
+        const int site = row * d1 + col;
+
+        // ---- event record -----------------------------------------------------------------------------
+        if (p.log_mode != KMC_LOG_NONE && lane == 0) {
+            const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
+            if (p.log_mode == KMC_LOG_FULL) {
+                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+                rec->site = (uint32_t)site; rec->cls = (uint8_t)csel; rec->slot = (uint8_t)slot;
+                rec->flags = pick.tie ? 1 : 0; rec->total_rate = pick.total; rec->pad = 0;
+            } else {
+                kmc_event_compact e;
+                e.site = (uint32_t)site; e.cls = (uint8_t)csel; e.slot = (uint8_t)slot;
+                e.flags = pick.tie ? 1 : 0; e.total_rate = pick.total;
+                reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
+            }
+        }
+        if (lane == csel) hist++;
+        if (pick.tie && lane == 0) n_ties++;
+
+        // ---- 4. the move (uniform): touched nodes, old and new status --------------------------------
+        const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
+        const int na = mv.na;
+        int os1 = 0, os2 = 0;                      // old status of nodes 1, 2 (node 0: s0)
+        if (slot >= 13) {
+            const bool create = slot < 15;
+            const int o = (slot - 13) & 1;
+            os1 = create ? S_DIVAC : S_TREF + 3 * o + 1;
+            os2 = create ? S_DIVAC : S_TREF + 3 * o + 2;
+        }
+        // bit planes: lane q < 6 maintains plane q (program order handles nodes sharing a row)
+        if (lane < N_PLANES) {
+            {
+                u64 wv = PL[lane * d0 + row];
+                const u64 bit = 1ull << col;
+                wv = (status_plane(mv.ns0) == lane) ? (wv | bit) : (wv & ~bit);
+                PL[lane * d0 + row] = wv;
+            }
+            if (na > 1) {
+                u64 wv = PL[lane * d0 + mv.a1];
+                const u64 bit = 1ull << mv.b1;
+                wv = (status_plane(mv.ns1) == lane) ? (wv | bit) : (wv & ~bit);
+                PL[lane * d0 + mv.a1] = wv;
+            }
+            if (na > 2) {
+                u64 wv = PL[lane * d0 + mv.a2];
+                const u64 bit = 1ull << mv.b2;
+                wv = (status_plane(mv.ns2) == lane) ? (wv | bit) : (wv & ~bit);
+                PL[lane * d0 + mv.a2] = wv;
+            }
+        }
+        // ---- 5a. own-status classes: owner lanes fold (old -> new) of each touched node -----------------
+        if (my_g1) {
+            int d = (int)((my_g1 >> (2 * mv.ns0)) & 3u) - (int)((my_g1 >> (2 * s0)) & 3u);
+            if (d) rc16[lane * d0e + row] = (uint16_t)(rc16[lane * d0e + row] + d);
+            int dsum = d;
+            if (na > 1) {
+                d = (int)((my_g1 >> (2 * mv.ns1)) & 3u) - (int)((my_g1 >> (2 * os1)) & 3u);
+                if (d) rc16[lane * d0e + mv.a1] = (uint16_t)(rc16[lane * d0e + mv.a1] + d);
+                dsum += d;
+            }
+            if (na > 2) {
+                d = (int)((my_g1 >> (2 * mv.ns2)) & 3u) - (int)((my_g1 >> (2 * os2)) & 3u);
+                if (d) rc16[lane * d0e + mv.a2] = (uint16_t)(rc16[lane * d0e + mv.a2] + d);
+                dsum += d;
+            }
+            tot += dsum;
+        }
+        __syncwarp();
+
+        // ---- 5b. MoveDivacancy: rows within +-1 of the touched rows, re-derived and replaced -------------
+        // touched rows relative to `row`: 0 (always), da of the target (moves), +2 (trefoils)
+        int lo = -1, hi = 1;
+        if (slot >= 13) hi = 3;
+        else if (slot >= 7) { const int da = nib(RING_DA, kring(slot - 7)); lo += da < 0 ? da : 0; hi += da > 0 ? da : 0; }
+        {
+            const bool act = my_j <= hi - lo;
+            const int ra = wrap1(wrap1(row + lo + my_j, d0), d0);
+            uint32_t pk01 = 0, pk23 = 0;
+            if (act) {
+                u64 pr, ne, fa;
+                dir_masks(PL, d0, ra, my_dir, rb, pr, ne, fa);
+                kind_counts(pr, ne, fa, pk01, pk23);
+            }
+            pk01 += __shfl_down_sync(FULL, pk01, 3);
+            pk23 += __shfl_down_sync(FULL, pk23, 3);
+            pk01 += __shfl_down_sync(FULL, pk01, 1) + __shfl_down_sync(FULL, pk01, 2);
+            pk23 += __shfl_down_sync(FULL, pk23, 1) + __shfl_down_sync(FULL, pk23, 2);
+            uint32_t d01 = 0, d23 = 0;
+            if (act && my_k == 0) {
+                uint16_t *q = rc16 + C_MOVE_DIV * d0e + ra;
+                const uint32_t o0 = q[0], o1 = q[d0e], o2 = q[2 * d0e], o3 = q[3 * d0e];
+                q[0] = (uint16_t)pk01; q[d0e] = (uint16_t)(pk01 >> 16);
+                q[2 * d0e] = (uint16_t)pk23; q[3 * d0e] = (uint16_t)(pk23 >> 16);
+                // signed 16-bit pair deltas as one integer each (hi*65536 + lo)
+                d01 = pk01 - (o0 | (o1 << 16));
+                d23 = pk23 - (o2 | (o3 << 16));
+            }
+            const int s01 = (int)__reduce_add_sync(FULL, d01);
+            const int s23 = (int)__reduce_add_sync(FULL, d23);
+            const int l01 = (int)(short)(s01 & 0xFFFF), l23 = (int)(short)(s23 & 0xFFFF);
+            if (lane == C_MOVE_DIV) tot += l01;
+            if (lane == C_MOVE_DIV + 1) tot += (s01 - l01) >> 16;
+            if (lane == C_MOVE_DIV + 2) tot += l23;
+            if (lane == C_MOVE_DIV + 3) tot += (s23 - l23) >> 16;
+        }
+        // ---- 5c. CreateTrefoil: anchor rows row-3 .. row+2 (covers t and t-2 of every touched row t) -----
+        {
+            const int ng = d0 < 6 ? d0 : 6;
+            int d = 0;
+            if (lane < ng) {
+                const int ra = wrap1(row + lane - 3, d0);
+                u64 up, dn;
+                trefoil_masks(PL, d0, ra, rb, up, dn);
+                const int nw = __popcll(up) + __popcll(dn);
+                uint16_t *q = rc16 + C_CREATE_TREF * d0e + ra;
+                d = nw - (int)q[0];
+                q[0] = (uint16_t)nw;
+            }
+            const int s = (int)__reduce_add_sync(FULL, (uint32_t)d);
+            if (lane == C_CREATE_TREF) tot += s;
+        }
+        __syncwarp();
+    }
+
+    // ---- epilogue ------------------------------------------------------------------------------------
+    const long long done = t;
+    if (p.validate) {
+        // KmcSim.validate (sim.py:159-168): incremental tables vs a fresh enumeration
+        bool bad = false;
+        for (int a = lane; a < d0; a += 32) {
+            uint32_t cnt[NC];
+            bp_row_counts(PL, d0, a, rb, cnt);
+#pragma unroll
+            for (int c = 0; c < NC; c++) bad |= (rc16[c * d0e + a] != (uint16_t)cnt[c]);
+            // plane consistency: at most one plane bit per site
+            u64 seen = 0, dup = 0;
+#pragma unroll
+            for (int q = 0; q < N_PLANES; q++) { const u64 x = PL[q * d0 + a]; dup |= seen & x; seen |= x; }
+            bad |= dup != 0;
+        }
+        if (lane < NC) {
+            int fresh = 0;
+            for (int a = 0; a < d0; a++) fresh += rc16[lane * d0e + a];
+            bad |= (fresh != tot);
+        }
+        if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
+    }
+    // bit planes -> status bytes.  Pass 1: every site from its own plane bit (non-anchor trefoil
+    // members get a placeholder); pass 2: each anchor writes the codes of its two partners.
+    for (int a = lane; a < d0; a += 32) {
+        const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a], m1 = PL[PL_M1 * d0 + a], m2 = PL[PL_M2 * d0 + a];
+        const u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        auto code_at = [&](int b) -> uint32_t {
+            return ((z >> b) & 1) ? 0u : ((dv >> b) & 1) ? 3u : ((m1 >> b) & 1) ? 1u : ((m2 >> b) & 1) ? 2u
+                 : ((a4 >> b) & 1) ? 4u : ((a7 >> b) & 1) ? 7u : 5u;
+        };
+        if ((d1 & 3) == 0) {
+            uint32_t *g32 = reinterpret_cast<uint32_t *>(gst + a * d1);
+            for (int b4 = 0; b4 < (d1 >> 2); b4++) {
+                const int b = 4 * b4;
+                g32[b4] = code_at(b) | (code_at(b + 1) << 8) | (code_at(b + 2) << 16) | (code_at(b + 3) << 24);
+            }
+        } else {
+            for (int b = 0; b < d1; b++) gst[a * d1 + b] = (uint8_t)code_at(b);
+        }
+    }
+    __syncwarp();
+    for (int a = lane; a < d0; a += 32) {
+        u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        const int a2 = wrap1(a + 2, d0);
+        while (a4) {
+            const int b = __ffsll((long long)a4) - 1; a4 &= a4 - 1;
+            gst[a2 * d1 + b] = (uint8_t)(S_TREF + 1);
+            gst[a * d1 + wrap1(b + 2, d1)] = (uint8_t)(S_TREF + 2);
+        }
+        while (a7) {
+            const int b = __ffsll((long long)a7) - 1; a7 &= a7 - 1;
+            gst[a2 * d1 + b] = (uint8_t)(S_TREF + 4);
+            gst[a2 * d1 + wrap1(b - 2, d1)] = (uint8_t)(S_TREF + 5);
+        }
+    }
+    if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane == 0) {
+        p.steps_done[rep] = step_base + (unsigned long long)done;
+        p.ties[rep] += n_ties;
+        if (flag) p.flags[rep] |= flag;
+    }
+}
+
+}  // namespace kmc

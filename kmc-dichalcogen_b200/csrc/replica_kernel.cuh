@@ -225,7 +225,7 @@ __device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int
 }
 
 template <int TD0, int TD1>
-__global__ void __launch_bounds__(1024, 1) kmc_replica_kernel(const ReplicaParams p)
+__global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;

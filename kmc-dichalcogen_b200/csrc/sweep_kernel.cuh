@@ -182,6 +182,176 @@ __global__ void __launch_bounds__(256) kmc_sweep_kernel(const SweepParams p)
     }
 }
 
+// ---- 16 sites per thread ---------------------------------------------------------------------------
+// Fast path for d1 % 16 == 0 with CTAs aligned to rows and replicas.  One thread owns 16 consecutive
+// sites of a row (one 128-bit load, 17 128-bit streaming stores); the per-byte flags of every loaded
+// word are derived once and shared by its four 4-site words; class counts are accumulated as per-byte
+// sums over the thread's words and reduced CTA-wide through shared memory, so row counts are written
+// with plain stores (no memset, no global atomics) and class totals are finished by the last CTA of
+// each replica (ticket), all in this one launch.
+struct ZD { uint32_t zero, div; };
+__host__ __device__ __forceinline__ ZD zd_flags(uint32_t w) {
+    const uint32_t e0 = w & ONES, e1 = (w >> 1) & ONES, hi = ((w >> 2) | (w >> 3)) & ONES;
+    ZD f; f.zero = (e0 | e1 | hi) ^ ONES; f.div = e0 & e1 & ~hi; return f;
+}
+struct ByteAcc { uint32_t zero, div, mono, anch, nat, met, cmb, bth, tref; };
+
+// slot words of one 4-site word; flags of the neighbouring words are passed in
+__host__ __device__ __forceinline__ void sweep_word16(uint32_t cw, const ZD &cp, const ZD &c, const ZD &cn,
+                                                      const ZD &m0, const ZD &m1, const ZD &pm, const ZD &p0,
+                                                      uint32_t qm_div, uint32_t q0_div, uint32_t out[NS], ByteAcc &acc)
+{
+    const uint32_t e0 = cw & ONES, e1 = (cw >> 1) & ONES, e2 = (cw >> 2) & ONES, e3 = (cw >> 3) & ONES;
+    const uint32_t mono = (e0 ^ e1) & ~(e2 | e3);
+    const uint32_t up_a = e2 & ~(e0 | e1 | e3), dn_a = e0 & e1 & e2 & ~e3;
+    const uint32_t s1 = mono & e0, s2 = mono & e1;
+    out[0] = code(c.zero, C_CREATE_DIV * ONES);
+    out[1] = code(c.div, C_FILL_DIV * ONES);
+    out[2] = code(c.zero | s2, (C_CMONO_FROM_DOUBLE * ONES) + s2);
+    out[3] = code(c.zero | s1, (C_CMONO_FROM_DOUBLE * ONES) + s1);
+    out[4] = code(c.div | s1, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    out[5] = code(c.div | s2, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    out[6] = code(mono, C_FLIP * ONES);
+    acc.zero += c.zero; acc.div += c.div; acc.mono += mono; acc.anch += up_a + dn_a;
+    uint32_t P[6], D[6];
+    P[0] = m0.zero;                              D[0] = m0.div;
+    P[1] = shl_sites(cp.zero, c.zero, 1);        D[1] = shl_sites(cp.div, c.div, 1);
+    P[2] = shl_sites(pm.zero, p0.zero, 1);       D[2] = shl_sites(pm.div, p0.div, 1);
+    P[3] = p0.zero;                              D[3] = p0.div;
+    P[4] = shr_sites(c.zero, cn.zero, 1);        D[4] = shr_sites(c.div, cn.div, 1);
+    P[5] = shr_sites(m0.zero, m1.zero, 1);       D[5] = shr_sites(m0.div, m1.div, 1);
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int i = kring(k);
+        const uint32_t near = (i & 1) ? D[(i + 5) % 6] : D[(i + 1) % 6];
+        const uint32_t far = (i & 1) ? D[(i + 1) % 6] : D[(i + 5) % 6];
+        const uint32_t present = c.div & P[i];
+        out[7 + k] = code(present, (C_MOVE_DIV * ONES) + near + (far << 1));
+        const uint32_t pn = present & near, pf = present & far, pnf = pn & far;
+        acc.bth += pnf; acc.met += pn ^ pnf; acc.cmb += pf ^ pnf; acc.nat += present & ~(near | far);
+    }
+    const uint32_t both = c.div & q0_div;
+    const uint32_t up = both & shr_sites(c.div, cn.div, 2), dn = both & shl_sites(qm_div, q0_div, 2);
+    out[13] = code(up, C_CREATE_TREF * ONES);
+    out[14] = code(dn, C_CREATE_TREF * ONES);
+    out[15] = code(up_a, C_DESTROY_TREF * ONES);
+    out[16] = code(dn_a, C_DESTROY_TREF * ONES);
+    acc.tref += up + dn;
+}
+
+struct Sweep16Params {
+    int d0, d1, n, n_replicas;
+    const uint8_t *status;             // [R][n]
+    uint8_t *slots;                    // [R][17][n] or nullptr
+    uint32_t *rowcnt;                  // [R][d0][16]
+    unsigned long long *acc;           // [R][16] running class totals, zero between launches
+    unsigned int *ticket;              // [R] CTAs finished, zero between launches
+    unsigned long long *counts;        // [R][13] class totals (output)
+    int ctas_per_replica;
+};
+
+__global__ void __launch_bounds__(256) kmc_sweep16_kernel(const Sweep16Params p)
+{
+    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
+    __shared__ unsigned int is_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
+    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
+    const int rows_in_cta = 256 / cpr;
+    const long long g = (long long)blockIdx.x * 256 + tid;
+    const int rep = (int)(g / cpl);
+    const int cl = (int)(g - (long long)rep * cpl);
+    const int a = cl / cpr, ci = cl - a * cpr;
+    const int row_local = tid / cpr;
+    for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+    __syncthreads();
+
+    const int d0 = p.d0;
+    const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+    const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+    const uint8_t *S = p.status + (size_t)rep * p.n;
+    const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+    const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+    const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+    const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
+    const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
+    const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
+    const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+    const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+    const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
+    const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
+
+    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
+    ZD cf[6], mf[5], pf[5];
+    uint32_t qd[5];
+    cf[0] = zd_flags(c_prev); cf[5] = zd_flags(c_next);
+    cf[1] = zd_flags(c4.x); cf[2] = zd_flags(c4.y); cf[3] = zd_flags(c4.z); cf[4] = zd_flags(c4.w);
+    mf[0] = zd_flags(m4.x); mf[1] = zd_flags(m4.y); mf[2] = zd_flags(m4.z); mf[3] = zd_flags(m4.w); mf[4] = zd_flags(m_next);
+    pf[0] = zd_flags(p_prev); pf[1] = zd_flags(p4.x); pf[2] = zd_flags(p4.y); pf[3] = zd_flags(p4.z); pf[4] = zd_flags(p4.w);
+    qd[0] = zd_flags(q_prev).div; qd[1] = zd_flags(q4.x).div; qd[2] = zd_flags(q4.y).div;
+    qd[3] = zd_flags(q4.z).div; qd[4] = zd_flags(q4.w).div;
+
+    ByteAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t o[4][NS];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        sweep_word16(cw[j], cf[j], cf[j + 1], cf[j + 2], mf[j], mf[j + 1], pf[j], pf[j + 1], qd[j], qd[j + 1], o[j], acc);
+    if (p.slots) {
+        uint4 *O = reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl;
+#pragma unroll
+        for (int j = 0; j < NS; j++) __stcs(O + (size_t)j * cpl, make_uint4(o[0][j], o[1][j], o[2][j], o[3][j]));
+    }
+    // K2: this thread's 13 class counts as 16-bit pairs, pooled per row
+    uint32_t pk[7];
+    {
+        const uint32_t z = hsum(acc.zero), dv = hsum(acc.div), mo = hsum(acc.mono);
+        pk[0] = z | (dv << 16);                                   // classes 0, 1
+        pk[1] = hsum(acc.nat) | (hsum(acc.met) << 16);            // 2, 3
+        pk[2] = hsum(acc.cmb) | (hsum(acc.bth) << 16);            // 4, 5
+        pk[3] = hsum(acc.tref) | (hsum(acc.anch) << 16);          // 6, 7
+        pk[4] = (2 * z) | (mo << 16);                             // 8, 9
+        pk[5] = mo | ((2 * dv) << 16);                            // 10, 11
+        pk[6] = mo;                                               // 12
+    }
+    const uint32_t mask = cpr >= 32 ? 0xFFFFFFFFu : __match_any_sync(0xFFFFFFFFu, row_local);
+#pragma unroll
+    for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+    if ((__ffs(mask) - 1) == lane) {
+        uint32_t *R = rows_sm + row_local * RCG_STRIDE;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
+            if (lo) atomicAdd(R + 2 * j, lo);
+            if (hi) atomicAdd(R + 2 * j + 1, hi);
+        }
+    }
+    __syncthreads();
+    // rows are complete inside this CTA: plain coalesced stores
+    {
+        const int first_row = a - row_local;
+        uint32_t *G = p.rowcnt + ((size_t)rep * d0 + first_row) * RCG_STRIDE;
+        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
+    }
+    // class totals: CTA partial sums -> running totals; the last CTA of the replica publishes them
+    if (tid < NC) {
+        unsigned long long s = 0;
+        for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
+        if (p.ctas_per_replica == 1) p.counts[(size_t)rep * NC + tid] = s;
+        else if (s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+    }
+    if (p.ctas_per_replica > 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+            if (tid == 0) p.ticket[rep] = 0u;
+        }
+    }
+}
+
 // Generic path (any d1 >= 5): one thread per site, scalar evaluation.
 __global__ void __launch_bounds__(256) kmc_sweep_kernel_generic(const SweepParams p)
 {

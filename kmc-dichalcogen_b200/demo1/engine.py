@@ -156,3 +156,7 @@ class Engine:
 
     def set_warps_per_block(self, warps):
         nat.check(self._lib.kmc_set_warps_per_block(self._h, int(warps)))
+
+    def set_replica_kernel(self, variant):
+        """0 auto, 1 byte-lattice kernel, 2 bit-sliced kernel (rows of <= 64 sites)."""
+        nat.check(self._lib.kmc_set_replica_kernel(self._h, int(variant)))

@@ -1,0 +1,34 @@
+"""Small profiling target for ncu: 3 full sweeps of a 4096x4096 lattice and 3 launches of the fused
+replica kernel (16384 replicas x 64x64, `--events` events each).  Run plain first, then under ncu."""
+import argparse
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "kmc-dichalcogen_b200"))
+import bench  # noqa: E402
+from demo1.engine import Engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--events", type=int, default=500)
+ap.add_argument("--replicas", type=int, default=16384)
+ap.add_argument("--what", default="both", choices=["both", "sweep", "replica"])
+args = ap.parse_args()
+rates, order = bench.wse2_rates(), bench.WSE2_ORDER
+if args.what in ("both", "sweep"):
+    sw = Engine(bench.SWEEP_DIM, rates, order, n_replicas=1)
+    sw.upload_state(bench.iid_lattice(bench.SWEEP_DIM, bench.SEED))
+    for _ in range(3):
+        sw.sweep()
+    sw.sync()
+    print("sweep counts", sw.counts()[0].tolist())
+    sw.close()
+if args.what in ("both", "replica"):
+    eng = Engine(bench.DIM, rates, order, n_replicas=args.replicas)
+    eng.upload_state(bench.synthetic_lattices(args.replicas, 0))
+    for _ in range(3):
+        eng.run(args.events, bench.SEED)
+    eng.sync()
+    print("replica hist", eng.histogram().tolist())
+    eng.close()

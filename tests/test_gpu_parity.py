@@ -106,6 +106,27 @@ def test_replicas_match_oracle(dim, rates, order, nrep, nsteps):
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("dim", [(64, 64), (33, 47), (5, 5), (9, 64), (130, 7), (16, 20)])
+def test_both_replica_kernels_match_oracle(dim, variant):
+    """The byte-lattice kernel (1) and the bit-sliced kernel (2) on the same lattices."""
+    nrep, nsteps, seed = 3, 6000, 99
+    st0 = np.stack([evolved_state(dim, 20 + r, nsteps=300) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(st0)
+    ev = eng.run(nsteps, seed, log_mode=nat.LOG_FULL, validate=True)
+    final = eng.download_state()
+    for r in range(nrep):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
+        _, want = o.run_philox(seed, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "variant %d replica %d" % (variant, r))
+        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (final[r] == o.status()).all()
+    eng.close()
+
+
 def test_stats_only_mode_equals_logged_mode():
     dim, nrep, nsteps = (64, 64), 40, 3000
     st0 = np.stack([exact_state(dim, 0.05, 0.05, r) for r in range(nrep)])
@@ -122,7 +143,8 @@ def test_stats_only_mode_equals_logged_mode():
     b.close()
 
 
-@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (256, 256), (7, 130)])
+@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (256, 256), (7, 130), (16, 16),
+                                 (128, 32), (512, 4096), (8, 8192)])
 def test_sweep_matches_oracle(dim):
     sts = [evolved_state(dim, 3) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3), iid_state(dim, 4)]
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
