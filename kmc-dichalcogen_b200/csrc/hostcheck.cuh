@@ -45,20 +45,24 @@ extern "C" int kmc_hostcheck_sweep_words16(const uint8_t *status, int d0, int d1
             const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
             const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
             const uint32_t *r0 = S + a * wpr, *rm = S + am * wpr, *rp = S + ap * wpr, *rq = S + ap2 * wpr;
-            ZD cf[6], mf[5], pf[5];
-            uint32_t qd[5], cw[4];
-            cf[0] = zd_flags(r0[4 * cim + 3]); cf[5] = zd_flags(r0[4 * cin]);
-            pf[0] = zd_flags(rp[4 * cim + 3]); qd[0] = zd_flags(rq[4 * cim + 3]).div;
-            mf[4] = zd_flags(rm[4 * cin]);
+            Chunk16 k;
+            k.c[0] = zd_flags(r0[4 * cim + 3]); k.c[5] = zd_flags(r0[4 * cin]);
+            k.p[0] = zd_flags(rp[4 * cim + 3]); k.q[0] = zd_flags(rq[4 * cim + 3]).div;
+            k.m[4] = zd_flags(rm[4 * cin]);
             for (int j = 0; j < 4; j++) {
-                cw[j] = r0[4 * ci + j];
-                cf[1 + j] = zd_flags(cw[j]); mf[j] = zd_flags(rm[4 * ci + j]);
-                pf[1 + j] = zd_flags(rp[4 * ci + j]); qd[1 + j] = zd_flags(rq[4 * ci + j]).div;
+                k.cw[j] = r0[4 * ci + j];
+                k.c[1 + j] = zd_flags(k.cw[j]); k.m[j] = zd_flags(rm[4 * ci + j]);
+                k.p[1 + j] = zd_flags(rp[4 * ci + j]); k.q[1 + j] = zd_flags(rq[4 * ci + j]).div;
             }
             ByteAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0};
             for (int j = 0; j < 4; j++) {
-                uint32_t out[NS];
-                sweep_word16(cw[j], cf[j], cf[j + 1], cf[j + 2], mf[j], mf[j + 1], pf[j], pf[j + 1], qd[j], qd[j + 1], out, acc);
+                uint32_t out[NS], o[9];
+                own_planes(k, j, o, acc);
+                for (int q = 0; q < 7; q++) out[q] = o[q];
+                out[15] = o[7]; out[16] = o[8];
+                out[7] = move_plane<0>(k, j, acc); out[8] = move_plane<1>(k, j, acc); out[9] = move_plane<2>(k, j, acc);
+                out[10] = move_plane<3>(k, j, acc); out[11] = move_plane<4>(k, j, acc); out[12] = move_plane<5>(k, j, acc);
+                trefoil_planes(k, j, out[13], out[14], acc);
                 for (int q = 0; q < NS; q++) memcpy(slots + (size_t)q * n + (size_t)a * d1 + 16 * ci + 4 * j, &out[q], 4);
             }
             const uint32_t z = hsum(acc.zero), dv = hsum(acc.div), mo = hsum(acc.mono);

@@ -26,7 +26,13 @@
 namespace kmc {
 
 typedef unsigned long long u64;
-enum { PL_Z = 0, PL_D = 1, PL_M1 = 2, PL_M2 = 3, PL_A4 = 4, PL_A7 = 5, N_PLANES = 6 };
+// Plane types (what a status byte maps to) and the planes held in shared memory.  Z and D are kept
+// three times: as is, and pre-rotated by one site either way (ZP: bit b = Z bit b+1, ZM: bit b = Z bit
+// b-1), so that "the neighbour at column offset +-1 is pristine / a divacancy" is a plain load of the
+// right plane instead of a per-lane variable 64-bit rotate.
+enum { T_Z = 0, T_D = 1, T_M1 = 2, T_M2 = 3, T_A4 = 4, T_A7 = 5, N_TYPES = 6 };
+enum { PL_Z = 0, PL_ZP = 1, PL_ZM = 2, PL_D = 3, PL_DP = 4, PL_DM = 5, PL_M1 = 6, PL_M2 = 7, PL_A4 = 8, PL_A7 = 9,
+       N_PLANES = 10 };
 
 __host__ __device__ inline size_t replica_bp_warp_bytes(int d0) {
     const size_t d0e = ((size_t)d0 + 1) & ~(size_t)1;
@@ -36,16 +42,21 @@ __host__ __device__ inline size_t replica_bp_warp_bytes(int d0) {
 }
 
 // neighbors_and_mutuals (reference state.py:443-459), direction k: (da, db) of nbr / near / far
-constexpr u64 NBR_DA = pack_nibbles({-1, 0, 1, 0, -1, 1}),  NBR_DB = pack_nibbles({1, -1, 0, 1, 0, -1});
-constexpr u64 NEAR_DA = pack_nibbles({0, -1, 1, -1, 0, 1}), NEAR_DB = pack_nibbles({1, 0, -1, 1, -1, 0});
-constexpr u64 FAR_DA = pack_nibbles({-1, 1, 0, 1, -1, 0}),  FAR_DB = pack_nibbles({0, -1, 1, 0, 1, -1});
-__host__ __device__ __forceinline__ int nib(u64 t, int k) { return (int)((t >> (4 * k)) & 0xF) - 2; }
+constexpr uint32_t NBR_DA = (uint32_t)pack_nibbles({-1, 0, 1, 0, -1, 1}),  NBR_DB = (uint32_t)pack_nibbles({1, -1, 0, 1, 0, -1});
+constexpr uint32_t NEAR_DA = (uint32_t)pack_nibbles({0, -1, 1, -1, 0, 1}), NEAR_DB = (uint32_t)pack_nibbles({1, 0, -1, 1, -1, 0});
+constexpr uint32_t FAR_DA = (uint32_t)pack_nibbles({-1, 1, 0, 1, -1, 0}),  FAR_DB = (uint32_t)pack_nibbles({0, -1, 1, 0, 1, -1});
+__host__ __device__ __forceinline__ int nib(uint32_t t, int k) { return (int)((t >> (4 * k)) & 0xF) - 2; }
 
-// status -> plane index + 1 (0 = no plane: non-anchor trefoil member)
-//   s:      0     1      2      3     4      5  6  7      8  9
-//   plane:  Z(1)  M1(3)  M2(4)  D(2)  A4(5)  0  0  A7(6)  0  0
-constexpr u64 STATUS_PLANE = 0x0060052431ull;
-__host__ __device__ __forceinline__ int status_plane(int s) { return (int)((STATUS_PLANE >> (4 * s)) & 0xF) - 1; }
+// status -> plane type + 1 (0 = none: non-anchor trefoil member)
+//   s:     0     1      2      3     4      5  6  7      8  9
+//   type:  Z(1)  M1(3)  M2(4)  D(2)  A4(5)  0  0  A7(6)  0  0
+constexpr u64 STATUS_TYPE = 0x0060052431ull;
+__host__ __device__ __forceinline__ int status_plane(int s) { return (int)((STATUS_TYPE >> (4 * s)) & 0xF) - 1; }
+// plane q (0..9) -> its type, and the column offset at which a site's bit lives in it
+//   q:      Z  ZP  ZM  D  DP  DM  M1 M2 A4 A7
+//   type:   0  0   0   1  1   1   2  3  4  5
+//   cshift: 0  -1  +1  0  -1  +1  0  0  0  0     (stored + 1)
+constexpr u64 PLANE_TYPE = 0x5432111000ull, PLANE_CSHIFT = 0x1111201201ull;
 
 template <int TD1>
 struct RowBits {
@@ -61,25 +72,33 @@ struct RowBits {
     __device__ __forceinline__ static u64 low(int n) { return n >= 64 ? ~0ull : ((1ull << n) - 1); }
 };
 
-struct DirConst { int da_n, s_n, da_e, s_e, da_f, s_f; };
-template <int TD1>
-__device__ __forceinline__ DirConst dir_const(int k, const RowBits<TD1> &rb) {
+__device__ __forceinline__ int wrap1(int x, int d) { return x < 0 ? x + d : (x >= d ? x - d : x); }
+// periodic index for |offset| <= 3; a compile-time power-of-two extent wraps with one AND
+template <int TD> __device__ __forceinline__ int wrapT(int x, int d) {
+    if (TD > 0 && (TD & (TD - 1)) == 0) return x & (TD - 1);
+    return wrap1(x, d);
+}
+
+// per-direction constants: element offsets (plane * d0) of the pre-rotated plane to read for the
+// neighbour / near / far site, and their row offsets
+struct DirConst { int off_n, da_n, off_e, da_e, off_f, da_f; };
+__device__ __forceinline__ DirConst dir_const(int k, int d0) {
     DirConst c;
-    c.da_n = nib(NBR_DA, k);  c.s_n = rb.amount(nib(NBR_DB, k));
-    c.da_e = nib(NEAR_DA, k); c.s_e = rb.amount(nib(NEAR_DB, k));
-    c.da_f = nib(FAR_DA, k);  c.s_f = rb.amount(nib(FAR_DB, k));
+    // column offset db -> plane: db = 0 -> base, +1 -> P (bit b = bit b+1), -1 -> M
+    const int dbn = nib(NBR_DB, k), dbe = nib(NEAR_DB, k), dbf = nib(FAR_DB, k);
+    c.off_n = (PL_Z + (dbn > 0 ? 1 : dbn < 0 ? 2 : 0)) * d0;  c.da_n = nib(NBR_DA, k);
+    c.off_e = (PL_D + (dbe > 0 ? 1 : dbe < 0 ? 2 : 0)) * d0;  c.da_e = nib(NEAR_DA, k);
+    c.off_f = (PL_D + (dbf > 0 ? 1 : dbf < 0 ? 2 : 0)) * d0;  c.da_f = nib(FAR_DA, k);
     return c;
 }
-__device__ __forceinline__ int wrap1(int x, int d) { return x < 0 ? x + d : (x >= d ? x - d : x); }
 
 // MoveDivacancy of row `a`, direction constants `c`: present / near / far masks over the row's sites
-template <int TD1>
-__device__ __forceinline__ void dir_masks(const u64 *PL, int d0, int a, const DirConst &c, const RowBits<TD1> &rb,
+template <int TD0>
+__device__ __forceinline__ void dir_masks(const u64 *PL, int d0, int a, const DirConst &c,
                                           u64 &present, u64 &near, u64 &far) {
-    const u64 Da = PL[PL_D * d0 + a];
-    present = Da & rb.rotl(PL[PL_Z * d0 + wrap1(a + c.da_n, d0)], c.s_n);
-    near = rb.rotl(PL[PL_D * d0 + wrap1(a + c.da_e, d0)], c.s_e);
-    far = rb.rotl(PL[PL_D * d0 + wrap1(a + c.da_f, d0)], c.s_f);
+    present = PL[PL_D * d0 + a] & PL[c.off_n + wrapT<TD0>(a + c.da_n, d0)];
+    near = PL[c.off_e + wrapT<TD0>(a + c.da_e, d0)];
+    far = PL[c.off_f + wrapT<TD0>(a + c.da_f, d0)];
 }
 // counts of the four kinds (natural, missing-metal, missing-comb, missing-both), 16 bits each
 __device__ __forceinline__ void kind_counts(u64 present, u64 near, u64 far, uint32_t &pk01, uint32_t &pk23) {
@@ -93,17 +112,17 @@ __device__ __forceinline__ u64 kind_select(u64 present, u64 near, u64 far, int q
     return present & ((q & 1) ? near : ~near) & ((q & 2) ? far : ~far);
 }
 // CreateTrefoil anchored in row `a`: Up / Down masks
-template <int TD1>
+template <int TD0, int TD1>
 __device__ __forceinline__ void trefoil_masks(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, u64 &up, u64 &dn) {
     const u64 Da = PL[PL_D * d0 + a];
-    const u64 Db = PL[PL_D * d0 + wrap1(a + 2, d0)];
+    const u64 Db = PL[PL_D * d0 + wrapT<TD0>(a + 2, d0)];
     const u64 both = Da & Db;
     up = both & rb.rotl(Da, rb.amount(2));
     dn = both & rb.rotl(Db, rb.amount(-2));
 }
 
 // all 13 class counts of row `a` (full enumeration of one row; used at launch start and by validate)
-template <int TD1>
+template <int TD0, int TD1>
 __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
     const uint32_t pz = __popcll(PL[PL_Z * d0 + a]), pd = __popcll(PL[PL_D * d0 + a]);
     const uint32_t pm = __popcll(PL[PL_M1 * d0 + a] | PL[PL_M2 * d0 + a]);
@@ -113,14 +132,14 @@ __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, cons
     out[C_FMONO_FROM_EMPTY] = 2 * pd; out[C_FLIP] = pm;
     uint32_t k01 = 0, k23 = 0;
     for (int k = 0; k < 6; k++) {
-        const DirConst c = dir_const(k, rb);
-        u64 p, n, f; dir_masks(PL, d0, a, c, rb, p, n, f);
+        const DirConst c = dir_const(k, d0);
+        u64 p, n, f; dir_masks<TD0>(PL, d0, a, c, p, n, f);
         uint32_t a01, a23; kind_counts(p, n, f, a01, a23);
         k01 += a01; k23 += a23;
     }
     out[C_MOVE_DIV] = k01 & 0xFFFF; out[C_MOVE_DIV + 1] = k01 >> 16;
     out[C_MOVE_DIV + 2] = k23 & 0xFFFF; out[C_MOVE_DIV + 3] = k23 >> 16;
-    u64 up, dn; trefoil_masks(PL, d0, a, rb, up, dn);
+    u64 up, dn; trefoil_masks<TD0>(PL, d0, a, rb, up, dn);
     out[C_CREATE_TREF] = __popcll(up) + __popcll(dn);
 }
 
@@ -132,6 +151,12 @@ __device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane) {
     const int L = __ffs(ball) - 1;
     const uint32_t below = __popcll(m & RowBits<64>::low(2 * L));
     return 2 * L + (int)!(((m >> (2 * L)) & 1ull) && idx == below);
+}
+
+// position of the (n)-th set bit (0-based) of a small mask; n is warp-uniform and tiny
+__device__ __forceinline__ int nth_bit_small(uint32_t m, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) m &= m - 1;
+    return __ffs(m) - 1;
 }
 
 template <int TD0, int TD1>
@@ -155,7 +180,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
     uint8_t *gst = p.status + (size_t)rep * n;
     for (int a = lane; a < d0; a += 32) {
-        u64 w[N_PLANES] = {0, 0, 0, 0, 0, 0};
+        u64 w[N_TYPES] = {0, 0, 0, 0, 0, 0};
         if ((d1 & 3) == 0) {
             const uint32_t *g32 = reinterpret_cast<const uint32_t *>(gst + a * d1);
             for (int b4 = 0; b4 < (d1 >> 2); b4++) {
@@ -164,24 +189,28 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
                 for (int i = 0; i < 4; i++) {
                     const int pl = status_plane((v >> (8 * i)) & 0xF);
 #pragma unroll
-                    for (int q = 0; q < N_PLANES; q++) w[q] |= (u64)(pl == q) << (4 * b4 + i);
+                    for (int q = 0; q < N_TYPES; q++) w[q] |= (u64)(pl == q) << (4 * b4 + i);
                 }
             }
         } else {
             for (int b = 0; b < d1; b++) {
                 const int pl = status_plane(gst[a * d1 + b]);
 #pragma unroll
-                for (int q = 0; q < N_PLANES; q++) w[q] |= (u64)(pl == q) << b;
+                for (int q = 0; q < N_TYPES; q++) w[q] |= (u64)(pl == q) << b;
             }
         }
-#pragma unroll
-        for (int q = 0; q < N_PLANES; q++) PL[q * d0 + a] = w[q];
+        PL[PL_Z * d0 + a] = w[T_Z];   PL[PL_ZP * d0 + a] = rb.rotl(w[T_Z], rb.amount(1));
+        PL[PL_ZM * d0 + a] = rb.rotl(w[T_Z], rb.amount(-1));
+        PL[PL_D * d0 + a] = w[T_D];   PL[PL_DP * d0 + a] = rb.rotl(w[T_D], rb.amount(1));
+        PL[PL_DM * d0 + a] = rb.rotl(w[T_D], rb.amount(-1));
+        PL[PL_M1 * d0 + a] = w[T_M1]; PL[PL_M2 * d0 + a] = w[T_M2];
+        PL[PL_A4 * d0 + a] = w[T_A4]; PL[PL_A7 * d0 + a] = w[T_A7];
     }
     __syncwarp();
     // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
     for (int a = lane; a < d0e; a += 32) {
         uint32_t cnt[NC];
-        if (a < d0) bp_row_counts(PL, d0, a, rb, cnt);
+        if (a < d0) bp_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
         for (int c = 0; c < NC; c++) rc16[c * d0e + a] = a < d0 ? (uint16_t)cnt[c] : (uint16_t)0;
     }
@@ -201,7 +230,10 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     bool need_sort = true;
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
     const int my_j = lane / 6, my_k = lane % 6;
-    const DirConst my_dir = dir_const(my_k, rb);
+    const DirConst my_dir = dir_const(my_k, d0);
+    // plane maintenance role: lane q < 10 keeps plane q; a site's bit sits at column col + my_cshift
+    const int my_ptype = lane < N_PLANES ? (int)((PLANE_TYPE >> (4 * lane)) & 0xF) : -1;
+    const int my_cshift = lane < N_PLANES ? (int)((PLANE_CSHIFT >> (4 * lane)) & 0xF) - 1 : 0;
 
     const unsigned long long step_base = p.steps_done[rep];
     double mu1 = 0.0, mu2 = 0.0;
@@ -279,7 +311,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
             // lanes 0..5 derive their direction's kind mask for this row, everyone gets all six
             u64 pr, ne, fa;
-            dir_masks(PL, d0, row, my_dir, rb, pr, ne, fa);
+            dir_masks<TD0>(PL, d0, row, my_dir, pr, ne, fa);
             const u64 mine = lane < 6 ? kind_select(pr, ne, fa, csel - C_MOVE_DIV) : 0ull;
             const u64 lowm = RowBits<64>::low(2 * lane + 2);
             uint32_t c = 0;
@@ -296,11 +328,11 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             uint32_t km = m0;
             col = 2 * L;
             if (rem >= n0) { rem -= n0; km = m1; col++; }
-            slot = 7 + (__fns(km, 0, (int)rem + 1) & 7);
+            slot = 7 + nth_bit_small(km, rem);
             s0 = S_DIVAC;
         } else if (csel == C_CREATE_TREF) {
             u64 up, dn;
-            trefoil_masks(PL, d0, row, rb, up, dn);
+            trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
             const u64 lowm = RowBits<64>::low(2 * lane + 2);
             const uint32_t c = __popcll(up & lowm) + __popcll(dn & lowm);
             const uint32_t ball = __ballot_sync(FULL, c > r);
@@ -363,24 +395,24 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             os1 = create ? S_DIVAC : S_TREF + 3 * o + 1;
             os2 = create ? S_DIVAC : S_TREF + 3 * o + 2;
         }
-        // bit planes: lane q < 6 maintains plane q (program order handles nodes sharing a row)
+        // bit planes: lane q < 10 maintains plane q (program order handles nodes sharing a row)
         if (lane < N_PLANES) {
             {
                 u64 wv = PL[lane * d0 + row];
-                const u64 bit = 1ull << col;
-                wv = (status_plane(mv.ns0) == lane) ? (wv | bit) : (wv & ~bit);
+                const u64 bit = 1ull << wrapT<TD1>(col + my_cshift, d1);
+                wv = (status_plane(mv.ns0) == my_ptype) ? (wv | bit) : (wv & ~bit);
                 PL[lane * d0 + row] = wv;
             }
             if (na > 1) {
                 u64 wv = PL[lane * d0 + mv.a1];
-                const u64 bit = 1ull << mv.b1;
-                wv = (status_plane(mv.ns1) == lane) ? (wv | bit) : (wv & ~bit);
+                const u64 bit = 1ull << wrapT<TD1>(mv.b1 + my_cshift, d1);
+                wv = (status_plane(mv.ns1) == my_ptype) ? (wv | bit) : (wv & ~bit);
                 PL[lane * d0 + mv.a1] = wv;
             }
             if (na > 2) {
                 u64 wv = PL[lane * d0 + mv.a2];
-                const u64 bit = 1ull << mv.b2;
-                wv = (status_plane(mv.ns2) == lane) ? (wv | bit) : (wv & ~bit);
+                const u64 bit = 1ull << wrapT<TD1>(mv.b2 + my_cshift, d1);
+                wv = (status_plane(mv.ns2) == my_ptype) ? (wv | bit) : (wv & ~bit);
                 PL[lane * d0 + mv.a2] = wv;
             }
         }
@@ -407,14 +439,14 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         // touched rows relative to `row`: 0 (always), da of the target (moves), +2 (trefoils)
         int lo = -1, hi = 1;
         if (slot >= 13) hi = 3;
-        else if (slot >= 7) { const int da = nib(RING_DA, kring(slot - 7)); lo += da < 0 ? da : 0; hi += da > 0 ? da : 0; }
+        else if (slot >= 7) { lo += mv.da1 < 0 ? mv.da1 : 0; hi += mv.da1 > 0 ? mv.da1 : 0; }
         {
             const bool act = my_j <= hi - lo;
-            const int ra = wrap1(wrap1(row + lo + my_j, d0), d0);
+            const int ra = wrapT<TD0>(row + lo + my_j, d0);
             uint32_t pk01 = 0, pk23 = 0;
             if (act) {
                 u64 pr, ne, fa;
-                dir_masks(PL, d0, ra, my_dir, rb, pr, ne, fa);
+                dir_masks<TD0>(PL, d0, ra, my_dir, pr, ne, fa);
                 kind_counts(pr, ne, fa, pk01, pk23);
             }
             pk01 += __shfl_down_sync(FULL, pk01, 3);
@@ -444,9 +476,9 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             const int ng = d0 < 6 ? d0 : 6;
             int d = 0;
             if (lane < ng) {
-                const int ra = wrap1(row + lane - 3, d0);
+                const int ra = wrapT<TD0>(row + lane - 3, d0);
                 u64 up, dn;
-                trefoil_masks(PL, d0, ra, rb, up, dn);
+                trefoil_masks<TD0>(PL, d0, ra, rb, up, dn);
                 const int nw = __popcll(up) + __popcll(dn);
                 uint16_t *q = rc16 + C_CREATE_TREF * d0e + ra;
                 d = nw - (int)q[0];
@@ -465,14 +497,18 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         bool bad = false;
         for (int a = lane; a < d0; a += 32) {
             uint32_t cnt[NC];
-            bp_row_counts(PL, d0, a, rb, cnt);
+            bp_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
             for (int c = 0; c < NC; c++) bad |= (rc16[c * d0e + a] != (uint16_t)cnt[c]);
-            // plane consistency: at most one plane bit per site
+            // plane consistency: at most one type bit per site; rotated copies agree with their base
+            const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a];
+            const u64 types[N_TYPES] = {z, dv, PL[PL_M1 * d0 + a], PL[PL_M2 * d0 + a], PL[PL_A4 * d0 + a], PL[PL_A7 * d0 + a]};
             u64 seen = 0, dup = 0;
 #pragma unroll
-            for (int q = 0; q < N_PLANES; q++) { const u64 x = PL[q * d0 + a]; dup |= seen & x; seen |= x; }
+            for (int q = 0; q < N_TYPES; q++) { dup |= seen & types[q]; seen |= types[q]; }
             bad |= dup != 0;
+            bad |= PL[PL_ZP * d0 + a] != rb.rotl(z, rb.amount(1)) || PL[PL_ZM * d0 + a] != rb.rotl(z, rb.amount(-1));
+            bad |= PL[PL_DP * d0 + a] != rb.rotl(dv, rb.amount(1)) || PL[PL_DM * d0 + a] != rb.rotl(dv, rb.amount(-1));
         }
         if (lane < NC) {
             int fresh = 0;

@@ -54,8 +54,8 @@ constexpr unsigned long long pack_nibbles(std::initializer_list<int> v) {
     return r;
 }
 // ring neighbours R0..R5 (state.py:392-394)
-constexpr unsigned long long RING_DA = pack_nibbles({-1, 0, 1, 1, 0, -1});
-constexpr unsigned long long RING_DB = pack_nibbles({0, -1, -1, 0, 1, 1});
+constexpr uint32_t RING_DA = (uint32_t)pack_nibbles({-1, 0, 1, 1, 0, -1});
+constexpr uint32_t RING_DB = (uint32_t)pack_nibbles({0, -1, -1, 0, 1, 1});
 // sites whose move counts can depend on a touched node p: p, its six neighbours (MoveDivacancy,
 // rules.py:115-117), and the anchors of the triangles containing p (p-(2,0), p-(0,2), p-(2,-2))
 constexpr unsigned long long REFRESH_DA = pack_nibbles({0, -1, 0, 1, 1, 0, -1, -2, 0, -2});
@@ -174,11 +174,11 @@ __device__ __forceinline__ uint32_t g1_const(int c) {
 
 // Rule.perform + nodes_affected_by (reference demo1/rules.py:62-65,79-82,96-101,143-148,178-183,
 // 204-214,279-283): the nodes a move touches and the status each one gets.
-struct MoveNodes { int na, a1, b1, a2, b2, ns0, ns1, ns2; };
+struct MoveNodes { int na, a1, b1, a2, b2, ns0, ns1, ns2, da1; };
 __device__ __forceinline__ MoveNodes move_nodes(int row, int col, int slot, int s0, int d0, int d1)
 {
     MoveNodes m;
-    m.na = 1; m.a1 = row; m.b1 = col; m.a2 = row; m.b2 = col; m.ns1 = 0; m.ns2 = 0;
+    m.na = 1; m.a1 = row; m.b1 = col; m.a2 = row; m.b2 = col; m.ns1 = 0; m.ns2 = 0; m.da1 = 0;
     if (slot < 7) {
         m.ns0 = slot == 0 ? S_DIVAC : slot == 1 ? S_PRISTINE : slot <= 3 ? (s0 | (slot - 1))
                 : slot <= 5 ? (s0 & ~(slot - 3)) : (s0 ^ 3);
@@ -188,7 +188,7 @@ __device__ __forceinline__ MoveNodes move_nodes(int row, int col, int slot, int 
         const int db = (int)((RING_DB >> (4 * ri)) & 0xF) - 2;
         m.a1 = wrap_inc(wrap_dec(row + da, d0), d0);
         m.b1 = wrap_inc(wrap_dec(col + db, d1), d1);
-        m.na = 2; m.ns0 = S_PRISTINE; m.ns1 = S_DIVAC;
+        m.na = 2; m.ns0 = S_PRISTINE; m.ns1 = S_DIVAC; m.da1 = da;
     } else {
         const int o = (slot - 13) & 1;
         const bool create = slot < 15;

@@ -37,10 +37,18 @@ __host__ __device__ __forceinline__ ByteFlags byte_flags(uint32_t w) {
 }
 // flags of the sites one / two to the right (+) or left (-) of each byte's site
 __host__ __device__ __forceinline__ uint32_t shr_sites(uint32_t cur, uint32_t next, int k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(cur, next, 8 * k);
+#else
     return k == 0 ? cur : (cur >> (8 * k)) | (next << (32 - 8 * k));
+#endif
 }
 __host__ __device__ __forceinline__ uint32_t shl_sites(uint32_t prev, uint32_t cur, int k) {
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(prev, cur, 8 * k);
+#else
     return k == 0 ? cur : (cur << (8 * k)) | (prev >> (32 - 8 * k));
+#endif
 }
 // code plane word: class id where flag set, 0xFF elsewhere
 __host__ __device__ __forceinline__ uint32_t code(uint32_t flag, uint32_t cls_bytes) {
@@ -184,11 +192,11 @@ __global__ void __launch_bounds__(256) kmc_sweep_kernel(const SweepParams p)
 
 // ---- 16 sites per thread ---------------------------------------------------------------------------
 // Fast path for d1 % 16 == 0 with CTAs aligned to rows and replicas.  One thread owns 16 consecutive
-// sites of a row (one 128-bit load, 17 128-bit streaming stores); the per-byte flags of every loaded
-// word are derived once and shared by its four 4-site words; class counts are accumulated as per-byte
-// sums over the thread's words and reduced CTA-wide through shared memory, so row counts are written
-// with plain stores (no memset, no global atomics) and class totals are finished by the last CTA of
-// each replica (ticket), all in this one launch.
+// sites of a row (one 128-bit load per neighbour row, 17 128-bit streaming stores).  The per-byte flags
+// of every loaded word are derived once; slot planes are emitted plane by plane (4 words -> one store)
+// so few registers stay live; class counts are per-byte sums over the thread's words, pooled per row
+// through shared memory, so row counts are written with plain stores (no memset, no global atomics)
+// and class totals are finished by the last CTA of each replica (ticket) -- all in this one launch.
 struct ZD { uint32_t zero, div; };
 __host__ __device__ __forceinline__ ZD zd_flags(uint32_t w) {
     const uint32_t e0 = w & ONES, e1 = (w >> 1) & ONES, hi = ((w >> 2) | (w >> 3)) & ONES;
@@ -196,47 +204,58 @@ __host__ __device__ __forceinline__ ZD zd_flags(uint32_t w) {
 }
 struct ByteAcc { uint32_t zero, div, mono, anch, nat, met, cmb, bth, tref; };
 
-// slot words of one 4-site word; flags of the neighbouring words are passed in
-__host__ __device__ __forceinline__ void sweep_word16(uint32_t cw, const ZD &cp, const ZD &c, const ZD &cn,
-                                                      const ZD &m0, const ZD &m1, const ZD &pm, const ZD &p0,
-                                                      uint32_t qm_div, uint32_t q0_div, uint32_t out[NS], ByteAcc &acc)
-{
+// Flags of one thread's 16 sites and their halo: own row c[0..5] = prev word, 4 own words, next word;
+// row a-1 m[0..4] = 4 words + next; row a+1 p[0..4] = prev + 4 words; row a+2 q[0..4] (divacancy only).
+struct Chunk16 { uint32_t cw[4]; ZD c[6], m[5], p[5]; uint32_t q[5]; };
+
+// pristine / divacancy flags of ring neighbour I (R0..R5) of the sites of word j
+template <int I> __host__ __device__ __forceinline__ ZD ring_flags(const Chunk16 &k, int j) {
+    ZD r;
+    if (I == 0) r = k.m[j];
+    else if (I == 1) { r.zero = shl_sites(k.c[j].zero, k.c[j + 1].zero, 1); r.div = shl_sites(k.c[j].div, k.c[j + 1].div, 1); }
+    else if (I == 2) { r.zero = shl_sites(k.p[j].zero, k.p[j + 1].zero, 1); r.div = shl_sites(k.p[j].div, k.p[j + 1].div, 1); }
+    else if (I == 3) r = k.p[j + 1];
+    else if (I == 4) { r.zero = shr_sites(k.c[j + 1].zero, k.c[j + 2].zero, 1); r.div = shr_sites(k.c[j + 1].div, k.c[j + 2].div, 1); }
+    else { r.zero = shr_sites(k.m[j].zero, k.m[j + 1].zero, 1); r.div = shr_sites(k.m[j].div, k.m[j + 1].div, 1); }
+    return r;
+}
+// slot plane 7+K of word j (MoveDivacancy direction K), accumulating the kind counts
+template <int K> __host__ __device__ __forceinline__ uint32_t move_plane(const Chunk16 &k, int j, ByteAcc &acc) {
+    constexpr int I = (0x204315 >> (4 * K)) & 7;           // kring(K)
+    constexpr int IN = (I & 1) ? (I + 5) % 6 : (I + 1) % 6, IF = (I & 1) ? (I + 1) % 6 : (I + 5) % 6;
+    const uint32_t present = k.c[j + 1].div & ring_flags<I>(k, j).zero;
+    const uint32_t near = ring_flags<IN>(k, j).div, far = ring_flags<IF>(k, j).div;
+    const uint32_t pn = present & near, pf = present & far, pnf = pn & far;
+    acc.bth += pnf; acc.met += pn ^ pnf; acc.cmb += pf ^ pnf; acc.nat += present & ~(near | far);
+    return code(present, (C_MOVE_DIV * ONES) + near + (far << 1));
+}
+// own-status planes 0..6, 15, 16 of word j
+__host__ __device__ __forceinline__ void own_planes(const Chunk16 &k, int j, uint32_t o[9], ByteAcc &acc) {
+    const uint32_t cw = k.cw[j];
+    const ZD c = k.c[j + 1];
     const uint32_t e0 = cw & ONES, e1 = (cw >> 1) & ONES, e2 = (cw >> 2) & ONES, e3 = (cw >> 3) & ONES;
     const uint32_t mono = (e0 ^ e1) & ~(e2 | e3);
     const uint32_t up_a = e2 & ~(e0 | e1 | e3), dn_a = e0 & e1 & e2 & ~e3;
     const uint32_t s1 = mono & e0, s2 = mono & e1;
-    out[0] = code(c.zero, C_CREATE_DIV * ONES);
-    out[1] = code(c.div, C_FILL_DIV * ONES);
-    out[2] = code(c.zero | s2, (C_CMONO_FROM_DOUBLE * ONES) + s2);
-    out[3] = code(c.zero | s1, (C_CMONO_FROM_DOUBLE * ONES) + s1);
-    out[4] = code(c.div | s1, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
-    out[5] = code(c.div | s2, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
-    out[6] = code(mono, C_FLIP * ONES);
+    o[0] = code(c.zero, C_CREATE_DIV * ONES);
+    o[1] = code(c.div, C_FILL_DIV * ONES);
+    o[2] = code(c.zero | s2, (C_CMONO_FROM_DOUBLE * ONES) + s2);
+    o[3] = code(c.zero | s1, (C_CMONO_FROM_DOUBLE * ONES) + s1);
+    o[4] = code(c.div | s1, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    o[5] = code(c.div | s2, (C_FMONO_MAKE_DOUBLE * ONES) + c.div);
+    o[6] = code(mono, C_FLIP * ONES);
+    o[7] = code(up_a, C_DESTROY_TREF * ONES);
+    o[8] = code(dn_a, C_DESTROY_TREF * ONES);
     acc.zero += c.zero; acc.div += c.div; acc.mono += mono; acc.anch += up_a + dn_a;
-    uint32_t P[6], D[6];
-    P[0] = m0.zero;                              D[0] = m0.div;
-    P[1] = shl_sites(cp.zero, c.zero, 1);        D[1] = shl_sites(cp.div, c.div, 1);
-    P[2] = shl_sites(pm.zero, p0.zero, 1);       D[2] = shl_sites(pm.div, p0.div, 1);
-    P[3] = p0.zero;                              D[3] = p0.div;
-    P[4] = shr_sites(c.zero, cn.zero, 1);        D[4] = shr_sites(c.div, cn.div, 1);
-    P[5] = shr_sites(m0.zero, m1.zero, 1);       D[5] = shr_sites(m0.div, m1.div, 1);
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        const int i = kring(k);
-        const uint32_t near = (i & 1) ? D[(i + 5) % 6] : D[(i + 1) % 6];
-        const uint32_t far = (i & 1) ? D[(i + 1) % 6] : D[(i + 5) % 6];
-        const uint32_t present = c.div & P[i];
-        out[7 + k] = code(present, (C_MOVE_DIV * ONES) + near + (far << 1));
-        const uint32_t pn = present & near, pf = present & far, pnf = pn & far;
-        acc.bth += pnf; acc.met += pn ^ pnf; acc.cmb += pf ^ pnf; acc.nat += present & ~(near | far);
-    }
-    const uint32_t both = c.div & q0_div;
-    const uint32_t up = both & shr_sites(c.div, cn.div, 2), dn = both & shl_sites(qm_div, q0_div, 2);
-    out[13] = code(up, C_CREATE_TREF * ONES);
-    out[14] = code(dn, C_CREATE_TREF * ONES);
-    out[15] = code(up_a, C_DESTROY_TREF * ONES);
-    out[16] = code(dn_a, C_DESTROY_TREF * ONES);
-    acc.tref += up + dn;
+}
+// CreateTrefoil planes 13 (Up) and 14 (Down) of word j
+__host__ __device__ __forceinline__ void trefoil_planes(const Chunk16 &k, int j, uint32_t &up, uint32_t &dn, ByteAcc &acc) {
+    const uint32_t both = k.c[j + 1].div & k.q[j + 1];
+    const uint32_t u = both & shr_sites(k.c[j + 1].div, k.c[j + 2].div, 2);
+    const uint32_t d = both & shl_sites(k.q[j], k.q[j + 1], 2);
+    acc.tref += u + d;
+    up = code(u, C_CREATE_TREF * ONES);
+    dn = code(d, C_CREATE_TREF * ONES);
 }
 
 struct Sweep16Params {
@@ -250,7 +269,14 @@ struct Sweep16Params {
     int ctas_per_replica;
 };
 
-__global__ void __launch_bounds__(256) kmc_sweep16_kernel(const Sweep16Params p)
+#ifdef __CUDACC__
+template <int K> __device__ __forceinline__ void emit_move_plane(const Chunk16 &k, uint4 *O, size_t cpl, ByteAcc &acc) {
+    const uint32_t a = move_plane<K>(k, 0, acc), b = move_plane<K>(k, 1, acc);
+    const uint32_t c = move_plane<K>(k, 2, acc), d = move_plane<K>(k, 3, acc);
+    if (O) __stcs(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
+}
+
+__global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params p)
 {
     __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
     __shared__ unsigned int is_last;
@@ -263,43 +289,57 @@ __global__ void __launch_bounds__(256) kmc_sweep16_kernel(const Sweep16Params p)
     const int cl = (int)(g - (long long)rep * cpl);
     const int a = cl / cpr, ci = cl - a * cpr;
     const int row_local = tid / cpr;
-    for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
-    __syncthreads();
-
     const int d0 = p.d0;
-    const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
-    const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
-    const uint8_t *S = p.status + (size_t)rep * p.n;
-    const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
-    const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
-    const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
-    const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
-    const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
-    const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
-    const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
-    const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
-    const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
-    const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
 
-    const uint32_t cw[4] = {c4.x, c4.y, c4.z, c4.w};
-    ZD cf[6], mf[5], pf[5];
-    uint32_t qd[5];
-    cf[0] = zd_flags(c_prev); cf[5] = zd_flags(c_next);
-    cf[1] = zd_flags(c4.x); cf[2] = zd_flags(c4.y); cf[3] = zd_flags(c4.z); cf[4] = zd_flags(c4.w);
-    mf[0] = zd_flags(m4.x); mf[1] = zd_flags(m4.y); mf[2] = zd_flags(m4.z); mf[3] = zd_flags(m4.w); mf[4] = zd_flags(m_next);
-    pf[0] = zd_flags(p_prev); pf[1] = zd_flags(p4.x); pf[2] = zd_flags(p4.y); pf[3] = zd_flags(p4.z); pf[4] = zd_flags(p4.w);
-    qd[0] = zd_flags(q_prev).div; qd[1] = zd_flags(q4.x).div; qd[2] = zd_flags(q4.y).div;
-    qd[3] = zd_flags(q4.z).div; qd[4] = zd_flags(q4.w).div;
-
+    // issue all loads first; the shared-memory zeroing and its barrier overlap their latency
+    Chunk16 k;
+    {
+        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+        const uint8_t *S = p.status + (size_t)rep * p.n;
+        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
+        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
+        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
+        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
+        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
+        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+        k.cw[0] = c4.x; k.cw[1] = c4.y; k.cw[2] = c4.z; k.cw[3] = c4.w;
+        k.c[0] = zd_flags(c_prev); k.c[5] = zd_flags(c_next);
+        k.c[1] = zd_flags(c4.x); k.c[2] = zd_flags(c4.y); k.c[3] = zd_flags(c4.z); k.c[4] = zd_flags(c4.w);
+        k.m[0] = zd_flags(m4.x); k.m[1] = zd_flags(m4.y); k.m[2] = zd_flags(m4.z); k.m[3] = zd_flags(m4.w);
+        k.m[4] = zd_flags(m_next);
+        k.p[0] = zd_flags(p_prev); k.p[1] = zd_flags(p4.x); k.p[2] = zd_flags(p4.y); k.p[3] = zd_flags(p4.z);
+        k.p[4] = zd_flags(p4.w);
+        k.q[0] = zd_flags(q_prev).div; k.q[1] = zd_flags(q4.x).div; k.q[2] = zd_flags(q4.y).div;
+        k.q[3] = zd_flags(q4.z).div; k.q[4] = zd_flags(q4.w).div;
+    }
     ByteAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    uint32_t o[4][NS];
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
+    {
+        uint32_t o0[9], o1[9], o2[9], o3[9];
+        own_planes(k, 0, o0, acc); own_planes(k, 1, o1, acc); own_planes(k, 2, o2, acc); own_planes(k, 3, o3, acc);
+        if (O) {
 #pragma unroll
-    for (int j = 0; j < 4; j++)
-        sweep_word16(cw[j], cf[j], cf[j + 1], cf[j + 2], mf[j], mf[j + 1], pf[j], pf[j + 1], qd[j], qd[j + 1], o[j], acc);
-    if (p.slots) {
-        uint4 *O = reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl;
+            for (int j = 0; j < 7; j++) __stcs(O + (size_t)j * cpl, make_uint4(o0[j], o1[j], o2[j], o3[j]));
+            __stcs(O + (size_t)15 * cpl, make_uint4(o0[7], o1[7], o2[7], o3[7]));
+            __stcs(O + (size_t)16 * cpl, make_uint4(o0[8], o1[8], o2[8], o3[8]));
+        }
+    }
+    emit_move_plane<0>(k, O, cpl, acc); emit_move_plane<1>(k, O, cpl, acc); emit_move_plane<2>(k, O, cpl, acc);
+    emit_move_plane<3>(k, O, cpl, acc); emit_move_plane<4>(k, O, cpl, acc); emit_move_plane<5>(k, O, cpl, acc);
+    {
+        uint32_t u[4], d[4];
 #pragma unroll
-        for (int j = 0; j < NS; j++) __stcs(O + (size_t)j * cpl, make_uint4(o[0][j], o[1][j], o[2][j], o[3][j]));
+        for (int j = 0; j < 4; j++) trefoil_planes(k, j, u[j], d[j], acc);
+        if (O) {
+            __stcs(O + (size_t)13 * cpl, make_uint4(u[0], u[1], u[2], u[3]));
+            __stcs(O + (size_t)14 * cpl, make_uint4(d[0], d[1], d[2], d[3]));
+        }
     }
     // K2: this thread's 13 class counts as 16-bit pairs, pooled per row
     uint32_t pk[7];
@@ -316,6 +356,7 @@ __global__ void __launch_bounds__(256) kmc_sweep16_kernel(const Sweep16Params p)
     const uint32_t mask = cpr >= 32 ? 0xFFFFFFFFu : __match_any_sync(0xFFFFFFFFu, row_local);
 #pragma unroll
     for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+    __syncthreads();                                              // rows_sm zeroed by everyone
     if ((__ffs(mask) - 1) == lane) {
         uint32_t *R = rows_sm + row_local * RCG_STRIDE;
 #pragma unroll
@@ -332,25 +373,34 @@ __global__ void __launch_bounds__(256) kmc_sweep16_kernel(const Sweep16Params p)
         uint32_t *G = p.rowcnt + ((size_t)rep * d0 + first_row) * RCG_STRIDE;
         for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
     }
-    // class totals: CTA partial sums -> running totals; the last CTA of the replica publishes them
-    if (tid < NC) {
+    // class totals: CTA partial sums -> running totals; the last CTA of the replica publishes them.
+    // Only warp 0 takes part; its lane 0 orders the 13 atomics before the ticket with one fence
+    // (fence cumulativity through __syncwarp), instead of every warp paying for a gpu-scope fence.
+    if (tid < 32) {
         unsigned long long s = 0;
-        for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
-        if (p.ctas_per_replica == 1) p.counts[(size_t)rep * NC + tid] = s;
-        else if (s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
-    }
-    if (p.ctas_per_replica > 1) {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
-            if (tid == 0) p.ticket[rep] = 0u;
+        if (tid < NC)
+            for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
+        if (p.ctas_per_replica == 1) {
+            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
+        } else {
+            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+            __syncwarp();
+            unsigned int last = 0;
+            if (tid == 0) {
+                __threadfence();
+                last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
+                if (last) __threadfence();
+            }
+            last = __shfl_sync(0xFFFFFFFFu, last, 0);
+            if (last) {
+                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid == 0) p.ticket[rep] = 0u;
+            }
         }
     }
+    (void)is_last;
 }
+#endif  // __CUDACC__
 
 // Generic path (any d1 >= 5): one thread per site, scalar evaluation.
 __global__ void __launch_bounds__(256) kmc_sweep_kernel_generic(const SweepParams p)
