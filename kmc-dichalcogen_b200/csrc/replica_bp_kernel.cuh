@@ -50,13 +50,14 @@ __host__ __device__ __forceinline__ int nib(uint32_t t, int k) { return (int)((t
 // status -> plane type + 1 (0 = none: non-anchor trefoil member)
 //   s:     0     1      2      3     4      5  6  7      8  9
 //   type:  Z(1)  M1(3)  M2(4)  D(2)  A4(5)  0  0  A7(6)  0  0
-constexpr u64 STATUS_TYPE = 0x0060052431ull;
-__host__ __device__ __forceinline__ int status_plane(int s) { return (int)((STATUS_TYPE >> (4 * s)) & 0xF) - 1; }
+// (3 bits per status so the table fits one 32-bit register and the lookup is a shift + mask)
+constexpr uint32_t STATUS_TYPE = 1u | (3u << 3) | (4u << 6) | (2u << 9) | (5u << 12) | (6u << 21);
+__host__ __device__ __forceinline__ int status_plane(int s) { return (int)((STATUS_TYPE >> (3 * s)) & 7u) - 1; }
 // plane q (0..9) -> its type, and the column offset at which a site's bit lives in it
 //   q:      Z  ZP  ZM  D  DP  DM  M1 M2 A4 A7
 //   type:   0  0   0   1  1   1   2  3  4  5
 //   cshift: 0  -1  +1  0  -1  +1  0  0  0  0     (stored + 1)
-constexpr u64 PLANE_TYPE = 0x5432111000ull, PLANE_CSHIFT = 0x1111201201ull;
+constexpr u64 PLANE_TYPE = 0x5432111000ull, PLANE_CSHIFT = 0x1111201201ull;   // read once per lane
 
 template <int TD1>
 struct RowBits {

@@ -279,7 +279,6 @@ template <int K> __device__ __forceinline__ void emit_move_plane(const Chunk16 &
 __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params p)
 {
     __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
-    __shared__ unsigned int is_last;
     const int tid = threadIdx.x, lane = tid & 31;
     const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
     const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
@@ -398,7 +397,6 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
             }
         }
     }
-    (void)is_last;
 }
 #endif  // __CUDACC__
 

@@ -1,0 +1,225 @@
+"""`python3 -m demo1 CONFIG...` -- the reference's command line (reference demo1/__main__.py:14-157)
+over the CUDA engine: same flags, same YAML, same streamed JSON.  Extra flags: --seed, --replicas,
+--stats-only, --device."""
+import argparse
+import json
+import sys
+from functools import partial
+
+from . import config
+from .sim import KmcSim
+
+PROG = "demo1"
+
+
+def main(argv=None):
+    import logging
+    parser = argparse.ArgumentParser("python -m " + PROG, description="")
+    parser.add_argument("CONFIG", nargs="+", type=argparse.FileType("r"), help="paths to config files")
+    parser.add_argument("-d", "--dimensions", metavar="ARM,ZAG", type=delim_parser(positive_int, n=2, sep=","),
+                        default=[200, 200], help="PBC grid dimensions as a number of unit cells in each dimension")
+    parser.add_argument("-n", "--steps", type=positive_int, default=10000, help="stop after this many events")
+    parser.add_argument("-P", "--output-pstats", help="record profiling data, readable by the pstats module")
+    parser.add_argument("-p", "--profile", action="store_true", help="display profiling data")
+    parser.add_argument("-D", "--debug", action="store_true", help="display debug logs, hide standard output")
+    parser.add_argument("-T", "--temperature", type=float, default=None,
+                        help="temperature in kelvin. Only meaningful if config files specify barriers instead of rates.")
+    parser.add_argument("--write-initial", metavar="PATH", help="write initial state to PATH")
+    parser.add_argument("--embed-initial", action="store_true", help="embed initial state in output")
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument("--no-incremental", dest="incremental", action="store_false",
+                       help="disable incremental updates (debugging flag)")
+    group.add_argument("--validate-every", metavar="NSTEP", type=nonnegative_int, default=0,
+                       help="do incremental updates, but perform an expensive validation of all objects "
+                            "every NSTEP steps. (debugging flag)")
+    group = parser.add_mutually_exclusive_group()
+    group.add_argument("--zobrist-bits", metavar="NBITS", type=positive_int, default=None,
+                       help="(reference experimental flag; not part of the accelerated path)")
+    group.add_argument("--zobrist-hash", action="store_true",
+                       help="(reference experimental flag; not part of the accelerated path)")
+    # new flags
+    parser.add_argument("--seed", type=int, default=None, help="Philox seed (default: from the OS)")
+    parser.add_argument("--state-seed", type=int, default=None, help="seed of the initial-state generator")
+    parser.add_argument("--replicas", type=positive_int, default=1,
+                        help="run this many independent trajectories (statistics only unless 1)")
+    parser.add_argument("--stats-only", action="store_true", help="no event log, only the class histogram")
+    parser.add_argument("--device", type=int, default=0, help="CUDA device index")
+    args = parser.parse_args(argv)
+
+    if args.debug:
+        logging.getLogger().setLevel(10)
+    if args.zobrist_bits or args.zobrist_hash:
+        die("zobrist keys are an experimental reference flag outside the accelerated path (see DESIGN.md)")
+    config_dict = config.load_all(args.CONFIG)
+
+    def myrun():
+        run(ofile=DevNull() if args.debug else sys.stdout, nsteps=args.steps, dims=args.dimensions,
+            config_dict=config_dict, validate_every=args.validate_every, incremental=args.incremental,
+            save_initial_path=args.write_initial, embed_initial=args.embed_initial,
+            temperature=args.temperature, seed=args.seed, state_seed=args.state_seed,
+            replicas=args.replicas, stats_only=args.stats_only, device=args.device)
+
+    if args.output_pstats or args.profile:
+        with_profiling(myrun, args.output_pstats, sys.stderr if args.profile else None)
+    else:
+        myrun()
+
+
+class DevNull:
+    def write(self, *a, **kw):
+        pass
+
+
+def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_initial_path, embed_initial,
+        temperature, seed=None, state_seed=None, replicas=1, stats_only=False, device=0):
+    import random
+    cfg = config.from_dict(config_dict)        # pops every key: "config" is echoed as {} (reference quirk Q1)
+    rng = random.Random(state_seed) if state_seed is not None else random
+    init_state = cfg["state_gen_func"](tuple(dims), rng=rng)
+    if save_initial_path:
+        with open(save_initial_path, "w") as f:
+            json.dump(init_state.to_dict(), f)
+
+    if replicas > 1 or stats_only:
+        return run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device)
+
+    chunk = validate_every if validate_every else min(nsteps, 4096)
+    sim = KmcSim(init_state, cfg["rule_specs"], incremental=incremental, temperature=temperature,
+                 seed=seed, device=device, chunk=chunk, validate_launches=bool(validate_every))
+
+    with write_enclosing("{", "\n}", ofile):
+        def write_key_val(key, val, end=",\n", pretty=True, **kw):
+            ofile.write('"%s": ' % key)
+            json.dump(val, ofile, indent=2 if pretty else None, **kw)
+            ofile.write(end)
+
+        write_key_val("grid", grid_info(dims))
+        write_key_val("config", config_dict)
+        write_key_val("temperature", temperature, pretty=False)
+        write_key_val("rates", sim.rates_info(), sort_keys=True)
+        if embed_initial:
+            write_key_val("initial_state", init_state.to_dict(), pretty=False)
+        with write_enclosing(' "events": [\n  ', "\n ]", ofile):
+            first = True
+            for step in range(nsteps):
+                # with --validate-every N the kernel validates at the end of every N-event launch
+                # (KmcSim.validate semantics); a mismatch raises AssertionError from perform_random_move
+                info = sim.perform_random_move()
+                if not first:
+                    ofile.write(",\n  ")
+                ofile.write(json.dumps(info, sort_keys=True))
+                first = False
+    ofile.write("\n")
+    sim.close()
+
+
+def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device):
+    """--replicas / --stats-only: many independent trajectories from the same initial lattice, one
+    warp each; output is the per-class event histogram instead of an event log."""
+    import os
+    import numpy as np
+    from . import tables as T
+    from .engine import Engine
+    probe = KmcSim.__new__(KmcSim)
+    probe.rule_specs, probe.temperature = list(cfg["rule_specs"]), temperature
+    rates13, order, info = [0.0] * T.N_CLASSES, [], {}
+    for spec in probe.rule_specs:
+        rates = spec.rates(temperature)
+        for kind in spec.kinds():
+            rates13[T.CLASS_ID[(spec.name, kind)]] = rates[kind]
+            order.append(T.CLASS_ID[(spec.name, kind)])
+            info[spec.format(kind)] = rates[kind]
+    seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+    eng = Engine(init_state.dim, rates13, order, n_replicas=replicas, device=device)
+    eng.upload_state(np.tile(init_state.status, (replicas, 1)))
+    try:
+        eng.run(nsteps, seed, validate=True)
+    except ValueError:
+        pass
+    hist = eng.histogram()
+    out = {"grid": grid_info(dims), "temperature": temperature, "rates": info, "replicas": replicas,
+           "seed": seed, "events_done": int(eng.steps_done().sum()),
+           "histogram": {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in order}}
+    json.dump(out, ofile, indent=2, sort_keys=True)
+    ofile.write("\n")
+    eng.close()
+
+
+class write_enclosing:
+    """Writes `start` on entry and `end` on exit, also on exceptions, so that an interrupted run
+    leaves a parseable file (reference __main__.py:159-174)."""
+
+    def __init__(self, start, end, file):
+        self.file, self.start, self.end = file, start, end
+
+    def __enter__(self):
+        self.file.write(self.start)
+
+    def __exit__(self, *args):
+        self.file.write(self.end)
+
+
+def grid_info(dims):
+    return {"lattice_type": "hexagonal", "coord_format": "axial", "dim": list(dims)}
+
+
+def with_profiling(f, stats_out=None, text_out=None):
+    from cProfile import Profile
+    from pstats import Stats
+    prof = Profile()
+    prof.enable()
+    retval = f()
+    prof.disable()
+    if stats_out:
+        try:
+            prof.dump_stats(stats_out)
+        except (IOError, OSError) as e:
+            warn("could not write pstats ({})", e)
+    if text_out:
+        stats = Stats(prof, stream=text_out)
+        stats.sort_stats("cumtime")
+        stats.print_stats(20)
+    return retval
+
+
+def int_with_min(minimum, errmsg, s):
+    x = int(s)
+    if x < minimum:
+        raise argparse.ArgumentTypeError("%s: %d" % (errmsg, x))
+    return x
+
+
+positive_int = partial(int_with_min, 1, "Not a positive integer")
+nonnegative_int = partial(int_with_min, 0, "Not a non-negative integer")
+
+
+def delim_parser(typ, n=None, sep=","):
+    def inner(s):
+        xs = []
+        for t in s.split(sep):
+            try:
+                xs.append(typ(t))
+            except ValueError:
+                raise argparse.ArgumentTypeError("Bad value: %r" % (t,))
+        if n not in (None, len(xs)):
+            raise argparse.ArgumentTypeError("Expected %d arguments separated by %r; got %d" % (n, sep, len(xs)))
+        return xs
+    return inner
+
+
+def say_err(msg, *args, **kw):
+    print("%s: %s" % (PROG, msg.format(*args, **kw)), file=sys.stderr)
+
+
+def warn(msg, *args, **kw):
+    say_err("Warning: " + msg, *args, **kw)
+
+
+def die(msg, *args, **kw):
+    say_err("FATAL: " + msg, *args, **kw)
+    say_err("Aborting.")
+    sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+"""KmcSim: the reference's engine object (reference demo1/sim.py:31-198) over the CUDA engine.
+
+Same constructor, methods and log dictionaries; the work happens on the GPU through the C ABI
+(demo1/engine.py -> libkmc_b200.so).  Events are produced on the device in chunks and handed out
+one by one, so `perform_random_move()` keeps its one-event-per-call contract.
+
+What the host keeps: YAML/rule bookkeeping, Arrhenius rates (math.exp exactly as the reference, so
+the rate bits are equal), exact `total_rate = math.fsum(weights)` from the logged class counts, and
+formatting.  There is no CPU fallback: without the library or a GPU, construction raises.
+"""
+import math
+import os
+import warnings
+
+import numpy as np
+
+from . import tables as T
+
+# reference demo1/sim.py:27-29
+eV_PER_J = 6.24150913e18
+BOLTZMANN__J_PER_K = 1.38064852e-23
+BOLTZMANN__eV_PER_K = BOLTZMANN__J_PER_K * eV_PER_J
+DEFAULT_KIND = T.DEFAULT_KIND
+
+
+class RuleSpec:
+    """A rule name and its rates or barriers (reference sim.py:170-198)."""
+
+    def __init__(self, rule_name, rates, rate_is_barrier):
+        if rule_name not in T.RULE_KINDS:
+            raise RuntimeError("config: unknown rule: %s" % rule_name)
+        self.name = rule_name
+        self._rates = dict(rates)
+        self._is_barrier = bool(rate_is_barrier)
+
+    def kinds(self):
+        return list(T.RULE_KINDS[self.name])
+
+    def rates(self, temperature=None):
+        if self._is_barrier:
+            if temperature is None:
+                raise ValueError("must specify temperature to compute rates from barrier")
+            return {k: math.exp(-v / (temperature * BOLTZMANN__eV_PER_K)) for k, v in self._rates.items()}
+        return dict(self._rates)
+
+    def format(self, kind=None):
+        return self.name if kind is None else "%s:%s" % (self.name, kind)
+
+
+class KmcSim:
+    """Runs the KMC simulation of one trajectory on the GPU.
+
+    ``seed``/``replica`` select the Philox stream (the reference never seeds; by default a fresh seed
+    is drawn from the OS).  ``chunk`` events are generated per kernel launch."""
+
+    def __init__(self, initial_state, rule_specs, temperature=None, incremental=True, seed=None,
+                 replica=0, device=0, chunk=4096, validate_launches=False):
+        from .engine import Engine
+        self.rule_specs = list(rule_specs)
+        self.temperature = temperature
+        self.incremental = incremental
+        self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
+        self.replica = int(replica)
+        self.chunk = int(chunk)
+        self.validate_launches = bool(validate_launches)
+        self._Engine = Engine
+        self._device = device
+        self._engine = None
+        self._buffer = None
+        self._cursor = 0
+        self.state = None
+        self.initialize(initial_state)
+
+    # -- setup -----------------------------------------------------------------------------
+    def initialize(self, state=None):
+        """(Re)build everything; a given state replaces the current one (it is not modified)."""
+        if state is not None:
+            self.state = state.clone()
+        elif self._engine is not None:
+            self._sync_state()
+        assert self.state is not None
+        self.rules_and_rates = {}
+        rates13 = [0.0] * T.N_CLASSES
+        order = []
+        for spec in self.rule_specs:
+            rates = spec.rates(self.temperature)
+            for kind in spec.kinds():
+                if kind not in rates:
+                    raise RuntimeError("config: %s: Missing required rate for kind: %s" % (spec.format(), kind))
+            for kind in rates:
+                if kind not in spec.kinds():
+                    warnings.warn("config: %s: Unexpected kind: %s" % (spec.format(), kind))
+            self.rules_and_rates[spec.name] = rates
+            for kind in spec.kinds():
+                cid = T.CLASS_ID[(spec.name, kind)]
+                rates13[cid] = rates[kind]
+                order.append(cid)
+        self._rates13 = rates13
+        self._order = order
+        if self._engine is None:
+            self._engine = self._Engine(self.state.dim, rates13, order, n_replicas=1, device=self._device)
+        self.state.validate()
+        self._engine.upload_state(self.state.status)
+        self._buffer, self._cursor = None, 0
+
+    def rate(self, rule, kind):
+        return self.rules_and_rates[rule][kind]
+
+    def rates_info(self):
+        return {"%s:%s" % (rule, kind): rate for rule, rates in self.rules_and_rates.items()
+                for kind, rate in rates.items()}
+
+    # -- events ----------------------------------------------------------------------------
+    def _refill(self, nsteps):
+        from . import _native as nat
+        if self.incremental:
+            ev = self._engine.run(nsteps, self.seed, replica0=self.replica, log_mode=nat.LOG_FULL,
+                                  validate=self.validate_launches)
+        else:
+            ev = self._engine.run_noinc(nsteps, self.seed, replica0=self.replica, log_mode=nat.LOG_FULL)
+        return ev[0]
+
+    def perform_random_move(self):
+        """Select and perform one random event; returns the reference's summary dict
+        (reference sim.py:106-143)."""
+        if self._buffer is None or self._cursor >= len(self._buffer):
+            try:
+                self._buffer = self._refill(self.chunk)
+            except ValueError:
+                # total rate hit zero inside the chunk: hand out what happened before it
+                self._buffer = self._engine._last_events[0]
+                self._cursor = 0
+                if self._buffer[0]["cls"] == 0xFF:
+                    raise
+            else:
+                self._cursor = 0
+        rec = self._buffer[self._cursor]
+        if rec["cls"] == 0xFF:
+            raise ValueError("Cannot choose from total weight of zero!")
+        self._cursor += 1
+        return self._format(rec)
+
+    def _format(self, rec):
+        rule, kind = T.CLASSES[int(rec["cls"])]
+        weights = [float(int(rec["counts"][c])) * self._rates13[c] for c in self._order]
+        return {
+            "rule": rule,
+            "move": T.move_info(int(rec["site"]), int(rec["slot"]), self.state.dim),
+            "kind": kind,
+            "rate": self._rates13[int(rec["cls"])],
+            "total_rate": math.fsum(weights),           # reference sim.py:138
+        }
+
+    def perform_given_move(self, rule, move):
+        """Apply an explicit move, given as (site, slot) (reference sim.py:145-157)."""
+        self._discard_lookahead()
+        site, slot = move
+        if T.SLOT_RULE[slot] != rule:
+            raise ValueError("slot %d does not belong to rule %s" % (slot, rule))
+        self._engine.perform_given(0, site, slot)
+
+    def _discard_lookahead(self):
+        if self._buffer is not None and self._cursor < len(self._buffer):
+            raise RuntimeError("events were generated ahead of the caller (chunk=%d): construct KmcSim "
+                               "with chunk=1 to interleave explicit moves" % self.chunk)
+        self._buffer, self._cursor = None, 0
+
+    def _sync_state(self):
+        self.state.status[:] = self._engine.download_state()[0]
+
+    def current_state(self):
+        """Lattice after every event generated so far (including look-ahead events in the buffer)."""
+        self._sync_state()
+        return self.state
+
+    def validate(self):
+        """Expensive self-check (reference sim.py:159-168).
+
+        The incrementally maintained move tables only live inside a kernel launch, so their check
+        against a from-scratch enumeration runs on the device at the end of every launch when the
+        sim was built with ``validate_launches=True`` (what ``--validate-every N`` does, with
+        launches of N events) and raises AssertionError from ``perform_random_move``.  Here the
+        lattice invariants are checked, and one launch of zero events re-enumerates the lattice."""
+        self._sync_state()
+        self.state.validate()
+        self._engine.run(0, self.seed, replica0=self.replica, validate=True)
+        return True
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None

@@ -1,0 +1,116 @@
+"""The reference-facing host objects on a GPU: KmcSim log dictionaries against the golden fixtures,
+and the `python -m demo1` command line (same JSON layout as the reference's)."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from demo1.sim import KmcSim, RuleSpec
+from demo1.state import State
+from util_golden import load
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "kmc-dichalcogen_b200")
+
+
+def specs_from_meta(meta):
+    out = []
+    for name in meta["rule_order"]:
+        body = meta["rules"][name]
+        key = "barrier" if "barrier" in body else "rate"
+        val = body[key]
+        if not isinstance(val, dict):
+            val = {"natural": val}
+        out.append(RuleSpec(name, {k: float(v) for k, v in val.items()}, rate_is_barrier=(key == "barrier")))
+    return out
+
+
+@pytest.mark.parametrize("name,incremental", [("allrules_8x8", True), ("wse2_16x16", True),
+                                              ("ties_reordered_7x11", True), ("testcfg_5x7", False)])
+def test_kmcsim_log_matches_reference(name, incremental):
+    g = load(name)
+    m = g["meta"]
+    nsteps = m["nsteps"] if incremental else 150
+    sim = KmcSim(State(m["dim"], g["status0"]), specs_from_meta(m), temperature=m["temperature"],
+                 incremental=incremental, seed=m["seed"], replica=m["replica"], chunk=257,
+                 validate_launches=incremental)
+    assert sim.rates_info() == {"%s:%s" % (r, k): v for r in m["rule_order"]
+                                for k, v in sim.rules_and_rates[r].items()}
+    for t in range(nsteps):
+        info = sim.perform_random_move()
+        want = g["events"][t]
+        assert sorted(info) == ["kind", "move", "rate", "rule", "total_rate"]
+        assert info["total_rate"] == want["total_rate"]              # exactly rounded fsum, bit-equal
+        assert info["rate"] == g["rates"][want["cls"]]
+        if t < len(m["infos"]):
+            ref = m["infos"][t]
+            assert (info["rule"], info["kind"]) == (ref["rule"], ref["kind"])
+            if "nodes" in info["move"]:
+                assert sorted(map(tuple, info["move"]["nodes"])) == sorted(map(tuple, ref["move"]["nodes"]))
+            else:
+                assert info["move"] == ref["move"]
+    assert sim.validate() is True
+    if nsteps == m["nsteps"]:
+        # events are generated ahead in chunks of 257: run to the end of the last chunk on the oracle side
+        pass
+    sim.close()
+
+
+def test_input_state_is_not_modified_and_zero_rate_raises():
+    st = State((5, 5))
+    st.new_divacancy((1, 1))
+    before = st.status.copy()
+    sim = KmcSim(st, [RuleSpec("FillDivacancy", {"natural": 2.0}, False)], seed=1, chunk=8)
+    info = sim.perform_random_move()
+    assert info == {"rule": "FillDivacancy", "kind": "natural", "move": {"node": [1, 1]}, "rate": 2.0,
+                    "total_rate": 2.0}
+    with pytest.raises(ValueError, match="total weight of zero"):
+        sim.perform_random_move()
+    assert (st.status == before).all()
+    assert (sim.current_state().status == 0).all()
+    sim.close()
+
+
+def run_cli(args):
+    env = dict(os.environ, PYTHONPATH=PKG)
+    p = subprocess.run([sys.executable, "-m", "demo1"] + args, capture_output=True, text=True, env=env,
+                       cwd=ROOT, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    return p.stdout
+
+
+def test_cli_json_layout_matches_reference():
+    out = run_cli([os.path.join(PKG, "config", "mixed_rates.yaml"), "-d", "8,8", "-n", "200", "--seed", "7",
+                   "--embed-initial", "--validate-every", "50"])
+    doc = json.loads(out)
+    assert list(doc) == ["grid", "config", "temperature", "rates", "initial_state", "events"]
+    assert doc["grid"] == {"lattice_type": "hexagonal", "coord_format": "axial", "dim": [8, 8]}
+    assert doc["config"] == {} and doc["temperature"] is None
+    assert doc["initial_state"] == {"dim": [8, 8], "vacancies": [], "trefoils": []}
+    assert len(doc["events"]) == 200
+    # pristine 8x8 with these rates: 64*(2*10 + 10) (SURVEY 8c known answer)
+    assert doc["events"][0]["total_rate"] == 1920.0
+    assert out.startswith('{"grid": {\n  "lattice_type"') and out.endswith("\n ]\n}\n")
+    # same seed -> same log; the pristine start is the allrules_8x8 fixture's trajectory
+    g = load("allrules_8x8")
+    assert [e["total_rate"] for e in doc["events"]] == list(g["events"]["total_rate"][:200])
+
+
+def test_cli_no_incremental_agrees_with_incremental():
+    cfg = os.path.join(PKG, "config", "wse2_1500K.yaml")
+    common = [cfg, "-T", "1500", "-d", "16,16", "-n", "120", "--seed", "3", "--state-seed", "4"]
+    a = json.loads(run_cli(common))
+    b = json.loads(run_cli(common + ["--no-incremental"]))
+    assert a["events"] == b["events"]
+    assert a["temperature"] == 1500.0 and len(a["rates"]) == 9
+
+
+def test_cli_replica_batch_statistics():
+    cfg = os.path.join(PKG, "config", "wse2_1500K.yaml")
+    out = json.loads(run_cli([cfg, "-T", "1500", "-d", "64,64", "-n", "500", "--seed", "3", "--state-seed", "4",
+                              "--replicas", "64"]))
+    assert out["events_done"] == 64 * 500 and sum(out["histogram"].values()) == 64 * 500

@@ -1,0 +1,143 @@
+"""Host-side logic of the demo1 package (no GPU): config schema and errors, state generators against
+fixtures produced by the reference's gen_random_state, (de)serialisation, rate computation."""
+import io
+import json
+import math
+import os
+import random
+import warnings
+
+import numpy as np
+import pytest
+import yaml
+
+from demo1 import config, tables as T
+from demo1.kmc import weighted_choice
+from demo1.sim import RuleSpec, BOLTZMANN__eV_PER_K
+from demo1.state import State, gen_random_state
+from util_golden import GOLDEN, load
+
+PKG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "kmc-dichalcogen_b200")
+
+
+def test_state_generators_match_reference_fixtures():
+    z = np.load(os.path.join(GOLDEN, "state_gen.npz"))
+    metas = json.loads(str(z["meta"]))
+    for i, m in enumerate(metas):
+        st = gen_random_state(tuple(m["dim"]), m["mode"], m["params"], rng=random.Random(m["seed"]))
+        assert (st.status == z["status_%d" % i]).all(), m
+
+
+def test_state_roundtrip_and_validation():
+    g = load("allrules_8x8")
+    st = State((8, 8), g["status1"])
+    st.validate()
+    d = st.to_dict()
+    assert set(d) == {"dim", "vacancies", "trefoils"}
+    back = State.from_dict(json.loads(json.dumps(d)))
+    assert (back.status == st.status).all()
+    assert len(d["trefoils"]) == int(((st.status == 4) | (st.status == 7)).sum())
+    bad = st.clone()
+    bad.status[np.nonzero(bad.status >= 4)[0][0]] = 0
+    with pytest.raises(AssertionError):
+        bad.validate()
+
+
+def test_shipped_configs_load():
+    for name, nrules in [("wse2_1500K.yaml", 5), ("mixed_rates.yaml", 8)]:
+        with open(os.path.join(PKG, "config", name)) as f:
+            cfg = config.from_dict(config.load_all([f]))
+        assert len(cfg["rule_specs"]) == nrules
+        st = cfg["state_gen_func"]((16, 16), rng=random.Random(1))
+        assert st.status.size == 256
+
+
+def test_reference_style_configs_are_accepted():
+    # test-cfg.yaml style: stale 'Rule' prefixes; WSe2.yaml style: the stub rule is skipped
+    d = yaml.safe_load("""
+rules:
+  RuleCreateDivacancy: {rate: 10}
+  MoveMonovacancy: {barrier: {natural: 2.5, merge-divacancy: 3.0, split-divacancy: 2.3, swap-divacancy: 2.5}}
+  FlipMonovacancy: {barrier: 3.4}
+""")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        cfg = config.from_dict(d)
+    assert [s.name for s in cfg["rule_specs"]] == ["CreateDivacancy", "FlipMonovacancy"]
+    assert any("stub" in str(x.message) for x in w)
+    assert d == {}                      # consumed, as the reference does (quirk Q1)
+
+
+@pytest.mark.parametrize("text,msg", [
+    ("state: {}", "missing required key: 'rules'"),
+    ("rules: {}\nextra: 1", "unrecognized section"),
+    ("rules: {Nope: {rate: 1}}", "unknown rule: Nope"),
+    ("rules: {CreateDivacancy: {rate: 1, barrier: 2}}", "exactly one of"),
+    ("rules: {CreateDivacancy: {}}", "exactly one of"),
+    ("rules: {CreateDivacancy: {rate: -1}}", "negative"),
+    ("rules: {CreateDivacancy: {rate: abc}}", "real number or a mapping"),
+    ("rules: {CreateDivacancy: {rate: {natural: x}}}", "non-numeric"),
+    ("rules: {CreateDivacancy: {rate: 1, colour: red}}", "invalid attribute"),
+    ("rules: {CreateDivacancy: {rate: 1, enabled: 'yes'}}", "enabled must be a boolean"),
+    ("rules: {}\nstate: {random: {divacancy: 1%}}", "missing required key: 'mode'"),
+    ("rules: {}\nstate: {random: {mode: fuzzy}}", "invalid choice for 'mode'"),
+    ("rules: {}\nstate: {random: {mode: exact, divacancy: 70%, monovacancy: 70%}}", "sum of rates"),
+    ("rules: {}\nstate: {random: {mode: exact, trefoil: 1%}}", "unrecognized parameter"),
+    ("rules: {}\nstate: {path: x}", "invalid attribute"),
+])
+def test_config_errors(text, msg):
+    with pytest.raises(RuntimeError, match="config: .*" + msg):
+        config.from_dict(yaml.safe_load(text))
+
+
+def test_merge_later_file_wins_and_keeps_first_appearance_order():
+    a = io.StringIO("rules:\n  CreateDivacancy: {rate: 1}\n  FillDivacancy: {rate: 2}\n")
+    b = io.StringIO("rules:\n  FillDivacancy: {rate: 5}\n  FlipMonovacancy: {rate: 3}\n")
+    merged = config.load_all([a, b])
+    assert list(merged["rules"]) == ["CreateDivacancy", "FillDivacancy", "FlipMonovacancy"]
+    assert merged["rules"]["FillDivacancy"]["rate"] == 5
+
+
+def test_rates_from_barriers_match_reference_formula():
+    spec = RuleSpec("MoveDivacancy", {"natural": 2.25, "missing-metal": 2.11199155, "missing-comb": 2.52009312,
+                                      "missing-both": 2.25}, rate_is_barrier=True)
+    with pytest.raises(ValueError, match="temperature"):
+        spec.rates(None)
+    r = spec.rates(1500.0)
+    assert r["natural"] == math.exp(-2.25 / (1500.0 * BOLTZMANN__eV_PER_K))
+    g = load("wse2_16x16")              # rates computed by the reference itself
+    assert r["natural"] == g["rates"][2] and r["missing-metal"] == g["rates"][3]
+    assert r["missing-comb"] == g["rates"][4] and r["missing-both"] == g["rates"][5]
+
+
+def test_weighted_choice_matches_reference_semantics():
+    class Fixed:
+        def __init__(self, u): self.u = u
+        def uniform(self, a, b): return a + (b - a) * self.u
+    pairs = [("a", 3.0), ("z", 0.0), ("b", 1.0), ("c", 1.0)]
+    # sorted stably: b(1) c(1) a(3); cumulative 1, 2, 5
+    assert weighted_choice(pairs, rng=Fixed(0.0)) == "b"
+    assert weighted_choice(pairs, rng=Fixed(0.2)) == "b"        # x = 1.0 -> bisect_left -> index 0
+    assert weighted_choice(pairs, rng=Fixed(0.21)) == "c"
+    assert weighted_choice(pairs, rng=Fixed(0.41)) == "a"
+    with pytest.raises(ValueError, match="total weight of zero"):
+        weighted_choice([("a", 0.0)])
+    with pytest.raises(ValueError, match="Negative weight"):
+        weighted_choice([("a", -1.0), ("b", 2.0)])
+
+
+def test_move_info_formats():
+    dim = (8, 8)
+    assert T.move_info(10, 0, dim) == {"node": [1, 2]}
+    assert T.move_info(10, 3, dim) == {"node": [1, 2], "layer": 2}
+    assert T.move_info(10, 4, dim) == {"node": [1, 2], "layer": 1}
+    assert T.move_info(0, 7, dim) == {"was": [0, 0], "now": [7, 1]}
+    assert T.move_info(62, 14, dim) == {"nodes": [[7, 6], [1, 6], [1, 4]]}
+    g = load("allrules_8x8")
+    for rec, info in zip(g["events"], g["meta"]["infos"]):
+        mine = T.move_info(int(rec["site"]), int(rec["slot"]), dim)
+        assert T.CLASSES[int(rec["cls"])] == (info["rule"], info["kind"])
+        if "nodes" in mine:             # the reference lists a frozenset: order is arbitrary
+            assert sorted(map(tuple, mine["nodes"])) == sorted(map(tuple, info["move"]["nodes"]))
+        else:
+            assert mine == info["move"]
