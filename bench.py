@@ -214,21 +214,18 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from demo1 import _native as nat
+    from demo1 import parallel
     from demo1.engine import Engine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world, local = parallel.world()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cuda = torch.device("cuda", local)
+    parallel.init(backend="nccl", device=cuda)
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        parallel.barrier()
         torch.cuda.synchronize()
 
     rates, order = wse2_rates(), WSE2_ORDER
@@ -264,19 +261,13 @@ def main():
     launches = eng.launch_count() - launches0
     clocks = sampler.stop()
     barrier()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
+    max_ms = parallel.max_over_ranks(total_ms, device=cuda)
     value = world * R * E * args.steps / (max_ms * 1e-3)
     steps_done = eng.steps_done()
     assert int(steps_done.min()) == (args.warmup + args.steps) * E, "a replica stopped early"
 
     # the one collective of the path: event histogram summed over GPUs (NCCL over NVLink)
-    hist = torch.from_numpy(eng.histogram()).to("cuda")
-    if world > 1:
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
-    hist = hist.cpu().numpy()
+    hist = parallel.reduce_histogram(eng.histogram(), device=cuda)
     assert int(hist.sum()) == world * R * E * (args.warmup + args.steps)
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------
@@ -296,10 +287,7 @@ def main():
         e2e_step()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * R * E * args.steps / float(t.item())
+    e2e_value = world * R * E * args.steps / parallel.max_over_ranks(e2e_s, device=cuda)
     h2d = R * DIM[0] * DIM[1]
     d2h = R * DIM[0] * DIM[1] + R * 13 * 8
     eng.close()
