@@ -149,6 +149,8 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
  * 1 = byte lattice, 2 = bit-sliced.  Both produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
+/* aligned-shape sweep kernel: 0 = nibble-parallel + PRMT tables (default), 1 = byte-parallel */
+int kmc_set_sweep_kernel(kmc_engine *h, int variant);
 
 /*
  * Event classes (reference demo1/rules.py):           Move slots per site (move key in the reference):

@@ -51,6 +51,7 @@ struct kmc_engine {
     int *d_result = nullptr;
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes
+    int sweep_variant = 0;                   // 0 nibble/PRMT kernel, 1 byte-parallel kernel (aligned shapes)
     long long launches = 0;
     bool swept = false;
     int max_smem_optin = 0;
@@ -236,7 +237,8 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
         q.ctas_per_replica = (h->n >> 4) / 256;
         const long long blocks = (long long)R * q.ctas_per_replica;
-        kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        if (h->sweep_variant == 1) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        else kmc_sweep16n_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         CU(cudaGetLastError());
         h->launches += 1;
         return KMC_OK;
@@ -559,6 +561,12 @@ extern "C" int kmc_set_warps_per_block(kmc_engine *h, int warps)
 {
     if (!h || warps < 0 || warps > 8) return fail(KMC_ERR_ARG, "warps per block must be 0..8");
     h->warps_per_block = warps;
+    return KMC_OK;
+}
+extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
+{
+    if (!h || variant < 0 || variant > 1) return fail(KMC_ERR_ARG, "variant must be 0 (nibble/PRMT) or 1 (byte-parallel)");
+    h->sweep_variant = variant;
     return KMC_OK;
 }
 extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)

@@ -400,6 +400,237 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
 }
 #endif  // __CUDACC__
 
+// ---- 16 sites per thread, nibble-parallel arithmetic, PRMT table output --------------------------------
+// Second-generation aligned kernel.  The byte-parallel version above is bound by the ALU pipe (LOP3/SHF
+// issue at half rate), not by HBM.  Here the 16 status bytes of a thread are packed to 4-bit fields
+// (8 sites per 32-bit word), so every predicate op covers 8 sites, and each slot plane is produced by
+// the byte-permute unit used as an 8-entry lookup table: the four low selector nibbles of a PRMT pick,
+// per site, the plane's code byte for that site's status (own-status planes) or for its
+// (present, near, far) triple (MoveDivacancy planes).  Counting uses per-nibble accumulators.
+constexpr uint32_t ONESN = 0x11111111u;
+__host__ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (sel >> (4 * i)) & 0xF;
+        uint32_t byte = (uint32_t)(v >> (8 * (n & 7))) & 0xFF;
+        if (n & 8) byte = (byte & 0x80) ? 0xFF : 0x00;
+        r |= byte << (8 * i);
+    }
+    return r;
+#endif
+}
+// 8 status bytes (two words) -> 8 nibbles
+__host__ __device__ __forceinline__ uint32_t pack_nib(uint32_t x, uint32_t y) {
+    return prmt(x | (x >> 4), y | (y >> 4), 0x6420);
+}
+__host__ __device__ __forceinline__ ZD nzd(uint32_t n) {
+    const uint32_t e0 = n & ONESN, e1 = (n >> 1) & ONESN, hi = ((n >> 2) | (n >> 3)) & ONESN;
+    ZD f; f.zero = (e0 | e1 | hi) ^ ONESN; f.div = e0 & e1 & ~hi; return f;
+}
+__host__ __device__ __forceinline__ uint32_t nshr(uint32_t cur, uint32_t next, int k) {   // site b -> b + k
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(cur, next, 4 * k);
+#else
+    return (cur >> (4 * k)) | (next << (32 - 4 * k));
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t nshl(uint32_t prev, uint32_t cur, int k) {   // site b -> b - k
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(prev, cur, 4 * k);
+#else
+    return (cur << (4 * k)) | (prev >> (32 - 4 * k));
+#endif
+}
+// own row c[0..3] = prev (its top nibbles), two own words, next (its low nibbles); row a-1 m[0..2] = own, own,
+// next; row a+1 p[0..2] = prev, own, own; row a+2 q[0..2] (divacancy flags only)
+struct Chunk16N { uint32_t cn[2]; ZD c[4], m[3], p[3]; uint32_t q[3]; };
+struct NibAcc { uint32_t pres, pn, pf, pnf; };      // per-nibble sums over directions and both words (<= 12)
+
+template <int I> __host__ __device__ __forceinline__ ZD ring_flags_n(const Chunk16N &k, int j) {
+    ZD r;
+    if (I == 0) r = k.m[j];
+    else if (I == 1) { r.zero = nshl(k.c[j].zero, k.c[j + 1].zero, 1); r.div = nshl(k.c[j].div, k.c[j + 1].div, 1); }
+    else if (I == 2) { r.zero = nshl(k.p[j].zero, k.p[j + 1].zero, 1); r.div = nshl(k.p[j].div, k.p[j + 1].div, 1); }
+    else if (I == 3) r = k.p[j + 1];
+    else if (I == 4) { r.zero = nshr(k.c[j + 1].zero, k.c[j + 2].zero, 1); r.div = nshr(k.c[j + 1].div, k.c[j + 2].div, 1); }
+    else { r.zero = nshr(k.m[j].zero, k.m[j + 1].zero, 1); r.div = nshr(k.m[j].div, k.m[j + 1].div, 1); }
+    return r;
+}
+// MoveDivacancy direction K of nibble word j: two output words (sites 0-3, 4-7 of the word)
+template <int K> __host__ __device__ __forceinline__ void move_plane_n(const Chunk16N &k, int j, uint32_t &o0,
+                                                                         uint32_t &o1, NibAcc &acc) {
+    constexpr int I = (0x204315 >> (4 * K)) & 7;           // kring(K)
+    constexpr int IN = (I & 1) ? (I + 5) % 6 : (I + 1) % 6, IF = (I & 1) ? (I + 1) % 6 : (I + 5) % 6;
+    const uint32_t present = k.c[j + 1].div & ring_flags_n<I>(k, j).zero;
+    const uint32_t near = ring_flags_n<IN>(k, j).div, far = ring_flags_n<IF>(k, j).div;
+    const uint32_t pn = present & near, pf = present & far;
+    acc.pres += present; acc.pn += pn; acc.pf += pf; acc.pnf += pn & far;
+    // selector nibble = present + 2*near + 4*far -> code 2 + near + 2*far, or 0xFF when absent
+    const uint32_t sel = far * 4u + (near * 2u + present);
+    o0 = prmt(0x03FF02FFu, 0x05FF04FFu, sel);
+    o1 = prmt(0x03FF02FFu, 0x05FF04FFu, sel >> 16);
+}
+__host__ __device__ __forceinline__ uint32_t nib_sum(uint32_t x) {      // sum of the 8 nibbles
+    return (((x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu)) * ONES) >> 24;
+}
+
+#ifdef __CUDACC__
+template <int K> __device__ __forceinline__ void emit_move_plane_n(const Chunk16N &k, uint4 *O, size_t cpl, NibAcc &acc) {
+    uint32_t a, b, c, d;
+    move_plane_n<K>(k, 0, a, b, acc);
+    move_plane_n<K>(k, 1, c, d, acc);
+    if (O) __stcs(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
+}
+__device__ __forceinline__ void emit_lut_plane(uint4 *O, size_t plane, size_t cpl, uint32_t lo, uint32_t hi,
+                                               uint32_t s0, uint32_t s0h, uint32_t s1, uint32_t s1h) {
+    if (O) __stcs(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
+}
+
+__global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Params p)
+{
+    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
+    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
+    const int rows_in_cta = 256 / cpr;
+    const long long g = (long long)blockIdx.x * 256 + tid;
+    const int rep = (int)(g / cpl);
+    const int cl = (int)(g - (long long)rep * cpl);
+    const int a = cl / cpr, ci = cl - a * cpr;
+    const int row_local = tid / cpr;
+    const int d0 = p.d0;
+
+    Chunk16N k;
+    {
+        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+        const uint8_t *S = p.status + (size_t)rep * p.n;
+        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
+        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
+        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
+        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
+        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
+        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+        k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
+        k.c[0] = nzd(pack_nib(0u, c_prev)); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]);
+        k.c[3] = nzd(pack_nib(c_next, 0u));
+        k.m[0] = nzd(pack_nib(m4.x, m4.y)); k.m[1] = nzd(pack_nib(m4.z, m4.w)); k.m[2] = nzd(pack_nib(m_next, 0u));
+        k.p[0] = nzd(pack_nib(0u, p_prev)); k.p[1] = nzd(pack_nib(p4.x, p4.y)); k.p[2] = nzd(pack_nib(p4.z, p4.w));
+        k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
+        k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
+    }
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
+    // own-status planes: table lookup by status (8, 9 -> 5, 6: all of 5, 6, 8, 9 carry no own-status move)
+    uint32_t n_zero, n_div, n_mono, n_anch;
+    {
+        const uint32_t e3a = (k.cn[0] >> 3) & ONESN, e3b = (k.cn[1] >> 3) & ONESN;
+        const uint32_t s0 = k.cn[0] - 3u * e3a, s1 = k.cn[1] - 3u * e3b;
+        const uint32_t s0h = s0 >> 16, s1h = s1 >> 16;
+        const uint32_t F = 0xFFFFFFFFu;
+        emit_lut_plane(O, 0, cpl, 0xFFFFFF00u, F, s0, s0h, s1, s1h);      // CreateDivacancy      s0 -> 0
+        emit_lut_plane(O, 1, cpl, 0x01FFFFFFu, F, s0, s0h, s1, s1h);      // FillDivacancy        s3 -> 1
+        emit_lut_plane(O, 2, cpl, 0xFF09FF08u, F, s0, s0h, s1, s1h);      // CreateMono layer 1   s0 -> 8, s2 -> 9
+        emit_lut_plane(O, 3, cpl, 0xFFFF0908u, F, s0, s0h, s1, s1h);      // CreateMono layer 2   s0 -> 8, s1 -> 9
+        emit_lut_plane(O, 4, cpl, 0x0BFF0AFFu, F, s0, s0h, s1, s1h);      // FillMono layer 1     s1 -> 10, s3 -> 11
+        emit_lut_plane(O, 5, cpl, 0x0B0AFFFFu, F, s0, s0h, s1, s1h);      // FillMono layer 2     s2 -> 10, s3 -> 11
+        emit_lut_plane(O, 6, cpl, 0xFF0C0CFFu, F, s0, s0h, s1, s1h);      // FlipMonovacancy      s1, s2 -> 12
+        emit_lut_plane(O, 15, cpl, F, 0xFFFFFF07u, s0, s0h, s1, s1h);     // DestroyTrefoil Up    s4 -> 7
+        emit_lut_plane(O, 16, cpl, F, 0x07FFFFFFu, s0, s0h, s1, s1h);     // DestroyTrefoil Down  s7 -> 7
+        // counts of the own-status classes from single-bit flags
+        uint32_t mono = 0, anch = 0;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t n = k.cn[j];
+            const uint32_t e0 = n & ONESN, e1 = (n >> 1) & ONESN, e2 = (n >> 2) & ONESN, e3 = (n >> 3) & ONESN;
+            mono += __popc((e0 ^ e1) & ~(e2 | e3));
+            anch += __popc((e2 & ~(e0 | e1 | e3)) | (e0 & e1 & e2 & ~e3));
+        }
+        n_mono = mono; n_anch = anch;
+        n_zero = __popc(k.c[1].zero) + __popc(k.c[2].zero);
+        n_div = __popc(k.c[1].div) + __popc(k.c[2].div);
+    }
+    NibAcc acc = {0, 0, 0, 0};
+    emit_move_plane_n<0>(k, O, cpl, acc); emit_move_plane_n<1>(k, O, cpl, acc); emit_move_plane_n<2>(k, O, cpl, acc);
+    emit_move_plane_n<3>(k, O, cpl, acc); emit_move_plane_n<4>(k, O, cpl, acc); emit_move_plane_n<5>(k, O, cpl, acc);
+    uint32_t n_tref;
+    {
+        uint32_t u[2], d[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const uint32_t both = k.c[j + 1].div & k.q[j + 1];
+            u[j] = both & nshr(k.c[j + 1].div, k.c[j + 2].div, 2);
+            d[j] = both & nshl(k.q[j], k.q[j + 1], 2);
+        }
+        n_tref = __popc(u[0]) + __popc(u[1]) + __popc(d[0]) + __popc(d[1]);
+        emit_lut_plane(O, 13, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, u[0], u[0] >> 16, u[1], u[1] >> 16);
+        emit_lut_plane(O, 14, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, d[0], d[0] >> 16, d[1], d[1] >> 16);
+    }
+    // K2: this thread's 13 class counts as 16-bit pairs, pooled per row
+    uint32_t pk[7];
+    {
+        const uint32_t P = nib_sum(acc.pres), PN = nib_sum(acc.pn), PF = nib_sum(acc.pf), PNF = nib_sum(acc.pnf);
+        const uint32_t met = PN - PNF, cmb = PF - PNF, nat = P - PN - PF + PNF;
+        pk[0] = n_zero | (n_div << 16);                           // classes 0, 1
+        pk[1] = nat | (met << 16);                                // 2, 3
+        pk[2] = cmb | (PNF << 16);                                // 4, 5
+        pk[3] = n_tref | (n_anch << 16);                          // 6, 7
+        pk[4] = (2 * n_zero) | (n_mono << 16);                    // 8, 9
+        pk[5] = n_mono | ((2 * n_div) << 16);                     // 10, 11
+        pk[6] = n_mono;                                           // 12
+    }
+    const uint32_t mask = cpr >= 32 ? 0xFFFFFFFFu : __match_any_sync(0xFFFFFFFFu, row_local);
+#pragma unroll
+    for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+    __syncthreads();                                              // rows_sm zeroed by everyone
+    if ((__ffs(mask) - 1) == lane) {
+        uint32_t *R = rows_sm + row_local * RCG_STRIDE;
+#pragma unroll
+        for (int j = 0; j < 7; j++) {
+            const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
+            if (lo) atomicAdd(R + 2 * j, lo);
+            if (hi) atomicAdd(R + 2 * j + 1, hi);
+        }
+    }
+    __syncthreads();
+    {
+        const int first_row = a - row_local;
+        uint32_t *G = p.rowcnt + ((size_t)rep * d0 + first_row) * RCG_STRIDE;
+        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
+    }
+    if (tid < 32) {
+        unsigned long long s = 0;
+        if (tid < NC)
+            for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
+        if (p.ctas_per_replica == 1) {
+            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
+        } else {
+            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+            __syncwarp();
+            unsigned int last = 0;
+            if (tid == 0) {
+                __threadfence();
+                last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
+                if (last) __threadfence();
+            }
+            last = __shfl_sync(0xFFFFFFFFu, last, 0);
+            if (last) {
+                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid == 0) p.ticket[rep] = 0u;
+            }
+        }
+    }
+}
+#endif  // __CUDACC__
+
 // Generic path (any d1 >= 5): one thread per site, scalar evaluation.
 __global__ void __launch_bounds__(256) kmc_sweep_kernel_generic(const SweepParams p)
 {

@@ -58,6 +58,7 @@ SYMBOLS = {
     "kmc_get_device_pointers": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_void_p)] * 4),
     "kmc_set_warps_per_block": (C.c_int, [C.c_void_p, C.c_int]),
     "kmc_set_replica_kernel": (C.c_int, [C.c_void_p, C.c_int]),
+    "kmc_set_sweep_kernel": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None

@@ -160,3 +160,7 @@ class Engine:
     def set_replica_kernel(self, variant):
         """0 auto, 1 byte-lattice kernel, 2 bit-sliced kernel (rows of <= 64 sites)."""
         nat.check(self._lib.kmc_set_replica_kernel(self._h, int(variant)))
+
+    def set_sweep_kernel(self, variant):
+        """Aligned-shape sweep kernel: 0 nibble-parallel + PRMT tables (default), 1 byte-parallel."""
+        nat.check(self._lib.kmc_set_sweep_kernel(self._h, int(variant)))

@@ -145,9 +145,11 @@ def test_stats_only_mode_equals_logged_mode():
 
 @pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (256, 256), (7, 130), (16, 16),
                                  (128, 32), (512, 4096), (8, 8192)])
-def test_sweep_matches_oracle(dim):
+@pytest.mark.parametrize("variant", [0, 1])
+def test_sweep_matches_oracle(dim, variant):
     sts = [evolved_state(dim, 3) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3), iid_state(dim, 4)]
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
+    eng.set_sweep_kernel(variant)
     eng.upload_state(np.stack(sts))
     eng.sweep()
     slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
@@ -166,6 +168,7 @@ def test_sweep_full_size_4096():
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=1)
     eng.upload_state(st)
     eng.sweep()
+    eng.sweep()             # twice: the running-total / ticket state must return to zero between launches
     ws, wc, wr = ko.sweep(st, dim)
     assert (eng.counts()[0] == wc).all()
     assert (eng.row_counts()[0] == wr).all()

@@ -14,6 +14,7 @@ def lib():
     L = nat.load()
     L.kmc_hostcheck_sweep_words.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.kmc_hostcheck_sweep_words16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.kmc_hostcheck_sweep_nibbles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.kmc_hostcheck_eval_sites.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.kmc_hostcheck_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]
@@ -38,13 +39,13 @@ def test_sweep_words_match_oracle(lib, dim, seed):
 
 @pytest.mark.parametrize("dim,seed", [((8, 16), 1), ((16, 16), 2), ((5, 32), 3), ((64, 64), 4), ((7, 48), 5),
                                       ((40, 80), 6)])
-def test_sweep_words16_match_oracle(lib, dim, seed):
+@pytest.mark.parametrize("fn", ["kmc_hostcheck_sweep_words16", "kmc_hostcheck_sweep_nibbles"])
+def test_sweep_words16_match_oracle(lib, dim, seed, fn):
     for st in (evolved_state(dim, seed), iid_state(dim, seed), np.full(dim[0] * dim[1], 3, np.uint8)):
         n = st.size
         slots = np.empty((17, n), dtype=np.uint8)
         counts = np.zeros(13, dtype=np.int64)
-        assert lib.kmc_hostcheck_sweep_words16(st.ctypes.data, dim[0], dim[1], slots.ctypes.data,
-                                               counts.ctypes.data) == 0
+        assert getattr(lib, fn)(st.ctypes.data, dim[0], dim[1], slots.ctypes.data, counts.ctypes.data) == 0
         want_slots, want_counts, _ = ko.sweep(st, dim)
         assert (slots.T == want_slots).all()
         assert (counts == want_counts).all()
