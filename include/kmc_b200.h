@@ -137,6 +137,9 @@ int kmc_reset_stats(kmc_engine *h);
 
 /* measurement helpers: CUDA events recorded on the handle's stream */
 int kmc_sync(kmc_engine *h);
+/* overwrite `bytes` (0 = 256 MiB, > the 126 MB L2) of scratch on the handle's stream, asynchronously:
+ * evicts L2 between timed launches without a host round trip */
+int kmc_flush_l2(kmc_engine *h, size_t bytes);
 int kmc_timer_start(kmc_engine *h);
 int kmc_timer_stop(kmc_engine *h, float *elapsed_ms);   /* synchronises */
 /* number of kernels this library has launched on the handle so far */

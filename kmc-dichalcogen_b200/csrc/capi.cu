@@ -49,6 +49,7 @@ struct kmc_engine {
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
     int *d_result = nullptr;
+    void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes
     int sweep_variant = 0;                   // 0 nibble/PRMT kernel, 1 byte-parallel kernel (aligned shapes)
@@ -129,7 +130,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
-    cudaFree(h->d_acc); cudaFree(h->d_ticket);
+    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -526,6 +527,19 @@ extern "C" int kmc_sync(kmc_engine *h)
 {
     int rc = bind(h); if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+extern "C" int kmc_flush_l2(kmc_engine *h, size_t bytes)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (bytes == 0) bytes = (size_t)256 << 20;
+    if (bytes > h->flush_bytes) {
+        if (h->d_flush) CU(cudaFree(h->d_flush));
+        h->d_flush = nullptr; h->flush_bytes = 0;
+        CU(cudaMalloc(&h->d_flush, bytes));
+        h->flush_bytes = bytes;
+    }
+    CU(cudaMemsetAsync(h->d_flush, 0, bytes, h->stream));     // asynchronous, on the handle's stream
     return KMC_OK;
 }
 extern "C" int kmc_timer_start(kmc_engine *h)

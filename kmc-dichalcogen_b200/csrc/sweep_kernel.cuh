@@ -400,6 +400,82 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
 }
 #endif  // __CUDACC__
 
+#ifdef __CUDACC__
+// K2 epilogue shared by the aligned kernels: per-row class counts from each thread's 16-bit count
+// pairs, plain row stores, class totals via running totals + ticket (last CTA of a replica publishes).
+__device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint32_t *rows_sm, uint32_t pk[7],
+                                                    int tid, int lane, int cpr, int rows_in_cta, int row_local,
+                                                    int rep, int a)
+{
+    if (cpr >= 32) {
+        // every warp lies inside one row: warp sums go to per-warp slots, no zeroing, no atomics
+#pragma unroll
+        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
+        if (lane < 7) {
+            uint32_t v = pk[0];
+#pragma unroll
+            for (int j = 1; j < 7; j++) v = lane == j ? pk[j] : v;
+            rows_sm[256 * RCG_STRIDE / 2 + (tid >> 5) * 8 + lane] = v;     // scratch in the upper half
+        }
+        __syncthreads();
+        const int wpr = cpr >> 5;                                          // warps per row
+        if (tid < rows_in_cta * RCG_STRIDE) {
+            const int r = tid >> 4, f = tid & 15;
+            uint32_t s = 0;
+            if (f < 2 * 7)
+                for (int w = 0; w < wpr; w++) {
+                    const uint32_t v = rows_sm[256 * RCG_STRIDE / 2 + (r * wpr + w) * 8 + (f >> 1)];
+                    s += (f & 1) ? (v >> 16) : (v & 0xFFFFu);
+                }
+            rows_sm[tid] = f < NC ? s : 0u;
+        }
+        __syncthreads();
+    } else {
+        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, row_local);
+#pragma unroll
+        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+        __syncthreads();                                                   // rows_sm zeroed by everyone
+        if ((__ffs(mask) - 1) == lane) {
+            uint32_t *R = rows_sm + row_local * RCG_STRIDE;
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
+                if (lo) atomicAdd(R + 2 * j, lo);
+                if (hi) atomicAdd(R + 2 * j + 1, hi);
+            }
+        }
+        __syncthreads();
+    }
+    {
+        const int first_row = a - row_local;
+        uint32_t *G = p.rowcnt + ((size_t)rep * p.d0 + first_row) * RCG_STRIDE;
+        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
+    }
+    if (tid < 32) {
+        unsigned long long s = 0;
+        if (tid < NC)
+            for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
+        if (p.ctas_per_replica == 1) {
+            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
+        } else {
+            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+            __syncwarp();
+            unsigned int last = 0;
+            if (tid == 0) {
+                __threadfence();
+                last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
+                if (last) __threadfence();
+            }
+            last = __shfl_sync(0xFFFFFFFFu, last, 0);
+            if (last) {
+                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid == 0) p.ticket[rep] = 0u;
+            }
+        }
+    }
+}
+#endif
+
 // ---- 16 sites per thread, nibble-parallel arithmetic, PRMT table output --------------------------------
 // Second-generation aligned kernel.  The byte-parallel version above is bound by the ALU pipe (LOP3/SHF
 // issue at half rate), not by HBM.  Here the 16 status bytes of a thread are packed to 4-bit fields
@@ -519,7 +595,8 @@ __global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Param
         const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
         const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
         const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
-        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+        if (cpr < 32)
+            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
         k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
         k.c[0] = nzd(pack_nib(0u, c_prev)); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]);
         k.c[3] = nzd(pack_nib(c_next, 0u));
@@ -587,47 +664,7 @@ __global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Param
         pk[5] = n_mono | ((2 * n_div) << 16);                     // 10, 11
         pk[6] = n_mono;                                           // 12
     }
-    const uint32_t mask = cpr >= 32 ? 0xFFFFFFFFu : __match_any_sync(0xFFFFFFFFu, row_local);
-#pragma unroll
-    for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
-    __syncthreads();                                              // rows_sm zeroed by everyone
-    if ((__ffs(mask) - 1) == lane) {
-        uint32_t *R = rows_sm + row_local * RCG_STRIDE;
-#pragma unroll
-        for (int j = 0; j < 7; j++) {
-            const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
-            if (lo) atomicAdd(R + 2 * j, lo);
-            if (hi) atomicAdd(R + 2 * j + 1, hi);
-        }
-    }
-    __syncthreads();
-    {
-        const int first_row = a - row_local;
-        uint32_t *G = p.rowcnt + ((size_t)rep * d0 + first_row) * RCG_STRIDE;
-        for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
-    }
-    if (tid < 32) {
-        unsigned long long s = 0;
-        if (tid < NC)
-            for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
-        if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
-        } else {
-            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
-            __syncwarp();
-            unsigned int last = 0;
-            if (tid == 0) {
-                __threadfence();
-                last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
-                if (last) __threadfence();
-            }
-            last = __shfl_sync(0xFFFFFFFFu, last, 0);
-            if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
-                if (tid == 0) p.ticket[rep] = 0u;
-            }
-        }
-    }
+    row_counts_epilogue(p, rows_sm, pk, tid, lane, cpr, rows_in_cta, row_local, rep, a);
 }
 #endif  // __CUDACC__
 

@@ -136,6 +136,9 @@ class Engine:
     def sync(self):
         nat.check(self._lib.kmc_sync(self._h))
 
+    def flush_l2(self, nbytes=0):
+        nat.check(self._lib.kmc_flush_l2(self._h, int(nbytes)))
+
     def timer_start(self):
         nat.check(self._lib.kmc_timer_start(self._h))
 

@@ -25,11 +25,9 @@ for l in lines[start + 1:]:
     if m:
         f = m.group(1).split("/")[-1]
         cur = "%s:%s" % (f, m.group(2))
-        if "inlined at" in m.group(3):
-            m2 = re.search(r'inlined at "([^"]+)", line (\d+)', m.group(3))
-            outer = "%s:%s" % (m2.group(1).split("/")[-1], m2.group(2)) if m2 else None
-        else:
-            outer = None
+        chain = re.findall(r'inlined at "([^"]+)", line (\d+)', m.group(3))
+        # outermost frame = the line of the kernel body this instruction belongs to
+        outer = "%s:%s" % (chain[-1][0].split("/")[-1], chain[-1][1]) if chain else cur
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
@@ -40,6 +38,7 @@ hdr = rows[1]
 ia, ii, isrc = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("Source")
 ist = hdr.index("Warp Stall Sampling (All Samples)")
 base = int(rows[2][ia], 16)
+per_outer = defaultdict(float)
 per_line = defaultdict(float)
 per_line_stall = defaultdict(float)
 per_op = defaultdict(float)
@@ -55,6 +54,7 @@ for r in rows[2:]:
     st = float(r[ist] or 0)
     c, o, txt = loc.get(off, ("?", None, r[isrc]))
     per_line[c] += n
+    per_outer[o or c] += n
     per_line_stall[c] += st
     per_op[txt.split()[0] if not txt.startswith("@") else txt.split()[1]] += n
     tot += n
@@ -64,6 +64,10 @@ print("--- by source line (>= %.1f per unit) ---   instr/unit   stall-sample sha
 for k, v in sorted(per_line.items(), key=lambda kv: -kv[1]):
     if v / div >= minv:
         print("%-32s %8.1f   %5.1f%%" % (k, v / div, 100 * per_line_stall[k] / max(tot_st, 1)))
+print("--- by kernel-body line (inlined callees folded into their call site; use nvdisasm --print-line-info-inline) ---")
+for k, v in sorted(per_outer.items(), key=lambda kv: kv[0]):
+    if v / div >= minv / 2:
+        print("%-32s %8.1f" % (k, v / div))
 print("--- by opcode ---")
 for k, v in sorted(per_op.items(), key=lambda kv: -kv[1])[:25]:
     print("%-24s %8.1f" % (k, v / div))
