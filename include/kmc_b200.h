@@ -149,7 +149,9 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
                             void **histogram);
 /* tuning knobs: warps (replicas) per CTA of the replica kernel, 0 = automatic (max 8); and which
  * replica kernel runs: 0 = automatic (bit-sliced lattice when dim1 <= 64, byte lattice otherwise),
- * 1 = byte lattice, 2 = bit-sliced.  Both produce identical results. */
+ * 1 = byte lattice in shared memory, 2 = bit-sliced, 3 = byte lattice left in HBM/L2 with only the
+ * row-count hierarchy in shared memory (chosen automatically when the lattice does not fit, e.g.
+ * 1024x1024).  All produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
 /* aligned-shape sweep kernel: 0 = nibble-parallel + PRMT tables (default), 1 = byte-parallel */

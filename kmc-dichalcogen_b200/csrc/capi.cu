@@ -51,7 +51,7 @@ struct kmc_engine {
     int *d_result = nullptr;
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
-    int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes
+    int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
     int sweep_variant = 0;                   // 0 nibble/PRMT kernel, 1 byte-parallel kernel (aligned shapes)
     long long launches = 0;
     bool swept = false;
@@ -354,9 +354,17 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
     if (log_mode != KMC_LOG_NONE && !host_events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
     // rows of <= 64 sites run on the bit-sliced kernel, wider rows on the byte-lattice kernel
-    const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64);
+    const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64 &&
+                                               replica_bp_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (bitplanes && h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernel needs dim1 <= 64");
-    const size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1);
+    size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1);
+    // lattices that do not fit shared memory stay in HBM/L2; only the row-count hierarchy is staged
+    const bool global_state = h->variant == 3 || (!bitplanes && wbytes > (size_t)h->max_smem_optin);
+    if (global_state) {
+        if (bitplanes) return fail(KMC_ERR_ARG, "variant 3 (HBM-resident lattice) uses the byte-lattice kernel");
+        wbytes = replica_rc_bytes(h->d0);
+        if (h->d1 > 10000) return fail(KMC_ERR_ARG, "rows longer than 10000 sites overflow the 16-bit row counts: use kmc_run_noinc");
+    }
     if (wbytes > (size_t)h->max_smem_optin) {
         char b[256];
         snprintf(b, sizeof b, "lattice %dx%d needs %zu B of shared memory per replica (limit %d): use kmc_run_noinc",
@@ -388,6 +396,8 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (bitplanes) {
         if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>));
         else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0>));
+    } else if (global_state) {
+        KMC_LAUNCH((kmc_replica_kernel<0, 0, true>));
     } else {
         if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_kernel<64, 64>));
         else KMC_LAUNCH((kmc_replica_kernel<0, 0>));
@@ -585,7 +595,8 @@ extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
 }
 extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)
 {
-    if (!h || variant < 0 || variant > 2) return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice) or 2 (bit planes)");
+    if (!h || variant < 0 || variant > 3)
+        return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice), 2 (bit planes) or 3 (byte lattice in HBM)");
     h->variant = variant;
     return KMC_OK;
 }

@@ -44,9 +44,8 @@ __global__ void __launch_bounds__(32) kmc_noinc_select_apply_kernel(const NoincP
     kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
 
     const double w = __dmul_rn((double)tot, rate);
-    int sc = lane & 15;
-    bool need_sort = true;
-    const ClassPick pick = pick_class(w, pos, sc, need_sort, u1, lane);
+    PickState pstate = pick_state_init(lane);
+    const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
     const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
     if (p.log_mode == KMC_LOG_FULL && lane < NC)
         (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = (uint32_t)tot;

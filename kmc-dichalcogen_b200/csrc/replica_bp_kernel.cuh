@@ -154,6 +154,44 @@ __device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane) {
     return 2 * L + (int)!(((m >> (2 * L)) & 1ull) && idx == below);
 }
 
+// Rule.perform + nodes_affected_by as a table (reference demo1/rules.py perform()/nodes_affected_by of the
+// 8 rules): per slot, how the anchor's status changes and which other nodes change to what.
+//   word0: [0:4) or-mask, [4:8) and-mask, [8:12) xor-mask of the anchor status  (new = ((s | or) & and) ^ xor)
+//          [12:14) number of touched nodes
+//   word1: [0:4) da1+2 [4:8) db1+2 [8:12) da2+2 [12:16) db2+2 [16:20) new1 [20:24) new2 [24:28) old1 [28:32) old2
+struct MoveEntry { uint32_t w0, w1; };
+constexpr MoveEntry make_move_entry(int slot) {
+    uint32_t orm = 0, andm = 0, xorm = 0, na = 1;
+    int da1 = 0, db1 = 0, da2 = 0, db2 = 0;
+    uint32_t n1 = 0, n2 = 0, o1 = 0, o2 = 0;
+    if (slot == 0) { xorm = 3; }                                    // -> divacancy
+    else if (slot == 1) { }                                         // -> pristine
+    else if (slot <= 3) { orm = slot - 1; andm = 0xF; }             // s | layer
+    else if (slot <= 5) { andm = 0xF & ~(uint32_t)(slot - 3); }     // s & ~layer
+    else if (slot == 6) { andm = 0xF; xorm = 3; }                   // flip layer
+    else if (slot <= 12) {                                          // MoveDivacancy: target = nbr_k
+        constexpr int NA[6] = {-1, 0, 1, 0, -1, 1}, NB[6] = {1, -1, 0, 1, 0, -1};
+        da1 = NA[slot - 7]; db1 = NB[slot - 7]; na = 2; n1 = 3; o1 = 0;
+    } else {
+        const int o = (slot - 13) & 1;
+        const bool create = slot < 15;
+        na = 3; da1 = 2; db1 = 0; da2 = o ? 2 : 0; db2 = o ? -2 : 2;
+        xorm = create ? 4 + 3 * o : 3;
+        n1 = create ? 4 + 3 * o + 1 : 3; n2 = create ? 4 + 3 * o + 2 : 3;
+        o1 = create ? 3 : 4 + 3 * o + 1; o2 = create ? 3 : 4 + 3 * o + 2;
+    }
+    MoveEntry e = {0, 0};
+    e.w0 = orm | (andm << 4) | (xorm << 8) | (na << 12);
+    e.w1 = (uint32_t)(da1 + 2) | ((uint32_t)(db1 + 2) << 4) | ((uint32_t)(da2 + 2) << 8) | ((uint32_t)(db2 + 2) << 12) |
+           (n1 << 16) | (n2 << 20) | (o1 << 24) | (o2 << 28);
+    return e;
+}
+__constant__ MoveEntry MOVE_TABLE[NS] = {
+    make_move_entry(0), make_move_entry(1), make_move_entry(2), make_move_entry(3), make_move_entry(4),
+    make_move_entry(5), make_move_entry(6), make_move_entry(7), make_move_entry(8), make_move_entry(9),
+    make_move_entry(10), make_move_entry(11), make_move_entry(12), make_move_entry(13), make_move_entry(14),
+    make_move_entry(15), make_move_entry(16)};
+
 // position of the (n)-th set bit (0-based) of a small mask; n is warp-uniform and tiny
 __device__ __forceinline__ int nth_bit_small(uint32_t m, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) m &= m - 1;
@@ -227,8 +265,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     // own-status classes: 2 bits per status = moves of my class a site of that status carries
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
     unsigned long long hist = 0, n_ties = 0;
-    int sc = lane & 15;
-    bool need_sort = true;
+    PickState pstate = pick_state_init(lane);
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
     const int my_j = lane / 6, my_k = lane % 6;
     const DirConst my_dir = dir_const(my_k, d0);
@@ -260,7 +297,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
 
         // ---- 1./2. weights and class choice (sim.py:120-122, kmc.py:21-54) ----------------------
         const double w = __dmul_rn((double)tot, rate);
-        const ClassPick pick = pick_class(w, pos, sc, need_sort, u1, lane);
+        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
         if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && lane == 0) {
@@ -387,15 +424,21 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         if (pick.tie && lane == 0) n_ties++;
 
         // ---- 4. the move (uniform): touched nodes, old and new status --------------------------------
-        const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
-        const int na = mv.na;
-        int os1 = 0, os2 = 0;                      // old status of nodes 1, 2 (node 0: s0)
-        if (slot >= 13) {
-            const bool create = slot < 15;
-            const int o = (slot - 13) & 1;
-            os1 = create ? S_DIVAC : S_TREF + 3 * o + 1;
-            os2 = create ? S_DIVAC : S_TREF + 3 * o + 2;
+        MoveNodes mv;
+        int os1, os2;                              // old status of nodes 1, 2 (node 0: s0)
+        {
+            const MoveEntry e = MOVE_TABLE[slot];
+            mv.ns0 = (int)((((uint32_t)s0 | (e.w0 & 0xF)) & ((e.w0 >> 4) & 0xF)) ^ ((e.w0 >> 8) & 0xF));
+            mv.na = (int)((e.w0 >> 12) & 3);
+            mv.da1 = (int)(e.w1 & 0xF) - 2;
+            mv.a1 = wrapT<TD0>(row + mv.da1, d0);
+            mv.b1 = wrapT<TD1>(col + (int)((e.w1 >> 4) & 0xF) - 2, d1);
+            mv.a2 = wrapT<TD0>(row + (int)((e.w1 >> 8) & 0xF) - 2, d0);
+            mv.b2 = wrapT<TD1>(col + (int)((e.w1 >> 12) & 0xF) - 2, d1);
+            mv.ns1 = (int)((e.w1 >> 16) & 0xF); mv.ns2 = (int)((e.w1 >> 20) & 0xF);
+            os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
+        const int na = mv.na;
         // bit planes: lane q < 10 maintains plane q (program order handles nodes sharing a row)
         if (lane < N_PLANES) {
             {

@@ -67,6 +67,9 @@ struct SmemStatus {
     __device__ __forceinline__ int operator()(int i) const { return p[i]; }
 };
 
+__host__ __device__ inline size_t replica_rc_bytes(int d0) {
+    return ((size_t)d0 * RC_WORDS * 4 + 15) & ~(size_t)15;
+}
 __host__ __device__ inline size_t replica_warp_bytes(int d0, int d1) {
     size_t n = (size_t)d0 * d1;
     size_t a = (n + 15) & ~(size_t)15;
@@ -92,19 +95,29 @@ __device__ __forceinline__ bool warp_rank_search(uint32_t v, uint32_t &r, int &L
 }
 
 // weighted_choice (reference demo1/kmc.py:21-54) over 16 lanes holding (weight, input position).
-// `sc` (lanes 0..15) is the class held at each sorted position; it persists between events and is
-// re-derived only when the (weight, position) order actually changed.
+// State kept across events (PickState): `sc` (lanes 0..15) = class held at each sorted position,
+// `spos` = sorted position of the lane's own class, `wprev` = the lane's weight at the previous event,
+// `cum` (lanes 0..15) = cumulative weight at the lane's sorted position.  The order is re-derived only when
+// the (weight, position) order actually changed, and the sequential prefix sums are recomputed only from
+// the first sorted position whose weight changed -- everything before it is bit-identical by construction.
+struct PickState { int sc, spos; double wprev, cum; bool need_sort; };
+__device__ __forceinline__ PickState pick_state_init(int lane) {
+    PickState s; s.sc = lane & 15; s.spos = lane & 15; s.wprev = -1.0; s.cum = 0.0; s.need_sort = true; return s;
+}
 struct ClassPick { int csel; double total; uint32_t tie; bool zero; };
-__device__ __forceinline__ ClassPick pick_class(double w, int pos, int &sc, bool &need_sort, double u1, int lane)
+__device__ __forceinline__ ClassPick pick_class(double w, int pos, PickState &st, double u1, int lane)
 {
-    double ws = __shfl_sync(FULL, w, sc);
-    int ps = __shfl_sync(FULL, pos, sc);
+    double ws = __shfl_sync(FULL, w, st.sc);
+    const int ps = __shfl_sync(FULL, pos, st.sc);
+    // first sorted position whose weight differs from the previous event
+    int first = (int)__reduce_min_sync(FULL, (lane < 16 && w != st.wprev) ? (unsigned)st.spos : 16u);
+    st.wprev = w;
     {
         // is the previous order still (w, pos)-sorted?  (almost always)
         const double wp = __shfl_up_sync(FULL, ws, 1);
         const int pp = __shfl_up_sync(FULL, ps, 1);
         const bool ok = (lane == 0) || (lane > 15) || (wp < ws) || (wp == ws && pp < ps);
-        if (need_sort || !__all_sync(FULL, ok)) {
+        if (st.need_sort || !__all_sync(FULL, ok)) {
             // stable ascending sort (kmc.py:35) as a rank sort of the 16 unique (w, pos) keys
             int rank = 0;
             for (int j = 0; j < 16; j++) {
@@ -112,12 +125,14 @@ __device__ __forceinline__ ClassPick pick_class(double w, int pos, int &sc, bool
                 const int pj = __shfl_sync(FULL, pos, j);
                 rank += (wj < w) || (wj == w && pj < pos);
             }
+            st.spos = rank;
             for (int j = 0; j < 16; j++) {
                 const int rj = __shfl_sync(FULL, rank, j);
-                if (rj == lane) sc = j;
+                if (rj == lane) st.sc = j;
             }
-            need_sort = false;
-            ws = __shfl_sync(FULL, w, sc);
+            st.need_sort = false;
+            ws = __shfl_sync(FULL, w, st.sc);
+            first = 0;
         }
     }
     ClassPick out;
@@ -125,19 +140,22 @@ __device__ __forceinline__ ClassPick pick_class(double w, int pos, int &sc, bool
     // sequential sum simply starts after them
     const int z = __popc(__ballot_sync(FULL, ws == 0.0) & 0xFFFFu);
     out.zero = (z == 16);
-    double acc = 0.0, cum = 0.0;
-    for (int k = z; k < 16; k++) {
+    const int start = first > z ? first : z;
+    double acc = __shfl_sync(FULL, st.cum, (start + 15) & 15);       // cumulative weight just before `start`
+    if (start == z) acc = 0.0;
+    for (int k = start; k < 16; k++) {
         const double wk = __shfl_sync(FULL, ws, k);
         acc = __dadd_rn(acc, wk);                              // util.py:65-68: sequential sums
-        if (lane == k) cum = acc;
+        if (lane == k) st.cum = acc;
     }
+    if (start == 16) acc = __shfl_sync(FULL, st.cum, 15);     // nothing changed: total is the old one
     out.total = acc;
     const double x = __dmul_rn(acc, u1);                       // random.uniform(0, total), kmc.py:49
     const bool live = (lane >= z) && (lane < 16);
-    const uint32_t ge = __ballot_sync(FULL, live && cum >= x); // bisect_left, kmc.py:50
+    const uint32_t ge = __ballot_sync(FULL, live && st.cum >= x); // bisect_left, kmc.py:50
     const int isel = ge ? (__ffs(ge) - 1) : 15;
-    out.tie = __ballot_sync(FULL, live && cum == x);
-    out.csel = __shfl_sync(FULL, sc, isel);
+    out.tie = __ballot_sync(FULL, live && st.cum == x);
+    out.csel = __shfl_sync(FULL, st.sc, isel);
     return out;
 }
 
@@ -224,7 +242,9 @@ __device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int
     out[0] = A0; out[1] = B0; out[2] = A1; out[3] = B1; out[4] = A2; out[5] = B2; out[6] = A3;
 }
 
-template <int TD0, int TD1>
+// GLOBAL_STATE = true: the lattice stays in HBM/L2 (lattices too large for shared memory, e.g.
+// 1024x1024 = 1 MiB per replica, BASELINE config 5); only the row-count hierarchy is in shared memory.
+template <int TD0, int TD1, bool GLOBAL_STATE = false>
 __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
@@ -237,14 +257,22 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     if (rep >= p.n_replicas) return;       // whole warp exits together; no block barriers are used
 
     extern __shared__ uint4 smem_raw[];
-    const size_t wbytes = replica_warp_bytes(d0, d1);
-    uint8_t *st = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * wbytes;
-    uint32_t *rc = reinterpret_cast<uint32_t *>(st + (((size_t)n + 15) & ~(size_t)15));
+    uint8_t *gst = p.status + (size_t)rep * n;
+    uint8_t *st;
+    uint32_t *rc;
+    if (GLOBAL_STATE) {
+        st = gst;
+        rc = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_rc_bytes(d0));
+    } else {
+        st = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_warp_bytes(d0, d1);
+        rc = reinterpret_cast<uint32_t *>(st + (((size_t)n + 15) & ~(size_t)15));
+    }
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(rc);
 
     // ---- load the lattice ------------------------------------------------------------------
-    uint8_t *gst = p.status + (size_t)rep * n;
-    if ((n & 15) == 0) {
+    if (GLOBAL_STATE) {
+        // nothing to stage
+    } else if ((n & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(gst);
         uint4 *dst = reinterpret_cast<uint4 *>(st);
         for (int i = lane; i < (n >> 4); i += 32) dst[i] = src[i];
@@ -273,8 +301,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     }
     unsigned long long hist = 0;
     unsigned long long n_ties = 0;
-    int sc = lane & 15;                    // class held at sorted position `lane` (lanes 0..15)
-    bool need_sort = true;
+    PickState pstate = pick_state_init(lane);
 
     // per-lane role in the refresh: node index and one of 10 offsets
     const int my_i = lane / 10, my_o = lane % 10;
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const double w = __dmul_rn((double)tot, rate);       // lanes >= 13: tot = 0, rate = 0
 
         // ---- 2. class choice -------------------------------------------------------------------
-        const ClassPick pick = pick_class(w, pos, sc, need_sort, u1, lane);
+        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
         if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && lane == 0) {
@@ -524,7 +551,9 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         }
         if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
     }
-    if ((n & 15) == 0) {
+    if (GLOBAL_STATE) {
+        // the lattice was updated in place
+    } else if ((n & 15) == 0) {
         uint4 *dst = reinterpret_cast<uint4 *>(gst);
         const uint4 *src = reinterpret_cast<const uint4 *>(st);
         for (int i = lane; i < (n >> 4); i += 32) dst[i] = src[i];

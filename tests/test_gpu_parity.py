@@ -106,10 +106,11 @@ def test_replicas_match_oracle(dim, rates, order, nrep, nsteps):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("dim", [(64, 64), (33, 47), (5, 5), (9, 64), (130, 7), (16, 20)])
 def test_both_replica_kernels_match_oracle(dim, variant):
-    """The byte-lattice kernel (1) and the bit-sliced kernel (2) on the same lattices."""
+    """The byte-lattice kernel (1), the bit-sliced kernel (2) and the byte-lattice kernel with the
+    lattice left in HBM (3) on the same lattices."""
     nrep, nsteps, seed = 3, 6000, 99
     st0 = np.stack([evolved_state(dim, 20 + r, nsteps=300) for r in range(nrep)])
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
@@ -123,6 +124,24 @@ def test_both_replica_kernels_match_oracle(dim, variant):
         assert_events_equal(ev[r], want, "variant %d replica %d" % (variant, r))
         assert (ev[r]["counts"] == want["counts"]).all()
         assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (final[r] == o.status()).all()
+    eng.close()
+
+
+def test_large_lattice_incremental_1024():
+    """BASELINE config 5 shape: 1024x1024 lattices (1 MiB each) do not fit shared memory; the incremental
+    kernel keeps them in HBM/L2 and only the row hierarchy on chip."""
+    dim, nrep, nsteps = (1024, 1024), 3, 3000
+    st0 = np.stack([exact_state(dim, 0.05, 0.05, 300 + r) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.upload_state(st0)
+    ev = eng.run(nsteps, 77, log_mode=nat.LOG_FULL, validate=True)
+    final = eng.download_state()
+    for r in range(nrep):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
+        _, want = o.run_philox(77, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "1024^2 replica %d" % r)
+        assert (ev[r]["counts"] == want["counts"]).all()
         assert (final[r] == o.status()).all()
     eng.close()
 
