@@ -172,7 +172,7 @@ int kmc_set_sweep_kernel(kmc_engine *h, int variant);
  *   10 FillMonovacancy:make-double  (:257-274)
  *   11 FillMonovacancy:from-empty
  *   12 FlipMonovacancy:natural      (:277-293)
- * In-class order (the rank the in-class draw indexes): site ascending, then slot ascending.
+ * In-class order (the rank the in-class draw indexes): row ascending, then slot ascending, then column.
  */
 
 #ifdef __cplusplus

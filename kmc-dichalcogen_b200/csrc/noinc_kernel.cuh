@@ -83,54 +83,11 @@ __global__ void __launch_bounds__(32) kmc_noinc_select_apply_kernel(const NoincP
         row = base + L;
         break;
     }
-    // site search inside the row
-    int col = 0;
-    const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
-    const uint32_t g1c = g1_const(csel);
-    for (int base = 0; base < d1; base += 32) {
-        const int b = base + lane;
-        uint32_t v = 0;
-        if (b < d1) {
-            v = group == 0 ? site_class_count<0>(st, row, b, d0, d1, csel, g1c)
-              : group == 1 ? site_class_count<1>(st, row, b, d0, d1, csel, g1c)
-                           : site_class_count<2>(st, row, b, d0, d1, csel, g1c);
-        }
-        int L;
-        if (warp_rank_search(v, r, L, lane)) { col = base + L; break; }
-    }
+    // site and slot inside the row (row, slot, column order)
+    int col, slot;
+    find_in_row_bytes(st, d0, d1, row, csel, r, lane, col, slot);
     const int site = row * d1 + col;
     const int s0 = st[site];
-    int slot;
-    if (group == 0) {
-        switch (csel) {
-            case C_CREATE_DIV: slot = 0; break;
-            case C_FILL_DIV: slot = 1; break;
-            case C_DESTROY_TREF: slot = (s0 == S_TREF) ? 15 : 16; break;
-            case C_CMONO_FROM_DOUBLE: slot = 2 + (int)r; break;
-            case C_CMONO_MAKE_EMPTY: slot = 1 + (3 & ~s0); break;
-            case C_FMONO_MAKE_DOUBLE: slot = 3 + s0; break;
-            case C_FMONO_FROM_EMPTY: slot = 4 + (int)r; break;
-            default: slot = 6; break;
-        }
-    } else if (group == 1) {
-        const int am = wrap_dec(row - 1, d0), ap = wrap_inc(row + 1, d0);
-        const int bm = wrap_dec(col - 1, d1), bp = wrap_inc(col + 1, d1);
-        RingMasks m = ring_masks(st[am * d1 + col], st[row * d1 + bm], st[ap * d1 + bm], st[ap * d1 + col],
-                                 st[row * d1 + bp], st[am * d1 + bp]);
-        const uint32_t km = kind_mask(m, csel - C_MOVE_DIV);
-        slot = 7;
-        int q = (int)r;
-#pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int bit = (km >> kring(k)) & 1;
-            if (bit && q == 0) slot = 7 + k;
-            q -= bit;
-        }
-    } else {
-        const int ap2 = wrap_inc(row + 2, d0), bp2 = wrap_inc(col + 2, d1);
-        const bool up = (st[ap2 * d1 + col] == S_DIVAC) && (st[row * d1 + bp2] == S_DIVAC);
-        slot = (up && r == 0) ? 13 : 14;
-    }
     __syncwarp();
     if (lane == 0) {
         apply_move(st, d0, d1, row, col, slot, s0);

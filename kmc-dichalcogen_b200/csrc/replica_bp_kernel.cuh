@@ -145,7 +145,7 @@ __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, cons
 }
 
 // position of the (idx)-th set bit (0-based) of a row mask, found by 32 lanes in parallel:
-// lane l counts the set bits below site 2l+2.  Returns the column; *before = set bits below it.
+// lane l counts the set bits below site 2l+2.  Returns the column.
 __device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane) {
     const uint32_t c = __popcll(m & RowBits<64>::low(2 * lane + 2));
     const uint32_t ball = __ballot_sync(FULL, c > idx);
@@ -268,7 +268,11 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     PickState pstate = pick_state_init(lane);
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
     const int my_j = lane / 6, my_k = lane % 6;
-    const DirConst my_dir = dir_const(my_k, d0);
+    DirConst my_dir = dir_const(my_k, d0);
+    // keep the six per-lane constants in registers: ptxas otherwise re-derives them from my_k inside the
+    // event loop (~30 instructions per event, profiles/round1_r6_replica_bp_by_line.txt)
+    asm volatile("" : "+r"(my_dir.off_n), "+r"(my_dir.da_n), "+r"(my_dir.off_e), "+r"(my_dir.da_e),
+                      "+r"(my_dir.off_f), "+r"(my_dir.da_f));
     // plane maintenance role: lane q < 10 keeps plane q; a site's bit sits at column col + my_cshift
     const int my_ptype = lane < N_PLANES ? (int)((PLANE_TYPE >> (4 * lane)) & 0xF) : -1;
     const int my_cshift = lane < N_PLANES ? (int)((PLANE_CSHIFT >> (4 * lane)) & 0xF) - 1 : 0;
@@ -344,64 +348,63 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
                 break;
             }
         }
-        // 3b/3c. site within the row and slot within the site
+        // 3b/3c. slot, then site, within the row (canonical order: row, slot, column)
         int col, slot, s0;
         if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
-            // lanes 0..5 derive their direction's kind mask for this row, everyone gets all six
+            // lanes 0..5 hold their direction's kind mask for this row; a 6-lane prefix picks the direction
             u64 pr, ne, fa;
             dir_masks<TD0>(PL, d0, row, my_dir, pr, ne, fa);
             const u64 mine = lane < 6 ? kind_select(pr, ne, fa, csel - C_MOVE_DIV) : 0ull;
-            const u64 lowm = RowBits<64>::low(2 * lane + 2);
-            uint32_t c = 0;
-#pragma unroll
-            for (int k = 0; k < 6; k++) c += __popcll(__shfl_sync(FULL, mine, k) & lowm);
-            const uint32_t ball = __ballot_sync(FULL, c > r);
-            const int L = __ffs(ball) - 1;
-            const uint32_t cprev = __shfl_sync(FULL, c, (L + 31) & 31);
-            uint32_t rem = r - (L ? cprev : 0u);
-            // directions present at sites 2L and 2L+1, as 6-bit masks in k order
-            const uint32_t m0 = __ballot_sync(FULL, (mine >> (2 * L)) & 1ull) & 0x3Fu;
-            const uint32_t m1 = __ballot_sync(FULL, (mine >> (2 * L + 1)) & 1ull) & 0x3Fu;
-            const uint32_t n0 = __popc(m0);
-            uint32_t km = m0;
-            col = 2 * L;
-            if (rem >= n0) { rem -= n0; km = m1; col++; }
-            slot = 7 + nth_bit_small(km, rem);
+            const uint32_t cntk = __popcll(mine);
+            uint32_t pre = cntk, t1;
+            t1 = __shfl_up_sync(FULL, pre, 1); if (lane >= 1) pre += t1;
+            t1 = __shfl_up_sync(FULL, pre, 2); if (lane >= 2) pre += t1;
+            t1 = __shfl_up_sync(FULL, pre, 4); if (lane >= 4) pre += t1;
+            const int ksel = __ffs(__ballot_sync(FULL, pre > r) & 0x3Fu) - 1;
+            const uint32_t rem = r - __shfl_sync(FULL, pre - cntk, ksel);
+            col = nth_set_bit(__shfl_sync(FULL, mine, ksel), rem, lane);
+            slot = 7 + ksel;
             s0 = S_DIVAC;
         } else if (csel == C_CREATE_TREF) {
             u64 up, dn;
             trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
-            const u64 lowm = RowBits<64>::low(2 * lane + 2);
-            const uint32_t c = __popcll(up & lowm) + __popcll(dn & lowm);
-            const uint32_t ball = __ballot_sync(FULL, c > r);
-            const int L = __ffs(ball) - 1;
-            const u64 lowL = RowBits<64>::low(2 * L);
-            uint32_t rem = r - (__popcll(up & lowL) + __popcll(dn & lowL));
-            const uint32_t u0 = (uint32_t)(up >> (2 * L)) & 1u, w0 = (uint32_t)(dn >> (2 * L)) & 1u;
-            const uint32_t u1b = (uint32_t)(up >> (2 * L + 1)) & 1u;
-            col = 2 * L;
-            if (rem >= u0 + w0) { rem -= u0 + w0; col++; slot = (u1b && rem == 0) ? 13 : 14; }
-            else slot = (u0 && rem == 0) ? 13 : 14;
+            const uint32_t nu = __popcll(up);
+            const bool second = r >= nu;
+            col = nth_set_bit(second ? dn : up, second ? r - nu : r, lane);
+            slot = 13 + (int)second;
             s0 = S_DIVAC;
         } else {
-            // own-status classes: the sites are one plane (or the union of two), 1 or 2 moves per site
-            const bool two = (csel == C_CMONO_FROM_DOUBLE) || (csel == C_FMONO_FROM_EMPTY);
-            const int pa = (csel == C_CREATE_DIV || csel == C_CMONO_FROM_DOUBLE) ? PL_Z
-                         : (csel == C_FILL_DIV || csel == C_FMONO_FROM_EMPTY) ? PL_D
-                         : (csel == C_DESTROY_TREF) ? PL_A4 : PL_M1;
-            const u64 first = PL[pa * d0 + row];
-            const u64 m = (pa == PL_A4 || pa == PL_M1) ? (first | PL[(pa + 1) * d0 + row]) : first;
-            col = nth_set_bit(m, two ? (r >> 1) : r, lane);
-            const bool in_first = (first >> col) & 1ull;
+            // own-status classes: one or two slots, each slot's sites are one plane (or a union)
+            //   class:        0   1   7    8   9    10   11  12
+            //   first slot:   Z   D   A4   Z   M2   M1   D   M1|M2
+            //   second slot:  -   -   A7   Z   M1   M2   D   -
+            int pa, pb = -1;
             switch (csel) {
-                case C_CREATE_DIV: slot = 0; s0 = 0; break;
-                case C_FILL_DIV: slot = 1; s0 = 3; break;
-                case C_DESTROY_TREF: s0 = in_first ? 4 : 7; slot = in_first ? 15 : 16; break;
-                case C_CMONO_FROM_DOUBLE: slot = 2 + (int)(r & 1); s0 = 0; break;
-                case C_CMONO_MAKE_EMPTY: s0 = in_first ? 1 : 2; slot = 1 + (3 & ~s0); break;
-                case C_FMONO_MAKE_DOUBLE: s0 = in_first ? 1 : 2; slot = 3 + s0; break;
-                case C_FMONO_FROM_EMPTY: slot = 4 + (int)(r & 1); s0 = 3; break;
-                default: s0 = in_first ? 1 : 2; slot = 6; break;
+                case C_CREATE_DIV: pa = PL_Z; break;
+                case C_FILL_DIV: pa = PL_D; break;
+                case C_DESTROY_TREF: pa = PL_A4; pb = PL_A7; break;
+                case C_CMONO_FROM_DOUBLE: pa = PL_Z; pb = PL_Z; break;
+                case C_CMONO_MAKE_EMPTY: pa = PL_M2; pb = PL_M1; break;
+                case C_FMONO_MAKE_DOUBLE: pa = PL_M1; pb = PL_M2; break;
+                case C_FMONO_FROM_EMPTY: pa = PL_D; pb = PL_D; break;
+                default: pa = PL_M1; break;
+            }
+            u64 ma = PL[pa * d0 + row];
+            const u64 mb = pb >= 0 ? PL[pb * d0 + row] : 0ull;
+            if (csel == C_FLIP) ma |= PL[PL_M2 * d0 + row];
+            const uint32_t n1 = __popcll(ma);
+            const bool second = r >= n1;
+            const u64 m = second ? mb : ma;
+            col = nth_set_bit(m, second ? r - n1 : r, lane);
+            slot = class_slot_base(csel) + (int)second;
+            // status of the chosen site before the event
+            switch (csel) {
+                case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0 = 0; break;
+                case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0 = 3; break;
+                case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
+                case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
+                case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
+                default: s0 = ((PL[PL_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
             }
         }
         const int site = row * d1 + col;

@@ -228,6 +228,75 @@ __device__ __forceinline__ void apply_move(uint8_t *st, int d0, int d1, int row,
     if (m.na > 2) st[m.a2 * d1 + m.b2] = (uint8_t)m.ns2;
 }
 
+// ---- in-class pick inside one row, byte lattice ---------------------------------------------------------
+// Canonical in-class order: rows ascending; inside a row the class's move slots in slot order; inside a
+// slot the sites by column.  A class owns 1, 2 or 6 slots: slot = class_slot_base(c) + bit index.
+__device__ __forceinline__ int class_slot_base(int c) {
+    //            c: 0  1  2  3  4  5  6   7   8  9  10 11 12
+    return (int)((0x6442'2FD7'7771'0ull >> (4 * c)) & 0xF);
+}
+// bit i set: the site carries the class's i-th slot
+__device__ __forceinline__ uint32_t site_slot_mask(const uint8_t *st, int a, int b, int d0, int d1, int c) {
+    const int s0 = st[a * d1 + b];
+    if (c >= C_MOVE_DIV && c < C_MOVE_DIV + 4) {
+        if (s0 != S_DIVAC) return 0u;
+        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
+        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
+        RingMasks m = ring_masks(st[am * d1 + b], st[a * d1 + bm], st[ap * d1 + bm], st[ap * d1 + b],
+                                 st[a * d1 + bp], st[am * d1 + bp]);
+        const uint32_t km = kind_mask(m, c - C_MOVE_DIV);          // by ring position
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) out |= ((km >> kring(k)) & 1u) << k;   // by direction k = slot - 7
+        return out;
+    }
+    if (c == C_CREATE_TREF) {
+        if (s0 != S_DIVAC) return 0u;
+        const int ap2 = wrap_inc(a + 2, d0), bp2 = wrap_inc(b + 2, d1), bm2 = wrap_dec(b - 2, d1);
+        const uint32_t t20 = st[ap2 * d1 + b] == S_DIVAC;
+        return (t20 & (uint32_t)(st[a * d1 + bp2] == S_DIVAC)) | ((t20 & (uint32_t)(st[ap2 * d1 + bm2] == S_DIVAC)) << 1);
+    }
+    switch (c) {
+        case C_CREATE_DIV: return s0 == 0;
+        case C_FILL_DIV: return s0 == 3;
+        case C_DESTROY_TREF: return (uint32_t)(s0 == 4) | ((uint32_t)(s0 == 7) << 1);       // slots 15, 16
+        case C_CMONO_FROM_DOUBLE: return s0 == 0 ? 3u : 0u;                                // slots 2, 3
+        case C_CMONO_MAKE_EMPTY: return (uint32_t)(s0 == 2) | ((uint32_t)(s0 == 1) << 1);   // slot 2 (layer 1), 3
+        case C_FMONO_MAKE_DOUBLE: return (uint32_t)(s0 == 1) | ((uint32_t)(s0 == 2) << 1);  // slot 4 (layer 1), 5
+        case C_FMONO_FROM_EMPTY: return s0 == 3 ? 3u : 0u;                                 // slots 4, 5
+        default: return s0 == 1 || s0 == 2;                                                // FlipMonovacancy
+    }
+}
+// the r-th move (0-based) of class c in row `row`: column and slot.  Two passes over the row: per-slot
+// totals, then a rank search among the sites of the chosen slot.
+__device__ __forceinline__ void find_in_row_bytes(const uint8_t *st, int d0, int d1, int row, int c, uint32_t r,
+                                                  int lane, int &col, int &slot) {
+    uint32_t a01 = 0, a23 = 0, a45 = 0;                     // six 16-bit per-slot counters
+    for (int base = 0; base < d1; base += 32) {
+        const int b = base + lane;
+        const uint32_t m = b < d1 ? site_slot_mask(st, row, b, d0, d1, c) : 0u;
+        a01 += (m & 1u) | ((m & 2u) << 15);
+        a23 += ((m >> 2) & 1u) | ((m & 8u) << 13);
+        a45 += ((m >> 4) & 1u) | ((m & 32u) << 11);
+    }
+    a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
+    int j = 0;
+    {
+        const uint32_t cnt[6] = {a01 & 0xFFFFu, a01 >> 16, a23 & 0xFFFFu, a23 >> 16, a45 & 0xFFFFu, a45 >> 16};
+#pragma unroll
+        for (int q = 0; q < 5; q++)
+            if (j == q && r >= cnt[q]) { r -= cnt[q]; j = q + 1; }
+    }
+    col = 0;
+    for (int base = 0; base < d1; base += 32) {
+        const int b = base + lane;
+        const uint32_t v = b < d1 ? ((site_slot_mask(st, row, b, d0, d1, c) >> j) & 1u) : 0u;
+        int L;
+        if (warp_rank_search(v, r, L, lane)) { col = base + L; break; }
+    }
+    slot = class_slot_base(c) + j;
+}
+
 // per-row class counts of row `a`, as 7 pair-words (two uint16 fields each)
 __device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int d1, uint32_t out[RC_WORDS]) {
     SmemStatus S{st};
@@ -391,67 +460,11 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
                 }
             }
         }
-        // 3b. site within the row: two sites per lane per pass
-        int col = 0;
-        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
-        {
-            const uint32_t g1c = g1_const(csel);
-            for (int base = 0; base < d1; base += 64) {
-                const int b0 = base + 2 * lane;
-                uint32_t v0 = 0, v1 = 0;
-                if (group == 0) {
-                    if (b0 < d1) v0 = site_class_count<0>(st, row, b0, d0, d1, csel, g1c);
-                    if (b0 + 1 < d1) v1 = site_class_count<0>(st, row, b0 + 1, d0, d1, csel, g1c);
-                } else if (group == 1) {
-                    if (b0 < d1) v0 = site_class_count<1>(st, row, b0, d0, d1, csel, g1c);
-                    if (b0 + 1 < d1) v1 = site_class_count<1>(st, row, b0 + 1, d0, d1, csel, g1c);
-                } else {
-                    if (b0 < d1) v0 = site_class_count<2>(st, row, b0, d0, d1, csel, g1c);
-                    if (b0 + 1 < d1) v1 = site_class_count<2>(st, row, b0 + 1, d0, d1, csel, g1c);
-                }
-                int L;
-                if (warp_rank_search(v0 + v1, r, L, lane)) {
-                    const uint32_t v0L = __shfl_sync(FULL, v0, L);
-                    col = base + 2 * L;
-                    if (r >= v0L) { r -= v0L; col++; }
-                    break;
-                }
-            }
-        }
-        // 3c. slot within the site (uniform across the warp)
+        // 3b/3c. site within the row and slot (row, slot, column order)
+        int col, slot;
+        find_in_row_bytes(st, d0, d1, row, csel, r, lane, col, slot);
         const int site = row * d1 + col;
         const int s0 = st[site];
-        int slot;
-        if (group == 0) {
-            switch (csel) {
-                case C_CREATE_DIV: slot = 0; break;
-                case C_FILL_DIV: slot = 1; break;
-                case C_DESTROY_TREF: slot = (s0 == S_TREF) ? 15 : 16; break;
-                case C_CMONO_FROM_DOUBLE: slot = 2 + (int)r; break;
-                case C_CMONO_MAKE_EMPTY: slot = 1 + (3 & ~s0); break;
-                case C_FMONO_MAKE_DOUBLE: slot = 3 + s0; break;
-                case C_FMONO_FROM_EMPTY: slot = 4 + (int)r; break;
-                default: slot = 6; break;
-            }
-        } else if (group == 1) {
-            const int am = wrap_dec(row - 1, d0), ap = wrap_inc(row + 1, d0);
-            const int bm = wrap_dec(col - 1, d1), bp = wrap_inc(col + 1, d1);
-            RingMasks m = ring_masks(st[am * d1 + col], st[row * d1 + bm], st[ap * d1 + bm], st[ap * d1 + col],
-                                     st[row * d1 + bp], st[am * d1 + bp]);
-            const uint32_t km = kind_mask(m, csel - C_MOVE_DIV);
-            slot = 7;
-            int rr = (int)r;
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                const int bit = (km >> kring(k)) & 1;
-                if (bit && rr == 0) slot = 7 + k;
-                rr -= bit;
-            }
-        } else {
-            const int ap2 = wrap_inc(row + 2, d0), bp2 = wrap_inc(col + 2, d1);
-            const bool up = (st[ap2 * d1 + col] == S_DIVAC) && (st[row * d1 + bp2] == S_DIVAC);
-            slot = (up && r == 0) ? 13 : 14;
-        }
 
         // ---- event record, part 2 ------------------------------------------------------------------
         if (p.log_mode != KMC_LOG_NONE && lane == 0) {

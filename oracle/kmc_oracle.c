@@ -27,7 +27,8 @@
  * in oracle/ref_oracle.py:
  *   - tie-break among equal class weights: position in `class_order` (rules in config order,
  *     kinds in rule.kinds() order); the reference uses Counter insertion order (sim.py:101);
- *   - in-class pick: rank min((int)(u2*n), n-1) in (site, slot) order; the reference picks
+ *   - in-class pick: rank min((int)(u2*n), n-1) in (row, slot, column) order, i.e. rows ascending, inside
+ *     a row the move slots in slot order, inside a slot the sites by column; the reference picks
  *     rng.choice() from a list whose order is a swap-remove artefact (incremental.py:283-326).
  * The probability law is the reference's (uniform within a class).
  *
@@ -332,18 +333,19 @@ int kmco_step(KmcOracle *o, double u1, double u2, KmcoEvent *ev)
     for (int i = 0; i < n; i++) tie |= (cum[i] == x);
     int c = cls[sel];
 
-    /* in-class pick: canonical rank (site-major, slot-minor) */
+    /* in-class pick: canonical rank order (row, slot, column) */
     int64_t cnt = o->count[c];
     int64_t r = (int64_t)(u2 * (double)cnt);
     if (r > cnt - 1) r = cnt - 1;
     int row = 0;
     while (r >= o->rowcnt[row * NC + c]) { r -= o->rowcnt[row * NC + c]; row++; }
     int site = -1, slot = -1;
-    for (int b = 0; b < o->d1 && site < 0; b++) {
-        const uint8_t *sl = o->slot + ((size_t)row * o->d1 + b) * NS;
-        for (int j = 0; j < NS; j++)
-            if (sl[j] == c) { if (r == 0) { site = row * o->d1 + b; slot = j; break; } r--; }
-    }
+    for (int j = 0; j < NS && site < 0; j++)
+        for (int b = 0; b < o->d1; b++)
+            if (o->slot[((size_t)row * o->d1 + b) * NS + j] == c) {
+                if (r == 0) { site = row * o->d1 + b; slot = j; break; }
+                r--;
+            }
     if (ev) {
         ev->site = (uint32_t)site; ev->cls = (uint8_t)c; ev->slot = (uint8_t)slot;
         ev->flags = (uint16_t)tie; ev->total_naive = total;
@@ -361,9 +363,12 @@ int kmco_step(KmcOracle *o, double u1, double u2, KmcoEvent *ev)
 /* Same pick, but by a linear scan of the whole slot table (no row hierarchy): cross-check only. */
 int kmco_rank_to_move_scan(const KmcOracle *o, int c, int64_t r, int *site, int *slot)
 {
-    for (int i = 0; i < o->n; i++)
+    for (int a = 0; a < o->d0; a++)
         for (int j = 0; j < NS; j++)
-            if (o->slot[(size_t)i * NS + j] == c) { if (r == 0) { *site = i; *slot = j; return 0; } r--; }
+            for (int b = 0; b < o->d1; b++) {
+                const int i = a * o->d1 + b;
+                if (o->slot[(size_t)i * NS + j] == c) { if (r == 0) { *site = i; *slot = j; return 0; } r--; }
+            }
     return 1;
 }
 

@@ -14,7 +14,7 @@ What is the reference's and what is ours:
                               of CPython's ``random.uniform``)
 * class order fed to it       OURS: canonical = rules in config order x ``rule.kinds()`` order
                               (the reference's order is Counter-insertion history, sim.py:101)
-* in-class pick               OURS: ``sorted(moves, key=(site, slot))[min(int(u2 * n), n - 1)]``
+* in-class pick               OURS: ``sorted(moves, key=(row, slot, column))[min(int(u2 * n), n - 1)]``
                               (the reference's list order is a swap-remove artefact, incremental.py:306)
 * mutation + refresh          reference: ``KmcSim.perform_given_move`` (sim.py:145-157)
 * total_rate                  reference formula: ``math.fsum`` of the weights (sim.py:138)
@@ -213,11 +213,16 @@ class RefStepper:
         (rule, kind) = self.mods["kmc"].weighted_choice(k_w_pairs, rng=rng)
 
         moves = rule.move_cache.undecided_sets()[frozenset([kind])]
-        keyed = sorted((canon.slot_from_move(rule.format(), m, self.dim), m) for m in moves)
+        d1 = self.dim[1]
+        keyed = []
+        for m in moves:
+            site, slot = canon.slot_from_move(rule.format(), m, self.dim)
+            keyed.append(((site // d1, slot, site % d1), site, slot, m))     # (row, slot, column) order
+        keyed.sort(key=lambda t: t[0])
         n = len(keyed)
         assert n == counts[(rule, kind)]
         idx = min(int(u2 * n), n - 1)
-        (site, slot), move = keyed[idx]
+        _, site, slot, move = keyed[idx]
 
         # boundary-tie bookkeeping: x landed exactly on a cumulative weight
         ws = sorted(w for (_, w) in k_w_pairs if w != 0.0)
