@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             if (lane < NC) rec->counts[lane] = (uint32_t)tot;
         }
 
-        // ---- 3. in-class pick: rank in (site, slot) order ------------------------------------------
+        // ---- 3. in-class pick: rank in (row, slot, column) order -----------------------------------
         const int cnt = __shfl_sync(FULL, tot, csel);
         uint32_t r;
         {

@@ -11,8 +11,8 @@
 //   1. weights w_c = count_c * rate_c                       (sim.py:120-121)
 //   2. class choice: weighted_choice bit for bit            (kmc.py:21-54, util.py:32-46,65-68):
 //      drop zeros, stable ascending sort, sequential fp64 prefix sums, x = total*u1, bisect_left
-//   3. in-class pick: rank floor(u2*count) in (site, slot) order -- hierarchical search
-//      rows -> sites of the row -> slots of the site   (replaces get_random_key, incremental.py:283)
+//   3. in-class pick: rank floor(u2*count) in (row, slot, column) order -- hierarchical search
+//      rows -> slots of the class -> sites of the row   (replaces get_random_key, incremental.py:283)
 //   4. apply the move                                        (rules.py perform())
 //   5. refresh the neighbourhood: every site whose moves can depend on the touched nodes has its
 //      13 class counts re-derived before and after the mutation; the difference goes to the row
