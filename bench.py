@@ -121,6 +121,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def recorded_traffic():
+    """dram bytes read + written per sweep launch, from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -205,6 +214,7 @@ def main():
     ap.add_argument("--warps-per-block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     ap.add_argument("--sweep-iters", type=int, default=20)
     args = ap.parse_args()
     if args.warmup < 3:
@@ -309,10 +319,52 @@ def main():
         achieved = nsites * SWEEP_BYTES_PER_SITE / (avg_ms * 1e-3) / 1e9
         roofline = {"kernel": "kmc_sweep16n_kernel (K1+K2, 4096x4096 full rate sweep)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "bytes_per_site": SWEEP_BYTES_PER_SITE,
+                    "traffic": (recorded_traffic() or {}).get("dram_bytes_per_launch"),
+                    "traffic_source": (recorded_traffic() or {}).get("source"), "peak_source": peak_src, "bytes_per_site": SWEEP_BYTES_PER_SITE,
                     "ms_per_sweep": avg_ms, "ms_min": float(np.min(ms)), "sites_per_s": nsites / (avg_ms * 1e-3),
                     "note": "timed region = exactly one launch (slot planes + row counts + class totals in one kernel), CUDA events on the engine's stream, L2 flushed before each launch"}
         launches += sweep_launches
+
+    # ---- the other BASELINE configs, briefly (parity-test shapes; reported for context, rank 0 only) ------
+    other = None
+    if rank == 0 and not args.no_other_configs:
+        other = {}
+        # configs[1]: 64x64, ONE trajectory, incremental (latency-bound: one warp on one SM)
+        one = Engine(DIM, rates, order, n_replicas=1, device=local)
+        one.upload_state(synthetic_lattices(1, 0))
+        one.run(20000, SEED)
+        one.sync()
+        one.timer_start()
+        one.run(500000, SEED)
+        ms1 = one.timer_stop()
+        one.close()
+        other["64x64_single_trajectory_incremental"] = {"events_per_s": 500000 / (ms1 * 1e-3), "events": 500000}
+        # configs[3] end to end: one `--no-incremental` event on 4096^2 = count-only sweep + select + apply
+        big = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
+        big.upload_state(iid_lattice(SWEEP_DIM, SEED))
+        big.run_noinc(5, SEED)
+        big.sync()
+        big.timer_start()
+        big.run_noinc(40, SEED)
+        msn = big.timer_stop()
+        big.close()
+        other["4096x4096_no_incremental_event"] = {"events_per_s": 40 / (msn * 1e-3), "ms_per_event": msn / 40,
+                                                   "launches_per_event": 2}
+        # configs[4] shape: 1024x1024 lattices stay in HBM/L2, row hierarchy in shared memory
+        nrep5, ev5 = 128, 4000
+        lat = Engine((1024, 1024), rates, order, n_replicas=nrep5, device=local)
+        rng = np.random.Generator(np.random.Philox(SEED))
+        base = rng.choice(np.arange(4, dtype=np.uint8), size=1024 * 1024, p=(0.90, 0.025, 0.025, 0.05)).astype(np.uint8)
+        lat.upload_state(np.tile(base, (nrep5, 1)))
+        lat.run(200, SEED)
+        lat.sync()
+        lat.timer_start()
+        lat.run(ev5, SEED)
+        ms5 = lat.timer_stop()
+        lat.close()
+        other["1024x1024_x128_replicas_incremental"] = {
+            "events_per_s": nrep5 * ev5 / (ms5 * 1e-3), "replicas": nrep5, "events_per_replica": ev5,
+            "note": "includes the per-launch rebuild of the row hierarchy (a full enumeration of 1 Mi sites per replica)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,6 +395,7 @@ def main():
                                "events_per_s_per_sm": per_sm, "sm_cycles_per_event": sm_clock / per_sm,
                                "hbm_bytes_per_event_algorithmic": 2.0 * DIM[0] * DIM[1] / E},
             "cpu_baseline": cpu,
+            "other_configs": other,
             "event_histogram": [int(x) for x in hist],
         }
         print(json.dumps(line), flush=True)

@@ -152,9 +152,10 @@ class KmcSim:
         }
 
     def perform_given_move(self, rule, move):
-        """Apply an explicit move, given as (site, slot) (reference sim.py:145-157)."""
+        """Apply an explicit move (reference sim.py:145-157).  ``move`` is either the reference's own
+        key for that rule (node / (node, layer, new) / (old, new) / three nodes) or a (site, slot) pair."""
         self._discard_lookahead()
-        site, slot = move
+        site, slot = T.slot_of_move(rule, move, self.state.dim)
         if T.SLOT_RULE[slot] != rule:
             raise ValueError("slot %d does not belong to rule %s" % (slot, rule))
         self._engine.perform_given(0, site, slot)

@@ -64,3 +64,63 @@ def move_info(site, slot, dim):
         return {"was": list(p), "now": list(add(p, MOVE_TARGET[slot - 7], dim))}
     orient = (slot - 13) & 1
     return {"nodes": [list(add(p, off, dim)) for off in TREFOIL_MEMBERS[orient]]}
+
+
+def slot_of_move(rule, move, dim):
+    """(site, slot) of a move given in the reference's own key form (reference demo1/rules.py):
+    a node for Create/FillDivacancy and FlipMonovacancy, (node, layer, new_layerset) for
+    Create/FillMonovacancy, (old, new) for MoveDivacancy, an iterable of three nodes for the trefoil
+    rules.  A pair (site, slot) of ints is passed through."""
+    if (isinstance(move, tuple) and len(move) == 2 and all(isinstance(x, int) for x in move)
+            and rule not in ("CreateDivacancy", "FillDivacancy", "FlipMonovacancy")):
+        return move
+    lin = lambda node: (node[0] % dim[0]) * dim[1] + (node[1] % dim[1])
+    if rule in ("CreateDivacancy", "FillDivacancy", "FlipMonovacancy"):
+        return lin(move), {"CreateDivacancy": 0, "FillDivacancy": 1, "FlipMonovacancy": 6}[rule]
+    if rule == "CreateMonovacancy":
+        return lin(move[0]), 1 + move[1]
+    if rule == "FillMonovacancy":
+        return lin(move[0]), 3 + move[1]
+    if rule == "MoveDivacancy":
+        old, new = move
+        ks = [k for k in range(6) if add(old, MOVE_TARGET[k], dim) == add(new, (0, 0), dim)]
+        if len(ks) != 1:
+            raise ValueError("not a nearest-neighbour move: %r" % (move,))
+        return lin(old), 7 + ks[0]
+    if rule in ("CreateTrefoil", "DestroyTrefoil"):
+        want = set(add(tuple(n), (0, 0), dim) for n in move)
+        for p in want:
+            for orient in (0, 1):
+                if set(add(p, off, dim) for off in TREFOIL_MEMBERS[orient]) == want:
+                    return lin(p), (13 if rule == "CreateTrefoil" else 15) + orient
+        raise ValueError("nodes do not form a trefoil: %r" % (move,))
+    raise KeyError(rule)
+
+
+def replay_event(status, event, dim):
+    """Apply one logged event (the dict `perform_random_move` returns / the CLI writes) to a flat
+    status array: an independent restatement of the transition function, in the spirit of the
+    reference's animate.py replay (animate.py:82-141)."""
+    rule, mv = event["rule"], event["move"]
+    lin = lambda node: (node[0] % dim[0]) * dim[1] + (node[1] % dim[1])
+    if rule == "CreateDivacancy":
+        status[lin(mv["node"])] = 3
+    elif rule == "FillDivacancy":
+        status[lin(mv["node"])] = 0
+    elif rule == "CreateMonovacancy":
+        status[lin(mv["node"])] |= mv["layer"]
+    elif rule == "FillMonovacancy":
+        status[lin(mv["node"])] &= ~mv["layer"] & 0xFF
+    elif rule == "FlipMonovacancy":
+        status[lin(mv["node"])] ^= 3
+    elif rule == "MoveDivacancy":
+        status[lin(mv["was"])] = 0
+        status[lin(mv["now"])] = 3
+    elif rule in ("CreateTrefoil", "DestroyTrefoil"):
+        site, slot = slot_of_move(rule, [tuple(n) for n in mv["nodes"]], dim)
+        orient = (slot - 13) & 1
+        p = node_of(site, dim)
+        for role, off in enumerate(TREFOIL_MEMBERS[orient]):
+            status[lin(add(p, off, dim))] = (TREFOIL_BASE + 3 * orient + role) if rule == "CreateTrefoil" else 3
+    else:
+        raise KeyError(rule)

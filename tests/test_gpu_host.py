@@ -100,6 +100,41 @@ def test_cli_json_layout_matches_reference():
     assert [e["total_rate"] for e in doc["events"]] == list(g["events"]["total_rate"][:200])
 
 
+def test_cli_event_log_replays_to_the_final_lattice(tmp_path):
+    """the JSON log written by the CLI, replayed animate.py-style from the embedded
+    initial state, reproduces the lattice the device ends with."""
+    from demo1 import tables as T
+    cfg = os.path.join(PKG, "config", "mixed_rates.yaml")
+    doc = json.loads(run_cli([cfg, "-d", "12,10", "-n", "1500", "--seed", "11", "--embed-initial"]))
+    dim = tuple(doc["grid"]["dim"])
+    st = State.from_dict(doc["initial_state"]).status
+    for ev in doc["events"]:
+        T.replay_event(st, ev, dim)
+    # same trajectory through KmcSim, then read the device lattice
+    from demo1 import config
+    with open(cfg) as f:
+        c = config.from_dict(config.load_all([f]))
+    sim = KmcSim(State(dim), c["rule_specs"], seed=11, chunk=1500)
+    for _ in range(1500):
+        sim.perform_random_move()
+    assert (sim.current_state().status == st).all()
+    assert {e["rule"] for e in doc["events"]} >= {"CreateTrefoil", "DestroyTrefoil", "MoveDivacancy"}
+    sim.close()
+
+
+def test_perform_given_move_accepts_reference_keys():
+    st = State((8, 8))
+    st.new_divacancy((2, 2))
+    sim = KmcSim(st, [RuleSpec("MoveDivacancy", {"natural": 1.0, "missing-metal": 1.0, "missing-comb": 1.0,
+                                                  "missing-both": 1.0}, False)], seed=1, chunk=1)
+    sim.perform_given_move("MoveDivacancy", ((2, 2), (1, 3)))
+    now = sim.current_state()
+    assert now.is_divacancy((1, 3)) and now.is_pristine((2, 2))
+    with pytest.raises(RuntimeError, match="does not exist"):
+        sim.perform_given_move("MoveDivacancy", ((2, 2), (1, 3)))
+    sim.close()
+
+
 def test_cli_no_incremental_agrees_with_incremental():
     cfg = os.path.join(PKG, "config", "wse2_1500K.yaml")
     common = [cfg, "-T", "1500", "-d", "16,16", "-n", "120", "--seed", "3", "--state-seed", "4"]

@@ -141,3 +141,35 @@ def test_move_info_formats():
             assert sorted(map(tuple, mine["nodes"])) == sorted(map(tuple, info["move"]["nodes"]))
         else:
             assert mine == info["move"]
+
+
+def test_reference_move_keys_map_to_slots():
+    dim = (8, 8)
+    assert T.slot_of_move("CreateDivacancy", (1, 2), dim) == (10, 0)
+    assert T.slot_of_move("FlipMonovacancy", (1, 2), dim) == (10, 6)
+    assert T.slot_of_move("CreateMonovacancy", ((1, 2), 2, 2), dim) == (10, 3)
+    assert T.slot_of_move("FillMonovacancy", ((1, 2), 1, 2), dim) == (10, 4)
+    assert T.slot_of_move("MoveDivacancy", ((0, 0), (7, 1)), dim) == (0, 7)
+    assert T.slot_of_move("MoveDivacancy", (10, 9), dim) == (10, 9)              # (site, slot) passes through
+    assert T.slot_of_move("CreateTrefoil", frozenset([(7, 6), (1, 6), (1, 4)]), dim) == (62, 14)
+    assert T.slot_of_move("DestroyTrefoil", [(0, 0), (2, 0), (0, 2)], dim) == (0, 15)
+    with pytest.raises(ValueError):
+        T.slot_of_move("MoveDivacancy", ((0, 0), (3, 3)), dim)
+    # every (site, slot) round-trips through move_info for the single-node and pair rules
+    for site in (0, 9, 63):
+        for slot in range(7, 13):
+            info = T.move_info(site, slot, dim)
+            assert T.slot_of_move("MoveDivacancy", (tuple(info["was"]), tuple(info["now"])), dim) == (site, slot)
+
+
+def test_replay_of_a_golden_log_reproduces_the_reference_lattice():
+    """The event log alone determines the lattice (animate.py-style replay) -- on the reference's fixtures."""
+    for name in ("allrules_8x8", "wse2_hot_24x24", "allrules_40x70"):
+        g = load(name)
+        dim = tuple(g["meta"]["dim"])
+        st = g["status0"].copy()
+        for rec in g["events"]:
+            rule, _ = T.CLASSES[int(rec["cls"])]
+            ev = {"rule": rule, "move": T.move_info(int(rec["site"]), int(rec["slot"]), dim)}
+            T.replay_event(st, ev, dim)
+        assert (st == g["status1"]).all(), name
