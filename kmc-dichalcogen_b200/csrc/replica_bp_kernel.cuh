@@ -146,12 +146,16 @@ __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, cons
 
 // position of the (idx)-th set bit (0-based) of a row mask, found by 32 lanes in parallel:
 // lane l counts the set bits below site 2l+2.  Returns the column.
-__device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane) {
-    const uint32_t c = __popcll(m & RowBits<64>::low(2 * lane + 2));
+// `low_lo/low_hi` = this lane's constant mask of the sites below 2l+2.
+__device__ __forceinline__ int nth_set_bit(u64 m, uint32_t idx, int lane, uint32_t low_lo, uint32_t low_hi) {
+    const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32);
+    const uint32_t c = __popc(mlo & low_lo) + __popc(mhi & low_hi);
     const uint32_t ball = __ballot_sync(FULL, c > idx);
     const int L = __ffs(ball) - 1;
-    const uint32_t below = __popcll(m & RowBits<64>::low(2 * L));
-    return 2 * L + (int)!(((m >> (2 * L)) & 1ull) && idx == below);
+    const uint32_t below = __shfl_sync(FULL, c, (L + 31) & 31);          // count below site 2L (lane L-1)
+    const uint32_t half = L & 16 ? mhi : mlo;                            // sites 2L, 2L+1 live in one half
+    const uint32_t first = (half >> ((2 * L) & 31)) & 1u;
+    return 2 * L + (int)!(first && idx == (L ? below : 0u));
 }
 
 // Rule.perform + nodes_affected_by as a table (reference demo1/rules.py perform()/nodes_affected_by of the
@@ -273,6 +277,10 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     // event loop (~30 instructions per event, profiles/round1_r6_replica_bp_by_line.txt)
     asm volatile("" : "+r"(my_dir.off_n), "+r"(my_dir.da_n), "+r"(my_dir.off_e), "+r"(my_dir.da_e),
                       "+r"(my_dir.off_f), "+r"(my_dir.da_f));
+    // this lane's mask of the sites below column 2*lane + 2 (for popcount-select)
+    uint32_t my_low_lo = lane >= 15 ? 0xFFFFFFFFu : ((4u << (2 * lane)) - 1u);
+    uint32_t my_low_hi = lane < 16 ? 0u : (lane == 31 ? 0xFFFFFFFFu : ((4u << (2 * (lane - 16))) - 1u));
+    asm volatile("" : "+r"(my_low_lo), "+r"(my_low_hi));
     // plane maintenance role: lane q < 10 keeps plane q; a site's bit sits at column col + my_cshift
     const int my_ptype = lane < N_PLANES ? (int)((PLANE_TYPE >> (4 * lane)) & 0xF) : -1;
     const int my_cshift = lane < N_PLANES ? (int)((PLANE_CSHIFT >> (4 * lane)) & 0xF) - 1 : 0;
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             t1 = __shfl_up_sync(FULL, pre, 4); if (lane >= 4) pre += t1;
             const int ksel = __ffs(__ballot_sync(FULL, pre > r) & 0x3Fu) - 1;
             const uint32_t rem = r - __shfl_sync(FULL, pre - cntk, ksel);
-            col = nth_set_bit(__shfl_sync(FULL, mine, ksel), rem, lane);
+            col = nth_set_bit(__shfl_sync(FULL, mine, ksel), rem, lane, my_low_lo, my_low_hi);
             slot = 7 + ksel;
             s0 = S_DIVAC;
         } else if (csel == C_CREATE_TREF) {
@@ -370,7 +378,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
             const uint32_t nu = __popcll(up);
             const bool second = r >= nu;
-            col = nth_set_bit(second ? dn : up, second ? r - nu : r, lane);
+            col = nth_set_bit(second ? dn : up, second ? r - nu : r, lane, my_low_lo, my_low_hi);
             slot = 13 + (int)second;
             s0 = S_DIVAC;
         } else {
@@ -395,7 +403,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             const uint32_t n1 = __popcll(ma);
             const bool second = r >= n1;
             const u64 m = second ? mb : ma;
-            col = nth_set_bit(m, second ? r - n1 : r, lane);
+            col = nth_set_bit(m, second ? r - n1 : r, lane, my_low_lo, my_low_hi);
             slot = class_slot_base(csel) + (int)second;
             // status of the chosen site before the event
             switch (csel) {
@@ -442,25 +450,27 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
         const int na = mv.na;
-        // bit planes: lane q < 10 maintains plane q (program order handles nodes sharing a row)
+        // bit planes: lane q < 10 maintains plane q, as 32-bit halves (program order handles nodes
+        // sharing a word): clear the site's bit, set it again if the new status belongs to this plane
         if (lane < N_PLANES) {
+            uint32_t *P32 = reinterpret_cast<uint32_t *>(PL + lane * d0);
             {
-                u64 wv = PL[lane * d0 + row];
-                const u64 bit = 1ull << wrapT<TD1>(col + my_cshift, d1);
-                wv = (status_plane(mv.ns0) == my_ptype) ? (wv | bit) : (wv & ~bit);
-                PL[lane * d0 + row] = wv;
+                const int c = wrapT<TD1>(col + my_cshift, d1);
+                uint32_t *wp = P32 + 2 * row + (c >> 5);
+                const uint32_t bit = 1u << (c & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns0) == my_ptype ? bit : 0u);
             }
             if (na > 1) {
-                u64 wv = PL[lane * d0 + mv.a1];
-                const u64 bit = 1ull << wrapT<TD1>(mv.b1 + my_cshift, d1);
-                wv = (status_plane(mv.ns1) == my_ptype) ? (wv | bit) : (wv & ~bit);
-                PL[lane * d0 + mv.a1] = wv;
+                const int c = wrapT<TD1>(mv.b1 + my_cshift, d1);
+                uint32_t *wp = P32 + 2 * mv.a1 + (c >> 5);
+                const uint32_t bit = 1u << (c & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns1) == my_ptype ? bit : 0u);
             }
             if (na > 2) {
-                u64 wv = PL[lane * d0 + mv.a2];
-                const u64 bit = 1ull << wrapT<TD1>(mv.b2 + my_cshift, d1);
-                wv = (status_plane(mv.ns2) == my_ptype) ? (wv | bit) : (wv & ~bit);
-                PL[lane * d0 + mv.a2] = wv;
+                const int c = wrapT<TD1>(mv.b2 + my_cshift, d1);
+                uint32_t *wp = P32 + 2 * mv.a2 + (c >> 5);
+                const uint32_t bit = 1u << (c & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns2) == my_ptype ? bit : 0u);
             }
         }
         // ---- 5a. own-status classes: owner lanes fold (old -> new) of each touched node -----------------
