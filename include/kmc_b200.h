@@ -154,7 +154,8 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
  * 1024x1024).  All produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
-/* aligned-shape sweep kernel: 0 = nibble-parallel + PRMT tables (default), 1 = byte-parallel */
+/* aligned-shape sweep kernel: 0 = automatic (rolling window over rows when a row fills a CTA, i.e. 4096
+ * sites; else nibble-parallel + PRMT tables), 1 = nibble-parallel + PRMT, 2 = byte-parallel.  Same results. */
 int kmc_set_sweep_kernel(kmc_engine *h, int variant);
 
 /*

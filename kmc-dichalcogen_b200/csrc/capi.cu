@@ -52,7 +52,8 @@ struct kmc_engine {
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
-    int sweep_variant = 0;                   // 0 nibble/PRMT kernel, 1 byte-parallel kernel (aligned shapes)
+    int sweep_variant = 0;                   // aligned shapes: 0 auto (rolling window for 4096-site rows, else
+                                             // nibble/PRMT), 1 nibble/PRMT, 2 byte-parallel
     long long launches = 0;
     bool swept = false;
     int max_smem_optin = 0;
@@ -232,13 +233,32 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
             CU(cudaMemsetAsync(h->d_acc, 0, R * 16 * sizeof(unsigned long long), h->stream));
             CU(cudaMemsetAsync(h->d_ticket, 0, R * sizeof(unsigned int), h->stream));
         }
+        if (cpr == 256 && h->sweep_variant == 0) {
+            // rows that fill a CTA: rolling window over rows; pick rows per CTA so that the grid is about one
+            // full wave (148 SMs x 3 resident CTAs)
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+            const long long slots = (long long)sms * 3;
+            int rpc = (int)(((long long)R * h->d0 + slots - 1) / slots);
+            if (rpc < 1) rpc = 1;
+            if (rpc > ROLL_MAX_ROWS) rpc = ROLL_MAX_ROWS;
+            SweepRollParams q;
+            q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
+            q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
+            q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
+            q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc;
+            kmc_sweep_roll_kernel<<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            return KMC_OK;
+        }
         Sweep16Params q;
         q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
         q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
         q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
         q.ctas_per_replica = (h->n >> 4) / 256;
         const long long blocks = (long long)R * q.ctas_per_replica;
-        if (h->sweep_variant == 1) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        if (h->sweep_variant == 2) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         else kmc_sweep16n_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         CU(cudaGetLastError());
         h->launches += 1;
@@ -589,7 +609,8 @@ extern "C" int kmc_set_warps_per_block(kmc_engine *h, int warps)
 }
 extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
 {
-    if (!h || variant < 0 || variant > 1) return fail(KMC_ERR_ARG, "variant must be 0 (nibble/PRMT) or 1 (byte-parallel)");
+    if (!h || variant < 0 || variant > 2)
+        return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (nibble/PRMT, one row per CTA pass) or 2 (byte-parallel)");
     h->sweep_variant = variant;
     return KMC_OK;
 }

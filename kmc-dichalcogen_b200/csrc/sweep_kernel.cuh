@@ -566,46 +566,10 @@ __device__ __forceinline__ void emit_lut_plane(uint4 *O, size_t plane, size_t cp
     if (O) __stcs(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
 }
 
-__global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Params p)
+// all 17 slot planes of one 16-site chunk (stored through O, stride cpl between planes) and the chunk's
+// 13 class counts as seven 16-bit pairs
+__device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_t cpl, uint32_t pk[7])
 {
-    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
-    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
-    const int rows_in_cta = 256 / cpr;
-    const long long g = (long long)blockIdx.x * 256 + tid;
-    const int rep = (int)(g / cpl);
-    const int cl = (int)(g - (long long)rep * cpl);
-    const int a = cl / cpr, ci = cl - a * cpr;
-    const int row_local = tid / cpr;
-    const int d0 = p.d0;
-
-    Chunk16N k;
-    {
-        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
-        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
-        const uint8_t *S = p.status + (size_t)rep * p.n;
-        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
-        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
-        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
-        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
-        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
-        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
-        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
-        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
-        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
-        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
-        if (cpr < 32)
-            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
-        k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
-        k.c[0] = nzd(pack_nib(0u, c_prev)); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]);
-        k.c[3] = nzd(pack_nib(c_next, 0u));
-        k.m[0] = nzd(pack_nib(m4.x, m4.y)); k.m[1] = nzd(pack_nib(m4.z, m4.w)); k.m[2] = nzd(pack_nib(m_next, 0u));
-        k.p[0] = nzd(pack_nib(0u, p_prev)); k.p[1] = nzd(pack_nib(p4.x, p4.y)); k.p[2] = nzd(pack_nib(p4.z, p4.w));
-        k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
-        k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
-    }
-    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
     // own-status planes: table lookup by status (8, 9 -> 5, 6: all of 5, 6, 8, 9 carry no own-status move)
     uint32_t n_zero, n_div, n_mono, n_anch;
     {
@@ -652,7 +616,6 @@ __global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Param
         emit_lut_plane(O, 14, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, d[0], d[0] >> 16, d[1], d[1] >> 16);
     }
     // K2: this thread's 13 class counts as 16-bit pairs, pooled per row
-    uint32_t pk[7];
     {
         const uint32_t P = nib_sum(acc.pres), PN = nib_sum(acc.pn), PF = nib_sum(acc.pf), PNF = nib_sum(acc.pnf);
         const uint32_t met = PN - PNF, cmb = PF - PNF, nat = P - PN - PF + PNF;
@@ -664,8 +627,171 @@ __global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Param
         pk[5] = n_mono | ((2 * n_div) << 16);                     // 10, 11
         pk[6] = n_mono;                                           // 12
     }
+}
+
+__global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Params p)
+{
+    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
+    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
+    const int rows_in_cta = 256 / cpr;
+    const long long g = (long long)blockIdx.x * 256 + tid;
+    const int rep = (int)(g / cpl);
+    const int cl = (int)(g - (long long)rep * cpl);
+    const int a = cl / cpr, ci = cl - a * cpr;
+    const int row_local = tid / cpr;
+    const int d0 = p.d0;
+
+    Chunk16N k;
+    {
+        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+        const uint8_t *S = p.status + (size_t)rep * p.n;
+        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
+        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
+        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
+        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
+        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
+        if (cpr < 32)
+            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+        k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
+        k.c[0] = nzd(pack_nib(0u, c_prev)); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]);
+        k.c[3] = nzd(pack_nib(c_next, 0u));
+        k.m[0] = nzd(pack_nib(m4.x, m4.y)); k.m[1] = nzd(pack_nib(m4.z, m4.w)); k.m[2] = nzd(pack_nib(m_next, 0u));
+        k.p[0] = nzd(pack_nib(0u, p_prev)); k.p[1] = nzd(pack_nib(p4.x, p4.y)); k.p[2] = nzd(pack_nib(p4.z, p4.w));
+        k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
+        k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
+    }
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
+    uint32_t pk[7];
+    sweep_chunk_n(k, O, (size_t)cpl, pk);
     row_counts_epilogue(p, rows_sm, pk, tid, lane, cpr, rows_in_cta, row_local, rep, a);
 }
+#endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// ---- rolling window over rows -----------------------------------------------------------------------------
+// For rows that fill a whole CTA (d1 = 4096: 256 threads x 16 sites).  A CTA walks `rows_per_cta`
+// consecutive rows.  Each thread keeps the nibble-packed flags of its 16-site column for the four rows a-1,
+// a, a+1, a+2 in registers and, per step, loads only row a+3 (one 128-bit load + two halo words, issued
+// before the current row is computed so the latency is hidden): every status word is unpacked once per
+// thread instead of four times, and the barrier / ticket epilogue is paid once per CTA.
+struct RowRec { uint32_t n0, n1; ZD prev, own0, own1, next; };
+struct RowRaw { uint4 own; uint32_t prev, next; };
+__device__ __forceinline__ RowRaw load_row_raw(const uint8_t *S, int d1, int a, int ci, int cim, int cin) {
+    const uint4 *r = reinterpret_cast<const uint4 *>(S + (size_t)a * d1);
+    RowRaw w;
+    w.own = __ldg(r + ci);
+    w.prev = __ldg(reinterpret_cast<const uint32_t *>(r + cim) + 3);
+    w.next = __ldg(reinterpret_cast<const uint32_t *>(r + cin));
+    return w;
+}
+__device__ __forceinline__ RowRec make_row(const RowRaw &w) {
+    RowRec r;
+    r.n0 = pack_nib(w.own.x, w.own.y); r.n1 = pack_nib(w.own.z, w.own.w);
+    r.prev = nzd(pack_nib(0u, w.prev)); r.own0 = nzd(r.n0); r.own1 = nzd(r.n1); r.next = nzd(pack_nib(w.next, 0u));
+    return r;
+}
+
+struct SweepRollParams {
+    int d0, d1, n, n_replicas;
+    const uint8_t *status;
+    uint8_t *slots;
+    uint32_t *rowcnt;
+    unsigned long long *acc;
+    unsigned int *ticket;
+    unsigned long long *counts;
+    int rows_per_cta, ctas_per_replica;
+};
+constexpr int ROLL_MAX_ROWS = 16;
+
+__global__ void __launch_bounds__(256, 3) kmc_sweep_roll_kernel(const SweepRollParams p)
+{
+    __shared__ uint32_t part[ROLL_MAX_ROWS][8][8];       // [row step][warp][7 count pairs]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d0 = p.d0, d1 = p.d1;
+    const int cpr = d1 >> 4;                              // == 256
+    const int cpl = p.n >> 4;
+    const int rep = blockIdx.x / p.ctas_per_replica;
+    const int a0 = (blockIdx.x - rep * p.ctas_per_replica) * p.rows_per_cta;
+    const int nrows = min(p.rows_per_cta, d0 - a0);
+    const int ci = tid, cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+    const uint8_t *S = p.status + (size_t)rep * p.n;
+    auto wrap = [d0](int a) { return a < 0 ? a + d0 : (a >= d0 ? a - d0 : a); };
+
+    RowRec rm = make_row(load_row_raw(S, d1, wrap(a0 - 1), ci, cim, cin));
+    RowRec rc = make_row(load_row_raw(S, d1, a0, ci, cim, cin));
+    RowRec rp = make_row(load_row_raw(S, d1, wrap(a0 + 1), ci, cim, cin));
+    RowRec rq = make_row(load_row_raw(S, d1, wrap(a0 + 2), ci, cim, cin));
+    for (int i = 0; i < nrows; i++) {
+        const int a = a0 + i;
+        // prefetch the row that enters the window next
+        const RowRaw nxt = load_row_raw(S, d1, wrap(wrap(a + 3)), ci, cim, cin);
+        Chunk16N k;
+        k.cn[0] = rc.n0; k.cn[1] = rc.n1;
+        k.c[0] = rc.prev; k.c[1] = rc.own0; k.c[2] = rc.own1; k.c[3] = rc.next;
+        k.m[0] = rm.own0; k.m[1] = rm.own1; k.m[2] = rm.next;
+        k.p[0] = rp.prev; k.p[1] = rp.own0; k.p[2] = rp.own1;
+        k.q[0] = rq.prev.div; k.q[1] = rq.own0.div; k.q[2] = rq.own1.div;
+        uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + ((size_t)a * cpr + ci) : nullptr;
+        uint32_t pk[7];
+        sweep_chunk_n(k, O, (size_t)cpl, pk);
+#pragma unroll
+        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
+        if (lane < 7) {
+            uint32_t v = pk[0];
+#pragma unroll
+            for (int j = 1; j < 7; j++) v = lane == j ? pk[j] : v;
+            part[i][warp][lane] = v;
+        }
+        rm = rc; rc = rp; rp = rq; rq = make_row(nxt);
+    }
+    __syncthreads();
+    // row counts: thread (row step i, field f) sums the 8 warps' partials; plain stores
+    unsigned long long mine = 0;
+    if (tid < nrows * RCG_STRIDE) {
+        const int i = tid >> 4, f = tid & 15;
+        uint32_t sum = 0;
+        if (f < 14)
+            for (int w = 0; w < 8; w++) { const uint32_t v = part[i][w][f >> 1]; sum += (f & 1) ? (v >> 16) : (v & 0xFFFFu); }
+        sum = f < NC ? sum : 0u;
+        p.rowcnt[((size_t)rep * d0 + a0 + i) * RCG_STRIDE + f] = sum;
+        mine = sum;
+    }
+    // class totals of this CTA: reduce over its rows (threads with the same f), then running totals + ticket
+    __shared__ unsigned long long tot_sm[16];
+    if (tid < 16) tot_sm[tid] = 0;
+    __syncthreads();
+    if (tid < nrows * RCG_STRIDE && mine) atomicAdd(&tot_sm[tid & 15], mine);
+    __syncthreads();
+    if (tid < 32) {
+        const unsigned long long sum = tid < NC ? tot_sm[tid] : 0ull;
+        if (p.ctas_per_replica == 1) {
+            if (tid < NC) p.counts[(size_t)rep * NC + tid] = sum;
+        } else {
+            if (tid < NC && sum) atomicAdd(&p.acc[(size_t)rep * 16 + tid], sum);
+            __syncwarp();
+            unsigned int last = 0;
+            if (tid == 0) {
+                __threadfence();
+                last = (atomicAdd(&p.ticket[rep], 1u) == (unsigned)p.ctas_per_replica - 1u);
+                if (last) __threadfence();
+            }
+            last = __shfl_sync(0xFFFFFFFFu, last, 0);
+            if (last) {
+                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid == 0) p.ticket[rep] = 0u;
+            }
+        }
+    }
+}
+
 #endif  // __CUDACC__
 
 // Generic path (any d1 >= 5): one thread per site, scalar evaluation.

@@ -165,5 +165,5 @@ class Engine:
         nat.check(self._lib.kmc_set_replica_kernel(self._h, int(variant)))
 
     def set_sweep_kernel(self, variant):
-        """Aligned-shape sweep kernel: 0 nibble-parallel + PRMT tables (default), 1 byte-parallel."""
+        """Aligned-shape sweep kernel: 0 auto (rolling window for 4096-site rows), 1 nibble/PRMT, 2 byte-parallel."""
         nat.check(self._lib.kmc_set_sweep_kernel(self._h, int(variant)))

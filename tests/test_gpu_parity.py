@@ -163,8 +163,8 @@ def test_stats_only_mode_equals_logged_mode():
 
 
 @pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (256, 256), (7, 130), (16, 16),
-                                 (128, 32), (512, 4096), (8, 8192)])
-@pytest.mark.parametrize("variant", [0, 1])
+                                 (128, 32), (512, 4096), (8, 8192), (37, 4096), (5, 4096)])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_sweep_matches_oracle(dim, variant):
     sts = [evolved_state(dim, 3) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3), iid_state(dim, 4)]
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
