@@ -384,7 +384,7 @@ def main():
                                    "5%% divacancy + 5%% monovacancy, %d independent replicas per GPU, "
                                    "one warp per replica" % R,
                        "replicas_per_gpu": R, "events_per_replica_per_step": E,
-                       "l2": "flushed (256 MiB memset on the engine's stream) before every timed launch", "seed": SEED,
+                       "l2": "flushed (256 MiB read on the engine's stream, leaves clean lines) before every timed launch", "seed": SEED,
                        "parallelism": "replicas sharded by contiguous global index; one NCCL all-reduce of "
                                       "the event histogram at the end"},
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

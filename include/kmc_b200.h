@@ -137,9 +137,13 @@ int kmc_reset_stats(kmc_engine *h);
 
 /* measurement helpers: CUDA events recorded on the handle's stream */
 int kmc_sync(kmc_engine *h);
-/* overwrite `bytes` (0 = 256 MiB, > the 126 MB L2) of scratch on the handle's stream, asynchronously:
- * evicts L2 between timed launches without a host round trip */
+/* read `bytes` (0 = 256 MiB, > the 126 MB L2) of scratch on the handle's stream, asynchronously: leaves
+ * L2 full of clean foreign lines, so the next launch starts cold without a host round trip and without
+ * having to write back dirty flush data inside its timed region */
 int kmc_flush_l2(kmc_engine *h, size_t bytes);
+/* measurement helper: writes the sweep's 17 slot planes with the sweep's store pattern and nothing else
+ * (no loads, no arithmetic): the practical ceiling of the sweep's write traffic on this device */
+int kmc_probe_store_pattern(kmc_engine *h);
 int kmc_timer_start(kmc_engine *h);
 int kmc_timer_stop(kmc_engine *h, float *elapsed_ms);   /* synchronises */
 /* number of kernels this library has launched on the handle so far */

@@ -26,31 +26,70 @@ struct NoincParams {
     uint32_t *flags;
 };
 
-__global__ void __launch_bounds__(32) kmc_noinc_select_apply_kernel(const NoincParams p)
+// exclusive prefix of `v` over the 256 threads of the block (wsum: 8 words of shared scratch)
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long *wsum,
+                                                                  int tid, unsigned long long &total)
 {
+    const int lane = tid & 31, warp = tid >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += t;
+    }
+    __syncthreads();                       // wsum may still be read from a previous call
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    unsigned long long base = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) { const unsigned long long x = wsum[w]; if (w < warp) base += x; tot += x; }
+    total = tot;
+    return base + inc - v;
+}
+
+// One CTA (256 threads) per replica: warp 0 chooses the class; all threads share the rank search over
+// the rows (each owns a contiguous block of rows) and over the sites of the chosen row.
+__global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const NoincParams p)
+{
+    __shared__ unsigned long long wsum[8];
+    __shared__ unsigned long long s_rank;
+    __shared__ double s_total;
+    __shared__ int s_csel, s_zero, s_tie, s_row, s_col;
+    __shared__ uint32_t s_rin;
+    __shared__ uint32_t s_slotcnt[6];
     const int rep = blockIdx.x;
-    const int lane = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
-    if (p.flags[rep] & FLAG_ZERO_RATE) return;          // this replica already stopped
+    if (p.flags[rep] & FLAG_ZERO_RATE) return;          // this replica already stopped (uniform)
     uint8_t *st = p.status + (size_t)rep * p.n;
     const uint32_t *rcg = p.rowcnt + (size_t)rep * d0 * RCG_STRIDE;
-
-    const int myc = lane < NC ? lane : 0;
-    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
-    const long long tot = lane < NC ? (long long)p.counts[(size_t)rep * NC + lane] : 0;
     const unsigned long long step = p.steps_done[rep];
-    double u1, u2;
-    kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
-
-    const double w = __dmul_rn((double)tot, rate);
-    PickState pstate = pick_state_init(lane);
-    const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
     const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
-    if (p.log_mode == KMC_LOG_FULL && lane < NC)
-        (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = (uint32_t)tot;
-    if (pick.zero) {
+
+    if (tid < 32) {
+        const int myc = lane < NC ? lane : 0;
+        const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+        const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+        const long long tot = lane < NC ? (long long)p.counts[(size_t)rep * NC + lane] : 0;
+        double u1, u2;
+        kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
+        const double w = __dmul_rn((double)tot, rate);
+        PickState pstate = pick_state_init(lane);
+        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
+        if (p.log_mode == KMC_LOG_FULL && lane < NC)
+            (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = (uint32_t)tot;
+        const long long cnt = __shfl_sync(FULL, tot, pick.zero ? 0 : pick.csel);
+        long long rr = (long long)__dmul_rn(u2, (double)cnt);
+        if (rr > cnt - 1) rr = cnt - 1;
         if (lane == 0) {
+            s_csel = pick.csel; s_zero = pick.zero; s_tie = pick.tie != 0; s_total = pick.total;
+            s_rank = (unsigned long long)(rr < 0 ? 0 : rr);
+        }
+    }
+    if (tid < 6) s_slotcnt[tid] = 0;
+    __syncthreads();
+    if (s_zero) {
+        if (tid == 0) {
             p.flags[rep] |= FLAG_ZERO_RATE;
             if (p.log_mode == KMC_LOG_FULL) {
                 kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
@@ -64,45 +103,91 @@ __global__ void __launch_bounds__(32) kmc_noinc_select_apply_kernel(const NoincP
         }
         return;
     }
-    const int csel = pick.csel;
-    const long long cnt = __shfl_sync(FULL, tot, csel);
-    long long rr = (long long)__dmul_rn(u2, (double)cnt);
-    if (rr > cnt - 1) rr = cnt - 1;
+    const int csel = s_csel;
+    const unsigned long long rank = s_rank;
 
-    // row search: 64-bit running rank until it fits a chunk
-    int row = 0;
-    uint32_t r = 0;
-    for (int base = 0; base < d0; base += 32) {
-        const int a = base + lane;
-        const uint32_t v = a < d0 ? rcg[(size_t)a * RCG_STRIDE + csel] : 0u;
-        const uint32_t chunk = __reduce_add_sync(FULL, v);
-        if (rr >= (long long)chunk) { rr -= chunk; continue; }
-        r = (uint32_t)rr;
-        int L;
-        warp_rank_search(v, r, L, lane);
-        row = base + L;
-        break;
+    // ---- row: each thread owns rows [tid*kr, tid*kr + kr) --------------------------------------------
+    {
+        const int kr = (d0 + 255) / 256;
+        const int r0 = tid * kr, r1 = min(r0 + kr, d0);
+        unsigned long long local = 0, total;
+        for (int a = r0; a < r1; a++) local += rcg[(size_t)a * RCG_STRIDE + csel];
+        const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
+        if (rank >= excl && rank < excl + local) {
+            unsigned long long r = rank - excl;
+            int a = r0;
+            for (; a < r1; a++) {
+                const unsigned long long v = rcg[(size_t)a * RCG_STRIDE + csel];
+                if (r < v) break;
+                r -= v;
+            }
+            s_row = a; s_rin = (uint32_t)r;
+        }
     }
-    // site and slot inside the row (row, slot, column order)
-    int col, slot;
-    find_in_row_bytes(st, d0, d1, row, csel, r, lane, col, slot);
-    const int site = row * d1 + col;
-    const int s0 = st[site];
-    __syncwarp();
-    if (lane == 0) {
+    __syncthreads();
+    const int row = s_row;
+    // ---- slot: per-slot totals of the class in this row (row, slot, column order) ------------------------
+    {
+        uint32_t a01 = 0, a23 = 0, a45 = 0;
+        for (int b = tid; b < d1; b += 256) {
+            const uint32_t m = site_slot_mask(st, row, b, d0, d1, csel);
+            a01 += (m & 1u) | ((m & 2u) << 15);
+            a23 += ((m >> 2) & 1u) | ((m & 8u) << 13);
+            a45 += ((m >> 4) & 1u) | ((m & 32u) << 11);
+        }
+        a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
+        if (lane == 0) {
+            if (a01 & 0xFFFFu) atomicAdd(&s_slotcnt[0], a01 & 0xFFFFu);
+            if (a01 >> 16) atomicAdd(&s_slotcnt[1], a01 >> 16);
+            if (a23 & 0xFFFFu) atomicAdd(&s_slotcnt[2], a23 & 0xFFFFu);
+            if (a23 >> 16) atomicAdd(&s_slotcnt[3], a23 >> 16);
+            if (a45 & 0xFFFFu) atomicAdd(&s_slotcnt[4], a45 & 0xFFFFu);
+            if (a45 >> 16) atomicAdd(&s_slotcnt[5], a45 >> 16);
+        }
+    }
+    __syncthreads();
+    uint32_t r = s_rin;
+    int j = 0;
+#pragma unroll
+    for (int q = 0; q < 5; q++)
+        if (j == q && r >= s_slotcnt[q]) { r -= s_slotcnt[q]; j = q + 1; }
+    // ---- site: each thread owns columns [tid*kc, tid*kc + kc) ---------------------------------------------
+    {
+        const int kc = (d1 + 255) / 256;
+        const int b0 = tid * kc, b1 = min(b0 + kc, d1);
+        unsigned long long local = 0, total;
+        for (int b = b0; b < b1; b++) local += (site_slot_mask(st, row, b, d0, d1, csel) >> j) & 1u;
+        const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
+        if ((unsigned long long)r >= excl && (unsigned long long)r < excl + local) {
+            uint32_t q = r - (uint32_t)excl;
+            int b = b0;
+            for (; b < b1; b++) {
+                const uint32_t v = (site_slot_mask(st, row, b, d0, d1, csel) >> j) & 1u;
+                if (v && q == 0) break;
+                q -= v;
+            }
+            s_col = b;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int col = s_col;
+        const int slot = class_slot_base(csel) + j;
+        const int site = row * d1 + col;
+        const int s0 = st[site];
         apply_move(st, d0, d1, row, col, slot, s0);
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
             rec->site = (uint32_t)site; rec->cls = (uint8_t)csel; rec->slot = (uint8_t)slot;
-            rec->flags = pick.tie ? 1 : 0; rec->total_rate = pick.total; rec->pad = 0;
+            rec->flags = s_tie ? 1 : 0; rec->total_rate = s_total; rec->pad = 0;
         } else if (p.log_mode == KMC_LOG_COMPACT) {
             kmc_event_compact e; e.site = (uint32_t)site; e.cls = (uint8_t)csel; e.slot = (uint8_t)slot;
-            e.flags = pick.tie ? 1 : 0; e.total_rate = pick.total;
+            e.flags = s_tie ? 1 : 0; e.total_rate = s_total;
             reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
         }
         p.steps_done[rep] = step + 1;
         p.hist[(size_t)rep * NC + csel] += 1;
-        if (pick.tie) p.ties[rep] += 1;
+        if (s_tie) p.ties[rep] += 1;
     }
 }
 

@@ -483,6 +483,18 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
 // the byte-permute unit used as an 8-entry lookup table: the four low selector nibbles of a PRMT pick,
 // per site, the plane's code byte for that site's status (own-status planes) or for its
 // (present, near, far) triple (MoveDivacancy planes).  Counting uses per-nibble accumulators.
+// slot-plane store flavour of the nibble kernels: 0 = st.global.cs (streaming / evict-first),
+// 1 = default write-back, 2 = st.global.wt
+#ifndef KMC_SLOT_STORE_KIND
+#define KMC_SLOT_STORE_KIND 0
+#endif
+#if KMC_SLOT_STORE_KIND == 0
+#define KMC_SLOT_STORE(ptr, val) __stcs((ptr), (val))
+#elif KMC_SLOT_STORE_KIND == 1
+#define KMC_SLOT_STORE(ptr, val) (*(ptr) = (val))
+#else
+#define KMC_SLOT_STORE(ptr, val) __stwt((ptr), (val))
+#endif
 constexpr uint32_t ONESN = 0x11111111u;
 __host__ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 #ifdef __CUDA_ARCH__
@@ -559,11 +571,11 @@ template <int K> __device__ __forceinline__ void emit_move_plane_n(const Chunk16
     uint32_t a, b, c, d;
     move_plane_n<K>(k, 0, a, b, acc);
     move_plane_n<K>(k, 1, c, d, acc);
-    if (O) __stcs(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
+    if (O) KMC_SLOT_STORE(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
 }
 __device__ __forceinline__ void emit_lut_plane(uint4 *O, size_t plane, size_t cpl, uint32_t lo, uint32_t hi,
                                                uint32_t s0, uint32_t s0h, uint32_t s1, uint32_t s1h) {
-    if (O) __stcs(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
+    if (O) KMC_SLOT_STORE(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
 }
 
 // all 17 slot planes of one 16-site chunk (stored through O, stride cpl between planes) and the chunk's
@@ -629,7 +641,10 @@ __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_
     }
 }
 
-__global__ void __launch_bounds__(256, 4) kmc_sweep16n_kernel(const Sweep16Params p)
+#ifndef KMC_SWEEP_OCC
+#define KMC_SWEEP_OCC 4
+#endif
+__global__ void __launch_bounds__(256, KMC_SWEEP_OCC) kmc_sweep16n_kernel(const Sweep16Params p)
 {
     __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
     const int tid = threadIdx.x, lane = tid & 31;

@@ -53,6 +53,7 @@ SYMBOLS = {
     "kmc_reset_stats": (C.c_int, [C.c_void_p]),
     "kmc_sync": (C.c_int, [C.c_void_p]),
     "kmc_flush_l2": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "kmc_probe_store_pattern": (C.c_int, [C.c_void_p]),
     "kmc_timer_start": (C.c_int, [C.c_void_p]),
     "kmc_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "kmc_get_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

@@ -139,6 +139,9 @@ class Engine:
     def flush_l2(self, nbytes=0):
         nat.check(self._lib.kmc_flush_l2(self._h, int(nbytes)))
 
+    def probe_store_pattern(self):
+        nat.check(self._lib.kmc_probe_store_pattern(self._h))
+
     def timer_start(self):
         nat.check(self._lib.kmc_timer_start(self._h))
 
