@@ -364,7 +364,7 @@ def main():
         lat.close()
         other["1024x1024_x128_replicas_incremental"] = {
             "events_per_s": nrep5 * ev5 / (ms5 * 1e-3), "replicas": nrep5, "events_per_replica": ev5,
-            "note": "includes the per-launch rebuild of the row hierarchy (a full enumeration of 1 Mi sites per replica)"}
+            "note": "lattices stay in HBM/L2; the row hierarchy persists between launches (no re-enumeration)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -50,6 +50,7 @@ struct kmc_engine {
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
     int *d_result = nullptr;
+    uint32_t *d_hier = nullptr; bool hier_valid = false;   // row hierarchy of HBM-resident lattices
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
@@ -132,7 +133,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
-    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush);
+    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -187,7 +188,7 @@ extern "C" int kmc_upload_state(kmc_engine *h, const uint8_t *host_status)
     int rc = bind(h); if (rc) return rc;
     if (!host_status) return fail(KMC_ERR_ARG, "kmc_upload_state: null buffer");
     CU(cudaMemcpyAsync(h->d_status, host_status, (size_t)h->R * h->n, cudaMemcpyHostToDevice, h->stream));
-    h->swept = false;
+    h->swept = false; h->hier_valid = false;
     return check_state_device(h);
 }
 
@@ -205,7 +206,7 @@ extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
     int rc = bind(h); if (rc) return rc;
     if (!dev_status) return fail(KMC_ERR_ARG, "kmc_set_state_device: null pointer");
     CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
-    h->swept = false;
+    h->swept = false; h->hier_valid = false;
     return check_state_device(h);
 }
 
@@ -418,6 +419,11 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
     p.validate = validate;
+    p.hier = nullptr; p.hier_valid = 0;
+    if (global_state) {
+        if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * RC_WORDS * sizeof(uint32_t)));
+        p.hier = h->d_hier; p.hier_valid = h->hier_valid ? 1 : 0;
+    }
     const unsigned blocks = (unsigned)((h->R + W - 1) / W);
 #define KMC_LAUNCH(KERNEL)                                                                               \
     do {                                                                                                 \
@@ -438,6 +444,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     CU(cudaGetLastError());
     h->launches += 1;
     h->swept = false;
+    h->hier_valid = global_state;          // only this path keeps it; any other lattice change drops it
     if (rs) {
         CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -482,7 +489,7 @@ extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int 
     int res = 0;
     CU(cudaMemcpyAsync(&res, h->d_result, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->swept = false;
+    h->swept = false; h->hier_valid = false;
     if (res) return fail(KMC_ERR_ARG, "kmc_perform_given: that move does not exist on the current lattice");
     return KMC_OK;
 }
@@ -511,7 +518,7 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
         CU(cudaGetLastError());
         h->launches += 1;
     }
-    h->swept = false;
+    h->swept = false; h->hier_valid = false;
     if (rs) CU(cudaMemcpyAsync(events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
     return check_flags(h, false);
 }

@@ -43,6 +43,10 @@ struct ReplicaParams {
     unsigned long long *ties;        // [R]
     uint32_t *flags;                 // [R] bit0 zero-rate stop, bit1 validate mismatch
     int validate;
+    // HBM-resident lattices only: the row-count hierarchy of each replica, kept between launches so that
+    // a launch does not have to re-enumerate a 1 Mi-site lattice first.  hier_valid != 0: load it.
+    uint32_t *hier;                  // [R][d0 * RC_WORDS] or nullptr
+    int hier_valid;
 };
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -351,11 +355,16 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     __syncwarp();
 
     // ---- build the row hierarchy (a full enumeration, as Rule.initialize_moves does) --------
-    for (int a = lane; a < d0; a += 32) {
-        uint32_t w[RC_WORDS];
-        row_counts(st, a, d0, d1, w);
+    if (GLOBAL_STATE && p.hier && p.hier_valid) {
+        const uint32_t *src = p.hier + (size_t)rep * d0 * RC_WORDS;
+        for (int i = lane; i < d0 * RC_WORDS; i += 32) rc[i] = src[i];
+    } else {
+        for (int a = lane; a < d0; a += 32) {
+            uint32_t w[RC_WORDS];
+            row_counts(st, a, d0, d1, w);
 #pragma unroll
-        for (int j = 0; j < RC_WORDS; j++) rc[a * RC_WORDS + j] = w[j];
+            for (int j = 0; j < RC_WORDS; j++) rc[a * RC_WORDS + j] = w[j];
+        }
     }
     __syncwarp();
 
@@ -565,7 +574,11 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
     }
     if (GLOBAL_STATE) {
-        // the lattice was updated in place
+        // the lattice was updated in place; keep the hierarchy for the next launch
+        if (p.hier) {
+            uint32_t *dst = p.hier + (size_t)rep * d0 * RC_WORDS;
+            for (int i = lane; i < d0 * RC_WORDS; i += 32) dst[i] = rc[i];
+        }
     } else if ((n & 15) == 0) {
         uint4 *dst = reinterpret_cast<uint4 *>(gst);
         const uint4 *src = reinterpret_cast<const uint4 *>(st);

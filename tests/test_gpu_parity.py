@@ -135,7 +135,8 @@ def test_large_lattice_incremental_1024():
     st0 = np.stack([exact_state(dim, 0.05, 0.05, 300 + r) for r in range(nrep)])
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
     eng.upload_state(st0)
-    ev = eng.run(nsteps, 77, log_mode=nat.LOG_FULL, validate=True)
+    # three launches: the second and third reuse the row hierarchy the previous one left in HBM
+    ev = np.concatenate([eng.run(n, 77, log_mode=nat.LOG_FULL, validate=True) for n in (1000, 1500, 500)], axis=1)
     final = eng.download_state()
     for r in range(nrep):
         o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
