@@ -296,9 +296,9 @@ def main():
     d2h = R * DIM[0] * DIM[1] + R * 13 * 8
     eng.close()
 
-    # ---- HBM roofline: 4096^2 full rate sweep (rank 0 of each GPU does it; reported from rank 0) -----
+    # ---- HBM roofline: 4096^2 full rate sweep (single lattice, "replicas only": rank 0 measures it) -----
     roofline = None
-    if not args.no_sweep:
+    if rank == 0 and not args.no_sweep:
         peak, peak_src = measured_peaks()
         sw = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
         sw.upload_state(iid_lattice(SWEEP_DIM, SEED))
