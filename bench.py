@@ -232,7 +232,19 @@ def main():
         raise SystemExit("bench.py: no CUDA device (the engine has no CPU fallback)")
     torch.cuda.set_device(local)
     cuda = torch.device("cuda", local)
-    parallel.init(backend="nccl", device=cuda)
+    # NCCL prints its version banner on stdout when the communicator is created; the contract is ONE JSON
+    # line on stdout, so stdout points at stderr while the process group comes up
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        parallel.init(backend="nccl", device=cuda)
+        parallel.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     def barrier():
         parallel.barrier()
