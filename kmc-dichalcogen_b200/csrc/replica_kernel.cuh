@@ -163,25 +163,6 @@ __device__ __forceinline__ ClassPick pick_class(double w, int pos, PickState &st
     return out;
 }
 
-// class count of the (uniform) class `c` at one site, specialised per class group
-template <int GROUP>   // 0: own-status classes, 1: MoveDivacancy kinds, 2: CreateTrefoil
-__device__ __forceinline__ uint32_t site_class_count(const uint8_t *st, int a, int b, int d0, int d1, int c,
-                                                    uint32_t g1const) {
-    const int s0 = st[a * d1 + b];
-    if (GROUP == 0) return (g1const >> (2 * s0)) & 3u;
-    if (s0 != S_DIVAC) return 0u;
-    if (GROUP == 1) {
-        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
-        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
-        RingMasks m = ring_masks(st[am * d1 + b], st[a * d1 + bm], st[ap * d1 + bm], st[ap * d1 + b],
-                                 st[a * d1 + bp], st[am * d1 + bp]);
-        return __popc(kind_mask(m, c - C_MOVE_DIV));
-    }
-    const int ap2 = wrap_inc(a + 2, d0), bp2 = wrap_inc(b + 2, d1), bm2 = wrap_dec(b - 2, d1);
-    uint32_t t20 = st[ap2 * d1 + b] == S_DIVAC;
-    return (t20 & (uint32_t)(st[a * d1 + bp2] == S_DIVAC)) + (t20 & (uint32_t)(st[ap2 * d1 + bm2] == S_DIVAC));
-}
-
 // 2 bits per status: number of class-c moves a site of that status carries (own-status classes)
 __device__ __forceinline__ uint32_t g1_const(int c) {
     switch (c) {
