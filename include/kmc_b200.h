@@ -134,6 +134,11 @@ int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out);
 int kmc_get_steps_done(kmc_engine *h, int64_t *out);
 int kmc_get_ties(kmc_engine *h, int64_t *out);
 int kmc_reset_stats(kmc_engine *h);
+/* Optional KMC clock (extension; the reference draws no time step, SURVEY F6, but logs total_rate so that
+ * time can be reconstructed, README.md:36-37): per replica t += 1 / total_rate at every event, the mean
+ * residence time estimator, accumulated in fp64 in event order.  out: [n_replicas]. */
+int kmc_enable_clock(kmc_engine *h, int on);
+int kmc_get_clock(kmc_engine *h, double *out);
 
 /* measurement helpers: CUDA events recorded on the handle's stream */
 int kmc_sync(kmc_engine *h);

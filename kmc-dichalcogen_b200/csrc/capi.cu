@@ -50,6 +50,7 @@ struct kmc_engine {
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
     int *d_result = nullptr;
+    double *d_clock = nullptr; bool clock_on = false;        // optional KMC clock per replica
     uint32_t *d_hier = nullptr; bool hier_valid = false;   // row hierarchy of HBM-resident lattices
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
@@ -133,7 +134,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
-    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier);
+    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -419,6 +420,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
     p.validate = validate;
+    p.clock = h->clock_on ? h->d_clock : nullptr;
     p.hier = nullptr; p.hier_valid = 0;
     if (global_state) {
         if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * RC_WORDS * sizeof(uint32_t)));
@@ -511,6 +513,7 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
     p.seed = seed; p.replica0 = replica0; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.nsteps = nsteps;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+    p.clock = h->clock_on ? h->d_clock : nullptr;
     for (long long t = 0; t < nsteps; t++) {
         rc = sweep_launch(h, false); if (rc) return rc;        // sim.py:114-115: initialize() every step
         p.rowcnt = h->d_rowcnt; p.counts = h->d_counts; p.t = t;
@@ -568,6 +571,27 @@ extern "C" int kmc_reset_stats(kmc_engine *h)
     CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
+    if (h->d_clock) CU(cudaMemsetAsync(h->d_clock, 0, R * sizeof(double), h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_enable_clock(kmc_engine *h, int on)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (on && !h->d_clock) {
+        CU(cudaMalloc(&h->d_clock, (size_t)h->R * sizeof(double)));
+        CU(cudaMemsetAsync(h->d_clock, 0, (size_t)h->R * sizeof(double), h->stream));
+    }
+    h->clock_on = on != 0;
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_clock(kmc_engine *h, double *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!h->d_clock) return fail(KMC_ERR_ARG, "kmc_get_clock: call kmc_enable_clock first");
+    CU(cudaMemcpyAsync(out, h->d_clock, (size_t)h->R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
 }
 

@@ -24,6 +24,7 @@ struct NoincParams {
     long long nsteps, t;                 // this launch handles local step index t
     unsigned long long *steps_done, *hist, *ties;
     uint32_t *flags;
+    double *clock;                       // [R] or nullptr
 };
 
 // exclusive prefix of `v` over the 256 threads of the block (wsum: 8 words of shared scratch)
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
             reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
         }
         p.steps_done[rep] = step + 1;
+        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], __ddiv_rn(1.0, s_total));
         p.hist[(size_t)rep * NC + csel] += 1;
         if (s_tie) p.ties[rep] += 1;
     }

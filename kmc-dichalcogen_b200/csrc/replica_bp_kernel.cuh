@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
     unsigned long long hist = 0, n_ties = 0;
     PickState pstate = pick_state_init(lane);
+    double tclock = 0.0;
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
     const int my_j = lane / 6, my_k = lane % 6;
     DirConst my_dir = dir_const(my_k, d0);
@@ -328,6 +329,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             break;
         }
         const int csel = pick.csel;
+        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, pick.total));
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
@@ -611,6 +613,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
     if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
+        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
         p.ties[rep] += n_ties;
         if (flag) p.flags[rep] |= flag;
     }

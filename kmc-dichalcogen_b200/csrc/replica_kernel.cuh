@@ -47,6 +47,9 @@ struct ReplicaParams {
     // a launch does not have to re-enumerate a 1 Mi-site lattice first.  hier_valid != 0: load it.
     uint32_t *hier;                  // [R][d0 * RC_WORDS] or nullptr
     int hier_valid;
+    // optional KMC clock: t += 1 / total_rate per event (mean residence time; the reference has no clock
+    // but logs total_rate for exactly this post-processing, README.md:36-37).  nullptr = off.
+    double *clock;                   // [R]
 };
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -361,6 +364,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     unsigned long long hist = 0;
     unsigned long long n_ties = 0;
     PickState pstate = pick_state_init(lane);
+    double tclock = 0.0;
 
     // per-lane role in the refresh: node index and one of 10 offsets
     const int my_i = lane / 10, my_o = lane % 10;
@@ -417,6 +421,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const int csel = pick.csel;
         const double total = pick.total;
         const uint32_t tie = pick.tie;
+        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, total));
 
         // ---- event record, part 1 (counts before the event) -------------------------------------
         if (p.log_mode == KMC_LOG_FULL) {
@@ -570,6 +575,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
+        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
         p.ties[rep] += n_ties;
         if (flag) p.flags[rep] |= flag;
     }

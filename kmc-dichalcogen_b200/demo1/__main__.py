@@ -7,7 +7,7 @@ import sys
 from functools import partial
 
 from . import config
-from .sim import KmcSim
+from .sim import KmcSim, class_table
 
 PROG = "demo1"
 
@@ -120,15 +120,8 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     import numpy as np
     from . import tables as T
     from .engine import Engine
-    probe = KmcSim.__new__(KmcSim)
-    probe.rule_specs, probe.temperature = list(cfg["rule_specs"]), temperature
-    rates13, order, info = [0.0] * T.N_CLASSES, [], {}
-    for spec in probe.rule_specs:
-        rates = spec.rates(temperature)
-        for kind in spec.kinds():
-            rates13[T.CLASS_ID[(spec.name, kind)]] = rates[kind]
-            order.append(T.CLASS_ID[(spec.name, kind)])
-            info[spec.format(kind)] = rates[kind]
+    rules_and_rates, rates13, order = class_table(cfg["rule_specs"], temperature)
+    info = {"%s:%s" % (rule, kind): rate for rule, rates in rules_and_rates.items() for kind, rate in rates.items()}
     seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
     eng = Engine(init_state.dim, rates13, order, n_replicas=replicas, device=device)
     eng.upload_state(np.tile(init_state.status, (replicas, 1)))

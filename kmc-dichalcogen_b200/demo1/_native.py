@@ -51,6 +51,8 @@ SYMBOLS = {
     "kmc_get_steps_done": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_get_ties": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "kmc_reset_stats": (C.c_int, [C.c_void_p]),
+    "kmc_enable_clock": (C.c_int, [C.c_void_p, C.c_int]),
+    "kmc_get_clock": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_sync": (C.c_int, [C.c_void_p]),
     "kmc_flush_l2": (C.c_int, [C.c_void_p, C.c_size_t]),
     "kmc_probe_store_pattern": (C.c_int, [C.c_void_p]),

@@ -129,6 +129,15 @@ class Engine:
         nat.check(self._lib.kmc_get_ties(self._h, C.byref(v)))
         return v.value
 
+    def enable_clock(self, on=True):
+        nat.check(self._lib.kmc_enable_clock(self._h, int(bool(on))))
+
+    def clock(self):
+        """Per-replica KMC time (sum of 1/total_rate over the events done)."""
+        out = np.empty(self.n_replicas, dtype=np.float64)
+        nat.check(self._lib.kmc_get_clock(self._h, out.ctypes.data))
+        return out
+
     def reset_stats(self):
         nat.check(self._lib.kmc_reset_stats(self._h))
 

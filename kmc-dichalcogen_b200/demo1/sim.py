@@ -47,6 +47,27 @@ class RuleSpec:
         return self.name if kind is None else "%s:%s" % (self.name, kind)
 
 
+def class_table(rule_specs, temperature):
+    """Rule specs -> (rates_by_rule, class_rate[13], class_order): the per-class rate vector and the
+    weighted_choice input order (rules in the given order x Rule.kinds() order) the engine needs.
+    Kind validation as in the reference (sim.py:71-78)."""
+    rules_and_rates, rates13, order = {}, [0.0] * T.N_CLASSES, []
+    for spec in rule_specs:
+        rates = spec.rates(temperature)
+        for kind in spec.kinds():
+            if kind not in rates:
+                raise RuntimeError("config: %s: Missing required rate for kind: %s" % (spec.format(), kind))
+        for kind in rates:
+            if kind not in spec.kinds():
+                warnings.warn("config: %s: Unexpected kind: %s" % (spec.format(), kind))
+        rules_and_rates[spec.name] = rates
+        for kind in spec.kinds():
+            cid = T.CLASS_ID[(spec.name, kind)]
+            rates13[cid] = rates[kind]
+            order.append(cid)
+    return rules_and_rates, rates13, order
+
+
 class KmcSim:
     """Runs the KMC simulation of one trajectory on the GPU.
 
@@ -79,22 +100,7 @@ class KmcSim:
         elif self._engine is not None:
             self._sync_state()
         assert self.state is not None
-        self.rules_and_rates = {}
-        rates13 = [0.0] * T.N_CLASSES
-        order = []
-        for spec in self.rule_specs:
-            rates = spec.rates(self.temperature)
-            for kind in spec.kinds():
-                if kind not in rates:
-                    raise RuntimeError("config: %s: Missing required rate for kind: %s" % (spec.format(), kind))
-            for kind in rates:
-                if kind not in spec.kinds():
-                    warnings.warn("config: %s: Unexpected kind: %s" % (spec.format(), kind))
-            self.rules_and_rates[spec.name] = rates
-            for kind in spec.kinds():
-                cid = T.CLASS_ID[(spec.name, kind)]
-                rates13[cid] = rates[kind]
-                order.append(cid)
+        self.rules_and_rates, rates13, order = class_table(self.rule_specs, self.temperature)
         self._rates13 = rates13
         self._order = order
         if self._engine is None:

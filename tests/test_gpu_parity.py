@@ -147,6 +147,36 @@ def test_large_lattice_incremental_1024():
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
+    """Extension: t = sum 1/total_rate, accumulated in event order, bit-equal to the
+    same sum over the logged totals; across two launches and for the no-incremental path."""
+    dim, nrep = (16, 20) if variant == 1 else (64, 64), 3
+    st0 = np.stack([exact_state(dim, 0.1, 0.1, 7 + r) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.set_replica_kernel(variant)
+    eng.enable_clock()
+    eng.upload_state(st0)
+    ev = np.concatenate([eng.run(n, 3, log_mode=nat.LOG_COMPACT) for n in (700, 300)], axis=1)
+    got = eng.clock()
+    for r in range(nrep):
+        t = 0.0
+        for n0, n1 in ((0, 700), (700, 1000)):
+            part = 0.0
+            for x in ev[r]["total_rate"][n0:n1]:
+                part += 1.0 / float(x)
+            t += part
+        assert got[r] == t
+    ev2 = eng.run_noinc(50, 3, log_mode=nat.LOG_COMPACT)
+    got2 = eng.clock()
+    for r in range(nrep):
+        t = got[r]
+        for x in ev2[r]["total_rate"]:
+            t += 1.0 / float(x)
+        assert got2[r] == t
+    eng.close()
+
+
 def test_stats_only_mode_equals_logged_mode():
     dim, nrep, nsteps = (64, 64), 40, 3000
     st0 = np.stack([exact_state(dim, 0.05, 0.05, r) for r in range(nrep)])
