@@ -157,8 +157,9 @@ int kmc_get_launch_count(kmc_engine *h, int64_t *out);
 int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **row_counts,
                             void **histogram);
 /* tuning knobs: warps (replicas) per CTA of the replica kernel, 0 = automatic (max 8); and which
- * replica kernel runs: 0 = automatic (bit-sliced lattice when dim1 <= 64, byte lattice otherwise),
- * 1 = byte lattice in shared memory, 2 = bit-sliced, 3 = byte lattice left in HBM/L2 with only the
+ * replica kernel runs: 0 = automatic (bit-sliced lattice, two replicas per warp, when dim1 <= 64; byte
+ * lattice otherwise), 1 = byte lattice in shared memory, 2 = bit-sliced with one warp per replica,
+ * 4 = bit-sliced with a half-warp per replica, 3 = byte lattice left in HBM/L2 with only the
  * row-count hierarchy in shared memory (chosen automatically when the lattice does not fit, e.g.
  * 1024x1024).  All produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);

@@ -14,6 +14,7 @@
 #include "noinc_kernel.cuh"
 #include "replica_kernel.cuh"
 #include "replica_bp_kernel.cuh"
+#include "replica_hw_kernel.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace kmc;
@@ -387,7 +388,44 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
     if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
     if (log_mode != KMC_LOG_NONE && !host_events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
-    // rows of <= 64 sites run on the bit-sliced kernel, wider rows on the byte-lattice kernel
+    // rows of <= 64 sites run on the bit-sliced kernels (two replicas per warp by default), wider rows on
+    // the byte-lattice kernel
+    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 &&
+                                              2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
+    if (halfwarp) {
+        if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
+        const size_t hbytes = replica_hw_bytes(h->d0);
+        if (2 * hbytes > (size_t)h->max_smem_optin) return fail(KMC_ERR_ARG, "lattice too large for the half-warp kernel");
+        int hpb = h->warps_per_block > 0 ? 2 * h->warps_per_block : 16;      // replicas (half-warps) per block
+        if (hpb > 16) hpb = 16;
+        while (hpb > 2 && hpb * hbytes > (size_t)h->max_smem_optin) hpb -= 2;
+        const size_t smem = hpb * hbytes;
+        const size_t rs = record_size(log_mode);
+        if (rs) { int rc = ensure_events(h, rs * (size_t)h->R * (size_t)nsteps); if (rc) return rc; }
+        ReplicaParams p;
+        p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
+        p.status = h->d_status;
+        for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+        p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
+        p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.validate = validate;
+        p.clock = h->clock_on ? h->d_clock : nullptr;
+        p.hier = nullptr; p.hier_valid = 0;
+        const unsigned blocks = (unsigned)((h->R + hpb - 1) / hpb);
+        if (h->d0 == 64 && h->d1 == 64) {
+            CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kmc_replica_hw_kernel<64, 64><<<blocks, hpb * 16, smem, h->stream>>>(p);
+        } else {
+            CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kmc_replica_hw_kernel<0, 0><<<blocks, hpb * 16, smem, h->stream>>>(p);
+        }
+        CU(cudaGetLastError());
+        h->launches += 1;
+        h->swept = false; h->hier_valid = false;
+        if (rs) CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
+        return KMC_OK;
+    }
     const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64 &&
                                                replica_bp_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (bitplanes && h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernel needs dim1 <= 64");
@@ -700,8 +738,9 @@ extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
 }
 extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)
 {
-    if (!h || variant < 0 || variant > 3)
-        return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice), 2 (bit planes) or 3 (byte lattice in HBM)");
+    if (!h || variant < 0 || variant > 4)
+        return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice), 2 (bit planes, warp per replica), "
+                                 "3 (byte lattice in HBM) or 4 (bit planes, half-warp per replica)");
     h->variant = variant;
     return KMC_OK;
 }

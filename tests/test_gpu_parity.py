@@ -106,7 +106,7 @@ def test_replicas_match_oracle(dim, rates, order, nrep, nsteps):
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("dim", [(64, 64), (33, 47), (5, 5), (9, 64), (130, 7), (16, 20)])
 def test_both_replica_kernels_match_oracle(dim, variant):
     """The byte-lattice kernel (1), the bit-sliced kernel (2) and the byte-lattice kernel with the
@@ -147,7 +147,7 @@ def test_large_lattice_incremental_1024():
     eng.close()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 4])
 def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
     """Extension: t = sum 1/total_rate, accumulated in event order, bit-equal to the
     same sum over the logged totals; across two launches and for the no-incremental path."""
