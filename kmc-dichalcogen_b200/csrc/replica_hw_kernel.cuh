@@ -14,6 +14,7 @@
 //   hl < 6    direction hl of the MoveDivacancy masks during the site search, CreateTrefoil anchor rows
 //   hl < 12   refresh: direction hl % 6 of band rows 2*pass + hl / 6
 #pragma once
+#include <type_traits>
 #include "replica_bp_kernel.cuh"
 
 namespace kmc {
@@ -25,27 +26,52 @@ __host__ __device__ inline size_t replica_hw_bytes(int d0) {      // per replica
     return planes + rc;
 }
 
+// Two execution modes of the same event code:
+//   LOCK = true   both halves of the warp run in lockstep: every data-dependent branch that contains a
+//                 shuffle or vote is taken if EITHER half needs it (its effects are predicated per half), so
+//                 all sync intrinsics can name the full warp (plain SHFL / VOTE, no WARPSYNC prologue);
+//   LOCK = false  a half runs on its own (the partner stopped on a zero total rate, or does not exist):
+//                 intrinsics name only the half's 16 lanes.
 struct Half { int hl, shift; uint32_t mask; };
-#define HSHFL(v, src) __shfl_sync(hw.mask, (v), (src), 16)
-#define HSHFL_UP(v, d) __shfl_up_sync(hw.mask, (v), (d), 16)
-#define HSHFL_DOWN(v, d) __shfl_down_sync(hw.mask, (v), (d), 16)
-__device__ __forceinline__ uint32_t hballot(const Half &hw, bool pred) {
-    return (__ballot_sync(hw.mask, pred) >> hw.shift) & 0xFFFFu;
+template <bool LOCK> struct HalfSync {
+    __device__ __forceinline__ static uint32_t m(const Half &hw) { return LOCK ? FULL : hw.mask; }
+    // "does any half that shares my instruction stream need this?"  (pred is uniform inside a half)
+    __device__ __forceinline__ static bool any(const Half &hw, bool pred) { return LOCK ? __any_sync(FULL, pred) : pred; }
+    __device__ __forceinline__ static uint32_t ballot(const Half &hw, bool pred) {
+        return (__ballot_sync(m(hw), pred) >> hw.shift) & 0xFFFFu;
+    }
+    // min / max over the halves that share the instruction stream (x is uniform inside a half)
+    __device__ __forceinline__ static int umin(const Half &hw, int x) { return LOCK ? (int)__reduce_min_sync(FULL, (unsigned)x) : x; }
+    __device__ __forceinline__ static int umax(const Half &hw, int x) { return LOCK ? (int)__reduce_max_sync(FULL, (unsigned)x) : x; }
+    __device__ __forceinline__ static void sync(const Half &hw) { __syncwarp(m(hw)); }
+};
+#define HSHFL(v, src) __shfl_sync(HS::m(hw), (v), (src), 16)
+#define HSHFL_UP(v, d) __shfl_up_sync(HS::m(hw), (v), (d), 16)
+#define HSHFL_DOWN(v, d) __shfl_down_sync(HS::m(hw), (v), (d), 16)
+// minimum over the 16 lanes of a half (4 xor steps; REDUX has no segment width)
+template <class HS> __device__ __forceinline__ uint32_t half_min(const Half &hw, uint32_t v) {
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) v = min(v, __shfl_xor_sync(HS::m(hw), v, o, 16));
+    return v;
 }
 
 // weighted_choice over the 16 lanes of a half (see pick_class in replica_kernel.cuh; same arithmetic)
+template <bool LOCK>
 __device__ __forceinline__ ClassPick pick_class_hw(double w, int pos, PickState &st, double u1, const Half &hw)
 {
+    typedef HalfSync<LOCK> HS;
     const int hl = hw.hl;
     double ws = HSHFL(w, st.sc);
     const int ps = HSHFL(pos, st.sc);
-    int first = (int)__reduce_min_sync(hw.mask, (w != st.wprev) ? (unsigned)st.spos : 16u);
+    int first = (int)half_min<HS>(hw, (w != st.wprev) ? (unsigned)st.spos : 16u);
     st.wprev = w;
     {
         const double wp = HSHFL_UP(ws, 1);
         const int pp = HSHFL_UP(ps, 1);
         const bool ok = (hl == 0) || (wp < ws) || (wp == ws && pp < ps);
-        if (st.need_sort || !__all_sync(hw.mask, ok)) {
+        const bool resort = st.need_sort || HS::ballot(hw, !ok) != 0;
+        if (HS::any(hw, resort)) {
+            // re-deriving the order of a half that did not need it reproduces its order exactly
             int rank = 0;
             for (int j = 0; j < 16; j++) {
                 const double wj = HSHFL(w, j);
@@ -59,41 +85,46 @@ __device__ __forceinline__ ClassPick pick_class_hw(double w, int pos, PickState 
             }
             st.need_sort = false;
             ws = HSHFL(w, st.sc);
-            first = 0;
+            if (resort) first = 0;
         }
     }
     ClassPick out;
-    const int z = __popc(hballot(hw, ws == 0.0));
+    const int z = __popc(HS::ballot(hw, ws == 0.0));
     out.zero = (z == 16);
     const int start = first > z ? first : z;
     double acc = HSHFL(st.cum, (start + 15) & 15);
     if (start == z) acc = 0.0;
-    for (int k = start; k < 16; k++) {
+    const int k0 = HS::umin(hw, start);                        // lockstep: the earlier of the two halves
+    for (int k = k0; k < 16; k++) {
         const double wk = HSHFL(ws, k);
-        acc = __dadd_rn(acc, wk);                              // util.py:65-68: sequential sums
-        if (hl == k) st.cum = acc;
+        if (k >= start) {
+            acc = __dadd_rn(acc, wk);                          // util.py:65-68: sequential sums
+            if (hl == k) st.cum = acc;
+        }
     }
-    if (start == 16) acc = HSHFL(st.cum, 15);
+    const double last = HSHFL(st.cum, 15);
+    if (start == 16) acc = last;
     out.total = acc;
     const double x = __dmul_rn(acc, u1);                       // random.uniform(0, total), kmc.py:49
     const bool live = hl >= z;
-    const uint32_t ge = hballot(hw, live && st.cum >= x);      // bisect_left, kmc.py:50
+    const uint32_t ge = HS::ballot(hw, live && st.cum >= x);   // bisect_left, kmc.py:50
     const int isel = ge ? (__ffs(ge) - 1) : 15;
-    out.tie = hballot(hw, live && st.cum == x);
+    out.tie = HS::ballot(hw, live && st.cum == x);
     out.csel = HSHFL(st.sc, isel);
     return out;
 }
 
 // column of the (idx)-th set bit of a row mask: lane hl counts the set bits below site 4*hl + 4
+template <class HS>
 __device__ __forceinline__ int nth_set_bit_hw(u64 m, uint32_t idx, const Half &hw, uint32_t low_lo, uint32_t low_hi) {
     const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32);
     const uint32_t c = __popc(mlo & low_lo) + __popc(mhi & low_hi);
-    const int L = __ffs(hballot(hw, c > idx)) - 1;
+    const int L = (__ffs(HS::ballot(hw, c > idx)) - 1) & 15;
     const uint32_t below = HSHFL(c, (L + 15) & 15);
     uint32_t nibble = ((L & 8 ? mhi : mlo) >> ((4 * L) & 31)) & 0xFu;
     const uint32_t rem = idx - (L ? below : 0u);
-    for (uint32_t i = 0; i < rem; i++) nibble &= nibble - 1;    // rem <= 3, uniform inside the half
-    return 4 * L + __ffs(nibble) - 1;
+    for (uint32_t i = 0; i < (rem & 3u); i++) nibble &= nibble - 1;    // rem <= 3, uniform inside the half
+    return 4 * L + ((__ffs(nibble) - 1) & 3);
 }
 
 template <int TD0, int TD1>
@@ -109,7 +140,9 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
     const int hl = hw.hl;
     const int slot_in_block = (threadIdx.x >> 4);                       // half-warp index inside the block
     const int rep = blockIdx.x * (blockDim.x >> 4) + slot_in_block;
-    if (rep >= p.n_replicas) return;       // a whole half exits; the other half never names these lanes
+    // lockstep needs both halves of the warp to own a replica
+    const bool pair_ok = __all_sync(FULL, rep < p.n_replicas);
+    if (rep >= p.n_replicas) return;       // a whole half exits; the other half then runs on its own
     const RowBits<TD1> rb(d1);
 
     extern __shared__ uint4 smem_raw[];
@@ -184,6 +217,10 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
     long long t = 0;
     uint32_t flag = 0;
 
+    // the event loop, in lockstep (both halves, full-warp intrinsics) or alone (half-warp intrinsics)
+    auto run = [&](auto lock_tag) {
+    constexpr bool LOCK = decltype(lock_tag)::value;
+    typedef HalfSync<LOCK> HS;
     for (; t < p.nsteps; t++) {
         // ---- draws: a block of 16 events at a time, one event per half-lane ---------------------
         if ((t & 15) == 0) {
@@ -203,7 +240,12 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
 
         // ---- 1./2. weights and class choice (sim.py:120-122, kmc.py:21-54) ----------------------
         const double w = __dmul_rn((double)tot, rate);
-        const ClassPick pick = pick_class_hw(w, pos, pstate, u1, hw);
+        const ClassPick pick = pick_class_hw<LOCK>(w, pos, pstate, u1, hw);
+        if (LOCK) {
+            // a half that cannot continue ends the lockstep phase before anything of this event is written;
+            // the class choice is redone (identically) by the lone loops
+            if (__any_sync(FULL, pick.zero)) { pstate.need_sort = true; return; }
+        }
         if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && hl == 0) {
@@ -239,53 +281,63 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         }
         // 3a. row: four rows per half-lane per pass (one 64-bit load of four uint16 counts)
         int row = 0;
-        for (int base = 0; base < d0; base += 64) {
-            const int r0 = base + 4 * hl;
-            const u64 v4 = (r0 < d0) ? rc64[(csel * d0p + r0) >> 2] : 0ull;
-            const uint32_t lo2 = (uint32_t)v4, hi2 = (uint32_t)(v4 >> 32);
-            const uint32_t s = (lo2 & 0xFFFFu) + (lo2 >> 16) + (hi2 & 0xFFFFu) + (hi2 >> 16);
-            uint32_t inc = s;
+        {
+            bool found = false;
+            for (int base = 0; base < d0; base += 64) {
+                const int r0 = base + 4 * hl;
+                const u64 v4 = (r0 < d0) ? rc64[(csel * d0p + r0) >> 2] : 0ull;
+                const uint32_t lo2 = (uint32_t)v4, hi2 = (uint32_t)(v4 >> 32);
+                const uint32_t s = (lo2 & 0xFFFFu) + (lo2 >> 16) + (hi2 & 0xFFFFu) + (hi2 >> 16);
+                uint32_t inc = s;
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const uint32_t tt = HSHFL_UP(inc, o);
-                if (hl >= o) inc += tt;
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t tt = HSHFL_UP(inc, o);
+                    if (hl >= o) inc += tt;
+                }
+                const uint32_t total = HSHFL(inc, 15);
+                const int L = (__ffs(HS::ballot(hw, inc > r)) - 1) & 15;
+                const uint32_t excl = HSHFL(inc - s, L);
+                const uint32_t wl = HSHFL(lo2, L), wh = HSHFL(hi2, L);
+                if (!found) {
+                    if (r >= total) r -= total;
+                    else {
+                        found = true;
+                        r -= excl;
+                        const uint32_t f0 = wl & 0xFFFFu, f1 = wl >> 16, f2 = wh & 0xFFFFu;
+                        int j = 0;
+                        if (r >= f0) { r -= f0; j = 1; if (r >= f1) { r -= f1; j = 2; if (r >= f2) { r -= f2; j = 3; } } }
+                        row = base + 4 * L + j;
+                    }
+                }
+                if (TD0 && TD0 <= 64) break;
             }
-            const uint32_t total = HSHFL(inc, 15);
-            if (r >= total) { r -= total; continue; }
-            const int L = __ffs(hballot(hw, inc > r)) - 1;
-            r -= HSHFL(inc - s, L);
-            const uint32_t wl = HSHFL(lo2, L), wh = HSHFL(hi2, L);
-            const uint32_t f0 = wl & 0xFFFFu, f1 = wl >> 16, f2 = wh & 0xFFFFu;
-            int j = 0;
-            if (r >= f0) { r -= f0; j = 1; if (r >= f1) { r -= f1; j = 2; if (r >= f2) { r -= f2; j = 3; } } }
-            row = base + 4 * L + j;
-            break;
         }
         // 3b/3c. slot, then site, within the row
-        int col, slot, s0;
-        if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
+        int col = 0, slot = 0, s0 = 0;
+        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
+        if (HS::any(hw, group == 1)) {
             u64 pr, ne, fa;
             dir_masks<TD0>(PL, d0, row, my_dir, pr, ne, fa);
-            const u64 mine = hl < 6 ? kind_select(pr, ne, fa, csel - C_MOVE_DIV) : 0ull;
+            const u64 mine = hl < 6 ? kind_select(pr, ne, fa, (csel - C_MOVE_DIV) & 3) : 0ull;
             const uint32_t cntk = __popcll(mine);
             uint32_t pre = cntk, t1;
             t1 = HSHFL_UP(pre, 1); if (hl >= 1) pre += t1;
             t1 = HSHFL_UP(pre, 2); if (hl >= 2) pre += t1;
             t1 = HSHFL_UP(pre, 4); if (hl >= 4) pre += t1;
-            const int ksel = __ffs(hballot(hw, pre > r) & 0x3Fu) - 1;
+            const int ksel = (__ffs(HS::ballot(hw, pre > r) & 0x3Fu) - 1) & 7;
             const uint32_t rem = r - HSHFL(pre - cntk, ksel);
-            col = nth_set_bit_hw(HSHFL(mine, ksel), rem, hw, my_low_lo, my_low_hi);
-            slot = 7 + ksel;
-            s0 = S_DIVAC;
-        } else if (csel == C_CREATE_TREF) {
+            const int c1 = nth_set_bit_hw<HS>(HSHFL(mine, ksel), rem, hw, my_low_lo, my_low_hi);
+            if (group == 1) { col = c1; slot = 7 + ksel; s0 = S_DIVAC; }
+        }
+        if (HS::any(hw, group == 2)) {
             u64 up, dn;
             trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
             const uint32_t nu = __popcll(up);
             const bool second = r >= nu;
-            col = nth_set_bit_hw(second ? dn : up, second ? r - nu : r, hw, my_low_lo, my_low_hi);
-            slot = 13 + (int)second;
-            s0 = S_DIVAC;
-        } else {
+            const int c1 = nth_set_bit_hw<HS>(second ? dn : up, second ? r - nu : r, hw, my_low_lo, my_low_hi);
+            if (group == 2) { col = c1; slot = 13 + (int)second; s0 = S_DIVAC; }
+        }
+        if (HS::any(hw, group == 0)) {
             int pa, pb = -1;
             switch (csel) {
                 case C_CREATE_DIV: pa = PL_Z; break;
@@ -302,15 +354,18 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
             if (csel == C_FLIP) ma |= PL[PL_M2 * d0 + row];
             const uint32_t n1 = __popcll(ma);
             const bool second = r >= n1;
-            col = nth_set_bit_hw(second ? mb : ma, second ? r - n1 : r, hw, my_low_lo, my_low_hi);
-            slot = class_slot_base(csel) + (int)second;
-            switch (csel) {
-                case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0 = 0; break;
-                case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0 = 3; break;
-                case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
-                case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
-                case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
-                default: s0 = ((PL[PL_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
+            const int c1 = nth_set_bit_hw<HS>(second ? mb : ma, second ? r - n1 : r, hw, my_low_lo, my_low_hi);
+            if (group == 0) {
+                col = c1;
+                slot = class_slot_base(csel) + (int)second;
+                switch (csel) {
+                    case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0 = 0; break;
+                    case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0 = 3; break;
+                    case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
+                    case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
+                    case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
+                    default: s0 = ((PL[PL_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
+                }
             }
         }
         const int site = row * d1 + col;
@@ -386,7 +441,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
             }
             tot += dsum;
         }
-        __syncwarp(hw.mask);
+        HS::sync(hw);
 
         // ---- 5b. MoveDivacancy: band rows row+lo .. row+hi re-derived and replaced, two rows per pass ----
         int lo = -1, hi = 1;
@@ -394,8 +449,9 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         else if (slot >= 7) { lo += mv.da1 < 0 ? mv.da1 : 0; hi += mv.da1 > 0 ? mv.da1 : 0; }
         {
             const int nrows = hi - lo + 1;
+            const int nloop = HS::umax(hw, nrows);              // lockstep: the longer band of the two halves
             uint32_t d01 = 0, d23 = 0;
-            for (int j0 = 0; j0 < nrows; j0 += 2) {
+            for (int j0 = 0; j0 < nloop; j0 += 2) {
                 const int j = j0 + my_g;
                 const bool act = hl < 12 && j < nrows;
                 const int ra = wrapT<TD0>(row + lo + (j < nrows ? j : 0), d0);
@@ -418,8 +474,9 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
                     d23 += pk23 - (o2 | (o3 << 16));
                 }
             }
-            const int s01 = (int)__reduce_add_sync(hw.mask, d01);
-            const int s23 = (int)__reduce_add_sync(hw.mask, d23);
+            // the two group leaders (half-lanes 0 and 6) hold the packed signed deltas
+            const int s01 = (int)(HSHFL(d01, 0) + HSHFL(d01, 6));
+            const int s23 = (int)(HSHFL(d23, 0) + HSHFL(d23, 6));
             const int l01 = (int)(short)(s01 & 0xFFFF), l23 = (int)(short)(s23 & 0xFFFF);
             if (hl == C_MOVE_DIV) tot += l01;
             if (hl == C_MOVE_DIV + 1) tot += (s01 - l01) >> 16;
@@ -439,11 +496,17 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
                 d = nw - (int)q[0];
                 q[0] = (uint16_t)nw;
             }
-            const int s = (int)__reduce_add_sync(hw.mask, (uint32_t)d);
+            int s = d + HSHFL_DOWN(d, 3);                      // half-lanes 0..5 hold the row deltas
+            s += HSHFL_DOWN(s, 1) + HSHFL_DOWN(s, 2);
+            s = HSHFL(s, 0);
             if (hl == C_CREATE_TREF) tot += s;
         }
-        __syncwarp(hw.mask);
+        HS::sync(hw);
     }
+    };   // run
+    if (pair_ok) run(std::true_type());
+    run(std::false_type());                 // the rest: nothing, or a half whose partner stopped / never existed
+
 
     // ---- epilogue ------------------------------------------------------------------------------------
     const long long done = t;
