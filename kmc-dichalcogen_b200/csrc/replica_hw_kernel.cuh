@@ -19,11 +19,70 @@
 
 namespace kmc {
 
+// Shared memory is what limits how many half-warps fit on an SM, so this kernel keeps only the six
+// type planes (3 KiB at 64 rows) and rotates neighbour rows on the fly (two funnel shifts per rotate)
+// instead of holding pre-rotated copies: 4.6 KiB per replica -> 48 replicas = 24 warps per SM.
+enum { HW_PLANES = N_TYPES };      // plane index == plane type: T_Z, T_D, T_M1, T_M2, T_A4, T_A7
+
 __host__ __device__ inline size_t replica_hw_bytes(int d0) {      // per replica
     const size_t d0p = ((size_t)d0 + 3) & ~(size_t)3;
-    const size_t planes = (size_t)N_PLANES * d0 * 8;
+    const size_t planes = (size_t)HW_PLANES * d0 * 8;
     const size_t rc = (NC * d0p * 2 + 15) & ~(size_t)15;
     return planes + rc;
+}
+
+// word whose bit b is bit (b + db) of x, db in {-1, 0, +1}: (sh, sw) = (0, no) / (1, no) / (31, swap halves)
+template <int TD1>
+__device__ __forceinline__ u64 rot_site(u64 x, int db, int sh, bool sw, const RowBits<TD1> &rb) {
+    if (TD1 == 64) {
+        const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+        const uint32_t a = sw ? hi : lo, b = sw ? lo : hi;
+        return (u64)__funnelshift_l(b, a, sh) | ((u64)__funnelshift_l(a, b, sh) << 32);
+    }
+    return rb.rotl(x, rb.amount(db));
+}
+struct HwDir { int da_n, db_n, sh_n, da_e, db_e, sh_e, da_f, db_f, sh_f; };
+__device__ __forceinline__ HwDir hw_dir_const(int k) {
+    HwDir c;
+    c.da_n = nib(NBR_DA, k);  c.db_n = nib(NBR_DB, k);  c.sh_n = c.db_n == 0 ? 0 : (c.db_n < 0 ? 1 : 31);
+    c.da_e = nib(NEAR_DA, k); c.db_e = nib(NEAR_DB, k); c.sh_e = c.db_e == 0 ? 0 : (c.db_e < 0 ? 1 : 31);
+    c.da_f = nib(FAR_DA, k);  c.db_f = nib(FAR_DB, k);  c.sh_f = c.db_f == 0 ? 0 : (c.db_f < 0 ? 1 : 31);
+    return c;
+}
+template <int TD0, int TD1>
+__device__ __forceinline__ void hw_dir_masks(const u64 *PL, int d0, int a, const HwDir &c, const RowBits<TD1> &rb,
+                                             u64 &present, u64 &near, u64 &far) {
+    present = PL[T_D * d0 + a] & rot_site(PL[T_Z * d0 + wrapT<TD0>(a + c.da_n, d0)], c.db_n, c.sh_n, c.db_n > 0, rb);
+    near = rot_site(PL[T_D * d0 + wrapT<TD0>(a + c.da_e, d0)], c.db_e, c.sh_e, c.db_e > 0, rb);
+    far = rot_site(PL[T_D * d0 + wrapT<TD0>(a + c.da_f, d0)], c.db_f, c.sh_f, c.db_f > 0, rb);
+}
+template <int TD0, int TD1>
+__device__ __forceinline__ void hw_trefoil_masks(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, u64 &up, u64 &dn) {
+    const u64 Da = PL[T_D * d0 + a];
+    const u64 Db = PL[T_D * d0 + wrapT<TD0>(a + 2, d0)];
+    const u64 both = Da & Db;
+    up = both & rb.rotl(Da, rb.amount(2));
+    dn = both & rb.rotl(Db, rb.amount(-2));
+}
+template <int TD0, int TD1>
+__device__ __forceinline__ void hw_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
+    const uint32_t pz = __popcll(PL[T_Z * d0 + a]), pd = __popcll(PL[T_D * d0 + a]);
+    const uint32_t pm = __popcll(PL[T_M1 * d0 + a] | PL[T_M2 * d0 + a]);
+    const uint32_t pa = __popcll(PL[T_A4 * d0 + a] | PL[T_A7 * d0 + a]);
+    out[C_CREATE_DIV] = pz; out[C_FILL_DIV] = pd; out[C_DESTROY_TREF] = pa;
+    out[C_CMONO_FROM_DOUBLE] = 2 * pz; out[C_CMONO_MAKE_EMPTY] = pm; out[C_FMONO_MAKE_DOUBLE] = pm;
+    out[C_FMONO_FROM_EMPTY] = 2 * pd; out[C_FLIP] = pm;
+    uint32_t k01 = 0, k23 = 0;
+    for (int k = 0; k < 6; k++) {
+        const HwDir c = hw_dir_const(k);
+        u64 p, n, f; hw_dir_masks<TD0>(PL, d0, a, c, rb, p, n, f);
+        uint32_t a01, a23; kind_counts(p, n, f, a01, a23);
+        k01 += a01; k23 += a23;
+    }
+    out[C_MOVE_DIV] = k01 & 0xFFFF; out[C_MOVE_DIV + 1] = k01 >> 16;
+    out[C_MOVE_DIV + 2] = k23 & 0xFFFF; out[C_MOVE_DIV + 3] = k23 >> 16;
+    u64 up, dn; hw_trefoil_masks<TD0>(PL, d0, a, rb, up, dn);
+    out[C_CREATE_TREF] = __popcll(up) + __popcll(dn);
 }
 
 // Two execution modes of the same event code:
@@ -128,7 +187,7 @@ __device__ __forceinline__ int nth_set_bit_hw(u64 m, uint32_t idx, const Half &h
 }
 
 template <int TD0, int TD1>
-__global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaParams p)
+__global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
@@ -147,7 +206,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
 
     extern __shared__ uint4 smem_raw[];
     u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot_in_block * replica_hw_bytes(d0));
-    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + N_PLANES * d0);      // [NC][d0p]
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + HW_PLANES * d0);      // [NC][d0p]
     const u64 *rc64 = reinterpret_cast<const u64 *>(rc16);
 
     // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
@@ -172,18 +231,14 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
                 for (int q = 0; q < N_TYPES; q++) w[q] |= (u64)(pl == q) << b;
             }
         }
-        PL[PL_Z * d0 + a] = w[T_Z];   PL[PL_ZP * d0 + a] = rb.rotl(w[T_Z], rb.amount(1));
-        PL[PL_ZM * d0 + a] = rb.rotl(w[T_Z], rb.amount(-1));
-        PL[PL_D * d0 + a] = w[T_D];   PL[PL_DP * d0 + a] = rb.rotl(w[T_D], rb.amount(1));
-        PL[PL_DM * d0 + a] = rb.rotl(w[T_D], rb.amount(-1));
-        PL[PL_M1 * d0 + a] = w[T_M1]; PL[PL_M2 * d0 + a] = w[T_M2];
-        PL[PL_A4 * d0 + a] = w[T_A4]; PL[PL_A7 * d0 + a] = w[T_A7];
+#pragma unroll
+        for (int q = 0; q < N_TYPES; q++) PL[q * d0 + a] = w[q];
     }
     __syncwarp(hw.mask);
     // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
     for (int a = hl; a < d0p; a += 16) {
         uint32_t cnt[NC];
-        if (a < d0) bp_row_counts<TD0>(PL, d0, a, rb, cnt);
+        if (a < d0) hw_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
         for (int c = 0; c < NC; c++) rc16[c * d0p + a] = a < d0 ? (uint16_t)cnt[c] : (uint16_t)0;
     }
@@ -202,15 +257,13 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
     double tclock = 0.0;
     // refresh roles: half-lanes 0..11 = direction hl % 6 of band rows 2*pass + hl / 6
     const int my_g = hl / 6, my_k = hl % 6;
-    DirConst my_dir = dir_const(my_k, d0);
-    asm volatile("" : "+r"(my_dir.off_n), "+r"(my_dir.da_n), "+r"(my_dir.off_e), "+r"(my_dir.da_e),
-                      "+r"(my_dir.off_f), "+r"(my_dir.da_f));
+    HwDir my_dir = hw_dir_const(my_k);
+    asm volatile("" : "+r"(my_dir.da_n), "+r"(my_dir.db_n), "+r"(my_dir.sh_n), "+r"(my_dir.da_e), "+r"(my_dir.db_e),
+                      "+r"(my_dir.sh_e), "+r"(my_dir.da_f), "+r"(my_dir.db_f), "+r"(my_dir.sh_f));
     // this lane's mask of the sites below column 4*hl + 4 (for popcount-select)
     uint32_t my_low_lo = hl >= 7 ? 0xFFFFFFFFu : ((16u << (4 * hl)) - 1u);
     uint32_t my_low_hi = hl < 8 ? 0u : (hl == 15 ? 0xFFFFFFFFu : ((16u << (4 * (hl - 8))) - 1u));
     asm volatile("" : "+r"(my_low_lo), "+r"(my_low_hi));
-    const int my_ptype = hl < N_PLANES ? (int)((PLANE_TYPE >> (4 * hl)) & 0xF) : -1;
-    const int my_cshift = hl < N_PLANES ? (int)((PLANE_CSHIFT >> (4 * hl)) & 0xF) - 1 : 0;
 
     const unsigned long long step_base = p.steps_done[rep];
     double mu1 = 0.0, mu2 = 0.0;
@@ -317,7 +370,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
         if (HS::any(hw, group == 1)) {
             u64 pr, ne, fa;
-            dir_masks<TD0>(PL, d0, row, my_dir, pr, ne, fa);
+            hw_dir_masks<TD0>(PL, d0, row, my_dir, rb, pr, ne, fa);
             const u64 mine = hl < 6 ? kind_select(pr, ne, fa, (csel - C_MOVE_DIV) & 3) : 0ull;
             const uint32_t cntk = __popcll(mine);
             uint32_t pre = cntk, t1;
@@ -331,7 +384,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         }
         if (HS::any(hw, group == 2)) {
             u64 up, dn;
-            trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
+            hw_trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
             const uint32_t nu = __popcll(up);
             const bool second = r >= nu;
             const int c1 = nth_set_bit_hw<HS>(second ? dn : up, second ? r - nu : r, hw, my_low_lo, my_low_hi);
@@ -340,18 +393,18 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         if (HS::any(hw, group == 0)) {
             int pa, pb = -1;
             switch (csel) {
-                case C_CREATE_DIV: pa = PL_Z; break;
-                case C_FILL_DIV: pa = PL_D; break;
-                case C_DESTROY_TREF: pa = PL_A4; pb = PL_A7; break;
-                case C_CMONO_FROM_DOUBLE: pa = PL_Z; pb = PL_Z; break;
-                case C_CMONO_MAKE_EMPTY: pa = PL_M2; pb = PL_M1; break;
-                case C_FMONO_MAKE_DOUBLE: pa = PL_M1; pb = PL_M2; break;
-                case C_FMONO_FROM_EMPTY: pa = PL_D; pb = PL_D; break;
-                default: pa = PL_M1; break;
+                case C_CREATE_DIV: pa = T_Z; break;
+                case C_FILL_DIV: pa = T_D; break;
+                case C_DESTROY_TREF: pa = T_A4; pb = T_A7; break;
+                case C_CMONO_FROM_DOUBLE: pa = T_Z; pb = T_Z; break;
+                case C_CMONO_MAKE_EMPTY: pa = T_M2; pb = T_M1; break;
+                case C_FMONO_MAKE_DOUBLE: pa = T_M1; pb = T_M2; break;
+                case C_FMONO_FROM_EMPTY: pa = T_D; pb = T_D; break;
+                default: pa = T_M1; break;
             }
             u64 ma = PL[pa * d0 + row];
             const u64 mb = pb >= 0 ? PL[pb * d0 + row] : 0ull;
-            if (csel == C_FLIP) ma |= PL[PL_M2 * d0 + row];
+            if (csel == C_FLIP) ma |= PL[T_M2 * d0 + row];
             const uint32_t n1 = __popcll(ma);
             const bool second = r >= n1;
             const int c1 = nth_set_bit_hw<HS>(second ? mb : ma, second ? r - n1 : r, hw, my_low_lo, my_low_hi);
@@ -364,7 +417,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
                     case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
                     case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
                     case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
-                    default: s0 = ((PL[PL_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
+                    default: s0 = ((PL[T_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
                 }
             }
         }
@@ -403,25 +456,22 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
         const int na = mv.na;
-        if (hl < N_PLANES) {
+        if (hl < HW_PLANES) {
             uint32_t *P32 = reinterpret_cast<uint32_t *>(PL + hl * d0);
             {
-                const int c = wrapT<TD1>(col + my_cshift, d1);
-                uint32_t *wp = P32 + 2 * row + (c >> 5);
-                const uint32_t bit = 1u << (c & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns0) == my_ptype ? bit : 0u);
+                uint32_t *wp = P32 + 2 * row + (col >> 5);
+                const uint32_t bit = 1u << (col & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns0) == hl ? bit : 0u);
             }
             if (na > 1) {
-                const int c = wrapT<TD1>(mv.b1 + my_cshift, d1);
-                uint32_t *wp = P32 + 2 * mv.a1 + (c >> 5);
-                const uint32_t bit = 1u << (c & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns1) == my_ptype ? bit : 0u);
+                uint32_t *wp = P32 + 2 * mv.a1 + (mv.b1 >> 5);
+                const uint32_t bit = 1u << (mv.b1 & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns1) == hl ? bit : 0u);
             }
             if (na > 2) {
-                const int c = wrapT<TD1>(mv.b2 + my_cshift, d1);
-                uint32_t *wp = P32 + 2 * mv.a2 + (c >> 5);
-                const uint32_t bit = 1u << (c & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns2) == my_ptype ? bit : 0u);
+                uint32_t *wp = P32 + 2 * mv.a2 + (mv.b2 >> 5);
+                const uint32_t bit = 1u << (mv.b2 & 31);
+                *wp = (*wp & ~bit) | (status_plane(mv.ns2) == hl ? bit : 0u);
             }
         }
         // ---- 5a. own-status classes: owner lanes fold (old -> new) of each touched node -----------------
@@ -458,7 +508,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
                 uint32_t pk01 = 0, pk23 = 0;
                 if (act) {
                     u64 pr, ne, fa;
-                    dir_masks<TD0>(PL, d0, ra, my_dir, pr, ne, fa);
+                    hw_dir_masks<TD0>(PL, d0, ra, my_dir, rb, pr, ne, fa);
                     kind_counts(pr, ne, fa, pk01, pk23);
                 }
                 pk01 += HSHFL_DOWN(pk01, 3);
@@ -490,7 +540,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
             if (hl < ng) {
                 const int ra = wrapT<TD0>(row + hl - 3, d0);
                 u64 up, dn;
-                trefoil_masks<TD0>(PL, d0, ra, rb, up, dn);
+                hw_trefoil_masks<TD0>(PL, d0, ra, rb, up, dn);
                 const int nw = __popcll(up) + __popcll(dn);
                 uint16_t *q = rc16 + C_CREATE_TREF * d0p + ra;
                 d = nw - (int)q[0];
@@ -514,17 +564,15 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         bool bad = false;
         for (int a = hl; a < d0; a += 16) {
             uint32_t cnt[NC];
-            bp_row_counts<TD0>(PL, d0, a, rb, cnt);
+            hw_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
             for (int c = 0; c < NC; c++) bad |= (rc16[c * d0p + a] != (uint16_t)cnt[c]);
-            const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a];
-            const u64 types[N_TYPES] = {z, dv, PL[PL_M1 * d0 + a], PL[PL_M2 * d0 + a], PL[PL_A4 * d0 + a], PL[PL_A7 * d0 + a]};
+            const u64 z = PL[T_Z * d0 + a], dv = PL[T_D * d0 + a];
+            const u64 types[N_TYPES] = {z, dv, PL[T_M1 * d0 + a], PL[T_M2 * d0 + a], PL[T_A4 * d0 + a], PL[T_A7 * d0 + a]};
             u64 seen = 0, dup = 0;
 #pragma unroll
             for (int q = 0; q < N_TYPES; q++) { dup |= seen & types[q]; seen |= types[q]; }
             bad |= dup != 0;
-            bad |= PL[PL_ZP * d0 + a] != rb.rotl(z, rb.amount(1)) || PL[PL_ZM * d0 + a] != rb.rotl(z, rb.amount(-1));
-            bad |= PL[PL_DP * d0 + a] != rb.rotl(dv, rb.amount(1)) || PL[PL_DM * d0 + a] != rb.rotl(dv, rb.amount(-1));
         }
         if (hl < NC) {
             int fresh = 0;
@@ -534,8 +582,8 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
         if (__any_sync(hw.mask, bad)) flag |= FLAG_VALIDATE;
     }
     for (int a = hl; a < d0; a += 16) {
-        const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a], m1 = PL[PL_M1 * d0 + a], m2 = PL[PL_M2 * d0 + a];
-        const u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        const u64 z = PL[T_Z * d0 + a], dv = PL[T_D * d0 + a], m1 = PL[T_M1 * d0 + a], m2 = PL[T_M2 * d0 + a];
+        const u64 a4 = PL[T_A4 * d0 + a], a7 = PL[T_A7 * d0 + a];
         auto code_at = [&](int b) -> uint32_t {
             return ((z >> b) & 1) ? 0u : ((dv >> b) & 1) ? 3u : ((m1 >> b) & 1) ? 1u : ((m2 >> b) & 1) ? 2u
                  : ((a4 >> b) & 1) ? 4u : ((a7 >> b) & 1) ? 7u : 5u;
@@ -552,7 +600,7 @@ __global__ void __launch_bounds__(256, 2) kmc_replica_hw_kernel(const ReplicaPar
     }
     __syncwarp(hw.mask);
     for (int a = hl; a < d0; a += 16) {
-        u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        u64 a4 = PL[T_A4 * d0 + a], a7 = PL[T_A7 * d0 + a];
         const int a2 = wrap1(a + 2, d0);
         while (a4) {
             const int b = __ffsll((long long)a4) - 1; a4 &= a4 - 1;
