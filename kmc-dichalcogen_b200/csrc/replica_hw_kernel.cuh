@@ -14,7 +14,6 @@
 //   hl < 6    direction hl of the MoveDivacancy masks during the site search, CreateTrefoil anchor rows
 //   hl < 12   refresh: direction hl % 6 of band rows 2*pass + hl / 6
 #pragma once
-#include <type_traits>
 #include "replica_bp_kernel.cuh"
 
 namespace kmc {
@@ -270,292 +269,16 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
     long long t = 0;
     uint32_t flag = 0;
 
-    // the event loop, in lockstep (both halves, full-warp intrinsics) or alone (half-warp intrinsics)
-    auto run = [&](auto lock_tag) {
-    constexpr bool LOCK = decltype(lock_tag)::value;
-    typedef HalfSync<LOCK> HS;
-    for (; t < p.nsteps; t++) {
-        // ---- draws: a block of 16 events at a time, one event per half-lane ---------------------
-        if ((t & 15) == 0) {
-            const long long tt = t + hl;
-            if (tt < p.nsteps) {
-                if (p.draws) {
-                    const double2 u = *reinterpret_cast<const double2 *>(
-                        p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)tt) * 2);
-                    mu1 = u.x; mu2 = u.y;
-                } else {
-                    kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step_base + (unsigned long long)tt, mu1, mu2);
-                }
-            }
-        }
-        const double u1 = HSHFL(mu1, (int)(t & 15));
-        const double u2 = HSHFL(mu2, (int)(t & 15));
-
-        // ---- 1./2. weights and class choice (sim.py:120-122, kmc.py:21-54) ----------------------
-        const double w = __dmul_rn((double)tot, rate);
-        const ClassPick pick = pick_class_hw<LOCK>(w, pos, pstate, u1, hw);
-        if (LOCK) {
-            // a half that cannot continue ends the lockstep phase before anything of this event is written;
-            // the class choice is redone (identically) by the lone loops
-            if (__any_sync(FULL, pick.zero)) { pstate.need_sort = true; return; }
-        }
-        if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
-            flag |= FLAG_ZERO_RATE;
-            if (p.log_mode != KMC_LOG_NONE && hl == 0) {
-                const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
-                if (p.log_mode == KMC_LOG_FULL) {
-                    kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
-                    rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
-                    rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
-                } else {
-                    kmc_event_compact e;
-                    e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE; e.flags = 0;
-                    e.total_rate = 0.0;
-                    reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
-                }
-            }
-            break;
-        }
-        const int csel = pick.csel;
-        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, pick.total));
-        if (p.log_mode == KMC_LOG_FULL) {
-            kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
-                                  ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-            if (hl < NC) rec->counts[hl] = (uint32_t)tot;
-        }
-
-        // ---- 3. in-class pick: rank in (row, slot, column) order -----------------------------------
-        const int cnt = HSHFL(tot, csel);
-        uint32_t r;
-        {
-            long long rr = (long long)__dmul_rn(u2, (double)cnt);
-            if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
-            r = (uint32_t)rr;
-        }
-        // 3a. row: four rows per half-lane per pass (one 64-bit load of four uint16 counts)
-        int row = 0;
-        {
-            bool found = false;
-            for (int base = 0; base < d0; base += 64) {
-                const int r0 = base + 4 * hl;
-                const u64 v4 = (r0 < d0) ? rc64[(csel * d0p + r0) >> 2] : 0ull;
-                const uint32_t lo2 = (uint32_t)v4, hi2 = (uint32_t)(v4 >> 32);
-                const uint32_t s = (lo2 & 0xFFFFu) + (lo2 >> 16) + (hi2 & 0xFFFFu) + (hi2 >> 16);
-                uint32_t inc = s;
-#pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
-                    const uint32_t tt = HSHFL_UP(inc, o);
-                    if (hl >= o) inc += tt;
-                }
-                const uint32_t total = HSHFL(inc, 15);
-                const int L = (__ffs(HS::ballot(hw, inc > r)) - 1) & 15;
-                const uint32_t excl = HSHFL(inc - s, L);
-                const uint32_t wl = HSHFL(lo2, L), wh = HSHFL(hi2, L);
-                if (!found) {
-                    if (r >= total) r -= total;
-                    else {
-                        found = true;
-                        r -= excl;
-                        const uint32_t f0 = wl & 0xFFFFu, f1 = wl >> 16, f2 = wh & 0xFFFFu;
-                        int j = 0;
-                        if (r >= f0) { r -= f0; j = 1; if (r >= f1) { r -= f1; j = 2; if (r >= f2) { r -= f2; j = 3; } } }
-                        row = base + 4 * L + j;
-                    }
-                }
-                if (TD0 && TD0 <= 64) break;
-            }
-        }
-        // 3b/3c. slot, then site, within the row
-        int col = 0, slot = 0, s0 = 0;
-        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
-        if (HS::any(hw, group == 1)) {
-            u64 pr, ne, fa;
-            hw_dir_masks<TD0>(PL, d0, row, my_dir, rb, pr, ne, fa);
-            const u64 mine = hl < 6 ? kind_select(pr, ne, fa, (csel - C_MOVE_DIV) & 3) : 0ull;
-            const uint32_t cntk = __popcll(mine);
-            uint32_t pre = cntk, t1;
-            t1 = HSHFL_UP(pre, 1); if (hl >= 1) pre += t1;
-            t1 = HSHFL_UP(pre, 2); if (hl >= 2) pre += t1;
-            t1 = HSHFL_UP(pre, 4); if (hl >= 4) pre += t1;
-            const int ksel = (__ffs(HS::ballot(hw, pre > r) & 0x3Fu) - 1) & 7;
-            const uint32_t rem = r - HSHFL(pre - cntk, ksel);
-            const int c1 = nth_set_bit_hw<HS>(HSHFL(mine, ksel), rem, hw, my_low_lo, my_low_hi);
-            if (group == 1) { col = c1; slot = 7 + ksel; s0 = S_DIVAC; }
-        }
-        if (HS::any(hw, group == 2)) {
-            u64 up, dn;
-            hw_trefoil_masks<TD0>(PL, d0, row, rb, up, dn);
-            const uint32_t nu = __popcll(up);
-            const bool second = r >= nu;
-            const int c1 = nth_set_bit_hw<HS>(second ? dn : up, second ? r - nu : r, hw, my_low_lo, my_low_hi);
-            if (group == 2) { col = c1; slot = 13 + (int)second; s0 = S_DIVAC; }
-        }
-        if (HS::any(hw, group == 0)) {
-            int pa, pb = -1;
-            switch (csel) {
-                case C_CREATE_DIV: pa = T_Z; break;
-                case C_FILL_DIV: pa = T_D; break;
-                case C_DESTROY_TREF: pa = T_A4; pb = T_A7; break;
-                case C_CMONO_FROM_DOUBLE: pa = T_Z; pb = T_Z; break;
-                case C_CMONO_MAKE_EMPTY: pa = T_M2; pb = T_M1; break;
-                case C_FMONO_MAKE_DOUBLE: pa = T_M1; pb = T_M2; break;
-                case C_FMONO_FROM_EMPTY: pa = T_D; pb = T_D; break;
-                default: pa = T_M1; break;
-            }
-            u64 ma = PL[pa * d0 + row];
-            const u64 mb = pb >= 0 ? PL[pb * d0 + row] : 0ull;
-            if (csel == C_FLIP) ma |= PL[T_M2 * d0 + row];
-            const uint32_t n1 = __popcll(ma);
-            const bool second = r >= n1;
-            const int c1 = nth_set_bit_hw<HS>(second ? mb : ma, second ? r - n1 : r, hw, my_low_lo, my_low_hi);
-            if (group == 0) {
-                col = c1;
-                slot = class_slot_base(csel) + (int)second;
-                switch (csel) {
-                    case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0 = 0; break;
-                    case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0 = 3; break;
-                    case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
-                    case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
-                    case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
-                    default: s0 = ((PL[T_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
-                }
-            }
-        }
-        const int site = row * d1 + col;
-
-        // ---- event record -----------------------------------------------------------------------------
-        if (p.log_mode != KMC_LOG_NONE && hl == 0) {
-            const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
-            if (p.log_mode == KMC_LOG_FULL) {
-                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
-                rec->site = (uint32_t)site; rec->cls = (uint8_t)csel; rec->slot = (uint8_t)slot;
-                rec->flags = pick.tie ? 1 : 0; rec->total_rate = pick.total; rec->pad = 0;
-            } else {
-                kmc_event_compact e;
-                e.site = (uint32_t)site; e.cls = (uint8_t)csel; e.slot = (uint8_t)slot;
-                e.flags = pick.tie ? 1 : 0; e.total_rate = pick.total;
-                reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
-            }
-        }
-        if (hl == csel) hist++;
-        if (pick.tie && hl == 0) n_ties++;
-
-        // ---- 4. the move (uniform inside the half): touched nodes, old and new status ------------------
-        MoveNodes mv;
-        int os1, os2;
-        {
-            const MoveEntry e = MOVE_TABLE[slot];
-            mv.ns0 = (int)((((uint32_t)s0 | (e.w0 & 0xF)) & ((e.w0 >> 4) & 0xF)) ^ ((e.w0 >> 8) & 0xF));
-            mv.na = (int)((e.w0 >> 12) & 3);
-            mv.da1 = (int)(e.w1 & 0xF) - 2;
-            mv.a1 = wrapT<TD0>(row + mv.da1, d0);
-            mv.b1 = wrapT<TD1>(col + (int)((e.w1 >> 4) & 0xF) - 2, d1);
-            mv.a2 = wrapT<TD0>(row + (int)((e.w1 >> 8) & 0xF) - 2, d0);
-            mv.b2 = wrapT<TD1>(col + (int)((e.w1 >> 12) & 0xF) - 2, d1);
-            mv.ns1 = (int)((e.w1 >> 16) & 0xF); mv.ns2 = (int)((e.w1 >> 20) & 0xF);
-            os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
-        }
-        const int na = mv.na;
-        if (hl < HW_PLANES) {
-            uint32_t *P32 = reinterpret_cast<uint32_t *>(PL + hl * d0);
-            {
-                uint32_t *wp = P32 + 2 * row + (col >> 5);
-                const uint32_t bit = 1u << (col & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns0) == hl ? bit : 0u);
-            }
-            if (na > 1) {
-                uint32_t *wp = P32 + 2 * mv.a1 + (mv.b1 >> 5);
-                const uint32_t bit = 1u << (mv.b1 & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns1) == hl ? bit : 0u);
-            }
-            if (na > 2) {
-                uint32_t *wp = P32 + 2 * mv.a2 + (mv.b2 >> 5);
-                const uint32_t bit = 1u << (mv.b2 & 31);
-                *wp = (*wp & ~bit) | (status_plane(mv.ns2) == hl ? bit : 0u);
-            }
-        }
-        // ---- 5a. own-status classes: owner lanes fold (old -> new) of each touched node -----------------
-        if (my_g1) {
-            int d = (int)((my_g1 >> (2 * mv.ns0)) & 3u) - (int)((my_g1 >> (2 * s0)) & 3u);
-            if (d) rc16[hl * d0p + row] = (uint16_t)(rc16[hl * d0p + row] + d);
-            int dsum = d;
-            if (na > 1) {
-                d = (int)((my_g1 >> (2 * mv.ns1)) & 3u) - (int)((my_g1 >> (2 * os1)) & 3u);
-                if (d) rc16[hl * d0p + mv.a1] = (uint16_t)(rc16[hl * d0p + mv.a1] + d);
-                dsum += d;
-            }
-            if (na > 2) {
-                d = (int)((my_g1 >> (2 * mv.ns2)) & 3u) - (int)((my_g1 >> (2 * os2)) & 3u);
-                if (d) rc16[hl * d0p + mv.a2] = (uint16_t)(rc16[hl * d0p + mv.a2] + d);
-                dsum += d;
-            }
-            tot += dsum;
-        }
-        HS::sync(hw);
-
-        // ---- 5b. MoveDivacancy: band rows row+lo .. row+hi re-derived and replaced, two rows per pass ----
-        int lo = -1, hi = 1;
-        if (slot >= 13) hi = 3;
-        else if (slot >= 7) { lo += mv.da1 < 0 ? mv.da1 : 0; hi += mv.da1 > 0 ? mv.da1 : 0; }
-        {
-            const int nrows = hi - lo + 1;
-            const int nloop = HS::umax(hw, nrows);              // lockstep: the longer band of the two halves
-            uint32_t d01 = 0, d23 = 0;
-            for (int j0 = 0; j0 < nloop; j0 += 2) {
-                const int j = j0 + my_g;
-                const bool act = hl < 12 && j < nrows;
-                const int ra = wrapT<TD0>(row + lo + (j < nrows ? j : 0), d0);
-                uint32_t pk01 = 0, pk23 = 0;
-                if (act) {
-                    u64 pr, ne, fa;
-                    hw_dir_masks<TD0>(PL, d0, ra, my_dir, rb, pr, ne, fa);
-                    kind_counts(pr, ne, fa, pk01, pk23);
-                }
-                pk01 += HSHFL_DOWN(pk01, 3);
-                pk23 += HSHFL_DOWN(pk23, 3);
-                pk01 += HSHFL_DOWN(pk01, 1) + HSHFL_DOWN(pk01, 2);
-                pk23 += HSHFL_DOWN(pk23, 1) + HSHFL_DOWN(pk23, 2);
-                if (act && my_k == 0) {
-                    uint16_t *q = rc16 + C_MOVE_DIV * d0p + ra;
-                    const uint32_t o0 = q[0], o1 = q[d0p], o2 = q[2 * d0p], o3 = q[3 * d0p];
-                    q[0] = (uint16_t)pk01; q[d0p] = (uint16_t)(pk01 >> 16);
-                    q[2 * d0p] = (uint16_t)pk23; q[3 * d0p] = (uint16_t)(pk23 >> 16);
-                    d01 += pk01 - (o0 | (o1 << 16));
-                    d23 += pk23 - (o2 | (o3 << 16));
-                }
-            }
-            // the two group leaders (half-lanes 0 and 6) hold the packed signed deltas
-            const int s01 = (int)(HSHFL(d01, 0) + HSHFL(d01, 6));
-            const int s23 = (int)(HSHFL(d23, 0) + HSHFL(d23, 6));
-            const int l01 = (int)(short)(s01 & 0xFFFF), l23 = (int)(short)(s23 & 0xFFFF);
-            if (hl == C_MOVE_DIV) tot += l01;
-            if (hl == C_MOVE_DIV + 1) tot += (s01 - l01) >> 16;
-            if (hl == C_MOVE_DIV + 2) tot += l23;
-            if (hl == C_MOVE_DIV + 3) tot += (s23 - l23) >> 16;
-        }
-        // ---- 5c. CreateTrefoil: anchor rows row-3 .. row+2 -------------------------------------------------
-        {
-            const int ng = d0 < 6 ? d0 : 6;
-            int d = 0;
-            if (hl < ng) {
-                const int ra = wrapT<TD0>(row + hl - 3, d0);
-                u64 up, dn;
-                hw_trefoil_masks<TD0>(PL, d0, ra, rb, up, dn);
-                const int nw = __popcll(up) + __popcll(dn);
-                uint16_t *q = rc16 + C_CREATE_TREF * d0p + ra;
-                d = nw - (int)q[0];
-                q[0] = (uint16_t)nw;
-            }
-            int s = d + HSHFL_DOWN(d, 3);                      // half-lanes 0..5 hold the row deltas
-            s += HSHFL_DOWN(s, 1) + HSHFL_DOWN(s, 2);
-            s = HSHFL(s, 0);
-            if (hl == C_CREATE_TREF) tot += s;
-        }
-        HS::sync(hw);
+    // the event loop: in lockstep while both halves can continue, then whatever is left on its own
+    // (normally nothing; a half whose partner hit a zero total rate, or never existed)
+    if (pair_ok) {
+#define KMC_HW_LOCK true
+#include "replica_hw_body.inc"
+#undef KMC_HW_LOCK
     }
-    };   // run
-    if (pair_ok) run(std::true_type());
-    run(std::false_type());                 // the rest: nothing, or a half whose partner stopped / never existed
+#define KMC_HW_LOCK false
+#include "replica_hw_body.inc"
+#undef KMC_HW_LOCK
 
 
     // ---- epilogue ------------------------------------------------------------------------------------
