@@ -390,7 +390,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (log_mode != KMC_LOG_NONE && !host_events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
     // rows of <= 64 sites run on the bit-sliced kernels (two replicas per warp by default), wider rows on
     // the byte-lattice kernel
-    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 &&
+    // (two replicas per warp pay off once one replica per warp would already fill the GPU; small batches and
+    // single trajectories are latency-bound and run faster with a full warp each)
+    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 && h->R >= 4096 &&
                                               2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
