@@ -399,7 +399,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         const size_t hbytes = replica_hw_bytes(h->d0);
         if (2 * hbytes > (size_t)h->max_smem_optin) return fail(KMC_ERR_ARG, "lattice too large for the half-warp kernel");
         int hpb = h->warps_per_block > 0 ? 2 * h->warps_per_block : 16;      // replicas (half-warps) per block
+        if (const char *e = getenv("KMC_HW_REPLICAS_PER_BLOCK")) hpb = atoi(e) & ~1;     // tuning knob
         if (hpb > 16) hpb = 16;
+        if (hpb < 2) hpb = 2;
         while (hpb > 2 && hpb * hbytes > (size_t)h->max_smem_optin) hpb -= 2;
         const size_t smem = hpb * hbytes;
         const size_t rs = record_size(log_mode);
