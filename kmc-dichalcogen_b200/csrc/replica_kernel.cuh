@@ -259,6 +259,41 @@ __device__ __forceinline__ uint32_t site_slot_mask(const uint8_t *st, int a, int
 // totals, then a rank search among the sites of the chosen slot.
 __device__ __forceinline__ void find_in_row_bytes(const uint8_t *st, int d0, int d1, int row, int c, uint32_t r,
                                                   int lane, int &col, int &slot) {
+    if (d1 > 64 && d1 <= 1024) {
+        // Wide rows: each lane owns a contiguous run of <= 32 sites and evaluates every site ONCE, keeping
+        // one bit mask per slot (a lane's sites share cache lines, and no cross-lane step sits between the
+        // loads, so the latency of an HBM/L2-resident lattice is paid once, not once per 32-site chunk).
+        const int per = (d1 + 31) >> 5;
+        const int b0 = lane * per;
+        uint32_t m[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        for (int i = 0; i < per; i++) {
+            const int b = b0 + i;
+            const uint32_t sm = b < d1 ? site_slot_mask(st, row, b, d0, d1, c) : 0u;
+#pragma unroll
+            for (int q = 0; q < 6; q++) m[q] |= ((sm >> q) & 1u) << i;
+        }
+        uint32_t a01 = __popc(m[0]) | (__popc(m[1]) << 16);
+        uint32_t a23 = __popc(m[2]) | (__popc(m[3]) << 16);
+        uint32_t a45 = __popc(m[4]) | (__popc(m[5]) << 16);
+        a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
+        int j = 0;
+        {
+            const uint32_t cnt[6] = {a01 & 0xFFFFu, a01 >> 16, a23 & 0xFFFFu, a23 >> 16, a45 & 0xFFFFu, a45 >> 16};
+#pragma unroll
+            for (int q = 0; q < 5; q++)
+                if (j == q && r >= cnt[q]) { r -= cnt[q]; j = q + 1; }
+        }
+        uint32_t mine = m[0];
+#pragma unroll
+        for (int q = 1; q < 6; q++) mine = j == q ? m[q] : mine;
+        int L = 0;
+        warp_rank_search(__popc(mine), r, L, lane);           // r becomes the rank inside lane L's run
+        uint32_t mL = __shfl_sync(FULL, mine, L);
+        for (uint32_t i = 0; i < r; i++) mL &= mL - 1;
+        col = L * per + __ffs(mL) - 1;
+        slot = class_slot_base(c) + j;
+        return;
+    }
     uint32_t a01 = 0, a23 = 0, a45 = 0;                     // six 16-bit per-slot counters
     for (int base = 0; base < d1; base += 32) {
         const int b = base + lane;
@@ -438,19 +473,25 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
             if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
             r = (uint32_t)rr;
         }
-        // 3a. row: two rows per lane per pass
+        // 3a. row: each lane owns a contiguous block of rows (2 per pass; 8 when the lattice is tall)
         int row = 0;
         {
             const int f = rc_field(csel);
-            for (int base = 0; base < d0; base += 64) {
-                const int r0 = base + 2 * lane;
-                const uint32_t v0 = (r0 < d0) ? rc16[r0 * (2 * RC_WORDS) + f] : 0u;
-                const uint32_t v1 = (r0 + 1 < d0) ? rc16[(r0 + 1) * (2 * RC_WORDS) + f] : 0u;
+            const int K = d0 > 256 ? 8 : 2;
+            for (int base = 0; base < d0; base += 32 * K) {
+                const int r0 = base + K * lane;
+                uint32_t sum = 0;
+                for (int q = 0; q < K; q++)
+                    if (r0 + q < d0) sum += rc16[(r0 + q) * (2 * RC_WORDS) + f];
                 int L;
-                if (warp_rank_search(v0 + v1, r, L, lane)) {
-                    const uint32_t v0L = __shfl_sync(FULL, v0, L);
-                    row = base + 2 * L;
-                    if (r >= v0L) { r -= v0L; row++; }
+                if (warp_rank_search(sum, r, L, lane)) {
+                    // walk the owner lane's rows (uniform: every lane reads the same entries)
+                    row = base + K * L;
+                    for (int q = 0; q < K - 1; q++) {
+                        const uint32_t v = rc16[row * (2 * RC_WORDS) + f];
+                        if (r < v) break;
+                        r -= v; row++;
+                    }
                     break;
                 }
             }
