@@ -275,6 +275,35 @@ def test_zero_total_rate_raises_value_error():
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [2, 4])
+def test_one_replica_of_a_pair_stops_the_other_continues(variant):
+    """Two replicas share a warp in the half-warp kernel: when one reaches total rate zero the lockstep
+    phase ends and the partner finishes on its own, still bit-equal to the oracle."""
+    dim = (8, 8)
+    rates = [0.0] * 13
+    rates[1] = 5.0                                   # FillDivacancy only: the lattice drains
+    a = np.zeros(64, np.uint8); a[[3, 17]] = 3       # two events, then nothing can happen
+    b = np.zeros(64, np.uint8); b[::2] = 3           # 32 events available
+    c = np.zeros(64, np.uint8); c[[5]] = 3
+    st0 = np.stack([a, b, c])
+    eng = Engine(dim, rates, [1], n_replicas=3)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(st0)
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.run(20, 7, log_mode=nat.LOG_FULL, validate=True)
+    ev = eng._last_events
+    assert list(eng.steps_done()) == [2, 20, 1]
+    for r in range(3):
+        o = ko.Oracle(dim, rates, [1], st0[r])
+        done, want = o.run_philox(7, r, 0, 20)
+        assert done == eng.steps_done()[r]
+        assert_events_equal(ev[r][:done], want[:done], "replica %d" % r)
+        assert ev[r]["cls"][done] == 0xFF if done < 20 else True
+    final = eng.download_state()
+    assert (final[0] == 0).all() and (final[2] == 0).all() and (final[1] == 3).sum() == 12
+    eng.close()
+
+
 def test_perform_given_move():
     dim = (8, 8)
     st = evolved_state(dim, 5)
