@@ -165,6 +165,35 @@ def main():
     trajectory("allrules_40x70", (40, 70), ALL_RULES, exact_state((40, 70), 0.1, 0.1, 2), seed=6,
                nsteps=1500, replica=3)
     state_gen_fixtures()
+    native_statistics()
+
+
+def native_statistics():
+    """The reference run with ITS OWN random draws (random / numpy.random, seeded only to make this file
+    reproducible): per-step class frequencies over many short trajectories.  Pins the probability law
+    -- in particular that our canonical tie-break and in-class order do not change it."""
+    import random as pyrandom
+    mods = ref_oracle.ref()
+    dim, nsteps, ntraj = (12, 12), 40, 400
+    status0 = exact_state(dim, 0.15, 0.10, 77)
+    counts = np.zeros((nsteps, canon.N_CLASSES), dtype=np.int64)
+    for tr in range(ntraj):
+        pyrandom.seed(1000 + tr)
+        np.random.seed(1000 + tr)
+        specs = ref_oracle.make_rule_specs(ALL_RULES)
+        init = ref_oracle.state_from_status(list(map(int, status0)), dim)
+        with ref_oracle.ref_modules():
+            sim = mods["sim"].KmcSim(init, specs, incremental=True)
+            for t in range(nsteps):
+                d = sim.perform_random_move()
+                counts[t, canon.CLASS_ID[(d["rule"], d["kind"])]] += 1
+    st = ref_oracle.RefStepper(list(map(int, status0)), dim, ALL_RULES)
+    path = os.path.join(OUT, "native_stats.npz")
+    np.savez_compressed(path, meta=json.dumps({"dim": list(dim), "nsteps": nsteps, "ntraj": ntraj,
+                                               "class_order": st.class_order(),
+                                               "source": "reference KmcSim.perform_random_move with its own RNGs"}),
+                        status0=status0, rates=np.array(st.rates()), counts=counts)
+    print("native_stats.npz: %d trajectories x %d steps (%d bytes)" % (ntraj, nsteps, os.path.getsize(path)))
 
 
 if __name__ == "__main__":

@@ -304,6 +304,29 @@ def test_one_replica_of_a_pair_stops_the_other_continues(variant):
     eng.close()
 
 
+def test_class_frequencies_match_the_reference_with_its_own_rng():
+    """Statistical parity: 4096 replicas on the GPU (Philox) against 400 trajectories of the reference run
+    with its own random draws (tests/golden/native_stats.npz): per-step class frequencies."""
+    import json
+    import os
+    from scipy.stats import chi2
+    from util_golden import GOLDEN, chi2_two_sample
+    z = np.load(os.path.join(GOLDEN, "native_stats.npz"))
+    m = json.loads(str(z["meta"]))
+    nrep, nsteps = 4096, m["nsteps"]
+    eng = Engine(m["dim"], z["rates"], m["class_order"], n_replicas=nrep)
+    eng.upload_state(np.tile(z["status0"], (nrep, 1)))
+    ev = eng.run(nsteps, 987654321, log_mode=nat.LOG_COMPACT, validate=True)
+    ours = np.zeros((nsteps, 13), dtype=np.int64)
+    for t in range(nsteps):
+        ours[t] = np.bincount(ev[:, t]["cls"], minlength=13)
+    for t in (0, 1, 5, 10, 20, 39):
+        stat, dof = chi2_two_sample(z["counts"][t], ours[t])
+        assert chi2.sf(stat, dof) > 1e-4, (t, stat, dof)
+    assert (eng.histogram() == ours.sum(axis=0)).all()
+    eng.close()
+
+
 def test_perform_given_move():
     dim = (8, 8)
     st = evolved_state(dim, 5)

@@ -125,3 +125,28 @@ def test_batch_runner_matches_single():
         o.run_philox(m["seed"], r, 0, 500, log=False)
         assert (o.status() == st[r]).all()
     assert hist.sum() == done
+
+
+def test_class_frequencies_match_the_reference_run_with_its_own_rng():
+    """Statistical parity (north star): the reference stepped with ITS OWN random draws versus the
+    oracle stepped with Philox draws -- per-step class frequencies over many trajectories must be
+    samples of the same distribution (two-sample chi-square, p > 1e-4 at every checked step)."""
+    import json
+    from scipy.stats import chi2
+    from util_golden import GOLDEN, chi2_two_sample
+    z = np.load(os.path.join(GOLDEN, "native_stats.npz"))
+    m = json.loads(str(z["meta"]))
+    dim, nsteps = m["dim"], m["nsteps"]
+    ours = np.zeros((nsteps, 13), dtype=np.int64)
+    ntraj = 3000
+    for r in range(ntraj):
+        o = ko.Oracle(dim, z["rates"], m["class_order"], z["status0"])
+        _, ev = o.run_philox(4242, r, 0, nsteps)
+        ours[np.arange(nsteps), ev["cls"]] += 1
+    worst = 1.0
+    for t in (0, 1, 5, 10, 20, 39):
+        stat, dof = chi2_two_sample(z["counts"][t], ours[t])
+        worst = min(worst, chi2.sf(stat, dof))
+    assert worst > 1e-4, worst
+    stat, dof = chi2_two_sample(z["counts"].sum(axis=0), ours.sum(axis=0))
+    assert chi2.sf(stat, dof) > 1e-4
