@@ -726,7 +726,10 @@ struct SweepRollParams {
 };
 constexpr int ROLL_MAX_ROWS = 16;
 
-__global__ void __launch_bounds__(256, 3) kmc_sweep_roll_kernel(const SweepRollParams p)
+#ifndef KMC_ROLL_OCC
+#define KMC_ROLL_OCC 3
+#endif
+__global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const SweepRollParams p)
 {
     __shared__ uint32_t part[ROLL_MAX_ROWS][8][8];       // [row step][warp][7 count pairs]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
