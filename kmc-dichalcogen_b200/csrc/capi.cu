@@ -15,6 +15,7 @@
 #include "replica_kernel.cuh"
 #include "replica_bp_kernel.cuh"
 #include "replica_hw_kernel.cuh"
+#include "replica_wide_kernel.cuh"
 #include "sweep_kernel.cuh"
 
 using namespace kmc;
@@ -53,6 +54,10 @@ struct kmc_engine {
     int *d_result = nullptr;
     double *d_clock = nullptr; bool clock_on = false;        // optional KMC clock per replica
     uint32_t *d_hier = nullptr; bool hier_valid = false;   // row hierarchy of HBM-resident lattices
+    // wide bit-sliced kernel (rows of 64*W sites): planes + row table live in HBM between launches.  While
+    // planes_valid they describe the current lattice; bytes_stale means d_status lags behind them.
+    unsigned long long *d_planes = nullptr; uint16_t *d_whier = nullptr, *d_whier_chk = nullptr;
+    bool planes_valid = false, bytes_stale = false;
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
@@ -136,6 +141,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock);
+    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -170,6 +176,18 @@ __global__ void kmc_check_state_kernel(const uint8_t *status, long long total, i
     }
 }
 
+// bring the status bytes up to date after launches of the wide bit-sliced kernel
+static int ensure_bytes(kmc_engine *h)
+{
+    if (!h->bytes_stale) return KMC_OK;
+    const long long cells = (long long)h->R * h->d0 * (h->d1 >> 6);
+    kmc_wide_unpack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_status, h->R, h->d0, h->d1);
+    CU(cudaGetLastError());
+    h->launches += 1;
+    h->bytes_stale = false;
+    return KMC_OK;
+}
+
 static int check_state_device(kmc_engine *h)
 {
     CU(cudaMemsetAsync(h->d_result, 0, sizeof(int), h->stream));
@@ -190,7 +208,7 @@ extern "C" int kmc_upload_state(kmc_engine *h, const uint8_t *host_status)
     int rc = bind(h); if (rc) return rc;
     if (!host_status) return fail(KMC_ERR_ARG, "kmc_upload_state: null buffer");
     CU(cudaMemcpyAsync(h->d_status, host_status, (size_t)h->R * h->n, cudaMemcpyHostToDevice, h->stream));
-    h->swept = false; h->hier_valid = false;
+    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
     return check_state_device(h);
 }
 
@@ -198,6 +216,7 @@ extern "C" int kmc_download_state(kmc_engine *h, uint8_t *host_status)
 {
     int rc = bind(h); if (rc) return rc;
     if (!host_status) return fail(KMC_ERR_ARG, "kmc_download_state: null buffer");
+    rc = ensure_bytes(h); if (rc) return rc;
     CU(cudaMemcpyAsync(host_status, h->d_status, (size_t)h->R * h->n, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
@@ -208,7 +227,7 @@ extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
     int rc = bind(h); if (rc) return rc;
     if (!dev_status) return fail(KMC_ERR_ARG, "kmc_set_state_device: null pointer");
     CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
-    h->swept = false; h->hier_valid = false;
+    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
     return check_state_device(h);
 }
 
@@ -216,6 +235,7 @@ extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)
 {
     int rc = bind(h); if (rc) return rc;
     if (!dev_status) return fail(KMC_ERR_ARG, "kmc_get_state_device: null pointer");
+    rc = ensure_bytes(h); if (rc) return rc;
     CU(cudaMemcpyAsync(dev_status, h->d_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
@@ -225,6 +245,7 @@ extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)
 static int sweep_launch(kmc_engine *h, bool with_slots)
 {
     const size_t R = (size_t)h->R;
+    { int rc = ensure_bytes(h); if (rc) return rc; }
     if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * RCG_STRIDE * sizeof(uint32_t)));
     if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * NS * h->n));
     // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas, one launch in total
@@ -392,6 +413,67 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // the byte-lattice kernel
     // (two replicas per warp pay off once one replica per warp would already fill the GPU; small batches and
     // single trajectories are latency-bound and run faster with a full warp each)
+    const bool wide_ok = h->d1 > 64 && (h->d1 & 63) == 0 && h->d1 <= 2048 &&
+                         wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
+    if (h->variant == 5 && !wide_ok)
+        return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs dim1 a multiple of 64 in (64, 2048] and dim0 <= ~8700");
+    // auto: lattices whose byte form does not fit shared memory
+    if (h->variant == 5 || (h->variant == 0 && wide_ok && replica_warp_bytes(h->d0, h->d1) > (size_t)h->max_smem_optin)) {
+        const int Ww = h->d1 >> 6, d0p = (h->d0 + 1) & ~1;
+        const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * Ww;
+        const size_t hier_elems = (size_t)h->R * NC * d0p;
+        if (!h->d_planes) {
+            CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
+            CU(cudaMalloc(&h->d_whier, hier_elems * sizeof(uint16_t)));
+        }
+        if (!h->planes_valid) {
+            int rc = ensure_bytes(h); if (rc) return rc;
+            const long long cells = (long long)h->R * h->d0 * Ww, rows = (long long)h->R * h->d0;
+            kmc_wide_pack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_status, h->d_planes, h->R, h->d0, h->d1);
+            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p);
+            CU(cudaGetLastError());
+            h->launches += 2;
+            h->planes_valid = true;
+        }
+        const size_t wbytes = wide_warp_bytes(h->d0);
+        int wpb = h->warps_per_block > 0 ? h->warps_per_block : (h->R + 147) / 148;    // spread small batches over the SMs
+        if (wpb > 8) wpb = 8;
+        while (wpb > 1 && wpb * wbytes > (size_t)h->max_smem_optin) wpb--;
+        const size_t smem = wpb * wbytes;
+        const size_t rs = record_size(log_mode);
+        if (rs) { int rc = ensure_events(h, rs * (size_t)h->R * (size_t)nsteps); if (rc) return rc; }
+        WideParams q;
+        ReplicaParams &p = q.base;
+        p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
+        p.status = h->d_status;
+        for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+        p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
+        p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.validate = validate;
+        p.clock = h->clock_on ? h->d_clock : nullptr;
+        p.hier = nullptr; p.hier_valid = 0;
+        q.planes = h->d_planes; q.hier = h->d_whier; q.W = Ww; q.d0p = d0p;
+        CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
+        CU(cudaGetLastError());
+        h->launches += 1;
+        if (validate) {          // the incrementally maintained row table against a fresh one from the planes
+            if (!h->d_whier_chk) CU(cudaMalloc(&h->d_whier_chk, hier_elems * sizeof(uint16_t)));
+            const long long rows = (long long)h->R * h->d0;
+            CU(cudaMemsetAsync(h->d_whier_chk, 0, hier_elems * sizeof(uint16_t), h->stream));
+            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier_chk, h->R, h->d0, h->d1, d0p);
+            kmc_wide_compare_kernel<<<(unsigned)((hier_elems + 255) / 256), 256, 0, h->stream>>>(
+                h->d_whier, h->d_whier_chk, (long long)NC * d0p, h->R, h->d_flags);
+            CU(cudaGetLastError());
+            h->launches += 2;
+        }
+        h->swept = false; h->hier_valid = false;
+        h->bytes_stale = true;
+        if (rs) CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
+        return KMC_OK;
+    }
+    { int rc = ensure_bytes(h); if (rc) return rc; }
     const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 && h->R >= 4096 &&
                                               2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
@@ -426,7 +508,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         }
         CU(cudaGetLastError());
         h->launches += 1;
-        h->swept = false; h->hier_valid = false;
+        h->swept = false; h->hier_valid = false; h->planes_valid = false;
         if (rs) CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
         return KMC_OK;
     }
@@ -489,6 +571,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     h->launches += 1;
     h->swept = false;
     h->hier_valid = global_state;          // only this path keeps it; any other lattice change drops it
+    h->planes_valid = false;
     if (rs) {
         CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
     }
@@ -526,6 +609,7 @@ extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int 
     int rc = bind(h); if (rc) return rc;
     if (replica < 0 || replica >= h->R || site >= (uint32_t)h->n || slot < 0 || slot >= NS)
         return fail(KMC_ERR_ARG, "kmc_perform_given: bad replica / site / slot");
+    rc = ensure_bytes(h); if (rc) return rc;
     kmc_apply_given_kernel<<<1, 1, 0, h->stream>>>(h->d_status + (size_t)replica * h->n, h->d0, h->d1,
                                                    (int)site, slot, h->d_result);
     CU(cudaGetLastError());
@@ -533,7 +617,7 @@ extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int 
     int res = 0;
     CU(cudaMemcpyAsync(&res, h->d_result, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->swept = false; h->hier_valid = false;
+    h->swept = false; h->hier_valid = false; h->planes_valid = false;
     if (res) return fail(KMC_ERR_ARG, "kmc_perform_given: that move does not exist on the current lattice");
     return KMC_OK;
 }
@@ -563,7 +647,7 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
         CU(cudaGetLastError());
         h->launches += 1;
     }
-    h->swept = false; h->hier_valid = false;
+    h->swept = false; h->hier_valid = false; h->planes_valid = false;
     if (rs) CU(cudaMemcpyAsync(events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
     return check_flags(h, false);
 }
@@ -721,7 +805,7 @@ extern "C" int kmc_get_launch_count(kmc_engine *h, int64_t *out)
 extern "C" int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **row_counts, void **histogram)
 {
     if (!h) return fail(KMC_ERR_ARG, "null engine handle");
-    if (status) *status = h->d_status;
+    if (status) { int rc = bind(h); if (rc) return rc; rc = ensure_bytes(h); if (rc) return rc; *status = h->d_status; }
     if (slots) *slots = h->d_slots;
     if (row_counts) *row_counts = h->d_rowcnt;
     if (histogram) *histogram = h->d_hist;
@@ -742,9 +826,9 @@ extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
 }
 extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)
 {
-    if (!h || variant < 0 || variant > 4)
+    if (!h || variant < 0 || variant > 5)
         return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (byte lattice), 2 (bit planes, warp per replica), "
-                                 "3 (byte lattice in HBM) or 4 (bit planes, half-warp per replica)");
+                                 "3 (byte lattice in HBM), 4 (bit planes, half-warp per replica) or 5 (wide bit planes in HBM)");
     h->variant = variant;
     return KMC_OK;
 }

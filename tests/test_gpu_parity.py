@@ -147,6 +147,82 @@ def test_large_lattice_incremental_1024():
     eng.close()
 
 
+@pytest.mark.parametrize("dim", [(12, 128), (40, 192), (7, 320), (130, 128), (64, 2048), (5, 128), (1100, 128)])
+def test_wide_bitplane_kernel_matches_oracle(dim):
+    """Variant 5: bit planes of rows wider than one word kept in HBM, row table in shared memory."""
+    nrep, nsteps, seed = 3, 5000, 4711
+    st0 = np.stack([evolved_state(dim, 40 + r, nsteps=300) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.set_replica_kernel(5)
+    eng.upload_state(st0)
+    n1 = 1777
+    ev = np.concatenate([eng.run(n1, seed, log_mode=nat.LOG_FULL, validate=True),
+                         eng.run(nsteps - n1, seed, log_mode=nat.LOG_FULL, validate=True)], axis=1)
+    final = eng.download_state()
+    for r in range(nrep):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
+        _, want = o.run_philox(seed, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "wide replica %d" % r)
+        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (final[r] == o.status()).all()
+    eng.close()
+
+
+def test_wide_kernel_interleaves_with_the_byte_paths():
+    """Planes are authoritative after a wide launch; every byte-side entry point must see the same lattice:
+    wide run -> sweep -> perform_given -> byte-kernel run -> wide run -> injected draws."""
+    dim, seed = (24, 128), 31
+    st0 = evolved_state(dim, 5, nsteps=300)
+    o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=1)
+    eng.set_replica_kernel(5)
+    eng.upload_state(st0)
+    ev = eng.run(700, seed, log_mode=nat.LOG_COMPACT, validate=True)[0]
+    _, want = o.run_philox(seed, 0, 0, 700)
+    assert_events_equal(ev, want, "wide 1")
+    eng.sweep()
+    assert (eng.counts()[0] == o.counts()).all()
+    assert (eng.slots()[0] == o.slots()).all()
+    # an explicit move: first CreateDivacancy-capable site
+    site = int(np.flatnonzero(o.status() == 0)[0])
+    o.perform_given(site, 0)
+    eng.perform_given(0, site, 0)
+    eng.set_replica_kernel(3)
+    ev = eng.run(500, seed, log_mode=nat.LOG_COMPACT, validate=True)[0]
+    _, want = o.run_philox(seed, 0, 700, 500)
+    assert_events_equal(ev, want, "byte after wide")
+    eng.set_replica_kernel(5)
+    ev = eng.run(500, seed, log_mode=nat.LOG_COMPACT, validate=True)[0]
+    _, want = o.run_philox(seed, 0, 1200, 500)
+    assert_events_equal(ev, want, "wide 2")
+    d = philox.draws(seed + 1, 0, 0, 300)
+    ev = eng.step_draws(d, log_mode=nat.LOG_COMPACT, validate=True)[0]
+    _, want = o.run_draws(d)
+    assert_events_equal(ev, want, "wide draws")
+    assert (eng.download_state()[0] == o.status()).all()
+    assert (eng.histogram_per_replica()[0] == o.hist()).all()
+    eng.close()
+
+
+def test_wide_kernel_stops_on_zero_total_rate():
+    dim = (8, 128)
+    rates = [0.0] * 13
+    rates[1] = 5.0                                   # FillDivacancy only: runs out after the divacancies
+    st0 = np.zeros(dim[0] * dim[1], np.uint8)
+    st0[[3, 200, 777]] = 3
+    eng = Engine(dim, rates, [1], n_replicas=2)
+    eng.set_replica_kernel(5)
+    eng.upload_state(np.stack([st0, st0]))
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.run(10, 1, log_mode=nat.LOG_COMPACT)
+    ev = eng._last_events
+    assert (eng.steps_done() == 3).all()
+    assert (ev[:, 3]["cls"] == nat.CLASS_NONE).all()
+    assert (eng.download_state() == 0).all()
+    eng.close()
+
+
 @pytest.mark.parametrize("variant", [1, 2, 4])
 def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
     """Extension: t = sum 1/total_rate, accumulated in event order, bit-equal to the
