@@ -381,6 +381,15 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
                 r -= v; row++;
             }
         }
+        // the refresh below reads Z and D of rows row-3 .. row+3: start those lines moving now, under the site search
+        {
+            const int lines = (W * 8 + 127) >> 7;              // 128-byte lines per plane row (<= 2)
+            const int j = lane >> 2, pl = (lane >> 1) & 1, li = lane & 1;
+            if (j < 7 && li < lines) {
+                const int a = wrap1(wrap1(row - 3 + j, d0), d0);
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)pl * d0 + a) * W + li * 16));
+            }
+        }
         // ---- slot and site inside the row: one lane per word (W <= 32), slots in class order ------------------
         int col, slot, s0;
         {
@@ -489,10 +498,12 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         const int na = mv.na;
         // lanes 0..5 own a plane each: start fetching the words they will rewrite
         const int as[3] = {row, mv.a1, mv.a2}, bcol[3] = {col, mv.b1, mv.b2}, ns[3] = {mv.ns0, mv.ns1, mv.ns2};
-        if (lane < N_TYPES) {
+        const int os[3] = {s0, os1, os2};
+        bool mine[3];                                          // does node i leave or enter this lane's plane?
 #pragma unroll
-            for (int i = 0; i < 3; i++)
-                if (i < na) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6)));
+        for (int i = 0; i < 3; i++) {
+            mine[i] = i < na && lane < N_TYPES && (status_plane(os[i]) == lane || status_plane(ns[i]) == lane);
+            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6)));
         }
         // Refresh of the five neighbourhood classes.  Every dependency of a site is inside its ring of six
         // neighbours (rows +-1, columns +-1) or, for trefoils, at (+2, 0), (0, +2), (+2, -2).  So the tasks
@@ -540,15 +551,13 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             }
         }
         __syncwarp();
-        if (lane < N_TYPES) {
 #pragma unroll
-            for (int i = 0; i < 3; i++)
-                if (i < na) {
-                    u64 *wptr = P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6);
-                    const u64 bit = 1ull << (bcol[i] & 63);
-                    *wptr = (*wptr & ~bit) | (status_plane(ns[i]) == lane ? bit : 0ull);
-                }
-        }
+        for (int i = 0; i < 3; i++)
+            if (mine[i]) {
+                u64 *wptr = P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6);
+                const u64 bit = 1ull << (bcol[i] & 63);
+                *wptr = (*wptr & ~bit) | (status_plane(ns[i]) == lane ? bit : 0ull);
+            }
         // own-status classes (owner lanes, shared-memory row table)
         if (my_g1) {
             int d = (int)((my_g1 >> (2 * mv.ns0)) & 3u) - (int)((my_g1 >> (2 * s0)) & 3u);
