@@ -87,6 +87,14 @@ int kmc_destroy(kmc_engine *h);
 /* KmcSim.initialize(state) (sim.py:46-54): replace the lattices.  host: [n_replicas][dim0*dim1]. */
 int kmc_upload_state(kmc_engine *h, const uint8_t *host_status);
 int kmc_download_state(kmc_engine *h, uint8_t *host_status);
+/* gen_random_state (state.py:329-378) on the device, one Philox stream per replica (key = (seed, replica0 + r),
+ * counter domain 1; see csrc/stategen_kernel.cuh for the draw recipe).  The caller passes the plan the
+ * reference derives on the host: mode 0 'exact' -- n_keys runs of the shuffled node list, run k = positions
+ * [bounds[k], bounds[k+1]) gets codes[k]; mode 1 'approx' -- the sorted live (key, weight) pairs of
+ * weighted_choice as cumulative weights cumul[n_keys].  codes: 3 divacancy, 1 monovacancy (layer drawn per
+ * site), 0 leave pristine.  n_keys <= 3.  Replaces all lattices of the handle. */
+int kmc_generate_state(kmc_engine *h, int mode, int n_keys, const int *codes, const int64_t *bounds,
+                       const double *cumul, uint64_t seed, uint32_t replica0);
 /* same, but the source/destination is a device pointer on the handle's device */
 int kmc_set_state_device(kmc_engine *h, const void *dev_status);
 int kmc_get_state_device(kmc_engine *h, void *dev_status);

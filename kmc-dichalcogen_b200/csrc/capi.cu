@@ -17,6 +17,7 @@
 #include "replica_hw_kernel.cuh"
 #include "replica_wide_kernel.cuh"
 #include "sweep_kernel.cuh"
+#include "stategen_kernel.cuh"
 
 using namespace kmc;
 
@@ -229,6 +230,52 @@ extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
     CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
     h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
     return check_state_device(h);
+}
+
+extern "C" int kmc_generate_state(kmc_engine *h, int mode, int n_keys, const int *codes, const int64_t *bounds,
+                                  const double *cumul, uint64_t seed, uint32_t replica0)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (mode < 0 || mode > 1) return fail(KMC_ERR_ARG, "kmc_generate_state: mode must be 0 (exact) or 1 (approx)");
+    if (n_keys < 1 || n_keys > 3 || !codes) return fail(KMC_ERR_ARG, "kmc_generate_state: 1..3 keys");
+    GenParams p;
+    p.mode = mode; p.n = h->n; p.n_replicas = h->R; p.n_keys = n_keys;
+    p.seed = seed; p.replica0 = replica0; p.status = h->d_status; p.perm = nullptr;
+    for (int k = 0; k < 3; k++) { p.code[k] = 0; p.cumul[k] = 0.0; }
+    for (int k = 0; k < 4; k++) p.bound[k] = 0;
+    for (int k = 0; k < n_keys; k++) {
+        if (codes[k] != 0 && codes[k] != 1 && codes[k] != 3) return fail(KMC_ERR_ARG, "kmc_generate_state: codes are 0, 1 or 3");
+        p.code[k] = codes[k];
+    }
+    if (mode == 0) {
+        if (!bounds) return fail(KMC_ERR_ARG, "kmc_generate_state: exact mode needs bounds");
+        for (int k = 0; k <= n_keys; k++) {
+            p.bound[k] = bounds[k];
+            if (bounds[k] < 0 || bounds[k] > h->n || (k && bounds[k] < bounds[k - 1]))
+                return fail(KMC_ERR_ARG, "kmc_generate_state: bounds must be ascending within [0, sites]");
+        }
+    } else {
+        if (!cumul) return fail(KMC_ERR_ARG, "kmc_generate_state: approx mode needs cumulative weights");
+        for (int k = 0; k < n_keys; k++) {
+            p.cumul[k] = cumul[k];
+            if (!(cumul[k] > 0.0) || (k && cumul[k] < cumul[k - 1]))
+                return fail(KMC_ERR_ARG, "kmc_generate_state: cumulative weights must be positive and ascending");
+        }
+    }
+    CU(cudaMemsetAsync(h->d_status, 0, (size_t)h->R * h->n, h->stream));
+    uint32_t *perm = nullptr;
+    if (mode == 0) {
+        CU(cudaMalloc(&perm, (size_t)h->R * h->n * sizeof(uint32_t)));
+        p.perm = perm;
+    }
+    kmc_generate_state_kernel<<<(unsigned)((h->R + 63) / 64), 64, 0, h->stream>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (perm) cudaFree(perm);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, cudaGetErrorString(e));
+    h->launches += 1;
+    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
+    return KMC_OK;
 }
 
 extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)

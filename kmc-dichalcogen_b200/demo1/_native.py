@@ -37,6 +37,8 @@ SYMBOLS = {
     "kmc_upload_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_download_state": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_set_state_device": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kmc_generate_state": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_uint64, C.c_uint32]),
     "kmc_get_state_device": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_sweep": (C.c_int, [C.c_void_p]),
     "kmc_get_counts": (C.c_int, [C.c_void_p, C.c_void_p]),

@@ -49,6 +49,19 @@ class Engine:
         nat.check(self._lib.kmc_download_state(self._h, out.ctypes.data))
         return out
 
+    def generate_state(self, mode, params, seed, replica0=0):
+        """gen_random_state (reference state.py:329-378) for every replica on the device; replica r gets what
+        ``state.gen_random_state(dim, mode, params, rng=state.PhiloxRandom(seed, replica0 + r))`` gives."""
+        from .state import generator_plan
+        mode_id, codes, bounds, cumul = generator_plan(self.n, mode, params)
+        codes = np.asarray(codes, dtype=np.int32)
+        bounds = np.asarray(bounds, dtype=np.int64)
+        cumul = np.asarray(cumul, dtype=np.float64)
+        nat.check(self._lib.kmc_generate_state(self._h, mode_id, len(codes), codes.ctypes.data,
+                                               bounds.ctypes.data if bounds.size else None,
+                                               cumul.ctypes.data if cumul.size else None,
+                                               int(seed) & (2 ** 64 - 1), int(replica0)))
+
     def set_state_device(self, dev_ptr):
         nat.check(self._lib.kmc_set_state_device(self._h, C.c_void_p(int(dev_ptr))))
 

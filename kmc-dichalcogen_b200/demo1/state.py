@@ -135,6 +135,70 @@ def _assign(state, key, node, rng):
         state.new_vacancy(node, rng.choice(LAYERS))
 
 
+class PhiloxRandom(random.Random):
+    """A ``random.Random`` whose bits come from the Philox stream the device generator uses
+    (csrc/stategen_kernel.cuh): call q of replica r is Philox4x32-10(counter = (q lo, q hi, seed hi, 1),
+    key = (seed lo, r)); ``random()`` = 53 high bits of (x0, x1), ``getrandbits(k <= 32)`` = top k bits of
+    x0.  shuffle / choice / uniform are CPython's own on top of those two."""
+
+    def __init__(self, seed, replica=0):
+        self._pseed, self._replica, self._q = int(seed) & (2 ** 64 - 1), int(replica) & 0xFFFFFFFF, 0
+        super().__init__(0)
+
+    def seed(self, *a, **k):              # the stream is fixed by (seed, replica); random.Random.__init__ calls this
+        pass
+
+    def _block(self):
+        q, s = self._q, self._pseed
+        self._q += 1
+        c = [q & 0xFFFFFFFF, (q >> 32) & 0xFFFFFFFF, s >> 32, 1]
+        k0, k1 = s & 0xFFFFFFFF, self._replica
+        for _ in range(10):
+            p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k0, p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k1, p0 & 0xFFFFFFFF]
+            k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+        return c
+
+    def random(self):
+        c = self._block()
+        return float(((c[0] << 32) | c[1]) >> 11) * 2.0 ** -53
+
+    def getrandbits(self, k):
+        if not 0 < k <= 32:
+            raise ValueError("PhiloxRandom.getrandbits supports 1..32 bits")
+        return self._block()[0] >> (32 - k)
+
+
+def generator_plan(n_sites, mode, params):
+    """What the reference derives before it starts drawing (state.py:342-378), as the arguments of
+    kmc_generate_state: (mode id, status code per key, run bounds [exact], cumulative weights [approx])."""
+    import math
+    params = {k: float(params.get(k, 0.0)) for k in RANDOM_PARAMS}
+    code_of = {"divacancy": 3, "monovacancy": 1, "remainder": 0}
+    if mode == "exact":
+        keys = sorted(RANDOM_PARAMS, key=lambda k: params[k])
+        cumul, acc = [0], 0
+        for k in keys:
+            acc = acc + params[k]
+            cumul.append(acc)
+        return 0, [code_of[k] for k in keys], [round(r * n_sites) for r in cumul], []
+    if mode == "approx":
+        pairs = [(k, params[k]) for k in RANDOM_PARAMS]
+        rest = 1.0 - math.fsum(params.values())
+        if rest > 0:
+            pairs.append(("remainder", rest))
+        live = [(k, w) for (k, w) in pairs if w != 0.0]          # weighted_choice (kmc.py:30-41)
+        if not live:
+            raise ValueError("Cannot choose from total weight of zero!")
+        live.sort(key=lambda kw: kw[1])
+        cumul, acc = [], 0
+        for _, w in live:
+            acc = acc + w
+            cumul.append(acc)
+        return 1, [code_of[k] for k, _ in live], [], cumul
+    raise AssertionError("complete switch")
+
+
 def gen_random_state(dim, mode, params, rng=random, **_kw):
     """Same procedure and the same draws from ``rng`` as the reference's generators, so a seeded
     ``random.Random`` gives the reference's lattice.  Ties between equal fractions are broken by

@@ -138,6 +138,36 @@ def state_gen_fixtures():
     print("state_gen.npz: %d cases (%d bytes)" % (len(cases), os.path.getsize(path)))
 
 
+PHILOX_STATE_CASES = [
+    ("exact", (12, 9), {"divacancy": 0.05, "monovacancy": 0.10}, 11, 0),
+    ("exact", (64, 64), {"divacancy": 0.05, "monovacancy": 0.05 + 1e-9}, 20261019, 0),
+    ("exact", (64, 64), {"divacancy": 0.05, "monovacancy": 0.05 + 1e-9}, 20261019, 16383),
+    ("exact", (7, 5), {"divacancy": 0.0, "monovacancy": 0.5}, 3, 2),
+    ("exact", (33, 47), {"divacancy": 0.30, "monovacancy": 0.20}, (7 << 32) | 9, 1),
+    ("approx", (12, 9), {"divacancy": 0.05, "monovacancy": 0.10}, 11, 0),
+    ("approx", (16, 16), {"divacancy": 0.2, "monovacancy": 0.3}, 5, 7),
+    ("approx", (8, 8), {"divacancy": 0.0, "monovacancy": 0.0}, 1, 0),
+    ("approx", (64, 64), {"divacancy": 0.6, "monovacancy": 0.4}, (1 << 40) + 3, 5),
+    ("approx", (40, 70), {"divacancy": 0.01, "monovacancy": 0.0}, 99, 3),
+]
+
+
+def state_gen_philox_fixtures():
+    """The reference's gen_random_state (state.py:329-378) handed philox.PhiloxRandom(seed, replica) as its
+    rng: pins the device-side generator (kmc_generate_state) and oracle/state_gen.py."""
+    stmod = ref_oracle.ref()["state"]
+    out, metas = {}, []
+    for i, (mode, dim, params, seed, replica) in enumerate(PHILOX_STATE_CASES):
+        rng = philox.PhiloxRandom(seed, replica)
+        state = stmod.gen_random_state(dim, mode, dict(params), rng=rng)
+        out["status_%d" % i] = np.array(ref_oracle.status_from_state(state), dtype=np.uint8)
+        metas.append({"mode": mode, "dim": list(dim), "params": params, "seed": seed, "replica": replica,
+                      "draws": rng.q})
+    path = os.path.join(OUT, "state_gen_philox.npz")
+    np.savez_compressed(path, meta=json.dumps(metas), **out)
+    print("state_gen_philox.npz: %d cases (%d bytes)" % (len(metas), os.path.getsize(path)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. all eight rules, pristine start: trefoils are created and destroyed along the way
@@ -165,6 +195,7 @@ def main():
     trajectory("allrules_40x70", (40, 70), ALL_RULES, exact_state((40, 70), 0.1, 0.1, 2), seed=6,
                nsteps=1500, replica=3)
     state_gen_fixtures()
+    state_gen_philox_fixtures()
     native_statistics()
 
 

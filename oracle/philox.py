@@ -46,3 +46,41 @@ def draws(seed, replica, step0, nsteps):
     u1 = (((x0 << np.uint64(32)) | x1) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
     u2 = (((x2 << np.uint64(32)) | x3) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
     return np.stack([u1, u2], axis=1)
+
+
+import random as _random
+
+
+class PhiloxRandom(_random.Random):
+    """random.Random over a Philox stream, used to drive the reference's gen_random_state (state.py:329-378)
+    with reproducible bits (TEST INFRASTRUCTURE ONLY; the device generator csrc/stategen_kernel.cuh consumes
+    the same stream):
+
+        block(q) = Philox4x32-10(counter = (q & 0xffffffff, q >> 32, seed >> 32, 1), key = (seed & 0xffffffff, replica))
+        random()       = (((x0 << 32) | x1) >> 11) * 2**-53          q += 1
+        getrandbits(k) = x0 >> (32 - k),  1 <= k <= 32               q += 1
+
+    Everything else (uniform, shuffle, choice, _randbelow with k = n.bit_length() and rejection) is
+    CPython's random.Random."""
+
+    def __init__(self, seed, replica=0):
+        self.pseed, self.replica, self.q = int(seed), int(replica), 0
+        super().__init__(0)
+
+    def seed(self, *args, **kwargs):
+        pass
+
+    def _x(self):
+        q = self.q
+        self.q += 1
+        x = philox4x32_10(q & 0xFFFFFFFF, q >> 32, self.pseed >> 32, 1, self.pseed & 0xFFFFFFFF,
+                          self.replica & 0xFFFFFFFF)
+        return [int(v) for v in x]
+
+    def random(self):
+        x = self._x()
+        return float(((x[0] << 32) | x[1]) >> 11) * 2.0 ** -53
+
+    def getrandbits(self, k):
+        assert 0 < k <= 32
+        return self._x()[0] >> (32 - k)

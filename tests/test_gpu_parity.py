@@ -457,3 +457,69 @@ def test_full_size_replica_batch_properties():
         o.run_philox(20261019, r, 0, nsteps, log=False)
         assert (final[r] == o.status()).all()
     eng.close()
+
+
+# ---- device-side initial-state generators -------------------------------------------
+def test_device_state_generator_matches_reference_fixtures():
+    """kmc_generate_state against the reference's gen_random_state driven by the same Philox stream
+    (tests/golden/state_gen_philox.npz)."""
+    import json
+    import os
+    from util_golden import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "state_gen_philox.npz"))
+    for i, m in enumerate(json.loads(str(z["meta"]))):
+        eng = Engine(m["dim"], TEST_RATES, ALL_ORDER, n_replicas=1)
+        eng.generate_state(m["mode"], m["params"], m["seed"], replica0=m["replica"])
+        assert (eng.download_state()[0] == z["status_%d" % i]).all(), m
+        eng.close()
+
+
+@pytest.mark.parametrize("mode,dim,params", [
+    ("exact", (64, 64), {"divacancy": 0.05, "monovacancy": 0.05}),
+    ("exact", (9, 130), {"divacancy": 0.4, "monovacancy": 0.1}),
+    ("approx", (64, 64), {"divacancy": 0.05, "monovacancy": 0.05}),
+    ("approx", (31, 17), {"divacancy": 0.5, "monovacancy": 0.5}),
+    ("exact", (16, 16), {}),
+])
+def test_device_state_generator_matches_oracle_per_replica(mode, dim, params):
+    """Several replicas in one call (replica r = stream (seed, replica0 + r)) against oracle/state_gen.py;
+    the generated lattices then run like uploaded ones."""
+    import state_gen
+    nrep, seed, replica0 = 5, (3 << 32) | 20261019, 1000
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.generate_state(mode, params, seed, replica0=replica0)
+    got = eng.download_state()
+    for r in range(nrep):
+        want = state_gen.generate(dim, mode, params, seed, replica0 + r)
+        assert (got[r] == want).all(), (mode, dim, r)
+    ev = eng.run(500, 7, log_mode=nat.LOG_COMPACT, validate=True)
+    o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, got[2])
+    _, want = o.run_philox(7, 2, 0, 500)
+    assert_events_equal(ev[2], want, "replica 2 after device generation")
+    eng.close()
+
+
+def test_device_state_generator_exact_counts_at_the_headline_batch():
+    """Size-independent property at 64x64 x 4096 replicas: 'exact' puts round(f*N) defects of each type in
+    every replica, replicas differ, layers are balanced."""
+    nrep, n = 4096, 64 * 64
+    eng = Engine((64, 64), wse2_rates(1500.0), WSE2_ORDER, n_replicas=nrep)
+    eng.generate_state("exact", {"divacancy": 0.05, "monovacancy": 0.05}, 20261019)
+    st = eng.download_state()
+    assert ((st == 3).sum(axis=1) == round(0.05 * n)).all()
+    assert (((st == 1) | (st == 2)).sum(axis=1) == round(0.10 * n) - round(0.05 * n)).all()
+    assert st.max() == 3
+    assert len({row.tobytes() for row in st[:64]}) == 64
+    frac_layer1 = (st == 1).sum() / ((st == 1) | (st == 2)).sum()
+    assert abs(frac_layer1 - 0.5) < 0.01
+    eng.close()
+
+
+def test_generate_state_argument_errors():
+    eng = Engine((8, 8), TEST_RATES, ALL_ORDER)
+    with pytest.raises((RuntimeError, ValueError)):
+        nat.check(eng._lib.kmc_generate_state(eng._h, 2, 1, np.zeros(1, np.int32).ctypes.data, None, None, 1, 0))
+    with pytest.raises((RuntimeError, ValueError)):
+        nat.check(eng._lib.kmc_generate_state(eng._h, 0, 1, np.array([3], np.int32).ctypes.data,
+                                              np.array([0, 65], np.int64).ctypes.data, None, 1, 0))
+    eng.close()

@@ -28,6 +28,27 @@ def test_state_generators_match_reference_fixtures():
         assert (st.status == z["status_%d" % i]).all(), m
 
 
+def test_philox_backed_generators_match_the_reference_driven_by_the_same_stream():
+    """tests/golden/state_gen_philox.npz: the reference's gen_random_state with a Philox-backed random.Random.
+    The host twin (demo1.state.PhiloxRandom) must give the same lattices and consume the same number of
+    draws; the plan handed to the device generator must describe the same runs / weights."""
+    from demo1.state import PhiloxRandom, generator_plan
+    z = np.load(os.path.join(GOLDEN, "state_gen_philox.npz"))
+    for i, m in enumerate(json.loads(str(z["meta"]))):
+        rng = PhiloxRandom(m["seed"], m["replica"])
+        st = gen_random_state(tuple(m["dim"]), m["mode"], m["params"], rng=rng)
+        want = z["status_%d" % i]
+        assert (st.status == want).all(), m
+        assert rng._q == m["draws"], m
+        mode_id, codes, bounds, cumul = generator_plan(want.size, m["mode"], m["params"])
+        if m["mode"] == "exact":
+            assert mode_id == 0 and bounds[0] == 0
+            for c, a, b in zip(codes, bounds[:-1], bounds[1:]):
+                assert b - a == ((want == 3).sum() if c == 3 else ((want == 1) | (want == 2)).sum()), m
+        else:
+            assert mode_id == 1 and len(cumul) == len(codes) and all(x > 0 for x in cumul)
+
+
 def test_state_roundtrip_and_validation():
     g = load("allrules_8x8")
     st = State((8, 8), g["status1"])

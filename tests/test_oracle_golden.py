@@ -11,7 +11,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import kmc_oracle as ko  # noqa: E402
 import philox  # noqa: E402
-from util_golden import load, trajectory_names, enabled_classes  # noqa: E402
+from util_golden import GOLDEN, load, trajectory_names, enabled_classes  # noqa: E402
 
 
 def test_philox_known_answers():
@@ -150,3 +150,14 @@ def test_class_frequencies_match_the_reference_run_with_its_own_rng():
     assert worst > 1e-4, worst
     stat, dof = chi2_two_sample(z["counts"].sum(axis=0), ours.sum(axis=0))
     assert chi2.sf(stat, dof) > 1e-4
+
+
+def test_state_generator_restatement_matches_the_reference_under_philox():
+    """oracle/state_gen.py against the reference's gen_random_state driven by philox.PhiloxRandom
+    (fixtures made by oracle/make_golden.py:state_gen_philox_fixtures)."""
+    import json
+    import state_gen
+    z = np.load(os.path.join(GOLDEN, "state_gen_philox.npz"))
+    for i, m in enumerate(json.loads(str(z["meta"]))):
+        got = state_gen.generate(tuple(m["dim"]), m["mode"], m["params"], m["seed"], m["replica"])
+        assert (got == z["status_%d" % i]).all(), m
