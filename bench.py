@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[2]): config/WSe2.yaml barriers at T = 1500 K (stub rule
 MoveMonovacancy disabled), 64x64 lattice with 5 % divacancies + 5 % monovacancies, 16384 independent
-replicas PER GPU (one warp per replica; weak scaling), Philox draws keyed by (seed, global replica).
+replicas PER GPU (two replicas per warp; weak scaling), Philox draws keyed by (seed, global replica).
 One "step" = one launch of the fused replica kernel = `--events` KMC events on every replica.
 
 One JSON line on stdout (rank 0):
@@ -329,7 +329,7 @@ def main():
         avg_ms = float(np.mean(ms))
         nsites = SWEEP_DIM[0] * SWEEP_DIM[1]
         achieved = nsites * SWEEP_BYTES_PER_SITE / (avg_ms * 1e-3) / 1e9
-        roofline = {"kernel": "kmc_sweep16n_kernel (K1+K2, 4096x4096 full rate sweep)", "bound": "hbm",
+        roofline = {"kernel": "kmc_sweep_roll_kernel (K1+K2, 4096x4096 full rate sweep)", "bound": "hbm",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": (recorded_traffic() or {}).get("dram_bytes_per_launch"),
                     "traffic_source": (recorded_traffic() or {}).get("source"), "peak_source": peak_src, "bytes_per_site": SWEEP_BYTES_PER_SITE,
@@ -376,7 +376,16 @@ def main():
         lat.close()
         other["1024x1024_x128_replicas_incremental"] = {
             "events_per_s": nrep5 * ev5 / (ms5 * 1e-3), "replicas": nrep5, "events_per_replica": ev5,
-            "note": "lattices stay in HBM/L2; the row hierarchy persists between launches (no re-enumeration)"}
+            "note": "bit planes + row table stay in HBM/L2 between launches (wide bit-plane kernel)"}
+        # the initial lattices generated on the device (reference gen_random_state 'exact' under
+        # a Philox stream per replica) instead of uploaded
+        gen = Engine(DIM, rates, order, n_replicas=R, device=local)
+        gen.generate_state("exact", {"divacancy": 0.05, "monovacancy": 0.05}, SEED)
+        gen.timer_start()
+        gen.generate_state("exact", {"divacancy": 0.05, "monovacancy": 0.05}, SEED)
+        msg = gen.timer_stop()
+        gen.close()
+        other["device_state_generation_exact_64x64"] = {"ms": msg, "replicas": R, "lattices_per_s": R / (msg * 1e-3)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -394,7 +403,7 @@ def main():
             "dtype": "u8 lattice / f64 rates", "data": "synthetic",
             "config": {"workload": "config/WSe2.yaml (MoveMonovacancy stub disabled) T=1500K, 64x64 lattice, "
                                    "5%% divacancy + 5%% monovacancy, %d independent replicas per GPU, "
-                                   "one warp per replica" % R,
+                                   "two replicas per warp (half-warp kernel)" % R,
                        "replicas_per_gpu": R, "events_per_replica_per_step": E,
                        "l2": "flushed (256 MiB read on the engine's stream, leaves clean lines) before every timed launch", "seed": SEED,
                        "parallelism": "replicas sharded by contiguous global index; one NCCL all-reduce of "

@@ -43,6 +43,9 @@ def main(argv=None):
     parser.add_argument("--replicas", type=positive_int, default=1,
                         help="run this many independent trajectories (statistics only unless 1)")
     parser.add_argument("--stats-only", action="store_true", help="no event log, only the class histogram")
+    parser.add_argument("--independent-states", action="store_true",
+                        help="with --replicas: every replica starts from its own lattice, generated on the GPU "
+                             "from the config's state.random section (Philox stream (state seed, replica))")
     parser.add_argument("--device", type=int, default=0, help="CUDA device index")
     args = parser.parse_args(argv)
 
@@ -57,7 +60,8 @@ def main(argv=None):
             config_dict=config_dict, validate_every=args.validate_every, incremental=args.incremental,
             save_initial_path=args.write_initial, embed_initial=args.embed_initial,
             temperature=args.temperature, seed=args.seed, state_seed=args.state_seed,
-            replicas=args.replicas, stats_only=args.stats_only, device=args.device)
+            replicas=args.replicas, stats_only=args.stats_only, device=args.device,
+            independent_states=args.independent_states)
 
     if args.output_pstats or args.profile:
         with_profiling(myrun, args.output_pstats, sys.stderr if args.profile else None)
@@ -71,7 +75,8 @@ class DevNull:
 
 
 def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_initial_path, embed_initial,
-        temperature, seed=None, state_seed=None, replicas=1, stats_only=False, device=0):
+        temperature, seed=None, state_seed=None, replicas=1, stats_only=False, device=0,
+        independent_states=False):
     import random
     cfg = config.from_dict(config_dict)        # pops every key: "config" is echoed as {} (reference quirk Q1)
     rng = random.Random(state_seed) if state_seed is not None else random
@@ -81,7 +86,10 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
             json.dump(init_state.to_dict(), f)
 
     if replicas > 1 or stats_only:
-        return run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device)
+        return run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device,
+                         state_seed if independent_states else None, independent_states)
+    if independent_states:
+        die("--independent-states needs --replicas N or --stats-only")
 
     chunk = validate_every if validate_every else min(nsteps, 4096)
     sim = KmcSim(init_state, cfg["rule_specs"], incremental=incremental, temperature=temperature,
@@ -113,7 +121,8 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
     sim.close()
 
 
-def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device):
+def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device, state_seed=None,
+              independent_states=False):
     """--replicas / --stats-only: many independent trajectories from the same initial lattice, one
     warp each; output is the per-class event histogram instead of an event log."""
     import os
@@ -124,7 +133,11 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     info = {"%s:%s" % (rule, kind): rate for rule, rates in rules_and_rates.items() for kind, rate in rates.items()}
     seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
     eng = Engine(init_state.dim, rates13, order, n_replicas=replicas, device=device)
-    eng.upload_state(np.tile(init_state.status, (replicas, 1)))
+    if independent_states:
+        gen = cfg["state_gen_func"].keywords          # partial(gen_random_state, mode=..., params=...)
+        eng.generate_state(gen["mode"], gen["params"], seed if state_seed is None else state_seed)
+    else:
+        eng.upload_state(np.tile(init_state.status, (replicas, 1)))
     try:
         eng.run(nsteps, seed, validate=True)
     except ValueError:

@@ -149,3 +149,27 @@ def test_cli_replica_batch_statistics():
     out = json.loads(run_cli([cfg, "-T", "1500", "-d", "64,64", "-n", "500", "--seed", "3", "--state-seed", "4",
                               "--replicas", "64"]))
     assert out["events_done"] == 64 * 500 and sum(out["histogram"].values()) == 64 * 500
+
+
+def test_cli_independent_replica_states_are_generated_on_the_device():
+    """--independent-states: replica r starts from gen_random_state under the Philox stream (state seed, r),
+    so the histogram equals that of oracle runs started from oracle/state_gen.py lattices."""
+    from util_cases import ko, WSE2_ORDER, wse2_rates         # puts oracle/ on sys.path
+    import state_gen
+    cfg = os.path.join(PKG, "config", "wse2_1500K.yaml")
+    nrep, nsteps = 6, 300
+    out = json.loads(run_cli([cfg, "-T", "1500", "-d", "16,16", "-n", str(nsteps), "--seed", "3", "--state-seed", "4",
+                              "--replicas", str(nrep), "--independent-states"]))
+    with open(cfg) as f:
+        import yaml
+        params = yaml.safe_load(f)["state"]["random"]
+    mode = params.pop("mode")
+    frac = {k: (float(v[:-1]) / 100 if isinstance(v, str) else float(v)) for k, v in params.items()}
+    hist = np.zeros(13, dtype=np.int64)
+    for r in range(nrep):
+        st0 = state_gen.generate((16, 16), mode, frac, 4, r)
+        o = ko.Oracle((16, 16), wse2_rates(1500.0), WSE2_ORDER, st0)
+        o.run_philox(3, r, 0, nsteps, log=False)
+        hist += np.asarray(o.hist())
+    from demo1 import tables as T
+    assert out["histogram"] == {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in WSE2_ORDER}
