@@ -140,6 +140,11 @@ int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica
 int kmc_get_histogram(kmc_engine *h, int64_t *out);
 int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out);
 int kmc_get_steps_done(kmc_engine *h, int64_t *out);
+/* Divacancy hop statistics (extension, SURVEY 8(f) rank 4 "diffusion observables"): per replica, the number of
+ * MoveDivacancy events per direction k = 0..5 (slot 7 + k; hop vector = neighbour k of demo1/state.py:392-394
+ * as listed in `neighbors_and_mutuals`, state.py:443-459) since the last kmc_reset_stats.  The net
+ * displacement of the divacancy population is sum_k hops[k] * nbr_k.  out: [n_replicas][6]. */
+int kmc_get_hops(kmc_engine *h, int64_t *out);
 int kmc_get_ties(kmc_engine *h, int64_t *out);
 int kmc_reset_stats(kmc_engine *h);
 /* Optional KMC clock (extension; the reference draws no time step, SURVEY F6, but logs total_rate so that

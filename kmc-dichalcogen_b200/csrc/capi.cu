@@ -48,7 +48,7 @@ struct kmc_engine {
     unsigned long long *d_counts = nullptr;  // [R][13]
     unsigned long long *d_acc = nullptr;     // [R][16] running totals of the aligned sweep (zero between launches)
     unsigned int *d_ticket = nullptr;        // [R]
-    unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr;
+    unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr, *d_hops = nullptr;
     uint32_t *d_flags = nullptr;
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
@@ -121,6 +121,7 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
     CU(cudaMalloc(&h->d_counts, R * NC * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_steps, R * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_hist, R * NC * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_hops, R * 6 * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_ties, R * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_flags, R * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_result, sizeof(int)));
@@ -128,6 +129,7 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
     CU(cudaMemsetAsync(h->d_counts, 0, R * NC * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -143,7 +145,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock);
     cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk);
-    cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_ties); cudaFree(h->d_flags);
+    cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -496,7 +498,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-        p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
         p.validate = validate;
         p.clock = h->clock_on ? h->d_clock : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
@@ -541,7 +543,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-        p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
         p.validate = validate;
         p.clock = h->clock_on ? h->d_clock : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
@@ -589,7 +591,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
     p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
     p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-    p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+    p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
     p.validate = validate;
     p.clock = h->clock_on ? h->d_clock : nullptr;
     p.hier = nullptr; p.hier_valid = 0;
@@ -685,7 +687,7 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
     for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
     p.seed = seed; p.replica0 = replica0; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.nsteps = nsteps;
-    p.steps_done = h->d_steps; p.hist = h->d_hist; p.ties = h->d_ties; p.flags = h->d_flags;
+    p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
     p.clock = h->clock_on ? h->d_clock : nullptr;
     for (long long t = 0; t < nsteps; t++) {
         rc = sweep_launch(h, false); if (rc) return rc;        // sim.py:114-115: initialize() every step
@@ -704,6 +706,15 @@ extern "C" int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
     CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_get_hops(kmc_engine *h, int64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_hops: null buffer");
+    CU(cudaMemcpyAsync(out, h->d_hops, (size_t)h->R * 6 * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
 }
@@ -742,6 +753,7 @@ extern "C" int kmc_reset_stats(kmc_engine *h)
     const size_t R = (size_t)h->R;
     CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
     if (h->d_clock) CU(cudaMemsetAsync(h->d_clock, 0, R * sizeof(double), h->stream));

@@ -22,7 +22,7 @@ struct NoincParams {
     int log_mode;
     void *events;                        // [R][nsteps]
     long long nsteps, t;                 // this launch handles local step index t
-    unsigned long long *steps_done, *hist, *ties;
+    unsigned long long *steps_done, *hist, *ties, *hops;
     uint32_t *flags;
     double *clock;                       // [R] or nullptr
 };
@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         p.steps_done[rep] = step + 1;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], __ddiv_rn(1.0, s_total));
         p.hist[(size_t)rep * NC + csel] += 1;
+        if (slot >= 7 && slot < 13) p.hops[(size_t)rep * 6 + slot - 7] += 1;
         if (s_tie) p.ties[rep] += 1;
     }
 }

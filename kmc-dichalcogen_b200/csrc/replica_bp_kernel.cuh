@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         for (int a = 0; a < d0; a++) tot += rc16[lane * d0e + a];
     // own-status classes: 2 bits per status = moves of my class a site of that status carries
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
-    unsigned long long hist = 0, n_ties = 0;
+    unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(lane);
     double tclock = 0.0;
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
             }
         }
         if (lane == csel) hist++;
+        if (lane == slot - 7) hops++;                          // lanes 0..5: divacancy hops per direction
         if (pick.tie && lane == 0) n_ties++;
 
         // ---- 4. the move (uniform): touched nodes, old and new status --------------------------------
@@ -611,6 +612,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaPar
         }
     }
     if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);

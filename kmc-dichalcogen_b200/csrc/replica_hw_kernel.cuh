@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
     if (hl < NC)
         for (int a = 0; a < d0; a++) tot += rc16[hl * d0p + a];
     const uint32_t my_g1 = (hl < NC && !(hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)) ? g1_const(hl) : 0u;
-    unsigned long long hist = 0, n_ties = 0;
+    unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(hl);
     double tclock = 0.0;
     // refresh roles: half-lanes 0..11 = direction hl % 6 of band rows 2*pass + hl / 6
@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
         }
     }
     if (hl < NC) p.hist[(size_t)rep * NC + hl] += hist;
+    if (hl < 6) p.hops[(size_t)rep * 6 + hl] += hops;
     if (hl == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);

@@ -40,6 +40,7 @@ struct ReplicaParams {
     void *events;                    // [R][nsteps] records or nullptr
     unsigned long long *steps_done;  // [R] in: step offset; out: += events done
     unsigned long long *hist;        // [R][NC]
+    unsigned long long *hops;        // [R][6] MoveDivacancy events per direction k (slot 7 + k)
     unsigned long long *ties;        // [R]
     uint32_t *flags;                 // [R] bit0 zero-rate stop, bit1 validate mismatch
     int validate;
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const int f = rc_field(lane);
         for (int a = 0; a < d0; a++) tot += rc16[a * (2 * RC_WORDS) + f];
     }
-    unsigned long long hist = 0;
+    unsigned long long hist = 0, hops = 0;
     unsigned long long n_ties = 0;
     PickState pstate = pick_state_init(lane);
     double tclock = 0.0;
@@ -518,6 +519,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
             }
         }
         if (lane == csel) hist++;
+        if (lane == slot - 7) hops++;                          // lanes 0..5: divacancy hops per direction
         if (tie && lane == 0) n_ties++;
 
         // ---- 4. the move: touched nodes and their new status (uniform) --------------------------------
@@ -614,6 +616,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         for (int i = lane; i < n; i += 32) gst[i] = st[i];
     }
     if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);

@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     if (lane < NC)
         for (int i = 0; i < 32; i++) tot += (int)bs[lane * 32 + i];
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
-    unsigned long long hist = 0, n_ties = 0;
+    unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(lane);
     double tclock = 0.0;
     const uint32_t my_desc = task_desc(lane < 7 ? lane : 6);          // lane k < 7 holds the descriptor of task kind k
@@ -477,6 +477,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             }
         }
         if (lane == csel) hist++;
+        if (lane == slot - 7) hops++;                          // lanes 0..5: divacancy hops per direction
         if (pick.tie && lane == 0) n_ties++;
 
         // ---- the move -----------------------------------------------------------------------------------
@@ -617,6 +618,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     }
     flag = __reduce_or_sync(FULL, flag);
     if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);

@@ -145,10 +145,21 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     hist = eng.histogram()
     out = {"grid": grid_info(dims), "temperature": temperature, "rates": info, "replicas": replicas,
            "seed": seed, "events_done": int(eng.steps_done().sum()),
-           "histogram": {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in order}}
+           "histogram": {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in order},
+           # divacancy hops per direction (neighbour order of state.py:443-459), summed over replicas, and the
+           # mean squared net displacement of a replica's divacancy population in axial lattice units
+           "divacancy_hops": [int(x) for x in eng.hops().sum(axis=0)],
+           "mean_squared_net_displacement": float(np.mean(axial_norm2(eng.displacement())))}
     json.dump(out, ofile, indent=2, sort_keys=True)
     ofile.write("\n")
     eng.close()
+
+
+def axial_norm2(d):
+    """|a * e1 + b * e2|^2 for axial hex coordinates (unit lattice constant): a^2 + a*b + b^2."""
+    import numpy as np
+    d = np.asarray(d, dtype=np.float64)
+    return d[:, 0] ** 2 + d[:, 0] * d[:, 1] + d[:, 1] ** 2
 
 
 class write_enclosing:

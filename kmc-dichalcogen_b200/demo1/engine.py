@@ -132,6 +132,18 @@ class Engine:
         nat.check(self._lib.kmc_get_histogram_per_replica(self._h, out.ctypes.data))
         return out
 
+    def hops(self):
+        """MoveDivacancy events per replica and direction k (slot 7 + k), shape (n_replicas, 6)."""
+        out = np.empty((self.n_replicas, 6), dtype=np.int64)
+        nat.check(self._lib.kmc_get_hops(self._h, out.ctypes.data))
+        return out
+
+    def displacement(self):
+        """Net axial displacement (da, db) of the divacancy population per replica: sum_k hops[k] * nbr_k with
+        the neighbour order of the reference's neighbors_and_mutuals (state.py:443-459)."""
+        from .tables import MOVE_TARGET as NBR
+        return self.hops() @ np.asarray(NBR, dtype=np.int64)
+
     def steps_done(self):
         out = np.empty(self.n_replicas, dtype=np.int64)
         nat.check(self._lib.kmc_get_steps_done(self._h, out.ctypes.data))

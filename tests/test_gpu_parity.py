@@ -523,3 +523,41 @@ def test_generate_state_argument_errors():
         nat.check(eng._lib.kmc_generate_state(eng._h, 0, 1, np.array([3], np.int32).ctypes.data,
                                               np.array([0, 65], np.int64).ctypes.data, None, 1, 0))
     eng.close()
+
+
+@pytest.mark.parametrize("variant,dim", [(1, (33, 47)), (2, (64, 64)), (3, (16, 80)), (4, (64, 64)), (5, (24, 128))])
+def test_divacancy_hop_counters_match_the_event_log(variant, dim):
+    """kmc_get_hops: MoveDivacancy events per direction, accumulated on the device, against the slots of the
+    oracle's event log; two launches accumulate, reset_stats clears."""
+    nrep, nsteps = 3, 3000
+    st0 = np.stack([evolved_state(dim, 60 + r, nsteps=200) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(st0)
+    eng.run(1000, 21)
+    eng.run(nsteps - 1000, 21)
+    hops = eng.hops()
+    disp = eng.displacement()
+    nbr = np.array([(-1, 1), (0, -1), (1, 0), (0, 1), (-1, 0), (1, -1)])
+    for r in range(nrep):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
+        _, want = o.run_philox(21, r, 0, nsteps)
+        slots = want["slot"].astype(int)
+        w = np.bincount(slots[(slots >= 7) & (slots < 13)] - 7, minlength=6)
+        assert (hops[r] == w).all(), (variant, r)
+        assert (disp[r] == w @ nbr).all()
+        assert w.sum() == o.hist()[2:6].sum()
+    eng.reset_stats()
+    assert (eng.hops() == 0).all()
+    eng.close()
+
+
+def test_hop_counters_in_the_no_incremental_path():
+    dim = (16, 16)
+    st0 = evolved_state(dim, 8, nsteps=100)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=1)
+    eng.upload_state(st0)
+    ev = eng.run_noinc(200, 4, log_mode=nat.LOG_COMPACT)[0]
+    slots = ev["slot"].astype(int)
+    assert (eng.hops()[0] == np.bincount(slots[(slots >= 7) & (slots < 13)] - 7, minlength=6)).all()
+    eng.close()
