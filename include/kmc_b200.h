@@ -145,6 +145,12 @@ int kmc_get_steps_done(kmc_engine *h, int64_t *out);
  * as listed in `neighbors_and_mutuals`, state.py:443-459) since the last kmc_reset_stats.  The net
  * displacement of the divacancy population is sum_k hops[k] * nbr_k.  out: [n_replicas][6]. */
 int kmc_get_hops(kmc_engine *h, int64_t *out);
+/* Zobrist key of every replica's current lattice, from scratch (State.zobrist_key / __validate_zobrist_key,
+ * demo1/state.py:136-141,306-317; ZobristKey, demo1/incremental.py:335-380): XOR over the entities on the
+ * lattice of a `bits`-wide value per (site, status code) from a fixed Philox table keyed by `seed`
+ * (csrc/zobrist_kernel.cuh; the reference draws its values on demand from `random`, so only the structure
+ * -- equal keys iff equal lattices -- carries over).  out: [n_replicas]. */
+int kmc_zobrist(kmc_engine *h, int bits, uint64_t seed, uint64_t *out);
 int kmc_get_ties(kmc_engine *h, int64_t *out);
 int kmc_reset_stats(kmc_engine *h);
 /* Optional KMC clock (extension; the reference draws no time step, SURVEY F6, but logs total_rate so that

@@ -18,6 +18,7 @@
 #include "replica_wide_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "stategen_kernel.cuh"
+#include "zobrist_kernel.cuh"
 
 using namespace kmc;
 
@@ -707,6 +708,28 @@ extern "C" int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out)
     int rc = bind(h); if (rc) return rc;
     CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    return KMC_OK;
+}
+
+extern "C" int kmc_zobrist(kmc_engine *h, int bits, uint64_t seed, uint64_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (bits < 1 || bits > 64) return fail(KMC_ERR_ARG, "kmc_zobrist: bits must be 1..64");
+    if (!out) return fail(KMC_ERR_ARG, "kmc_zobrist: null buffer");
+    rc = ensure_bytes(h); if (rc) return rc;
+    unsigned long long *d_keys = nullptr;
+    CU(cudaMalloc(&d_keys, (size_t)h->R * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d_keys, 0, (size_t)h->R * sizeof(unsigned long long), h->stream);
+    if (e == cudaSuccess) {
+        const unsigned bx = (unsigned)std::min<long long>(((long long)h->n + 255) / 256, 64);
+        kmc_zobrist_kernel<<<dim3(bx, (unsigned)h->R), 256, 0, h->stream>>>(h->d_status, h->n, bits, seed, d_keys);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_keys, (size_t)h->R * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_keys);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, cudaGetErrorString(e));
+    h->launches += 1;
     return KMC_OK;
 }
 

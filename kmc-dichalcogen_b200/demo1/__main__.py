@@ -34,9 +34,10 @@ def main(argv=None):
                             "every NSTEP steps. (debugging flag)")
     group = parser.add_mutually_exclusive_group()
     group.add_argument("--zobrist-bits", metavar="NBITS", type=positive_int, default=None,
-                       help="(reference experimental flag; not part of the accelerated path)")
+                       help="Experimental flag. Computes and prints zobrist keys with this many bits (1..64). "
+                            "Values come from a fixed Philox table keyed by --seed, so keys are reproducible.")
     group.add_argument("--zobrist-hash", action="store_true",
-                       help="(reference experimental flag; not part of the accelerated path)")
+                       help="Experimental flag. Deterministic zobrist keys: 64 bits from the table keyed by 0.")
     # new flags
     parser.add_argument("--seed", type=int, default=None, help="Philox seed (default: from the OS)")
     parser.add_argument("--state-seed", type=int, default=None, help="seed of the initial-state generator")
@@ -51,8 +52,8 @@ def main(argv=None):
 
     if args.debug:
         logging.getLogger().setLevel(10)
-    if args.zobrist_bits or args.zobrist_hash:
-        die("zobrist keys are an experimental reference flag outside the accelerated path (see DESIGN.md)")
+    if args.zobrist_bits is not None and args.zobrist_bits > 64:
+        die("--zobrist-bits: at most 64")
     config_dict = config.load_all(args.CONFIG)
 
     def myrun():
@@ -61,7 +62,8 @@ def main(argv=None):
             save_initial_path=args.write_initial, embed_initial=args.embed_initial,
             temperature=args.temperature, seed=args.seed, state_seed=args.state_seed,
             replicas=args.replicas, stats_only=args.stats_only, device=args.device,
-            independent_states=args.independent_states)
+            independent_states=args.independent_states,
+            zobrist=(64, 0) if args.zobrist_hash else ((args.zobrist_bits, None) if args.zobrist_bits else None))
 
     if args.output_pstats or args.profile:
         with_profiling(myrun, args.output_pstats, sys.stderr if args.profile else None)
@@ -76,7 +78,7 @@ class DevNull:
 
 def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_initial_path, embed_initial,
         temperature, seed=None, state_seed=None, replicas=1, stats_only=False, device=0,
-        independent_states=False):
+        independent_states=False, zobrist=None):
     import random
     cfg = config.from_dict(config_dict)        # pops every key: "config" is echoed as {} (reference quirk Q1)
     rng = random.Random(state_seed) if state_seed is not None else random
@@ -93,7 +95,8 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
 
     chunk = validate_every if validate_every else min(nsteps, 4096)
     sim = KmcSim(init_state, cfg["rule_specs"], incremental=incremental, temperature=temperature,
-                 seed=seed, device=device, chunk=chunk, validate_launches=bool(validate_every))
+                 seed=seed, device=device, chunk=chunk, validate_launches=bool(validate_every),
+                 zobrist_bits=zobrist[0] if zobrist else None, zobrist_seed=zobrist[1] if zobrist else None)
 
     with write_enclosing("{", "\n}", ofile):
         def write_key_val(key, val, end=",\n", pretty=True, **kw):
@@ -122,7 +125,7 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
 
 
 def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device, state_seed=None,
-              independent_states=False):
+              independent_states=False, zobrist=None):
     """--replicas / --stats-only: many independent trajectories from the same initial lattice, one
     warp each; output is the per-class event histogram instead of an event log."""
     import os

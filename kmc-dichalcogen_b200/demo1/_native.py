@@ -50,6 +50,7 @@ SYMBOLS = {
     "kmc_run_noinc": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]),
     "kmc_get_histogram": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_get_histogram_per_replica": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kmc_zobrist": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
     "kmc_get_hops": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_get_steps_done": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_get_ties": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),

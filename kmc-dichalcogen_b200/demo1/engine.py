@@ -132,6 +132,12 @@ class Engine:
         nat.check(self._lib.kmc_get_histogram_per_replica(self._h, out.ctypes.data))
         return out
 
+    def zobrist(self, bits=64, seed=0):
+        """Zobrist key of each replica's current lattice, computed from scratch on the device (uint64[R])."""
+        out = np.empty(self.n_replicas, dtype=np.uint64)
+        nat.check(self._lib.kmc_zobrist(self._h, int(bits), int(seed) & (2 ** 64 - 1), out.ctypes.data))
+        return out
+
     def hops(self):
         """MoveDivacancy events per replica and direction k (slot 7 + k), shape (n_replicas, 6)."""
         out = np.empty((self.n_replicas, 6), dtype=np.int64)

@@ -75,7 +75,7 @@ class KmcSim:
     is drawn from the OS).  ``chunk`` events are generated per kernel launch."""
 
     def __init__(self, initial_state, rule_specs, temperature=None, incremental=True, seed=None,
-                 replica=0, device=0, chunk=4096, validate_launches=False):
+                 replica=0, device=0, chunk=4096, validate_launches=False, zobrist_bits=None, zobrist_seed=None):
         from .engine import Engine
         self.rule_specs = list(rule_specs)
         self.temperature = temperature
@@ -84,6 +84,10 @@ class KmcSim:
         self.replica = int(replica)
         self.chunk = int(chunk)
         self.validate_launches = bool(validate_launches)
+        # Zobrist key per logged event (reference state.py:52-54, sim.py:141-142): off unless bits are given
+        self.zobrist_bits = None if zobrist_bits is None else int(zobrist_bits)
+        self.zobrist_seed = self.seed if zobrist_seed is None else int(zobrist_seed)
+        self._zobrist = None
         self._Engine = Engine
         self._device = device
         self._engine = None
@@ -108,6 +112,9 @@ class KmcSim:
         self.state.validate()
         self._engine.upload_state(self.state.status)
         self._buffer, self._cursor = None, 0
+        if self.zobrist_bits is not None:
+            from .zobrist import ZobristTracker
+            self._zobrist = ZobristTracker(self.state.status, self.state.dim, self.zobrist_bits, self.zobrist_seed)
 
     def rate(self, rule, kind):
         return self.rules_and_rates[rule][kind]
@@ -149,13 +156,24 @@ class KmcSim:
     def _format(self, rec):
         rule, kind = T.CLASSES[int(rec["cls"])]
         weights = [float(int(rec["counts"][c])) * self._rates13[c] for c in self._order]
-        return {
+        d = {
             "rule": rule,
             "move": T.move_info(int(rec["site"]), int(rec["slot"]), self.state.dim),
             "kind": kind,
             "rate": self._rates13[int(rec["cls"])],
             "total_rate": math.fsum(weights),           # reference sim.py:138
         }
+        if self._zobrist is not None:
+            d["zobrist"] = self._zobrist.apply(d)       # reference sim.py:141-142
+        return d
+
+    def is_zobrist_enabled(self):
+        return self._zobrist is not None
+
+    def zobrist_key(self):
+        """Key of the lattice after the events handed out so far (reference state.py:306-317)."""
+        assert self._zobrist is not None, "shouldn't be called unless zobrist bits are set"
+        return self._zobrist.key
 
     def perform_given_move(self, rule, move):
         """Apply an explicit move (reference sim.py:145-157).  ``move`` is either the reference's own
@@ -165,6 +183,8 @@ class KmcSim:
         if T.SLOT_RULE[slot] != rule:
             raise ValueError("slot %d does not belong to rule %s" % (slot, rule))
         self._engine.perform_given(0, site, slot)
+        if self._zobrist is not None:
+            self._zobrist.apply({"rule": rule, "move": T.move_info(site, slot, self.state.dim)})
 
     def _discard_lookahead(self):
         if self._buffer is not None and self._cursor < len(self._buffer):
@@ -191,6 +211,11 @@ class KmcSim:
         self._sync_state()
         self.state.validate()
         self._engine.run(0, self.seed, replica0=self.replica, validate=True)
+        if self._zobrist is not None and (self._buffer is None or self._cursor >= len(self._buffer)):
+            # incrementally toggled key against a from-scratch pass over the device lattice
+            # (reference state.py:136-141); only meaningful when no look-ahead events are pending
+            fresh = int(self._engine.zobrist(self.zobrist_bits, self.zobrist_seed)[0])
+            assert fresh == self._zobrist.key, "zobrist key mismatch: %x != %x" % (fresh, self._zobrist.key)
         return True
 
     def close(self):

@@ -97,6 +97,17 @@ def slot_of_move(rule, move, dim):
     raise KeyError(rule)
 
 
+def event_sites(event, dim):
+    """Linear indices of the sites a logged event touches (the reference's nodes_affected_by, rules.py)."""
+    mv = event["move"]
+    lin = lambda node: (node[0] % dim[0]) * dim[1] + (node[1] % dim[1])
+    if "nodes" in mv:
+        return [lin(n) for n in mv["nodes"]]
+    if "was" in mv:
+        return [lin(mv["was"]), lin(mv["now"])]
+    return [lin(mv["node"])]
+
+
 def replay_event(status, event, dim):
     """Apply one logged event (the dict `perform_random_move` returns / the CLI writes) to a flat
     status array: an independent restatement of the transition function, in the spirit of the

@@ -168,6 +168,35 @@ def state_gen_philox_fixtures():
     print("state_gen_philox.npz: %d cases (%d bytes)" % (len(metas), os.path.getsize(path)))
 
 
+def zobrist_reference_fixture():
+    """A trajectory of the reference with its Zobrist key enabled (state.py:52, 64 bits): per step the
+    reference's own key and the event.  The key VALUES are not reproducible (drawn on demand from the global
+    random module); what the fixture pins is which steps share a key, i.e. share a lattice."""
+    import random as pyrandom
+    pyrandom.seed(12345)                     # only makes this file reproducible
+    dim, nsteps = (5, 5), 1500
+    rules = dict(ALL_RULES)
+    status0 = exact_state(dim, 0.2, 0.2, 4)
+    st = ref_oracle.RefStepper(list(map(int, status0)), dim, rules, zobrist=64)
+    d = philox.draws(77, 0, 0, nsteps)
+    ev = np.zeros(nsteps, dtype=[("cls", "u1"), ("slot", "u1"), ("site", "<u4")])
+    keys = np.zeros(nsteps + 1, dtype=np.uint64)
+    keys[0] = st.sim.state.zobrist_key()
+    for t in range(nsteps):
+        r = st.step(float(d[t, 0]), float(d[t, 1]))
+        ev[t] = (r["class"], r["slot"], r["site"])
+        keys[t + 1] = st.sim.state.zobrist_key()
+    with ref_oracle.ref_modules():
+        st.validate()
+    path = os.path.join(OUT, "zobrist_ref.npz")
+    np.savez_compressed(path, meta=json.dumps({"dim": list(dim), "seed": 77, "nsteps": nsteps, "rules": rules,
+                                               "class_order": st.class_order(), "bits": 64}),
+                        rates=np.array(st.rates()), status0=status0, events=ev, ref_keys=keys,
+                        status1=np.array(st.status(), dtype=np.uint8))
+    print("zobrist_ref.npz: %d steps, %d distinct keys (%d bytes)" % (nsteps, len(set(keys.tolist())),
+                                                                     os.path.getsize(path)))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. all eight rules, pristine start: trefoils are created and destroyed along the way
@@ -196,6 +225,7 @@ def main():
                nsteps=1500, replica=3)
     state_gen_fixtures()
     state_gen_philox_fixtures()
+    zobrist_reference_fixture()
     native_statistics()
 
 

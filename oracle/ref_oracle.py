@@ -108,10 +108,10 @@ class _FixedUniform:
         return self.x
 
 
-def state_from_status(status, dim):
+def state_from_status(status, dim, zobrist=None):
     """Build a reference ``State`` from a flat uint8 status array (canon status codes)."""
     st = ref()["state"]
-    s = st.State(tuple(dim))
+    s = st.State(tuple(dim), zobrist=zobrist)
     for i, code in enumerate(status):
         code = int(code)
         node = canon.unlin(i, dim)
@@ -149,11 +149,11 @@ def make_rule_specs(rules_cfg, order=None):
 class RefStepper:
     """One reference ``KmcSim`` driven by injected draws."""
 
-    def __init__(self, status, dim, rules_cfg, temperature=None, rule_order=None):
+    def __init__(self, status, dim, rules_cfg, temperature=None, rule_order=None, zobrist=None):
         self.dim = tuple(dim)
         self.mods = ref()
         specs = make_rule_specs(rules_cfg, rule_order)
-        init = state_from_status(status, self.dim)
+        init = state_from_status(status, self.dim, zobrist=zobrist)
         with ref_modules():
             self.sim = self.mods["sim"].KmcSim(init, specs, temperature=temperature,
                                                incremental=True)

@@ -173,3 +173,29 @@ def test_cli_independent_replica_states_are_generated_on_the_device():
         hist += np.asarray(o.hist())
     from demo1 import tables as T
     assert out["histogram"] == {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in WSE2_ORDER}
+
+
+def test_kmcsim_zobrist_keys_follow_the_lattice():
+    """KmcSim(zobrist_bits=...): every event dict carries the key of the lattice after it (reference
+    sim.py:141-142); validate() checks the incrementally toggled key against a device pass from scratch."""
+    from util_cases import ko  # noqa: F401  (puts oracle/ on sys.path)
+    import zobrist as oz
+    g = load("allrules_8x8")
+    m = g["meta"]
+    sim = KmcSim(State(m["dim"], g["status0"]), specs_from_meta(m), seed=m["seed"], chunk=100, zobrist_bits=48,
+                 zobrist_seed=11)
+    assert sim.is_zobrist_enabled() and sim.zobrist_key() == oz.key(g["status0"], 48, 11)
+    keys = [sim.perform_random_move()["zobrist"] for _ in range(300)]
+    assert sim.validate() is True
+    assert keys[-1] == sim.zobrist_key() == oz.key(sim.current_state().status, 48, 11)
+    assert all(0 <= k < 2 ** 48 for k in keys)
+    sim.close()
+
+
+def test_cli_zobrist_bits_adds_keys_to_the_log():
+    cfg = os.path.join(PKG, "config", "mixed_rates.yaml")
+    out = json.loads(run_cli([cfg, "-d", "8,8", "-n", "50", "--seed", "3", "--state-seed", "4", "--zobrist-bits", "20"]))
+    keys = [e["zobrist"] for e in out["events"]]
+    assert len(keys) == 50 and all(0 <= k < 2 ** 20 for k in keys)
+    out2 = json.loads(run_cli([cfg, "-d", "8,8", "-n", "50", "--seed", "3", "--state-seed", "4", "--zobrist-bits", "20"]))
+    assert [e["zobrist"] for e in out2["events"]] == keys

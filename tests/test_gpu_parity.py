@@ -561,3 +561,25 @@ def test_hop_counters_in_the_no_incremental_path():
     slots = ev["slot"].astype(int)
     assert (eng.hops()[0] == np.bincount(slots[(slots >= 7) & (slots < 13)] - 7, minlength=6)).all()
     eng.close()
+
+
+# ---- Zobrist key -------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [(64, 64), (33, 47), (24, 128)])
+def test_device_zobrist_key_matches_oracle(dim):
+    import zobrist as oz
+    nrep = 4
+    st0 = np.stack([evolved_state(dim, 70 + r, nsteps=400) for r in range(nrep)])
+    assert (st0 >= 4).any()                                  # trefoils present
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.upload_state(st0)
+    for bits, seed in ((64, 0), (32, 123456789012345), (17, 9)):
+        got = eng.zobrist(bits, seed)
+        for r in range(nrep):
+            assert int(got[r]) == oz.key(st0[r], bits, seed), (bits, r)
+    # after a run (wide kernel: planes are authoritative) the key follows the lattice
+    eng.run(500, 3)
+    final = eng.download_state()
+    got = eng.zobrist(64, 1)
+    for r in range(nrep):
+        assert int(got[r]) == oz.key(final[r], 64, 1)
+    eng.close()

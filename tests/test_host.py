@@ -194,3 +194,38 @@ def test_replay_of_a_golden_log_reproduces_the_reference_lattice():
             ev = {"rule": rule, "move": T.move_info(int(rec["site"]), int(rec["slot"]), dim)}
             T.replay_event(st, ev, dim)
         assert (st == g["status1"]).all(), name
+
+
+def _labels_by_first_occurrence(keys):
+    first, out = {}, []
+    for k in keys:
+        out.append(first.setdefault(int(k), len(first)))
+    return out
+
+
+def test_zobrist_keys_partition_the_trajectory_like_the_reference():
+    """tests/golden/zobrist_ref.npz: the reference's own 64-bit Zobrist key after every event of a 5x5
+    trajectory with revisits.  Its values are unreproducible (drawn on demand from `random`), but which steps
+    share a key is a property of the lattices alone -- the host tracker must induce the same partition, and
+    equal the from-scratch key (oracle/zobrist.py) of the replayed lattice."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(GOLDEN), "..", "oracle"))
+    import zobrist as oz
+    from demo1.zobrist import ZobristTracker
+    z = np.load(os.path.join(GOLDEN, "zobrist_ref.npz"))
+    m = json.loads(str(z["meta"]))
+    dim = tuple(m["dim"])
+    for bits, seed in ((64, 5), (40, (9 << 32) | 1)):
+        tr = ZobristTracker(z["status0"], dim, bits, seed)
+        keys = [tr.key]
+        assert tr.key == oz.key(z["status0"], bits, seed) == ZobristTracker.from_scratch(z["status0"], bits, seed)
+        for t, ev in enumerate(z["events"]):
+            rule, _kind = T.CLASSES[int(ev["cls"])]
+            keys.append(tr.apply({"rule": rule, "move": T.move_info(int(ev["site"]), int(ev["slot"]), dim)}))
+            if t % 97 == 0:
+                assert keys[-1] == oz.key(tr.status, bits, seed)
+        assert (np.array(tr.status, dtype=np.uint8) == z["status1"]).all()
+        assert keys[-1] == oz.key(z["status1"], bits, seed)
+        assert all(k < 2 ** bits for k in keys)
+        assert _labels_by_first_occurrence(keys) == _labels_by_first_occurrence(z["ref_keys"])
+    assert len(set(int(k) for k in z["ref_keys"])) < len(z["ref_keys"])        # the fixture does revisit states
