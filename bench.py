@@ -351,6 +351,19 @@ def main():
         ms1 = one.timer_stop()
         one.close()
         other["64x64_single_trajectory_incremental"] = {"events_per_s": 500000 / (ms1 * 1e-3), "events": 500000}
+        # configs[0]: the reference's own CPU-runnable case (`python3 -m demo1 test-cfg.yaml`: 200x200, pristine
+        # start, test-cfg.yaml rates, one trajectory); the Python reference does ~2.5e3 events/s on it
+        tc_rates = [10.0, 0.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 0.0]
+        tc_order = [8, 9, 10, 11, 0, 2, 3, 4, 5, 6, 7]
+        tc = Engine((200, 200), tc_rates, tc_order, n_replicas=1, device=local)
+        tc.upload_state(np.zeros((1, 200 * 200), dtype=np.uint8))
+        tc.run(10000, SEED)
+        tc.sync()
+        tc.timer_start()
+        tc.run(200000, SEED)
+        mst = tc.timer_stop()
+        tc.close()
+        other["200x200_testcfg_single_trajectory"] = {"events_per_s": 200000 / (mst * 1e-3), "events": 200000}
         # configs[3] end to end: one `--no-incremental` event on 4096^2 = count-only sweep + select + apply
         big = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
         big.upload_state(iid_lattice(SWEEP_DIM, SEED))
