@@ -121,6 +121,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def recorded_replica_counters():
+    """ncu counters of the fused replica kernel from the committed capture (instructions and issue-slot use
+    per event: the quantities that bound it, since it moves ~0 HBM bytes)."""
+    p = os.path.join(ROOT, "profiles", "replica_counters.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return None
+
+
 def recorded_traffic():
     """dram bytes read + written per sweep launch, from the committed `ncu --set full` capture."""
     p = os.path.join(ROOT, "profiles", "sweep_traffic.json")
@@ -427,7 +437,8 @@ def main():
             "roofline": roofline,
             "replica_kernel": {"bound": "sm-issue / shared-memory (lattice resident in smem, ~0 HBM bytes per event)",
                                "events_per_s_per_sm": per_sm, "sm_cycles_per_event": sm_clock / per_sm,
-                               "hbm_bytes_per_event_algorithmic": 2.0 * DIM[0] * DIM[1] / E},
+                               "hbm_bytes_per_event_algorithmic": 2.0 * DIM[0] * DIM[1] / E,
+                               "ncu": recorded_replica_counters()},
             "cpu_baseline": cpu,
             "other_configs": other,
             "event_histogram": [int(x) for x in hist],
