@@ -361,6 +361,25 @@ def main():
         ms1 = one.timer_stop()
         one.close()
         other["64x64_single_trajectory_incremental"] = {"events_per_s": 500000 / (ms1 * 1e-3), "events": 500000}
+        # the same trajectory through the reference-facing API with the reference's JSON event log produced for
+        # every event (KmcSim.iter_json_lines: kernel launches of 4096 events + host formatting), wall clock
+        from demo1.sim import KmcSim, RuleSpec
+        from demo1.state import State
+        specs = [RuleSpec("CreateMonovacancy", {"from-double": 6.72584072, "make-empty": 6.72584072}, True),
+                 RuleSpec("FlipMonovacancy", {"natural": 3.41217502}, True),
+                 RuleSpec("MoveDivacancy", {"natural": 2.25, "missing-metal": 2.11199155, "missing-comb": 2.52009312,
+                                            "missing-both": 2.25}, True),
+                 RuleSpec("CreateTrefoil", {"natural": 3.12293677}, True),
+                 RuleSpec("DestroyTrefoil", {"natural": 4.43051273}, True)]
+        sim = KmcSim(State(DIM, synthetic_lattices(1, 0)[0]), specs, temperature=TEMPERATURE, seed=SEED, device=local)
+        nlog, nchar = 200000, 0
+        t0 = time.perf_counter()
+        for lines in sim.iter_json_lines(nlog):
+            nchar += sum(map(len, lines))
+        dt = time.perf_counter() - t0
+        sim.close()
+        other["64x64_single_trajectory_json_event_log"] = {"events_per_s": nlog / dt, "events": nlog,
+                                                           "json_bytes_per_event": nchar / nlog}
         # configs[0]: the reference's own CPU-runnable case (`python3 -m demo1 test-cfg.yaml`: 200x200, pristine
         # start, test-cfg.yaml rates, one trajectory); the Python reference does ~2.5e3 events/s on it
         tc_rates = [10.0, 0.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 0.0]

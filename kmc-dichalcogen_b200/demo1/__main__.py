@@ -112,14 +112,12 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
             write_key_val("initial_state", init_state.to_dict(), pretty=False)
         with write_enclosing(' "events": [\n  ', "\n ]", ofile):
             first = True
-            for step in range(nsteps):
-                # with --validate-every N the kernel validates at the end of every N-event launch
-                # (KmcSim.validate semantics); a mismatch raises AssertionError from perform_random_move
-                info = sim.perform_random_move()
-                if not first:
-                    ofile.write(",\n  ")
-                ofile.write(json.dumps(info, sort_keys=True))
-                first = False
+            # with --validate-every N the kernel validates at the end of every N-event launch
+            # (KmcSim.validate semantics); a mismatch raises AssertionError from the iterator
+            for lines in sim.iter_json_lines(nsteps):
+                if lines:
+                    ofile.write(("" if first else ",\n  ") + ",\n  ".join(lines))
+                    first = False
     ofile.write("\n")
     sim.close()
 

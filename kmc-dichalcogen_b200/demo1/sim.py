@@ -68,6 +68,13 @@ def class_table(rule_specs, temperature):
     return rules_and_rates, rates13, order
 
 
+def np_first_stop(recs):
+    """Index of the first 'nothing can happen' record (class 0xFF) in a chunk, or None."""
+    import numpy as np
+    hit = np.flatnonzero(recs["cls"] == 0xFF)
+    return int(hit[0]) if hit.size else None
+
+
 class KmcSim:
     """Runs the KMC simulation of one trajectory on the GPU.
 
@@ -166,6 +173,80 @@ class KmcSim:
         if self._zobrist is not None:
             d["zobrist"] = self._zobrist.apply(d)       # reference sim.py:141-142
         return d
+
+    # -- bulk log writer --------------------------------------------------------------------
+    def format_records_json(self, recs):
+        """``[json.dumps(self._format(r), sort_keys=True) for r in recs]`` without building a dict per event:
+        the products count*rate are taken for the whole chunk at once (same single rounding as the Python
+        floats of the slow path), ``math.fsum`` runs per event in C, the move payloads are formatted from
+        precomputed coordinates.  Character-identical to the slow path (tests/test_host.py)."""
+        import numpy as np
+        n = len(recs)
+        if n == 0:
+            return []
+        d0, d1 = self.state.dim
+        order = list(self._order)
+        rates = np.array([self._rates13[c] for c in order], dtype=np.float64)
+        weights = (recs["counts"][:, order].astype(np.float64) * rates[None, :]).tolist()
+        totals = [repr(math.fsum(w)) for w in weights]
+        site = recs["site"].astype(np.int64)
+        a, b = (site // d1), (site % d1)
+        cls, slot = recs["cls"].tolist(), recs["slot"].tolist()
+        a, b = a.tolist(), b.tolist()
+        head = ['{"kind": "%s", "move": ' % T.CLASSES[c][1] for c in range(T.N_CLASSES)]
+        import json
+        tail = [', "rate": %s, "rule": "%s", "total_rate": ' % (json.dumps(self._rates13[c]), T.CLASSES[c][0])
+                for c in range(T.N_CLASSES)]
+        out = []
+        for i in range(n):
+            sl, x, y = slot[i], a[i], b[i]
+            if sl in (0, 1, 6):
+                mv = '{"node": [%d, %d]}' % (x, y)
+            elif sl <= 5:
+                mv = '{"layer": %d, "node": [%d, %d]}' % (sl - 1 if sl <= 3 else sl - 3, x, y)
+            elif sl <= 12:
+                da, db = T.MOVE_TARGET[sl - 7]
+                mv = '{"now": [%d, %d], "was": [%d, %d]}' % ((x + da) % d0, (y + db) % d1, x, y)
+            else:
+                m = T.TREFOIL_MEMBERS[(sl - 13) & 1]
+                mv = '{"nodes": [[%d, %d], [%d, %d], [%d, %d]]}' % (
+                    x, y, (x + m[1][0]) % d0, (y + m[1][1]) % d1, (x + m[2][0]) % d0, (y + m[2][1]) % d1)
+            c = cls[i]
+            out.append(head[c] + mv + tail[c] + totals[i] + "}")
+        return out
+
+    def iter_json_lines(self, nsteps):
+        """The next ``nsteps`` events as JSON strings, chunk by chunk (what the CLI writes; same content and
+        order as calling perform_random_move ``nsteps`` times).  Raises ValueError like perform_random_move
+        when the total rate reaches zero, after yielding the events before it."""
+        import json
+        done = 0
+        while done < nsteps:
+            if self._zobrist is not None:
+                yield [json.dumps(self.perform_random_move(), sort_keys=True)]
+                done += 1
+                continue
+            if self._buffer is None or self._cursor >= len(self._buffer):
+                self.perform_random_move_prefetch()
+            take = min(nsteps - done, len(self._buffer) - self._cursor)
+            recs = self._buffer[self._cursor:self._cursor + take]
+            stop = np_first_stop(recs)
+            if stop is not None:
+                if stop:
+                    yield self.format_records_json(recs[:stop])
+                self._cursor += stop
+                raise ValueError("Cannot choose from total weight of zero!")
+            self._cursor += take
+            done += take
+            yield self.format_records_json(recs)
+
+    def perform_random_move_prefetch(self):
+        """Fill the look-ahead buffer (one kernel launch of ``chunk`` events)."""
+        try:
+            self._buffer = self._refill(self.chunk)
+        except ValueError:
+            self._buffer = self._engine._last_events[0]
+        self._cursor = 0
 
     def is_zobrist_enabled(self):
         return self._zobrist is not None

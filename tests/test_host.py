@@ -229,3 +229,33 @@ def test_zobrist_keys_partition_the_trajectory_like_the_reference():
         assert all(k < 2 ** bits for k in keys)
         assert _labels_by_first_occurrence(keys) == _labels_by_first_occurrence(z["ref_keys"])
     assert len(set(int(k) for k in z["ref_keys"])) < len(z["ref_keys"])        # the fixture does revisit states
+
+
+def test_bulk_json_writer_is_character_identical_to_the_per_event_path():
+    """KmcSim.format_records_json (what the CLI writes) against json.dumps(KmcSim._format(rec), sort_keys=True)
+    on synthetic records covering every class, slot, lattice edge (periodic wrap) and integer-valued rates."""
+    from demo1 import _native as nat
+    from demo1.sim import KmcSim
+    from demo1.state import State
+    sim = KmcSim.__new__(KmcSim)                       # no device: only the formatting state
+    sim.state = State((7, 9))
+    sim._rates13 = [10, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 1e-23, 300.5, 100.0, 0.1, 55]
+    sim._order = [8, 9, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 12]
+    sim._zobrist = None
+    slot_class = {0: [0], 1: [1], 2: [8, 9], 3: [8, 9], 4: [10, 11], 5: [10, 11], 6: [12]}
+    slot_class.update({s: [2, 3, 4, 5] for s in range(7, 13)})
+    slot_class.update({13: [6], 14: [6], 15: [7], 16: [7]})
+    rng = np.random.default_rng(5)
+    recs = []
+    for slot, classes in slot_class.items():
+        for cls in classes:
+            for site in (0, 8, 9 * 6, 62, int(rng.integers(0, 63))):
+                r = np.zeros((), dtype=nat.EVENT_FULL)
+                r["site"], r["cls"], r["slot"] = site, cls, slot
+                r["counts"] = rng.integers(0, 2 ** 20, 13)
+                recs.append(r)
+    recs = np.array(recs, dtype=nat.EVENT_FULL)
+    fast = sim.format_records_json(recs)
+    slow = [json.dumps(sim._format(r), sort_keys=True) for r in recs]
+    assert fast == slow
+    assert sim.format_records_json(recs[:0]) == []
