@@ -218,27 +218,57 @@ class KmcSim:
     def iter_json_lines(self, nsteps):
         """The next ``nsteps`` events as JSON strings, chunk by chunk (what the CLI writes; same content and
         order as calling perform_random_move ``nsteps`` times).  Raises ValueError like perform_random_move
-        when the total rate reaches zero, after yielding the events before it."""
+        when the total rate reaches zero, after yielding the events before it.  While one chunk is being
+        formatted the kernel launch for the next one runs on a helper thread (ctypes drops the GIL), but only
+        if the caller still needs events from it, so the lattice never runs ahead of ``nsteps`` by more than
+        the usual look-ahead of one chunk."""
         import json
+        from concurrent.futures import ThreadPoolExecutor
         done = 0
-        while done < nsteps:
-            if self._zobrist is not None:
-                yield [json.dumps(self.perform_random_move(), sort_keys=True)]
-                done += 1
-                continue
-            if self._buffer is None or self._cursor >= len(self._buffer):
-                self.perform_random_move_prefetch()
-            take = min(nsteps - done, len(self._buffer) - self._cursor)
-            recs = self._buffer[self._cursor:self._cursor + take]
-            stop = np_first_stop(recs)
-            if stop is not None:
-                if stop:
-                    yield self.format_records_json(recs[:stop])
-                self._cursor += stop
-                raise ValueError("Cannot choose from total weight of zero!")
-            self._cursor += take
-            done += take
-            yield self.format_records_json(recs)
+        pool, pending = None, None
+
+        def fetch():
+            try:
+                return self._refill(self.chunk), None
+            except ValueError:
+                return self._engine._last_events[0], None
+            except BaseException as e:                     # AssertionError (validate), RuntimeError (CUDA)
+                return None, e
+
+        try:
+            while done < nsteps:
+                if self._zobrist is not None:
+                    yield [json.dumps(self.perform_random_move(), sort_keys=True)]
+                    done += 1
+                    continue
+                if self._buffer is None or self._cursor >= len(self._buffer):
+                    buf, err = pending.result() if pending is not None else fetch()
+                    pending = None
+                    if err is not None:
+                        raise err
+                    self._buffer, self._cursor = buf, 0
+                take = min(nsteps - done, len(self._buffer) - self._cursor)
+                recs = self._buffer[self._cursor:self._cursor + take]
+                stop = np_first_stop(recs)
+                if stop is None and self._cursor + take >= len(self._buffer) and done + take < nsteps:
+                    if pool is None:
+                        pool = ThreadPoolExecutor(max_workers=1)
+                    pending = pool.submit(fetch)           # next launch overlaps the formatting below
+                if stop is not None:
+                    if stop:
+                        yield self.format_records_json(recs[:stop])
+                    self._cursor += stop
+                    raise ValueError("Cannot choose from total weight of zero!")
+                self._cursor += take
+                done += take
+                yield self.format_records_json(recs)
+        finally:
+            if pending is not None:                        # generator abandoned mid-way: keep the look-ahead
+                buf, err = pending.result()
+                if err is None:
+                    self._buffer, self._cursor = buf, 0
+            if pool is not None:
+                pool.shutdown(wait=True)
 
     def perform_random_move_prefetch(self):
         """Fill the look-ahead buffer (one kernel launch of ``chunk`` events)."""

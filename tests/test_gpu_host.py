@@ -199,3 +199,29 @@ def test_cli_zobrist_bits_adds_keys_to_the_log():
     assert len(keys) == 50 and all(0 <= k < 2 ** 20 for k in keys)
     out2 = json.loads(run_cli([cfg, "-d", "8,8", "-n", "50", "--seed", "3", "--state-seed", "4", "--zobrist-bits", "20"]))
     assert [e["zobrist"] for e in out2["events"]] == keys
+
+
+def test_bulk_json_lines_equal_the_per_event_api_across_launches():
+    """KmcSim.iter_json_lines (prefetching the next launch on a helper thread) against perform_random_move,
+    same seed, chunk boundaries inside the run; then the zero-rate stop."""
+    g = load("allrules_8x8")
+    m = g["meta"]
+    a = KmcSim(State(m["dim"], g["status0"]), specs_from_meta(m), seed=m["seed"], chunk=257, validate_launches=True)
+    b = KmcSim(State(m["dim"], g["status0"]), specs_from_meta(m), seed=m["seed"], chunk=100)
+    fast = [line for lines in a.iter_json_lines(700) for line in lines]
+    fast += [line for lines in a.iter_json_lines(333) for line in lines]          # resumes inside a chunk
+    slow = [json.dumps(b.perform_random_move(), sort_keys=True) for _ in range(1033)]
+    assert fast == slow
+    assert json.loads(fast[0])["total_rate"] == g["events"][0]["total_rate"]
+    a.close()
+    b.close()
+    # only FillDivacancy on a lattice with two divacancies: two events, then ValueError
+    st = State((5, 5))
+    st.status[3] = st.status[17] = 3
+    sim = KmcSim(st, [RuleSpec("FillDivacancy", {"natural": 5.0}, False)], seed=1, chunk=10)
+    got = []
+    with pytest.raises(ValueError, match="total weight of zero"):
+        for lines in sim.iter_json_lines(8):
+            got += lines
+    assert len(got) == 2 and all(json.loads(x)["rule"] == "FillDivacancy" for x in got)
+    sim.close()
