@@ -583,3 +583,27 @@ def test_device_zobrist_key_matches_oracle(dim):
     for r in range(nrep):
         assert int(got[r]) == oz.key(final[r], 64, 1)
     eng.close()
+
+
+def test_million_step_single_trajectory_is_bit_exact():
+    """BASELINE config 2 at its full length: 64x64 WSe2 at 1500 K, one trajectory, 10^6 events in launches of
+    2^17, every event (class, site, slot, sequential total rate) and the final lattice against the C oracle."""
+    dim, nsteps, seed = (64, 64), 1_000_000, 20261019
+    rates = wse2_rates(1500.0)
+    st0 = exact_state(dim, 0.05, 0.05, seed)
+    o = ko.Oracle(dim, rates, WSE2_ORDER, st0)
+    done, want = o.run_philox(seed, 0, 0, nsteps)
+    assert done == nsteps
+    eng = Engine(dim, rates, WSE2_ORDER, n_replicas=1)
+    eng.upload_state(st0)
+    pos = 0
+    while pos < nsteps:
+        n = min(1 << 17, nsteps - pos)
+        ev = eng.run(n, seed, log_mode=nat.LOG_COMPACT, validate=True)[0]
+        w = want[pos:pos + n]
+        assert (ev["site"] == w["site"]).all() and (ev["cls"] == w["cls"]).all() and (ev["slot"] == w["slot"]).all()
+        assert (ev["total_rate"].view(np.uint64) == w["total_naive"].view(np.uint64)).all()
+        pos += n
+    assert (eng.download_state()[0] == o.status()).all()
+    assert (eng.histogram_per_replica()[0] == o.hist()).all()
+    eng.close()
