@@ -459,6 +459,35 @@ def test_full_size_replica_batch_properties():
     eng.close()
 
 
+def test_headline_batch_at_full_size():
+    """BASELINE config 3 exactly as benchmarked: 64x64 WSe2, 16384 replicas (two per warp), 10^4 events each
+    in one launch, lattices generated on the device.  Every replica validates its incremental tables against a
+    fresh enumeration; totals are conserved; a sample of replicas -- both halves of warps, first and last
+    blocks -- is bit-equal to the oracle in lattice, histogram and hop counters."""
+    dim, nrep, nsteps, seed = (64, 64), 16384, 10000, 20261019
+    rates, order = wse2_rates(1500.0), WSE2_ORDER
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    eng.generate_state("exact", {"divacancy": 0.05, "monovacancy": 0.05}, seed)
+    st0 = eng.download_state()
+    eng.run(nsteps, seed, log_mode=nat.LOG_NONE, validate=True)
+    assert (eng.steps_done() == nsteps).all()
+    hist = eng.histogram_per_replica()
+    assert (hist.sum(axis=1) == nsteps).all()
+    hops = eng.hops()
+    assert (hops.sum(axis=1) == hist[:, 2:6].sum(axis=1)).all()
+    final = eng.download_state()
+    assert ((final == 3).sum(axis=1) + 3 * (final == 4).sum(axis=1) + 3 * (final == 7).sum(axis=1)
+            == (st0 == 3).sum(axis=1)).all()              # WSe2 rules conserve divacancies (trefoil = 3 of them)
+    for r in [0, 1, 14, 15, 16, 4097, 8190, 8191, 16382, 16383]:
+        o = ko.Oracle(dim, rates, order, st0[r])
+        _, ev = o.run_philox(seed, r, 0, nsteps)
+        assert (final[r] == o.status()).all(), r
+        assert (hist[r] == o.hist()).all(), r
+        slots = ev["slot"].astype(int)
+        assert (hops[r] == np.bincount(slots[(slots >= 7) & (slots < 13)] - 7, minlength=6)).all(), r
+    eng.close()
+
+
 # ---- device-side initial-state generators (SURVEY 8(f) rank 3) -------------------------------------------
 def test_device_state_generator_matches_reference_fixtures():
     """kmc_generate_state against the reference's gen_random_state driven by the same Philox stream
