@@ -488,6 +488,29 @@ def test_headline_batch_at_full_size():
     eng.close()
 
 
+def test_config5_batch_at_per_gpu_size():
+    """BASELINE config 5, one GPU's share: 1024x1024 x 128 replicas on the wide bit-plane kernel, lattices
+    generated on the device ('approx': 5 % divacancies, 5 % monovacancies), two launches; the row table is
+    validated against a fresh one on every replica and a sample of replicas is bit-equal to the oracle."""
+    dim, nrep, seed = (1024, 1024), 128, 20261019
+    rates, order = wse2_rates(1500.0), WSE2_ORDER
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    eng.generate_state("approx", {"divacancy": 0.05, "monovacancy": 0.05}, seed)
+    picks = [0, 77, 127]
+    st0 = eng.download_state()[picks].copy()
+    eng.run(3000, seed, validate=True)
+    eng.run(2000, seed, validate=True)
+    assert (eng.steps_done() == 5000).all()
+    final = eng.download_state()
+    hist = eng.histogram_per_replica()
+    for i, r in enumerate(picks):
+        o = ko.Oracle(dim, rates, order, st0[i])
+        o.run_philox(seed, r, 0, 5000, log=False)
+        assert (final[r] == o.status()).all(), r
+        assert (hist[r] == o.hist()).all(), r
+    eng.close()
+
+
 # ---- device-side initial-state generators (SURVEY 8(f) rank 3) -------------------------------------------
 def test_device_state_generator_matches_reference_fixtures():
     """kmc_generate_state against the reference's gen_random_state driven by the same Philox stream
