@@ -89,7 +89,7 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
 
     if replicas > 1 or stats_only:
         return run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device,
-                         state_seed if independent_states else None, independent_states)
+                         state_seed, independent_states)
     if independent_states:
         die("--independent-states needs --replicas N or --stats-only")
 
@@ -124,36 +124,63 @@ def run(ofile, nsteps, dims, config_dict, validate_every, incremental, save_init
 
 def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas, device, state_seed=None,
               independent_states=False, zobrist=None):
-    """--replicas / --stats-only: many independent trajectories from the same initial lattice, one
-    warp each; output is the per-class event histogram instead of an event log."""
+    """--replicas / --stats-only: many independent trajectories; output is the per-class event histogram and
+    the divacancy hop statistics instead of an event log.  Under torchrun (one process per GPU) the replicas are
+    sharded by contiguous global index; replica r's trajectory depends only on (seed, r), so the result does
+    not depend on the number of GPUs.  Rank 0 writes the output."""
     import os
     import numpy as np
+    from . import parallel
     from . import tables as T
     from .engine import Engine
     rules_and_rates, rates13, order = class_table(cfg["rule_specs"], temperature)
     info = {"%s:%s" % (rule, kind): rate for rule, rates in rules_and_rates.items() for kind, rate in rates.items()}
+    rank, size, local = parallel.world()
+    if size > 1:
+        if seed is None or (state_seed is None and not independent_states):
+            die("--seed (and --state-seed, unless --independent-states) are required when several processes "
+                "share a batch")
+        import torch
+        device = local
+        torch.cuda.set_device(local)
+        parallel.init_quiet(device=torch.device("cuda", local))
     seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
-    eng = Engine(init_state.dim, rates13, order, n_replicas=replicas, device=device)
+    lo, hi = parallel.replica_range(replicas, size, rank)
+    if hi == lo:
+        die("more processes than replicas")
+    eng = Engine(init_state.dim, rates13, order, n_replicas=hi - lo, device=device)
     if independent_states:
         gen = cfg["state_gen_func"].keywords          # partial(gen_random_state, mode=..., params=...)
-        eng.generate_state(gen["mode"], gen["params"], seed if state_seed is None else state_seed)
+        eng.generate_state(gen["mode"], gen["params"], seed if state_seed is None else state_seed, replica0=lo)
     else:
-        eng.upload_state(np.tile(init_state.status, (replicas, 1)))
+        eng.upload_state(np.tile(init_state.status, (hi - lo, 1)))
     try:
-        eng.run(nsteps, seed, validate=True)
+        eng.run(nsteps, seed, replica0=lo, validate=True)
     except ValueError:
         pass
-    hist = eng.histogram()
+    dev = None
+    if size > 1:
+        import torch
+        dev = torch.device("cuda", local)
+    sums = np.concatenate([eng.histogram(), eng.hops().sum(axis=0), [int(eng.steps_done().sum())]]).astype(np.int64)
+    sums = parallel.reduce_histogram(sums, device=dev)
+    # sum of squared net displacements as exact integers (a^2 + a*b + b^2 per replica)
+    d = eng.displacement()
+    sq = parallel.reduce_histogram(np.array([int((d[:, 0] ** 2 + d[:, 0] * d[:, 1] + d[:, 1] ** 2).sum())],
+                                            dtype=np.int64), device=dev)
+    eng.close()
+    if rank != 0:
+        return
+    hist, hops, done = sums[:13], sums[13:19], sums[19]
     out = {"grid": grid_info(dims), "temperature": temperature, "rates": info, "replicas": replicas,
-           "seed": seed, "events_done": int(eng.steps_done().sum()),
+           "seed": seed, "events_done": int(done), "processes": size,
            "histogram": {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in order},
            # divacancy hops per direction (neighbour order of state.py:443-459), summed over replicas, and the
            # mean squared net displacement of a replica's divacancy population in axial lattice units
-           "divacancy_hops": [int(x) for x in eng.hops().sum(axis=0)],
-           "mean_squared_net_displacement": float(np.mean(axial_norm2(eng.displacement())))}
+           "divacancy_hops": [int(x) for x in hops],
+           "mean_squared_net_displacement": float(sq[0]) / replicas}
     json.dump(out, ofile, indent=2, sort_keys=True)
     ofile.write("\n")
-    eng.close()
 
 
 def axial_norm2(d):

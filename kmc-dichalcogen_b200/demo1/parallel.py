@@ -36,6 +36,26 @@ def init(backend=None, device=None):
     return rank, size, local
 
 
+def init_quiet(backend=None, device=None):
+    """init() + a first barrier with file descriptor 1 pointed at stderr: NCCL prints its version banner on
+    stdout when the communicator comes up, and our stdout carries JSON."""
+    import sys
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        out = init(backend=backend, device=device)
+        barrier()
+        if device is not None:
+            import torch
+            torch.cuda.synchronize(device)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    return out
+
+
 def reduce_histogram(hist, device=None):
     """Sum an int64 histogram (numpy) over all ranks; returns numpy on every rank."""
     import torch

@@ -225,3 +225,23 @@ def test_bulk_json_lines_equal_the_per_event_api_across_launches():
             got += lines
     assert len(got) == 2 and all(json.loads(x)["rule"] == "FillDivacancy" for x in got)
     sim.close()
+
+
+def test_cli_batch_is_independent_of_the_number_of_gpus():
+    """The replica batch under torchrun (one process per GPU, replicas sharded by global index, NCCL all-reduce
+    of the statistics) gives the same output as one process: replica r depends only on (seed, r)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = os.path.join(PKG, "config", "wse2_1500K.yaml")
+    args = [cfg, "-T", "1500", "-d", "64,64", "-n", "400", "--seed", "3", "--state-seed", "4", "--replicas", "101",
+            "--independent-states"]
+    one = json.loads(run_cli(args))
+    env = dict(os.environ, PYTHONPATH=PKG)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", "-m", "demo1"] + args,
+                       capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert p.returncode == 0, p.stderr[-3000:]
+    two = json.loads(p.stdout)
+    assert two.pop("processes") == 2 and one.pop("processes") == 1
+    assert two == one
