@@ -659,3 +659,25 @@ def test_million_step_single_trajectory_is_bit_exact():
     assert (eng.download_state()[0] == o.status()).all()
     assert (eng.histogram_per_replica()[0] == o.hist()).all()
     eng.close()
+
+
+@pytest.mark.parametrize("variant,dim", [(1, (16, 20)), (2, (33, 47)), (3, (16, 80)), (4, (64, 64)), (4, (9, 64)),
+                                         (5, (12, 128))])
+def test_injected_draws_on_every_replica_kernel(variant, dim):
+    """kmc_step_draws (caller-supplied uniforms, the parity seam of SURVEY 8(c)) on every kernel variant, three
+    replicas with different draw streams, two calls."""
+    nrep, nsteps = 3, 1500
+    st0 = np.stack([evolved_state(dim, 90 + r, nsteps=200) for r in range(nrep)])
+    d = np.stack([philox.draws(1234, 50 + r, 0, nsteps) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(st0)
+    ev = np.concatenate([eng.step_draws(d[:, :700], log_mode=nat.LOG_COMPACT, validate=True),
+                         eng.step_draws(d[:, 700:], log_mode=nat.LOG_COMPACT, validate=True)], axis=1)
+    final = eng.download_state()
+    for r in range(nrep):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
+        _, want = o.run_draws(d[r])
+        assert_events_equal(ev[r], want, "variant %d replica %d" % (variant, r))
+        assert (final[r] == o.status()).all()
+    eng.close()
