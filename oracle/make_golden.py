@@ -197,6 +197,44 @@ def zobrist_reference_fixture():
                                                                      os.path.getsize(path)))
 
 
+def animate_replay_fixture():
+    """the product's JSON log (grid / initial_state / events in the formats of
+    kmc-dichalcogen_b200/demo1: State.to_dict, tables.move_info) replayed by the reference's own consumer,
+    animate.py do_basic.  For three golden trajectories the replayed final lattice must equal the reference
+    simulation's; the fixture keeps the replayed array and a digest of the product-formatted log."""
+    import hashlib
+    import importlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    T = importlib.import_module("kmc-dichalcogen_b200.demo1.tables")
+    S = importlib.import_module("kmc-dichalcogen_b200.demo1.state")
+    import animate_replay
+    out, metas = {}, []
+    for name in ("allrules_8x8", "wse2_hot_24x24", "allrules_40x70"):
+        g = np.load(os.path.join(OUT, name + ".npz"))
+        m = json.loads(str(g["meta"]))
+        dim = tuple(m["dim"])
+        events = [{"rule": T.CLASSES[int(e["cls"])][0], "kind": T.CLASSES[int(e["cls"])][1],
+                   "move": T.move_info(int(e["site"]), int(e["slot"]), dim)} for e in g["events"]]
+        full = {"grid": {"lattice_type": "hexagonal", "coord_format": "axial", "dim": list(dim)},
+                "initial_state": S.State(dim, g["status0"]).to_dict(), "events": events}
+        full = json.loads(json.dumps(full))               # exactly what a consumer reads back
+        final = animate_replay.replay(full)
+        want = g["status1"].reshape(dim).astype(np.int64)
+        assert ((final < 65536) == (want < 4)).all(), name
+        assert (final[want < 4] == want[want < 4]).all(), name
+        # nodes of one trefoil share an id; different trefoils differ
+        ids = {}
+        for a, b in zip(*np.nonzero(want >= 4)):
+            ids.setdefault(int(final[a, b]), []).append(int(want[a, b]))
+        assert all(sorted(v) in ([4, 5, 6], [7, 8, 9]) for v in ids.values()), name
+        out["final_" + name] = final.astype(np.int32)
+        metas.append({"name": name, "n_events": len(events), "n_trefoils": len(ids),
+                      "log_sha256": hashlib.sha256(json.dumps(full, sort_keys=True).encode()).hexdigest()})
+        print("animate replay %-16s %5d events, %d trefoils at the end: ok" % (name, len(events), len(ids)))
+    path = os.path.join(OUT, "animate_replay.npz")
+    np.savez_compressed(path, meta=json.dumps(metas), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. all eight rules, pristine start: trefoils are created and destroyed along the way
@@ -226,6 +264,7 @@ def main():
     state_gen_fixtures()
     state_gen_philox_fixtures()
     zobrist_reference_fixture()
+    animate_replay_fixture()
     native_statistics()
 
 

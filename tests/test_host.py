@@ -259,3 +259,27 @@ def test_bulk_json_writer_is_character_identical_to_the_per_event_path():
     slow = [json.dumps(sim._format(r), sort_keys=True) for r in recs]
     assert fast == slow
     assert sim.format_records_json(recs[:0]) == []
+
+
+def test_product_log_format_replays_in_the_references_animate_consumer():
+    """tests/golden/animate_replay.npz: the reference's animate.py `do_basic` (its own consumer of the JSON log,
+    sliced from the source and run unmodified by oracle/animate_replay.py in the build container) was fed logs
+    in this package's formats (State.to_dict, tables.move_info) and reproduced the reference simulation's final
+    lattices.  Here: the log this package writes for the same events still has the digest that was replayed,
+    and the replayed arrays agree with the fixtures' final lattices."""
+    import hashlib
+    z = np.load(os.path.join(GOLDEN, "animate_replay.npz"))
+    for m in json.loads(str(z["meta"])):
+        g = load(m["name"])
+        dim = tuple(g["meta"]["dim"])
+        events = [{"rule": T.CLASSES[int(e["cls"])][0], "kind": T.CLASSES[int(e["cls"])][1],
+                   "move": T.move_info(int(e["site"]), int(e["slot"]), dim)} for e in g["events"]]
+        full = {"grid": {"lattice_type": "hexagonal", "coord_format": "axial", "dim": list(dim)},
+                "initial_state": State(dim, g["status0"]).to_dict(), "events": events}
+        full = json.loads(json.dumps(full))
+        assert hashlib.sha256(json.dumps(full, sort_keys=True).encode()).hexdigest() == m["log_sha256"], m["name"]
+        final = z["final_" + m["name"]]
+        want = g["status1"].reshape(dim)
+        assert ((final < 65536) == (want < 4)).all()
+        assert (final[want < 4] == want[want < 4]).all()
+        assert len(set(final[want >= 4].tolist())) == m["n_trefoils"] == (want == 4).sum() + (want == 7).sum()

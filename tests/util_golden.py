@@ -10,7 +10,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def trajectory_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith(("state_gen", "native_stats", "zobrist_ref")))
+                  if not os.path.basename(p).startswith(("state_gen", "native_stats", "zobrist_ref", "animate_replay")))
 
 
 def load(name):
