@@ -530,10 +530,17 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
         const size_t hbytes = replica_hw_bytes(h->d0);
         if (2 * hbytes > (size_t)h->max_smem_optin) return fail(KMC_ERR_ARG, "lattice too large for the half-warp kernel");
-        int hpb = h->warps_per_block > 0 ? 2 * h->warps_per_block : 16;      // replicas (half-warps) per block
+        // replicas (half-warps) per block: a multiple of 8 (4 warps, one per scheduler), at most 56 (28 warps of
+        // 72 registers fill an SM); small batches get smaller blocks so that every SM has one
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        int hpb = (int)(((long long)h->R + sms - 1) / sms);
+        hpb = (hpb + 7) & ~7;
+        if (h->warps_per_block > 0) hpb = 2 * h->warps_per_block;
         if (const char *e = getenv("KMC_HW_REPLICAS_PER_BLOCK")) hpb = atoi(e) & ~1;     // tuning knob
-        if (hpb > 16) hpb = 16;
+        if (hpb > HW_MAX_THREADS / 16) hpb = HW_MAX_THREADS / 16;
         if (hpb < 2) hpb = 2;
+        while (hpb > 8 && hpb * hbytes > (size_t)h->max_smem_optin) hpb -= 8;
         while (hpb > 2 && hpb * hbytes > (size_t)h->max_smem_optin) hpb -= 2;
         const size_t smem = hpb * hbytes;
         const size_t rs = record_size(log_mode);

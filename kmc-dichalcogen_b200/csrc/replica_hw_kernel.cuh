@@ -23,11 +23,24 @@ namespace kmc {
 // instead of holding pre-rotated copies: 4.6 KiB per replica -> 48 replicas = 24 warps per SM.
 enum { HW_PLANES = N_TYPES };      // plane index == plane type: T_Z, T_D, T_M1, T_M2, T_A4, T_A7
 
+// Row counts are kept only for the five neighbourhood classes (MoveDivacancy x 4, CreateTrefoil); the row
+// counts of the eight own-status classes are popcounts of the planes (derived when such a class is chosen).
+enum { HW_RC = 5 };
 __host__ __device__ inline size_t replica_hw_bytes(int d0) {      // per replica
     const size_t d0p = ((size_t)d0 + 3) & ~(size_t)3;
     const size_t planes = (size_t)HW_PLANES * d0 * 8;
-    const size_t rc = (NC * d0p * 2 + 15) & ~(size_t)15;
+    const size_t rc = (HW_RC * d0p * 2 + 15) & ~(size_t)15;
     return planes + rc;
+}
+// total number of moves of an own-status class over the lattice: sum over plane types of
+// g1(status of the type) * popcount (g1: 2 bits per status, see g1_const)
+__device__ __forceinline__ int hw_own_total(const u64 *PL, int d0, uint32_t g1) {
+    int tot = 0;
+    for (int a = 0; a < d0; a++)
+        tot += (int)(g1 & 3u) * __popcll(PL[T_Z * d0 + a]) + (int)((g1 >> 6) & 3u) * __popcll(PL[T_D * d0 + a]) +
+               (int)((g1 >> 2) & 3u) * __popcll(PL[T_M1 * d0 + a]) + (int)((g1 >> 4) & 3u) * __popcll(PL[T_M2 * d0 + a]) +
+               (int)((g1 >> 8) & 3u) * __popcll(PL[T_A4 * d0 + a]) + (int)((g1 >> 14) & 3u) * __popcll(PL[T_A7 * d0 + a]);
+    return tot;
 }
 
 // word whose bit b is bit (b + db) of x, db in {-1, 0, +1}: (sh, sw) = (0, no) / (1, no) / (31, swap halves)
@@ -185,8 +198,12 @@ __device__ __forceinline__ int nth_set_bit_hw(u64 m, uint32_t idx, const Half &h
     return 4 * L + ((__ffs(nibble) - 1) & 3);
 }
 
+// One block of up to 28 warps (56 replicas) per SM: 72 registers per thread let 28 warps be resident, 7 per
+// scheduler (a block shape that is not a multiple of 4 warps loads the schedulers unevenly: 3 blocks of 9
+// warps measured 1.89e9 events/s, 2 blocks of 14 warps 2.22e9, 1 block of 28 warps 2.37e9).
+constexpr int HW_MAX_THREADS = 896;
 template <int TD0, int TD1>
-__global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaParams p)
+__global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
 
     extern __shared__ uint4 smem_raw[];
     u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot_in_block * replica_hw_bytes(d0));
-    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + HW_PLANES * d0);      // [NC][d0p]
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + HW_PLANES * d0);      // [HW_RC][d0p]: classes 2..6
     const u64 *rc64 = reinterpret_cast<const u64 *>(rc16);
 
     // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
@@ -239,7 +256,7 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
         uint32_t cnt[NC];
         if (a < d0) hw_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
-        for (int c = 0; c < NC; c++) rc16[c * d0p + a] = a < d0 ? (uint16_t)cnt[c] : (uint16_t)0;
+        for (int c = 0; c < HW_RC; c++) rc16[c * d0p + a] = a < d0 ? (uint16_t)cnt[C_MOVE_DIV + c] : (uint16_t)0;
     }
     __syncwarp(hw.mask);
 
@@ -247,10 +264,11 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
     const int myc = hl < NC ? hl : 0;
     const double rate = (hl < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
     const int pos = (hl < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + hl;
-    int tot = 0;
-    if (hl < NC)
-        for (int a = 0; a < d0; a++) tot += rc16[hl * d0p + a];
     const uint32_t my_g1 = (hl < NC && !(hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)) ? g1_const(hl) : 0u;
+    int tot = 0;
+    if (hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)
+        for (int a = 0; a < d0; a++) tot += rc16[(hl - C_MOVE_DIV) * d0p + a];
+    else if (my_g1) tot = hw_own_total(PL, d0, my_g1);
     unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(hl);
     double tclock = 0.0;
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
             uint32_t cnt[NC];
             hw_row_counts<TD0>(PL, d0, a, rb, cnt);
 #pragma unroll
-            for (int c = 0; c < NC; c++) bad |= (rc16[c * d0p + a] != (uint16_t)cnt[c]);
+            for (int c = 0; c < HW_RC; c++) bad |= (rc16[c * d0p + a] != (uint16_t)cnt[C_MOVE_DIV + c]);
             const u64 z = PL[T_Z * d0 + a], dv = PL[T_D * d0 + a];
             const u64 types[N_TYPES] = {z, dv, PL[T_M1 * d0 + a], PL[T_M2 * d0 + a], PL[T_A4 * d0 + a], PL[T_A7 * d0 + a]};
             u64 seen = 0, dup = 0;
@@ -297,10 +315,12 @@ __global__ void __launch_bounds__(256, 3) kmc_replica_hw_kernel(const ReplicaPar
             for (int q = 0; q < N_TYPES; q++) { dup |= seen & types[q]; seen |= types[q]; }
             bad |= dup != 0;
         }
-        if (hl < NC) {
+        if (hl >= C_MOVE_DIV && hl <= C_CREATE_TREF) {
             int fresh = 0;
-            for (int a = 0; a < d0; a++) fresh += rc16[hl * d0p + a];
+            for (int a = 0; a < d0; a++) fresh += rc16[(hl - C_MOVE_DIV) * d0p + a];
             bad |= (fresh != tot);
+        } else if (my_g1) {
+            bad |= (hw_own_total(PL, d0, my_g1) != tot);
         }
         if (__any_sync(hw.mask, bad)) flag |= FLAG_VALIDATE;
     }
