@@ -467,8 +467,18 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
                          wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
     if (h->variant == 5 && !wide_ok)
         return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs dim1 a multiple of 64 in (64, 2048] and dim0 <= ~8700");
-    // auto: lattices whose byte form does not fit shared memory
-    if (h->variant == 5 || (h->variant == 0 && wide_ok && replica_warp_bytes(h->d0, h->d1) > (size_t)h->max_smem_optin)) {
+    // auto: lattices whose byte form does not fit shared memory, and batches too large for all replicas to be
+    // resident with their byte lattices in shared memory (then the byte kernel runs in waves of a few warps per
+    // SM: 1184 replicas of 256x256 take 11.9 us per event there, 4.7 us here)
+    bool wide_auto = false;
+    if (h->variant == 0 && wide_ok) {
+        const size_t bbytes = replica_warp_bytes(h->d0, h->d1);
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const long long per_sm = bbytes <= (size_t)h->max_smem_optin ? (long long)((size_t)h->max_smem_optin / bbytes) : 0;
+        wide_auto = per_sm == 0 || (long long)h->R > per_sm * sms;
+    }
+    if (h->variant == 5 || wide_auto) {
         const int Ww = h->d1 >> 6, d0p = (h->d0 + 1) & ~1;
         const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * Ww;
         const size_t hier_elems = (size_t)h->R * NC * d0p;
