@@ -181,8 +181,8 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
  * 4 = bit-sliced with a half-warp per replica, 3 = byte lattice left in HBM/L2 with only the
  * row-count hierarchy in shared memory (chosen automatically when the lattice does not fit and variant 5
  * does not apply), 5 = bit planes of rows wider than 64 sites kept in HBM/L2 with the row table in shared
- * memory (dim1 a multiple of 64 in (64, 2048]; chosen automatically when the byte lattice does not fit
- * shared memory, e.g. 1024x1024).  All produce identical results. */
+ * memory (64 < dim1 <= 2048; chosen automatically when the byte lattices of the batch cannot all be resident
+ * in shared memory, e.g. 1024x1024 or a thousand 256x256 replicas).  All produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
 /* aligned-shape sweep kernel: 0 = automatic (rolling window over rows when a row fills a CTA, i.e. 4096

@@ -184,7 +184,7 @@ __global__ void kmc_check_state_kernel(const uint8_t *status, long long total, i
 static int ensure_bytes(kmc_engine *h)
 {
     if (!h->bytes_stale) return KMC_OK;
-    const long long cells = (long long)h->R * h->d0 * (h->d1 >> 6);
+    const long long cells = (long long)h->R * h->d0 * wide_anchor_words(h->d1);
     kmc_wide_unpack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_status, h->R, h->d0, h->d1);
     CU(cudaGetLastError());
     h->launches += 1;
@@ -463,10 +463,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // the byte-lattice kernel
     // (two replicas per warp pay off once one replica per warp would already fill the GPU; small batches and
     // single trajectories are latency-bound and run faster with a full warp each)
-    const bool wide_ok = h->d1 > 64 && (h->d1 & 63) == 0 && h->d1 <= 2048 &&
+    const bool wide_ok = h->d1 > 64 && h->d1 <= 2048 &&
                          wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
     if (h->variant == 5 && !wide_ok)
-        return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs dim1 a multiple of 64 in (64, 2048] and dim0 <= ~8700");
+        return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs 64 < dim1 <= 2048 and dim0 <= ~8700");
     // auto: lattices whose byte form does not fit shared memory, and batches too large for all replicas to be
     // resident with their byte lattices in shared memory (then the byte kernel runs in waves of a few warps per
     // SM: 1184 replicas of 256x256 take 11.9 us per event there, 4.7 us here)
@@ -479,8 +479,8 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         wide_auto = per_sm == 0 || (long long)h->R > per_sm * sms;
     }
     if (h->variant == 5 || wide_auto) {
-        const int Ww = h->d1 >> 6, d0p = (h->d0 + 1) & ~1;
-        const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * Ww;
+        const int Wa = wide_anchor_words(h->d1), We = wide_row_words(h->d1), d0p = (h->d0 + 1) & ~1;
+        const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * We;
         const size_t hier_elems = (size_t)h->R * NC * d0p;
         if (!h->d_planes) {
             CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
@@ -488,7 +488,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         }
         if (!h->planes_valid) {
             int rc = ensure_bytes(h); if (rc) return rc;
-            const long long cells = (long long)h->R * h->d0 * Ww, rows = (long long)h->R * h->d0;
+            const long long cells = (long long)h->R * h->d0 * We, rows = (long long)h->R * h->d0;
             kmc_wide_pack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_status, h->d_planes, h->R, h->d0, h->d1);
             kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p);
             CU(cudaGetLastError());
@@ -513,7 +513,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.validate = validate;
         p.clock = h->clock_on ? h->d_clock : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
-        q.planes = h->d_planes; q.hier = h->d_whier; q.W = Ww; q.d0p = d0p;
+        q.planes = h->d_planes; q.hier = h->d_whier; q.Wa = Wa; q.d0p = d0p;
         CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
         CU(cudaGetLastError());

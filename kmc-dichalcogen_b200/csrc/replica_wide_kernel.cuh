@@ -1,16 +1,26 @@
-// replica_wide_kernel.cuh -- K3 + K4 for lattices too large for shared memory (e.g. 1024 x 1024,
-// BASELINE config 5): the bit-sliced algorithm of replica_bp_kernel.cuh with the six predicate planes held
-// in HBM/L2 (rows of W = d1/64 words) and only the class-major row-count table in shared memory.
+// replica_wide_kernel.cuh -- K3 + K4 for lattices with rows wider than 64 sites that are too large, or too
+// many, for shared memory (e.g. 1024 x 1024, BASELINE config 5): the bit-sliced algorithm of
+// replica_bp_kernel.cuh with the six predicate planes held in HBM/L2 and only the class-major row-count table
+// in shared memory.
+//
+// Plane rows carry a two-column halo on each side so that neighbour columns never need wrap logic: a row is a
+// bit array of d1 + 4 positions, position q holding column (q - 2) mod d1 (positions 0, 1 repeat the last two
+// columns, positions d1 + 2, d1 + 3 the first two).  The window of anchor word w (columns 64w .. 64w + 63)
+// shifted by db in [-2, 2] columns starts at position 64w + db + 2, i.e. always inside words w and w + 1:
+//     window = (X[w] >> (db + 2)) | (X[w + 1] << (62 - db))
+// Rows have Wa = ceil(d1 / 64) anchor words and We = Wa + 1 stored words; d1 need not be a multiple of 64 (the
+// last anchor word is masked).  A site update writes its main position and, within 2 columns of a row end, its
+// halo copy.
 //
 // One warp owns one replica.  What keeps an event cheap on a 1 Mi-site lattice is that everything is local
 // to a handful of 64-site words:
-//   * site search inside the chosen row: one lane per word builds the six MoveDivacancy direction masks of
-//     its word from a 3x3 neighbourhood of plane words (one round of independent loads), per-direction
-//     totals come from six warp reductions, one warp scan finds the word, a popcount-select the bit;
-//   * refresh: only the (row, word) cells within 3 rows and 2 columns of the touched nodes can change;
-//     one lane per cell re-derives the cell's counts of the five neighbourhood classes before and after the
-//     move and adds the difference to the row table (packed 16-bit shared-memory atomics) -- independent of
-//     the lattice size.
+//   * site search inside the chosen row: one lane per anchor word builds the six MoveDivacancy direction masks
+//     of its word from the plane words of rows a-1 .. a+1 (one round of independent loads), per-direction
+//     totals come from three packed warp reductions, one warp scan finds the word, a popcount bisection the bit;
+//   * refresh: only tasks (row, word, direction | trefoil) within 1 row (trefoils: the touched rows and 2
+//     above) and 2 columns of the touched nodes can change; one lane per task re-derives its counts before and
+//     after the move and adds the difference to the row table (packed 16-bit shared-memory atomics) --
+//     independent of the lattice size.
 // Pack / unpack (status bytes <-> planes) and the initial row table are separate grid-wide kernels, run
 // only when the lattice was replaced; planes and table persist between launches.
 #pragma once
@@ -20,64 +30,58 @@ namespace kmc {
 
 struct WideParams {
     ReplicaParams base;
-    u64 *planes;                     // [R][N_TYPES][d0][W]
+    u64 *planes;                     // [R][N_TYPES][d0][We]
     uint16_t *hier;                  // [R][NC][d0p] row counts, persists between launches
-    int W, d0p;
+    int Wa, d0p;
 };
 
+__host__ __device__ inline int wide_anchor_words(int d1) { return (d1 + 63) >> 6; }
+__host__ __device__ inline int wide_row_words(int d1) { return wide_anchor_words(d1) + 1; }
 __host__ __device__ inline size_t wide_warp_bytes(int d0) {
     const size_t d0p = ((size_t)d0 + 1) & ~(size_t)1;
     return ((NC * d0p * 2 + 15) & ~(size_t)15) + NC * 32 * sizeof(uint32_t);      // row table + 32 block sums per class
 }
 
 struct WGeom {
-    const u64 *P; int d0, W;
-    __device__ __forceinline__ u64 word(int pl, int a, int w) const { return P[((size_t)pl * d0 + a) * W + w]; }
+    const u64 *P; int d0, d1, Wa, We;
+    __device__ __forceinline__ const u64 *rowp(int pl, int a) const { return P + ((size_t)pl * d0 + a) * We; }
+    // anchor columns of word w that exist (all ones except in a ragged last word)
+    __device__ __forceinline__ u64 valid(int w) const {
+        const int left = d1 - 64 * w;
+        return left >= 64 ? ~0ull : ((1ull << left) - 1ull);
+    }
 };
+// the 64 columns 64w + db .. 64w + db + 63 of a plane row (halo layout), |db| <= 2
+__device__ __forceinline__ u64 window(u64 x0, u64 x1, int db) {
+    const int o = db + 2;
+    return o ? (x0 >> o) | (x1 << (64 - o)) : x0;
+}
+__device__ __forceinline__ u64 window_at(const u64 *rowp, int w, int db) { return window(rowp[w], rowp[w + 1], db); }
 
-// plane words of rows a-1, a, a+1 (Z and D) and a+2 (D), words w-1, w, w+1 (periodic)
-struct Nbhd { u64 z[3][3], d[4][3]; };
+// words w, w + 1 of planes Z and D in rows a-1, a, a+1 and of plane D in row a+2
+struct Nbhd { u64 z[3][2], d[4][2]; u64 valid; };
 template <bool WITH_ROW2 = true>
 __device__ __forceinline__ void load_nbhd(const WGeom &g, int a, int w, Nbhd &n) {
-    const int wm = w == 0 ? g.W - 1 : w - 1, wp = w + 1 == g.W ? 0 : w + 1;
-    const int ws[3] = {wm, w, wp};
 #pragma unroll
     for (int r = 0; r < (WITH_ROW2 ? 4 : 3); r++) {
         const int ar = wrap1(wrap1(a + r - 1, g.d0), g.d0);
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            n.d[r][c] = g.word(T_D, ar, ws[c]);
-            if (r < 3) n.z[r][c] = g.word(T_Z, ar, ws[c]);
-        }
+        const u64 *dp = g.rowp(T_D, ar);
+        n.d[r][0] = dp[w]; n.d[r][1] = dp[w + 1];
+        if (r < 3) { const u64 *zp = g.rowp(T_Z, ar); n.z[r][0] = zp[w]; n.z[r][1] = zp[w + 1]; }
     }
-}
-// word whose bit i is column 64*w + i + db of a row given as its words (w-1, w, w+1); |db| <= 2
-__device__ __forceinline__ u64 shifted(const u64 x[3], int db) {
-    if (db == 0) return x[1];
-    if (db > 0) return (x[1] >> db) | (x[2] << (64 - db));
-    return (x[1] << -db) | (x[0] >> (64 + db));
+    n.valid = g.valid(w);
 }
 // MoveDivacancy direction k of the cell: present / near / far masks
 __device__ __forceinline__ void cell_dir_masks(const Nbhd &n, int k, u64 &present, u64 &near, u64 &far) {
-    present = n.d[1][1] & shifted(n.z[nib(NBR_DA, k) + 1], nib(NBR_DB, k));
-    near = shifted(n.d[nib(NEAR_DA, k) + 1], nib(NEAR_DB, k));
-    far = shifted(n.d[nib(FAR_DA, k) + 1], nib(FAR_DB, k));
-}
-// the same with a run-time direction (keeps the neighbourhood in registers)
-__device__ __forceinline__ void cell_dir_masks_dyn(const Nbhd &n, int k, u64 &present, u64 &near, u64 &far) {
-    switch (k) {
-        case 0: cell_dir_masks(n, 0, present, near, far); break;
-        case 1: cell_dir_masks(n, 1, present, near, far); break;
-        case 2: cell_dir_masks(n, 2, present, near, far); break;
-        case 3: cell_dir_masks(n, 3, present, near, far); break;
-        case 4: cell_dir_masks(n, 4, present, near, far); break;
-        default: cell_dir_masks(n, 5, present, near, far); break;
-    }
+    const int rn = nib(NBR_DA, k) + 1, re = nib(NEAR_DA, k) + 1, rf = nib(FAR_DA, k) + 1;
+    present = window(n.d[1][0], n.d[1][1], 0) & n.valid & window(n.z[rn][0], n.z[rn][1], nib(NBR_DB, k));
+    near = window(n.d[re][0], n.d[re][1], nib(NEAR_DB, k));
+    far = window(n.d[rf][0], n.d[rf][1], nib(FAR_DB, k));
 }
 __device__ __forceinline__ void cell_trefoil_masks(const Nbhd &n, u64 &up, u64 &dn) {
-    const u64 both = n.d[1][1] & n.d[3][1];
-    up = both & shifted(n.d[1], 2);
-    dn = both & shifted(n.d[3], -2);
+    const u64 both = window(n.d[1][0], n.d[1][1], 0) & n.valid & window(n.d[3][0], n.d[3][1], 0);
+    up = both & window(n.d[1][0], n.d[1][1], 2);
+    dn = both & window(n.d[3][0], n.d[3][1], -2);
 }
 // counts of classes 2..5 (16-bit pairs) and 6 of the sites of one cell
 __device__ __forceinline__ void cell_counts(const Nbhd &n, uint32_t &k01, uint32_t &k23, uint32_t &tre) {
@@ -109,94 +113,85 @@ __device__ __forceinline__ int nth_bit64(u64 m, uint32_t r) {
 }
 
 // ---- grid-wide helpers ----------------------------------------------------------------------------------
-// status bytes -> planes: one thread per (replica, row, word)
+// status bytes -> planes: one thread per (replica, row, stored word)
 __global__ void kmc_wide_pack_kernel(const uint8_t *status, u64 *planes, int R, int d0, int d1)
 {
-    const int W = d1 >> 6;
+    const int We = wide_row_words(d1);
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)R * d0 * W) return;
-    const int w = (int)(g % W);
-    const int a = (int)((g / W) % d0);
-    const long long rep = g / ((long long)W * d0);
-    const uint4 *src = reinterpret_cast<const uint4 *>(status + (rep * d0 + a) * (long long)d1 + 64 * w);
+    if (g >= (long long)R * d0 * We) return;
+    const int w = (int)(g % We);
+    const int a = (int)((g / We) % d0);
+    const long long rep = g / ((long long)We * d0);
+    const uint8_t *src = status + (rep * d0 + a) * (long long)d1;
     u64 out[N_TYPES] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 64; i++) {
+        const int q = 64 * w + i;
+        if (q >= d1 + 4) break;
+        int c = q - 2;
+        c = c < 0 ? c + d1 : (c >= d1 ? c - d1 : c);
+        const int pl = status_plane(src[c] & 0xF);
 #pragma unroll
-    for (int q4 = 0; q4 < 4; q4++) {
-        const uint4 v = src[q4];
-        const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int pl = status_plane((wds[j] >> (8 * i)) & 0xF);
-                const int bit = 16 * q4 + 4 * j + i;
-#pragma unroll
-                for (int q = 0; q < N_TYPES; q++) out[q] |= (u64)(pl == q) << bit;
-            }
+        for (int t = 0; t < N_TYPES; t++) out[t] |= (u64)(pl == t) << i;
     }
 #pragma unroll
-    for (int q = 0; q < N_TYPES; q++) planes[((rep * N_TYPES + q) * d0 + a) * W + w] = out[q];
+    for (int t = 0; t < N_TYPES; t++) planes[((rep * N_TYPES + t) * d0 + a) * We + w] = out[t];
 }
 
-// planes -> status bytes: one thread per (replica, row, word); trefoil members are recognised from the
+// planes -> status bytes: one thread per (replica, row, anchor word); trefoil members are recognised from the
 // anchor planes of the rows / columns they sit relative to
 __global__ void kmc_wide_unpack_kernel(const u64 *planes, uint8_t *status, int R, int d0, int d1)
 {
-    const int W = d1 >> 6;
+    const int Wa = wide_anchor_words(d1), We = Wa + 1;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (long long)R * d0 * W) return;
-    const int w = (int)(g % W);
-    const int a = (int)((g / W) % d0);
-    const long long rep = g / ((long long)W * d0);
-    WGeom G{planes + rep * N_TYPES * d0 * W, d0, W};
-    const int wm = w == 0 ? W - 1 : w - 1, wp = w + 1 == W ? 0 : w + 1;
+    if (g >= (long long)R * d0 * Wa) return;
+    const int w = (int)(g % Wa);
+    const int a = (int)((g / Wa) % d0);
+    const long long rep = g / ((long long)Wa * d0);
+    WGeom G{planes + rep * N_TYPES * d0 * We, d0, d1, Wa, We};
     const int am2 = wrap1(a - 2, d0);
-    const u64 z = G.word(T_Z, a, w), dv = G.word(T_D, a, w), m1 = G.word(T_M1, a, w), m2 = G.word(T_M2, a, w);
-    const u64 a4 = G.word(T_A4, a, w), a7 = G.word(T_A7, a, w);
+    const u64 z = window_at(G.rowp(T_Z, a), w, 0), dv = window_at(G.rowp(T_D, a), w, 0);
+    const u64 m1 = window_at(G.rowp(T_M1, a), w, 0), m2 = window_at(G.rowp(T_M2, a), w, 0);
+    const u64 a4 = window_at(G.rowp(T_A4, a), w, 0), a7 = window_at(G.rowp(T_A7, a), w, 0);
     // members: Up anchor q=(x,y): (x+2,y) role 1 -> code 5, (x,y+2) role 2 -> code 6;
     //          Down anchor:        (x+2,y) role 1 -> code 8, (x+2,y-2) role 2 -> code 9
-    const u64 c5 = G.word(T_A4, am2, w);
-    const u64 x4[3] = {G.word(T_A4, a, wm), a4, G.word(T_A4, a, wp)};
-    const u64 c6 = shifted(x4, -2);                                      // anchor two columns to the left
-    const u64 c8 = G.word(T_A7, am2, w);
-    const u64 x7[3] = {G.word(T_A7, am2, wm), c8, G.word(T_A7, am2, wp)};
-    const u64 c9 = shifted(x7, 2);                                       // anchor at (x-2, y+2)
-    uint4 *dst = reinterpret_cast<uint4 *>(status + (rep * d0 + a) * (long long)d1 + 64 * w);
+    const u64 c5 = window_at(G.rowp(T_A4, am2), w, 0);
+    const u64 c6 = window_at(G.rowp(T_A4, a), w, -2);                    // anchor two columns to the left
+    const u64 c8 = window_at(G.rowp(T_A7, am2), w, 0);
+    uint8_t *dst = status + (rep * d0 + a) * (long long)d1 + 64 * w;
+    const int ncols = min(64, d1 - 64 * w);
+    const bool words = (d1 & 3) == 0;                                     // row starts are 4-byte aligned
+    for (int b4 = 0; b4 < 16; b4++) {
+        uint32_t word = 0;
 #pragma unroll
-    for (int q4 = 0; q4 < 4; q4++) {
-        uint32_t o[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int b = 16 * q4 + 4 * j + i;
-                const uint32_t s = ((z >> b) & 1) ? 0u : ((dv >> b) & 1) ? 3u : ((m1 >> b) & 1) ? 1u : ((m2 >> b) & 1) ? 2u
-                                 : ((a4 >> b) & 1) ? 4u : ((a7 >> b) & 1) ? 7u : ((c5 >> b) & 1) ? 5u
-                                 : ((c6 >> b) & 1) ? 6u : ((c8 >> b) & 1) ? 8u : 9u;
-                word |= s << (8 * i);
-            }
-            o[j] = word;
+        for (int i = 0; i < 4; i++) {
+            const int b = 4 * b4 + i;
+            const uint32_t s = ((z >> b) & 1) ? 0u : ((dv >> b) & 1) ? 3u : ((m1 >> b) & 1) ? 1u : ((m2 >> b) & 1) ? 2u
+                             : ((a4 >> b) & 1) ? 4u : ((a7 >> b) & 1) ? 7u : ((c5 >> b) & 1) ? 5u
+                             : ((c6 >> b) & 1) ? 6u : ((c8 >> b) & 1) ? 8u : 9u;
+            word |= s << (8 * i);
         }
-        dst[q4] = make_uint4(o[0], o[1], o[2], o[3]);
+        if (words && 4 * b4 + 4 <= ncols) *reinterpret_cast<uint32_t *>(dst + 4 * b4) = word;
+        else
+            for (int i = 0; i < 4; i++)
+                if (4 * b4 + i < ncols) dst[4 * b4 + i] = (uint8_t)(word >> (8 * i));
     }
-    (void)c9;
 }
 
 // row table from the planes: one thread per (replica, row)
 __global__ void kmc_wide_hier_kernel(const u64 *planes, uint16_t *hier, int R, int d0, int d1, int d0p)
 {
-    const int W = d1 >> 6;
+    const int Wa = wide_anchor_words(d1), We = Wa + 1;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (long long)R * d0) return;
     const int a = (int)(g % d0);
     const long long rep = g / d0;
-    WGeom G{planes + rep * N_TYPES * d0 * W, d0, W};
+    WGeom G{planes + rep * N_TYPES * d0 * We, d0, d1, Wa, We};
     uint32_t pz = 0, pd = 0, pm = 0, pa = 0, k01 = 0, k23 = 0, tre = 0;
-    for (int w = 0; w < W; w++) {
-        pz += __popcll(G.word(T_Z, a, w)); pd += __popcll(G.word(T_D, a, w));
-        pm += __popcll(G.word(T_M1, a, w) | G.word(T_M2, a, w));
-        pa += __popcll(G.word(T_A4, a, w) | G.word(T_A7, a, w));
+    for (int w = 0; w < Wa; w++) {
+        const u64 v = G.valid(w);
+        pz += __popcll(window_at(G.rowp(T_Z, a), w, 0) & v); pd += __popcll(window_at(G.rowp(T_D, a), w, 0) & v);
+        pm += __popcll((window_at(G.rowp(T_M1, a), w, 0) | window_at(G.rowp(T_M2, a), w, 0)) & v);
+        pa += __popcll((window_at(G.rowp(T_A4, a), w, 0) | window_at(G.rowp(T_A7, a), w, 0)) & v);
         Nbhd n;
         load_nbhd(G, a, w, n);
         uint32_t c01, c23, ct;
@@ -236,27 +231,23 @@ __device__ __forceinline__ uint32_t task_desc(int k) {
                (operand_desc(T_D, nib(FAR_DA, k), nib(FAR_DB, k)) << 14);
     return operand_desc(T_D, 2, 0) | (operand_desc(T_D, 0, 2) << 7) | (operand_desc(T_D, 2, -2) << 14);
 }
-// the operand's word for anchor word w of anchor row a: one 64-bit load, one 32-bit load of the half word that
-// shifts in from the neighbouring word, two funnel shifts
-__device__ __forceinline__ u64 operand_word(const u64 *P, int d0, int W, int a, int w, uint32_t od) {
-    const int pl = (int)(od & 1u), da = (int)((od >> 1) & 7u) - 2, db = (int)((od >> 4) & 7u) - 2;
+// the operand's window for anchor word w of anchor row a: two 64-bit loads and a funnel shift by db + 2
+__device__ __forceinline__ u64 operand_word(const u64 *P, int d0, int We, int a, int w, uint32_t od) {
+    const int pl = (int)(od & 1u), da = (int)((od >> 1) & 7u) - 2, o = (int)((od >> 4) & 7u);
     int ar = a + da;
     ar = ar < 0 ? ar + d0 : (ar >= d0 ? ar - d0 : ar);
-    const uint32_t base = (uint32_t)(pl * d0 + ar) * (uint32_t)W;
-    const uint2 x1 = *reinterpret_cast<const uint2 *>(P + base + w);
-    const int wn = db < 0 ? (w == 0 ? W - 1 : w - 1) : (w + 1 == W ? 0 : w + 1);
-    const uint32_t nbh = reinterpret_cast<const uint32_t *>(P + base + wn)[db < 0 ? 1 : 0];
-    const uint32_t h0 = db < 0 ? nbh : x1.x, h1 = db < 0 ? x1.x : x1.y, h2 = db < 0 ? x1.y : nbh;
-    const uint32_t sh = (uint32_t)(db < 0 ? 32 + db : db);
-    return (u64)__funnelshift_r(h0, h1, sh) | ((u64)__funnelshift_r(h1, h2, sh) << 32);
+    const u64 *rp = P + (uint32_t)(pl * d0 + ar) * (uint32_t)We + w;
+    const u64 x0 = rp[0], x1 = rp[1];
+    return (x0 >> o) | ((x1 << 1) << (63 - o));            // o in [0, 4]: no shift by 64
 }
 // packed counts of a task: classes (2,3) in c01, (4,5) in c23 for k < 6; class 6 in c45 for k == 6
-__device__ __forceinline__ void task_counts(const u64 *P, int d0, int W, int a, int w, int k, uint32_t desc,
+__device__ __forceinline__ void task_counts(const u64 *P, int d0, int We, int a, int w, int k, uint32_t desc, u64 valid,
                                             uint32_t &c01, uint32_t &c23, uint32_t &c45) {
-    const u64 D0 = P[(uint32_t)(T_D * d0 + a) * (uint32_t)W + w];
-    const u64 A = operand_word(P, d0, W, a, w, desc & 0x7Fu);
-    const u64 Bv = operand_word(P, d0, W, a, w, (desc >> 7) & 0x7Fu);
-    const u64 C = operand_word(P, d0, W, a, w, (desc >> 14) & 0x7Fu);
+    const u64 *dp = P + (uint32_t)(T_D * d0 + a) * (uint32_t)We + w;
+    const u64 D0 = ((dp[0] >> 2) | (dp[1] << 62)) & valid;
+    const u64 A = operand_word(P, d0, We, a, w, desc & 0x7Fu);
+    const u64 Bv = operand_word(P, d0, We, a, w, (desc >> 7) & 0x7Fu);
+    const u64 C = operand_word(P, d0, We, a, w, (desc >> 14) & 0x7Fu);
     const u64 first = D0 & A;
     c01 = 0; c23 = 0; c45 = 0;
     if (k < 6) kind_counts(first, Bv, C, c01, c23);
@@ -272,7 +263,7 @@ __device__ __forceinline__ void reduce_packed_diff(uint32_t x, uint32_t y, int &
 __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WideParams wp)
 {
     const ReplicaParams &p = wp.base;
-    const int d0 = p.d0, d1 = p.d1, W = wp.W, d0p = wp.d0p;
+    const int d0 = p.d0, d1 = p.d1, Wa = wp.Wa, We = wp.Wa + 1, d0p = wp.d0p;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rep = blockIdx.x * (blockDim.x >> 5) + warp;
     if (rep >= p.n_replicas) return;
@@ -281,8 +272,8 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * wide_warp_bytes(d0));
     uint32_t *rc32 = reinterpret_cast<uint32_t *>(rc16);
     uint32_t *bs = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(rc16) + ((NC * (size_t)d0p * 2 + 15) & ~(size_t)15));
-    u64 *P = wp.planes + (size_t)rep * N_TYPES * d0 * W;
-    WGeom G{P, d0, W};
+    u64 *P = wp.planes + (size_t)rep * N_TYPES * d0 * We;
+    WGeom G{P, d0, d1, Wa, We};
     uint16_t *ghier = wp.hier + (size_t)rep * NC * d0p;
     for (int i = lane; i < (NC * d0p) / 2; i += 32) rc32[i] = reinterpret_cast<const uint32_t *>(ghier)[i];
     __syncwarp();
@@ -383,19 +374,19 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         }
         // the refresh below reads Z and D of rows row-3 .. row+3: start those lines moving now, under the site search
         {
-            const int lines = (W * 8 + 127) >> 7;              // 128-byte lines per plane row (<= 2)
+            const int lines = (We * 8 + 127) >> 7;             // 128-byte lines per plane row (<= 3)
             const int j = lane >> 2, pl = (lane >> 1) & 1, li = lane & 1;
             if (j < 7 && li < lines) {
                 const int a = wrap1(wrap1(row - 3 + j, d0), d0);
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)pl * d0 + a) * W + li * 16));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)pl * d0 + a) * We + min(li * 16, We - 1)));
             }
         }
-        // ---- slot and site inside the row: one lane per word (W <= 32), slots in class order ------------------
+        // ---- slot and site inside the row: one lane per anchor word (Wa <= 32), slots in class order ---------
         int col, slot, s0;
         {
             u64 m[6] = {0, 0, 0, 0, 0, 0};                 // this lane's word: mask of the class per slot
             const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
-            if (lane < W) {
+            if (lane < Wa) {
                 if (group == 1) {
                     Nbhd nb;
                     load_nbhd<false>(G, row, lane, nb);
@@ -406,12 +397,11 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
                         m[k] = kind_select(pr, ne, fa, csel - C_MOVE_DIV);
                     }
                 } else if (group == 2) {
-                    const int a2 = wrap1(row + 2, d0), wm = lane == 0 ? W - 1 : lane - 1, wq = lane + 1 == W ? 0 : lane + 1;
-                    const u64 da[3] = {0, G.word(T_D, row, lane), G.word(T_D, row, wq)};
-                    const u64 db[3] = {G.word(T_D, a2, wm), G.word(T_D, a2, lane), 0};
-                    const u64 both = da[1] & db[1];
-                    m[0] = both & shifted(da, 2);
-                    m[1] = both & shifted(db, -2);
+                    const u64 *ra = G.rowp(T_D, row), *rb2 = G.rowp(T_D, wrap1(row + 2, d0));
+                    const u64 a0 = ra[lane], a1 = ra[lane + 1], b0 = rb2[lane], b1 = rb2[lane + 1];
+                    const u64 both = window(a0, a1, 0) & window(b0, b1, 0) & G.valid(lane);
+                    m[0] = both & window(a0, a1, 2);
+                    m[1] = both & window(b0, b1, -2);
                 } else {
                     int pa = T_M1, pb = -1;
                     switch (csel) {
@@ -424,9 +414,10 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
                         case C_FMONO_FROM_EMPTY: pa = T_D; pb = T_D; break;
                         default: break;
                     }
-                    m[0] = G.word(pa, row, lane);
-                    if (csel == C_FLIP) m[0] |= G.word(T_M2, row, lane);
-                    if (pb >= 0) m[1] = G.word(pb, row, lane);
+                    const u64 v = G.valid(lane);
+                    m[0] = window_at(G.rowp(pa, row), lane, 0) & v;
+                    if (csel == C_FLIP) m[0] |= window_at(G.rowp(T_M2, row), lane, 0) & v;
+                    if (pb >= 0) m[1] = window_at(G.rowp(pb, row), lane, 0) & v;
                 }
             }
             const uint32_t c01 = __popcll(m[0]) | (__popcll(m[1]) << 16);
@@ -459,7 +450,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
                 case C_DESTROY_TREF: s0 = j ? 7 : 4; break;
                 case C_CMONO_MAKE_EMPTY: s0 = j ? 1 : 2; break;
                 case C_FMONO_MAKE_DOUBLE: s0 = j ? 2 : 1; break;
-                default: s0 = ((G.word(T_M1, row, L) >> bit) & 1ull) ? 1 : 2; break;
+                default: s0 = ((window_at(G.rowp(T_M1, row), L, 0) >> bit) & 1ull) ? 1 : 2; break;
             }
         }
         const int site = row * d1 + col;
@@ -504,7 +495,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             mine[i] = i < na && lane < N_TYPES && (status_plane(os[i]) == lane || status_plane(ns[i]) == lane);
-            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6)));
+            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)lane * d0 + as[i]) * We + ((bcol[i] + 2) >> 6)));
         }
         // Refresh of the five neighbourhood classes.  Every dependency of a site is inside its ring of six
         // neighbours (rows +-1, columns +-1) or, for trefoils, at (+2, 0), (0, +2), (+2, -2).  So the tasks
@@ -516,12 +507,15 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (i < na) {
-                wmask |= 1ull << (wrap1(bcol[i] - 2, d1) >> 6);
-                wmask |= 1ull << (bcol[i] >> 6);
-                wmask |= 1ull << (wrap1(bcol[i] + 2, d1) >> 6);
+                // every column within 2 of the node (a ragged last word of one column can sit strictly between
+                // columns c and c + 2 across the wrap, so the end points alone do not bracket the words)
+#pragma unroll
+                for (int dc = -2; dc <= 2; dc++) wmask |= 1ull << (wrap1(bcol[i] + dc, d1) >> 6);
             }
         const int nw = __popcll(wmask);
+        // at most three words: two in the interior, three when the span wraps over a ragged last word
         const int wA = __ffsll((long long)wmask) - 1, wB = 63 - __clzll((long long)wmask);
+        const int wM = nw == 3 ? __ffsll((long long)(wmask & (wmask - 1))) - 1 : wA;
         // rows of the direction tasks: lo2 .. lo2 + n2 - 1 (relative to `row`); trefoil rows: g3 (nibbles, +3)
         int lo2, n2, n3;
         uint32_t g3;
@@ -533,31 +527,44 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         } else { lo2 = -1; n2 = 5; n3 = 3; g3 = 0x531u; }                            // {-2, 0, 2}
         if (n2 > d0) n2 = d0;
         const int ntask = (6 * n2 + n3) * nw;
-        uint32_t b01[3] = {0, 0, 0}, b23[3] = {0, 0, 0}, b45[3] = {0, 0, 0};
-        int ta[3] = {0, 0, 0};                                 // row | word << 16 | k << 24 of the lane's tasks
-        uint32_t td[3] = {0, 0, 0};
+        uint32_t b01[4] = {0, 0, 0, 0}, b23[4] = {0, 0, 0, 0}, b45[4] = {0, 0, 0, 0};
+        int ta[4] = {0, 0, 0, 0};                              // row | word << 16 | k << 24 of the lane's tasks
+        uint32_t td[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int it = 0; it < 3; it++) {
+        for (int it = 0; it < 4; it++) {
             const int tk = lane + 32 * it;
             if (32 * it < ntask) {                             // warp-uniform
-                const int u = nw == 2 ? tk >> 1 : tk;
-                const int wd = (nw == 2 && (tk & 1)) ? wB : wA;
+                const int u = nw == 1 ? tk : (nw == 2 ? tk >> 1 : (tk * 171) >> 9);      // tk / nw
+                const int iw = tk - u * nw;
+                const int wd = iw == 0 ? wA : (iw == nw - 1 ? wB : wM);
                 int k = 6, a;
                 if (u < 6 * n2) { const int j = (u * 43) >> 8; k = u - 6 * j; a = row + lo2 + j; }       // u / 6 for u < 48
                 else a = row + (int)((g3 >> (4 * ((u - 6 * n2) & 7))) & 0xF) - 3;
                 a = wrap1(wrap1(a, d0), d0);
                 ta[it] = a | (wd << 16) | (k << 24);
                 td[it] = __shfl_sync(FULL, my_desc, k);
-                if (tk < ntask) task_counts(P, d0, W, a, wd, k, td[it], b01[it], b23[it], b45[it]);
+                if (tk < ntask) task_counts(P, d0, We, a, wd, k, td[it], G.valid(wd), b01[it], b23[it], b45[it]);
             }
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 3; i++)
             if (mine[i]) {
-                u64 *wptr = P + ((size_t)lane * d0 + as[i]) * W + (bcol[i] >> 6);
-                const u64 bit = 1ull << (bcol[i] & 63);
-                *wptr = (*wptr & ~bit) | (status_plane(ns[i]) == lane ? bit : 0ull);
+                // the site's main position and, within two columns of a row end, its halo copy
+                u64 *rowp = P + ((size_t)lane * d0 + as[i]) * We;
+                const bool set = status_plane(ns[i]) == lane;
+                const int q0 = bcol[i] + 2;
+                const int q1 = bcol[i] < 2 ? bcol[i] + d1 + 2 : (bcol[i] >= d1 - 2 ? bcol[i] + 2 - d1 : -1);
+                {
+                    u64 *wptr = rowp + (q0 >> 6);
+                    const u64 bit = 1ull << (q0 & 63);
+                    *wptr = (*wptr & ~bit) | (set ? bit : 0ull);
+                }
+                if (q1 >= 0) {
+                    u64 *wptr = rowp + (q1 >> 6);
+                    const u64 bit = 1ull << (q1 & 63);
+                    *wptr = (*wptr & ~bit) | (set ? bit : 0ull);
+                }
             }
         // own-status classes (owner lanes, shared-memory row table)
         if (my_g1) {
@@ -580,12 +587,12 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         __syncwarp();
         uint32_t x01 = 0, y01 = 0, x23 = 0, y23 = 0, x45 = 0, y45 = 0;       // after / before, summed over the lane's tasks
 #pragma unroll
-        for (int it = 0; it < 3; it++) {
+        for (int it = 0; it < 4; it++) {
             const int tk = lane + 32 * it;
             if (tk < ntask) {
                 const int a = ta[it] & 0xFFFF, wd = (ta[it] >> 16) & 0xFF, k = ta[it] >> 24;
                 uint32_t a01, a23, a45;
-                task_counts(P, d0, W, a, wd, k, td[it], a01, a23, a45);
+                task_counts(P, d0, We, a, wd, k, td[it], G.valid(wd), a01, a23, a45);
                 const int dd[5] = {(int)(a01 & 0xFFFF) - (int)(b01[it] & 0xFFFF), (int)(a01 >> 16) - (int)(b01[it] >> 16),
                                    (int)(a23 & 0xFFFF) - (int)(b23[it] & 0xFFFF), (int)(a23 >> 16) - (int)(b23[it] >> 16),
                                    (int)a45 - (int)b45[it]};

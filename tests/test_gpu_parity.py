@@ -147,7 +147,8 @@ def test_large_lattice_incremental_1024():
     eng.close()
 
 
-@pytest.mark.parametrize("dim", [(12, 128), (40, 192), (7, 320), (130, 128), (64, 2048), (5, 128), (1100, 128)])
+@pytest.mark.parametrize("dim", [(12, 128), (40, 192), (7, 320), (130, 128), (64, 2048), (5, 128), (1100, 128),
+                                 (12, 130), (40, 200), (7, 70), (9, 65), (200, 200), (20, 2044), (5, 67), (33, 127)])
 def test_wide_bitplane_kernel_matches_oracle(dim):
     """Variant 5: bit planes of rows wider than one word kept in HBM, row table in shared memory."""
     nrep, nsteps, seed = 3, 5000, 4711
