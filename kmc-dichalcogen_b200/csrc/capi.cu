@@ -596,8 +596,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
                  h->d0, h->d1, wbytes, h->max_smem_optin);
         return fail(KMC_ERR_ARG, b);
     }
-    int W = h->warps_per_block > 0 ? h->warps_per_block : 8;
+    // warps (replicas) per block: spread small batches over the SMs, at most 8
+    int W = h->warps_per_block > 0 ? h->warps_per_block : (h->R + 147) / 148;
     if (W > 8) W = 8;
+    if (W < 1) W = 1;
     while (W > 1 && W * wbytes > (size_t)h->max_smem_optin) W--;
     const size_t smem = W * wbytes;
     const size_t rs = record_size(log_mode);
@@ -625,7 +627,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         KERNEL<<<blocks, W * 32, smem, h->stream>>>(p);                                                   \
     } while (0)
     if (bitplanes) {
-        if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>));
+        // small batches cannot use the occupancy the 64-register build is compiled for: latency build (96 registers)
+        const bool lat = getenv("KMC_BP_LAT") ? atoi(getenv("KMC_BP_LAT")) != 0 : h->R <= 16 * 148;
+        if (h->d0 == 64 && h->d1 == 64) { if (lat) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, true>)); else KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>)); }
         else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0>));
     } else if (global_state) {
         KMC_LAUNCH((kmc_replica_kernel<0, 0, true>));

@@ -202,8 +202,10 @@ __device__ __forceinline__ int nth_bit_small(uint32_t m, uint32_t n) {
     return __ffs(m) - 1;
 }
 
-template <int TD0, int TD1>
-__global__ void __launch_bounds__(256, 4) kmc_replica_bp_kernel(const ReplicaParams p)
+// LAT = true: the latency build for small batches and single trajectories -- same code, but the register
+// allocator is not held to 64 registers for occupancy that such launches cannot use
+template <int TD0, int TD1, bool LAT = false>
+__global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
