@@ -457,6 +457,13 @@ def main():
             "replica_kernel": {"bound": "sm-issue / shared-memory (lattice resident in smem, ~0 HBM bytes per event)",
                                "events_per_s_per_sm": per_sm, "sm_cycles_per_event": sm_clock / per_sm,
                                "hbm_bytes_per_event_algorithmic": 2.0 * DIM[0] * DIM[1] / E,
+                               # instruction-issue roofline: warp-instructions per event (ncu, recorded) x measured
+                               # events/s against 4 issue slots per SM per cycle at the sampled SM clock
+                               "issue_roofline": (lambda c: None if not c else {
+                                   "achieved_warp_inst_per_s": c["warp_instructions_per_event"] * value / world,
+                                   "peak_warp_inst_per_s": 148 * 4 * sm_clock,
+                                   "frac": c["warp_instructions_per_event"] * value / world / (148 * 4 * sm_clock)})(
+                                       recorded_replica_counters()),
                                "ncu": recorded_replica_counters()},
             "cpu_baseline": cpu,
             "other_configs": other,
