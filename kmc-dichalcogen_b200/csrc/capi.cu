@@ -711,10 +711,15 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
     p.nsteps = nsteps;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
     p.clock = h->clock_on ? h->d_clock : nullptr;
+    // rows row-1 .. row+2 of the chosen row are staged in shared memory when they fit
+    const size_t stage_bytes = 4 * (size_t)h->d1 <= (size_t)h->max_smem_optin - 4096 ? 4 * (size_t)h->d1 : 0;
+    p.stage = stage_bytes ? 1 : 0;
+    if (stage_bytes > 40 * 1024)
+        CU(cudaFuncSetAttribute(kmc_noinc_select_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes));
     for (long long t = 0; t < nsteps; t++) {
         rc = sweep_launch(h, false); if (rc) return rc;        // sim.py:114-115: initialize() every step
         p.rowcnt = h->d_rowcnt; p.counts = h->d_counts; p.t = t;
-        kmc_noinc_select_apply_kernel<<<h->R, 256, 0, h->stream>>>(p);
+        kmc_noinc_select_apply_kernel<<<h->R, 256, stage_bytes, h->stream>>>(p);
         CU(cudaGetLastError());
         h->launches += 1;
     }

@@ -25,6 +25,7 @@ struct NoincParams {
     unsigned long long *steps_done, *hist, *ties, *hops;
     uint32_t *flags;
     double *clock;                       // [R] or nullptr
+    int stage;                           // 1: stage rows row-1 .. row+2 of the chosen row in shared memory (4 * d1 bytes)
 };
 
 // exclusive prefix of `v` over the 256 threads of the block (wsum: 8 words of shared scratch)
@@ -127,11 +128,35 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
     }
     __syncthreads();
     const int row = s_row;
+    // The two passes below evaluate every site of the chosen row with its neighbours.  Straight from the lattice
+    // that is a chain of dependent L2 round trips per site; staging the four rows they can touch (row-1 .. row+2)
+    // in shared memory turns it into one coalesced round of loads.  The staged rows form a 4-row lattice in which
+    // the chosen row is row 1 and none of the offsets used (-1 .. +2) wraps.
+    extern __shared__ uint4 s_stage[];
+    const uint8_t *view = st;
+    int vrow = row, vd0 = d0;
+    if (p.stage) {
+        uint8_t *dst = reinterpret_cast<uint8_t *>(s_stage);
+        for (int j = 0; j < 4; j++) {
+            int a = row - 1 + j;
+            a = a < 0 ? a + d0 : (a >= d0 ? a - d0 : a);
+            const uint8_t *src = st + (size_t)a * d1;
+            if ((d1 & 15) == 0) {
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst + (size_t)j * d1);
+                for (int i = tid; i < (d1 >> 4); i += 256) d4[i] = s4[i];
+            } else {
+                for (int i = tid; i < d1; i += 256) dst[(size_t)j * d1 + i] = src[i];
+            }
+        }
+        __syncthreads();
+        view = dst; vrow = 1; vd0 = 4;
+    }
     // ---- slot: per-slot totals of the class in this row (row, slot, column order) ------------------------
     {
         uint32_t a01 = 0, a23 = 0, a45 = 0;
         for (int b = tid; b < d1; b += 256) {
-            const uint32_t m = site_slot_mask(st, row, b, d0, d1, csel);
+            const uint32_t m = site_slot_mask(view, vrow, b, vd0, d1, csel);
             a01 += (m & 1u) | ((m & 2u) << 15);
             a23 += ((m >> 2) & 1u) | ((m & 8u) << 13);
             a45 += ((m >> 4) & 1u) | ((m & 32u) << 11);
@@ -157,13 +182,13 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int kc = (d1 + 255) / 256;
         const int b0 = tid * kc, b1 = min(b0 + kc, d1);
         unsigned long long local = 0, total;
-        for (int b = b0; b < b1; b++) local += (site_slot_mask(st, row, b, d0, d1, csel) >> j) & 1u;
+        for (int b = b0; b < b1; b++) local += (site_slot_mask(view, vrow, b, vd0, d1, csel) >> j) & 1u;
         const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
         if ((unsigned long long)r >= excl && (unsigned long long)r < excl + local) {
             uint32_t q = r - (uint32_t)excl;
             int b = b0;
             for (; b < b1; b++) {
-                const uint32_t v = (site_slot_mask(st, row, b, d0, d1, csel) >> j) & 1u;
+                const uint32_t v = (site_slot_mask(view, vrow, b, vd0, d1, csel) >> j) & 1u;
                 if (v && q == 0) break;
                 q -= v;
             }
