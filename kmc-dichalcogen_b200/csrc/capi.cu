@@ -333,7 +333,8 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
             q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
             q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
             q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc;
-            kmc_sweep_roll_kernel<<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
+            if (with_slots) kmc_sweep_roll_kernel<true><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
+            else kmc_sweep_roll_kernel<false><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
             CU(cudaGetLastError());
             h->launches += 1;
             return KMC_OK;

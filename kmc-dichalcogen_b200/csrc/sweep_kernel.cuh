@@ -549,8 +549,8 @@ template <int I> __host__ __device__ __forceinline__ ZD ring_flags_n(const Chunk
     return r;
 }
 // MoveDivacancy direction K of nibble word j: two output words (sites 0-3, 4-7 of the word)
-template <int K> __host__ __device__ __forceinline__ void move_plane_n(const Chunk16N &k, int j, uint32_t &o0,
-                                                                         uint32_t &o1, NibAcc &acc) {
+template <int K, bool STORE = true>
+__host__ __device__ __forceinline__ void move_plane_n(const Chunk16N &k, int j, uint32_t &o0, uint32_t &o1, NibAcc &acc) {
     constexpr int I = (0x204315 >> (4 * K)) & 7;           // kring(K)
     constexpr int IN = (I & 1) ? (I + 5) % 6 : (I + 1) % 6, IF = (I & 1) ? (I + 1) % 6 : (I + 5) % 6;
     const uint32_t present = k.c[j + 1].div & ring_flags_n<I>(k, j).zero;
@@ -558,28 +558,33 @@ template <int K> __host__ __device__ __forceinline__ void move_plane_n(const Chu
     const uint32_t pn = present & near, pf = present & far;
     acc.pres += present; acc.pn += pn; acc.pf += pf; acc.pnf += pn & far;
     // selector nibble = present + 2*near + 4*far -> code 2 + near + 2*far, or 0xFF when absent
-    const uint32_t sel = far * 4u + (near * 2u + present);
-    o0 = prmt(0x03FF02FFu, 0x05FF04FFu, sel);
-    o1 = prmt(0x03FF02FFu, 0x05FF04FFu, sel >> 16);
+    if (STORE) {
+        const uint32_t sel = far * 4u + (near * 2u + present);
+        o0 = prmt(0x03FF02FFu, 0x05FF04FFu, sel);
+        o1 = prmt(0x03FF02FFu, 0x05FF04FFu, sel >> 16);
+    }
 }
 __host__ __device__ __forceinline__ uint32_t nib_sum(uint32_t x) {      // sum of the 8 nibbles
     return (((x & 0x0F0F0F0Fu) + ((x >> 4) & 0x0F0F0F0Fu)) * ONES) >> 24;
 }
 
 #ifdef __CUDACC__
-template <int K> __device__ __forceinline__ void emit_move_plane_n(const Chunk16N &k, uint4 *O, size_t cpl, NibAcc &acc) {
-    uint32_t a, b, c, d;
-    move_plane_n<K>(k, 0, a, b, acc);
-    move_plane_n<K>(k, 1, c, d, acc);
-    if (O) KMC_SLOT_STORE(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
+// STORE = false: the count-only sweep of the no-incremental path (no slot planes are built at all)
+template <int K, bool STORE> __device__ __forceinline__ void emit_move_plane_n(const Chunk16N &k, uint4 *O, size_t cpl, NibAcc &acc) {
+    uint32_t a = 0, b = 0, c = 0, d = 0;
+    move_plane_n<K, STORE>(k, 0, a, b, acc);
+    move_plane_n<K, STORE>(k, 1, c, d, acc);
+    if (STORE && O) KMC_SLOT_STORE(O + (size_t)(7 + K) * cpl, make_uint4(a, b, c, d));
 }
+template <bool STORE>
 __device__ __forceinline__ void emit_lut_plane(uint4 *O, size_t plane, size_t cpl, uint32_t lo, uint32_t hi,
                                                uint32_t s0, uint32_t s0h, uint32_t s1, uint32_t s1h) {
-    if (O) KMC_SLOT_STORE(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
+    if (STORE && O) KMC_SLOT_STORE(O + plane * cpl, make_uint4(prmt(lo, hi, s0), prmt(lo, hi, s0h), prmt(lo, hi, s1), prmt(lo, hi, s1h)));
 }
 
 // all 17 slot planes of one 16-site chunk (stored through O, stride cpl between planes) and the chunk's
 // 13 class counts as seven 16-bit pairs
+template <bool STORE = true>
 __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_t cpl, uint32_t pk[7])
 {
     // own-status planes: table lookup by status (8, 9 -> 5, 6: all of 5, 6, 8, 9 carry no own-status move)
@@ -589,15 +594,15 @@ __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_
         const uint32_t s0 = k.cn[0] - 3u * e3a, s1 = k.cn[1] - 3u * e3b;
         const uint32_t s0h = s0 >> 16, s1h = s1 >> 16;
         const uint32_t F = 0xFFFFFFFFu;
-        emit_lut_plane(O, 0, cpl, 0xFFFFFF00u, F, s0, s0h, s1, s1h);      // CreateDivacancy      s0 -> 0
-        emit_lut_plane(O, 1, cpl, 0x01FFFFFFu, F, s0, s0h, s1, s1h);      // FillDivacancy        s3 -> 1
-        emit_lut_plane(O, 2, cpl, 0xFF09FF08u, F, s0, s0h, s1, s1h);      // CreateMono layer 1   s0 -> 8, s2 -> 9
-        emit_lut_plane(O, 3, cpl, 0xFFFF0908u, F, s0, s0h, s1, s1h);      // CreateMono layer 2   s0 -> 8, s1 -> 9
-        emit_lut_plane(O, 4, cpl, 0x0BFF0AFFu, F, s0, s0h, s1, s1h);      // FillMono layer 1     s1 -> 10, s3 -> 11
-        emit_lut_plane(O, 5, cpl, 0x0B0AFFFFu, F, s0, s0h, s1, s1h);      // FillMono layer 2     s2 -> 10, s3 -> 11
-        emit_lut_plane(O, 6, cpl, 0xFF0C0CFFu, F, s0, s0h, s1, s1h);      // FlipMonovacancy      s1, s2 -> 12
-        emit_lut_plane(O, 15, cpl, F, 0xFFFFFF07u, s0, s0h, s1, s1h);     // DestroyTrefoil Up    s4 -> 7
-        emit_lut_plane(O, 16, cpl, F, 0x07FFFFFFu, s0, s0h, s1, s1h);     // DestroyTrefoil Down  s7 -> 7
+        emit_lut_plane<STORE>(O, 0, cpl, 0xFFFFFF00u, F, s0, s0h, s1, s1h);      // CreateDivacancy      s0 -> 0
+        emit_lut_plane<STORE>(O, 1, cpl, 0x01FFFFFFu, F, s0, s0h, s1, s1h);      // FillDivacancy        s3 -> 1
+        emit_lut_plane<STORE>(O, 2, cpl, 0xFF09FF08u, F, s0, s0h, s1, s1h);      // CreateMono layer 1   s0 -> 8, s2 -> 9
+        emit_lut_plane<STORE>(O, 3, cpl, 0xFFFF0908u, F, s0, s0h, s1, s1h);      // CreateMono layer 2   s0 -> 8, s1 -> 9
+        emit_lut_plane<STORE>(O, 4, cpl, 0x0BFF0AFFu, F, s0, s0h, s1, s1h);      // FillMono layer 1     s1 -> 10, s3 -> 11
+        emit_lut_plane<STORE>(O, 5, cpl, 0x0B0AFFFFu, F, s0, s0h, s1, s1h);      // FillMono layer 2     s2 -> 10, s3 -> 11
+        emit_lut_plane<STORE>(O, 6, cpl, 0xFF0C0CFFu, F, s0, s0h, s1, s1h);      // FlipMonovacancy      s1, s2 -> 12
+        emit_lut_plane<STORE>(O, 15, cpl, F, 0xFFFFFF07u, s0, s0h, s1, s1h);     // DestroyTrefoil Up    s4 -> 7
+        emit_lut_plane<STORE>(O, 16, cpl, F, 0x07FFFFFFu, s0, s0h, s1, s1h);     // DestroyTrefoil Down  s7 -> 7
         // counts of the own-status classes from single-bit flags
         uint32_t mono = 0, anch = 0;
 #pragma unroll
@@ -612,8 +617,8 @@ __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_
         n_div = __popc(k.c[1].div) + __popc(k.c[2].div);
     }
     NibAcc acc = {0, 0, 0, 0};
-    emit_move_plane_n<0>(k, O, cpl, acc); emit_move_plane_n<1>(k, O, cpl, acc); emit_move_plane_n<2>(k, O, cpl, acc);
-    emit_move_plane_n<3>(k, O, cpl, acc); emit_move_plane_n<4>(k, O, cpl, acc); emit_move_plane_n<5>(k, O, cpl, acc);
+    emit_move_plane_n<0, STORE>(k, O, cpl, acc); emit_move_plane_n<1, STORE>(k, O, cpl, acc); emit_move_plane_n<2, STORE>(k, O, cpl, acc);
+    emit_move_plane_n<3, STORE>(k, O, cpl, acc); emit_move_plane_n<4, STORE>(k, O, cpl, acc); emit_move_plane_n<5, STORE>(k, O, cpl, acc);
     uint32_t n_tref;
     {
         uint32_t u[2], d[2];
@@ -624,8 +629,8 @@ __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_
             d[j] = both & nshl(k.q[j], k.q[j + 1], 2);
         }
         n_tref = __popc(u[0]) + __popc(u[1]) + __popc(d[0]) + __popc(d[1]);
-        emit_lut_plane(O, 13, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, u[0], u[0] >> 16, u[1], u[1] >> 16);
-        emit_lut_plane(O, 14, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, d[0], d[0] >> 16, d[1], d[1] >> 16);
+        emit_lut_plane<STORE>(O, 13, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, u[0], u[0] >> 16, u[1], u[1] >> 16);
+        emit_lut_plane<STORE>(O, 14, cpl, 0xFFFF06FFu, 0xFFFFFFFFu, d[0], d[0] >> 16, d[1], d[1] >> 16);
     }
     // K2: this thread's 13 class counts as 16-bit pairs, pooled per row
     {
@@ -729,6 +734,7 @@ constexpr int ROLL_MAX_ROWS = 16;
 #ifndef KMC_ROLL_OCC
 #define KMC_ROLL_OCC 3
 #endif
+template <bool STORE>
 __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const SweepRollParams p)
 {
     __shared__ uint32_t part[ROLL_MAX_ROWS][8][8];       // [row step][warp][7 count pairs]
@@ -757,9 +763,9 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
         k.m[0] = rm.own0; k.m[1] = rm.own1; k.m[2] = rm.next;
         k.p[0] = rp.prev; k.p[1] = rp.own0; k.p[2] = rp.own1;
         k.q[0] = rq.prev.div; k.q[1] = rq.own0.div; k.q[2] = rq.own1.div;
-        uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + ((size_t)a * cpr + ci) : nullptr;
+        uint4 *O = (STORE && p.slots) ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + ((size_t)a * cpr + ci) : nullptr;
         uint32_t pk[7];
-        sweep_chunk_n(k, O, (size_t)cpl, pk);
+        sweep_chunk_n<STORE>(k, O, (size_t)cpl, pk);
 #pragma unroll
         for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
         if (lane < 7) {
