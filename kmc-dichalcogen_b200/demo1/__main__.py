@@ -154,6 +154,7 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
         eng.generate_state(gen["mode"], gen["params"], seed if state_seed is None else state_seed, replica0=lo)
     else:
         eng.upload_state(np.tile(init_state.status, (hi - lo, 1)))
+    eng.enable_clock(True)            # simulated time per replica: sum of 1 / total_rate (mean residence times)
     try:
         eng.run(nsteps, seed, replica0=lo, validate=True)
     except ValueError:
@@ -168,6 +169,7 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     d = eng.displacement()
     sq = parallel.reduce_histogram(np.array([int((d[:, 0] ** 2 + d[:, 0] * d[:, 1] + d[:, 1] ** 2).sum())],
                                             dtype=np.int64), device=dev)
+    time_sum = parallel.sum_over_ranks(float(eng.clock().sum()), device=dev)
     eng.close()
     if rank != 0:
         return
@@ -178,7 +180,10 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
            # divacancy hops per direction (neighbour order of state.py:443-459), summed over replicas, and the
            # mean squared net displacement of a replica's divacancy population in axial lattice units
            "divacancy_hops": [int(x) for x in hops],
-           "mean_squared_net_displacement": float(sq[0]) / replicas}
+           "mean_squared_net_displacement": float(sq[0]) / replicas,
+           # simulated time per replica, averaged (the reference draws no time step; its log carries total_rate
+           # for exactly this reconstruction, README.md:36-37): sum over events of 1 / total_rate
+           "mean_time": time_sum / replicas}
     json.dump(out, ofile, indent=2, sort_keys=True)
     ofile.write("\n")
 

@@ -68,6 +68,18 @@ def reduce_histogram(hist, device=None):
     return t.cpu().numpy()
 
 
+def sum_over_ranks(value, device=None):
+    """Sum of a Python float over all ranks."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.cpu().item())
+
+
 def max_over_ranks(value, device=None):
     """Max of a Python float over all ranks (timings are reported as the slowest rank's)."""
     import torch

@@ -149,6 +149,10 @@ def test_cli_replica_batch_statistics():
     out = json.loads(run_cli([cfg, "-T", "1500", "-d", "64,64", "-n", "500", "--seed", "3", "--state-seed", "4",
                               "--replicas", "64"]))
     assert out["events_done"] == 64 * 500 and sum(out["histogram"].values()) == 64 * 500
+    assert sum(out["divacancy_hops"]) == sum(v for k, v in out["histogram"].items() if k.startswith("MoveDivacancy"))
+    # simulated time = sum of 1 / total_rate: ~200 divacancies x ~5 free directions at 2.8e-8 .. 8e-8 per hop give a
+    # total rate of a few 1e-5, so a 500-event run lasts of the order of 1e7 time units
+    assert 1e6 < out["mean_time"] < 1e9 and out["mean_squared_net_displacement"] > 0
 
 
 def test_cli_independent_replica_states_are_generated_on_the_device():
