@@ -100,6 +100,7 @@ class KmcSim:
         self._engine = None
         self._buffer = None
         self._cursor = 0
+        self._decoded_for = None
         self.state = None
         self.initialize(initial_state)
 
@@ -154,11 +155,37 @@ class KmcSim:
                     raise
             else:
                 self._cursor = 0
-        rec = self._buffer[self._cursor]
-        if rec["cls"] == 0xFF:
+        if self._decoded_for is not self._buffer:
+            self._decode_buffer()
+        i = self._cursor
+        cls = self._dec_cls[i]
+        if cls == 0xFF:
             raise ValueError("Cannot choose from total weight of zero!")
         self._cursor += 1
-        return self._format(rec)
+        rule, kind = T.CLASSES[cls]
+        d = {
+            "rule": rule,
+            "move": T.move_info(self._dec_site[i], self._dec_slot[i], self.state.dim),
+            "kind": kind,
+            "rate": self._rates13[cls],
+            "total_rate": self._dec_total[i],           # reference sim.py:138
+        }
+        if self._zobrist is not None:
+            d["zobrist"] = self._zobrist.apply(d)       # reference sim.py:141-142
+        return d
+
+    def _decode_buffer(self):
+        """Per-launch decoding of the event records for perform_random_move: class / site / slot as Python ints
+        and the exactly rounded total rate (math.fsum of count * rate, sim.py:138) of every event, taken for the
+        whole chunk at once -- the same values `_format` computes record by record."""
+        import numpy as np
+        recs = self._buffer
+        order = list(self._order)
+        rates = np.array([self._rates13[c] for c in order], dtype=np.float64)
+        weights = (recs["counts"][:, order].astype(np.float64) * rates[None, :]).tolist()
+        self._dec_total = [math.fsum(w) for w in weights]
+        self._dec_cls, self._dec_site, self._dec_slot = recs["cls"].tolist(), recs["site"].tolist(), recs["slot"].tolist()
+        self._decoded_for = recs
 
     def _format(self, rec):
         rule, kind = T.CLASSES[int(rec["cls"])]

@@ -259,6 +259,9 @@ def test_bulk_json_writer_is_character_identical_to_the_per_event_path():
     slow = [json.dumps(sim._format(r), sort_keys=True) for r in recs]
     assert fast == slow
     assert sim.format_records_json(recs[:0]) == []
+    # perform_random_move decodes a whole launch at once: same dictionaries as the record-by-record formatter
+    sim._buffer, sim._cursor, sim._decoded_for = recs, 0, None
+    assert [sim.perform_random_move() for _ in range(len(recs))] == [sim._format(r) for r in recs]
 
 
 def test_product_log_format_replays_in_the_references_animate_consumer():
