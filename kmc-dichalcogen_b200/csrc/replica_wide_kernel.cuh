@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
 
         // ---- the move -----------------------------------------------------------------------------------
         MoveNodes mv;
-        int os1, os2, da2;
+        int os1, os2, da2, db1, db2;
         {
             const MoveEntry e = MOVE_TABLE[slot];
             mv.ns0 = (int)((((uint32_t)s0 | (e.w0 & 0xF)) & ((e.w0 >> 4) & 0xF)) ^ ((e.w0 >> 8) & 0xF));
@@ -481,9 +481,11 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             mv.da1 = (int)(e.w1 & 0xF) - 2;
             da2 = (int)((e.w1 >> 8) & 0xF) - 2;
             mv.a1 = wrap1(row + mv.da1, d0);
-            mv.b1 = wrap1(col + (int)((e.w1 >> 4) & 0xF) - 2, d1);
+            db1 = (int)((e.w1 >> 4) & 0xF) - 2;
+            db2 = (int)((e.w1 >> 12) & 0xF) - 2;
+            mv.b1 = wrap1(col + db1, d1);
             mv.a2 = wrap1(row + da2, d0);
-            mv.b2 = wrap1(col + (int)((e.w1 >> 12) & 0xF) - 2, d1);
+            mv.b2 = wrap1(col + db2, d1);
             mv.ns1 = (int)((e.w1 >> 16) & 0xF); mv.ns2 = (int)((e.w1 >> 20) & 0xF);
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             mine[i] = i < na && lane < N_TYPES && (status_plane(os[i]) == lane || status_plane(ns[i]) == lane);
-            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + ((size_t)lane * d0 + as[i]) * We + ((bcol[i] + 2) >> 6)));
+            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + (uint32_t)((lane * d0 + as[i]) * We + ((bcol[i] + 2) >> 6))));
         }
         // Refresh of the five neighbourhood classes.  Every dependency of a site is inside its ring of six
         // neighbours (rows +-1, columns +-1) or, for trefoils, at (+2, 0), (0, +2), (+2, -2).  So the tasks
@@ -503,19 +505,20 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         // trefoil shapes of the touched rows and the rows 2 above them -- in the words that hold a column
         // within 2 of a touched column (at most two words).  Counted before and after the move; the
         // difference goes to the row table.
-        u64 wmask = 0;
-#pragma unroll
-        for (int i = 0; i < 3; i++)
-            if (i < na) {
-                // every column within 2 of the node (a ragged last word of one column can sit strictly between
-                // columns c and c + 2 across the wrap, so the end points alone do not bracket the words)
-#pragma unroll
-                for (int dc = -2; dc <= 2; dc++) wmask |= 1ull << (wrap1(bcol[i] + dc, d1) >> 6);
-            }
-        const int nw = __popcll(wmask);
+        // words holding a column within 2 of a touched column: the touched columns are col + {0, db1, db2} (the
+        // table holds 0 for nodes a move does not have), so the span is one unwrapped column range of at most 9
+        // columns: one or two words, or -- across the row end -- the words of its two ends plus the last and the
+        // first word (a superset is harmless: unchanged tasks contribute a zero difference)
+        uint32_t wmask;
+        {
+            const int lo = col + min(0, min(db1, db2)) - 2, hi = col + max(0, max(db1, db2)) + 2;
+            if (lo >= 0 && hi < d1) wmask = (1u << (lo >> 6)) | (1u << (hi >> 6));
+            else wmask = (1u << ((lo < 0 ? lo + d1 : lo) >> 6)) | (1u << ((hi >= d1 ? hi - d1 : hi) >> 6)) | 1u | (1u << (Wa - 1));
+        }
+        const int nw = __popc(wmask);
         // at most three words: two in the interior, three when the span wraps over a ragged last word
-        const int wA = __ffsll((long long)wmask) - 1, wB = 63 - __clzll((long long)wmask);
-        const int wM = nw == 3 ? __ffsll((long long)(wmask & (wmask - 1))) - 1 : wA;
+        const int wA = __ffs((int)wmask) - 1, wB = 31 - __clz((int)wmask);
+        const int wM = nw == 3 ? __ffs((int)(wmask & (wmask - 1))) - 1 : wA;
         // rows of the direction tasks: lo2 .. lo2 + n2 - 1 (relative to `row`); trefoil rows: g3 (nibbles, +3)
         int lo2, n2, n3;
         uint32_t g3;
@@ -551,7 +554,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         for (int i = 0; i < 3; i++)
             if (mine[i]) {
                 // the site's main position and, within two columns of a row end, its halo copy
-                u64 *rowp = P + ((size_t)lane * d0 + as[i]) * We;
+                u64 *rowp = P + (uint32_t)((lane * d0 + as[i]) * We);
                 const bool set = status_plane(ns[i]) == lane;
                 const int q0 = bcol[i] + 2;
                 const int q1 = bcol[i] < 2 ? bcol[i] + d1 + 2 : (bcol[i] >= d1 - 2 ? bcol[i] + 2 - d1 : -1);
