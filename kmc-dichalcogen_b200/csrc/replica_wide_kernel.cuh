@@ -237,8 +237,9 @@ __device__ __forceinline__ u64 operand_word(const u64 *P, int d0, int We, int a,
     int ar = a + da;
     ar = ar < 0 ? ar + d0 : (ar >= d0 ? ar - d0 : ar);
     const u64 *rp = P + (uint32_t)(pl * d0 + ar) * (uint32_t)We + w;
-    const u64 x0 = rp[0], x1 = rp[1];
-    return (x0 >> o) | ((x1 << 1) << (63 - o));            // o in [0, 4]: no shift by 64
+    const uint2 x0 = *reinterpret_cast<const uint2 *>(rp);
+    const uint32_t x1lo = *reinterpret_cast<const uint32_t *>(rp + 1);      // o <= 4: only the low half shifts in
+    return (u64)__funnelshift_r(x0.x, x0.y, o) | ((u64)__funnelshift_r(x0.y, x1lo, o) << 32);
 }
 // packed counts of a task: classes (2,3) in c01, (4,5) in c23 for k < 6; class 6 in c45 for k == 6
 __device__ __forceinline__ void task_counts(const u64 *P, int d0, int We, int a, int w, int k, uint32_t desc, u64 valid,
