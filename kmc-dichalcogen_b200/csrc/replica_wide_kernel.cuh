@@ -44,7 +44,8 @@ __host__ __device__ inline size_t wide_warp_bytes(int d0) {
 
 struct WGeom {
     const u64 *P; int d0, d1, Wa, We;
-    __device__ __forceinline__ const u64 *rowp(int pl, int a) const { return P + ((size_t)pl * d0 + a) * We; }
+    // (a replica's planes hold fewer than 2^32 words, so the offset is taken in 32 bits)
+    __device__ __forceinline__ const u64 *rowp(int pl, int a) const { return P + (uint32_t)((pl * d0 + a) * We); }
     // anchor columns of word w that exist (all ones except in a ragged last word)
     __device__ __forceinline__ u64 valid(int w) const {
         const int left = d1 - 64 * w;
