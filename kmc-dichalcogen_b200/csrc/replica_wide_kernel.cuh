@@ -39,7 +39,8 @@ __host__ __device__ inline int wide_anchor_words(int d1) { return (d1 + 63) >> 6
 __host__ __device__ inline int wide_row_words(int d1) { return wide_anchor_words(d1) + 1; }
 __host__ __device__ inline size_t wide_warp_bytes(int d0) {
     const size_t d0p = ((size_t)d0 + 1) & ~(size_t)1;
-    return ((NC * d0p * 2 + 15) & ~(size_t)15) + NC * 32 * sizeof(uint32_t);      // row table + 32 block sums per class
+    // row table + 32 block sums per class + the before-counts of up to 4 x 32 refresh tasks (5 words each)
+    return ((NC * d0p * 2 + 15) & ~(size_t)15) + NC * 32 * sizeof(uint32_t) + 4 * 5 * 32 * sizeof(uint32_t);
 }
 
 struct WGeom {
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * wide_warp_bytes(d0));
     uint32_t *rc32 = reinterpret_cast<uint32_t *>(rc16);
     uint32_t *bs = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(rc16) + ((NC * (size_t)d0p * 2 + 15) & ~(size_t)15));
+    uint32_t *scr = bs + NC * 32;                          // [4 rounds][5 fields][32 lanes]
     u64 *P = wp.planes + (size_t)rep * N_TYPES * d0 * We;
     WGeom G{P, d0, d1, Wa, We};
     uint16_t *ghier = wp.hier + (size_t)rep * NC * d0p;
@@ -532,24 +534,23 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         } else { lo2 = -1; n2 = 5; n3 = 3; g3 = 0x531u; }                            // {-2, 0, 2}
         if (n2 > d0) n2 = d0;
         const int ntask = (6 * n2 + n3) * nw;
-        uint32_t b01[4] = {0, 0, 0, 0}, b23[4] = {0, 0, 0, 0}, b45[4] = {0, 0, 0, 0};
-        int ta[4] = {0, 0, 0, 0};                              // row | word << 16 | k << 24 of the lane's tasks
-        uint32_t td[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
+        // one task per lane and round (a single round unless the span crosses a word boundary); the task and its
+        // before-counts wait in shared memory for the after-pass, so the task code exists once
+#pragma unroll 1
+        for (int it = 0; 32 * it < ntask; it++) {
             const int tk = lane + 32 * it;
-            if (32 * it < ntask) {                             // warp-uniform
-                const int u = nw == 1 ? tk : (nw == 2 ? tk >> 1 : (tk * 171) >> 9);      // tk / nw
-                const int iw = tk - u * nw;
-                const int wd = iw == 0 ? wA : (iw == nw - 1 ? wB : wM);
-                int k = 6, a;
-                if (u < 6 * n2) { const int j = (u * 43) >> 8; k = u - 6 * j; a = row + lo2 + j; }       // u / 6 for u < 48
-                else a = row + (int)((g3 >> (4 * ((u - 6 * n2) & 7))) & 0xF) - 3;
-                a = wrap1(wrap1(a, d0), d0);
-                ta[it] = a | (wd << 16) | (k << 24);
-                td[it] = __shfl_sync(FULL, my_desc, k);
-                if (tk < ntask) task_counts(P, d0, We, a, wd, k, td[it], G.valid(wd), b01[it], b23[it], b45[it]);
-            }
+            const int u = nw == 1 ? tk : (nw == 2 ? tk >> 1 : (tk * 171) >> 9);      // tk / nw
+            const int iw = tk - u * nw;
+            const int wd = iw == 0 ? wA : (iw == nw - 1 ? wB : wM);
+            int k = 6, a;
+            if (u < 6 * n2) { const int j = (u * 43) >> 8; k = u - 6 * j; a = row + lo2 + j; }       // u / 6 for u < 48
+            else a = row + (int)((g3 >> (4 * ((u - 6 * n2) & 7))) & 0xF) - 3;
+            a = wrap1(wrap1(a, d0), d0);
+            const uint32_t desc = __shfl_sync(FULL, my_desc, k);
+            uint32_t b01 = 0, b23 = 0, b45 = 0;
+            if (tk < ntask) task_counts(P, d0, We, a, wd, k, desc, G.valid(wd), b01, b23, b45);
+            uint32_t *sc = scr + it * 160 + lane;
+            sc[0] = b01; sc[32] = b23; sc[64] = b45; sc[96] = (uint32_t)(a | (wd << 16) | (k << 24)); sc[128] = desc;
         }
         __syncwarp();
 #pragma unroll
@@ -591,23 +592,25 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         __threadfence_block();
         __syncwarp();
         uint32_t x01 = 0, y01 = 0, x23 = 0, y23 = 0, x45 = 0, y45 = 0;       // after / before, summed over the lane's tasks
-#pragma unroll
-        for (int it = 0; it < 4; it++) {
+#pragma unroll 1
+        for (int it = 0; 32 * it < ntask; it++) {
             const int tk = lane + 32 * it;
             if (tk < ntask) {
-                const int a = ta[it] & 0xFFFF, wd = (ta[it] >> 16) & 0xFF, k = ta[it] >> 24;
+                const uint32_t *sc = scr + it * 160 + lane;
+                const uint32_t b01 = sc[0], b23 = sc[32], b45 = sc[64], tak = sc[96], desc = sc[128];
+                const int a = tak & 0xFFFF, wd = (tak >> 16) & 0xFF, k = tak >> 24;
                 uint32_t a01, a23, a45;
-                task_counts(P, d0, We, a, wd, k, td[it], G.valid(wd), a01, a23, a45);
-                const int dd[5] = {(int)(a01 & 0xFFFF) - (int)(b01[it] & 0xFFFF), (int)(a01 >> 16) - (int)(b01[it] >> 16),
-                                   (int)(a23 & 0xFFFF) - (int)(b23[it] & 0xFFFF), (int)(a23 >> 16) - (int)(b23[it] >> 16),
-                                   (int)a45 - (int)b45[it]};
+                task_counts(P, d0, We, a, wd, k, desc, G.valid(wd), a01, a23, a45);
+                const int dd[5] = {(int)(a01 & 0xFFFF) - (int)(b01 & 0xFFFF), (int)(a01 >> 16) - (int)(b01 >> 16),
+                                   (int)(a23 & 0xFFFF) - (int)(b23 & 0xFFFF), (int)(a23 >> 16) - (int)(b23 >> 16),
+                                   (int)a45 - (int)b45};
 #pragma unroll
                 for (int q = 0; q < 5; q++)
                     if (dd[q]) {
                         atomicAdd(&rc32[((C_MOVE_DIV + q) * d0p + a) >> 1], (uint32_t)dd[q] << (16 * (a & 1)));
                         atomicAdd(&bs[(C_MOVE_DIV + q) * 32 + (a >> bshift)], (uint32_t)dd[q]);
                     }
-                x01 += a01; y01 += b01[it]; x23 += a23; y23 += b23[it]; x45 += a45; y45 += b45[it];
+                x01 += a01; y01 += b01; x23 += a23; y23 += b23; x45 += a45; y45 += b45;
             }
         }
         {
