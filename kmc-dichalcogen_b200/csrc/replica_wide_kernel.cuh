@@ -494,14 +494,13 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
         const int na = mv.na;
-        // lanes 0..5 own a plane each: start fetching the words they will rewrite
+        // lanes 0..5 own a plane each (the Z and D rows they rewrite were prefetched with the refresh rows)
         const int as[3] = {row, mv.a1, mv.a2}, bcol[3] = {col, mv.b1, mv.b2}, ns[3] = {mv.ns0, mv.ns1, mv.ns2};
         const int os[3] = {s0, os1, os2};
         bool mine[3];                                          // does node i leave or enter this lane's plane?
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             mine[i] = i < na && lane < N_TYPES && (status_plane(os[i]) == lane || status_plane(ns[i]) == lane);
-            if (mine[i]) asm volatile("prefetch.global.L1 [%0];" :: "l"(P + (uint32_t)((lane * d0 + as[i]) * We + ((bcol[i] + 2) >> 6))));
         }
         // Refresh of the five neighbourhood classes.  Every dependency of a site is inside its ring of six
         // neighbours (rows +-1, columns +-1) or, for trefoils, at (+2, 0), (0, +2), (+2, -2).  So the tasks
