@@ -55,8 +55,9 @@ struct WGeom {
 };
 // the 64 columns 64w + db .. 64w + db + 63 of a plane row (halo layout), |db| <= 2
 __device__ __forceinline__ u64 window(u64 x0, u64 x1, int db) {
-    const int o = db + 2;
-    return o ? (x0 >> o) | (x1 << (64 - o)) : x0;
+    const uint32_t o = (uint32_t)(db + 2);                 // 0 .. 4: only the low half of x1 shifts in
+    const uint32_t a = (uint32_t)x0, b = (uint32_t)(x0 >> 32), c = (uint32_t)x1;
+    return (u64)__funnelshift_r(a, b, o) | ((u64)__funnelshift_r(b, c, o) << 32);
 }
 __device__ __forceinline__ u64 window_at(const u64 *rowp, int w, int db) { return window(rowp[w], rowp[w + 1], db); }
 
@@ -64,12 +65,13 @@ __device__ __forceinline__ u64 window_at(const u64 *rowp, int w, int db) { retur
 struct Nbhd { u64 z[3][2], d[4][2]; u64 valid; };
 template <bool WITH_ROW2 = true>
 __device__ __forceinline__ void load_nbhd(const WGeom &g, int a, int w, Nbhd &n) {
+    const uint32_t plane = (uint32_t)(g.d0 * g.We);          // words per plane: Z is plane 0, D plane 1
 #pragma unroll
     for (int r = 0; r < (WITH_ROW2 ? 4 : 3); r++) {
-        const int ar = wrap1(wrap1(a + r - 1, g.d0), g.d0);
-        const u64 *dp = g.rowp(T_D, ar);
-        n.d[r][0] = dp[w]; n.d[r][1] = dp[w + 1];
-        if (r < 3) { const u64 *zp = g.rowp(T_Z, ar); n.z[r][0] = zp[w]; n.z[r][1] = zp[w + 1]; }
+        const int ar = wrap1(a + r - 1, g.d0);                 // offsets -1 .. +2 wrap at most once (d0 >= 5)
+        const u64 *zp = g.P + (uint32_t)(ar * g.We + w);
+        n.d[r][0] = zp[plane]; n.d[r][1] = zp[plane + 1];
+        if (r < 3) { n.z[r][0] = zp[0]; n.z[r][1] = zp[1]; }
     }
     n.valid = g.valid(w);
 }
@@ -247,7 +249,7 @@ __device__ __forceinline__ u64 operand_word(const u64 *P, int d0, int We, int a,
 __device__ __forceinline__ void task_counts(const u64 *P, int d0, int We, int a, int w, int k, uint32_t desc, u64 valid,
                                             uint32_t &c01, uint32_t &c23, uint32_t &c45) {
     const u64 *dp = P + (uint32_t)(T_D * d0 + a) * (uint32_t)We + w;
-    const u64 D0 = ((dp[0] >> 2) | (dp[1] << 62)) & valid;
+    const u64 D0 = window(dp[0], dp[1], 0) & valid;
     const u64 A = operand_word(P, d0, We, a, w, desc & 0x7Fu);
     const u64 Bv = operand_word(P, d0, We, a, w, (desc >> 7) & 0x7Fu);
     const u64 C = operand_word(P, d0, We, a, w, (desc >> 14) & 0x7Fu);
