@@ -261,6 +261,8 @@ def main():
     # 6. non-square, larger than a warp's row span
     trajectory("allrules_40x70", (40, 70), ALL_RULES, exact_state((40, 70), 0.1, 0.1, 2), seed=6,
                nsteps=1500, replica=3)
+    # 7. the reference's own default run: `python3 -m demo1 test-cfg.yaml` = 200x200, pristine start (BASELINE config 1)
+    trajectory("testcfg_200x200", (200, 200), TEST_CFG_RULES, np.zeros(40000, np.uint8), seed=20261019, nsteps=3000)
     state_gen_fixtures()
     state_gen_philox_fixtures()
     zobrist_reference_fixture()
