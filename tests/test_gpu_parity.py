@@ -56,6 +56,28 @@ def test_golden_trajectory_philox(name):
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [1, 3, 5])
+@pytest.mark.parametrize("name", ["allrules_40x70", "testcfg_200x200"])
+def test_golden_wide_rows_on_every_kernel(name, variant):
+    """The reference-made fixtures with rows wider than 64 sites (among them the reference's own default run,
+    200x200) on the byte kernel in shared memory, the byte kernel with the lattice in HBM and the wide bit-plane
+    kernel."""
+    g = load(name)
+    m = g["meta"]
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(g["status0"])
+    half = m["nsteps"] // 2
+    ev = np.concatenate([eng.run(half, m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL, validate=True)[0],
+                         eng.run(m["nsteps"] - half, m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL,
+                                 validate=True)[0]])
+    assert_events_equal(ev, g["events"], name)
+    got = fsum_totals(ev, g["rates"], m["class_order"])
+    assert (got.view(np.uint64) == g["events"]["total_rate"].view(np.uint64)).all()
+    assert (eng.download_state()[0] == g["status1"]).all()
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["allrules_8x8", "ties_7x11", "wse2_hot_24x24"])
 def test_golden_trajectory_injected_draws(name):
     """Same trajectories through the draw-injection seam (kmc_step_draws), in two chunks."""
