@@ -263,6 +263,8 @@ def main():
                nsteps=1500, replica=3)
     # 7. the reference's own default run: `python3 -m demo1 test-cfg.yaml` = 200x200, pristine start (BASELINE config 1)
     trajectory("testcfg_200x200", (200, 200), TEST_CFG_RULES, np.zeros(40000, np.uint8), seed=20261019, nsteps=3000)
+    # 8. rows wider than 64 sites with a ragged last word (the wide bit-plane kernel's layout), trefoils live
+    trajectory("allrules_12x130", (12, 130), ALL_RULES, exact_state((12, 130), 0.2, 0.1, 8), seed=13, nsteps=2500, replica=1)
     state_gen_fixtures()
     state_gen_philox_fixtures()
     zobrist_reference_fixture()

@@ -57,7 +57,7 @@ def test_golden_trajectory_philox(name):
 
 
 @pytest.mark.parametrize("variant", [1, 3, 5])
-@pytest.mark.parametrize("name", ["allrules_40x70", "testcfg_200x200"])
+@pytest.mark.parametrize("name", ["allrules_40x70", "testcfg_200x200", "allrules_12x130"])
 def test_golden_wide_rows_on_every_kernel(name, variant):
     """The reference-made fixtures with rows wider than 64 sites (among them the reference's own default run,
     200x200) on the byte kernel in shared memory, the byte kernel with the lattice in HBM and the wide bit-plane
