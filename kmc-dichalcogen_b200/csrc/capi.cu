@@ -271,6 +271,11 @@ extern "C" int kmc_generate_state(kmc_engine *h, int mode, int n_keys, const int
         CU(cudaMalloc(&perm, (size_t)h->R * h->n * sizeof(uint32_t)));
         p.perm = perm;
     }
+    if (mode == 1) {
+        const long long sites = (long long)h->R * h->n;
+        kmc_generate_approx_sites_kernel<<<(unsigned)((sites + 255) / 256), 256, 0, h->stream>>>(p);
+        h->launches += 1;
+    }
     kmc_generate_state_kernel<<<(unsigned)((h->R + 63) / 64), 64, 0, h->stream>>>(p);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);

@@ -53,6 +53,21 @@ struct GenParams {
     uint32_t *perm;                 // exact: [n][R] scratch
 };
 
+// 'approx', first half (state.py:342-356 through kmc.py:41-50): site i takes draw i of its replica's stream,
+// x = 0.0 + (total - 0.0) * random(), category = bisect_left(cumulative weights, x).  One thread per site.
+__global__ void kmc_generate_approx_sites_kernel(const GenParams p)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)p.n_replicas * p.n) return;
+    const int r = (int)(gid / p.n);
+    const int i = (int)(gid - (long long)r * p.n);
+    GenStream g{p.seed, (unsigned long long)i, p.replica0 + (uint32_t)r};
+    const double x = __dmul_rn(p.cumul[p.n_keys - 1], g.random());
+    int k = 0;
+    while (k < p.n_keys - 1 && p.cumul[k] < x) k++;
+    p.status[gid] = p.code[k] == 1 ? 0xFF : (uint8_t)p.code[k];
+}
+
 __global__ void kmc_generate_state_kernel(const GenParams p)
 {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,14 +90,22 @@ __global__ void kmc_generate_state_kernel(const GenParams p)
                 else if (p.code[k] == 1) st[node] = (uint8_t)(1 + g.randbelow(2u));
             }
     } else {
-        const double total = p.cumul[p.n_keys - 1];
-        for (int i = 0; i < n; i++) {
-            const double x = __dmul_rn(total, g.random());          // 0.0 + (total - 0.0) * random()
-            int k = 0;
-            while (k < p.n_keys - 1 && p.cumul[k] < x) k++;          // bisect_left
-            st[i] = p.code[k] == 1 ? 0xFF : (uint8_t)p.code[k];
+        // 'approx', second half: the per-site categories were drawn by kmc_generate_approx_sites_kernel (draw i
+        // belongs to site i, so that part is parallel); the layer of every monovacancy comes next in the stream,
+        // in node order, with rejection sampling -- sequential
+        g.q = (unsigned long long)n;
+        int i = 0;
+        if ((n & 15) == 0) {                    // skip 16 sites at a time where no monovacancy is marked
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(st);
+            for (; i < n; i += 16) {
+                const uint4 v = s4[i >> 4];
+                const uint32_t any = (v.x & (v.x >> 1)) | (v.y & (v.y >> 1)) | (v.z & (v.z >> 1)) | (v.w & (v.w >> 1));
+                if (!(any & 0x40404040u)) continue;             // codes here are 0, 3 or 0xFF: bit 6 set only in 0xFF
+                for (int j = i; j < i + 16; j++)
+                    if (st[j] == 0xFF) st[j] = (uint8_t)(1 + g.randbelow(2u));
+            }
         }
-        for (int i = 0; i < n; i++)
+        for (; i < n; i++)
             if (st[i] == 0xFF) st[i] = (uint8_t)(1 + g.randbelow(2u));
     }
 }
