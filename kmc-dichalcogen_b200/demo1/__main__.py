@@ -4,7 +4,6 @@ over the CUDA engine: same flags, same YAML, same streamed JSON.  Extra flags: -
 import argparse
 import json
 import sys
-from functools import partial
 
 from . import config
 from .sim import KmcSim, class_table
@@ -213,52 +212,52 @@ def grid_info(dims):
     return {"lattice_type": "hexagonal", "coord_format": "axial", "dim": list(dims)}
 
 
-def with_profiling(f, stats_out=None, text_out=None):
-    from cProfile import Profile
-    from pstats import Stats
-    prof = Profile()
-    prof.enable()
-    retval = f()
-    prof.disable()
-    if stats_out:
-        try:
-            prof.dump_stats(stats_out)
-        except (IOError, OSError) as e:
-            warn("could not write pstats ({})", e)
-    if text_out:
-        stats = Stats(prof, stream=text_out)
-        stats.sort_stats("cumtime")
-        stats.print_stats(20)
-    return retval
+def with_profiling(job, stats_out=None, text_out=None):
+    """Run ``job()`` under cProfile (``-P PATH`` dumps pstats data, ``-p`` prints the 20 most expensive calls by
+    cumulative time).  ``python -m demo1`` cannot be combined with ``-m cProfile``, hence the wrapper."""
+    import cProfile
+    import pstats
+    profiler = cProfile.Profile()
+    try:
+        return profiler.runcall(job)
+    finally:
+        if stats_out:
+            try:
+                profiler.dump_stats(stats_out)
+            except OSError as err:
+                warn("could not write pstats ({})", err)
+        if text_out:
+            pstats.Stats(profiler, stream=text_out).sort_stats("cumtime").print_stats(20)
 
 
-def int_with_min(minimum, errmsg, s):
-    x = int(s)
-    if x < minimum:
-        raise argparse.ArgumentTypeError("%s: %d" % (errmsg, x))
-    return x
+def _bounded_int(lowest, what):
+    def parse(text):
+        value = int(text)
+        if value < lowest:
+            raise argparse.ArgumentTypeError("%s: %d" % (what, value))
+        return value
+    return parse
 
 
-positive_int = partial(int_with_min, 1, "Not a positive integer")
-nonnegative_int = partial(int_with_min, 0, "Not a non-negative integer")
+positive_int = _bounded_int(1, "Not a positive integer")
+nonnegative_int = _bounded_int(0, "Not a non-negative integer")
 
 
 def delim_parser(typ, n=None, sep=","):
-    def inner(s):
-        xs = []
-        for t in s.split(sep):
-            try:
-                xs.append(typ(t))
-            except ValueError:
-                raise argparse.ArgumentTypeError("Bad value: %r" % (t,))
-        if n not in (None, len(xs)):
-            raise argparse.ArgumentTypeError("Expected %d arguments separated by %r; got %d" % (n, sep, len(xs)))
-        return xs
-    return inner
+    """argparse type for ``A<sep>B<sep>...``: a list of ``typ`` values, exactly ``n`` of them if given."""
+    def parse(text):
+        pieces = text.split(sep)
+        if n is not None and len(pieces) != n:
+            raise argparse.ArgumentTypeError("Expected %d arguments separated by %r; got %d" % (n, sep, len(pieces)))
+        try:
+            return [typ(piece) for piece in pieces]
+        except ValueError:
+            raise argparse.ArgumentTypeError("Bad value in %r" % (text,))
+    return parse
 
 
 def say_err(msg, *args, **kw):
-    print("%s: %s" % (PROG, msg.format(*args, **kw)), file=sys.stderr)
+    sys.stderr.write("%s: %s\n" % (PROG, msg.format(*args, **kw)))
 
 
 def warn(msg, *args, **kw):
@@ -268,7 +267,7 @@ def warn(msg, *args, **kw):
 def die(msg, *args, **kw):
     say_err("FATAL: " + msg, *args, **kw)
     say_err("Aborting.")
-    sys.exit(1)
+    raise SystemExit(1)
 
 
 if __name__ == "__main__":

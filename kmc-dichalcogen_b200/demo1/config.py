@@ -13,7 +13,7 @@ Two deliberate tolerances so that the reference's own shipped files load as they
 """
 import logging
 import warnings
-from functools import partial, reduce
+from functools import partial
 
 import yaml
 
@@ -112,28 +112,31 @@ def _consume_state_random(d):
     return partial(state_mod.gen_random_state, mode=mode, params=params)
 
 
-def merge(left, right, path=()):
-    """Recursive dictionary merge; the newer value wins, loudly.  Key order is first appearance
-    (the reference iterates a set here, which makes the rule order hash-dependent -- SURVEY Q3)."""
-    if type(left) is dict and type(right) is dict:
-        out = {}
-        for key in list(left) + [k for k in right if k not in left]:
-            if key in left and key in right:
-                out[key] = merge(left[key], right[key], path + (key,))
-            else:
-                out[key] = left[key] if key in left else right[key]
-        return out
-    if left != right:
-        logging.warning("config key overriden at %s\n  old: %r\n  new: %r",
-                        ":".join(map(repr, path)) or "root", left, right)
-    return right
+def merge(older, newer, where=()):
+    """Deep merge of two config trees: mappings are merged key by key, anything else is replaced by the newer
+    value with a logged warning.  Keys keep their order of first appearance (the reference walks a set here,
+    which makes the rule order -- and with it tie-breaks -- hash-dependent: SURVEY Q3)."""
+    both_maps = type(older) is dict and type(newer) is dict
+    if not both_maps:
+        if older != newer:
+            logging.warning("config key overriden at %s\n  old: %r\n  new: %r",
+                            ":".join(repr(k) for k in where) or "root", older, newer)
+        return newer
+    merged = dict(older)
+    for key, value in newer.items():
+        merged[key] = merge(older[key], value, where + (key,)) if key in older else value
+    return merged
 
 
 def load_all(files):
-    dicts = [yaml.safe_load(f) for f in files]
-    if any(d is None for d in dicts):
-        logging.debug("empty config file")
-    dicts = [x for x in dicts if x is not None]
-    if not all(isinstance(d, dict) for d in dicts):
-        error("config must be a YAML mapping")
-    return reduce(merge, dicts, {})
+    """Parse every config file and fold them left to right with merge(); empty files are skipped."""
+    result = {}
+    for handle in files:
+        tree = yaml.safe_load(handle)
+        if tree is None:
+            logging.debug("empty config file")
+            continue
+        if not isinstance(tree, dict):
+            error("config must be a YAML mapping")
+        result = merge(result, tree)
+    return result
