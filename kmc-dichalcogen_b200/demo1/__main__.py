@@ -170,6 +170,7 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
                                             dtype=np.int64), device=dev)
     time_sum = parallel.sum_over_ranks(float(eng.clock().sum()), device=dev)
     eng.close()
+    parallel.shutdown()
     if rank != 0:
         return
     hist, hops, done = sums[:13], sums[13:19], sums[19]

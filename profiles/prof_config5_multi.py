@@ -35,3 +35,4 @@ if rank == 0:
                       "ms": ms, "event_histogram": [int(x) for x in hist], "divacancy_hops": [int(x) for x in hops],
                       "mean_squared_net_displacement": sq / TOTAL, "mean_time": tsum / TOTAL}))
 eng.close()
+parallel.shutdown()
