@@ -574,7 +574,11 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.clock = h->clock_on ? h->d_clock : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
         const unsigned blocks = (unsigned)((h->R + hpb - 1) / hpb);
-        if (h->d0 == 64 && h->d1 == 64) {
+        const bool plain = log_mode == KMC_LOG_NONE && !d_draws && !p.clock;
+        if (h->d0 == 64 && h->d1 == 64 && plain) {
+            CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kmc_replica_hw_kernel<64, 64, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
+        } else if (h->d0 == 64 && h->d1 == 64) {
             CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kmc_replica_hw_kernel<64, 64><<<blocks, hpb * 16, smem, h->stream>>>(p);
         } else {

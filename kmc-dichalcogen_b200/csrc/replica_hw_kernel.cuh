@@ -202,7 +202,9 @@ __device__ __forceinline__ int nth_set_bit_hw(u64 m, uint32_t idx, const Half &h
 // scheduler (a block shape that is not a multiple of 4 warps loads the schedulers unevenly: 3 blocks of 9
 // warps measured 1.89e9 events/s, 2 blocks of 14 warps 2.22e9, 1 block of 28 warps 2.37e9).
 constexpr int HW_MAX_THREADS = 896;
-template <int TD0, int TD1>
+// PLAIN = true: the statistics-only build (no event log, no injected draws, no clock) -- what a production
+// batch runs; the general build keeps every option.
+template <int TD0, int TD1, bool PLAIN = false>
 __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const ReplicaParams p)
 {
     const int d0 = TD0 ? TD0 : p.d0;
@@ -283,6 +285,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     asm volatile("" : "+r"(my_low_lo), "+r"(my_low_hi));
 
     const unsigned long long step_base = p.steps_done[rep];
+    const int log_mode = PLAIN ? KMC_LOG_NONE : p.log_mode;
+    const double *const draws = PLAIN ? nullptr : p.draws;
+    double *const clockp = PLAIN ? nullptr : p.clock;
     double mu1 = 0.0, mu2 = 0.0;
     long long t = 0;
     uint32_t flag = 0;
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     if (hl < 6) p.hops[(size_t)rep * 6 + hl] += hops;
     if (hl == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
+        if (clockp) clockp[rep] = __dadd_rn(clockp[rep], tclock);
         p.ties[rep] += n_ties;
         if (flag) p.flags[rep] |= flag;
     }
