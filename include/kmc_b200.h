@@ -119,7 +119,9 @@ int kmc_get_row_counts(kmc_engine *h, uint32_t *out);
  * kmc_event_compact / kmc_event_full according to log_mode, or NULL with KMC_LOG_NONE.
  * validate != 0 re-enumerates every lattice at the end of the launch and compares with the
  * incrementally maintained tables (KmcSim.validate, sim.py:159-168) -> KMC_ERR_VALIDATE.
- * Returns KMC_ERR_ZERO_RATE if a replica stopped early (see kmc_get_steps_done). */
+ * Returns KMC_ERR_ZERO_RATE if a replica stopped early (see kmc_get_steps_done).  The batch kernel (two
+ * replicas per warp) takes at most 2^30 events per launch (KMC_ERR_ARG beyond that): split longer runs, the
+ * step numbering continues. */
 int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
             void *events, int validate);
 /* Same, with the caller's uniform draws u[n_replicas][nsteps][2] (host buffer): the seam the

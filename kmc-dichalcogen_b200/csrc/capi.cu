@@ -546,6 +546,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
                                               2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
+        if (nsteps > (1ll << 30)) return fail(KMC_ERR_ARG, "at most 2^30 events per launch of the half-warp kernel: split the run");
         const size_t hbytes = replica_hw_bytes(h->d0);
         if (2 * hbytes > (size_t)h->max_smem_optin) return fail(KMC_ERR_ARG, "lattice too large for the half-warp kernel");
         // replicas (half-warps) per block: a multiple of 8 (4 warps, one per scheduler), at most 56 (28 warps of

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     if (hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)
         for (int a = 0; a < d0; a++) tot += rc16[(hl - C_MOVE_DIV) * d0p + a];
     else if (my_g1) tot = hw_own_total(PL, d0, my_g1);
-    unsigned long long hist = 0, hops = 0, n_ties = 0;
+    uint32_t hist = 0, hops = 0, n_ties = 0;                 // per launch (a launch holds at most 2^30 events)
     PickState pstate = pick_state_init(hl);
     double tclock = 0.0;
     // refresh roles: half-lanes 0..11 = direction hl % 6 of band rows 2*pass + hl / 6
@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     const double *const draws = PLAIN ? nullptr : p.draws;
     double *const clockp = PLAIN ? nullptr : p.clock;
     double mu1 = 0.0, mu2 = 0.0;
-    long long t = 0;
+    const int nsteps = (int)p.nsteps;
+    int t = 0;
     uint32_t flag = 0;
 
     // the event loop: in lockstep while both halves can continue, then whatever is left on its own
