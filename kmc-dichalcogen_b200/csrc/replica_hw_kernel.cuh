@@ -134,8 +134,10 @@ __device__ __forceinline__ ClassPick pick_class_hw(double w, int pos, PickState 
     const int hl = hw.hl;
     double ws = HSHFL(w, st.sc);
     const int ps = HSHFL(pos, st.sc);
-    int first = (int)half_min<HS>(hw, (w != st.wprev) ? (unsigned)st.spos : 16u);
-    st.wprev = w;
+    // first sorted position whose weight differs from the previous event's (st.wprev holds the weight this
+    // lane's sorted position had one event ago; meaningless after a re-sort, which starts from 0 anyway)
+    const uint32_t changed = HS::ballot(hw, ws != st.wprev);
+    int first = changed ? __ffs((int)changed) - 1 : 16;
     {
         const double wp = HSHFL_UP(ws, 1);
         const int pp = HSHFL_UP(ps, 1);
@@ -159,6 +161,7 @@ __device__ __forceinline__ ClassPick pick_class_hw(double w, int pos, PickState 
             if (resort) first = 0;
         }
     }
+    st.wprev = ws;
     ClassPick out;
     const int z = __popc(HS::ballot(hw, ws == 0.0));
     out.zero = (z == 16);
