@@ -1,16 +1,21 @@
-// replica_hw_kernel.cuh -- K3 + K4 on the bit-sliced lattice with TWO replicas per warp.
+// replica_hw_kernel.cuh -- K3 + K4 on the bit-sliced lattice with TWO replicas per warp (the batch kernel).
 //
-// Same state and the same per-event algorithm as replica_bp_kernel.cuh (bit-sliced lattice, pre-rotated
-// Z/D planes, class-major row-count table, recompute-and-replace refresh); what changes is the mapping:
-// a replica is owned by a HALF-warp (16 lanes).  Almost all of an event is warp-uniform work that needs at
-// most 16 lanes (class choice over 13+3 weight lanes, rank bookkeeping, move decoding, plane and own-status
-// updates on 10 / 13 lanes, six direction lanes), so a full warp per replica spends most issue slots on
-// instructions whose upper 16 lanes are idle.  With two replicas per warp those instructions serve two
-// events.  Every shuffle / vote / redux names only its own half (mask 0x0000FFFF or 0xFFFF0000, width 16),
-// so the halves may diverge freely (different classes, loop trip counts, early stop).
+// Same per-event algorithm as replica_bp_kernel.cuh (bit-sliced lattice, class-major row-count table,
+// recompute-and-replace refresh); what changes is the mapping and the footprint:
+//   * a replica is owned by a HALF-warp (16 lanes).  Almost all of an event is work that needs at most 16 lanes
+//     (class choice over 13+3 weight lanes, rank bookkeeping, move decoding, six plane lanes, 2 x 6 direction
+//     lanes), so a full warp per replica spends most issue slots on instructions whose upper half is idle;
+//   * the two halves of a warp run in LOCKSTEP (see HalfSync below): data-dependent branches that contain a
+//     shuffle or vote are taken if either half needs them, so every intrinsic names the full warp with width 16;
+//     a half whose partner stopped (total rate zero) or does not exist finishes with half-warp masks
+//     (replica_hw_body.inc is included once for each mode);
+//   * shared memory and registers bound residency together, so the kernel keeps only the six type planes
+//     (neighbour rows are rotated on the fly, two funnel shifts per rotate) and row counts only for the five
+//     neighbourhood classes (own-status row counts are plane popcounts): 3.6 KiB per replica at 64 rows,
+//     one block of 28 warps = 56 replicas per SM at 72 registers.
 //
 // Lane roles inside a half (hl = lane & 15):
-//   hl < 13   owns class hl (total count, rate, own-status row counts)      hl < 10  maintains bit plane hl
+//   hl < 13   owns class hl (total count, rate)                             hl < 6   maintains bit plane hl
 //   hl < 6    direction hl of the MoveDivacancy masks during the site search, CreateTrefoil anchor rows
 //   hl < 12   refresh: direction hl % 6 of band rows 2*pass + hl / 6
 #pragma once
@@ -18,9 +23,7 @@
 
 namespace kmc {
 
-// Shared memory is what limits how many half-warps fit on an SM, so this kernel keeps only the six
-// type planes (3 KiB at 64 rows) and rotates neighbour rows on the fly (two funnel shifts per rotate)
-// instead of holding pre-rotated copies: 4.6 KiB per replica -> 48 replicas = 24 warps per SM.
+// plane index == plane type (no pre-rotated copies here)
 enum { HW_PLANES = N_TYPES };      // plane index == plane type: T_Z, T_D, T_M1, T_M2, T_A4, T_A7
 
 // Row counts are kept only for the five neighbourhood classes (MoveDivacancy x 4, CreateTrefoil); the row
