@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--replicas", type=int, default=16384, help="replicas per GPU")
+    ap.add_argument("--strong-replicas", type=int, default=16384,
+                    help="replicas in TOTAL for the strong-scaling block (BASELINE configs[2] as worded)")
     ap.add_argument("--events", type=int, default=10000, help="events per replica per step (launch)")
     ap.add_argument("--warps-per-block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -263,87 +265,114 @@ def main():
         torch.cuda.synchronize()
 
     rates, order = wse2_rates(), WSE2_ORDER
-    R, E = args.replicas, args.events
-    replica0 = rank * R                     # global replica index -> results independent of GPU count
-    lattices = synthetic_lattices(R, replica0)
-    host = torch.from_numpy(lattices).pin_memory()
-    host_out = torch.empty_like(host).pin_memory()
-    eng = Engine(DIM, rates, order, n_replicas=R, device=local)
-    if args.warps_per_block:
-        eng.set_warps_per_block(args.warps_per_block)
-    eng.upload_state(host.numpy())
-    # ---- device-resident throughput ------------------------------------------------------------
-    for _ in range(args.warmup):
-        eng.run(E, SEED, replica0=replica0)
-    eng.sync()
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    launches0 = eng.launch_count()
-    total_ms = 0.0
-    for _ in range(args.steps):
-        eng.flush_l2()                      # on the engine's stream: L2 is cold, the GPU never idles
-        eng.timer_start()
-        eng.run(E, SEED, replica0=replica0)
-        total_ms += eng.timer_stop()
-    launches = eng.launch_count() - launches0
-    clocks = sampler.stop()
-    barrier()
-    max_ms = parallel.max_over_ranks(total_ms, device=cuda)
-    value = world * R * E * args.steps / (max_ms * 1e-3)
-    steps_done = eng.steps_done()
-    assert int(steps_done.min()) == (args.warmup + args.steps) * E, "a replica stopped early"
+    E = args.events
 
-    # the one collective of the path: event histogram summed over GPUs (NCCL over NVLink)
-    hist = parallel.reduce_histogram(eng.histogram(), device=cuda)
-    assert int(hist.sum()) == world * R * E * (args.warmup + args.steps)
+    def measure_batch(R, sample_clocks):
+        """Device-resident and end-to-end events/s of R replicas per GPU (global replica index = rank * R + r)."""
+        replica0 = rank * R                 # global replica index -> results independent of GPU count
+        lattices = synthetic_lattices(R, replica0)
+        host = torch.from_numpy(lattices).pin_memory()
+        host_out = torch.empty_like(host).pin_memory()
+        eng = Engine(DIM, rates, order, n_replicas=R, device=local)
+        if args.warps_per_block:
+            eng.set_warps_per_block(args.warps_per_block)
+        eng.upload_state(host.numpy())
+        # ---- device-resident throughput --------------------------------------------------------
+        for _ in range(args.warmup):
+            eng.run(E, SEED, replica0=replica0)
+        eng.sync()
+        barrier()
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        launches0 = eng.launch_count()
+        total_ms = 0.0
+        for _ in range(args.steps):
+            eng.flush_l2()                  # on the engine's stream: L2 is cold, the GPU never idles
+            eng.timer_start()
+            eng.run(E, SEED, replica0=replica0)
+            total_ms += eng.timer_stop()
+        n_launch = eng.launch_count() - launches0
+        clk = sampler.stop() if sampler else None
+        barrier()
+        eng.check_status()                  # a statistics-only launch is asynchronous: this is where a stop shows
+        max_ms = parallel.max_over_ranks(total_ms, device=cuda)
+        value = world * R * E * args.steps / (max_ms * 1e-3)
+        steps_done = eng.steps_done()
+        assert int(steps_done.min()) == (args.warmup + args.steps) * E, "a replica stopped early"
+        # the one collective of the path: event histogram summed over GPUs (NCCL over NVLink)
+        hist = parallel.reduce_histogram(eng.histogram(), device=cuda)
+        assert int(hist.sum()) == world * R * E * (args.warmup + args.steps)
 
-    # ---- end to end through the C ABI with host buffers ------------------------------------------
-    # Every step: H2D of that step's lattices from pinned memory, the launch, D2H of the final lattices and of
-    # the per-replica statistics.  Two handles (two streams), each driven by its own host thread, keep two steps
-    # in flight so that one step's copies run under the other's kernel (ctypes releases the GIL in the calls);
-    # `--e2e-in-flight 1` gives the strictly sequential figure.
-    n_flight = max(1, min(2, args.e2e_in_flight))
-    engines = [eng] + [Engine(DIM, rates, order, n_replicas=R, device=local) for _ in range(n_flight - 1)]
-    hosts_in = [host] + [host.clone().pin_memory() for _ in range(n_flight - 1)]
-    hosts_out = [host_out] + [torch.empty_like(host).pin_memory() for _ in range(n_flight - 1)]
-    checks = [0] * n_flight
+        # ---- end to end through the C ABI with host buffers --------------------------------------
+        # Every step: H2D of that step's lattices from pinned memory, the launch, D2H of the final lattices and
+        # of the per-replica statistics.  Two handles (two streams), each driven by its own host thread, keep two
+        # steps in flight so that one step's copies run under the other's kernel (ctypes releases the GIL in the
+        # calls); `--e2e-in-flight 1` gives the strictly sequential figure.
+        n_flight = max(1, min(2, args.e2e_in_flight))
+        engines = [eng] + [Engine(DIM, rates, order, n_replicas=R, device=local) for _ in range(n_flight - 1)]
+        hosts_in = [host] + [host.clone().pin_memory() for _ in range(n_flight - 1)]
+        hosts_out = [host_out] + [torch.empty_like(host).pin_memory() for _ in range(n_flight - 1)]
+        checks = [0] * n_flight
 
-    def e2e_step(i):
-        e = engines[i]
-        e.upload_state(hosts_in[i].numpy())                # H2D from pinned memory (+ device-side validation)
-        e.run(E, SEED, replica0=replica0)
-        e.download_state_into(hosts_out[i].numpy())        # D2H final lattices
-        checks[i] = int(e.histogram_per_replica().sum())   # D2H statistics
+        def e2e_step(i):
+            e = engines[i]
+            e.upload_state(hosts_in[i].numpy())                # H2D from pinned memory (+ device-side validation)
+            e.run(E, SEED, replica0=replica0)
+            e.download_state_into(hosts_out[i].numpy())        # D2H final lattices
+            checks[i] = int(e.histogram_per_replica().sum())   # D2H statistics
 
-    def e2e_run(nsteps):
-        shares = [nsteps // n_flight + (1 if i < nsteps % n_flight else 0) for i in range(n_flight)]
-        def work(i):
-            for _ in range(shares[i]):
-                e2e_step(i)
-        if n_flight == 1:
-            work(0)
-            return
-        ts = [threading.Thread(target=work, args=(i,)) for i in range(n_flight)]
-        for th in ts:
-            th.start()
-        for th in ts:
-            th.join()
+        def e2e_run(nsteps):
+            shares = [nsteps // n_flight + (1 if i < nsteps % n_flight else 0) for i in range(n_flight)]
 
-    for e in engines:
-        e.reset_stats()
-    e2e_run(2 * n_flight)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert sum(checks) > 0
-    e2e_value = world * R * E * args.steps / parallel.max_over_ranks(e2e_s, device=cuda)
-    h2d = R * DIM[0] * DIM[1]
-    d2h = R * DIM[0] * DIM[1] + R * 13 * 8
-    for e in engines:
-        e.close()
+            def work(i):
+                for _ in range(shares[i]):
+                    e2e_step(i)
+            if n_flight == 1:
+                work(0)
+                return
+            ts = [threading.Thread(target=work, args=(i,)) for i in range(n_flight)]
+            for th in ts:
+                th.start()
+            for th in ts:
+                th.join()
+
+        for e in engines:
+            e.reset_stats()
+        e2e_run(2 * n_flight)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(args.steps)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        assert sum(checks) > 0
+        for e in engines:
+            e.check_status()
+        e2e_value = world * R * E * args.steps / parallel.max_over_ranks(e2e_s, device=cuda)
+        for e in engines:
+            e.close()
+        return {"value": value, "max_ms": max_ms, "e2e": e2e_value, "launches": n_launch, "clocks": clk,
+                "hist": hist, "h2d": R * DIM[0] * DIM[1], "d2h": R * DIM[0] * DIM[1] + R * 13 * 8,
+                "n_flight": n_flight}
+
+    R = args.replicas
+    weak = measure_batch(R, True)
+    value, max_ms, e2e_value, launches, clocks, hist = (weak[k] for k in ("value", "max_ms", "e2e", "launches",
+                                                                          "clocks", "hist"))
+    h2d, d2h, n_flight = weak["h2d"], weak["d2h"], weak["n_flight"]
+    # BASELINE configs[2] as worded: 16384 replicas IN TOTAL, sharded over the GPUs (strong scaling).  At one GPU
+    # that is the headline batch itself.
+    total_strong = args.strong_replicas
+    if world == 1 and total_strong == R:
+        strong = weak
+    else:
+        strong = measure_batch(max(1, total_strong // world), False)
+        launches += strong["launches"]
+    strong_block = {"replicas_total": (total_strong // world) * world, "replicas_per_gpu": total_strong // world,
+                    "value": strong["value"], "unit": "events/s", "ms_per_step": strong["max_ms"] / args.steps,
+                    "e2e": {"value": strong["e2e"], "unit": "events/s", "h2d_bytes_per_step": strong["h2d"],
+                            "d2h_bytes_per_step": strong["d2h"]},
+                    "scaling": "strong", "events_per_replica_per_step": E}
 
     # ---- HBM roofline: 4096^2 full rate sweep (single lattice, "replicas only": rank 0 measures it) -----
     roofline = None
@@ -361,6 +390,18 @@ def main():
             sw.timer_start()
             sw.sweep()
             ms.append(sw.timer_stop())
+        # steady state: back-to-back sweeps over two alternating slot-plane buffers, ONE event pair, no L2 flush
+        # in between -- each launch starts with the previous launch's last ~60 MB still dirty in L2 and pays for
+        # their write-back, exactly as it leaves its own behind: DRAM bytes inside the window = algorithmic bytes
+        sw.set_sweep_double_buffer(True)
+        for _ in range(4):
+            sw.sweep()
+        sw.sync()
+        n_steady = max(20, args.sweep_iters)
+        sw.timer_start()
+        for _ in range(n_steady):
+            sw.sweep()
+        steady_ms = sw.timer_stop() / n_steady
         sweep_launches = sw.launch_count() - l0
         sw.close()
         avg_ms = float(np.mean(ms))
@@ -371,6 +412,10 @@ def main():
                     "traffic": (recorded_traffic() or {}).get("dram_bytes_per_launch"),
                     "traffic_source": (recorded_traffic() or {}).get("source"), "peak_source": peak_src, "bytes_per_site": SWEEP_BYTES_PER_SITE,
                     "ms_per_sweep": avg_ms, "ms_min": float(np.min(ms)), "sites_per_s": nsites / (avg_ms * 1e-3),
+                    "ms_per_sweep_steady": steady_ms,
+                    "achieved_steady": nsites * SWEEP_BYTES_PER_SITE / (steady_ms * 1e-3) / 1e9,
+                    "frac_steady": nsites * SWEEP_BYTES_PER_SITE / (steady_ms * 1e-3) / 1e9 / peak,
+                    "steady_note": "%d back-to-back launches alternating two slot-plane buffers, one CUDA event pair, no flush" % n_steady,
                     "note": "timed region = exactly one launch (slot planes + row counts + class totals in one kernel), CUDA events on the engine's stream, L2 flushed before each launch"}
         launches += sweep_launches
 
@@ -388,6 +433,23 @@ def main():
         ms1 = one.timer_stop()
         one.close()
         other["64x64_single_trajectory_incremental"] = {"events_per_s": 500000 / (ms1 * 1e-3), "events": 500000}
+        # the headline batch with every implemented rule live (config/mixed_rates.yaml: 13 classes, the two halves
+        # of a warp mostly choose different classes -- the half-warp kernel's worst case for lockstep)
+        mx_rates = [10.0, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 55.0]
+        mx_order = [8, 9, 10, 11, 0, 2, 3, 4, 5, 6, 7, 12, 1]
+        mx = Engine(DIM, mx_rates, mx_order, n_replicas=R, device=local)
+        mx.upload_state(synthetic_lattices(R, 0))
+        mx.run(2000, SEED)
+        mx.sync()
+        mx.timer_start()
+        mx.run(E, SEED)
+        msx = mx.timer_stop()
+        mx.check_status()
+        mxh = mx.histogram()
+        mx.close()
+        other["64x64_x%d_mixed_rates" % R] = {"events_per_s": R * E / (msx * 1e-3), "replicas": R, "events_per_replica": E,
+                                              "config": "kmc-dichalcogen_b200/config/mixed_rates.yaml (13 live classes)",
+                                              "event_histogram": [int(x) for x in mxh]}
         # the same trajectory through the reference-facing API with the reference's JSON event log produced for
         # every event (KmcSim.iter_json_lines: kernel launches of 4096 events + host formatting), wall clock
         from demo1.sim import KmcSim, RuleSpec
@@ -479,6 +541,7 @@ def main():
                                       "the event histogram at the end"},
             "e2e": {"value": e2e_value, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps_in_flight": n_flight},
+            "strong_scaling": strong_block,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,

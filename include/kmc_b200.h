@@ -119,9 +119,12 @@ int kmc_get_row_counts(kmc_engine *h, uint32_t *out);
  * kmc_event_compact / kmc_event_full according to log_mode, or NULL with KMC_LOG_NONE.
  * validate != 0 re-enumerates every lattice at the end of the launch and compares with the
  * incrementally maintained tables (KmcSim.validate, sim.py:159-168) -> KMC_ERR_VALIDATE.
- * Returns KMC_ERR_ZERO_RATE if a replica stopped early (see kmc_get_steps_done).  The batch kernel (two
- * replicas per warp) takes at most 2^30 events per launch (KMC_ERR_ARG beyond that): split longer runs, the
- * step numbering continues. */
+ * A replica whose total rate reaches zero stops (reference: ValueError, kmc.py:31-32; see kmc_get_steps_done).
+ * With an event log or validate != 0 the call synchronises and returns KMC_ERR_ZERO_RATE / KMC_ERR_VALIDATE
+ * itself.  A statistics-only launch (KMC_LOG_NONE, validate == 0) is ASYNCHRONOUS and returns KMC_OK once
+ * queued: the stop is then reported by the next kmc_check_status() on the handle (it stays raised until
+ * kmc_reset_stats or until the lattice is replaced).  The batch kernel (two replicas per warp) takes at most
+ * 2^30 events per launch (KMC_ERR_ARG beyond that): split longer runs, the step numbering continues. */
 int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
             void *events, int validate);
 /* Same, with the caller's uniform draws u[n_replicas][nsteps][2] (host buffer): the seam the
@@ -129,6 +132,11 @@ int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int
  * (incremental.py:283). */
 int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events,
                    int validate);
+/* Wait for the handle's stream, then report what the launches since the last kmc_reset_stats / lattice
+ * replacement raised: KMC_ERR_ZERO_RATE if some replica stopped on a total rate of zero (kmc.py:31-32),
+ * KMC_ERR_VALIDATE if a validating launch found a mismatch, else KMC_OK.  The synchronous counterpart of an
+ * asynchronous kmc_run. */
+int kmc_check_status(kmc_engine *h);
 /* KmcSim.perform_given_move (sim.py:145-157) on one replica: apply move (site, slot). */
 int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot);
 
@@ -136,6 +144,8 @@ int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot);
  * class selection + hierarchical in-class rank search, apply.  Same draws and records as kmc_run. */
 int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
                   void *events);
+/* the same event with the caller's draws u[n_replicas][nsteps][2] (the kmc_step_draws seam on this path) */
+int kmc_step_draws_noinc(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events);
 
 /* statistics: events per class summed over replicas [13]; per replica [n_replicas][13];
  * events done per replica [n_replicas]; boundary ties summed over replicas. */
@@ -155,11 +165,24 @@ int kmc_get_hops(kmc_engine *h, int64_t *out);
 int kmc_zobrist(kmc_engine *h, int bits, uint64_t seed, uint64_t *out);
 int kmc_get_ties(kmc_engine *h, int64_t *out);
 int kmc_reset_stats(kmc_engine *h);
-/* Optional KMC clock (extension; the reference draws no time step, SURVEY F6, but logs total_rate so that
- * time can be reconstructed, README.md:36-37): per replica t += 1 / total_rate at every event, the mean
- * residence time estimator, accumulated in fp64 in event order.  out: [n_replicas]. */
-int kmc_enable_clock(kmc_engine *h, int on);
+/* Optional KMC clock (extension; the reference draws no time step, SURVEY F6, but logs total_rate so that time
+ * can be reconstructed, sim.py:138, README.md:36-37).  Per replica, accumulated in fp64 in event order across
+ * launches:  mode 1: t += 1 / total_rate (the mean residence time);  mode 2: the BKL / Gillespie residence time
+ * t += -ln(u3) / total_rate with a third Philox draw per event, u3 in (0, 1] from counter domain 3 of the
+ * replica's stream (csrc/kmc_common.cuh: kmc_draw3, kmc_log -- a fixed sequence of IEEE operations, so the value
+ * is bit-identical on the device, the host and the oracle).  mode 0 switches it off.  out: [n_replicas]. */
+int kmc_enable_clock(kmc_engine *h, int mode);
 int kmc_get_clock(kmc_engine *h, double *out);
+/* Optional divacancy tracers (extension, SURVEY 8(f) rank 4 "diffusion observables"): every divacancy carries its
+ * unwrapped displacement (axial da, db; int16 each) since it appeared (CreateDivacancy, CreateMonovacancy
+ * make-empty, DestroyTrefoil), since the lattice was replaced, or since kmc_reset_stats; a MoveDivacancy hop in
+ * direction k adds neighbour k of neighbors_and_mutuals (state.py:443-459).  kmc_get_msd: per replica the sum
+ * over its divacancies of da^2 + da*db + db^2 (squared length in lattice constants) and their number, so that
+ * MSD = sum / count and, with the clock, D = MSD / (4 t).  [n_replicas] each.  kmc_get_tracers: the raw table
+ * of one replica, [dim0*dim1] words da | db << 16 (entries of sites without a divacancy are stale). */
+int kmc_enable_tracers(kmc_engine *h, int on);
+int kmc_get_msd(kmc_engine *h, int64_t *sum_sq, int64_t *n_tracers);
+int kmc_get_tracers(kmc_engine *h, int replica, uint32_t *out);
 
 /* measurement helpers: CUDA events recorded on the handle's stream */
 int kmc_sync(kmc_engine *h);
@@ -190,6 +213,9 @@ int kmc_set_replica_kernel(kmc_engine *h, int variant);
 /* aligned-shape sweep kernel: 0 = automatic (rolling window over rows when a row fills a CTA, i.e. 4096
  * sites; else nibble-parallel + PRMT tables), 1 = nibble-parallel + PRMT, 2 = byte-parallel.  Same results. */
 int kmc_set_sweep_kernel(kmc_engine *h, int variant);
+/* measurement helper: successive kmc_sweep calls write two alternating slot-plane buffers (steady-state
+ * bandwidth: no launch rewrites lines its predecessor left dirty in L2).  Getters read the latest one. */
+int kmc_set_sweep_double_buffer(kmc_engine *h, int on);
 
 /*
  * Event classes (reference demo1/rules.py):           Move slots per site (move key in the reference):

@@ -14,7 +14,7 @@ SOURCES = ["capi.cu"]       # single translation unit; the .cuh files are includ
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--fmad=false",              # fp64 class weights / prefix sums must not be contracted
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared", "-cudart", "static",
 ]
 
 

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/kmc_b200.h"
@@ -45,16 +46,19 @@ struct kmc_engine {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t *d_status = nullptr;
     uint8_t *d_slots = nullptr;              // [R][17][n], allocated on first sweep
+    uint8_t *d_slots_alt = nullptr; bool slots_double = false;   // measurement: alternate output buffers
     uint32_t *d_rowcnt = nullptr;            // [R][d0][16]
     unsigned long long *d_counts = nullptr;  // [R][13]
     unsigned long long *d_acc = nullptr;     // [R][16] running totals of the aligned sweep (zero between launches)
     unsigned int *d_ticket = nullptr;        // [R]
     unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr, *d_hops = nullptr;
     uint32_t *d_flags = nullptr;
+    uint32_t *d_anyflag = nullptr;           // OR of every replica's flags: the handle's asynchronous status word
     void *d_events = nullptr; size_t events_cap = 0;
     double *d_draws = nullptr; size_t draws_cap = 0;
     int *d_result = nullptr;
-    double *d_clock = nullptr; bool clock_on = false;        // optional KMC clock per replica
+    double *d_clock = nullptr; int clock_mode = 0;           // optional KMC clock per replica: 0 off, 1 mean residence, 2 stochastic
+    uint32_t *d_tracer = nullptr; bool tracer_on = false;    // optional divacancy tracers [R][n] (int16 da | int16 db << 16)
     uint32_t *d_hier = nullptr; bool hier_valid = false;   // row hierarchy of HBM-resident lattices
     // wide bit-sliced kernel (rows of 64*W sites): planes + row table live in HBM between launches.  While
     // planes_valid they describe the current lattice; bytes_stale means d_status lags behind them.
@@ -84,6 +88,8 @@ static int bind(kmc_engine *h) {
     return KMC_OK;
 }
 
+static int create_device_side(kmc_engine *h);
+
 extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int n_replicas,
                           const double *class_rate, const int *class_order, int n_order)
 {
@@ -112,6 +118,16 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
         if (!(class_rate[c] >= 0.0)) { delete h; return fail(KMC_ERR_ARG, "kmc_create: negative or NaN rate"); }   // kmc.py:37-39
         h->order_pos[c] = i; h->rate[c] = class_rate[c];
     }
+    const int rc = create_device_side(h);
+    if (rc) { const std::string msg = g_err; kmc_destroy(h); return fail(rc, msg); }   // frees whatever was allocated
+    *out = h;
+    return KMC_OK;
+}
+
+// device half of kmc_create; on failure the caller destroys the half-built engine
+static int create_device_side(kmc_engine *h)
+{
+    const int device = h->device, n_replicas = h->R;
     CU(cudaSetDevice(device));
     CU(cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -133,8 +149,9 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
     CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
+    CU(cudaMalloc(&h->d_anyflag, sizeof(uint32_t)));
+    CU(cudaMemsetAsync(h->d_anyflag, 0, sizeof(uint32_t), h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    *out = h;
     return KMC_OK;
 }
 
@@ -143,10 +160,10 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (!h) return KMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
-    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock);
+    cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
+    cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock); cudaFree(h->d_tracer);
     cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk);
-    cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags);
+    cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags); cudaFree(h->d_anyflag);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -192,6 +209,18 @@ static int ensure_bytes(kmc_engine *h)
     return KMC_OK;
 }
 
+// The zero-rate / validation flags describe the lattice they were raised on: whenever the lattice is
+// replaced or edited they are cleared (KmcSim.initialize starts afresh, sim.py:46-68).
+static int lattice_replaced(kmc_engine *h)
+{
+    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
+    CU(cudaMemsetAsync(h->d_flags, 0, (size_t)h->R * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_anyflag, 0, sizeof(uint32_t), h->stream));
+    // every divacancy of a new lattice is a new tracer
+    if (h->d_tracer) CU(cudaMemsetAsync(h->d_tracer, 0, (size_t)h->R * h->n * sizeof(uint32_t), h->stream));
+    return KMC_OK;
+}
+
 static int check_state_device(kmc_engine *h)
 {
     CU(cudaMemsetAsync(h->d_result, 0, sizeof(int), h->stream));
@@ -212,7 +241,7 @@ extern "C" int kmc_upload_state(kmc_engine *h, const uint8_t *host_status)
     int rc = bind(h); if (rc) return rc;
     if (!host_status) return fail(KMC_ERR_ARG, "kmc_upload_state: null buffer");
     CU(cudaMemcpyAsync(h->d_status, host_status, (size_t)h->R * h->n, cudaMemcpyHostToDevice, h->stream));
-    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
+    rc = lattice_replaced(h); if (rc) return rc;
     return check_state_device(h);
 }
 
@@ -231,7 +260,7 @@ extern "C" int kmc_set_state_device(kmc_engine *h, const void *dev_status)
     int rc = bind(h); if (rc) return rc;
     if (!dev_status) return fail(KMC_ERR_ARG, "kmc_set_state_device: null pointer");
     CU(cudaMemcpyAsync(h->d_status, dev_status, (size_t)h->R * h->n, cudaMemcpyDeviceToDevice, h->stream));
-    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
+    rc = lattice_replaced(h); if (rc) return rc;
     return check_state_device(h);
 }
 
@@ -282,8 +311,7 @@ extern "C" int kmc_generate_state(kmc_engine *h, int mode, int n_keys, const int
     if (perm) cudaFree(perm);
     if (e != cudaSuccess) return fail(KMC_ERR_CUDA, cudaGetErrorString(e));
     h->launches += 1;
-    h->swept = false; h->hier_valid = false; h->planes_valid = false; h->bytes_stale = false;
-    return KMC_OK;
+    return lattice_replaced(h);
 }
 
 extern "C" int kmc_get_state_device(kmc_engine *h, void *dev_status)
@@ -303,6 +331,12 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     { int rc = ensure_bytes(h); if (rc) return rc; }
     if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * RCG_STRIDE * sizeof(uint32_t)));
     if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * NS * h->n));
+    if (with_slots && h->slots_double) {
+        // steady-state measurement: successive sweeps write alternating buffers, so that a launch's stores
+        // never hit lines the previous launch left dirty in L2 (the result the getters read is the last one)
+        if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * NS * h->n));
+        std::swap(h->d_slots, h->d_slots_alt);
+    }
     // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas, one launch in total
     const int cpr = h->d1 >> 4;
     const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
@@ -387,6 +421,7 @@ extern "C" int kmc_sweep(kmc_engine *h)
 extern "C" int kmc_get_counts(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_counts: null buffer");
     if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_counts: call kmc_sweep first");
     CU(cudaMemcpyAsync(out, h->d_counts, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -396,6 +431,7 @@ extern "C" int kmc_get_counts(kmc_engine *h, int64_t *out)
 extern "C" int kmc_get_slots(kmc_engine *h, uint8_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_slots: null buffer");
     if (!h->swept || !h->d_slots) return fail(KMC_ERR_ARG, "kmc_get_slots: call kmc_sweep first");
     std::vector<uint8_t> planes((size_t)NS * h->n);
     for (int r = 0; r < h->R; r++) {
@@ -412,6 +448,7 @@ extern "C" int kmc_get_slots(kmc_engine *h, uint8_t *out)
 extern "C" int kmc_get_row_counts(kmc_engine *h, uint32_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_row_counts: null buffer");
     if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_row_counts: call kmc_sweep first");
     std::vector<uint32_t> tmp((size_t)h->R * h->d0 * RCG_STRIDE);
     CU(cudaMemcpyAsync(tmp.data(), h->d_rowcnt, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -433,6 +470,9 @@ static int ensure_events(kmc_engine *h, size_t bytes) {
         CU(cudaMalloc(&h->d_events, bytes));
         h->events_cap = bytes;
     }
+    // records a launch does not reach (everything after a zero-rate stop) read back as CLASS_NONE / site
+    // 0xFFFFFFFF instead of whatever an earlier launch left there
+    if (bytes) CU(cudaMemsetAsync(h->d_events, 0xFF, bytes, h->stream));
     return KMC_OK;
 }
 
@@ -493,6 +533,8 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         if (!h->d_planes) {
             CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
             CU(cudaMalloc(&h->d_whier, hier_elems * sizeof(uint16_t)));
+            // rows a >= d0 of the padded table are never written by the kernels but ARE compared by validate
+            CU(cudaMemsetAsync(h->d_whier, 0, hier_elems * sizeof(uint16_t), h->stream));
         }
         if (!h->planes_valid) {
             int rc = ensure_bytes(h); if (rc) return rc;
@@ -517,9 +559,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
         p.validate = validate;
-        p.clock = h->clock_on ? h->d_clock : nullptr;
+        p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
+        p.tracer = h->tracer_on ? h->d_tracer : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
         q.planes = h->d_planes; q.hier = h->d_whier; q.Wa = Wa; q.d0p = d0p;
         CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -542,7 +585,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         return KMC_OK;
     }
     { int rc = ensure_bytes(h); if (rc) return rc; }
-    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 && h->R >= 4096 &&
+    long long hw_min = 4096;
+    if (const char *e = getenv("KMC_HW_MIN_REPLICAS")) hw_min = atoll(e);              // tuning knob
+    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
                                               2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
@@ -570,12 +615,13 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
+        p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
         p.validate = validate;
-        p.clock = h->clock_on ? h->d_clock : nullptr;
+        p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
+        p.tracer = h->tracer_on ? h->d_tracer : nullptr;
         p.hier = nullptr; p.hier_valid = 0;
         const unsigned blocks = (unsigned)((h->R + hpb - 1) / hpb);
-        const bool plain = log_mode == KMC_LOG_NONE && !d_draws && !p.clock;
+        const bool plain = log_mode == KMC_LOG_NONE && !d_draws && !p.clock && !p.tracer;
         if (h->d0 == 64 && h->d1 == 64 && plain) {
             CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kmc_replica_hw_kernel<64, 64, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
@@ -624,9 +670,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
     p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
     p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
-    p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
+    p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
     p.validate = validate;
-    p.clock = h->clock_on ? h->d_clock : nullptr;
+    p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
+        p.tracer = h->tracer_on ? h->d_tracer : nullptr;
     p.hier = nullptr; p.hier_valid = 0;
     if (global_state) {
         if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * RC_WORDS * sizeof(uint32_t)));
@@ -668,7 +715,26 @@ extern "C" int kmc_run(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t re
     int rc = bind(h); if (rc) return rc;
     rc = replica_launch(h, nsteps, seed, replica0, nullptr, log_mode, events, validate); if (rc) return rc;
     if (log_mode != KMC_LOG_NONE || validate) return check_flags(h, validate != 0);
-    return KMC_OK;       // asynchronous: statistics getters / kmc_sync order after the launch
+    // statistics-only launches are asynchronous: a zero-rate stop raised by this launch is reported by the
+    // next kmc_sync / kmc_check_status on the handle (one status word, see include/kmc_b200.h)
+    return KMC_OK;
+}
+
+// synchronise, then report the handle's status word: KMC_ERR_ZERO_RATE if any replica has stopped since the
+// flags were last cleared (kmc_reset_stats, or the lattice being replaced)
+static int status_after_sync(kmc_engine *h)
+{
+    uint32_t any = 0;
+    CU(cudaMemcpyAsync(&any, h->d_anyflag, sizeof any, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (any & (FLAG_ZERO_RATE | FLAG_VALIDATE)) return check_flags(h, true);     // names the replica
+    return KMC_OK;
+}
+
+extern "C" int kmc_check_status(kmc_engine *h)
+{
+    int rc = bind(h); if (rc) return rc;
+    return status_after_sync(h);
 }
 
 extern "C" int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events,
@@ -676,6 +742,7 @@ extern "C" int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, in
 {
     int rc = bind(h); if (rc) return rc;
     if (!u) return fail(KMC_ERR_ARG, "kmc_step_draws: null draws");
+    if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
     const size_t bytes = (size_t)h->R * (size_t)nsteps * 2 * sizeof(double);
     if (bytes > h->draws_cap) {
         if (h->d_draws) CU(cudaFree(h->d_draws));
@@ -695,22 +762,52 @@ extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int 
         return fail(KMC_ERR_ARG, "kmc_perform_given: bad replica / site / slot");
     rc = ensure_bytes(h); if (rc) return rc;
     kmc_apply_given_kernel<<<1, 1, 0, h->stream>>>(h->d_status + (size_t)replica * h->n, h->d0, h->d1,
-                                                   (int)site, slot, h->d_result);
+                                                   (int)site, slot, h->d_result,
+                                                   h->tracer_on ? h->d_tracer + (size_t)replica * h->n : nullptr);
     CU(cudaGetLastError());
     h->launches += 1;
     int res = 0;
     CU(cudaMemcpyAsync(&res, h->d_result, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    h->swept = false; h->hier_valid = false; h->planes_valid = false;
     if (res) return fail(KMC_ERR_ARG, "kmc_perform_given: that move does not exist on the current lattice");
+    // the lattice was edited in place: derived tables are stale, flags start afresh (tracers carry on)
+    h->swept = false; h->hier_valid = false; h->planes_valid = false;
+    CU(cudaMemsetAsync(h->d_flags, 0, (size_t)h->R * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_anyflag, 0, sizeof(uint32_t), h->stream));
     return KMC_OK;
 }
 
 // ---- the --no-incremental event on HBM-resident lattices ---------------------------------------
+static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, const double *d_draws,
+                        int log_mode, void *events);
+
 extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
                              void *events)
 {
     int rc = bind(h); if (rc) return rc;
+    return noinc_launch(h, nsteps, seed, replica0, nullptr, log_mode, events);
+}
+
+extern "C" int kmc_step_draws_noinc(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!u) return fail(KMC_ERR_ARG, "kmc_step_draws_noinc: null draws");
+    if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
+    const size_t bytes = (size_t)h->R * (size_t)nsteps * 2 * sizeof(double);
+    if (bytes > h->draws_cap) {
+        if (h->d_draws) CU(cudaFree(h->d_draws));
+        h->d_draws = nullptr; h->draws_cap = 0;
+        CU(cudaMalloc(&h->d_draws, bytes ? bytes : 16));
+        h->draws_cap = bytes;
+    }
+    CU(cudaMemcpyAsync(h->d_draws, u, bytes, cudaMemcpyHostToDevice, h->stream));
+    return noinc_launch(h, nsteps, 0, 0, h->d_draws, log_mode, events);
+}
+
+static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, const double *d_draws,
+                        int log_mode, void *events)
+{
+    int rc;
     if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
     if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
     if (log_mode != KMC_LOG_NONE && !events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
@@ -723,7 +820,9 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
     p.seed = seed; p.replica0 = replica0; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.nsteps = nsteps;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
-    p.clock = h->clock_on ? h->d_clock : nullptr;
+    p.any_flag = h->d_anyflag; p.draws = d_draws;
+    p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
+        p.tracer = h->tracer_on ? h->d_tracer : nullptr;
     // rows row-1 .. row+2 of the chosen row are staged in shared memory when they fit
     const size_t stage_bytes = 4 * (size_t)h->d1 <= (size_t)h->max_smem_optin - 4096 ? 4 * (size_t)h->d1 : 0;
     p.stage = stage_bytes ? 1 : 0;
@@ -745,6 +844,7 @@ extern "C" int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint3
 extern "C" int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_histogram_per_replica: null buffer");
     CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
@@ -761,7 +861,7 @@ extern "C" int kmc_zobrist(kmc_engine *h, int bits, uint64_t seed, uint64_t *out
     cudaError_t e = cudaMemsetAsync(d_keys, 0, (size_t)h->R * sizeof(unsigned long long), h->stream);
     if (e == cudaSuccess) {
         const unsigned bx = (unsigned)std::min<long long>(((long long)h->n + 255) / 256, 64);
-        kmc_zobrist_kernel<<<dim3(bx, (unsigned)h->R), 256, 0, h->stream>>>(h->d_status, h->n, bits, seed, d_keys);
+        kmc_zobrist_kernel<<<dim3((unsigned)h->R, bx), 256, 0, h->stream>>>(h->d_status, h->n, bits, seed, d_keys);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_keys, (size_t)h->R * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream);
@@ -783,7 +883,8 @@ extern "C" int kmc_get_hops(kmc_engine *h, int64_t *out)
 
 extern "C" int kmc_get_histogram(kmc_engine *h, int64_t *out)
 {
-    std::vector<int64_t> tmp((size_t)(h ? h->R : 0) * NC);
+    if (!h || !out) return fail(KMC_ERR_ARG, "kmc_get_histogram: null argument");
+    std::vector<int64_t> tmp((size_t)h->R * NC);
     int rc = kmc_get_histogram_per_replica(h, tmp.data()); if (rc) return rc;
     for (int c = 0; c < NC; c++) out[c] = 0;
     for (int r = 0; r < h->R; r++) for (int c = 0; c < NC; c++) out[c] += tmp[(size_t)r * NC + c];
@@ -793,6 +894,7 @@ extern "C" int kmc_get_histogram(kmc_engine *h, int64_t *out)
 extern "C" int kmc_get_steps_done(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_steps_done: null buffer");
     CU(cudaMemcpyAsync(out, h->d_steps, (size_t)h->R * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
@@ -801,6 +903,7 @@ extern "C" int kmc_get_steps_done(kmc_engine *h, int64_t *out)
 extern "C" int kmc_get_ties(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_ties: null buffer");
     std::vector<int64_t> tmp(h->R);
     CU(cudaMemcpyAsync(tmp.data(), h->d_ties, tmp.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -818,7 +921,9 @@ extern "C" int kmc_reset_stats(kmc_engine *h)
     CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
+    CU(cudaMemsetAsync(h->d_anyflag, 0, sizeof(uint32_t), h->stream));
     if (h->d_clock) CU(cudaMemsetAsync(h->d_clock, 0, R * sizeof(double), h->stream));
+    if (h->d_tracer) CU(cudaMemsetAsync(h->d_tracer, 0, R * h->n * sizeof(uint32_t), h->stream));
     return KMC_OK;
 }
 
@@ -829,13 +934,84 @@ extern "C" int kmc_enable_clock(kmc_engine *h, int on)
         CU(cudaMalloc(&h->d_clock, (size_t)h->R * sizeof(double)));
         CU(cudaMemsetAsync(h->d_clock, 0, (size_t)h->R * sizeof(double), h->stream));
     }
-    h->clock_on = on != 0;
+    if (on < 0 || on > 2) return fail(KMC_ERR_ARG, "kmc_enable_clock: 0 off, 1 mean residence time, 2 stochastic");
+    h->clock_mode = on;
+    return KMC_OK;
+}
+
+extern "C" int kmc_enable_tracers(kmc_engine *h, int on)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (on && !h->d_tracer) {
+        CU(cudaMalloc(&h->d_tracer, (size_t)h->R * h->n * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_tracer, 0, (size_t)h->R * h->n * sizeof(uint32_t), h->stream));
+    }
+    h->tracer_on = on != 0;
+    return KMC_OK;
+}
+
+// sum over the divacancies of a replica of |displacement|^2 = da^2 + da*db + db^2 (axial hex coordinates, unit
+// lattice constant), and their number
+__global__ void __launch_bounds__(256) kmc_msd_kernel(const uint8_t *status, const uint32_t *tracer, int n,
+                                                     long long *sumsq, long long *count)
+{
+    const int rep = blockIdx.x;
+    const uint8_t *st = status + (size_t)rep * n;
+    const uint32_t *T = tracer + (size_t)rep * n;
+    long long sq = 0, cnt = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (st[i] == S_DIVAC) {
+            const uint32_t v = T[i];
+            const long long da = (short)(v & 0xFFFFu), db = (short)(v >> 16);
+            sq += da * da + da * db + db * db;
+            cnt += 1;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o); cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(sumsq + rep), (unsigned long long)sq);
+        atomicAdd(reinterpret_cast<unsigned long long *>(count + rep), (unsigned long long)cnt);
+    }
+}
+
+extern "C" int kmc_get_msd(kmc_engine *h, int64_t *sum_sq, int64_t *n_tracers)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!sum_sq || !n_tracers) return fail(KMC_ERR_ARG, "kmc_get_msd: null buffer");
+    if (!h->d_tracer) return fail(KMC_ERR_ARG, "kmc_get_msd: call kmc_enable_tracers first");
+    rc = ensure_bytes(h); if (rc) return rc;
+    long long *d_out = nullptr;
+    const size_t bytes = 2 * (size_t)h->R * sizeof(long long);
+    CU(cudaMalloc(&d_out, bytes));
+    cudaError_t e = cudaMemsetAsync(d_out, 0, bytes, h->stream);
+    if (e == cudaSuccess) {
+        kmc_msd_kernel<<<(unsigned)h->R, 256, 0, h->stream>>>(h->d_status, h->d_tracer, h->n, d_out, d_out + h->R);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sum_sq, d_out, bytes / 2, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n_tracers, d_out + h->R, bytes / 2, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, cudaGetErrorString(e));
+    h->launches += 1;
+    return KMC_OK;
+}
+
+// raw tracer table of one replica (parity / debug): [n] packed int16 pairs
+extern "C" int kmc_get_tracers(kmc_engine *h, int replica, uint32_t *out)
+{
+    int rc = bind(h); if (rc) return rc;
+    if (!out || replica < 0 || replica >= h->R) return fail(KMC_ERR_ARG, "kmc_get_tracers: bad argument");
+    if (!h->d_tracer) return fail(KMC_ERR_ARG, "kmc_get_tracers: call kmc_enable_tracers first");
+    CU(cudaMemcpyAsync(out, h->d_tracer + (size_t)replica * h->n, (size_t)h->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
 }
 
 extern "C" int kmc_get_clock(kmc_engine *h, double *out)
 {
     int rc = bind(h); if (rc) return rc;
+    if (!out) return fail(KMC_ERR_ARG, "kmc_get_clock: null buffer");
     if (!h->d_clock) return fail(KMC_ERR_ARG, "kmc_get_clock: call kmc_enable_clock first");
     CU(cudaMemcpyAsync(out, h->d_clock, (size_t)h->R * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -943,6 +1119,12 @@ extern "C" int kmc_set_sweep_kernel(kmc_engine *h, int variant)
     if (!h || variant < 0 || variant > 2)
         return fail(KMC_ERR_ARG, "variant must be 0 (auto), 1 (nibble/PRMT, one row per CTA pass) or 2 (byte-parallel)");
     h->sweep_variant = variant;
+    return KMC_OK;
+}
+extern "C" int kmc_set_sweep_double_buffer(kmc_engine *h, int on)
+{
+    if (!h) return fail(KMC_ERR_ARG, "null engine handle");
+    h->slots_double = on != 0;
     return KMC_OK;
 }
 extern "C" int kmc_set_replica_kernel(kmc_engine *h, int variant)

@@ -166,3 +166,11 @@ extern "C" void kmc_hostcheck_draw(uint64_t seed, uint32_t replica, uint64_t ste
 }
 
 extern "C" int kmc_hostcheck_rc_field(int c) { return rc_field(c); }
+
+// the stochastic clock's pieces as the host compiler builds them (same source as the device code)
+extern "C" double kmc_hostcheck_log(double x) { return kmc_log(x); }
+extern "C" double kmc_hostcheck_draw3(uint64_t seed, uint32_t replica, uint64_t step) { return kmc_draw3(seed, replica, step); }
+extern "C" double kmc_hostcheck_time_step(int mode, double total, uint64_t seed, uint32_t replica, uint64_t step)
+{
+    return kmc_time_step(mode, total, seed, replica, step);
+}

@@ -142,4 +142,50 @@ KMC_HD void kmc_draw(uint64_t seed, uint32_t replica, uint64_t step, double &u1,
     u2 = (double)((((uint64_t)c2 << 32) | c3) >> 11) * 0x1.0p-53;
 }
 
+// ---- stochastic KMC clock (extension) -----------------------------------------
+// The reference draws no time step (it logs total_rate "so that time can be reconstructed", README.md:36-37,
+// sim.py:138).  The BKL residence time of an event is dt = -ln(u3) / total_rate with a third uniform draw:
+//     (x0, x1, ..) = Philox4x32-10(counter = (step lo, step hi, seed hi, 3), key = (seed lo, replica))
+//     u3 = ((((x0 << 32) | x1) >> 11) + 1) * 2^-53        in (0, 1]  (never 0: ln stays finite)
+// kmc_log is a fixed sequence of IEEE fp64 +, -, *, / (no FMA contraction: --fmad=false here,
+// -ffp-contract=off in the oracle), so the device, the host and oracle/kmc_oracle.c produce the same bits;
+// it is within 2 ulp of the correctly rounded logarithm (tests/test_hostcheck.py).
+KMC_HD double kmc_draw3(uint64_t seed, uint32_t replica, uint64_t step) {
+    uint32_t c0 = (uint32_t)step, c1 = (uint32_t)(step >> 32), c2 = (uint32_t)(seed >> 32), c3 = 3u;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, replica);
+    return (double)(((((uint64_t)c0 << 32) | c1) >> 11) + 1ull) * 0x1.0p-53;
+}
+KMC_HD double kmc_log(double x) {
+    unsigned long long bits;
+#ifdef __CUDA_ARCH__
+    bits = (unsigned long long)__double_as_longlong(x);
+#else
+    __builtin_memcpy(&bits, &x, 8);
+#endif
+    int e = (int)(bits >> 52) - 1023;                       // x is a positive normal number
+    bits = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m;
+#ifdef __CUDA_ARCH__
+    m = __longlong_as_double((long long)bits);
+#else
+    __builtin_memcpy(&m, &bits, 8);
+#endif
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }    // m in (0.7071, 1.4143]
+    const double s = (m - 1.0) / (m + 1.0);                 // |s| <= 0.1716
+    const double z = s * s;
+    // ln m = 2 atanh s = 2 s (1 + z/3 + z^2/5 + ... + z^11/23), Horner from the top
+    double q = 1.0 / 23.0;
+    q = q * z + 1.0 / 21.0; q = q * z + 1.0 / 19.0; q = q * z + 1.0 / 17.0; q = q * z + 1.0 / 15.0;
+    q = q * z + 1.0 / 13.0; q = q * z + 1.0 / 11.0; q = q * z + 1.0 / 9.0;  q = q * z + 1.0 / 7.0;
+    q = q * z + 1.0 / 5.0;  q = q * z + 1.0 / 3.0;  q = q * z + 1.0;
+    const double lnm = (s + s) * q;
+    const double ed = (double)e;
+    return ed * 0x1.62e42fee00000p-1 + (ed * 0x1.a39ef35793c76p-33 + lnm);   // ln 2 = hi + lo, hi has 21 zero bits
+}
+// one event's time increment: mode 1 = mean residence time 1 / R, mode 2 = -ln(u3) / R
+KMC_HD double kmc_time_step(int mode, double total, uint64_t seed, uint32_t replica, uint64_t step) {
+    if (mode == 2) return (0.0 - kmc_log(kmc_draw3(seed, replica, step))) / total;
+    return 1.0 / total;
+}
+
 }  // namespace kmc

@@ -23,8 +23,11 @@ struct NoincParams {
     void *events;                        // [R][nsteps]
     long long nsteps, t;                 // this launch handles local step index t
     unsigned long long *steps_done, *hist, *ties, *hops;
-    uint32_t *flags;
+    uint32_t *flags, *any_flag;
+    const double *draws;                 // [R][nsteps][2] injected draws or nullptr (Philox)
     double *clock;                       // [R] or nullptr
+    int clock_mode;
+    uint32_t *tracer;                    // [R][n] or nullptr (see ReplicaParams)
     int stage;                           // 1: stage rows row-1 .. row+2 of the chosen row in shared memory (4 * d1 bytes)
 };
 
@@ -62,11 +65,24 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
     const int rep = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
-    if (p.flags[rep] & FLAG_ZERO_RATE) return;          // this replica already stopped (uniform)
+    const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
+    if (p.flags[rep] & FLAG_ZERO_RATE) {                // this replica already stopped (uniform): no event
+        if (threadIdx.x == 0) {
+            if (p.log_mode == KMC_LOG_FULL) {
+                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+                rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
+                rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
+            } else if (p.log_mode == KMC_LOG_COMPACT) {
+                kmc_event_compact e; e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE;
+                e.flags = 0; e.total_rate = 0.0;
+                reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
+            }
+        }
+        return;
+    }
     uint8_t *st = p.status + (size_t)rep * p.n;
     const uint32_t *rcg = p.rowcnt + (size_t)rep * d0 * RCG_STRIDE;
     const unsigned long long step = p.steps_done[rep];
-    const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
 
     if (tid < 32) {
         const int myc = lane < NC ? lane : 0;
@@ -74,7 +90,12 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
         const long long tot = lane < NC ? (long long)p.counts[(size_t)rep * NC + lane] : 0;
         double u1, u2;
-        kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
+        if (p.draws) {
+            const double2 u = *reinterpret_cast<const double2 *>(p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)p.t) * 2);
+            u1 = u.x; u2 = u.y;
+        } else {
+            kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
+        }
         const double w = __dmul_rn((double)tot, rate);
         PickState pstate = pick_state_init(lane);
         const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
@@ -93,6 +114,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
     if (s_zero) {
         if (tid == 0) {
             p.flags[rep] |= FLAG_ZERO_RATE;
+            atomicOr(p.any_flag, FLAG_ZERO_RATE);
             if (p.log_mode == KMC_LOG_FULL) {
                 kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
                 rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
@@ -202,6 +224,11 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int site = row * d1 + col;
         const int s0 = st[site];
         apply_move(st, d0, d1, row, col, slot, s0);
+        if (p.tracer) {
+            const MoveNodes m = move_nodes(row, col, slot, s0, d0, d1);
+            tracer_update(p.tracer + (size_t)rep * p.n, slot, m.na, site, m.ns0, m.a1 * d1 + m.b1, m.ns1,
+                          m.a2 * d1 + m.b2, m.ns2);
+        }
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
             rec->site = (uint32_t)site; rec->cls = (uint8_t)csel; rec->slot = (uint8_t)slot;
@@ -212,7 +239,8 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
             reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
         }
         p.steps_done[rep] = step + 1;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], __ddiv_rn(1.0, s_total));
+        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], kmc_time_step(p.clock_mode, s_total, p.seed,
+                                                                          p.replica0 + (uint32_t)rep, step));
         p.hist[(size_t)rep * NC + csel] += 1;
         if (slot >= 7 && slot < 13) p.hops[(size_t)rep * 6 + slot - 7] += 1;
         if (s_tie) p.ties[rep] += 1;
@@ -221,7 +249,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
 
 // KmcSim.perform_given_move (sim.py:145-157) for one explicit move; result[0] = 0 ok, 1 = the move
 // does not exist on the current lattice.
-__global__ void kmc_apply_given_kernel(uint8_t *st, int d0, int d1, int site, int slot, int *result)
+__global__ void kmc_apply_given_kernel(uint8_t *st, int d0, int d1, int site, int slot, int *result, uint32_t *tracer)
 {
     const int a = site / d1, b = site - a * d1;
     struct G { const uint8_t *p; __device__ int operator()(int k) const { return p[k]; } } S{st};
@@ -244,7 +272,13 @@ __global__ void kmc_apply_given_kernel(uint8_t *st, int d0, int d1, int site, in
         ok = s0 == 3 && t20 && (slot == 13 ? st[a * d1 + bp2] == 3 : st[ap2 * d1 + bm2] == 3);
         (void)f;
     } else ok = (slot == 15 && s0 == 4) || (slot == 16 && s0 == 7);
-    if (ok) apply_move(st, d0, d1, a, b, slot, s0);
+    if (ok) {
+        apply_move(st, d0, d1, a, b, slot, s0);
+        if (tracer) {
+            const MoveNodes m = move_nodes(a, b, slot, s0, d0, d1);
+            tracer_update(tracer, slot, m.na, site, m.ns0, m.a1 * d1 + m.b1, m.ns1, m.a2 * d1 + m.b2, m.ns2);
+        }
+    }
     result[0] = ok ? 0 : 1;
 }
 

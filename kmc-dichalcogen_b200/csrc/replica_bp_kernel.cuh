@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
     unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(lane);
-    double tclock = 0.0;
+    double tclock = p.clock ? p.clock[rep] : 0.0;          // continues across launches in event order
+    uint32_t *const tracer = p.tracer ? p.tracer + (size_t)rep * n : nullptr;
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
     const int my_j = lane / 6, my_k = lane % 6;
     DirConst my_dir = dir_const(my_k, d0);
@@ -331,7 +332,8 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             break;
         }
         const int csel = pick.csel;
-        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, pick.total));
+        if (p.clock) tclock = __dadd_rn(tclock, kmc_time_step(p.clock_mode, pick.total, p.seed, p.replica0 + (uint32_t)rep,
+                                                            step_base + (unsigned long long)t));
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
@@ -455,6 +457,8 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
         const int na = mv.na;
+        if (tracer && lane == 31)
+            tracer_update(tracer, slot, na, row * d1 + col, mv.ns0, mv.a1 * d1 + mv.b1, mv.ns1, mv.a2 * d1 + mv.b2, mv.ns2);
         // bit planes: lane q < 10 maintains plane q, as 32-bit halves (program order handles nodes
         // sharing a word): clear the site's bit, set it again if the new status belongs to this plane
         if (lane < N_PLANES) {
@@ -617,9 +621,9 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
+        if (p.clock) p.clock[rep] = tclock;
         p.ties[rep] += n_ties;
-        if (flag) p.flags[rep] |= flag;
+        if (flag) { p.flags[rep] |= flag; atomicOr(p.any_flag, flag); }
     }
 }
 

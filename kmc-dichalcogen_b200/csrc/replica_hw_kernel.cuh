@@ -279,7 +279,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     else if (my_g1) tot = hw_own_total(PL, d0, my_g1);
     uint32_t hist = 0, hops = 0, n_ties = 0;                 // per launch (a launch holds at most 2^30 events)
     PickState pstate = pick_state_init(hl);
-    double tclock = 0.0;
+    double *const clockp = PLAIN ? nullptr : p.clock;
+    double tclock = clockp ? clockp[rep] : 0.0;            // continues across launches in event order
+    uint32_t *const tracer = (PLAIN || !p.tracer) ? nullptr : p.tracer + (size_t)rep * n;
     // refresh roles: half-lanes 0..11 = direction hl % 6 of band rows 2*pass + hl / 6
     const int my_g = hl / 6, my_k = hl % 6;
     HwDir my_dir = hw_dir_const(my_k);
@@ -293,7 +295,6 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     const unsigned long long step_base = p.steps_done[rep];
     const int log_mode = PLAIN ? KMC_LOG_NONE : p.log_mode;
     const double *const draws = PLAIN ? nullptr : p.draws;
-    double *const clockp = PLAIN ? nullptr : p.clock;
     double mu1 = 0.0, mu2 = 0.0;
     const int nsteps = (int)p.nsteps;
     int t = 0;
@@ -372,9 +373,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     if (hl < 6) p.hops[(size_t)rep * 6 + hl] += hops;
     if (hl == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
-        if (clockp) clockp[rep] = __dadd_rn(clockp[rep], tclock);
+        if (clockp) clockp[rep] = tclock;
         p.ties[rep] += n_ties;
-        if (flag) p.flags[rep] |= flag;
+        if (flag) { p.flags[rep] |= flag; atomicOr(p.any_flag, flag); }
     }
 }
 

@@ -43,6 +43,7 @@ struct ReplicaParams {
     unsigned long long *hops;        // [R][6] MoveDivacancy events per direction k (slot 7 + k)
     unsigned long long *ties;        // [R]
     uint32_t *flags;                 // [R] bit0 zero-rate stop, bit1 validate mismatch
+    uint32_t *any_flag;              // OR of all replicas' flags (one word: the asynchronous status of the handle)
     int validate;
     // HBM-resident lattices only: the row-count hierarchy of each replica, kept between launches so that
     // a launch does not have to re-enumerate a 1 Mi-site lattice first.  hier_valid != 0: load it.
@@ -51,6 +52,10 @@ struct ReplicaParams {
     // optional KMC clock: t += 1 / total_rate per event (mean residence time; the reference has no clock
     // but logs total_rate for exactly this post-processing, README.md:36-37).  nullptr = off.
     double *clock;                   // [R]
+    int clock_mode;                  // 1: t += 1 / total_rate; 2: t += -ln(u3) / total_rate (kmc_common.cuh)
+    // optional divacancy tracers (extension): per site the unwrapped displacement
+    // (int16 da | int16 db << 16, axial) of the divacancy sitting there since it appeared.  nullptr = off.
+    uint32_t *tracer;                // [R][n]
 };
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -69,6 +74,26 @@ constexpr uint32_t RING_DB = (uint32_t)pack_nibbles({0, -1, -1, 0, 1, 1});
 constexpr unsigned long long REFRESH_DA = pack_nibbles({0, -1, 0, 1, 1, 0, -1, -2, 0, -2});
 constexpr unsigned long long REFRESH_DB = pack_nibbles({0, 0, -1, -1, 0, 1, 1, 0, -2, 2});
 constexpr uint32_t FLAG_ZERO_RATE = 1u, FLAG_VALIDATE = 2u;
+
+// Tracer bookkeeping for one event (uniform; executed by one lane).  A MoveDivacancy hop (slot 7 + k) carries
+// the displacement from the old site to the new one and adds neighbour k of neighbors_and_mutuals
+// (state.py:443-459); any other event that turns a site into a divacancy starts a new tracer at 0 there.
+// Entries of sites that hold no divacancy are stale and never read.
+__device__ __forceinline__ uint32_t tracer_step(int k) {
+    const int ri = kring(k);
+    const int da = (int)((RING_DA >> (4 * ri)) & 0xF) - 2, db = (int)((RING_DB >> (4 * ri)) & 0xF) - 2;
+    return ((uint32_t)da & 0xFFFFu) | ((uint32_t)db << 16);
+}
+__device__ __forceinline__ void tracer_update(uint32_t *T, int slot, int na, int site0, int ns0, int site1, int ns1,
+                                              int site2, int ns2) {
+    if (slot >= 7 && slot < 13) {
+        T[site1] = __vadd2(T[site0], tracer_step(slot - 7));
+    } else {
+        if (ns0 == S_DIVAC) T[site0] = 0u;
+        if (na > 1 && ns1 == S_DIVAC) T[site1] = 0u;
+        if (na > 2 && ns2 == S_DIVAC) T[site2] = 0u;
+    }
+}
 
 struct SmemStatus {
     const uint8_t *p;
@@ -400,7 +425,8 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     unsigned long long hist = 0, hops = 0;
     unsigned long long n_ties = 0;
     PickState pstate = pick_state_init(lane);
-    double tclock = 0.0;
+    double tclock = p.clock ? p.clock[rep] : 0.0;          // continues across launches in event order
+    uint32_t *const tracer = p.tracer ? p.tracer + (size_t)rep * n : nullptr;
 
     // per-lane role in the refresh: node index and one of 10 offsets
     const int my_i = lane / 10, my_o = lane % 10;
@@ -457,7 +483,8 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const int csel = pick.csel;
         const double total = pick.total;
         const uint32_t tie = pick.tie;
-        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, total));
+        if (p.clock) tclock = __dadd_rn(tclock, kmc_time_step(p.clock_mode, total, p.seed, p.replica0 + (uint32_t)rep,
+                                                            step_base + (unsigned long long)t));
 
         // ---- event record, part 1 (counts before the event) -------------------------------------
         if (p.log_mode == KMC_LOG_FULL) {
@@ -526,6 +553,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
         const int na = mv.na, a1 = mv.a1, b1 = mv.b1, a2 = mv.a2, b2 = mv.b2;
         const int ns0 = mv.ns0, ns1 = mv.ns1, ns2 = mv.ns2;
+        if (tracer && lane == 0) tracer_update(tracer, slot, na, site, ns0, a1 * d1 + b1, ns1, a2 * d1 + b2, ns2);
 
         // ---- 5. neighbourhood refresh -----------------------------------------------------------------
         const bool act = my_i < na;
@@ -619,9 +647,9 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
+        if (p.clock) p.clock[rep] = tclock;
         p.ties[rep] += n_ties;
-        if (flag) p.flags[rep] |= flag;
+        if (flag) { p.flags[rep] |= flag; atomicOr(p.any_flag, flag); }
     }
 }
 

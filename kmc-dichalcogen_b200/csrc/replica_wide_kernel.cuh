@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
     unsigned long long hist = 0, hops = 0, n_ties = 0;
     PickState pstate = pick_state_init(lane);
-    double tclock = 0.0;
+    double tclock = p.clock ? p.clock[rep] : 0.0;          // continues across launches in event order
+    uint32_t *const tracer = p.tracer ? p.tracer + (size_t)rep * p.n : nullptr;
     const uint32_t my_desc = task_desc(lane < 7 ? lane : 6);          // lane k < 7 holds the descriptor of task kind k
     const int r2 = B > 32 ? B >> 5 : 1;                 // rows per lane in the second level of the row search
 
@@ -347,7 +348,8 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             break;
         }
         const int csel = pick.csel;
-        if (p.clock) tclock = __dadd_rn(tclock, __ddiv_rn(1.0, pick.total));
+        if (p.clock) tclock = __dadd_rn(tclock, kmc_time_step(p.clock_mode, pick.total, p.seed, p.replica0 + (uint32_t)rep,
+                                                            step_base + (unsigned long long)t));
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
@@ -496,6 +498,8 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
         }
         const int na = mv.na;
+        if (tracer && lane == 31)
+            tracer_update(tracer, slot, na, row * d1 + col, mv.ns0, mv.a1 * d1 + mv.b1, mv.ns1, mv.a2 * d1 + mv.b2, mv.ns2);
         // lanes 0..5 own a plane each (the Z and D rows they rewrite were prefetched with the refresh rows)
         const int as[3] = {row, mv.a1, mv.a2}, bcol[3] = {col, mv.b1, mv.b2}, ns[3] = {mv.ns0, mv.ns1, mv.ns2};
         const int os[3] = {s0, os1, os2};
@@ -637,9 +641,9 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], tclock);
+        if (p.clock) p.clock[rep] = tclock;
         p.ties[rep] += n_ties;
-        if (flag) p.flags[rep] |= flag;
+        if (flag) { p.flags[rep] |= flag; atomicOr(p.any_flag, flag); }
     }
 }
 

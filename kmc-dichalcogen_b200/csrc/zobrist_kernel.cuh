@@ -19,14 +19,14 @@ KMC_HD unsigned long long zobrist_value(uint32_t site, uint32_t code, int bits, 
     return ((((unsigned long long)c0) << 32) | c1) >> (64 - bits);
 }
 
-// grid: (blocks per replica, n_replicas); out[rep] must be zero on entry
+// grid: (n_replicas, blocks per replica) -- replicas on grid.x, which has no 65535 limit; out[rep] must be zero on entry
 __global__ void kmc_zobrist_kernel(const uint8_t *status, int n, int bits, unsigned long long seed,
                                    unsigned long long *out)
 {
-    const int rep = blockIdx.y;
+    const int rep = blockIdx.x;
     const uint8_t *st = status + (size_t)rep * n;
     unsigned long long acc = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         const uint32_t s = st[i];
         if ((s >= 1 && s <= 4) || s == 7) acc ^= zobrist_value((uint32_t)i, s, bits, seed);
     }

@@ -153,7 +153,11 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
         eng.generate_state(gen["mode"], gen["params"], seed if state_seed is None else state_seed, replica0=lo)
     else:
         eng.upload_state(np.tile(init_state.status, (hi - lo, 1)))
-    eng.enable_clock(True)            # simulated time per replica: sum of 1 / total_rate (mean residence times)
+    # simulated time per replica: the BKL clock t += -ln(u3) / total_rate (a third Philox draw per event; the
+    # reference draws no time step but logs total_rate for this reconstruction, README.md:36-37), and one tracer
+    # per divacancy carrying its unwrapped displacement
+    eng.enable_clock("stochastic")
+    eng.enable_tracers(True)
     try:
         eng.run(nsteps, seed, replica0=lo, validate=True)
     except ValueError:
@@ -169,6 +173,8 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     sq = parallel.reduce_histogram(np.array([int((d[:, 0] ** 2 + d[:, 0] * d[:, 1] + d[:, 1] ** 2).sum())],
                                             dtype=np.int64), device=dev)
     time_sum = parallel.sum_over_ranks(float(eng.clock().sum()), device=dev)
+    tsq, tcnt = eng.msd()
+    tr = parallel.reduce_histogram(np.array([int(tsq.sum()), int(tcnt.sum())], dtype=np.int64), device=dev)
     eng.close()
     parallel.shutdown()
     if rank != 0:
@@ -181,9 +187,13 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
            # mean squared net displacement of a replica's divacancy population in axial lattice units
            "divacancy_hops": [int(x) for x in hops],
            "mean_squared_net_displacement": float(sq[0]) / replicas,
-           # simulated time per replica, averaged (the reference draws no time step; its log carries total_rate
-           # for exactly this reconstruction, README.md:36-37): sum over events of 1 / total_rate
-           "mean_time": time_sum / replicas}
+           # simulated time per replica, averaged: sum over events of -ln(u3) / total_rate
+           "mean_time": time_sum / replicas,
+           # tracer diffusion: mean squared displacement (lattice constants^2) of the divacancies present at the
+           # end, each measured from where it appeared (or from the initial lattice), and D = MSD / (4 t)
+           "tracers": int(tr[1]),
+           "msd": (float(tr[0]) / float(tr[1])) if tr[1] else None,
+           "D": (float(tr[0]) / float(tr[1]) / (4.0 * time_sum / replicas)) if tr[1] and time_sum > 0 else None}
     json.dump(out, ofile, indent=2, sort_keys=True)
     ofile.write("\n")
 

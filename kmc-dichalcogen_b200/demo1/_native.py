@@ -46,8 +46,10 @@ SYMBOLS = {
     "kmc_get_row_counts": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_run": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_int]),
     "kmc_step_draws": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int]),
+    "kmc_check_status": (C.c_int, [C.c_void_p]),
     "kmc_perform_given": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_int]),
     "kmc_run_noinc": (C.c_int, [C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p]),
+    "kmc_step_draws_noinc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "kmc_get_histogram": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_get_histogram_per_replica": (C.c_int, [C.c_void_p, C.c_void_p]),
     "kmc_zobrist": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]),
@@ -57,6 +59,9 @@ SYMBOLS = {
     "kmc_reset_stats": (C.c_int, [C.c_void_p]),
     "kmc_enable_clock": (C.c_int, [C.c_void_p, C.c_int]),
     "kmc_get_clock": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "kmc_enable_tracers": (C.c_int, [C.c_void_p, C.c_int]),
+    "kmc_get_msd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kmc_get_tracers": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "kmc_sync": (C.c_int, [C.c_void_p]),
     "kmc_flush_l2": (C.c_int, [C.c_void_p, C.c_size_t]),
     "kmc_probe_store_pattern": (C.c_int, [C.c_void_p]),
@@ -67,6 +72,7 @@ SYMBOLS = {
     "kmc_set_warps_per_block": (C.c_int, [C.c_void_p, C.c_int]),
     "kmc_set_replica_kernel": (C.c_int, [C.c_void_p, C.c_int]),
     "kmc_set_sweep_kernel": (C.c_int, [C.c_void_p, C.c_int]),
+    "kmc_set_sweep_double_buffer": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None

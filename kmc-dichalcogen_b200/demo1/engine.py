@@ -118,6 +118,22 @@ class Engine:
         nat.check(rc)
         return ev
 
+    def step_draws_noinc(self, draws, log_mode=nat.LOG_FULL):
+        draws = np.ascontiguousarray(draws, dtype=np.float64).reshape(self.n_replicas, -1, 2)
+        nsteps = draws.shape[1]
+        ev = self._events_buffer(nsteps, log_mode)
+        rc = self._lib.kmc_step_draws_noinc(self._h, draws.ctypes.data, nsteps, log_mode,
+                                            ev.ctypes.data if ev is not None else None)
+        self._last_events = ev
+        nat.check(rc)
+        return ev
+
+    def check_status(self):
+        """Wait for the queued launches and raise what they raised: ValueError when a replica stopped on a total
+        rate of zero (reference kmc.py:31-32), AssertionError on a validation mismatch.  The synchronous
+        counterpart of a statistics-only ``run`` (which returns as soon as the launch is queued)."""
+        nat.check(self._lib.kmc_check_status(self._h))
+
     def perform_given(self, replica, site, slot):
         nat.check(self._lib.kmc_perform_given(self._h, int(replica), int(site), int(slot)))
 
@@ -160,11 +176,33 @@ class Engine:
         nat.check(self._lib.kmc_get_ties(self._h, C.byref(v)))
         return v.value
 
-    def enable_clock(self, on=True):
-        nat.check(self._lib.kmc_enable_clock(self._h, int(bool(on))))
+    def enable_clock(self, mode=1):
+        """0 / False off, 1 / True mean residence time (sum of 1 / total_rate), 2 or "stochastic": the BKL clock
+        t += -ln(u3) / total_rate with a third Philox draw per event."""
+        mode = 2 if mode == "stochastic" else int(mode)
+        nat.check(self._lib.kmc_enable_clock(self._h, mode))
+
+    def enable_tracers(self, on=True):
+        """Track the unwrapped displacement of every divacancy (see include/kmc_b200.h)."""
+        nat.check(self._lib.kmc_enable_tracers(self._h, int(bool(on))))
+
+    def msd(self):
+        """(sum of squared tracer displacements, number of tracers) per replica, int64 each; the squared length
+        of an axial displacement (da, db) is da^2 + da*db + db^2 lattice constants^2."""
+        sq = np.empty(self.n_replicas, dtype=np.int64)
+        cnt = np.empty(self.n_replicas, dtype=np.int64)
+        nat.check(self._lib.kmc_get_msd(self._h, sq.ctypes.data, cnt.ctypes.data))
+        return sq, cnt
+
+    def tracers(self, replica=0):
+        """Raw tracer table of one replica as an (n, 2) int16 array of axial displacements (da, db); only the rows
+        of sites that currently hold a divacancy are meaningful."""
+        out = np.empty(self.n, dtype=np.uint32)
+        nat.check(self._lib.kmc_get_tracers(self._h, int(replica), out.ctypes.data))
+        return out.view(np.int16).reshape(self.n, 2)
 
     def clock(self):
-        """Per-replica KMC time (sum of 1/total_rate over the events done)."""
+        """Per-replica KMC time accumulated since the last reset_stats (see enable_clock)."""
         out = np.empty(self.n_replicas, dtype=np.float64)
         nat.check(self._lib.kmc_get_clock(self._h, out.ctypes.data))
         return out
@@ -206,6 +244,10 @@ class Engine:
     def set_replica_kernel(self, variant):
         """0 auto, 1 byte-lattice kernel, 2 bit-sliced kernel (rows of <= 64 sites)."""
         nat.check(self._lib.kmc_set_replica_kernel(self._h, int(variant)))
+
+    def set_sweep_double_buffer(self, on=True):
+        """Measurement helper: successive sweeps alternate between two slot-plane buffers."""
+        nat.check(self._lib.kmc_set_sweep_double_buffer(self._h, int(bool(on))))
 
     def set_sweep_kernel(self, variant):
         """Aligned-shape sweep kernel: 0 auto (rolling window for 4096-site rows), 1 nibble/PRMT, 2 byte-parallel."""

@@ -85,6 +85,11 @@ typedef struct {
     int64_t hist[NC];
     int64_t n_ties;
     int64_t steps_done;
+    /* extensions (the reference has neither, README.md:36-37): KMC clock and divacancy tracers */
+    int clock_mode;       /* 0 off, 1 t += 1/R, 2 t += -ln(u3)/R */
+    double clock;
+    uint64_t clk_seed, clk_step; uint32_t clk_replica;   /* Philox coordinates of the current event's u3 */
+    int32_t *trc;         /* [n][2] unwrapped axial displacement of the divacancy at each site, or NULL */
 } KmcOracle;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -172,13 +177,65 @@ KmcOracle *kmco_create(int d0, int d1, const double *rate, const int *order, int
 void kmco_destroy(KmcOracle *o)
 {
     if (!o) return;
-    free(o->status); free(o->slot); free(o->rowcnt); free(o);
+    free(o->status); free(o->slot); free(o->rowcnt); free(o->trc); free(o);
+}
+
+/* ---- extensions: clock and tracers (same definitions as kmc-dichalcogen_b200/csrc/kmc_common.cuh) ---- */
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1);
+/* u3 in (0, 1]: Philox counter domain 3 of the replica's stream */
+static double draw3(uint64_t seed, uint32_t replica, uint64_t step)
+{
+    uint32_t c[4] = {(uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(seed >> 32), 3u};
+    philox4x32_10(c, (uint32_t)seed, replica);
+    return (double)(((((uint64_t)c[0] << 32) | c[1]) >> 11) + 1ull) * 0x1.0p-53;
+}
+/* natural logarithm as a fixed sequence of IEEE fp64 operations (no libm: libm's and CUDA's log differ in the
+ * last bit; this one is the same everywhere).  Within 2 ulp of the correctly rounded value. */
+double kmco_log(double x)
+{
+    uint64_t bits; memcpy(&bits, &x, 8);
+    int e = (int)(bits >> 52) - 1023;
+    bits = (bits & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull;
+    double m; memcpy(&m, &bits, 8);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double s = (m - 1.0) / (m + 1.0);
+    const double z = s * s;
+    double q = 1.0 / 23.0;
+    q = q * z + 1.0 / 21.0; q = q * z + 1.0 / 19.0; q = q * z + 1.0 / 17.0; q = q * z + 1.0 / 15.0;
+    q = q * z + 1.0 / 13.0; q = q * z + 1.0 / 11.0; q = q * z + 1.0 / 9.0;  q = q * z + 1.0 / 7.0;
+    q = q * z + 1.0 / 5.0;  q = q * z + 1.0 / 3.0;  q = q * z + 1.0;
+    const double lnm = (s + s) * q;
+    const double ed = (double)e;
+    return ed * 0x1.62e42fee00000p-1 + (ed * 0x1.a39ef35793c76p-33 + lnm);
+}
+double kmco_draw3(uint64_t seed, uint32_t replica, uint64_t step) { return draw3(seed, replica, step); }
+void kmco_set_clock(KmcOracle *o, int mode) { o->clock_mode = mode; o->clock = 0.0; }
+double kmco_get_clock(const KmcOracle *o) { return o->clock; }
+void kmco_set_clock_key(KmcOracle *o, uint64_t seed, uint32_t replica) { o->clk_seed = seed; o->clk_replica = replica; }
+void kmco_enable_tracers(KmcOracle *o)
+{
+    if (!o->trc) o->trc = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)o->n);
+    memset(o->trc, 0, sizeof(int32_t) * 2 * (size_t)o->n);
+}
+/* per site (da, db), meaningful where the site holds a divacancy */
+void kmco_get_tracers(const KmcOracle *o, int32_t *out) { memcpy(out, o->trc, sizeof(int32_t) * 2 * (size_t)o->n); }
+/* sum over divacancies of da^2 + da*db + db^2, and their number */
+void kmco_get_msd(const KmcOracle *o, int64_t *sumsq, int64_t *count)
+{
+    int64_t sq = 0, c = 0;
+    for (int i = 0; i < o->n; i++)
+        if (o->status[i] == DIVAC) {
+            int64_t da = o->trc[2 * i], db = o->trc[2 * i + 1];
+            sq += da * da + da * db + db * db; c++;
+        }
+    *sumsq = sq; *count = c;
 }
 
 /* KmcSim.initialize(state): replace the lattice and re-enumerate everything (sim.py:46-68). */
 void kmco_set_status(KmcOracle *o, const uint8_t *status)
 {
     memcpy(o->status, status, (size_t)o->n);
+    if (o->trc) memset(o->trc, 0, sizeof(int32_t) * 2 * (size_t)o->n);      /* every divacancy is a new tracer */
     kmco_sweep(o->status, o->d0, o->d1, o->slot, o->count, o->rowcnt);
 }
 void kmco_get_status(const KmcOracle *o, uint8_t *out) { memcpy(out, o->status, (size_t)o->n); }
@@ -187,7 +244,11 @@ void kmco_get_counts(const KmcOracle *o, int64_t *out) { memcpy(out, o->count, s
 void kmco_get_hist(const KmcOracle *o, int64_t *out) { memcpy(out, o->hist, sizeof(int64_t) * NC); }
 int64_t kmco_get_ties(const KmcOracle *o) { return o->n_ties; }
 int64_t kmco_get_steps(const KmcOracle *o) { return o->steps_done; }
-void kmco_reset_stats(KmcOracle *o) { memset(o->hist, 0, sizeof o->hist); o->n_ties = 0; o->steps_done = 0; }
+void kmco_reset_stats(KmcOracle *o)
+{
+    memset(o->hist, 0, sizeof o->hist); o->n_ties = 0; o->steps_done = 0; o->clock = 0.0;
+    if (o->trc) memset(o->trc, 0, sizeof(int32_t) * 2 * (size_t)o->n);
+}
 
 /* Re-derive slots [j0, j1) at one site and fold the difference into the counts.
  * (clear_move before the mutation + add_move after it, collapsed: sim.py:149-157.) */
@@ -226,7 +287,19 @@ static void refresh_after(KmcOracle *o, const int (*nodes)[2], int n_nodes)
 }
 
 /* Rule.perform for the move in (site, slot); returns the affected nodes (nodes_affected_by). */
+static int perform_move(KmcOracle *o, int site, int slot, int nodes[3][2]);
+/* + tracers: a site that BECOMES a divacancy by anything but a hop starts a new tracer at displacement 0 */
 static int perform(KmcOracle *o, int site, int slot, int nodes[3][2])
+{
+    int nn = perform_move(o, site, slot, nodes);
+    if (o->trc && !(slot >= 7 && slot <= 12))
+        for (int i = 0; i < nn; i++) {
+            int j = nodes[i][0] * o->d1 + nodes[i][1];
+            if (o->status[j] == DIVAC) { o->trc[2 * j] = 0; o->trc[2 * j + 1] = 0; }
+        }
+    return nn;
+}
+static int perform_move(KmcOracle *o, int site, int slot, int nodes[3][2])
 {
     int d0 = o->d0, d1 = o->d1;
     int a = site / d1, b = site % d1;
@@ -242,6 +315,10 @@ static int perform(KmcOracle *o, int site, int slot, int nodes[3][2])
         int na = wrapi(a + NBR[k][0], d0), nb = wrapi(b + NBR[k][1], d1);
         s[site] = PRISTINE; s[na * d1 + nb] = DIVAC;
         nodes[1][0] = na; nodes[1][1] = nb;
+        if (o->trc) {                                              /* the hop carries the tracer along */
+            o->trc[2 * (na * d1 + nb)] = o->trc[2 * site] + NBR[k][0];
+            o->trc[2 * (na * d1 + nb) + 1] = o->trc[2 * site + 1] + NBR[k][1];
+        }
         return 2;
     }
     int o_ = (slot - 13) & 1, create = slot < 15;                  /* trefoils (rules.py:143-146,178-181) */
@@ -352,6 +429,9 @@ int kmco_step(KmcOracle *o, double u1, double u2, KmcoEvent *ev)
     }
     o->n_ties += tie;
     o->hist[c]++;
+    if (o->clock_mode == 1) o->clock = o->clock + 1.0 / total;
+    else if (o->clock_mode == 2)
+        o->clock = o->clock + (0.0 - kmco_log(draw3(o->clk_seed, o->clk_replica, o->clk_step))) / total;
     o->steps_done++;
 
     int nodes[3][2];
@@ -438,8 +518,10 @@ void kmco_draw(uint64_t seed, uint32_t replica, uint64_t step, double *u1, doubl
  * (stops early when the total weight is zero). */
 int64_t kmco_run_draws(KmcOracle *o, const double *u, int64_t nsteps, KmcoEvent *ev)
 {
-    for (int64_t t = 0; t < nsteps; t++)
+    for (int64_t t = 0; t < nsteps; t++) {
+        o->clk_step = (uint64_t)o->steps_done;       /* injected draws: u3 from (seed, replica) set by kmco_set_clock_key */
         if (kmco_step(o, u[2 * t], u[2 * t + 1], ev ? ev + t : NULL)) return t;
+    }
     return nsteps;
 }
 
@@ -449,6 +531,7 @@ int64_t kmco_run_philox(KmcOracle *o, uint64_t seed, uint32_t replica, uint64_t 
     for (int64_t t = 0; t < nsteps; t++) {
         double u1, u2;
         kmco_draw(seed, replica, step0 + (uint64_t)t, &u1, &u2);
+        o->clk_seed = seed; o->clk_replica = replica; o->clk_step = step0 + (uint64_t)t;
         if (kmco_step(o, u1, u2, ev ? ev + t : NULL)) return t;
     }
     return nsteps;

@@ -65,6 +65,17 @@ def lib():
         L.kmco_run_replicas.argtypes = [C.c_int, C.c_int, P(C.c_double), P(C.c_int), C.c_int, C.c_void_p,
                                         C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int64,
                                         C.c_void_p, C.c_int]
+        L.kmco_log.restype = C.c_double
+        L.kmco_log.argtypes = [C.c_double]
+        L.kmco_draw3.restype = C.c_double
+        L.kmco_draw3.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+        L.kmco_set_clock.argtypes = [C.c_void_p, C.c_int]
+        L.kmco_get_clock.restype = C.c_double
+        L.kmco_get_clock.argtypes = [C.c_void_p]
+        L.kmco_set_clock_key.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.kmco_enable_tracers.argtypes = [C.c_void_p]
+        L.kmco_get_tracers.argtypes = [C.c_void_p, C.c_void_p]
+        L.kmco_get_msd.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
         assert L.kmco_event_size() == EVENT_DTYPE.itemsize
         _lib = L
     return _lib
@@ -89,6 +100,15 @@ def sweep(status, dim):
     rowcnt = np.zeros((d0, NC), dtype=np.int32)
     lib().kmco_sweep(status.ctypes.data, d0, d1, slots.ctypes.data, counts.ctypes.data, rowcnt.ctypes.data)
     return slots, counts, rowcnt
+
+
+def log(x):
+    """The engine's deterministic fp64 logarithm (kmc_common.cuh:kmc_log restated in kmc_oracle.c)."""
+    return float(lib().kmco_log(float(x)))
+
+
+def draw3(seed, replica, step):
+    return float(lib().kmco_draw3(int(seed), int(replica), int(step)))
 
 
 def draw(seed, replica, step):
@@ -166,6 +186,31 @@ class Oracle:
         s, j = C.c_int(), C.c_int()
         rc = lib().kmco_rank_to_move_scan(self._h, int(cls), int(rank), C.byref(s), C.byref(j))
         return rc, s.value, j.value
+
+    # -- extensions: KMC clock and divacancy tracers (same definitions as the CUDA engine) -----------
+    def set_clock(self, mode):
+        """1: t += 1/total_rate; 2: t += -ln(u3)/total_rate (u3 = third Philox draw of the event)."""
+        lib().kmco_set_clock(self._h, int(mode))
+
+    def set_clock_key(self, seed, replica):
+        """Philox key of u3 when the class / in-class draws are injected (run_draws)."""
+        lib().kmco_set_clock_key(self._h, int(seed), int(replica))
+
+    def clock(self):
+        return float(lib().kmco_get_clock(self._h))
+
+    def enable_tracers(self):
+        lib().kmco_enable_tracers(self._h)
+
+    def tracers(self):
+        out = np.empty((self.n, 2), dtype=np.int32)
+        lib().kmco_get_tracers(self._h, out.ctypes.data)
+        return out
+
+    def msd(self):
+        sq, cnt = C.c_int64(), C.c_int64()
+        lib().kmco_get_msd(self._h, C.byref(sq), C.byref(cnt))
+        return sq.value, cnt.value
 
     def validate(self):
         """0 when the incremental tables equal a from-scratch enumeration (sim.py:159-168)."""

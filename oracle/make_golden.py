@@ -16,6 +16,7 @@ which must reproduce every event (class, site, slot), the fsum total rate, and t
 bit for bit.
 """
 import json
+import math
 import os
 import random
 import sys
@@ -235,8 +236,88 @@ def animate_replay_fixture():
     np.savez_compressed(path, meta=json.dumps(metas), **out)
 
 
+def _tie_draw(stepper, want_index):
+    """A class draw u1 in [0, 1) for which ``random.uniform(0, total)`` (kmc.py:49: 0 + (total - 0) * u1) lands
+    EXACTLY on the ``want_index``-th cumulative weight of weighted_choice's sorted list (kmc.py:35-42), or None
+    when no double does.  The candidates are the doubles next to cum / total."""
+    counts = stepper.counts()
+    rates = stepper.rates()
+    ws = sorted(w for w in (counts[c] * rates[c] for c in stepper.class_order()) if w != 0.0)
+    cum, acc = [], 0
+    for w in ws:
+        acc = acc + w
+        cum.append(acc)
+    if want_index >= len(cum) - 1:          # the last boundary needs u1 == 1: not a draw
+        return None
+    total, target = cum[-1], cum[want_index]
+    u = target / total
+    for _ in range(4):
+        u = math.nextafter(u, 0.0)
+    for _ in range(9):
+        if 0.0 <= u < 1.0 and 0.0 + (total - 0.0) * u == target:
+            return u
+        u = math.nextafter(u, 2.0)
+    return None
+
+
+def boundary_tie_trajectory(name, dim, rules, status0, seed, nsteps, every=3):
+    """north star: "trajectories that diverge only at a cumulative-rate boundary tie are reported and counted".
+    Philox draws, except that every ``every``-th step the class draw is replaced by one that puts x exactly on a
+    cumulative-weight boundary (cycling over the boundaries), and a few steps use the extreme draws u1 = 0 and
+    u1 = 1 - 2**-53.  The reference's own bisect_left (kmc.py:50) decides each of them; n_ties > 0."""
+    st = ref_oracle.RefStepper(list(map(int, status0)), dim, rules)
+    d = philox.draws(seed, 0, 0, nsteps).copy()
+    ev = np.zeros(nsteps, dtype=[("cls", "u1"), ("slot", "u1"), ("site", "<u4"), ("total_rate", "<f8")])
+    tie_steps = []
+    counts0 = st.counts()
+    for t in range(nsteps):
+        if t % every == 0:
+            u = _tie_draw(st, (t // every) % 5)
+            if u is None:
+                u = _tie_draw(st, 0)
+            if u is not None:
+                d[t, 0] = u
+        elif t % 50 == 1:
+            d[t, 0] = 0.0
+        elif t % 50 == 2:
+            d[t, 0] = 1.0 - 2.0 ** -53
+        before = st.n_ties
+        r = st.step(float(d[t, 0]), float(d[t, 1]))
+        if st.n_ties > before:
+            tie_steps.append(t)
+        ev[t] = (r["class"], r["slot"], r["site"], r["total_rate"])
+    with ref_oracle.ref_modules():
+        st.validate()
+    assert st.n_ties > 0 and st.n_ties == len(tie_steps)
+    meta = {"name": name, "dim": list(dim), "seed": seed, "replica": 0, "nsteps": nsteps, "temperature": None,
+            "rules": rules, "rule_order": list(rules), "class_order": st.class_order(), "n_ties": st.n_ties,
+            "tie_steps": tie_steps, "injected_draws": True,
+            "source": "unmodified /root/reference/demo1 driven by oracle/ref_oracle.py with injected draws"}
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(
+        path, meta=json.dumps(meta), rates=np.array(st.rates(), dtype=np.float64), draws=d,
+        status0=np.asarray(status0, dtype=np.uint8), events=ev, counts0=np.array(counts0, dtype=np.int64),
+        status1=np.array(st.status(), dtype=np.uint8), counts1=np.array(st.counts(), dtype=np.int64),
+        slots1=np.array(st.slot_table(), dtype=np.uint8))
+    print("%-28s dim=%s steps=%d boundary ties=%d (%d bytes)" % (name, dim, nsteps, st.n_ties, os.path.getsize(path)))
+
+
+def boundary_tie_fixtures():
+    # equal class weights on a pristine start (two weights of 770 -> u1 = 0.5 is a boundary), then mixed
+    boundary_tie_trajectory("boundary_ties_7x11", (7, 11), TIE_RULES, np.zeros(77, np.uint8), seed=31, nsteps=600)
+    # rows wider than 64 sites: also runs on the wide bit-plane kernel
+    boundary_tie_trajectory("boundary_ties_5x70", (5, 70), ALL_RULES, exact_state((5, 70), 0.2, 0.1, 4), seed=32,
+                            nsteps=600)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1:                     # regenerate only the named groups, e.g. `make_golden.py boundary_ties`
+        for g in sys.argv[1:]:
+            {"boundary_ties": boundary_tie_fixtures, "state_gen": state_gen_fixtures,
+             "state_gen_philox": state_gen_philox_fixtures, "zobrist": zobrist_reference_fixture,
+             "animate": animate_replay_fixture, "native_stats": native_statistics}[g]()
+        return
     # 1. all eight rules, pristine start: trefoils are created and destroyed along the way
     trajectory("allrules_8x8", (8, 8), ALL_RULES, np.zeros(64, np.uint8), seed=7, nsteps=3000)
     # 2. the reference's own test-cfg.yaml rule set, ragged odd dims
@@ -265,6 +346,7 @@ def main():
     trajectory("testcfg_200x200", (200, 200), TEST_CFG_RULES, np.zeros(40000, np.uint8), seed=20261019, nsteps=3000)
     # 8. rows wider than 64 sites with a ragged last word (the wide bit-plane kernel's layout), trefoils live
     trajectory("allrules_12x130", (12, 130), ALL_RULES, exact_state((12, 130), 0.2, 0.1, 8), seed=13, nsteps=2500, replica=1)
+    boundary_tie_fixtures()
     state_gen_fixtures()
     state_gen_philox_fixtures()
     zobrist_reference_fixture()

@@ -48,6 +48,19 @@ def draws(seed, replica, step0, nsteps):
     return np.stack([u1, u2], axis=1)
 
 
+def draws3(seed, replica, step0, nsteps):
+    """u3 in (0, 1] for steps step0 .. step0+nsteps-1: the clock draw of the stochastic KMC clock,
+    counter domain 3 of the same stream: ((((x0 << 32) | x1) >> 11) + 1) * 2**-53."""
+    seed = int(seed)
+    steps = np.arange(step0, step0 + nsteps, dtype=np.uint64)
+    x0, x1, _, _ = philox4x32_10(
+        steps & MASK, steps >> np.uint64(32),
+        np.full(nsteps, seed >> 32, dtype=np.uint64), np.full(nsteps, 3, dtype=np.uint64),
+        np.full(nsteps, seed & 0xFFFFFFFF, dtype=np.uint64),
+        np.full(nsteps, int(replica) & 0xFFFFFFFF, dtype=np.uint64))
+    return ((((x0 << np.uint64(32)) | x1) >> np.uint64(11)) + np.uint64(1)).astype(np.float64) * 2.0 ** -53
+
+
 import random as _random
 
 

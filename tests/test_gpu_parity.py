@@ -11,7 +11,7 @@ import pytest
 
 from util_cases import (ko, philox, ALL_ORDER, TEST_RATES, WSE2_ORDER, wse2_rates, exact_state,
                         evolved_state, iid_state)
-from util_golden import load, trajectory_names, enabled_classes
+from util_golden import load, trajectory_names, boundary_tie_names, enabled_classes
 from demo1 import _native as nat
 from demo1.engine import Engine
 
@@ -91,6 +91,37 @@ def test_golden_trajectory_injected_draws(name):
     ev2 = eng.step_draws(d[half:], log_mode=nat.LOG_COMPACT, validate=True)[0]
     ev = np.concatenate([ev1, ev2])
     assert_events_equal(ev, g["events"], name)
+    assert (eng.download_state()[0] == g["status1"]).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, "noinc"])
+@pytest.mark.parametrize("name", boundary_tie_names())
+def test_boundary_ties_on_every_kernel(name, variant):
+    """north star: "trajectories that diverge only at a cumulative-rate boundary tie are reported and counted".
+    The fixtures (made from the unmodified reference, oracle/make_golden.py:boundary_tie_trajectory) place a
+    third of the class draws EXACTLY on a cumulative weight, where the reference's bisect_left (kmc.py:50) takes
+    the class whose cumulative weight equals x.  Every kernel must take the same class, flag the event and
+    count the tie."""
+    g = load(name)
+    m = g["meta"]
+    d1 = m["dim"][1]
+    if (variant in (2, 4) and d1 > 64) or (variant == 5 and d1 <= 64):
+        pytest.skip("kernel variant does not take this row length")
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.upload_state(g["status0"])
+    if variant == "noinc":
+        ev = eng.step_draws_noinc(g["draws"], log_mode=nat.LOG_FULL)[0]
+    else:
+        eng.set_replica_kernel(variant)
+        half = m["nsteps"] // 2 + 3
+        ev = np.concatenate([eng.step_draws(g["draws"][:half], log_mode=nat.LOG_FULL, validate=True)[0],
+                             eng.step_draws(g["draws"][half:], log_mode=nat.LOG_FULL, validate=True)[0]])
+    assert_events_equal(ev, g["events"], name)
+    got = fsum_totals(ev, g["rates"], m["class_order"])
+    assert (got.view(np.uint64) == g["events"]["total_rate"].view(np.uint64)).all()
+    assert np.nonzero(ev["flags"] & 1)[0].tolist() == m["tie_steps"]
+    assert m["n_ties"] > 100 and eng.ties() == m["n_ties"]
     assert (eng.download_state()[0] == g["status1"]).all()
     eng.close()
 
@@ -248,8 +279,8 @@ def test_wide_kernel_stops_on_zero_total_rate():
 
 @pytest.mark.parametrize("variant", [1, 2, 4])
 def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
-    """Extension: t = sum 1/total_rate, accumulated in event order, bit-equal to the
-    same sum over the logged totals; across two launches and for the no-incremental path."""
+    """Extension: t = sum 1/total_rate, accumulated in event order ACROSS launches, bit-equal
+    to the same sum over the logged totals; and for the no-incremental path."""
     dim, nrep = (16, 20) if variant == 1 else (64, 64), 3
     st0 = np.stack([exact_state(dim, 0.1, 0.1, 7 + r) for r in range(nrep)])
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
@@ -260,11 +291,8 @@ def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
     got = eng.clock()
     for r in range(nrep):
         t = 0.0
-        for n0, n1 in ((0, 700), (700, 1000)):
-            part = 0.0
-            for x in ev[r]["total_rate"][n0:n1]:
-                part += 1.0 / float(x)
-            t += part
+        for x in ev[r]["total_rate"]:
+            t += 1.0 / float(x)
         assert got[r] == t
     ev2 = eng.run_noinc(50, 3, log_mode=nat.LOG_COMPACT)
     got2 = eng.clock()
@@ -274,6 +302,69 @@ def test_kmc_clock_is_the_sum_of_inverse_total_rates(variant):
             t += 1.0 / float(x)
         assert got2[r] == t
     eng.close()
+
+
+@pytest.mark.parametrize("variant,dim", [(1, (33, 47)), (2, (64, 64)), (3, (16, 80)), (4, (64, 64)), (4, (9, 24)),
+                                         (5, (24, 128)), ("noinc", (20, 36))])
+def test_stochastic_clock_and_tracers_match_the_oracle(variant, dim):
+    """the BKL clock t += -ln(u3) / total_rate (third Philox draw per event, deterministic
+    fp64 logarithm) is BIT-equal to the oracle's on every kernel, across launches; the divacancy tracers
+    (unwrapped displacement carried through MoveDivacancy hops, reset when a divacancy appears) and the summed
+    squared displacement are integer-exact.  Hot WSe2 rates: trefoils form and break, so tracers are born and die."""
+    import math
+    nrep, seed = 3, 77
+    rates, order = wse2_rates(4000.0), WSE2_ORDER
+    st0 = np.stack([exact_state(dim, 0.30, 0.05, 40 + r) for r in range(nrep)])
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    if variant != "noinc":
+        eng.set_replica_kernel(variant)
+    eng.enable_clock("stochastic")
+    eng.enable_tracers()
+    eng.upload_state(st0)
+    chunks = (60, 40) if variant == "noinc" else (1500, 1, 999)
+    for nsteps in chunks:
+        if variant == "noinc":
+            eng.run_noinc(nsteps, seed, replica0=5)
+        else:
+            eng.run(nsteps, seed, replica0=5, validate=True)
+    t = eng.clock()
+    sq, cnt = eng.msd()
+    final = eng.download_state()
+    for r in range(nrep):
+        o = ko.Oracle(dim, rates, order, st0[r])
+        o.enable_tracers()
+        o.set_clock(2)
+        o.run_philox(seed, 5 + r, 0, sum(chunks), log=False)
+        assert (final[r] == o.status()).all()
+        assert t[r] == o.clock() and t[r] > 0, (t[r], o.clock())
+        div = final[r] == 3
+        assert (eng.tracers(r)[div] == o.tracers()[div]).all()
+        assert (int(sq[r]), int(cnt[r])) == o.msd()
+        assert cnt[r] == div.sum()
+    assert sq.sum() > 0
+    # reset_stats restarts clock and tracers; a replaced lattice restarts the tracers
+    eng.reset_stats()
+    assert (eng.clock() == 0).all() and (eng.msd()[0] == 0).all()
+    eng.close()
+
+
+def test_mean_residence_clock_and_stochastic_clock_agree_on_average():
+    """E[-ln u3] = 1: over many replicas the stochastic clock averages to the mean-residence clock."""
+    dim, nrep, nsteps = (64, 64), 512, 400
+    rates, order = wse2_rates(1500.0), WSE2_ORDER
+    st0 = np.tile(exact_state(dim, 0.05, 0.05, 3), (nrep, 1))
+    out = []
+    for mode in (1, 2):
+        eng = Engine(dim, rates, order, n_replicas=nrep)
+        eng.enable_clock(mode)
+        eng.upload_state(st0)
+        eng.run(nsteps, 11)
+        eng.check_status()
+        out.append(eng.clock())
+        eng.close()
+    mean, stoch = out
+    assert abs(stoch.mean() / mean.mean() - 1.0) < 4.0 / np.sqrt(nrep * nsteps)
+    assert stoch.std() > 2 * mean.std()
 
 
 def test_stats_only_mode_equals_logged_mode():
@@ -372,6 +463,80 @@ def test_zero_total_rate_raises_value_error():
     assert eng.steps_done()[0] == 2
     assert (eng.download_state() == 0).all()
     eng.close()
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4, 5])
+def test_statistics_only_launch_reports_a_stop_through_check_status(variant):
+    """include/kmc_b200.h: a statistics-only kmc_run is asynchronous and returns KMC_OK; the zero-rate stop
+    (reference: ValueError, kmc.py:31-32) is reported by the next kmc_check_status, stays raised until the
+    lattice is replaced, and does not leak into a run on a new lattice."""
+    dim = (8, 128) if variant == 5 else (8, 8)
+    n = dim[0] * dim[1]
+    rates = [0.0] * 13
+    rates[1] = 5.0                                   # FillDivacancy only: the lattice drains
+    a = np.zeros(n, np.uint8); a[[3, 17]] = 3
+    b = np.zeros(n, np.uint8); b[::2] = 3
+    eng = Engine(dim, rates, [1], n_replicas=2)
+    eng.set_replica_kernel(variant)
+    eng.upload_state(np.stack([a, b]))
+    eng.run(20, 7)                                   # KMC_LOG_NONE, no validation: returns once queued
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.check_status()
+    with pytest.raises(ValueError, match="replica 0"):
+        eng.check_status()                           # still raised
+    assert list(eng.steps_done()) == [2, 20]
+    # a new lattice starts with a clean status: the old stop must not fail (or short-circuit) this run
+    eng.upload_state(np.stack([b, b]))
+    ev = eng.run(10, 7, log_mode=nat.LOG_COMPACT)
+    eng.check_status()
+    assert (ev["cls"] == 1).all()
+    assert ((eng.download_state() == 3).sum(axis=1) == n // 2 - 10).all()
+    eng.close()
+
+
+def test_no_incremental_path_after_a_stop_on_an_earlier_lattice():
+    """kmc_noinc_select_apply_kernel returns at entry when the replica's zero-rate flag is set; the
+    flag must be cleared with the lattice, and records of steps that never ran must read CLASS_NONE."""
+    dim = (9, 11)
+    rates = [0.0] * 13
+    rates[1] = 5.0
+    a = np.zeros(99, np.uint8); a[[3, 17]] = 3
+    b = np.zeros(99, np.uint8); b[::3] = 3
+    eng = Engine(dim, rates, [1])
+    eng.upload_state(a)
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.run_noinc(6, 5, log_mode=nat.LOG_COMPACT)
+    ev = eng._last_events[0]
+    assert list(ev["cls"]) == [1, 1, 0xFF, 0xFF, 0xFF, 0xFF]            # no stale records after the stop
+    assert (ev["site"][2:] == 0xFFFFFFFF).all()
+    eng.upload_state(b)
+    ev = eng.run_noinc(6, 5, log_mode=nat.LOG_COMPACT)[0]
+    assert (ev["cls"] == 1).all() and (eng.download_state()[0] == 3).sum() == 33 - 6
+    o = ko.Oracle(dim, rates, [1], b)
+    _, want = o.run_philox(5, 0, 2, 6)               # the step counter kept running: 2 events were done before
+    assert_events_equal(ev, want, "noinc after stop")
+    eng.close()
+
+
+def test_event_records_after_a_stop_are_class_none():
+    """records past a replica's stop must not carry an earlier launch's data."""
+    rates = [0.0] * 13
+    rates[1] = 5.0
+    full = np.zeros(64, np.uint8); full[::2] = 3
+    few = np.zeros(64, np.uint8); few[[1, 9]] = 3
+    for variant in (1, 2, 4):
+        eng = Engine((8, 8), rates, [1], n_replicas=2)
+        eng.set_replica_kernel(variant)
+        eng.upload_state(np.stack([full, full]))
+        eng.run(16, 3, log_mode=nat.LOG_FULL)                 # fills the device event buffer with real records
+        eng.upload_state(np.stack([few, full]))
+        with pytest.raises(ValueError):
+            eng.run(16, 3, log_mode=nat.LOG_FULL)
+        ev = eng._last_events
+        assert (ev[0]["cls"][:2] == 1).all() and (ev[0]["cls"][2:] == 0xFF).all(), variant
+        assert (ev[0]["site"][2:] == 0xFFFFFFFF).all(), variant
+        assert (ev[1]["cls"] == 1).all()
+        eng.close()
 
 
 @pytest.mark.parametrize("variant", [2, 4])

@@ -74,3 +74,23 @@ def test_row_count_field_map_is_a_bijection(lib):
     lib.kmc_hostcheck_rc_field.argtypes = [C.c_int]
     fields = [lib.kmc_hostcheck_rc_field(c) for c in range(13)]
     assert len(set(fields)) == 13 and max(fields) < 14 and min(fields) >= 0
+
+
+def test_clock_pieces_match_the_oracle_bit_for_bit(lib):
+    """kmc_common.cuh:kmc_log / kmc_draw3 / kmc_time_step as compiled for the host == oracle/kmc_oracle.c."""
+    import math
+    lib.kmc_hostcheck_log.restype = C.c_double
+    lib.kmc_hostcheck_log.argtypes = [C.c_double]
+    lib.kmc_hostcheck_draw3.restype = C.c_double
+    lib.kmc_hostcheck_draw3.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
+    lib.kmc_hostcheck_time_step.restype = C.c_double
+    lib.kmc_hostcheck_time_step.argtypes = [C.c_int, C.c_double, C.c_uint64, C.c_uint32, C.c_uint64]
+    rng = np.random.default_rng(9)
+    for x in np.concatenate([rng.random(5000), [1.0, 2.0 ** -53, 0.5, 1.0 - 2.0 ** -53, 0.7071067811865476]]):
+        if x > 0:
+            assert lib.kmc_hostcheck_log(float(x)) == ko.log(float(x))
+    for seed, rep, step in [(0, 0, 0), (20261019, 7, 123), ((1 << 45) + 3, 4000000000, (1 << 35) + 9)]:
+        u3 = lib.kmc_hostcheck_draw3(seed, rep, step)
+        assert u3 == ko.draw3(seed, rep, step) == philox.draws3(seed, rep, step, 1)[0]
+        assert lib.kmc_hostcheck_time_step(2, 3.5e-5, seed, rep, step) == (0.0 - ko.log(u3)) / 3.5e-5
+        assert lib.kmc_hostcheck_time_step(1, 3.5e-5, seed, rep, step) == 1.0 / 3.5e-5

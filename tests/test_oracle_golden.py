@@ -11,7 +11,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
 import kmc_oracle as ko  # noqa: E402
 import philox  # noqa: E402
-from util_golden import GOLDEN, load, trajectory_names, enabled_classes  # noqa: E402
+from util_golden import GOLDEN, load, trajectory_names, boundary_tie_names, enabled_classes  # noqa: E402
 
 
 def test_philox_known_answers():
@@ -60,6 +60,25 @@ def test_trajectory_matches_reference(name):
     assert rel.max() < 1e-12
 
 
+@pytest.mark.parametrize("name", boundary_tie_names())
+def test_boundary_ties_resolve_like_the_reference_bisect(name):
+    """x == cumulative weight exactly (kmc.py:47-50: uniform(0, total) then bisect_left): the reference picks the
+    class whose cumulative weight EQUALS x.  Every such draw is counted (north star: ties are reported)."""
+    g = load(name)
+    m = g["meta"]
+    assert m["n_ties"] > 100
+    o = ko.Oracle(m["dim"], g["rates"], m["class_order"], g["status0"])
+    done, ev = o.run_draws(g["draws"])
+    assert done == m["nsteps"]
+    for f in ("cls", "site", "slot"):
+        assert (ev[f] == g["events"][f]).all(), f
+    assert (ev["total_rate"].view(np.uint64) == g["events"]["total_rate"].view(np.uint64)).all()
+    assert (o.status() == g["status1"]).all()
+    assert o.ties() == m["n_ties"]
+    assert np.nonzero(ev["flags"] & 1)[0].tolist() == m["tie_steps"]
+    assert o.validate() == 0
+
+
 @pytest.mark.parametrize("name", ["allrules_8x8", "wse2_hot_24x24", "allrules_40x70"])
 def test_incremental_equals_full_sweep(name):
     """kmco_validate restates KmcSim.validate (sim.py:159-168)."""
@@ -72,6 +91,93 @@ def test_incremental_equals_full_sweep(name):
         slots, counts, rowcnt = ko.sweep(o.status(), m["dim"])
         assert (slots == o.slots()).all() and (counts == o.counts()).all()
         assert (rowcnt.sum(axis=0) == counts).all()
+
+
+def replay_tracers(dim, status0, events):
+    """Independent (pure Python) statement of the tracer rule, driven by an event log: a MoveDivacancy hop
+    (slot 7 + k) carries the displacement to neighbour k of neighbors_and_mutuals (state.py:443-459); any other
+    event that makes a site a divacancy starts a tracer at (0, 0).  Returns {site: (da, db)} of the divacancies
+    on the final lattice, and that lattice."""
+    import canon
+    st = [int(x) for x in status0]
+    disp = {i: (0, 0) for i, v in enumerate(st) if v == 3}
+    for e in events:
+        site, slot = int(e["site"]), int(e["slot"])
+        p = canon.unlin(site, dim)
+        if 7 <= slot <= 12:
+            off = canon.NBR_NEAR_FAR[slot - 7][0]
+            q = canon.lin(canon.add(p, off, dim), dim)
+            da, db = disp.pop(site)
+            disp[q] = (da + off[0], db + off[1])
+            st[site], st[q] = 0, 3
+            continue
+        if slot == 0: new = {site: 3}
+        elif slot == 1: new = {site: 0}
+        elif slot in (2, 3): new = {site: st[site] | (slot - 1)}
+        elif slot in (4, 5): new = {site: st[site] & ~(slot - 3)}
+        elif slot == 6: new = {site: st[site] ^ 3}
+        else:
+            orient = (slot - 13) & 1
+            nodes = [canon.lin(x, dim) for x in canon.trefoil_nodes(p, orient, dim)]
+            new = {x: (4 + 3 * orient + r if slot < 15 else 3) for r, x in enumerate(nodes)}
+        for x, v in new.items():
+            if st[x] == 3 and v != 3:
+                disp.pop(x)
+            if v == 3 and st[x] != 3:
+                disp[x] = (0, 0)
+            st[x] = v
+    return disp, st
+
+
+@pytest.mark.parametrize("name", ["allrules_8x8", "wse2_hot_24x24", "wse2_16x16", "allrules_12x130"])
+def test_clock_and_tracers_follow_the_reference_event_log(name):
+    """SURVEY 8(f) rank 4 (extensions; the reference only logs total_rate for this, sim.py:138, README.md:36-37).
+    The oracle's tracers against an independent replay of the REFERENCE-made event log, and its clocks against
+    math.log / plain division over the logged totals (1e-12: kmc_log is within 2 ulp of libm)."""
+    import math
+    g = load(name)
+    m = g["meta"]
+    dim, n = tuple(m["dim"]), m["nsteps"]
+    for mode in (1, 2):
+        o = ko.Oracle(dim, g["rates"], m["class_order"], g["status0"])
+        o.enable_tracers()
+        o.set_clock(mode)
+        _, ev = o.run_philox(m["seed"], m["replica"], 0, n)
+        assert (ev["site"] == g["events"]["site"]).all()
+        u3 = philox.draws3(m["seed"], m["replica"], 0, n)
+        assert ((u3 > 0) & (u3 <= 1)).all()
+        if mode == 1:
+            want = math.fsum(1.0 / x for x in ev["total_naive"])
+        else:
+            want = math.fsum(-math.log(u) / x for u, x in zip(u3, ev["total_naive"]))
+        assert abs(o.clock() - want) <= 1e-12 * want
+        # the exactly rounded totals the reference logs (fsum) give the same time to 1e-12 as well
+        want_ref = math.fsum((1.0 if mode == 1 else -math.log(u)) / x for u, x in zip(u3, g["events"]["total_rate"]))
+        assert abs(o.clock() - want_ref) <= 1e-12 * want_ref
+    disp, st = replay_tracers(dim, g["status0"], g["events"])
+    assert st == [int(x) for x in g["status1"]]
+    trc = o.tracers()
+    assert sorted(disp) == np.nonzero(g["status1"] == 3)[0].tolist()
+    for site, d in disp.items():
+        assert tuple(trc[site]) == d
+    sq, cnt = o.msd()
+    assert cnt == len(disp) and sq == sum(a * a + a * b + b * b for a, b in disp.values())
+    if name.startswith("wse2"):
+        assert sq > 0
+
+
+def test_deterministic_log_is_within_two_ulp_of_libm():
+    import math
+    rng = np.random.default_rng(5)
+    xs = np.concatenate([rng.random(20000), 2.0 ** -rng.integers(0, 53, 200).astype(float),
+                         [1.0, 2.0 ** -53, 0.5, 0.7071067811865476, 0.7071067811865475, 1.0 - 2.0 ** -53]])
+    for x in xs:
+        if x <= 0:
+            continue
+        a, b = ko.log(x), math.log(x)
+        assert (a == 0.0 and b == 0.0) or abs(a - b) <= 2 * math.ulp(b)
+    for step in (0, 1, 12345, (1 << 33) + 9):
+        assert ko.draw3(20261019, 7, step) == philox.draws3(20261019, 7, step, 1)[0]
 
 
 def test_rank_search_equals_linear_scan():

@@ -10,7 +10,13 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def trajectory_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not os.path.basename(p).startswith(("state_gen", "native_stats", "zobrist_ref", "animate_replay")))
+                  if not os.path.basename(p).startswith(("state_gen", "native_stats", "zobrist_ref", "animate_replay",
+                                                         "boundary_ties")))
+
+
+def boundary_tie_names():
+    """Fixtures whose class draws were placed exactly on cumulative-weight boundaries (injected draws)."""
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "boundary_ties*.npz")))
 
 
 def load(name):
