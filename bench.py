@@ -45,7 +45,7 @@ SWEEP_BYTES_PER_SITE = 18                         # 1 B status read + 17 B slot 
 
 def wse2_rates():
     import math
-    r = [0.0] * 13
+    r = [0.0] * 17
     for c, e in WSE2_BARRIERS.items():
         r[c] = math.exp(-e / (TEMPERATURE * KB_EV))
     return r
@@ -352,7 +352,7 @@ def main():
         for e in engines:
             e.close()
         return {"value": value, "max_ms": max_ms, "e2e": e2e_value, "launches": n_launch, "clocks": clk,
-                "hist": hist, "h2d": R * DIM[0] * DIM[1], "d2h": R * DIM[0] * DIM[1] + R * 13 * 8,
+                "hist": hist, "h2d": R * DIM[0] * DIM[1], "d2h": R * DIM[0] * DIM[1] + R * 17 * 8,
                 "n_flight": n_flight}
 
     R = args.replicas

@@ -20,7 +20,11 @@
  *     reference's vacant layer set, demo1/state.py:22-23,171-177), 4 + 3*orientation + role for a
  *     trefoil member (orientation 0: {p, p+(2,0), p+(0,2)}, 1: {p, p+(2,0), p+(2,-2)}; role = index
  *     in that list; role 0 is the anchor p).
- *   - event classes (rule:kind) 0..12 and per-site move slots 0..16: see the tables at the end.
+ *   - event classes (rule:kind) 0..16 and per-site move slots 0..28: see the tables at the end.  Classes 0..12 /
+ *     slots 0..16 are the rules the reference implements; classes 13..16 / slots 17..28 are MoveMonovacancy, which
+ *     the reference's config/WSe2.yaml:8-13 names but its code only stubs (demo1/rules.py:295-296) -- an extension
+ *     with stated semantics, pinned by fixtures made from the reference engine running that
+ *     rule as a MultiKindRule subclass (oracle/move_monovacancy.py).
  */
 #ifndef KMC_B200_H
 #define KMC_B200_H
@@ -31,8 +35,8 @@
 extern "C" {
 #endif
 
-#define KMC_N_CLASSES 13
-#define KMC_N_SLOTS   17
+#define KMC_N_CLASSES 17
+#define KMC_N_SLOTS   29
 #define KMC_SLOT_NONE 0xFF
 #define KMC_CLASS_NONE 0xFF      /* event.cls when the total rate is zero (reference kmc.py:31-32) */
 
@@ -51,8 +55,8 @@ typedef enum {
  * the host recomputes exactly from `counts` (full records) -- the two agree to <= 1e-12 relative. */
 typedef struct {
     uint32_t site;               /* anchor site of the move                                          */
-    uint8_t  cls;                /* event class 0..12, or KMC_CLASS_NONE                             */
-    uint8_t  slot;               /* move slot 0..16                                                  */
+    uint8_t  cls;                /* event class 0..16, or KMC_CLASS_NONE                             */
+    uint8_t  slot;               /* move slot 0..28                                                  */
     uint16_t flags;              /* bit0: the class draw landed exactly on a cumulative boundary     */
     double   total_rate;
 } kmc_event_compact;             /* 16 bytes */
@@ -65,7 +69,7 @@ typedef struct {
     double   total_rate;
     uint32_t counts[KMC_N_CLASSES];   /* moves per class BEFORE the event (sim.py:90-104)          */
     uint32_t pad;
-} kmc_event_full;                /* 72 bytes */
+} kmc_event_full;                /* 88 bytes */
 
 enum { KMC_LOG_NONE = 0, KMC_LOG_COMPACT = 1, KMC_LOG_FULL = 2 };
 
@@ -81,7 +85,7 @@ int kmc_device_count(void);
  * kinds in Rule.kinds() order): it is the tie-break among equal weights (kmc.py:35 is a stable
  * sort).  The lattice starts pristine. */
 int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int n_replicas,
-               const double *class_rate /*[13]*/, const int *class_order, int n_order);
+               const double *class_rate /*[17]*/, const int *class_order, int n_order);
 int kmc_destroy(kmc_engine *h);
 
 /* KmcSim.initialize(state) (sim.py:46-54): replace the lattices.  host: [n_replicas][dim0*dim1]. */
@@ -103,13 +107,13 @@ int kmc_get_state_device(kmc_engine *h, void *dev_status);
  * `--no-incremental` sweep (sim.py:114-115): status planes -> 17 slot planes (class id or 0xFF per
  * site), per-row and per-replica class counts.  Everything stays on the device. */
 int kmc_sweep(kmc_engine *h);
-/* IncrementalMoveCache.undecided_counts for every rule (incremental.py:103-110): [n_replicas][13],
+/* IncrementalMoveCache.undecided_counts for every rule (incremental.py:103-110): [n_replicas][17],
  * from the last kmc_sweep(). */
 int kmc_get_counts(kmc_engine *h, int64_t *out);
-/* IncrementalMoveCache.undecided_sets (incremental.py:112-123) as a table: [n_replicas][n][17]
+/* IncrementalMoveCache.undecided_sets (incremental.py:112-123) as a table: [n_replicas][n][29]
  * class id or 0xFF, from the last kmc_sweep().  Parity / debug. */
 int kmc_get_slots(kmc_engine *h, uint8_t *out);
-/* per-row class counts of the last kmc_sweep(): [n_replicas][dim0][13] */
+/* per-row class counts of the last kmc_sweep(): [n_replicas][dim0][17] */
 int kmc_get_row_counts(kmc_engine *h, uint32_t *out);
 
 /* KmcSim.perform_random_move x nsteps (sim.py:106-143) for every replica, incremental tables held
@@ -147,7 +151,7 @@ int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica
 /* the same event with the caller's draws u[n_replicas][nsteps][2] (the kmc_step_draws seam on this path) */
 int kmc_step_draws_noinc(kmc_engine *h, const double *u, int64_t nsteps, int log_mode, void *events);
 
-/* statistics: events per class summed over replicas [13]; per replica [n_replicas][13];
+/* statistics: events per class summed over replicas [17]; per replica [n_replicas][17];
  * events done per replica [n_replicas]; boundary ties summed over replicas. */
 int kmc_get_histogram(kmc_engine *h, int64_t *out);
 int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out);
@@ -232,6 +236,12 @@ int kmc_set_sweep_double_buffer(kmc_engine *h, int on);
  *   10 FillMonovacancy:make-double  (:257-274)
  *   11 FillMonovacancy:from-empty
  *   12 FlipMonovacancy:natural      (:277-293)
+ *   13 MoveMonovacancy:natural          (stub :295-296; kinds from    17..28 MoveMonovacancy  (node, nbr_k, layer L): 17 + 2k + (L-1)
+ *   14 MoveMonovacancy:merge-divacancy   config/WSe2.yaml:8-13)              the vacancy in layer L of `node` hops to nbr_k, whose
+ *   15 MoveMonovacancy:split-divacancy                                       layer set must be defined and lack L;
+ *   16 MoveMonovacancy:swap-divacancy                                        kind = 2*(node is a divacancy) + (nbr_k not pristine)
+ * While any of classes 13..16 is enabled the engine runs its general kernels (byte lattice; one thread per site in
+ * the sweep); the bit-sliced replica kernels and the aligned sweep kernels serve the reference's own 13 classes.
  * In-class order (the rank the in-class draw indexes): row ascending, then slot ascending, then column.
  */
 

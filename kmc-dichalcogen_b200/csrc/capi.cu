@@ -40,8 +40,9 @@ static int fail(int code, const std::string &msg) { g_err = msg; return code; }
 
 struct kmc_engine {
     int device = 0, d0 = 0, d1 = 0, n = 0, R = 0;
-    double rate[NC];
-    int order_pos[NC];
+    double rate[NCA];
+    int order_pos[NCA];
+    bool mm = false;                         // a MoveMonovacancy class (13..16) is enabled: general kernels only
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t *d_status = nullptr;
@@ -100,7 +101,7 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
                                  "(smaller lattices alias the trefoil geometry under periodic boundaries)");
     if ((long long)dim0 * dim1 > 0x7FFFFFFFLL / 32) return fail(KMC_ERR_ARG, "kmc_create: lattice too large");
     if (n_replicas < 1) return fail(KMC_ERR_ARG, "kmc_create: n_replicas must be >= 1");
-    if (!class_rate || (n_order > 0 && !class_order) || n_order < 0 || n_order > NC)
+    if (!class_rate || (n_order > 0 && !class_order) || n_order < 0 || n_order > NCA)
         return fail(KMC_ERR_ARG, "kmc_create: bad class_rate / class_order");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -111,12 +112,13 @@ extern "C" int kmc_create(kmc_engine **out, int device, int dim0, int dim1, int 
     if (device < 0 || device >= ndev) return fail(KMC_ERR_ARG, "kmc_create: bad device index");
     kmc_engine *h = new kmc_engine();
     h->device = device; h->d0 = dim0; h->d1 = dim1; h->n = dim0 * dim1; h->R = n_replicas;
-    for (int c = 0; c < NC; c++) { h->rate[c] = 0.0; h->order_pos[c] = -1; }
+    for (int c = 0; c < NCA; c++) { h->rate[c] = 0.0; h->order_pos[c] = -1; }
     for (int i = 0; i < n_order; i++) {
         int c = class_order[i];
-        if (c < 0 || c >= NC || h->order_pos[c] >= 0) { delete h; return fail(KMC_ERR_ARG, "kmc_create: class_order must list distinct class ids 0..12"); }
+        if (c < 0 || c >= NCA || h->order_pos[c] >= 0) { delete h; return fail(KMC_ERR_ARG, "kmc_create: class_order must list distinct class ids 0..16"); }
         if (!(class_rate[c] >= 0.0)) { delete h; return fail(KMC_ERR_ARG, "kmc_create: negative or NaN rate"); }   // kmc.py:37-39
         h->order_pos[c] = i; h->rate[c] = class_rate[c];
+        if (c >= C_MOVE_MONO) h->mm = true;
     }
     const int rc = create_device_side(h);
     if (rc) { const std::string msg = g_err; kmc_destroy(h); return fail(rc, msg); }   // frees whatever was allocated
@@ -135,17 +137,17 @@ static int create_device_side(kmc_engine *h)
     CU(cudaEventCreate(&h->ev1));
     const size_t R = (size_t)n_replicas;
     CU(cudaMalloc(&h->d_status, R * h->n));
-    CU(cudaMalloc(&h->d_counts, R * NC * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_counts, R * NCA * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_steps, R * sizeof(unsigned long long)));
-    CU(cudaMalloc(&h->d_hist, R * NC * sizeof(unsigned long long)));
+    CU(cudaMalloc(&h->d_hist, R * NCA * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_hops, R * 6 * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_ties, R * sizeof(unsigned long long)));
     CU(cudaMalloc(&h->d_flags, R * sizeof(uint32_t)));
     CU(cudaMalloc(&h->d_result, sizeof(int)));
     CU(cudaMemsetAsync(h->d_status, 0, R * h->n, h->stream));
-    CU(cudaMemsetAsync(h->d_counts, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_counts, 0, R * NCA * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
-    CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hist, 0, R * NCA * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
@@ -329,12 +331,27 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
 {
     const size_t R = (size_t)h->R;
     { int rc = ensure_bytes(h); if (rc) return rc; }
-    if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * RCG_STRIDE * sizeof(uint32_t)));
-    if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * NS * h->n));
+    const int rcs = h->mm ? RCG_STRIDE_MM : RCG_STRIDE, nsl = h->mm ? NSA : NS;
+    if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * rcs * sizeof(uint32_t)));
+    if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * nsl * h->n));
+    if (h->mm) {
+        // MoveMonovacancy live: the general enumeration kernel (all 9 rules, 29 slot planes, one thread per site)
+        CU(cudaMemsetAsync(h->d_rowcnt, 0, R * h->d0 * rcs * sizeof(uint32_t), h->stream));
+        SweepParams p;
+        p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R; p.total_words = 0;
+        p.status = h->d_status; p.slots = with_slots ? h->d_slots : nullptr; p.rowcnt = h->d_rowcnt;
+        const long long blocks = ((long long)R * h->n + 255) / 256;
+        kmc_sweep_kernel_mm<<<(unsigned)blocks, 256, 0, h->stream>>>(p);
+        CU(cudaGetLastError());
+        kmc_reduce_counts_mm_kernel<<<h->R, 256, 0, h->stream>>>(h->d_rowcnt, h->d0, h->R, h->d_counts);
+        CU(cudaGetLastError());
+        h->launches += 2;
+        return KMC_OK;
+    }
     if (with_slots && h->slots_double) {
         // steady-state measurement: successive sweeps write alternating buffers, so that a launch's stores
         // never hit lines the previous launch left dirty in L2 (the result the getters read is the last one)
-        if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * NS * h->n));
+        if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * (h->mm ? NSA : NS) * h->n));
         std::swap(h->d_slots, h->d_slots_alt);
     }
     // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas, one launch in total
@@ -423,7 +440,7 @@ extern "C" int kmc_get_counts(kmc_engine *h, int64_t *out)
     int rc = bind(h); if (rc) return rc;
     if (!out) return fail(KMC_ERR_ARG, "kmc_get_counts: null buffer");
     if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_counts: call kmc_sweep first");
-    CU(cudaMemcpyAsync(out, h->d_counts, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out, h->d_counts, (size_t)h->R * NCA * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
 }
@@ -433,14 +450,15 @@ extern "C" int kmc_get_slots(kmc_engine *h, uint8_t *out)
     int rc = bind(h); if (rc) return rc;
     if (!out) return fail(KMC_ERR_ARG, "kmc_get_slots: null buffer");
     if (!h->swept || !h->d_slots) return fail(KMC_ERR_ARG, "kmc_get_slots: call kmc_sweep first");
-    std::vector<uint8_t> planes((size_t)NS * h->n);
+    const int nsl = h->mm ? NSA : NS;                 // slot planes the sweep kernels of this engine write
+    std::vector<uint8_t> planes((size_t)nsl * h->n);
     for (int r = 0; r < h->R; r++) {
-        CU(cudaMemcpyAsync(planes.data(), h->d_slots + (size_t)r * NS * h->n, planes.size(),
+        CU(cudaMemcpyAsync(planes.data(), h->d_slots + (size_t)r * nsl * h->n, planes.size(),
                            cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        uint8_t *o = out + (size_t)r * h->n * NS;
-        for (int j = 0; j < NS; j++)
-            for (int i = 0; i < h->n; i++) o[(size_t)i * NS + j] = planes[(size_t)j * h->n + i];
+        uint8_t *o = out + (size_t)r * h->n * NSA;
+        for (int i = 0; i < h->n; i++)
+            for (int j = 0; j < NSA; j++) o[(size_t)i * NSA + j] = j < nsl ? planes[(size_t)j * h->n + i] : (uint8_t)KMC_SLOT_NONE;
     }
     return KMC_OK;
 }
@@ -450,11 +468,12 @@ extern "C" int kmc_get_row_counts(kmc_engine *h, uint32_t *out)
     int rc = bind(h); if (rc) return rc;
     if (!out) return fail(KMC_ERR_ARG, "kmc_get_row_counts: null buffer");
     if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_row_counts: call kmc_sweep first");
-    std::vector<uint32_t> tmp((size_t)h->R * h->d0 * RCG_STRIDE);
+    const int rcs = h->mm ? RCG_STRIDE_MM : RCG_STRIDE, ncx = h->mm ? NCA : NC;
+    std::vector<uint32_t> tmp((size_t)h->R * h->d0 * rcs);
     CU(cudaMemcpyAsync(tmp.data(), h->d_rowcnt, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < (size_t)h->R * h->d0; i++)
-        for (int c = 0; c < NC; c++) out[i * NC + c] = tmp[i * RCG_STRIDE + c];
+        for (int c = 0; c < NCA; c++) out[i * NCA + c] = c < ncx ? tmp[i * rcs + c] : 0u;
     return KMC_OK;
 }
 
@@ -509,7 +528,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // the byte-lattice kernel
     // (two replicas per warp pay off once one replica per warp would already fill the GPU; small batches and
     // single trajectories are latency-bound and run faster with a full warp each)
-    const bool wide_ok = h->d1 > 64 && h->d1 <= 2048 &&
+    // MoveMonovacancy live: only the byte-lattice kernel maintains its four classes (variants 1 and 3)
+    if (h->mm && (h->variant == 2 || h->variant == 4 || h->variant == 5))
+        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: only replica kernels 0 (auto), 1 and 3 (byte lattice) apply");
+    const bool wide_ok = !h->mm && h->d1 > 64 && h->d1 <= 2048 &&
                          wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
     if (h->variant == 5 && !wide_ok)
         return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs 64 < dim1 <= 2048 and dim0 <= ~8700");
@@ -556,7 +578,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         ReplicaParams &p = q.base;
         p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
         p.status = h->d_status;
-        for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+        for (int c = 0; c < NCA; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
         p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
@@ -587,7 +609,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     { int rc = ensure_bytes(h); if (rc) return rc; }
     long long hw_min = 4096;
     if (const char *e = getenv("KMC_HW_MIN_REPLICAS")) hw_min = atoll(e);              // tuning knob
-    const bool halfwarp = h->variant == 4 || (h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
+    const bool halfwarp = h->variant == 4 || (!h->mm && h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
                                               2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
@@ -612,7 +634,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         ReplicaParams p;
         p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
         p.status = h->d_status;
-        for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+        for (int c = 0; c < NCA; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
         p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
         p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
         p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
@@ -638,15 +660,15 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         if (rs) CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
         return KMC_OK;
     }
-    const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64 &&
+    const bool bitplanes = h->variant == 2 || (!h->mm && h->variant == 0 && h->d1 <= 64 &&
                                                replica_bp_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (bitplanes && h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernel needs dim1 <= 64");
-    size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1);
+    size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1, h->mm);
     // lattices that do not fit shared memory stay in HBM/L2; only the row-count hierarchy is staged
     const bool global_state = h->variant == 3 || (!bitplanes && wbytes > (size_t)h->max_smem_optin);
     if (global_state) {
         if (bitplanes) return fail(KMC_ERR_ARG, "variant 3 (HBM-resident lattice) uses the byte-lattice kernel");
-        wbytes = replica_rc_bytes(h->d0);
+        wbytes = replica_rc_bytes(h->d0, h->mm);
         if (h->d1 > 10000) return fail(KMC_ERR_ARG, "rows longer than 10000 sites overflow the 16-bit row counts: use kmc_run_noinc");
     }
     if (wbytes > (size_t)h->max_smem_optin) {
@@ -667,7 +689,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     ReplicaParams p;
     p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
     p.status = h->d_status;
-    for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+    for (int c = 0; c < NCA; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
     p.nsteps = nsteps; p.seed = seed; p.replica0 = replica0;
     p.draws = d_draws; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags; p.any_flag = h->d_anyflag;
@@ -676,7 +698,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
     p.hier = nullptr; p.hier_valid = 0;
     if (global_state) {
-        if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * RC_WORDS * sizeof(uint32_t)));
+        if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * (h->mm ? 9 : 7) * sizeof(uint32_t)));
         p.hier = h->d_hier; p.hier_valid = h->hier_valid ? 1 : 0;
     }
     const unsigned blocks = (unsigned)((h->R + W - 1) / W);
@@ -692,7 +714,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         if (h->d0 == 64 && h->d1 == 64) { if (lat) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, true>)); else KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>)); }
         else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0>));
     } else if (global_state) {
-        KMC_LAUNCH((kmc_replica_kernel<0, 0, true>));
+        if (h->mm) KMC_LAUNCH((kmc_replica_kernel<0, 0, true, true>)); else KMC_LAUNCH((kmc_replica_kernel<0, 0, true>));
+    } else if (h->mm) {
+        if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_kernel<64, 64, false, true>));
+        else KMC_LAUNCH((kmc_replica_kernel<0, 0, false, true>));
     } else {
         if (h->d0 == 64 && h->d1 == 64) KMC_LAUNCH((kmc_replica_kernel<64, 64>));
         else KMC_LAUNCH((kmc_replica_kernel<0, 0>));
@@ -758,7 +783,7 @@ extern "C" int kmc_step_draws(kmc_engine *h, const double *u, int64_t nsteps, in
 extern "C" int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot)
 {
     int rc = bind(h); if (rc) return rc;
-    if (replica < 0 || replica >= h->R || site >= (uint32_t)h->n || slot < 0 || slot >= NS)
+    if (replica < 0 || replica >= h->R || site >= (uint32_t)h->n || slot < 0 || slot >= NSA)
         return fail(KMC_ERR_ARG, "kmc_perform_given: bad replica / site / slot");
     rc = ensure_bytes(h); if (rc) return rc;
     kmc_apply_given_kernel<<<1, 1, 0, h->stream>>>(h->d_status + (size_t)replica * h->n, h->d0, h->d1,
@@ -816,7 +841,8 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
     NoincParams p;
     p.d0 = h->d0; p.d1 = h->d1; p.n = h->n; p.n_replicas = h->R;
     p.status = h->d_status;
-    for (int c = 0; c < NC; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+    for (int c = 0; c < NCA; c++) { p.rate[c] = h->rate[c]; p.order_pos[c] = h->order_pos[c]; }
+    p.mm = h->mm ? 1 : 0; p.rc_stride = h->mm ? RCG_STRIDE_MM : RCG_STRIDE;
     p.seed = seed; p.replica0 = replica0; p.log_mode = log_mode; p.events = rs ? h->d_events : nullptr;
     p.nsteps = nsteps;
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
@@ -845,7 +871,7 @@ extern "C" int kmc_get_histogram_per_replica(kmc_engine *h, int64_t *out)
 {
     int rc = bind(h); if (rc) return rc;
     if (!out) return fail(KMC_ERR_ARG, "kmc_get_histogram_per_replica: null buffer");
-    CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NC * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(out, h->d_hist, (size_t)h->R * NCA * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return KMC_OK;
 }
@@ -884,10 +910,10 @@ extern "C" int kmc_get_hops(kmc_engine *h, int64_t *out)
 extern "C" int kmc_get_histogram(kmc_engine *h, int64_t *out)
 {
     if (!h || !out) return fail(KMC_ERR_ARG, "kmc_get_histogram: null argument");
-    std::vector<int64_t> tmp((size_t)h->R * NC);
+    std::vector<int64_t> tmp((size_t)h->R * NCA);
     int rc = kmc_get_histogram_per_replica(h, tmp.data()); if (rc) return rc;
-    for (int c = 0; c < NC; c++) out[c] = 0;
-    for (int r = 0; r < h->R; r++) for (int c = 0; c < NC; c++) out[c] += tmp[(size_t)r * NC + c];
+    for (int c = 0; c < NCA; c++) out[c] = 0;
+    for (int r = 0; r < h->R; r++) for (int c = 0; c < NCA; c++) out[c] += tmp[(size_t)r * NCA + c];
     return KMC_OK;
 }
 
@@ -917,7 +943,7 @@ extern "C" int kmc_reset_stats(kmc_engine *h)
     int rc = bind(h); if (rc) return rc;
     const size_t R = (size_t)h->R;
     CU(cudaMemsetAsync(h->d_steps, 0, R * sizeof(unsigned long long), h->stream));
-    CU(cudaMemsetAsync(h->d_hist, 0, R * NC * sizeof(unsigned long long), h->stream));
+    CU(cudaMemsetAsync(h->d_hist, 0, R * NCA * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_hops, 0, R * 6 * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_ties, 0, R * sizeof(unsigned long long), h->stream));
     CU(cudaMemsetAsync(h->d_flags, 0, R * sizeof(uint32_t), h->stream));
@@ -1071,6 +1097,7 @@ extern "C" int kmc_probe_store_pattern(kmc_engine *h)
 {
     int rc = bind(h); if (rc) return rc;
     if (h->n & 15) return fail(KMC_ERR_ARG, "kmc_probe_store_pattern: needs dim0*dim1 % 16 == 0");
+    if (h->mm) return fail(KMC_ERR_ARG, "kmc_probe_store_pattern: measures the 17-plane sweep (MoveMonovacancy disabled)");
     if (!h->d_slots) CU(cudaMalloc(&h->d_slots, (size_t)h->R * NS * h->n));
     const long long chunks = (long long)h->R * (h->n >> 4);
     kmc_store_pattern_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, h->stream>>>(h->d_slots, h->n, h->R);

@@ -160,6 +160,18 @@ extern "C" int kmc_hostcheck_eval_sites(const uint8_t *status, int d0, int d1, u
     return 0;
 }
 
+// the MoveMonovacancy-aware evaluator: out [n][17]
+extern "C" int kmc_hostcheck_eval_sites_mm(const uint8_t *status, int d0, int d1, uint8_t *out)
+{
+    struct H { const uint8_t *p; __host__ __device__ int operator()(int i) const { return p[i]; } } S{status};
+    for (int a = 0; a < d0; a++)
+        for (int b = 0; b < d1; b++) {
+            F4 f = eval_site<true>(S, a, b, d0, d1);
+            for (int c = 0; c < NCA; c++) out[(size_t)(a * d1 + b) * NCA + c] = (uint8_t)f4_class(f, c);
+        }
+    return 0;
+}
+
 extern "C" void kmc_hostcheck_draw(uint64_t seed, uint32_t replica, uint64_t step, double *u1, double *u2)
 {
     kmc_draw(seed, replica, step, *u1, *u2);

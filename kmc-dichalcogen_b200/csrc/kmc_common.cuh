@@ -16,9 +16,18 @@
 
 namespace kmc {
 
-constexpr int NC = 13;        // event classes
-constexpr int NS = 17;        // move slots per site
-constexpr int RC_WORDS = 7;   // row-count words per row: 14 uint16 fields, 13 used
+// Two widths.  NC / NS: the classes and slots of the rules the reference implements itself -- what the
+// bit-sliced replica kernels and the aligned sweep kernels maintain.  NCA / NSA: those plus MoveMonovacancy
+// (4 kinds, 12 (direction, layer) slots; a stub in the reference, rules.py:295-296, semantics in DESIGN.md
+// section 2) -- the width of every table that crosses the C ABI and of the general (byte-lattice) kernels.
+constexpr int NC = 13;        // event classes of the reference's own rules
+constexpr int NS = 17;        // move slots per site of the reference's own rules
+constexpr int NCA = 17;       // all event classes (ABI width)
+constexpr int NSA = 29;       // all move slots per site (ABI width)
+constexpr int MM_SLOT0 = 17;  // MoveMonovacancy slot of (direction k, layer L): 17 + 2k + (L - 1)
+// row-count words per row of the byte-lattice kernel (two uint16 fields each): 13 classes -> 7, 17 -> 9
+template <bool MM> struct RcWords { static constexpr int value = MM ? 9 : 7; };
+constexpr int RC_WORDS = 7;
 
 // status codes
 constexpr int S_PRISTINE = 0, S_DIVAC = 3, S_TREF = 4;
@@ -26,7 +35,8 @@ constexpr int S_PRISTINE = 0, S_DIVAC = 3, S_TREF = 4;
 // class ids
 enum : int { C_CREATE_DIV = 0, C_FILL_DIV = 1, C_MOVE_DIV = 2, C_CREATE_TREF = 6, C_DESTROY_TREF = 7,
              C_CMONO_FROM_DOUBLE = 8, C_CMONO_MAKE_EMPTY = 9, C_FMONO_MAKE_DOUBLE = 10,
-             C_FMONO_FROM_EMPTY = 11, C_FLIP = 12 };
+             C_FMONO_FROM_EMPTY = 11, C_FLIP = 12,
+             C_MOVE_MONO = 13 /* natural, 14 merge-divacancy, 15 split-divacancy, 16 swap-divacancy */ };
 
 // The six neighbours in ring order (60-degree rotations, state.py:392-394):
 //   R0=(-1,0) R1=(0,-1) R2=(1,-1) R3=(1,0) R4=(0,1) R5=(-1,1)
@@ -37,11 +47,12 @@ KMC_HD int kring(int k) { return (0x204315 >> (4 * k)) & 7; }
 
 // ---- per-site class counts, byte-packed -------------------------------------------------------
 // F4.w[j] byte q = number of moves of class 4*j+q anchored at the site.
-struct F4 { uint32_t w0, w1, w2, w3; };
+// (w4 byte 0 = class 16; only the MoveMonovacancy-aware build looks at it)
+struct F4 { uint32_t w0, w1, w2, w3, w4; };
 
 // contributions that depend on the site's own status only (classes 0,1,7,8..12)
 KMC_HD F4 g1_of_status(int s) {
-    F4 f = {0u, 0u, 0u, 0u};
+    F4 f = {0u, 0u, 0u, 0u, 0u};
     if (s == 0) { f.w0 = 0x00000001u; f.w2 = 0x00000002u; }                 // c0 x1, c8 x2
     else if (s == 1 || s == 2) { f.w2 = 0x00010100u; f.w3 = 0x00000001u; }  // c9, c10, c12
     else if (s == 3) { f.w0 = 0x00000100u; f.w2 = 0x02000000u; }            // c1 x1, c11 x2
@@ -85,12 +96,30 @@ KMC_HD int wrap_dec(int x, int d) { return x < 0 ? x + d : x; }
 
 // Full per-site evaluation: byte-packed counts of all 13 classes for moves anchored at (a, b).
 // `S` is any accessor with int operator()(int site_index).
-template <class S>
+// MoveMonovacancy counts of a site of status s0 in 1..3 from its six ring statuses: the vacancy in layer L hops
+// to a neighbour whose layer set is defined and lacks L; kind = 2 * (s0 is a divacancy) + (target not pristine).
+// Returns natural | merge << 8 | split << 16 | swap << 24.
+KMC_HD uint32_t mm_counts(int s0, int r0, int r1, int r2, int r3, int r4, int r5) {
+    const uint32_t p = (r0 == 0) + (r1 == 0) + (r2 == 0) + (r3 == 0) + (r4 == 0) + (r5 == 0);
+    const uint32_t m1 = (r0 == 1) + (r1 == 1) + (r2 == 1) + (r3 == 1) + (r4 == 1) + (r5 == 1);
+    const uint32_t m2 = (r0 == 2) + (r1 == 2) + (r2 == 2) + (r3 == 2) + (r4 == 2) + (r5 == 2);
+    if (s0 == 1) return p | (m2 << 8);
+    if (s0 == 2) return p | (m1 << 8);
+    return ((2u * p) << 16) | ((m1 + m2) << 24);
+}
+
+template <bool MM = false, class S>
 KMC_HD F4 eval_site(const S &s, int a, int b, int d0, int d1) {
     const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
     const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
     const int s0 = s(a * d1 + b);
     F4 f = g1_of_status(s0);
+    if (MM && s0 >= 1 && s0 <= 3) {
+        const uint32_t c = mm_counts(s0, s(am * d1 + b), s(a * d1 + bm), s(ap * d1 + bm), s(ap * d1 + b),
+                                     s(a * d1 + bp), s(am * d1 + bp));
+        f.w3 |= (c & 0x00FFFFFFu) << 8;               // classes 13, 14, 15 = bytes 1..3 of word 3
+        f.w4 = c >> 24;                               // class 16
+    }
     if (s0 == S_DIVAC) {
         RingMasks m = ring_masks(s(am * d1 + b), s(a * d1 + bm), s(ap * d1 + bm), s(ap * d1 + b),
                                  s(a * d1 + bp), s(am * d1 + bp));
@@ -109,7 +138,7 @@ KMC_HD F4 eval_site(const S &s, int a, int b, int d0, int d1) {
 
 // number of class-c moves in a byte-packed F4
 KMC_HD uint32_t f4_class(const F4 &f, int c) {
-    uint32_t w = (c < 4) ? f.w0 : (c < 8) ? f.w1 : (c < 12) ? f.w2 : f.w3;
+    uint32_t w = (c < 4) ? f.w0 : (c < 8) ? f.w1 : (c < 12) ? f.w2 : (c < 16) ? f.w3 : f.w4;
     return (w >> (8 * (c & 3))) & 0xFFu;
 }
 

@@ -13,10 +13,12 @@ namespace kmc {
 struct NoincParams {
     int d0, d1, n, n_replicas;
     uint8_t *status;                     // [R][n]
-    const uint32_t *rowcnt;              // [R][d0][16]
-    const unsigned long long *counts;    // [R][13]
-    double rate[NC];
-    int order_pos[NC];
+    const uint32_t *rowcnt;              // [R][d0][rc_stride]
+    const unsigned long long *counts;    // [R][NCA]
+    int rc_stride;                       // 16 (aligned sweep kernels) or 32 (MoveMonovacancy-aware sweep)
+    int mm;                              // MoveMonovacancy classes are live: 17 classes
+    double rate[NCA];
+    int order_pos[NCA];
     unsigned long long seed;
     uint32_t replica0;
     int log_mode;
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
     __shared__ double s_total;
     __shared__ int s_csel, s_zero, s_tie, s_row, s_col;
     __shared__ uint32_t s_rin;
-    __shared__ uint32_t s_slotcnt[6];
+    __shared__ uint32_t s_slotcnt[12];
     const int rep = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
@@ -81,14 +83,16 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         return;
     }
     uint8_t *st = p.status + (size_t)rep * p.n;
-    const uint32_t *rcg = p.rowcnt + (size_t)rep * d0 * RCG_STRIDE;
+    const int rcs = p.rc_stride;
+    const uint32_t *rcg = p.rowcnt + (size_t)rep * d0 * rcs;
     const unsigned long long step = p.steps_done[rep];
 
     if (tid < 32) {
-        const int myc = lane < NC ? lane : 0;
-        const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-        const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
-        const long long tot = lane < NC ? (long long)p.counts[(size_t)rep * NC + lane] : 0;
+        const int ncx = p.mm ? NCA : NC;
+        const int myc = lane < ncx ? lane : 0;
+        const double rate = (lane < ncx && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+        const int pos = (lane < ncx && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+        const long long tot = lane < ncx ? (long long)p.counts[(size_t)rep * NCA + lane] : 0;
         double u1, u2;
         if (p.draws) {
             const double2 u = *reinterpret_cast<const double2 *>(p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)p.t) * 2);
@@ -97,9 +101,10 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
             kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
         }
         const double w = __dmul_rn((double)tot, rate);
-        PickState pstate = pick_state_init(lane);
-        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
-        if (p.log_mode == KMC_LOG_FULL && lane < NC)
+        ClassPick pick;
+        if (p.mm) { PickState pstate = pick_state_init_n<32>(lane); pick = pick_class<32>(w, pos, pstate, u1, lane); }
+        else { PickState pstate = pick_state_init_n<16>(lane); pick = pick_class<16>(w, pos, pstate, u1, lane); }
+        if (p.log_mode == KMC_LOG_FULL && lane < NCA)
             (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = (uint32_t)tot;
         const long long cnt = __shfl_sync(FULL, tot, pick.zero ? 0 : pick.csel);
         long long rr = (long long)__dmul_rn(u2, (double)cnt);
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
             s_rank = (unsigned long long)(rr < 0 ? 0 : rr);
         }
     }
-    if (tid < 6) s_slotcnt[tid] = 0;
+    if (tid < 12) s_slotcnt[tid] = 0;
     __syncthreads();
     if (s_zero) {
         if (tid == 0) {
@@ -135,13 +140,13 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int kr = (d0 + 255) / 256;
         const int r0 = tid * kr, r1 = min(r0 + kr, d0);
         unsigned long long local = 0, total;
-        for (int a = r0; a < r1; a++) local += rcg[(size_t)a * RCG_STRIDE + csel];
+        for (int a = r0; a < r1; a++) local += rcg[(size_t)a * rcs + csel];
         const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
         if (rank >= excl && rank < excl + local) {
             unsigned long long r = rank - excl;
             int a = r0;
             for (; a < r1; a++) {
-                const unsigned long long v = rcg[(size_t)a * RCG_STRIDE + csel];
+                const unsigned long long v = rcg[(size_t)a * rcs + csel];
                 if (r < v) break;
                 r -= v;
             }
@@ -176,28 +181,26 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
     }
     // ---- slot: per-slot totals of the class in this row (row, slot, column order) ------------------------
     {
-        uint32_t a01 = 0, a23 = 0, a45 = 0;
+        uint32_t acc[6] = {0u, 0u, 0u, 0u, 0u, 0u};               // twelve 16-bit per-slot counters
         for (int b = tid; b < d1; b += 256) {
             const uint32_t m = site_slot_mask(view, vrow, b, vd0, d1, csel);
-            a01 += (m & 1u) | ((m & 2u) << 15);
-            a23 += ((m >> 2) & 1u) | ((m & 8u) << 13);
-            a45 += ((m >> 4) & 1u) | ((m & 32u) << 11);
+#pragma unroll
+            for (int q = 0; q < 6; q++) acc[q] += ((m >> (2 * q)) & 1u) | (((m >> (2 * q + 1)) & 1u) << 16);
         }
-        a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
-        if (lane == 0) {
-            if (a01 & 0xFFFFu) atomicAdd(&s_slotcnt[0], a01 & 0xFFFFu);
-            if (a01 >> 16) atomicAdd(&s_slotcnt[1], a01 >> 16);
-            if (a23 & 0xFFFFu) atomicAdd(&s_slotcnt[2], a23 & 0xFFFFu);
-            if (a23 >> 16) atomicAdd(&s_slotcnt[3], a23 >> 16);
-            if (a45 & 0xFFFFu) atomicAdd(&s_slotcnt[4], a45 & 0xFFFFu);
-            if (a45 >> 16) atomicAdd(&s_slotcnt[5], a45 >> 16);
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+            const uint32_t a = __reduce_add_sync(FULL, acc[q]);
+            if (lane == 0) {
+                if (a & 0xFFFFu) atomicAdd(&s_slotcnt[2 * q], a & 0xFFFFu);
+                if (a >> 16) atomicAdd(&s_slotcnt[2 * q + 1], a >> 16);
+            }
         }
     }
     __syncthreads();
     uint32_t r = s_rin;
     int j = 0;
 #pragma unroll
-    for (int q = 0; q < 5; q++)
+    for (int q = 0; q < 11; q++)
         if (j == q && r >= s_slotcnt[q]) { r -= s_slotcnt[q]; j = q + 1; }
     // ---- site: each thread owns columns [tid*kc, tid*kc + kc) ---------------------------------------------
     {
@@ -223,11 +226,11 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int slot = class_slot_base(csel) + j;
         const int site = row * d1 + col;
         const int s0 = st[site];
+        const MoveNodes m = move_nodes_st(st, row, col, slot, s0, d0, d1);      // before the lattice changes
         apply_move(st, d0, d1, row, col, slot, s0);
         if (p.tracer) {
-            const MoveNodes m = move_nodes(row, col, slot, s0, d0, d1);
             tracer_update(p.tracer + (size_t)rep * p.n, slot, m.na, site, m.ns0, m.a1 * d1 + m.b1, m.ns1,
-                          m.a2 * d1 + m.b2, m.ns2);
+                          m.a2 * d1 + m.b2, m.ns2, s0);
         }
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
@@ -241,7 +244,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         p.steps_done[rep] = step + 1;
         if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], kmc_time_step(p.clock_mode, s_total, p.seed,
                                                                           p.replica0 + (uint32_t)rep, step));
-        p.hist[(size_t)rep * NC + csel] += 1;
+        p.hist[(size_t)rep * NCA + csel] += 1;
         if (slot >= 7 && slot < 13) p.hops[(size_t)rep * 6 + slot - 7] += 1;
         if (s_tie) p.ties[rep] += 1;
     }
@@ -271,13 +274,18 @@ __global__ void kmc_apply_given_kernel(uint8_t *st, int d0, int d1, int site, in
         const bool t20 = st[ap2 * d1 + b] == 3;
         ok = s0 == 3 && t20 && (slot == 13 ? st[a * d1 + bp2] == 3 : st[ap2 * d1 + bm2] == 3);
         (void)f;
-    } else ok = (slot == 15 && s0 == 4) || (slot == 16 && s0 == 7);
+    } else if (slot <= 16) ok = (slot == 15 && s0 == 4) || (slot == 16 && s0 == 7);
+    else {                                                 // MoveMonovacancy (direction, layer)
+        const int ri = kring((slot - MM_SLOT0) >> 1), layer = ((slot - MM_SLOT0) & 1) + 1;
+        const int na = wrap_inc(wrap_dec(a + (int)((RING_DA >> (4 * ri)) & 0xF) - 2, d0), d0);
+        const int nb = wrap_inc(wrap_dec(b + (int)((RING_DB >> (4 * ri)) & 0xF) - 2, d1), d1);
+        const int dst = st[na * d1 + nb];
+        ok = s0 >= 1 && s0 <= 3 && (s0 & layer) && dst <= 3 && !(dst & layer);
+    }
     if (ok) {
+        const MoveNodes m = move_nodes_st(st, a, b, slot, s0, d0, d1);
         apply_move(st, d0, d1, a, b, slot, s0);
-        if (tracer) {
-            const MoveNodes m = move_nodes(a, b, slot, s0, d0, d1);
-            tracer_update(tracer, slot, m.na, site, m.ns0, m.a1 * d1 + m.b1, m.ns1, m.a2 * d1 + m.b2, m.ns2);
-        }
+        if (tracer) tracer_update(tracer, slot, m.na, site, m.ns0, m.a1 * d1 + m.b1, m.ns1, m.a2 * d1 + m.b2, m.ns2, s0);
     }
     result[0] = ok ? 0 : 1;
 }

@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-            if (lane < NC) rec->counts[lane] = (uint32_t)tot;
+            if (lane < NCA) rec->counts[lane] = lane < NC ? (uint32_t)tot : 0u;
         }
 
         // ---- 3. in-class pick: rank in (row, slot, column) order -----------------------------------
@@ -617,7 +617,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             gst[a2 * d1 + wrap1(b - 2, d1)] = (uint8_t)(S_TREF + 5);
         }
     }
-    if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < NC) p.hist[(size_t)rep * NCA + lane] += hist;
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
             gst[a2 * d1 + wrap1(b - 2, d1)] = (uint8_t)(S_TREF + 5);
         }
     }
-    if (hl < NC) p.hist[(size_t)rep * NC + hl] += hist;
+    if (hl < NC) p.hist[(size_t)rep * NCA + hl] += hist;
     if (hl < 6) p.hops[(size_t)rep * 6 + hl] += hops;
     if (hl == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

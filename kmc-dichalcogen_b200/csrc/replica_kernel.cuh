@@ -30,8 +30,8 @@ struct ReplicaParams {
     int d0, d1, n;
     int n_replicas;
     uint8_t *status;                 // [R][n]
-    double rate[NC];                 // per-class rate (0 for disabled)
-    int order_pos[NC];               // position in weighted_choice input order, or -1
+    double rate[NCA];                // per-class rate (0 for disabled)
+    int order_pos[NCA];              // position in weighted_choice input order, or -1
     long long nsteps;
     unsigned long long seed;
     uint32_t replica0;
@@ -39,7 +39,7 @@ struct ReplicaParams {
     int log_mode;
     void *events;                    // [R][nsteps] records or nullptr
     unsigned long long *steps_done;  // [R] in: step offset; out: += events done
-    unsigned long long *hist;        // [R][NC]
+    unsigned long long *hist;        // [R][NCA]
     unsigned long long *hops;        // [R][6] MoveDivacancy events per direction k (slot 7 + k)
     unsigned long long *ties;        // [R]
     uint32_t *flags;                 // [R] bit0 zero-rate stop, bit1 validate mismatch
@@ -85,9 +85,13 @@ __device__ __forceinline__ uint32_t tracer_step(int k) {
     return ((uint32_t)da & 0xFFFFu) | ((uint32_t)db << 16);
 }
 __device__ __forceinline__ void tracer_update(uint32_t *T, int slot, int na, int site0, int ns0, int site1, int ns1,
-                                              int site2, int ns2) {
+                                              int site2, int ns2, int s0 = 0) {
     if (slot >= 7 && slot < 13) {
         T[site1] = __vadd2(T[site0], tracer_step(slot - 7));
+    } else if (slot >= MM_SLOT0) {
+        // MoveMonovacancy: a divacancy that trades places with a monovacancy (swap) keeps its displacement; a
+        // merge makes a new divacancy; a split ends one
+        if (ns1 == S_DIVAC) T[site1] = s0 == S_DIVAC ? __vadd2(T[site0], tracer_step((slot - MM_SLOT0) >> 1)) : 0u;
     } else {
         if (ns0 == S_DIVAC) T[site0] = 0u;
         if (na > 1 && ns1 == S_DIVAC) T[site1] = 0u;
@@ -100,14 +104,13 @@ struct SmemStatus {
     __device__ __forceinline__ int operator()(int i) const { return p[i]; }
 };
 
-__host__ __device__ inline size_t replica_rc_bytes(int d0) {
-    return ((size_t)d0 * RC_WORDS * 4 + 15) & ~(size_t)15;
+__host__ __device__ inline size_t replica_rc_bytes(int d0, bool mm = false) {
+    return ((size_t)d0 * (mm ? 9 : 7) * 4 + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t replica_warp_bytes(int d0, int d1) {
+__host__ __device__ inline size_t replica_warp_bytes(int d0, int d1, bool mm = false) {
     size_t n = (size_t)d0 * d1;
     size_t a = (n + 15) & ~(size_t)15;
-    size_t b = ((size_t)d0 * RC_WORDS * 4 + 15) & ~(size_t)15;
-    return a + b;
+    return a + replica_rc_bytes(d0, mm);
 }
 
 // find the lane whose inclusive prefix first exceeds r; v = per-lane count.
@@ -138,28 +141,36 @@ __device__ __forceinline__ PickState pick_state_init(int lane) {
     PickState s; s.sc = lane & 15; s.spos = lane & 15; s.wprev = -1.0; s.cum = 0.0; s.need_sort = true; return s;
 }
 struct ClassPick { int csel; double total; uint32_t tie; bool zero; };
+// NL = number of lanes that hold a (weight, position) pair: 16 for the 13 classes of the reference's own rules,
+// 32 once MoveMonovacancy's four classes are in play (17 classes)
+template <int NL = 16>
+__device__ __forceinline__ PickState pick_state_init_n(int lane) {
+    PickState s; s.sc = lane & (NL - 1); s.spos = lane & (NL - 1); s.wprev = -1.0; s.cum = 0.0; s.need_sort = true; return s;
+}
+template <int NL = 16>
 __device__ __forceinline__ ClassPick pick_class(double w, int pos, PickState &st, double u1, int lane)
 {
+    constexpr uint32_t LANES = NL == 32 ? 0xFFFFFFFFu : 0xFFFFu;
     double ws = __shfl_sync(FULL, w, st.sc);
     const int ps = __shfl_sync(FULL, pos, st.sc);
     // first sorted position whose weight differs from the previous event
-    int first = (int)__reduce_min_sync(FULL, (lane < 16 && w != st.wprev) ? (unsigned)st.spos : 16u);
+    int first = (int)__reduce_min_sync(FULL, (lane < NL && w != st.wprev) ? (unsigned)st.spos : (unsigned)NL);
     st.wprev = w;
     {
         // is the previous order still (w, pos)-sorted?  (almost always)
         const double wp = __shfl_up_sync(FULL, ws, 1);
         const int pp = __shfl_up_sync(FULL, ps, 1);
-        const bool ok = (lane == 0) || (lane > 15) || (wp < ws) || (wp == ws && pp < ps);
+        const bool ok = (lane == 0) || (lane > NL - 1) || (wp < ws) || (wp == ws && pp < ps);
         if (st.need_sort || !__all_sync(FULL, ok)) {
-            // stable ascending sort (kmc.py:35) as a rank sort of the 16 unique (w, pos) keys
+            // stable ascending sort (kmc.py:35) as a rank sort of the NL unique (w, pos) keys
             int rank = 0;
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < NL; j++) {
                 const double wj = __shfl_sync(FULL, w, j);
                 const int pj = __shfl_sync(FULL, pos, j);
                 rank += (wj < w) || (wj == w && pj < pos);
             }
             st.spos = rank;
-            for (int j = 0; j < 16; j++) {
+            for (int j = 0; j < NL; j++) {
                 const int rj = __shfl_sync(FULL, rank, j);
                 if (rj == lane) st.sc = j;
             }
@@ -171,22 +182,22 @@ __device__ __forceinline__ ClassPick pick_class(double w, int pos, PickState &st
     ClassPick out;
     // zero weights are dropped (kmc.py:30); they sort first and adding them is exact, so the
     // sequential sum simply starts after them
-    const int z = __popc(__ballot_sync(FULL, ws == 0.0) & 0xFFFFu);
-    out.zero = (z == 16);
+    const int z = __popc(__ballot_sync(FULL, ws == 0.0) & LANES);
+    out.zero = (z == NL);
     const int start = first > z ? first : z;
-    double acc = __shfl_sync(FULL, st.cum, (start + 15) & 15);       // cumulative weight just before `start`
+    double acc = __shfl_sync(FULL, st.cum, (start + NL - 1) & (NL - 1));   // cumulative weight just before `start`
     if (start == z) acc = 0.0;
-    for (int k = start; k < 16; k++) {
+    for (int k = start; k < NL; k++) {
         const double wk = __shfl_sync(FULL, ws, k);
         acc = __dadd_rn(acc, wk);                              // util.py:65-68: sequential sums
         if (lane == k) st.cum = acc;
     }
-    if (start == 16) acc = __shfl_sync(FULL, st.cum, 15);     // nothing changed: total is the old one
+    if (start == NL) acc = __shfl_sync(FULL, st.cum, NL - 1);  // nothing changed: total is the old one
     out.total = acc;
     const double x = __dmul_rn(acc, u1);                       // random.uniform(0, total), kmc.py:49
-    const bool live = (lane >= z) && (lane < 16);
+    const bool live = (lane >= z) && (lane < NL);
     const uint32_t ge = __ballot_sync(FULL, live && st.cum >= x); // bisect_left, kmc.py:50
-    const int isel = ge ? (__ffs(ge) - 1) : 15;
+    const int isel = ge ? (__ffs(ge) - 1) : NL - 1;
     out.tie = __ballot_sync(FULL, live && st.cum == x);
     out.csel = __shfl_sync(FULL, st.sc, isel);
     return out;
@@ -221,6 +232,15 @@ __device__ __forceinline__ MoveNodes move_nodes(int row, int col, int slot, int 
         m.a1 = wrap_inc(wrap_dec(row + da, d0), d0);
         m.b1 = wrap_inc(wrap_dec(col + db, d1), d1);
         m.na = 2; m.ns0 = S_PRISTINE; m.ns1 = S_DIVAC; m.da1 = da;
+    } else if (slot >= MM_SLOT0) {
+        // MoveMonovacancy (direction k, layer L): source loses the layer; the target gains it -- its new status
+        // depends on its old one, the caller ORs that in (move_nodes_mm)
+        const int ri = kring((slot - MM_SLOT0) >> 1), layer = ((slot - MM_SLOT0) & 1) + 1;
+        const int da = (int)((RING_DA >> (4 * ri)) & 0xF) - 2;
+        const int db = (int)((RING_DB >> (4 * ri)) & 0xF) - 2;
+        m.a1 = wrap_inc(wrap_dec(row + da, d0), d0);
+        m.b1 = wrap_inc(wrap_dec(col + db, d1), d1);
+        m.na = 2; m.ns0 = s0 & ~layer; m.ns1 = layer; m.da1 = da;
     } else {
         const int o = (slot - 13) & 1;
         const bool create = slot < 15;
@@ -234,9 +254,16 @@ __device__ __forceinline__ MoveNodes move_nodes(int row, int col, int slot, int 
     }
     return m;
 }
+// the same with the lattice at hand: completes a MoveMonovacancy target (old status | layer)
+__device__ __forceinline__ MoveNodes move_nodes_st(const uint8_t *st, int row, int col, int slot, int s0, int d0, int d1)
+{
+    MoveNodes m = move_nodes(row, col, slot, s0, d0, d1);
+    if (slot >= MM_SLOT0) m.ns1 |= st[m.a1 * d1 + m.b1];
+    return m;
+}
 __device__ __forceinline__ void apply_move(uint8_t *st, int d0, int d1, int row, int col, int slot, int s0)
 {
-    const MoveNodes m = move_nodes(row, col, slot, s0, d0, d1);
+    const MoveNodes m = move_nodes_st(st, row, col, slot, s0, d0, d1);
     st[row * d1 + col] = (uint8_t)m.ns0;
     if (m.na > 1) st[m.a1 * d1 + m.b1] = (uint8_t)m.ns1;
     if (m.na > 2) st[m.a2 * d1 + m.b2] = (uint8_t)m.ns2;
@@ -246,12 +273,31 @@ __device__ __forceinline__ void apply_move(uint8_t *st, int d0, int d1, int row,
 // Canonical in-class order: rows ascending; inside a row the class's move slots in slot order; inside a
 // slot the sites by column.  A class owns 1, 2 or 6 slots: slot = class_slot_base(c) + bit index.
 __device__ __forceinline__ int class_slot_base(int c) {
-    //            c: 0  1  2  3  4  5  6   7   8  9  10 11 12
-    return (int)((0x6442'2FD7'7771'0ull >> (4 * c)) & 0xF);
+    //            c: 0  1  2  3  4  5  6   7   8  9  10 11 12     (13..16 MoveMonovacancy: 17)
+    return c >= C_MOVE_MONO ? MM_SLOT0 : (int)((0x6442'2FD7'7771'0ull >> (4 * c)) & 0xF);
 }
 // bit i set: the site carries the class's i-th slot
 __device__ __forceinline__ uint32_t site_slot_mask(const uint8_t *st, int a, int b, int d0, int d1, int c) {
     const int s0 = st[a * d1 + b];
+    if (c >= C_MOVE_MONO) {
+        // MoveMonovacancy kind c - 13: bit 2k + (L - 1) for direction k (neighbors_and_mutuals order), layer L
+        if (s0 < 1 || s0 > 3 || ((c - C_MOVE_MONO) >> 1) != (s0 == S_DIVAC)) return 0u;
+        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
+        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
+        const int ring[6] = {st[am * d1 + b], st[a * d1 + bm], st[ap * d1 + bm], st[ap * d1 + b], st[a * d1 + bp],
+                             st[am * d1 + bp]};
+        const int want_nonpristine = (c - C_MOVE_MONO) & 1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int dst = ring[kring(k)];
+#pragma unroll
+            for (int layer = 1; layer <= 2; layer++)
+                if ((s0 & layer) && dst <= 3 && !(dst & layer) && (int)(dst != 0) == want_nonpristine)
+                    out |= 1u << (2 * k + layer - 1);
+        }
+        return out;
+    }
     if (c >= C_MOVE_DIV && c < C_MOVE_DIV + 4) {
         if (s0 != S_DIVAC) return 0u;
         const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
@@ -282,36 +328,40 @@ __device__ __forceinline__ uint32_t site_slot_mask(const uint8_t *st, int a, int
     }
 }
 // the r-th move (0-based) of class c in row `row`: column and slot.  Two passes over the row: per-slot
-// totals, then a rank search among the sites of the chosen slot.
+// totals, then a rank search among the sites of the chosen slot.  NSL = slots a class can own: 6 for the
+// reference's own rules, 12 with MoveMonovacancy (direction x layer).
+template <int NSL = 6>
 __device__ __forceinline__ void find_in_row_bytes(const uint8_t *st, int d0, int d1, int row, int c, uint32_t r,
                                                   int lane, int &col, int &slot) {
+    constexpr int NP = NSL / 2;                              // packed pairs of 16-bit counters
     if (d1 > 64 && d1 <= 1024) {
         // Wide rows: each lane owns a contiguous run of <= 32 sites and evaluates every site ONCE, keeping
         // one bit mask per slot (a lane's sites share cache lines, and no cross-lane step sits between the
         // loads, so the latency of an HBM/L2-resident lattice is paid once, not once per 32-site chunk).
         const int per = (d1 + 31) >> 5;
         const int b0 = lane * per;
-        uint32_t m[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+        uint32_t m[NSL];
+#pragma unroll
+        for (int q = 0; q < NSL; q++) m[q] = 0u;
         for (int i = 0; i < per; i++) {
             const int b = b0 + i;
             const uint32_t sm = b < d1 ? site_slot_mask(st, row, b, d0, d1, c) : 0u;
 #pragma unroll
-            for (int q = 0; q < 6; q++) m[q] |= ((sm >> q) & 1u) << i;
+            for (int q = 0; q < NSL; q++) m[q] |= ((sm >> q) & 1u) << i;
         }
-        uint32_t a01 = __popc(m[0]) | (__popc(m[1]) << 16);
-        uint32_t a23 = __popc(m[2]) | (__popc(m[3]) << 16);
-        uint32_t a45 = __popc(m[4]) | (__popc(m[5]) << 16);
-        a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
-        int j = 0;
-        {
-            const uint32_t cnt[6] = {a01 & 0xFFFFu, a01 >> 16, a23 & 0xFFFFu, a23 >> 16, a45 & 0xFFFFu, a45 >> 16};
+        uint32_t cnt[NSL];
 #pragma unroll
-            for (int q = 0; q < 5; q++)
-                if (j == q && r >= cnt[q]) { r -= cnt[q]; j = q + 1; }
+        for (int q = 0; q < NP; q++) {
+            const uint32_t a = __reduce_add_sync(FULL, __popc(m[2 * q]) | (__popc(m[2 * q + 1]) << 16));
+            cnt[2 * q] = a & 0xFFFFu; cnt[2 * q + 1] = a >> 16;
         }
+        int j = 0;
+#pragma unroll
+        for (int q = 0; q < NSL - 1; q++)
+            if (j == q && r >= cnt[q]) { r -= cnt[q]; j = q + 1; }
         uint32_t mine = m[0];
 #pragma unroll
-        for (int q = 1; q < 6; q++) mine = j == q ? m[q] : mine;
+        for (int q = 1; q < NSL; q++) mine = j == q ? m[q] : mine;
         int L = 0;
         warp_rank_search(__popc(mine), r, L, lane);           // r becomes the rank inside lane L's run
         uint32_t mL = __shfl_sync(FULL, mine, L);
@@ -320,20 +370,25 @@ __device__ __forceinline__ void find_in_row_bytes(const uint8_t *st, int d0, int
         slot = class_slot_base(c) + j;
         return;
     }
-    uint32_t a01 = 0, a23 = 0, a45 = 0;                     // six 16-bit per-slot counters
+    uint32_t acc[NP];                                        // NSL 16-bit per-slot counters
+#pragma unroll
+    for (int q = 0; q < NP; q++) acc[q] = 0u;
     for (int base = 0; base < d1; base += 32) {
         const int b = base + lane;
         const uint32_t m = b < d1 ? site_slot_mask(st, row, b, d0, d1, c) : 0u;
-        a01 += (m & 1u) | ((m & 2u) << 15);
-        a23 += ((m >> 2) & 1u) | ((m & 8u) << 13);
-        a45 += ((m >> 4) & 1u) | ((m & 32u) << 11);
+#pragma unroll
+        for (int q = 0; q < NP; q++) acc[q] += ((m >> (2 * q)) & 1u) | (((m >> (2 * q + 1)) & 1u) << 16);
     }
-    a01 = __reduce_add_sync(FULL, a01); a23 = __reduce_add_sync(FULL, a23); a45 = __reduce_add_sync(FULL, a45);
     int j = 0;
     {
-        const uint32_t cnt[6] = {a01 & 0xFFFFu, a01 >> 16, a23 & 0xFFFFu, a23 >> 16, a45 & 0xFFFFu, a45 >> 16};
+        uint32_t cnt[NSL];
 #pragma unroll
-        for (int q = 0; q < 5; q++)
+        for (int q = 0; q < NP; q++) {
+            const uint32_t a = __reduce_add_sync(FULL, acc[q]);
+            cnt[2 * q] = a & 0xFFFFu; cnt[2 * q + 1] = a >> 16;
+        }
+#pragma unroll
+        for (int q = 0; q < NSL - 1; q++)
             if (j == q && r >= cnt[q]) { r -= cnt[q]; j = q + 1; }
     }
     col = 0;
@@ -346,25 +401,32 @@ __device__ __forceinline__ void find_in_row_bytes(const uint8_t *st, int d0, int
     slot = class_slot_base(c) + j;
 }
 
-// per-row class counts of row `a`, as 7 pair-words (two uint16 fields each)
-__device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int d1, uint32_t out[RC_WORDS]) {
+// per-row class counts of row `a`, as 7 (9 with MoveMonovacancy) pair-words (two uint16 fields each)
+template <bool MM = false>
+__device__ __forceinline__ void row_counts(const uint8_t *st, int a, int d0, int d1, uint32_t out[RcWords<MM>::value]) {
     SmemStatus S{st};
-    uint32_t A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0, A3 = 0;
+    uint32_t A0 = 0, B0 = 0, A1 = 0, B1 = 0, A2 = 0, B2 = 0, A3 = 0, B3 = 0, A4 = 0;
     for (int b = 0; b < d1; b++) {
-        F4 f = eval_site(S, a, b, d0, d1);
+        F4 f = eval_site<MM>(S, a, b, d0, d1);
         A0 += f.w0 & 0x00FF00FFu; B0 += (f.w0 >> 8) & 0x00FF00FFu;
         A1 += f.w1 & 0x00FF00FFu; B1 += (f.w1 >> 8) & 0x00FF00FFu;
         A2 += f.w2 & 0x00FF00FFu; B2 += (f.w2 >> 8) & 0x00FF00FFu;
         A3 += f.w3 & 0x00FF00FFu;
+        if (MM) { B3 += (f.w3 >> 8) & 0x00FF00FFu; A4 += f.w4 & 0x00FF00FFu; }
     }
     out[0] = A0; out[1] = B0; out[2] = A1; out[3] = B1; out[4] = A2; out[5] = B2; out[6] = A3;
+    if (MM) { out[7] = B3; out[8] = A4; }
 }
 
 // GLOBAL_STATE = true: the lattice stays in HBM/L2 (lattices too large for shared memory, e.g.
 // 1024x1024 = 1 MiB per replica, BASELINE config 5); only the row-count hierarchy is in shared memory.
-template <int TD0, int TD1, bool GLOBAL_STATE = false>
+// MM = true: MoveMonovacancy's four classes are maintained as well (17 classes, 9 row-count words, 32 weight lanes).
+template <int TD0, int TD1, bool GLOBAL_STATE = false, bool MM = false>
 __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams p)
 {
+    constexpr int RCW = RcWords<MM>::value;          // row-count words per row
+    constexpr int NCX = MM ? NCA : NC;               // classes this build maintains
+    constexpr int NL = MM ? 32 : 16;                 // lanes holding a class weight
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
     const int n = d0 * d1;
@@ -380,9 +442,9 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     uint32_t *rc;
     if (GLOBAL_STATE) {
         st = gst;
-        rc = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_rc_bytes(d0));
+        rc = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_rc_bytes(d0, MM));
     } else {
-        st = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_warp_bytes(d0, d1);
+        st = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_warp_bytes(d0, d1, MM);
         rc = reinterpret_cast<uint32_t *>(st + (((size_t)n + 15) & ~(size_t)15));
     }
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(rc);
@@ -401,30 +463,30 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
 
     // ---- build the row hierarchy (a full enumeration, as Rule.initialize_moves does) --------
     if (GLOBAL_STATE && p.hier && p.hier_valid) {
-        const uint32_t *src = p.hier + (size_t)rep * d0 * RC_WORDS;
-        for (int i = lane; i < d0 * RC_WORDS; i += 32) rc[i] = src[i];
+        const uint32_t *src = p.hier + (size_t)rep * d0 * RCW;
+        for (int i = lane; i < d0 * RCW; i += 32) rc[i] = src[i];
     } else {
         for (int a = lane; a < d0; a += 32) {
-            uint32_t w[RC_WORDS];
-            row_counts(st, a, d0, d1, w);
+            uint32_t w[RCW];
+            row_counts<MM>(st, a, d0, d1, w);
 #pragma unroll
-            for (int j = 0; j < RC_WORDS; j++) rc[a * RC_WORDS + j] = w[j];
+            for (int j = 0; j < RCW; j++) rc[a * RCW + j] = w[j];
         }
     }
     __syncwarp();
 
     // per-lane class state: lane c < 13 owns class c; lanes 13..15 are permanent zero weights
-    const int myc = lane < NC ? lane : 0;
-    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    const int myc = lane < NCX ? lane : 0;
+    const double rate = (lane < NCX && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (lane < NCX && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
     int tot = 0;
-    if (lane < NC) {
+    if (lane < NCX) {
         const int f = rc_field(lane);
-        for (int a = 0; a < d0; a++) tot += rc16[a * (2 * RC_WORDS) + f];
+        for (int a = 0; a < d0; a++) tot += rc16[a * (2 * RCW) + f];
     }
     unsigned long long hist = 0, hops = 0;
     unsigned long long n_ties = 0;
-    PickState pstate = pick_state_init(lane);
+    PickState pstate = pick_state_init_n<NL>(lane);
     double tclock = p.clock ? p.clock[rep] : 0.0;          // continues across launches in event order
     uint32_t *const tracer = p.tracer ? p.tracer + (size_t)rep * n : nullptr;
 
@@ -462,7 +524,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const double w = __dmul_rn((double)tot, rate);       // lanes >= 13: tot = 0, rate = 0
 
         // ---- 2. class choice -------------------------------------------------------------------
-        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
+        const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
         if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && lane == 0) {
@@ -490,7 +552,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-            if (lane < NC) rec->counts[lane] = (uint32_t)tot;
+            if (lane < NCA) rec->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
         }
 
         // ---- 3. in-class pick --------------------------------------------------------------------
@@ -510,13 +572,13 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
                 const int r0 = base + K * lane;
                 uint32_t sum = 0;
                 for (int q = 0; q < K; q++)
-                    if (r0 + q < d0) sum += rc16[(r0 + q) * (2 * RC_WORDS) + f];
+                    if (r0 + q < d0) sum += rc16[(r0 + q) * (2 * RCW) + f];
                 int L;
                 if (warp_rank_search(sum, r, L, lane)) {
                     // walk the owner lane's rows (uniform: every lane reads the same entries)
                     row = base + K * L;
                     for (int q = 0; q < K - 1; q++) {
-                        const uint32_t v = rc16[row * (2 * RC_WORDS) + f];
+                        const uint32_t v = rc16[row * (2 * RCW) + f];
                         if (r < v) break;
                         r -= v; row++;
                     }
@@ -526,7 +588,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         }
         // 3b/3c. site within the row and slot (row, slot, column order)
         int col, slot;
-        find_in_row_bytes(st, d0, d1, row, csel, r, lane, col, slot);
+        find_in_row_bytes<MM ? 12 : 6>(st, d0, d1, row, csel, r, lane, col, slot);
         const int site = row * d1 + col;
         const int s0 = st[site];
 
@@ -550,10 +612,10 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         if (tie && lane == 0) n_ties++;
 
         // ---- 4. the move: touched nodes and their new status (uniform) --------------------------------
-        const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
+        const MoveNodes mv = move_nodes_st(st, row, col, slot, s0, d0, d1);
         const int na = mv.na, a1 = mv.a1, b1 = mv.b1, a2 = mv.a2, b2 = mv.b2;
         const int ns0 = mv.ns0, ns1 = mv.ns1, ns2 = mv.ns2;
-        if (tracer && lane == 0) tracer_update(tracer, slot, na, site, ns0, a1 * d1 + b1, ns1, a2 * d1 + b2, ns2);
+        if (tracer && lane == 0) tracer_update(tracer, slot, na, site, ns0, a1 * d1 + b1, ns1, a2 * d1 + b2, ns2, s0);
 
         // ---- 5. neighbourhood refresh -----------------------------------------------------------------
         const bool act = my_i < na;
@@ -567,8 +629,8 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         const bool leader = act && ((__ffs(same) - 1) == lane);
 
         SmemStatus S{st};
-        F4 fb = {0u, 0u, 0u, 0u};
-        if (leader) fb = eval_site(S, xa, xb, d0, d1);
+        F4 fb = {0u, 0u, 0u, 0u, 0u};
+        if (leader) fb = eval_site<MM>(S, xa, xb, d0, d1);
         __syncwarp();
         if (lane == 0) {
             st[site] = (uint8_t)ns0;
@@ -576,12 +638,12 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
             if (na > 2) st[a2 * d1 + b2] = (uint8_t)ns2;
         }
         __syncwarp();
-        F4 fa = {0u, 0u, 0u, 0u};
-        if (leader) fa = eval_site(S, xa, xb, d0, d1);
+        F4 fa = {0u, 0u, 0u, 0u, 0u};
+        if (leader) fa = eval_site<MM>(S, xa, xb, d0, d1);
 
         // per-byte (after - before), biased by 0x80 so no borrow crosses bytes; then spread to
         // 16-bit pair-words whose integer value is hi*65536 + lo with signed lo, hi
-        uint32_t dw[RC_WORDS];
+        uint32_t dw[RCW];
         {
             const uint32_t e0 = (fa.w0 | 0x80808080u) - fb.w0, e1 = (fa.w1 | 0x80808080u) - fb.w1;
             const uint32_t e2 = (fa.w2 | 0x80808080u) - fb.w2, e3 = (fa.w3 | 0x80808080u) - fb.w3;
@@ -589,15 +651,20 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
             dw[2] = (e1 & 0x00FF00FFu) - 0x00800080u; dw[3] = ((e1 >> 8) & 0x00FF00FFu) - 0x00800080u;
             dw[4] = (e2 & 0x00FF00FFu) - 0x00800080u; dw[5] = ((e2 >> 8) & 0x00FF00FFu) - 0x00800080u;
             dw[6] = (e3 & 0x00FF00FFu) - 0x00800080u;
+            if (MM) {
+                const uint32_t e4 = (fa.w4 | 0x80808080u) - fb.w4;
+                dw[7] = ((e3 >> 8) & 0x00FF00FFu) - 0x00800080u;
+                dw[8] = (e4 & 0x00FF00FFu) - 0x00800080u;
+            }
         }
         // row counts: the few lanes with a change add their packed deltas
 #pragma unroll
-        for (int j = 0; j < RC_WORDS; j++)
-            if (dw[j] != 0u) atomicAdd(&rc[xa * RC_WORDS + j], dw[j]);
+        for (int j = 0; j < RCW; j++)
+            if (dw[j] != 0u) atomicAdd(&rc[xa * RCW + j], dw[j]);
         // class totals: warp-sum of the packed deltas, then lane c unpacks its own field
         int keep = 0;
 #pragma unroll
-        for (int j = 0; j < RC_WORDS; j++) {
+        for (int j = 0; j < RCW; j++) {
             const int sj = (int)__reduce_add_sync(FULL, dw[j]);
             if (lane == j) keep = sj;
         }
@@ -606,7 +673,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
             const int v = __shfl_sync(FULL, keep, fld >> 1);
             const int lo = (int)(short)(v & 0xFFFF);
             const int hi = (v - lo) >> 16;
-            if (lane < NC) tot += (fld & 1) ? hi : lo;
+            if (lane < NCX) tot += (fld & 1) ? hi : lo;
         }
         __syncwarp();
     }
@@ -617,15 +684,15 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
         // KmcSim.validate (sim.py:159-168): incremental tables vs a fresh enumeration
         bool bad = false;
         for (int a = lane; a < d0; a += 32) {
-            uint32_t w[RC_WORDS];
-            row_counts(st, a, d0, d1, w);
+            uint32_t w[RCW];
+            row_counts<MM>(st, a, d0, d1, w);
 #pragma unroll
-            for (int j = 0; j < RC_WORDS; j++) bad |= (rc[a * RC_WORDS + j] != w[j]);
+            for (int j = 0; j < RCW; j++) bad |= (rc[a * RCW + j] != w[j]);
         }
-        if (lane < NC) {
+        if (lane < NCX) {
             const int f = rc_field(lane);
             int fresh = 0;
-            for (int a = 0; a < d0; a++) fresh += rc16[a * (2 * RC_WORDS) + f];
+            for (int a = 0; a < d0; a++) fresh += rc16[a * (2 * RCW) + f];
             bad |= (fresh != tot);
         }
         if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
@@ -633,8 +700,8 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     if (GLOBAL_STATE) {
         // the lattice was updated in place; keep the hierarchy for the next launch
         if (p.hier) {
-            uint32_t *dst = p.hier + (size_t)rep * d0 * RC_WORDS;
-            for (int i = lane; i < d0 * RC_WORDS; i += 32) dst[i] = rc[i];
+            uint32_t *dst = p.hier + (size_t)rep * d0 * RCW;
+            for (int i = lane; i < d0 * RCW; i += 32) dst[i] = rc[i];
         }
     } else if ((n & 15) == 0) {
         uint4 *dst = reinterpret_cast<uint4 *>(gst);
@@ -643,7 +710,7 @@ __global__ void __launch_bounds__(256, 4) kmc_replica_kernel(const ReplicaParams
     } else {
         for (int i = lane; i < n; i += 32) gst[i] = st[i];
     }
-    if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < NCX) p.hist[(size_t)rep * NCA + lane] += hist;
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-            if (lane < NC) rec->counts[lane] = (uint32_t)tot;
+            if (lane < NCA) rec->counts[lane] = lane < NC ? (uint32_t)tot : 0u;
         }
         const int cnt = __shfl_sync(FULL, tot, csel);
         uint32_t r;
@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide_kernel(const WidePara
         if (fresh != tot || blocks != tot) flag |= FLAG_VALIDATE;      // totals and block sums vs the row table
     }
     flag = __reduce_or_sync(FULL, flag);
-    if (lane < NC) p.hist[(size_t)rep * NC + lane] += hist;
+    if (lane < NC) p.hist[(size_t)rep * NCA + lane] += hist;
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
         if (tid < NC)
             for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
         if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
+            if (tid < NC) p.counts[(size_t)rep * NCA + tid] = s;
         } else {
             if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
             __syncwarp();
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }
@@ -456,7 +456,7 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
         if (tid < NC)
             for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
         if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NC + tid] = s;
+            if (tid < NC) p.counts[(size_t)rep * NCA + tid] = s;
         } else {
             if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
             __syncwarp();
@@ -468,7 +468,7 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
     if (tid < 32) {
         const unsigned long long sum = tid < NC ? tot_sm[tid] : 0ull;
         if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NC + tid] = sum;
+            if (tid < NC) p.counts[(size_t)rep * NCA + tid] = sum;
         } else {
             if (tid < NC && sum) atomicAdd(&p.acc[(size_t)rep * 16 + tid], sum);
             __syncwarp();
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NC + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }
@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(256) kmc_sweep_kernel_generic(const SweepParam
     }
 }
 
-// class totals per replica from the row counts: counts[R][13]
+// class totals per replica from the row counts: counts[R][NCA]
 __global__ void kmc_reduce_counts_kernel(const uint32_t *rowcnt, int d0, int n_replicas,
                                          unsigned long long *counts)
 {
@@ -873,7 +873,75 @@ __global__ void kmc_reduce_counts_kernel(const uint32_t *rowcnt, int d0, int n_r
     for (int a = part; a < d0; a += nparts) s += rowcnt[((size_t)rep * d0 + a) * RCG_STRIDE + c];
     atomicAdd(&acc[c], s);
     __syncthreads();
-    if (threadIdx.x < NC) counts[(size_t)rep * NC + threadIdx.x] = acc[threadIdx.x];
+    if (threadIdx.x < NCA) counts[(size_t)rep * NCA + threadIdx.x] = threadIdx.x < NC ? acc[threadIdx.x] : 0ull;
+}
+
+// ---- MoveMonovacancy-aware full enumeration: all 9 rules, 29 slot planes, 17 classes -----------------------
+// One thread per site (any shape).  Row counts use a stride of RCG_STRIDE_MM words and must be zero on entry.
+constexpr int RCG_STRIDE_MM = 32;
+__global__ void __launch_bounds__(256) kmc_sweep_kernel_mm(const SweepParams p)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)p.n_replicas * p.n) return;
+    const int rep = (int)(g / p.n);
+    const int i = (int)(g - (long long)rep * p.n);
+    const int a = i / p.d1, b = i - a * p.d1;
+    const uint8_t *st = p.status + (size_t)rep * p.n;
+    struct G { const uint8_t *p; __device__ int operator()(int k) const { return __ldg(p + k); } } S{st};
+    const int d0 = p.d0, d1 = p.d1;
+    const int s0 = st[i];
+    uint8_t out[NSA];
+#pragma unroll
+    for (int j = 0; j < NSA; j++) out[j] = 0xFF;
+    if (s0 == 0) { out[0] = C_CREATE_DIV; out[2] = out[3] = C_CMONO_FROM_DOUBLE; }
+    if (s0 == 1) { out[3] = C_CMONO_MAKE_EMPTY; out[4] = C_FMONO_MAKE_DOUBLE; out[6] = C_FLIP; }
+    if (s0 == 2) { out[2] = C_CMONO_MAKE_EMPTY; out[5] = C_FMONO_MAKE_DOUBLE; out[6] = C_FLIP; }
+    if (s0 >= 1 && s0 <= 3) {
+        const int am = wrap_dec(a - 1, d0), ap = wrap_inc(a + 1, d0);
+        const int bm = wrap_dec(b - 1, d1), bp = wrap_inc(b + 1, d1);
+        const int ring[6] = {S(am * d1 + b), S(a * d1 + bm), S(ap * d1 + bm), S(ap * d1 + b), S(a * d1 + bp), S(am * d1 + bp)};
+        // MoveMonovacancy: layer L of this site hops to neighbour k if that neighbour's layer set lacks L
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int dst = ring[kring(k)];
+#pragma unroll
+            for (int layer = 1; layer <= 2; layer++)
+                if ((s0 & layer) && dst <= 3 && !(dst & layer))
+                    out[MM_SLOT0 + 2 * k + layer - 1] = (uint8_t)(C_MOVE_MONO + 2 * (s0 == 3) + (dst != 0));
+        }
+        if (s0 == 3) {
+            out[1] = C_FILL_DIV; out[4] = out[5] = C_FMONO_FROM_EMPTY;
+            RingMasks m = ring_masks(ring[0], ring[1], ring[2], ring[3], ring[4], ring[5]);
+            for (int k = 0; k < 6; k++) {
+                const int ri = kring(k);
+                if ((m.P >> ri) & 1) out[7 + k] = (uint8_t)(C_MOVE_DIV + ((m.N >> ri) & 1) + 2 * ((m.F >> ri) & 1));
+            }
+            const int ap2 = wrap_inc(a + 2, d0), bp2 = wrap_inc(b + 2, d1), bm2 = wrap_dec(b - 2, d1);
+            const bool t20 = S(ap2 * d1 + b) == 3;
+            if (t20 && S(a * d1 + bp2) == 3) out[13] = C_CREATE_TREF;
+            if (t20 && S(ap2 * d1 + bm2) == 3) out[14] = C_CREATE_TREF;
+        }
+    }
+    if (s0 == 4) out[15] = C_DESTROY_TREF;
+    if (s0 == 7) out[16] = C_DESTROY_TREF;
+    uint32_t *R = p.rowcnt + ((size_t)rep * d0 + a) * RCG_STRIDE_MM;
+    for (int j = 0; j < NSA; j++) {
+        if (p.slots) p.slots[((size_t)rep * NSA + j) * p.n + i] = out[j];
+        if (out[j] != 0xFF) atomicAdd(R + out[j], 1u);
+    }
+}
+__global__ void kmc_reduce_counts_mm_kernel(const uint32_t *rowcnt, int d0, int n_replicas, unsigned long long *counts)
+{
+    const int rep = blockIdx.x;
+    const int c = threadIdx.x & 31, part = threadIdx.x >> 5, nparts = blockDim.x >> 5;
+    __shared__ unsigned long long acc[32];
+    if (threadIdx.x < 32) acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long s = 0;
+    for (int a = part; a < d0; a += nparts) s += rowcnt[((size_t)rep * d0 + a) * RCG_STRIDE_MM + c];
+    atomicAdd(&acc[c], s);
+    __syncthreads();
+    if (threadIdx.x < NCA) counts[(size_t)rep * NCA + threadIdx.x] = acc[threadIdx.x];
 }
 
 }  // namespace kmc

@@ -179,7 +179,8 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     parallel.shutdown()
     if rank != 0:
         return
-    hist, hops, done = sums[:13], sums[13:19], sums[19]
+    nc = T.N_CLASSES
+    hist, hops, done = sums[:nc], sums[nc:nc + 6], sums[nc + 6]
     out = {"grid": grid_info(dims), "temperature": temperature, "rates": info, "replicas": replicas,
            "seed": seed, "events_done": int(done), "processes": size,
            "histogram": {"%s:%s" % T.CLASSES[c]: int(hist[c]) for c in order},

@@ -11,8 +11,8 @@ import numpy as np
 PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(PKG_ROOT, "libkmc_b200.so")
 
-N_CLASSES = 13
-N_SLOTS = 17
+N_CLASSES = 17
+N_SLOTS = 29
 SLOT_NONE = 0xFF
 CLASS_NONE = 0xFF
 LOG_NONE, LOG_COMPACT, LOG_FULL = 0, 1, 2
@@ -25,7 +25,7 @@ EVENT_COMPACT = np.dtype([("site", "<u4"), ("cls", "u1"), ("slot", "u1"), ("flag
                           ("total_rate", "<f8")])
 EVENT_FULL = np.dtype([("site", "<u4"), ("cls", "u1"), ("slot", "u1"), ("flags", "<u2"),
                        ("total_rate", "<f8"), ("counts", "<u4", (N_CLASSES,)), ("pad", "<u4")])
-assert EVENT_COMPACT.itemsize == 16 and EVENT_FULL.itemsize == 72
+assert EVENT_COMPACT.itemsize == 16 and EVENT_FULL.itemsize == 88
 
 # every symbol include/kmc_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = {

@@ -6,10 +6,10 @@ flag and exactly one of `barrier` / `rate`, given as a number (shorthand for {na
 {kind: number} mapping with non-negative values; `state.random` with `mode` in {exact, approx} and
 `divacancy` / `monovacancy` fractions (float or "N%").  Several files are deep-merged, later wins.
 
-Two deliberate tolerances so that the reference's own shipped files load as they are:
+Two deliberate differences so that the reference's own shipped files run as they are:
   * a leading "Rule" in a rule name is accepted (test-cfg.yaml still uses the class names);
-  * a rule the reference only stubs (MoveMonovacancy, rules.py:295-296) is skipped with a warning
-    instead of raising NotImplementedError.
+  * MoveMonovacancy, which config/WSe2.yaml:8-13 names with four kinds but the reference only stubs
+    (rules.py:295-296 -> NotImplementedError), is a real rule here (semantics: tables.py / DESIGN.md section 2).
 """
 import logging
 import warnings
@@ -44,11 +44,6 @@ def consume_rule_specs(config):
     for key in list(rules_map):
         name = key[4:] if key.startswith("Rule") else key
         rule_map = rules_map.pop(key)
-        if name in T.STUB_RULES:
-            enabled = rule_map.get("enabled", True) if isinstance(rule_map, dict) else True
-            if enabled:
-                warnings.warn("config: rule %s is a stub in the reference (no semantics defined); skipped" % name)
-            continue
         if name not in T.RULE_KINDS:
             error("unknown rule: %s" % name)
         enabled = rule_map.pop("enabled", True)

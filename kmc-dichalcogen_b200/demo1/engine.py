@@ -18,7 +18,9 @@ class Engine:
         self.device = int(device)
         self._lib = nat.load()
         self._h = C.c_void_p()
-        rates = (C.c_double * nat.N_CLASSES)(*[float(x) for x in class_rates])
+        class_rates = [float(x) for x in class_rates]
+        class_rates += [0.0] * (nat.N_CLASSES - len(class_rates))       # 13-entry tables predate MoveMonovacancy
+        rates = (C.c_double * nat.N_CLASSES)(*class_rates)
         order = (C.c_int * max(1, len(class_order)))(*[int(c) for c in class_order])
         nat.check(self._lib.kmc_create(C.byref(self._h), self.device, self.dim[0], self.dim[1],
                                        self.n_replicas, rates, order, len(class_order)))

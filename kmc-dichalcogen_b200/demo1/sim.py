@@ -234,6 +234,10 @@ class KmcSim:
             elif sl <= 12:
                 da, db = T.MOVE_TARGET[sl - 7]
                 mv = '{"now": [%d, %d], "was": [%d, %d]}' % ((x + da) % d0, (y + db) % d1, x, y)
+            elif sl >= T.MM_SLOT0:
+                da, db = T.MOVE_TARGET[(sl - T.MM_SLOT0) >> 1]
+                mv = '{"layer": %d, "now": [%d, %d], "was": [%d, %d]}' % (
+                    ((sl - T.MM_SLOT0) & 1) + 1, (x + da) % d0, (y + db) % d1, x, y)
             else:
                 m = T.TREFOIL_MEMBERS[(sl - 13) & 1]
                 mv = '{"nodes": [[%d, %d], [%d, %d], [%d, %d]]}' % (

@@ -21,6 +21,13 @@ CLASSES = [
     ("CreateMonovacancy", "from-double"), ("CreateMonovacancy", "make-empty"),
     ("FillMonovacancy", "make-double"), ("FillMonovacancy", "from-empty"),
     ("FlipMonovacancy", "natural"),
+    # MoveMonovacancy: named with four kinds and barriers in the reference's config/WSe2.yaml:8-13 but only a
+    # stub there (rules.py:295-296).  Extension with stated semantics: the chalcogen
+    # vacancy in one layer of a node hops to a neighbouring node whose layer set lacks that layer;
+    # kind = [natural, merge-divacancy, split-divacancy, swap-divacancy][2 * (source is a divacancy)
+    #                                                                    + (target is not pristine)]
+    ("MoveMonovacancy", "natural"), ("MoveMonovacancy", "merge-divacancy"),
+    ("MoveMonovacancy", "split-divacancy"), ("MoveMonovacancy", "swap-divacancy"),
 ]
 CLASS_ID = {rk: i for i, rk in enumerate(CLASSES)}
 N_CLASSES = len(CLASSES)
@@ -30,12 +37,15 @@ RULE_KINDS = {}
 for _r, _k in CLASSES:
     RULE_KINDS.setdefault(_r, []).append(_k)
 IMPLEMENTED_RULES = list(RULE_KINDS)
-# named in config/WSe2.yaml:8-13 but a stub in the reference (rules.py:295-296)
-STUB_RULES = {"MoveMonovacancy": ["natural", "merge-divacancy", "split-divacancy", "swap-divacancy"]}
+STUB_RULES = {}                     # (round 1: MoveMonovacancy was skipped with a warning)
+# classes the reference implements itself; 13.. are the MoveMonovacancy extension
+N_REFERENCE_CLASSES = 13
 
-N_SLOTS = 17
+N_SLOTS = 29
+MM_SLOT0 = 17                       # MoveMonovacancy (node, nbr_k, layer): slot 17 + 2*k + (layer - 1)
 SLOT_RULE = (["CreateDivacancy", "FillDivacancy"] + ["CreateMonovacancy"] * 2 + ["FillMonovacancy"] * 2 +
-             ["FlipMonovacancy"] + ["MoveDivacancy"] * 6 + ["CreateTrefoil"] * 2 + ["DestroyTrefoil"] * 2)
+             ["FlipMonovacancy"] + ["MoveDivacancy"] * 6 + ["CreateTrefoil"] * 2 + ["DestroyTrefoil"] * 2 +
+             ["MoveMonovacancy"] * 12)
 
 # neighbors_and_mutuals order (state.py:443-459): offset of the move target for slot 7 + k
 MOVE_TARGET = [(-1, 1), (0, -1), (1, 0), (0, 1), (-1, 0), (1, -1)]
@@ -62,6 +72,9 @@ def move_info(site, slot, dim):
         return {"node": list(p), "layer": slot - 1 if slot <= 3 else slot - 3}
     if 7 <= slot <= 12:
         return {"was": list(p), "now": list(add(p, MOVE_TARGET[slot - 7], dim))}
+    if slot >= MM_SLOT0:
+        k, layer = divmod(slot - MM_SLOT0, 2)
+        return {"was": list(p), "now": list(add(p, MOVE_TARGET[k], dim)), "layer": layer + 1}
     orient = (slot - 13) & 1
     return {"nodes": [list(add(p, off, dim)) for off in TREFOIL_MEMBERS[orient]]}
 
@@ -87,6 +100,12 @@ def slot_of_move(rule, move, dim):
         if len(ks) != 1:
             raise ValueError("not a nearest-neighbour move: %r" % (move,))
         return lin(old), 7 + ks[0]
+    if rule == "MoveMonovacancy":
+        old, new, layer = move
+        ks = [k for k in range(6) if add(old, MOVE_TARGET[k], dim) == add(new, (0, 0), dim)]
+        if len(ks) != 1 or layer not in (1, 2):
+            raise ValueError("not a nearest-neighbour single-layer move: %r" % (move,))
+        return lin(old), MM_SLOT0 + 2 * ks[0] + (layer - 1)
     if rule in ("CreateTrefoil", "DestroyTrefoil"):
         want = set(add(tuple(n), (0, 0), dim) for n in move)
         for p in want:
@@ -127,6 +146,9 @@ def replay_event(status, event, dim):
     elif rule == "MoveDivacancy":
         status[lin(mv["was"])] = 0
         status[lin(mv["now"])] = 3
+    elif rule == "MoveMonovacancy":
+        status[lin(mv["was"])] &= ~mv["layer"] & 0xFF
+        status[lin(mv["now"])] |= mv["layer"]
     elif rule in ("CreateTrefoil", "DestroyTrefoil"):
         site, slot = slot_of_move(rule, [tuple(n) for n in mv["nodes"]], dim)
         orient = (slot - 13) & 1

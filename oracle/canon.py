@@ -55,19 +55,27 @@ CLASSES = [
     ("FillMonovacancy", "make-double"),      # 10
     ("FillMonovacancy", "from-empty"),       # 11
     ("FlipMonovacancy", "natural"),          # 12
+    # MoveMonovacancy is a stub in the reference (rules.py:295-296); its kinds are named in config/WSe2.yaml:8-13.
+    # Semantics: oracle/move_monovacancy.py (extension, stated in DESIGN.md).
+    ("MoveMonovacancy", "natural"),          # 13  monovacancy -> pristine neighbour
+    ("MoveMonovacancy", "merge-divacancy"),  # 14  monovacancy -> neighbour with the opposite-layer monovacancy
+    ("MoveMonovacancy", "split-divacancy"),  # 15  one layer of a divacancy -> pristine neighbour
+    ("MoveMonovacancy", "swap-divacancy"),   # 16  one layer of a divacancy -> opposite-layer monovacancy
 ]
 N_CLASSES = len(CLASSES)
 CLASS_ID = {rk: i for i, rk in enumerate(CLASSES)}
 RULES = ["CreateDivacancy", "FillDivacancy", "MoveDivacancy", "CreateTrefoil",
-         "DestroyTrefoil", "CreateMonovacancy", "FillMonovacancy", "FlipMonovacancy"]
+         "DestroyTrefoil", "CreateMonovacancy", "FillMonovacancy", "FlipMonovacancy", "MoveMonovacancy"]
 RULE_KINDS = {r: [k for (rr, k) in CLASSES if rr == r] for r in RULES}
 
 # --- per-site move slots ------------------------------------------------------------------
-N_SLOTS = 17
+N_SLOTS = 29
 SLOT_NONE = 0xFF
+# slots 17..28: MoveMonovacancy (node, nbr_k, layer) at 17 + 2*k + (layer - 1), k in neighbors_and_mutuals order
+MM_SLOT0 = 17
 SLOT_RULE = (["CreateDivacancy", "FillDivacancy"] + ["CreateMonovacancy"] * 2 +
              ["FillMonovacancy"] * 2 + ["FlipMonovacancy"] + ["MoveDivacancy"] * 6 +
-             ["CreateTrefoil"] * 2 + ["DestroyTrefoil"] * 2)
+             ["CreateTrefoil"] * 2 + ["DestroyTrefoil"] * 2 + ["MoveMonovacancy"] * 12)
 assert len(SLOT_RULE) == N_SLOTS
 
 
@@ -123,6 +131,9 @@ def move_from_slot(site, slot, status, dim):
         return rule, (p, layer, status & ~layer)
     if 7 <= slot <= 12:
         return rule, (p, add(p, NBR_NEAR_FAR[slot - 7][0], dim))
+    if slot >= MM_SLOT0:
+        k, layer = divmod(slot - MM_SLOT0, 2)
+        return rule, (p, add(p, NBR_NEAR_FAR[k][0], dim), layer + 1)
     orient = (slot - 13) & 1
     return rule, frozenset(trefoil_nodes(p, orient, dim))
 
@@ -143,6 +154,12 @@ def slot_from_move(rule, move, dim):
         if len(ks) != 1:
             raise ValueError("aliased MoveDivacancy geometry (lattice too small): %r" % (move,))
         return lin(old, dim), 7 + ks[0]
+    if rule == "MoveMonovacancy":
+        old, new, layer = move
+        ks = [k for k in range(6) if add(old, NBR_NEAR_FAR[k][0], dim) == tuple(new)]
+        if len(ks) != 1:
+            raise ValueError("aliased MoveMonovacancy geometry (lattice too small): %r" % (move,))
+        return lin(old, dim), MM_SLOT0 + 2 * ks[0] + (layer - 1)
     if rule in ("CreateTrefoil", "DestroyTrefoil"):
         anchor, orient = trefoil_anchor(move, dim)
         return lin(anchor, dim), (13 if rule == "CreateTrefoil" else 15) + orient

@@ -40,8 +40,9 @@
 #include <math.h>
 #include <pthread.h>
 
-#define NC 13          /* event classes (rule:kind)            */
-#define NS 17          /* move slots per site                   */
+#define NC 17          /* event classes (rule:kind): 13 of the reference's rules + 4 of MoveMonovacancy */
+#define NS 29          /* move slots per site: 17 + 12 MoveMonovacancy (direction, layer) */
+#define MM_SLOT0 17
 #define NONE 0xFF
 
 /* status codes: 0 pristine, 1/2 monovacancy layer, 3 divacancy, 4+3*orient+role trefoil member */
@@ -50,7 +51,11 @@ enum { PRISTINE = 0, DIVAC = 3, TREF = 4 };
 /* class ids */
 enum { C_CREATE_DIV = 0, C_FILL_DIV = 1, C_MOVE_DIV = 2 /*..5*/, C_CREATE_TREF = 6, C_DESTROY_TREF = 7,
        C_CMONO_FROM_DOUBLE = 8, C_CMONO_MAKE_EMPTY = 9, C_FMONO_MAKE_DOUBLE = 10, C_FMONO_FROM_EMPTY = 11,
-       C_FLIP = 12 };
+       C_FLIP = 12,
+       /* MoveMonovacancy: a stub in the reference (rules.py:295-296; kinds named in config/WSe2.yaml:8-13).
+        * Semantics stated in oracle/move_monovacancy.py and pinned by fixtures made from the reference engine
+        * running that rule class: kind = 2 * (source is a divacancy) + (target is not pristine). */
+       C_MOVE_MONO = 13 /* natural, 14 merge-divacancy, 15 split-divacancy, 16 swap-divacancy */ };
 
 /* Grid.neighbors_and_mutuals order (state.py:443-459): nbr, near, far */
 static const int NBR[6][2]  = {{-1, 1}, {0, -1}, {1, 0}, {0, 1}, {-1, 0}, {1, -1}};
@@ -65,13 +70,13 @@ static const int TMEM[2][3][2] = {{{0, 0}, {2, 0}, {0, 2}}, {{0, 0}, {2, 0}, {2,
 typedef struct {
     uint32_t site;        /* linear index a*d1+b of the move's anchor site        */
     uint8_t  cls;         /* class id 0..12 ; 0xFF = total weight zero (kmc.py:32) */
-    uint8_t  slot;        /* move slot 0..16                                       */
+    uint8_t  slot;        /* move slot 0..28                                       */
     uint16_t flags;       /* bit0: x landed exactly on a cumulative-weight boundary */
     double   total_rate;  /* math.fsum of the class weights (sim.py:138)           */
     double   total_naive; /* sequential prefix-sum total used for selection (kmc.py:41-42) */
     uint32_t counts[NC];  /* per-class move counts BEFORE the event               */
     uint32_t pad;
-} KmcoEvent;              /* 80 bytes */
+} KmcoEvent;              /* 96 bytes */
 
 typedef struct {
     int d0, d1, n;
@@ -132,6 +137,17 @@ static void eval_site(const uint8_t *s, int d0, int d1, int a, int b, uint8_t ou
             for (int r = 1; r < 3; r++)
                 ok &= s[at(d0, d1, a + TMEM[o][r][0], b + TMEM[o][r][1])] == DIVAC;
             if (ok) out[13 + o] = C_CREATE_TREF;
+        }
+    }
+    /* MoveMonovacancy (oracle/move_monovacancy.py): the vacancy in `layer` hops to neighbour k when the
+     * neighbour has a defined layer set without that layer; slot 17 + 2k + (layer - 1) */
+    if (st >= 1 && st <= 3) {
+        for (int k = 0; k < 6; k++) {
+            int dst = s[at(d0, d1, a + NBR[k][0], b + NBR[k][1])];
+            if (dst > 3) continue;                   /* trefoil member: no defined layer set */
+            for (int layer = 1; layer <= 2; layer++)
+                if ((st & layer) && !(dst & layer))
+                    out[MM_SLOT0 + 2 * k + (layer - 1)] = (uint8_t)(C_MOVE_MONO + 2 * (st == DIVAC) + (dst != 0));
         }
     }
     /* DestroyTrefoil: one move per existing trefoil (rules.py:189), anchored at its role-0 node */
@@ -277,6 +293,9 @@ static void refresh_after(KmcOracle *o, const int (*nodes)[2], int n_nodes)
         /* MoveDivacancy: all nodes within distance <= 1 (rules.py:115-117) */
         refresh_slots(o, a, b, 7, 13);
         for (int k = 0; k < 6; k++) refresh_slots(o, a + RING[k][0], b + RING[k][1], 7, 13);
+        /* MoveMonovacancy: likewise all nodes within distance <= 1 (move_monovacancy.py:moves_dependent_on) */
+        refresh_slots(o, a, b, MM_SLOT0, NS);
+        for (int k = 0; k < 6; k++) refresh_slots(o, a + RING[k][0], b + RING[k][1], MM_SLOT0, NS);
         /* Create/DestroyTrefoil: every triangle containing this node (rules.py:159-174,192-198):
          * anchors p, p-(2,0), p-(0,2) [Up] and p, p-(2,0), p-(2,-2) [Down] */
         refresh_slots(o, a, b, 13, 17);
@@ -292,7 +311,9 @@ static int perform_move(KmcOracle *o, int site, int slot, int nodes[3][2]);
 static int perform(KmcOracle *o, int site, int slot, int nodes[3][2])
 {
     int nn = perform_move(o, site, slot, nodes);
-    if (o->trc && !(slot >= 7 && slot <= 12))
+    int carried = nn < 0;
+    if (carried) nn = -nn;
+    if (o->trc && !(slot >= 7 && slot <= 12) && !carried)
         for (int i = 0; i < nn; i++) {
             int j = nodes[i][0] * o->d1 + nodes[i][1];
             if (o->status[j] == DIVAC) { o->trc[2 * j] = 0; o->trc[2 * j + 1] = 0; }
@@ -318,6 +339,21 @@ static int perform_move(KmcOracle *o, int site, int slot, int nodes[3][2])
         if (o->trc) {                                              /* the hop carries the tracer along */
             o->trc[2 * (na * d1 + nb)] = o->trc[2 * site] + NBR[k][0];
             o->trc[2 * (na * d1 + nb) + 1] = o->trc[2 * site + 1] + NBR[k][1];
+        }
+        return 2;
+    }
+    if (slot >= MM_SLOT0) {                                        /* MoveMonovacancy (move_monovacancy.py:perform) */
+        int k = (slot - MM_SLOT0) >> 1, layer = ((slot - MM_SLOT0) & 1) + 1;
+        int na = wrapi(a + NBR[k][0], d0), nb = wrapi(b + NBR[k][1], d1);
+        int was_div = s[site] == DIVAC;
+        s[site] &= (uint8_t)~layer; s[na * d1 + nb] |= (uint8_t)layer;
+        nodes[1][0] = na; nodes[1][1] = nb;
+        /* tracers: a divacancy that trades places with a monovacancy (swap) carries its displacement along;
+         * a merge starts a new tracer (handled by the caller: the target became a divacancy) */
+        if (o->trc && was_div && s[na * d1 + nb] == DIVAC) {
+            o->trc[2 * (na * d1 + nb)] = o->trc[2 * site] + NBR[k][0];
+            o->trc[2 * (na * d1 + nb) + 1] = o->trc[2 * site + 1] + NBR[k][1];
+            return -2;                                             /* 2 nodes, tracer already carried */
         }
         return 2;
     }

@@ -12,13 +12,13 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkmc_oracle.so")
-NC, NS, NONE = 13, 17, 0xFF
+NC, NS, NONE = 17, 29, 0xFF
 
 EVENT_DTYPE = np.dtype([
     ("site", "<u4"), ("cls", "u1"), ("slot", "u1"), ("flags", "<u2"),
     ("total_rate", "<f8"), ("total_naive", "<f8"), ("counts", "<u4", (NC,)), ("pad", "<u4"),
 ])
-assert EVENT_DTYPE.itemsize == 80
+assert EVENT_DTYPE.itemsize == 96
 
 
 def build(force=False):
@@ -82,7 +82,8 @@ def lib():
 
 
 def _rates(rates):
-    r = (C.c_double * NC)(*[float(x) for x in rates])
+    rates = [float(x) for x in rates]
+    r = (C.c_double * NC)(*(rates + [0.0] * (NC - len(rates))))      # 13-entry tables predate MoveMonovacancy
     return r
 
 

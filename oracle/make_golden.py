@@ -49,6 +49,21 @@ WSE2_RULES = {              # /root/reference/config/WSe2.yaml:2-24 minus the st
     "CreateTrefoil": {"barrier": 3.12293677},
     "DestroyTrefoil": {"barrier": 4.43051273},
 }
+# /root/reference/config/WSe2.yaml:2-24 with EVERY rule it names: MoveMonovacancy is a stub in the reference
+# (rules.py:295-296); oracle/move_monovacancy.py supplies it as a rule class of the reference's framework
+WSE2_FULL_RULES = {
+    "CreateMonovacancy": {"barrier": {"from-double": 6.72584072, "make-empty": 6.72584072}},
+    "FlipMonovacancy": {"barrier": 3.41217502},
+    "MoveMonovacancy": {"barrier": {"natural": 2.56175687, "merge-divacancy": 3.03662851,
+                                    "split-divacancy": 2.33673358, "swap-divacancy": 2.56175687}},
+    "MoveDivacancy": {"barrier": {"natural": 2.25, "missing-metal": 2.11199155,
+                                  "missing-comb": 2.52009312, "missing-both": 2.25}},
+    "CreateTrefoil": {"barrier": 3.12293677},
+    "DestroyTrefoil": {"barrier": 4.43051273},
+}
+# all nine rules live at comparable rates (17 classes)
+ALL_MM_RULES = dict(ALL_RULES, MoveMonovacancy={"rate": {"natural": 30.0, "merge-divacancy": 60.0,
+                                                         "split-divacancy": 20.0, "swap-divacancy": 40.0}})
 # equal weights on a pristine lattice: 10*N == 5*(2N) == 10*N -> exercises the stable tie-break
 TIE_RULES = {
     "CreateMonovacancy": {"rate": {"from-double": 5, "make-empty": 40}},
@@ -302,6 +317,25 @@ def boundary_tie_trajectory(name, dim, rules, status0, seed, nsteps, every=3):
     print("%-28s dim=%s steps=%d boundary ties=%d (%d bytes)" % (name, dim, nsteps, st.n_ties, os.path.getsize(path)))
 
 
+def move_monovacancy_fixtures():
+    """the reference engine running oracle/move_monovacancy.py's rule class."""
+    # config/WSe2.yaml as shipped, every rule: at 1500 K divacancies split and the monovacancies wander
+    trajectory("wse2_full_16x16", (16, 16), WSE2_FULL_RULES, exact_state((16, 16), 0.05, 0.05, 20261019),
+               seed=20261019, nsteps=3000, temperature=1500.0)
+    trajectory("wse2_full_64x64", (64, 64), WSE2_FULL_RULES, exact_state((64, 64), 0.05, 0.05, 20261019),
+               seed=20261019, nsteps=2000, temperature=1500.0)
+    # hot and dense: all four MoveMonovacancy kinds, all four MoveDivacancy kinds and trefoils are live
+    trajectory("wse2_full_hot_24x24", (24, 24), WSE2_FULL_RULES, exact_state((24, 24), 0.30, 0.10, 9),
+               seed=98, nsteps=3000, temperature=6000.0)
+    # all nine rules (17 classes) at comparable rates: pristine start, odd ragged dims, rows wider than 64
+    trajectory("allrules_mm_8x8", (8, 8), ALL_MM_RULES, np.zeros(64, np.uint8), seed=17, nsteps=3000)
+    trajectory("allrules_mm_5x7", (5, 7), ALL_MM_RULES, exact_state((5, 7), 0.2, 0.2, 6), seed=18, nsteps=2000)
+    trajectory("allrules_mm_64x64", (64, 64), ALL_MM_RULES, exact_state((64, 64), 0.05, 0.05, 1), seed=19,
+               nsteps=2000)
+    trajectory("allrules_mm_12x130", (12, 130), ALL_MM_RULES, exact_state((12, 130), 0.2, 0.1, 8), seed=20,
+               nsteps=2500, replica=1)
+
+
 def boundary_tie_fixtures():
     # equal class weights on a pristine start (two weights of 770 -> u1 = 0.5 is a boundary), then mixed
     boundary_tie_trajectory("boundary_ties_7x11", (7, 11), TIE_RULES, np.zeros(77, np.uint8), seed=31, nsteps=600)
@@ -314,7 +348,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1:                     # regenerate only the named groups, e.g. `make_golden.py boundary_ties`
         for g in sys.argv[1:]:
-            {"boundary_ties": boundary_tie_fixtures, "state_gen": state_gen_fixtures,
+            {"boundary_ties": boundary_tie_fixtures, "move_monovacancy": move_monovacancy_fixtures, "state_gen": state_gen_fixtures,
              "state_gen_philox": state_gen_philox_fixtures, "zobrist": zobrist_reference_fixture,
              "animate": animate_replay_fixture, "native_stats": native_statistics}[g]()
         return
@@ -347,6 +381,7 @@ def main():
     # 8. rows wider than 64 sites with a ragged last word (the wide bit-plane kernel's layout), trefoils live
     trajectory("allrules_12x130", (12, 130), ALL_RULES, exact_state((12, 130), 0.2, 0.1, 8), seed=13, nsteps=2500, replica=1)
     boundary_tie_fixtures()
+    move_monovacancy_fixtures()
     state_gen_fixtures()
     state_gen_philox_fixtures()
     zobrist_reference_fixture()

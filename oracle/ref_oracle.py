@@ -54,6 +54,10 @@ def _import_reference():
         assert os.path.abspath(mods["sim"].__file__).startswith(os.path.abspath(REFERENCE_ROOT))
         mods["_sys_modules"] = {k: v for k, v in sys.modules.items()
                                 if k == "demo1" or k.startswith("demo1.")}
+        # MoveMonovacancy is a stub in the reference (rules.py:295-296): our stated semantics, as a rule class of
+        # the reference's own framework, take its place on the module object (oracle/move_monovacancy.py)
+        import move_monovacancy
+        move_monovacancy.install(mods)
     finally:
         # leave the reference's modules reachable only through ``mods`` / ``ref_modules()``
         for k in [k for k in sys.modules if k == "demo1" or k.startswith("demo1.")]:

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_record_layouts_match_header():
     assert nat.EVENT_COMPACT.itemsize == 16
-    assert nat.EVENT_FULL.itemsize == 72
+    assert nat.EVENT_FULL.itemsize == 88
     assert nat.EVENT_FULL.fields["counts"][1] == 16
 
 
@@ -38,13 +38,13 @@ def test_no_device_is_a_loud_error():
         pytest.skip("a CUDA device is present")
     from demo1.engine import Engine
     with pytest.raises(RuntimeError, match="no CUDA device"):
-        Engine((8, 8), [1.0] * 13, [0])
+        Engine((8, 8), [1.0] * 17, [0])
 
 
 def test_bad_dimensions_are_rejected_before_touching_the_device():
     lib = nat.load()
     h = C.c_void_p()
-    rates = (C.c_double * 13)(*([1.0] * 13))
+    rates = (C.c_double * 17)(*([1.0] * 17))
     order = (C.c_int * 1)(0)
     for dim in [(4, 8), (8, 6), (2, 2)]:
         assert lib.kmc_create(C.byref(h), 0, dim[0], dim[1], 1, rates, order, 1) == nat.KMC_ERR_ARG

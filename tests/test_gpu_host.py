@@ -169,7 +169,7 @@ def test_cli_independent_replica_states_are_generated_on_the_device():
         params = yaml.safe_load(f)["state"]["random"]
     mode = params.pop("mode")
     frac = {k: (float(v[:-1]) / 100 if isinstance(v, str) else float(v)) for k, v in params.items()}
-    hist = np.zeros(13, dtype=np.int64)
+    hist = np.zeros(17, dtype=np.int64)
     for r in range(nrep):
         st0 = state_gen.generate((16, 16), mode, frac, 4, r)
         o = ko.Oracle((16, 16), wse2_rates(1500.0), WSE2_ORDER, st0)

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 
 from util_cases import (ko, philox, ALL_ORDER, TEST_RATES, WSE2_ORDER, wse2_rates, exact_state,
-                        evolved_state, iid_state)
+                        evolved_state, iid_state, MM_ORDER, MM_RATES, WSE2_FULL_ORDER, wse2_full_rates,
+                        reference_rules_only)
 from util_golden import load, trajectory_names, boundary_tie_names, enabled_classes
 from demo1 import _native as nat
 from demo1.engine import Engine
@@ -50,7 +51,7 @@ def test_golden_trajectory_philox(name):
     slots = eng.slots()[0]
     mask = np.isin(slots, en)
     assert (np.where(mask, slots, 0xFF) == g["slots1"]).all()
-    assert (eng.histogram() == np.bincount(g["events"]["cls"], minlength=13)).all()
+    assert (eng.histogram() == np.bincount(g["events"]["cls"], minlength=17)).all()
     assert eng.steps_done()[0] == m["nsteps"]
     assert eng.ties() == m["n_ties"]
     eng.close()
@@ -152,7 +153,7 @@ def test_replicas_match_oracle(dim, rates, order, nrep, nsteps):
         assert done == nsteps
         assert_events_equal(ev[r], want, "replica %d" % r)
         assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
-        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all() and (ev[r]["counts"][:, 13:] == 0).all()
         assert (ev[r]["flags"] == want["flags"]).all()
         assert (final[r] == o.status()).all()
         assert (hist[r] == o.hist()).all()
@@ -175,7 +176,7 @@ def test_both_replica_kernels_match_oracle(dim, variant):
         o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
         _, want = o.run_philox(seed, r, 0, nsteps)
         assert_events_equal(ev[r], want, "variant %d replica %d" % (variant, r))
-        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all() and (ev[r]["counts"][:, 13:] == 0).all()
         assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
         assert (final[r] == o.status()).all()
     eng.close()
@@ -195,7 +196,7 @@ def test_large_lattice_incremental_1024():
         o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
         _, want = o.run_philox(77, r, 0, nsteps)
         assert_events_equal(ev[r], want, "1024^2 replica %d" % r)
-        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all() and (ev[r]["counts"][:, 13:] == 0).all()
         assert (final[r] == o.status()).all()
     eng.close()
 
@@ -217,7 +218,7 @@ def test_wide_bitplane_kernel_matches_oracle(dim):
         o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0[r])
         _, want = o.run_philox(seed, r, 0, nsteps)
         assert_events_equal(ev[r], want, "wide replica %d" % r)
-        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all() and (ev[r]["counts"][:, 13:] == 0).all()
         assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
         assert (final[r] == o.status()).all()
     eng.close()
@@ -236,8 +237,8 @@ def test_wide_kernel_interleaves_with_the_byte_paths():
     _, want = o.run_philox(seed, 0, 0, 700)
     assert_events_equal(ev, want, "wide 1")
     eng.sweep()
-    assert (eng.counts()[0] == o.counts()).all()
-    assert (eng.slots()[0] == o.slots()).all()
+    assert (eng.counts()[0] == reference_rules_only(counts=o.counts())).all()
+    assert (eng.slots()[0] == reference_rules_only(o.slots())).all()
     # an explicit move: first CreateDivacancy-capable site
     site = int(np.flatnonzero(o.status() == 0)[0])
     o.perform_given(site, 0)
@@ -394,10 +395,28 @@ def test_sweep_matches_oracle(dim, variant):
     eng.sweep()
     slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
     for r in range(2):
+        ws, wc, wr = reference_rules_only(*ko.sweep(sts[r], dim))
+        assert (slots[r] == ws).all()
+        assert (counts[r] == wc).all()
+        assert (rows[r] == wr).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (7, 130), (128, 32), (300, 260), (37, 1024)])
+def test_sweep_with_move_monovacancy_matches_oracle(dim):
+    """All nine rules: 29 slot planes, 17 classes, per-row counts."""
+    sts = [evolved_state(dim, 3, rates=MM_RATES, order=MM_ORDER) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3),
+           iid_state(dim, 4, p=(0.6, 0.15, 0.15, 0.1))]
+    eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=2)
+    eng.upload_state(np.stack(sts))
+    eng.sweep()
+    slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
+    for r in range(2):
         ws, wc, wr = ko.sweep(sts[r], dim)
         assert (slots[r] == ws).all()
         assert (counts[r] == wc).all()
         assert (rows[r] == wr).all()
+        assert wc[13:].sum() > 0
     eng.close()
 
 
@@ -409,7 +428,7 @@ def test_sweep_full_size_4096():
     eng.upload_state(st)
     eng.sweep()
     eng.sweep()             # twice: the running-total / ticket state must return to zero between launches
-    ws, wc, wr = ko.sweep(st, dim)
+    ws, wc, wr = reference_rules_only(*ko.sweep(st, dim))
     assert (eng.counts()[0] == wc).all()
     assert (eng.row_counts()[0] == wr).all()
     slots = eng.slots()[0]
@@ -428,7 +447,7 @@ def test_no_incremental_path_matches_oracle(dim, nsteps):
         o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st0)
         _, want = o.run_philox(9, r, 0, nsteps)
         assert_events_equal(ev[r], want, "noinc replica %d" % r)
-        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all() and (ev[r]["counts"][:, 13:] == 0).all()
         assert (final[r] == o.status()).all()
     eng.close()
 
@@ -581,11 +600,11 @@ def test_class_frequencies_match_the_reference_with_its_own_rng():
     eng = Engine(m["dim"], z["rates"], m["class_order"], n_replicas=nrep)
     eng.upload_state(np.tile(z["status0"], (nrep, 1)))
     ev = eng.run(nsteps, 987654321, log_mode=nat.LOG_COMPACT, validate=True)
-    ours = np.zeros((nsteps, 13), dtype=np.int64)
+    ours = np.zeros((nsteps, 17), dtype=np.int64)
     for t in range(nsteps):
-        ours[t] = np.bincount(ev[:, t]["cls"], minlength=13)
+        ours[t] = np.bincount(ev[:, t]["cls"], minlength=17)
     for t in (0, 1, 5, 10, 20, 39):
-        stat, dof = chi2_two_sample(z["counts"][t], ours[t])
+        stat, dof = chi2_two_sample(z["counts"][t], ours[t][:13])
         assert chi2.sf(stat, dof) > 1e-4, (t, stat, dof)
     assert (eng.histogram() == ours.sum(axis=0)).all()
     eng.close()
@@ -869,3 +888,118 @@ def test_injected_draws_on_every_replica_kernel(variant, dim):
         assert_events_equal(ev[r], want, "variant %d replica %d" % (variant, r))
         assert (final[r] == o.status()).all()
     eng.close()
+
+
+# ---- MoveMonovacancy (a stub in the reference, semantics in DESIGN.md section 2) ------------------
+MM_FIXTURES = ["wse2_full_16x16", "wse2_full_64x64", "wse2_full_hot_24x24", "allrules_mm_8x8", "allrules_mm_5x7",
+               "allrules_mm_64x64", "allrules_mm_12x130"]
+
+
+@pytest.mark.parametrize("variant", [1, 3, "noinc", "draws"])
+@pytest.mark.parametrize("name", MM_FIXTURES)
+def test_move_monovacancy_fixtures_on_the_general_kernels(name, variant):
+    """Fixtures made by the REFERENCE engine running oracle/move_monovacancy.py's rule class (all of
+    config/WSe2.yaml's rules; all nine rules at comparable rates): byte-lattice kernel with the lattice in shared
+    memory (1) and in HBM (3), the no-incremental path, and the draw-injection seam."""
+    g = load(name)
+    m = g["meta"]
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.upload_state(g["status0"])
+    n = m["nsteps"] if variant != "noinc" else min(m["nsteps"], 400)
+    if variant == "noinc":
+        ev = eng.run_noinc(n, m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL)[0]
+    elif variant == "draws":
+        d = philox.draws(m["seed"], m["replica"], 0, n)
+        ev = np.concatenate([eng.step_draws(d[:n // 3], log_mode=nat.LOG_FULL, validate=True)[0],
+                             eng.step_draws(d[n // 3:], log_mode=nat.LOG_FULL, validate=True)[0]])
+    else:
+        eng.set_replica_kernel(variant)
+        ev = np.concatenate([eng.run(n // 2, m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL, validate=True)[0],
+                             eng.run(n - n // 2, m["seed"], replica0=m["replica"], log_mode=nat.LOG_FULL, validate=True)[0]])
+    assert_events_equal(ev, g["events"][:n], name)
+    got = fsum_totals(ev, g["rates"], m["class_order"])
+    assert (got.view(np.uint64) == g["events"]["total_rate"][:n].view(np.uint64)).all()
+    if n == m["nsteps"]:
+        assert (eng.download_state()[0] == g["status1"]).all()
+        eng.sweep()
+        en = enabled_classes(m)
+        assert (eng.counts()[0][en] == g["counts1"][en]).all()
+        slots = eng.slots()[0]
+        assert (np.where(np.isin(slots, en), slots, 0xFF) == g["slots1"]).all()
+    assert (ev["cls"] >= 13).sum() > 40
+    eng.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1, 3])
+@pytest.mark.parametrize("dim,rates,order", [((64, 64), MM_RATES, MM_ORDER), ((33, 47), MM_RATES, MM_ORDER),
+                                             ((5, 5), MM_RATES, MM_ORDER), ((7, 130), MM_RATES, MM_ORDER),
+                                             ((64, 64), wse2_full_rates(1500.0), WSE2_FULL_ORDER),
+                                             ((24, 40), wse2_full_rates(5000.0), WSE2_FULL_ORDER)])
+def test_move_monovacancy_replicas_match_oracle(dim, rates, order, variant):
+    """Several replicas, long runs, two launches, with the clock and the divacancy tracers on (a swap carries a
+    tracer along, a merge starts one, a split ends one), against the C oracle."""
+    nrep, nsteps, seed = 3, 6000, 515
+    st0 = np.stack([exact_state(dim, 0.12 + 0.03 * r, 0.10, 300 + r) for r in range(nrep)])
+    eng = Engine(dim, rates, order, n_replicas=nrep)
+    eng.set_replica_kernel(variant)
+    eng.enable_clock("stochastic")
+    eng.enable_tracers()
+    eng.upload_state(st0)
+    ev = np.concatenate([eng.run(2500, seed, replica0=4, log_mode=nat.LOG_FULL, validate=True),
+                         eng.run(nsteps - 2500, seed, replica0=4, log_mode=nat.LOG_FULL, validate=True)], axis=1)
+    final, hist, t = eng.download_state(), eng.histogram_per_replica(), eng.clock()
+    sq, cnt = eng.msd()
+    for r in range(nrep):
+        o = ko.Oracle(dim, rates, order, st0[r])
+        o.enable_tracers()
+        o.set_clock(2)
+        done, want = o.run_philox(seed, 4 + r, 0, nsteps)
+        assert done == nsteps
+        assert_events_equal(ev[r], want, "replica %d" % r)
+        assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (ev[r]["counts"] == want["counts"]).all()
+        assert (final[r] == o.status()).all()
+        assert (hist[r] == o.hist()).all()
+        assert t[r] == o.clock()
+        div = final[r] == 3
+        assert (eng.tracers(r)[div] == o.tracers()[div]).all()
+        assert (int(sq[r]), int(cnt[r])) == o.msd()
+    assert hist[:, 13:].sum() > 1000
+    eng.close()
+
+
+def test_bit_sliced_kernels_decline_move_monovacancy():
+    eng = Engine((64, 64), MM_RATES, MM_ORDER)
+    for variant in (2, 4):
+        eng.set_replica_kernel(variant)
+        with pytest.raises(RuntimeError, match="MoveMonovacancy is enabled"):
+            eng.run(10, 1)
+    eng.close()
+
+
+def test_move_monovacancy_incremental_equals_no_incremental_and_perform_given():
+    dim = (20, 36)
+    st0 = exact_state(dim, 0.15, 0.15, 8)
+    a = Engine(dim, MM_RATES, MM_ORDER)
+    b = Engine(dim, MM_RATES, MM_ORDER)
+    a.upload_state(st0)
+    b.upload_state(st0)
+    ea = a.run(300, 21, log_mode=nat.LOG_COMPACT, validate=True)[0]
+    eb = b.run_noinc(300, 21, log_mode=nat.LOG_COMPACT)[0]
+    assert (ea == eb).all()
+    assert (a.download_state() == b.download_state()).all()
+    # explicit moves: one of every MoveMonovacancy slot that exists on the lattice
+    o = ko.Oracle(dim, MM_RATES, MM_ORDER, a.download_state()[0])
+    done = set()
+    for site, slot in np.argwhere(o.slots() != 0xFF):
+        if slot < 17 or slot in done or o.slots()[site, slot] == 0xFF:
+            continue
+        done.add(slot)
+        assert o.perform_given(site, slot) == 0
+        a.perform_given(0, site, slot)
+        assert (a.download_state()[0] == o.status()).all()
+    assert len(done) == 12
+    with pytest.raises(RuntimeError, match="does not exist"):
+        a.perform_given(0, int(np.flatnonzero(o.status() == 0)[0]), 17)
+    a.close()
+    b.close()

@@ -74,7 +74,8 @@ def test_shipped_configs_load():
 
 
 def test_reference_style_configs_are_accepted():
-    # test-cfg.yaml style: stale 'Rule' prefixes; WSe2.yaml style: the stub rule is skipped
+    # test-cfg.yaml style: stale 'Rule' prefixes; WSe2.yaml style: MoveMonovacancy, which the
+    # reference only stubs (rules.py:295-296), is a real rule here and loads without a warning
     d = yaml.safe_load("""
 rules:
   RuleCreateDivacancy: {rate: 10}
@@ -84,9 +85,16 @@ rules:
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         cfg = config.from_dict(d)
-    assert [s.name for s in cfg["rule_specs"]] == ["CreateDivacancy", "FlipMonovacancy"]
-    assert any("stub" in str(x.message) for x in w)
+    assert [s.name for s in cfg["rule_specs"]] == ["CreateDivacancy", "MoveMonovacancy", "FlipMonovacancy"]
+    assert not w
     assert d == {}                      # consumed, as the reference does (quirk Q1)
+    from demo1.sim import class_table
+    _, rates, order = class_table(cfg["rule_specs"], 1500.0)
+    assert order == [0, 13, 14, 15, 16, 12] and len(rates) == 17 and rates[15] > rates[13] > rates[14] > 0
+    # a kind the rule does not have is still an error, a missing one too (reference sim.py:71-78)
+    bad = yaml.safe_load("rules: {MoveMonovacancy: {rate: {natural: 1, merge-divacancy: 1, split-divacancy: 1}}}")
+    with pytest.raises((RuntimeError, TypeError)):
+        class_table(config.from_dict(bad)["rule_specs"], None)
 
 
 @pytest.mark.parametrize("text,msg", [
@@ -239,12 +247,13 @@ def test_bulk_json_writer_is_character_identical_to_the_per_event_path():
     from demo1.state import State
     sim = KmcSim.__new__(KmcSim)                       # no device: only the formatting state
     sim.state = State((7, 9))
-    sim._rates13 = [10, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 1e-23, 300.5, 100.0, 0.1, 55]
-    sim._order = [8, 9, 10, 11, 0, 1, 2, 3, 4, 5, 6, 7, 12]
+    sim._rates13 = [10, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 1e-23, 300.5, 100.0, 0.1, 55, 30.0, 60, 2e-7, 40.5]
+    sim._order = [8, 9, 10, 11, 0, 1, 13, 14, 15, 16, 2, 3, 4, 5, 6, 7, 12]
     sim._zobrist = None
     slot_class = {0: [0], 1: [1], 2: [8, 9], 3: [8, 9], 4: [10, 11], 5: [10, 11], 6: [12]}
     slot_class.update({s: [2, 3, 4, 5] for s in range(7, 13)})
     slot_class.update({13: [6], 14: [6], 15: [7], 16: [7]})
+    slot_class.update({s: [13, 14, 15, 16] for s in range(17, 29)})       # MoveMonovacancy (direction, layer)
     rng = np.random.default_rng(5)
     recs = []
     for slot, classes in slot_class.items():
@@ -252,7 +261,7 @@ def test_bulk_json_writer_is_character_identical_to_the_per_event_path():
             for site in (0, 8, 9 * 6, 62, int(rng.integers(0, 63))):
                 r = np.zeros((), dtype=nat.EVENT_FULL)
                 r["site"], r["cls"], r["slot"] = site, cls, slot
-                r["counts"] = rng.integers(0, 2 ** 20, 13)
+                r["counts"] = rng.integers(0, 2 ** 20, 17)
                 recs.append(r)
     recs = np.array(recs, dtype=nat.EVENT_FULL)
     fast = sim.format_records_json(recs)

@@ -16,6 +16,7 @@ def lib():
     L.kmc_hostcheck_sweep_words16.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.kmc_hostcheck_sweep_nibbles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.kmc_hostcheck_eval_sites.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.kmc_hostcheck_eval_sites_mm.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.kmc_hostcheck_draw.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.POINTER(C.c_double),
                                      C.POINTER(C.c_double)]
     return L
@@ -32,9 +33,10 @@ def test_sweep_words_match_oracle(lib, dim, seed):
         counts = np.zeros(13, dtype=np.int64)
         assert lib.kmc_hostcheck_sweep_words(st.ctypes.data, dim[0], dim[1], slots.ctypes.data,
                                              counts.ctypes.data) == 0
+        # (these kernels enumerate the 13 classes / 17 slots of the reference's own rules)
         want_slots, want_counts, _ = ko.sweep(st, dim)
-        assert (slots.T == want_slots).all()
-        assert (counts == want_counts).all()
+        assert (slots.T == want_slots[:, :17]).all()
+        assert (counts == want_counts[:13]).all()
 
 
 @pytest.mark.parametrize("dim,seed", [((8, 16), 1), ((16, 16), 2), ((5, 32), 3), ((64, 64), 4), ((7, 48), 5),
@@ -46,9 +48,10 @@ def test_sweep_words16_match_oracle(lib, dim, seed, fn):
         slots = np.empty((17, n), dtype=np.uint8)
         counts = np.zeros(13, dtype=np.int64)
         assert getattr(lib, fn)(st.ctypes.data, dim[0], dim[1], slots.ctypes.data, counts.ctypes.data) == 0
+        # (these kernels enumerate the 13 classes / 17 slots of the reference's own rules)
         want_slots, want_counts, _ = ko.sweep(st, dim)
-        assert (slots.T == want_slots).all()
-        assert (counts == want_counts).all()
+        assert (slots.T == want_slots[:, :17]).all()
+        assert (counts == want_counts[:13]).all()
 
 
 @pytest.mark.parametrize("dim,seed", CASES + [((5, 5), 8), ((7, 9), 9), ((11, 5), 10)])
@@ -60,6 +63,11 @@ def test_eval_site_matches_oracle(lib, dim, seed):
         want_slots, _, _ = ko.sweep(st, dim)
         want = np.stack([(want_slots == c).sum(axis=1) for c in range(13)], axis=1)
         assert (out == want).all()
+        # the MoveMonovacancy-aware evaluator: all 17 classes
+        out17 = np.empty((n, 17), dtype=np.uint8)
+        lib.kmc_hostcheck_eval_sites_mm(st.ctypes.data, dim[0], dim[1], out17.ctypes.data)
+        want17 = np.stack([(want_slots == c).sum(axis=1) for c in range(17)], axis=1)
+        assert (out17 == want17).all()
 
 
 def test_device_draw_recipe_matches_oracle(lib):

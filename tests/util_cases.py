@@ -11,6 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import kmc_oracle as ko  # noqa: E402  (the checker)
 import philox  # noqa: E402
 
+# the 13 classes of the rules the reference implements itself (classes 13..16 = MoveMonovacancy, an extension)
 ALL_ORDER = list(range(13))
 TEST_RATES = [10.0, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 55.0]
 
@@ -43,9 +44,9 @@ def exact_state(dim, frac_div, frac_mono, seed):
     return st
 
 
-def evolved_state(dim, seed, nsteps=400, rates=None):
+def evolved_state(dim, seed, nsteps=400, rates=None, order=None):
     """A lattice with every status code present (trefoils included): run the oracle for a while."""
-    o = ko.Oracle(dim, rates or TEST_RATES, ALL_ORDER, exact_state(dim, 0.25, 0.15, seed))
+    o = ko.Oracle(dim, rates or TEST_RATES, order or ALL_ORDER, exact_state(dim, 0.25, 0.15, seed))
     o.run_philox(seed, 0, 0, nsteps, log=False)
     return o.status()
 
@@ -54,3 +55,36 @@ def iid_state(dim, seed, p=(0.90, 0.025, 0.025, 0.05)):
     """SURVEY section 8(d) config-4 recipe: iid status per site, no trefoils."""
     rng = np.random.Generator(np.random.Philox(seed))
     return rng.choice(np.arange(4, dtype=np.uint8), size=dim[0] * dim[1], p=p).astype(np.uint8)
+
+
+# all nine rules: the reference's eight + MoveMonovacancy (17 classes)
+MM_ORDER = list(range(17))
+MM_RATES = TEST_RATES + [30.0, 60.0, 20.0, 40.0]
+WSE2_FULL_BARRIERS = {**WSE2_BARRIERS, 13: 2.56175687, 14: 3.03662851, 15: 2.33673358, 16: 2.56175687}
+WSE2_FULL_ORDER = [8, 9, 12, 13, 14, 15, 16, 2, 3, 4, 5, 6, 7]      # config/WSe2.yaml rule order, every rule
+
+
+def wse2_full_rates(temperature):
+    r = [0.0] * 17
+    for c, e in WSE2_FULL_BARRIERS.items():
+        r[c] = math.exp(-e / (temperature * KB_EV))
+    return r
+
+
+def reference_rules_only(slots=None, counts=None, rows=None):
+    """The oracle always enumerates all nine rules; an engine without MoveMonovacancy rates reports only the
+    reference's own 13 classes / 17 slots.  Blank the rest of an oracle table before comparing."""
+    out = []
+    if slots is not None:
+        s2 = np.array(slots, copy=True)
+        s2[..., 17:] = 0xFF
+        out.append(s2)
+    if counts is not None:
+        c2 = np.array(counts, copy=True)
+        c2[..., 13:] = 0
+        out.append(c2)
+    if rows is not None:
+        r2 = np.array(rows, copy=True)
+        r2[..., 13:] = 0
+        out.append(r2)
+    return out[0] if len(out) == 1 else out

@@ -19,10 +19,21 @@ def boundary_tie_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "boundary_ties*.npz")))
 
 
+N_CLASSES, N_SLOTS = 17, 29
+
+
 def load(name):
+    """Fixtures made before MoveMonovacancy existed carry 13-class / 17-slot tables: pad them to the current
+    widths (absent classes have rate 0 / count 0, absent slots are empty)."""
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     d = {k: z[k] for k in z.files if k != "meta"}
     d["meta"] = json.loads(str(z["meta"]))
+    for k in ("rates", "counts0", "counts1"):
+        if k in d and d[k].shape[-1] < N_CLASSES:
+            d[k] = np.concatenate([d[k], np.zeros(N_CLASSES - d[k].shape[-1], dtype=d[k].dtype)])
+    if "slots1" in d and d["slots1"].shape[-1] < N_SLOTS:
+        pad = np.full((d["slots1"].shape[0], N_SLOTS - d["slots1"].shape[1]), 0xFF, dtype=np.uint8)
+        d["slots1"] = np.concatenate([d["slots1"], pad], axis=1)
     return d
 
 
