@@ -450,6 +450,28 @@ def main():
         other["64x64_x%d_mixed_rates" % R] = {"events_per_s": R * E / (msx * 1e-3), "replicas": R, "events_per_replica": E,
                                               "config": "kmc-dichalcogen_b200/config/mixed_rates.yaml (13 live classes)",
                                               "event_histogram": [int(x) for x in mxh]}
+        # the reference's config/WSe2.yaml with EVERY rule it names, i.e. MoveMonovacancy live (a stub in the
+        # reference; extension with stated semantics): 13 classes, ~90 % of the events are monovacancy hops.  The
+        # MoveMonovacancy-aware build of the half-warp kernel (8 row tables, class 16 on a disabled class's lane).
+        fw_bar = dict(WSE2_BARRIERS)
+        fw_bar.update({13: 2.56175687, 14: 3.03662851, 15: 2.33673358, 16: 2.56175687})
+        import math as _m
+        fw_rates = [(_m.exp(-fw_bar[c] / (TEMPERATURE * KB_EV)) if c in fw_bar else 0.0) for c in range(17)]
+        fw_order = [8, 9, 12, 13, 14, 15, 16, 2, 3, 4, 5, 6, 7]
+        fw = Engine(DIM, fw_rates, fw_order, n_replicas=R, device=local)
+        fw.upload_state(synthetic_lattices(R, 0))
+        fw.run(1000, SEED)
+        fw.sync()
+        fw.timer_start()
+        fw.run(E, SEED)
+        msf = fw.timer_stop()
+        fw.check_status()
+        fwh = fw.histogram()
+        fw.close()
+        other["64x64_x%d_wse2_full_with_move_monovacancy" % R] = {
+            "events_per_s": R * E / (msf * 1e-3), "replicas": R, "events_per_replica": E,
+            "config": "kmc-dichalcogen_b200/config/wse2_full.yaml (= reference config/WSe2.yaml, all rules)",
+            "kernel": "kmc_replica_hw_kernel<64,64,PLAIN,MM>", "event_histogram": [int(x) for x in fwh]}
         # the same trajectory through the reference-facing API with the reference's JSON event log produced for
         # every event (KmcSim.iter_json_lines: kernel launches of 4096 events + host formatting), wall clock
         from demo1.sim import KmcSim, RuleSpec

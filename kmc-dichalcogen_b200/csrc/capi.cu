@@ -529,8 +529,18 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // (two replicas per warp pay off once one replica per warp would already fill the GPU; small batches and
     // single trajectories are latency-bound and run faster with a full warp each)
     // MoveMonovacancy live: only the byte-lattice kernel maintains its four classes (variants 1 and 3)
-    if (h->mm && (h->variant == 2 || h->variant == 4 || h->variant == 5))
-        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: only replica kernels 0 (auto), 1 and 3 (byte lattice) apply");
+    // MoveMonovacancy live: the byte-lattice kernel (variants 1 and 3) maintains its four classes for any rule set and
+    // shape; the half-warp kernel (variant 4) does when rows have <= 64 sites and one of the own-status classes is
+    // disabled (17 classes, 16 lanes: class 16 takes that class's lane)
+    int lane16 = -1;
+    if (h->mm) {
+        const int cand[8] = {0, 1, 7, 8, 9, 10, 11, 12};
+        for (int i = 0; i < 8 && lane16 < 0; i++) if (h->order_pos[cand[i]] < 0) lane16 = cand[i];
+    }
+    const bool hw_mm_ok = h->mm && lane16 >= 0 && h->d1 <= 64 && 2 * replica_hw_bytes(h->d0, true) <= (size_t)h->max_smem_optin;
+    if (h->mm && (h->variant == 2 || h->variant == 5 || (h->variant == 4 && !hw_mm_ok)))
+        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: replica kernels 0 (auto), 1, 3 (byte lattice) and -- for rows of "
+                                 "<= 64 sites with at least one own-status class disabled -- 4 (half-warp) apply");
     const bool wide_ok = !h->mm && h->d1 > 64 && h->d1 <= 2048 &&
                          wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
     if (h->variant == 5 && !wide_ok)
@@ -585,7 +595,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.validate = validate;
         p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
-        p.hier = nullptr; p.hier_valid = 0;
+        p.hier = nullptr; p.hier_valid = 0; p.lane16 = -1;
         q.planes = h->d_planes; q.hier = h->d_whier; q.Wa = Wa; q.d0p = d0p;
         CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
@@ -609,12 +619,13 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     { int rc = ensure_bytes(h); if (rc) return rc; }
     long long hw_min = 4096;
     if (const char *e = getenv("KMC_HW_MIN_REPLICAS")) hw_min = atoll(e);              // tuning knob
-    const bool halfwarp = h->variant == 4 || (!h->mm && h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
-                                              2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
+    const bool halfwarp = h->variant == 4 || (h->variant == 0 && hw_mm_ok) ||
+                          (!h->mm && h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
+                           2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
         if (h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernels need dim1 <= 64");
         if (nsteps > (1ll << 30)) return fail(KMC_ERR_ARG, "at most 2^30 events per launch of the half-warp kernel: split the run");
-        const size_t hbytes = replica_hw_bytes(h->d0);
+        const size_t hbytes = replica_hw_bytes(h->d0, h->mm);
         if (2 * hbytes > (size_t)h->max_smem_optin) return fail(KMC_ERR_ARG, "lattice too large for the half-warp kernel");
         // replicas (half-warps) per block: a multiple of 8 (4 warps, one per scheduler), at most 56 (28 warps of
         // 72 registers fill an SM); small batches get smaller blocks so that every SM has one
@@ -641,10 +652,21 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.validate = validate;
         p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
-        p.hier = nullptr; p.hier_valid = 0;
+        p.hier = nullptr; p.hier_valid = 0; p.lane16 = lane16;
         const unsigned blocks = (unsigned)((h->R + hpb - 1) / hpb);
         const bool plain = log_mode == KMC_LOG_NONE && !d_draws && !p.clock && !p.tracer;
-        if (h->d0 == 64 && h->d1 == 64 && plain) {
+        if (h->mm) {
+            if (h->d0 == 64 && h->d1 == 64 && plain) {
+                CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kmc_replica_hw_kernel<64, 64, true, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
+            } else if (h->d0 == 64 && h->d1 == 64) {
+                CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kmc_replica_hw_kernel<64, 64, false, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
+            } else {
+                CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<0, 0, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kmc_replica_hw_kernel<0, 0, false, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
+            }
+        } else if (h->d0 == 64 && h->d1 == 64 && plain) {
             CU(cudaFuncSetAttribute(kmc_replica_hw_kernel<64, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kmc_replica_hw_kernel<64, 64, true><<<blocks, hpb * 16, smem, h->stream>>>(p);
         } else if (h->d0 == 64 && h->d1 == 64) {
@@ -696,7 +718,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     p.validate = validate;
     p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
-    p.hier = nullptr; p.hier_valid = 0;
+    p.hier = nullptr; p.hier_valid = 0; p.lane16 = -1;
     if (global_state) {
         if (!h->d_hier) CU(cudaMalloc(&h->d_hier, (size_t)h->R * h->d0 * (h->mm ? 9 : 7) * sizeof(uint32_t)));
         p.hier = h->d_hier; p.hier_valid = h->hier_valid ? 1 : 0;

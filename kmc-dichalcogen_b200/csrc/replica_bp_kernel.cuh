@@ -176,6 +176,11 @@ constexpr MoveEntry make_move_entry(int slot) {
     else if (slot <= 12) {                                          // MoveDivacancy: target = nbr_k
         constexpr int NA[6] = {-1, 0, 1, 0, -1, 1}, NB[6] = {1, -1, 0, 1, 0, -1};
         da1 = NA[slot - 7]; db1 = NB[slot - 7]; na = 2; n1 = 3; o1 = 0;
+    } else if (slot >= MM_SLOT0) {                                  // MoveMonovacancy (direction k, layer L)
+        constexpr int NA[6] = {-1, 0, 1, 0, -1, 1}, NB[6] = {1, -1, 0, 1, 0, -1};
+        const int k = (slot - MM_SLOT0) >> 1, layer = ((slot - MM_SLOT0) & 1) + 1;
+        da1 = NA[k]; db1 = NB[k]; na = 2; andm = 0xF & ~(uint32_t)layer;   // source: s & ~L
+        n1 = 0; o1 = 0;                                             // target: old | L, filled in from the kind
     } else {
         const int o = (slot - 13) & 1;
         const bool create = slot < 15;
@@ -190,11 +195,13 @@ constexpr MoveEntry make_move_entry(int slot) {
            (n1 << 16) | (n2 << 20) | (o1 << 24) | (o2 << 28);
     return e;
 }
-__constant__ MoveEntry MOVE_TABLE[NS] = {
+__constant__ MoveEntry MOVE_TABLE[NSA] = {
     make_move_entry(0), make_move_entry(1), make_move_entry(2), make_move_entry(3), make_move_entry(4),
     make_move_entry(5), make_move_entry(6), make_move_entry(7), make_move_entry(8), make_move_entry(9),
     make_move_entry(10), make_move_entry(11), make_move_entry(12), make_move_entry(13), make_move_entry(14),
-    make_move_entry(15), make_move_entry(16)};
+    make_move_entry(15), make_move_entry(16), make_move_entry(17), make_move_entry(18), make_move_entry(19),
+    make_move_entry(20), make_move_entry(21), make_move_entry(22), make_move_entry(23), make_move_entry(24),
+    make_move_entry(25), make_move_entry(26), make_move_entry(27), make_move_entry(28)};
 
 // position of the (n)-th set bit (0-based) of a small mask; n is warp-uniform and tiny
 __device__ __forceinline__ int nth_bit_small(uint32_t m, uint32_t n) {

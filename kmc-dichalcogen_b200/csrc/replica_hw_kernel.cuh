@@ -28,12 +28,22 @@ enum { HW_PLANES = N_TYPES };      // plane index == plane type: T_Z, T_D, T_M1,
 
 // Row counts are kept only for the five neighbourhood classes (MoveDivacancy x 4, CreateTrefoil); the row
 // counts of the eight own-status classes are popcounts of the planes (derived when such a class is chosen).
-enum { HW_RC = 5 };
-__host__ __device__ inline size_t replica_hw_bytes(int d0) {      // per replica
+// With MoveMonovacancy (MM build) three more tables follow: natural (5), merge-divacancy (6), swap-divacancy (7);
+// split-divacancy needs none: a divacancy with a pristine neighbour in direction k offers that hop in both layers,
+// so its row count is twice the sum of the row's four MoveDivacancy counts.
+enum { HW_RC = 5, HW_RC_MM = 8 };
+__host__ __device__ inline size_t replica_hw_bytes(int d0, bool mm = false) {      // per replica
     const size_t d0p = ((size_t)d0 + 3) & ~(size_t)3;
     const size_t planes = (size_t)HW_PLANES * d0 * 8;
-    const size_t rc = (HW_RC * d0p * 2 + 15) & ~(size_t)15;
+    const size_t rc = ((mm ? HW_RC_MM : HW_RC) * d0p * 2 + 15) & ~(size_t)15;
     return planes + rc;
+}
+// row table of a class, or -1 when its row counts are derived (own-status classes: plane popcounts; split: see above)
+template <bool MM> __device__ __forceinline__ int hw_table_of(int c) {
+    if (c >= C_MOVE_DIV && c <= C_CREATE_TREF) return c - C_MOVE_DIV;
+    if (MM && (c == C_MOVE_MONO || c == C_MOVE_MONO + 1)) return c - 8;          // 13 -> 5, 14 -> 6
+    if (MM && c == C_MOVE_MONO + 3) return 7;
+    return -1;
 }
 // total number of moves of an own-status class over the lattice: sum over plane types of
 // g1(status of the type) * popcount (g1: 2 bits per status, see g1_const)
@@ -79,8 +89,32 @@ __device__ __forceinline__ void hw_trefoil_masks(const u64 *PL, int d0, int a, c
     up = both & rb.rotl(Da, rb.amount(2));
     dn = both & rb.rotl(Db, rb.amount(-2));
 }
+// MoveMonovacancy of row `a`, direction constants `c` (only the neighbour part is used): per-kind masks of the
+// sites whose vacancy can hop that way.  natural / merge are per layer (the layer-1 and layer-2 masks are
+// disjoint, so their union has the summed popcount); split is hw_dir_masks' `present`; swap as below.
 template <int TD0, int TD1>
-__device__ __forceinline__ void hw_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
+__device__ __forceinline__ void hw_mm_masks(const u64 *PL, int d0, int a, const HwDir &c, const RowBits<TD1> &rb,
+                                            u64 &nat1, u64 &nat2, u64 &mer1, u64 &mer2, u64 &swp1, u64 &swp2) {
+    const int an = wrapT<TD0>(a + c.da_n, d0);
+    const u64 zn = rot_site(PL[T_Z * d0 + an], c.db_n, c.sh_n, c.db_n > 0, rb);
+    const u64 m1n = rot_site(PL[T_M1 * d0 + an], c.db_n, c.sh_n, c.db_n > 0, rb);
+    const u64 m2n = rot_site(PL[T_M2 * d0 + an], c.db_n, c.sh_n, c.db_n > 0, rb);
+    const u64 m1 = PL[T_M1 * d0 + a], m2 = PL[T_M2 * d0 + a], dv = PL[T_D * d0 + a];
+    nat1 = m1 & zn; nat2 = m2 & zn;          // layer L vacancy -> pristine neighbour
+    mer1 = m1 & m2n; mer2 = m2 & m1n;        // -> neighbour holding the opposite-layer monovacancy
+    swp1 = dv & m2n; swp2 = dv & m1n;        // layer L of a divacancy -> opposite-layer monovacancy
+}
+// counts of (natural | merge << 16, swap) of one (row, direction)
+template <int TD0, int TD1>
+__device__ __forceinline__ void hw_mm_counts(const u64 *PL, int d0, int a, const HwDir &c, const RowBits<TD1> &rb,
+                                             uint32_t &nm, uint32_t &sw) {
+    u64 n1, n2, e1, e2, s1, s2;
+    hw_mm_masks<TD0>(PL, d0, a, c, rb, n1, n2, e1, e2, s1, s2);
+    nm = (uint32_t)__popcll(n1 | n2) | ((uint32_t)__popcll(e1 | e2) << 16);
+    sw = (uint32_t)__popcll(s1) + (uint32_t)__popcll(s2);
+}
+template <int TD0, int TD1, bool MM = false>
+__device__ __forceinline__ void hw_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NCA]) {
     const uint32_t pz = __popcll(PL[T_Z * d0 + a]), pd = __popcll(PL[T_D * d0 + a]);
     const uint32_t pm = __popcll(PL[T_M1 * d0 + a] | PL[T_M2 * d0 + a]);
     const uint32_t pa = __popcll(PL[T_A4 * d0 + a] | PL[T_A7 * d0 + a]);
@@ -98,6 +132,17 @@ __device__ __forceinline__ void hw_row_counts(const u64 *PL, int d0, int a, cons
     out[C_MOVE_DIV + 2] = k23 & 0xFFFF; out[C_MOVE_DIV + 3] = k23 >> 16;
     u64 up, dn; hw_trefoil_masks<TD0>(PL, d0, a, rb, up, dn);
     out[C_CREATE_TREF] = __popcll(up) + __popcll(dn);
+    if (MM) {
+        uint32_t nm = 0, sw = 0;
+        for (int k = 0; k < 6; k++) {
+            const HwDir c = hw_dir_const(k);
+            uint32_t a_nm, a_sw; hw_mm_counts<TD0>(PL, d0, a, c, rb, a_nm, a_sw);
+            nm += a_nm; sw += a_sw;
+        }
+        out[C_MOVE_MONO] = nm & 0xFFFF; out[C_MOVE_MONO + 1] = nm >> 16;
+        out[C_MOVE_MONO + 2] = 2 * ((k01 & 0xFFFF) + (k01 >> 16) + (k23 & 0xFFFF) + (k23 >> 16));
+        out[C_MOVE_MONO + 3] = sw;
+    }
 }
 
 // Two execution modes of the same event code:
@@ -210,9 +255,13 @@ __device__ __forceinline__ int nth_set_bit_hw(u64 m, uint32_t idx, const Half &h
 constexpr int HW_MAX_THREADS = 896;
 // PLAIN = true: the statistics-only build (no event log, no injected draws, no clock) -- what a production
 // batch runs; the general build keeps every option.
-template <int TD0, int TD1, bool PLAIN = false>
+// MM = true: MoveMonovacancy's four classes are maintained as well.  Half-lanes 13, 14, 15 own classes 13, 14, 15; class
+// 16 (swap-divacancy) lives on half-lane p.lane16, the lane of a disabled own-status class (17 classes, 16 lanes: a
+// rule set with all 17 enabled runs on the byte-lattice kernel instead).
+template <int TD0, int TD1, bool PLAIN = false, bool MM = false>
 __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const ReplicaParams p)
 {
+    constexpr int NRC = MM ? HW_RC_MM : HW_RC;
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
     const int n = d0 * d1;
@@ -229,8 +278,8 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     const RowBits<TD1> rb(d1);
 
     extern __shared__ uint4 smem_raw[];
-    u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot_in_block * replica_hw_bytes(d0));
-    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + HW_PLANES * d0);      // [HW_RC][d0p]: classes 2..6
+    u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)slot_in_block * replica_hw_bytes(d0, MM));
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + HW_PLANES * d0);      // [NRC][d0p]: classes 2..6 (+ 13, 14, 16)
     const u64 *rc64 = reinterpret_cast<const u64 *>(rc16);
 
     // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
@@ -261,22 +310,34 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     __syncwarp(hw.mask);
     // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
     for (int a = hl; a < d0p; a += 16) {
-        uint32_t cnt[NC];
-        if (a < d0) hw_row_counts<TD0>(PL, d0, a, rb, cnt);
+        uint32_t cnt[NCA];
+        if (a < d0) hw_row_counts<TD0, TD1, MM>(PL, d0, a, rb, cnt);
 #pragma unroll
         for (int c = 0; c < HW_RC; c++) rc16[c * d0p + a] = a < d0 ? (uint16_t)cnt[C_MOVE_DIV + c] : (uint16_t)0;
+        if (MM) {
+            rc16[5 * d0p + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO] : (uint16_t)0;
+            rc16[6 * d0p + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO + 1] : (uint16_t)0;
+            rc16[7 * d0p + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO + 3] : (uint16_t)0;
+        }
     }
     __syncwarp(hw.mask);
 
-    // per-lane class state: half-lane c < 13 owns class c; 13..15 are permanent zero weights
-    const int myc = hl < NC ? hl : 0;
-    const double rate = (hl < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-    const int pos = (hl < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + hl;
-    const uint32_t my_g1 = (hl < NC && !(hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)) ? g1_const(hl) : 0u;
+    // per-lane class state: half-lane c < 13 owns class c; 13..15 are permanent zero weights -- or, in the MM build,
+    // own classes 13..15, with class 16 on half-lane p.lane16
+    const int lane16 = MM ? p.lane16 : -1;
+    const int nown = MM ? 16 : NC;
+    const int myc = (MM && hl == lane16) ? C_MOVE_MONO + 3 : (hl < nown ? hl : 0);      // the class this lane owns
+    const bool has_class = hl < nown;
+    const double rate = (has_class && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (has_class && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + hl;
+    const uint32_t my_g1 = (myc < NC && has_class && !(myc >= C_MOVE_DIV && myc <= C_CREATE_TREF)) ? g1_const(myc) : 0u;
+    const int my_tab = has_class ? hw_table_of<MM>(myc) : -1;
     int tot = 0;
-    if (hl >= C_MOVE_DIV && hl <= C_CREATE_TREF)
-        for (int a = 0; a < d0; a++) tot += rc16[(hl - C_MOVE_DIV) * d0p + a];
-    else if (my_g1) tot = hw_own_total(PL, d0, my_g1);
+    if (my_tab >= 0)
+        for (int a = 0; a < d0; a++) tot += rc16[my_tab * d0p + a];
+    else if (MM && myc == C_MOVE_MONO + 2) {
+        for (int a = 0; a < d0; a++) tot += 2 * (rc16[a] + rc16[d0p + a] + rc16[2 * d0p + a] + rc16[3 * d0p + a]);
+    } else if (my_g1) tot = hw_own_total(PL, d0, my_g1);
     uint32_t hist = 0, hops = 0, n_ties = 0;                 // per launch (a launch holds at most 2^30 events)
     PickState pstate = pick_state_init(hl);
     double *const clockp = PLAIN ? nullptr : p.clock;
@@ -287,6 +348,9 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     HwDir my_dir = hw_dir_const(my_k);
     asm volatile("" : "+r"(my_dir.da_n), "+r"(my_dir.db_n), "+r"(my_dir.sh_n), "+r"(my_dir.da_e), "+r"(my_dir.db_e),
                       "+r"(my_dir.sh_e), "+r"(my_dir.da_f), "+r"(my_dir.db_f), "+r"(my_dir.sh_f));
+    // MM site search: half-lane l < 12 holds slot 17 + l = (direction l >> 1, layer (l & 1) + 1)
+    HwDir mm_dir = hw_dir_const(hl < 12 ? hl >> 1 : 0);
+    if (MM) asm volatile("" : "+r"(mm_dir.da_n), "+r"(mm_dir.db_n), "+r"(mm_dir.sh_n));
     // this lane's mask of the sites below column 4*hl + 4 (for popcount-select)
     uint32_t my_low_lo = hl >= 7 ? 0xFFFFFFFFu : ((16u << (4 * hl)) - 1u);
     uint32_t my_low_hi = hl < 8 ? 0u : (hl == 15 ? 0xFFFFFFFFu : ((16u << (4 * (hl - 8))) - 1u));
@@ -317,10 +381,15 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
     if (p.validate) {
         bool bad = false;
         for (int a = hl; a < d0; a += 16) {
-            uint32_t cnt[NC];
-            hw_row_counts<TD0>(PL, d0, a, rb, cnt);
+            uint32_t cnt[NCA];
+            hw_row_counts<TD0, TD1, MM>(PL, d0, a, rb, cnt);
 #pragma unroll
             for (int c = 0; c < HW_RC; c++) bad |= (rc16[c * d0p + a] != (uint16_t)cnt[C_MOVE_DIV + c]);
+            if (MM) {
+                bad |= rc16[5 * d0p + a] != (uint16_t)cnt[C_MOVE_MONO];
+                bad |= rc16[6 * d0p + a] != (uint16_t)cnt[C_MOVE_MONO + 1];
+                bad |= rc16[7 * d0p + a] != (uint16_t)cnt[C_MOVE_MONO + 3];
+            }
             const u64 z = PL[T_Z * d0 + a], dv = PL[T_D * d0 + a];
             const u64 types[N_TYPES] = {z, dv, PL[T_M1 * d0 + a], PL[T_M2 * d0 + a], PL[T_A4 * d0 + a], PL[T_A7 * d0 + a]};
             u64 seen = 0, dup = 0;
@@ -328,9 +397,13 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
             for (int q = 0; q < N_TYPES; q++) { dup |= seen & types[q]; seen |= types[q]; }
             bad |= dup != 0;
         }
-        if (hl >= C_MOVE_DIV && hl <= C_CREATE_TREF) {
+        if (my_tab >= 0) {
             int fresh = 0;
-            for (int a = 0; a < d0; a++) fresh += rc16[(hl - C_MOVE_DIV) * d0p + a];
+            for (int a = 0; a < d0; a++) fresh += rc16[my_tab * d0p + a];
+            bad |= (fresh != tot);
+        } else if (MM && myc == C_MOVE_MONO + 2) {
+            int fresh = 0;
+            for (int a = 0; a < d0; a++) fresh += 2 * (rc16[a] + rc16[d0p + a] + rc16[2 * d0p + a] + rc16[3 * d0p + a]);
             bad |= (fresh != tot);
         } else if (my_g1) {
             bad |= (hw_own_total(PL, d0, my_g1) != tot);
@@ -369,7 +442,7 @@ __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const
             gst[a2 * d1 + wrap1(b - 2, d1)] = (uint8_t)(S_TREF + 5);
         }
     }
-    if (hl < NC) p.hist[(size_t)rep * NCA + hl] += hist;
+    if (has_class) p.hist[(size_t)rep * NCA + myc] += hist;
     if (hl < 6) p.hops[(size_t)rep * 6 + hl] += hops;
     if (hl == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

@@ -56,6 +56,9 @@ struct ReplicaParams {
     // optional divacancy tracers (extension): per site the unwrapped displacement
     // (int16 da | int16 db << 16, axial) of the divacancy sitting there since it appeared.  nullptr = off.
     uint32_t *tracer;                // [R][n]
+    // half-warp kernel with MoveMonovacancy (17 classes, 16 lanes): the half-lane that owns class 16 (swap-divacancy);
+    // it is the lane of a DISABLED own-status class (capi.cu picks it)
+    int lane16;
 };
 
 constexpr uint32_t FULL = 0xFFFFFFFFu;

@@ -30,7 +30,9 @@ def specs_from_meta(meta):
 
 
 @pytest.mark.parametrize("name,incremental", [("allrules_8x8", True), ("wse2_16x16", True),
-                                              ("ties_reordered_7x11", True), ("testcfg_5x7", False)])
+                                              ("ties_reordered_7x11", True), ("testcfg_5x7", False),
+                                              ("wse2_full_16x16", True), ("allrules_mm_8x8", True),
+                                              ("allrules_mm_5x7", False)])
 def test_kmcsim_log_matches_reference(name, incremental):
     g = load(name)
     m = g["meta"]
@@ -120,6 +122,38 @@ def test_cli_event_log_replays_to_the_final_lattice(tmp_path):
     assert (sim.current_state().status == st).all()
     assert {e["rule"] for e in doc["events"]} >= {"CreateTrefoil", "DestroyTrefoil", "MoveDivacancy"}
     sim.close()
+
+
+def test_cli_runs_the_full_wse2_rule_set_without_warnings(tmp_path):
+    """the reference's config/WSe2.yaml names MoveMonovacancy (a stub there, so the reference
+    cannot run its own file); here the full rule set runs with no skip warning, the log carries the rule's
+    payload {was, now, layer}, replays to the device's final lattice, and --validate-every holds."""
+    import subprocess
+    import sys
+    from demo1 import tables as T
+    cfg = os.path.join(PKG, "config", "wse2_full.yaml")
+    args = [cfg, "-T", "1500", "-d", "16,16", "-n", "1200", "--seed", "20261019", "--state-seed", "5",
+            "--embed-initial", "--validate-every", "300"]
+    env = dict(os.environ, PYTHONPATH=PKG)
+    proc = subprocess.run([sys.executable, "-m", "demo1"] + args, capture_output=True, text=True, env=env, cwd=ROOT,
+                          timeout=300)
+    assert proc.returncode == 0, proc.stderr
+    assert "stub" not in proc.stderr and "skipped" not in proc.stderr
+    doc = json.loads(proc.stdout)
+    assert len(doc["rates"]) == 13 and "MoveMonovacancy:split-divacancy" in doc["rates"]
+    mm = [e for e in doc["events"] if e["rule"] == "MoveMonovacancy"]
+    assert len(mm) > 600 and all(sorted(e["move"]) == ["layer", "now", "was"] for e in mm)
+    assert {e["kind"] for e in mm} >= {"natural", "split-divacancy"}
+    dim = tuple(doc["grid"]["dim"])
+    st = State.from_dict(doc["initial_state"]).status
+    for ev in doc["events"]:
+        T.replay_event(st, ev, dim)
+    # the same trajectory on the oracle
+    from util_cases import ko, WSE2_FULL_ORDER, wse2_full_rates
+    o = ko.Oracle(dim, wse2_full_rates(1500.0), WSE2_FULL_ORDER, State.from_dict(doc["initial_state"]).status)
+    _, want = o.run_philox(20261019, 0, 0, 1200)
+    assert (o.status() == st).all()
+    assert [e["total_rate"] for e in doc["events"]] == list(want["total_rate"])
 
 
 def test_perform_given_move_accepts_reference_keys():
