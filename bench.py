@@ -168,6 +168,43 @@ def cpu_port_events_per_sec(n_threads, target_seconds, rates, order):
     return done / dt, "%d replicas x %d events, %d threads, %.1f s" % (n_rep, n_ev, n_threads, dt), dt
 
 
+def python_reference_events_per_sec(n_procs, nsteps=6000):
+    """The ACTUAL Python reference (unmodified, staged under baseline/_ref/reference by __graft_entry__.build(); the
+    py3.12 compat shim oracle/ref_shim on PYTHONPATH), one process per core -- it has no threads -- on the headline
+    workload: config/WSe2.yaml with the stub MoveMonovacancy disabled by an overlay file, -T 1500, 64x64, 5 % + 5 %
+    seeded defects.  events/s = processes * nsteps / (wall(nsteps) - wall(1 step)): initialisation subtracted."""
+    import tempfile
+    ref = os.path.join(ROOT, "baseline", "_ref", "reference")
+    if not os.path.isdir(os.path.join(ref, "demo1")):
+        return None
+    tmp = tempfile.mkdtemp(prefix="kmc_ref_")
+    with open(os.path.join(tmp, "overlay.yaml"), "w") as f:
+        f.write("rules:\n  MoveMonovacancy: {enabled: false}\nstate:\n  random:\n    mode: exact\n"
+                "    divacancy: 5%\n    monovacancy: 5%\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "oracle", "ref_shim"), PYTHONDONTWRITEBYTECODE="1")
+
+    def wall(n):
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen([sys.executable, "-m", "demo1", "config/WSe2.yaml", os.path.join(tmp, "overlay.yaml"),
+                                   "-T", "1500", "-d", "64,64", "-n", str(n)], cwd=ref, env=env,
+                                  stdout=subprocess.DEVNULL, stderr=subprocess.PIPE) for _ in range(n_procs)]
+        errs = [p.communicate()[1] for p in procs]
+        if any(p.returncode != 0 for p in procs):
+            raise RuntimeError("reference run failed: %s" % errs[0][-500:].decode("utf-8", "replace"))
+        return time.perf_counter() - t0
+    try:
+        wall(1)                                   # warm the page cache / bytecode-less imports
+        t1 = min(wall(1), wall(1))
+        tn = wall(nsteps)
+    except (RuntimeError, OSError) as e:
+        return {"unavailable": str(e)[:300]}
+    v = n_procs * (nsteps - 1) / max(tn - t1, 1e-9)
+    return {"value": v, "unit": "events/s", "cores": n_procs, "kind": "reference",
+            "sample": "%d processes x %d events (python -m demo1 config/WSe2.yaml + overlay, -T 1500 -d 64,64), "
+                      "init subtracted; %.1f s" % (n_procs, nsteps, t1 + tn),
+            "events_per_s_per_core": v / n_procs}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path, as its C port (the Python
     reference cannot travel to the GPU box), on all host threads, same workload/metric/unit."""
@@ -540,11 +577,12 @@ def main():
         gen.close()
         other["device_state_generation_exact_64x64"] = {"ms": msg, "replicas": R, "lattices_per_s": R / (msg * 1e-3)}
 
-    cpu = None
+    cpu = cpu_py = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_threads = os.cpu_count() or 1
         v, sample, _ = cpu_port_events_per_sec(n_threads, 12.0, rates, order)
         cpu = {"value": v, "unit": "events/s", "cores": n_threads, "kind": "port", "sample": sample}
+        cpu_py = python_reference_events_per_sec(min(n_threads, 32))
 
     if rank == 0:
         sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
@@ -579,6 +617,9 @@ def main():
                                        recorded_replica_counters()),
                                "ncu": recorded_replica_counters()},
             "cpu_baseline": cpu,
+            # the unmodified Python reference itself on the same host cores (one process per core), so that the
+            # comparison does not hinge on how fast the C port of it is
+            "cpu_baseline_python": cpu_py,
             "other_configs": other,
             "event_histogram": [int(x) for x in hist],
         }

@@ -172,7 +172,9 @@ def run_batch(ofile, nsteps, dims, cfg, init_state, temperature, seed, replicas,
     d = eng.displacement()
     sq = parallel.reduce_histogram(np.array([int((d[:, 0] ** 2 + d[:, 0] * d[:, 1] + d[:, 1] ** 2).sum())],
                                             dtype=np.int64), device=dev)
-    time_sum = parallel.sum_over_ranks(float(eng.clock().sum()), device=dev)
+    # per-replica times gathered and summed exactly (fsum), so the result does not depend on the sharding
+    import math
+    time_sum = math.fsum(parallel.gather_float64(eng.clock(), device=dev).tolist())
     tsq, tcnt = eng.msd()
     tr = parallel.reduce_histogram(np.array([int(tsq.sum()), int(tcnt.sum())], dtype=np.int64), device=dev)
     eng.close()

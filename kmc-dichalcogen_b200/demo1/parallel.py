@@ -68,6 +68,32 @@ def reduce_histogram(hist, device=None):
     return t.cpu().numpy()
 
 
+def gather_float64(values, device=None):
+    """Concatenation, in rank order, of every rank's float64 vector (lengths may differ); numpy on every rank.
+    Used for statistics that must not depend on how the replicas were sharded: the caller reduces the gathered
+    per-replica values with an exactly rounded sum (math.fsum) instead of summing per-rank partial sums."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    v = np.ascontiguousarray(values, dtype=np.float64).ravel()
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return v
+    world = dist.get_world_size()
+    n = torch.tensor([v.size], dtype=torch.int64)
+    if device is not None:
+        n = n.to(device)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    sizes = [int(x.item()) for x in sizes]
+    buf = torch.zeros(max(sizes), dtype=torch.float64)
+    buf[:v.size] = torch.from_numpy(v)
+    if device is not None:
+        buf = buf.to(device)
+    parts = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    return np.concatenate([pt.cpu().numpy()[:k] for pt, k in zip(parts, sizes)])
+
+
 def sum_over_ranks(value, device=None):
     """Sum of a Python float over all ranks."""
     import torch

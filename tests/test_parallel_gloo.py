@@ -40,8 +40,11 @@ def _worker(rank, world_size, port, out_dir):
     total = parallel.reduce_histogram(hist)
     slowest = parallel.max_over_ranks(float(rank + 1))
     both = parallel.sum_over_ranks(0.5 + rank)
+    # uneven shards (4 + 3 replicas) gathered in rank order: what the batch CLI sums exactly with fsum
+    gathered = parallel.gather_float64(np.arange(lo, hi, dtype=np.float64) * 0.1)
     parallel.barrier()
-    np.savez(os.path.join(out_dir, "rank%d.npz" % r), hist=total, slowest=slowest, both=both, st=st, lo=lo, hi=hi)
+    np.savez(os.path.join(out_dir, "rank%d.npz" % r), hist=total, slowest=slowest, both=both, st=st, lo=lo, hi=hi,
+             gathered=gathered)
 
 
 def _free_port():
@@ -64,5 +67,6 @@ def test_two_ranks_reduce_to_the_single_process_result(tmp_path):
         assert (p["hist"] == single_hist).all()          # every rank holds the global histogram
         assert float(p["slowest"]) == 2.0                # max over ranks
         assert float(p["both"]) == 2.0                   # sum over ranks: 0.5 + 1.5
+        assert (p["gathered"] == np.arange(N_TOTAL, dtype=np.float64) * 0.1).all()
         assert (p["st"] == single_st[int(p["lo"]):int(p["hi"])]).all()   # results independent of sharding
     assert [int(p["lo"]) for p in parts] == [0, 4] and [int(p["hi"]) for p in parts] == [4, 7]
