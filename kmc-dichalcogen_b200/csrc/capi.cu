@@ -13,6 +13,7 @@
 #include "../../include/kmc_b200.h"
 #include "kmc_common.cuh"
 #include "noinc_kernel.cuh"
+#include "noinc_planes_kernel.cuh"
 #include "replica_kernel.cuh"
 #include "replica_bp_kernel.cuh"
 #include "replica_hw_kernel.cuh"
@@ -65,6 +66,8 @@ struct kmc_engine {
     // planes_valid they describe the current lattice; bytes_stale means d_status lags behind them.
     unsigned long long *d_planes = nullptr; uint16_t *d_whier = nullptr, *d_whier_chk = nullptr;
     bool planes_valid = false, bytes_stale = false;
+    bool whier_valid = false;                // d_whier matches the planes (the no-incremental plane path does not maintain it)
+    uint32_t *d_prowc = nullptr, *d_pblk = nullptr;   // no-incremental path on planes: class-major row counts, CTA sums
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
@@ -164,7 +167,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock); cudaFree(h->d_tracer);
-    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk);
+    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags); cudaFree(h->d_anyflag);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -562,20 +565,26 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         const int Wa = wide_anchor_words(h->d1), We = wide_row_words(h->d1), d0p = (h->d0 + 1) & ~1;
         const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * We;
         const size_t hier_elems = (size_t)h->R * NC * d0p;
-        if (!h->d_planes) {
-            CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
+        if (!h->d_planes) CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
+        if (!h->d_whier) {
             CU(cudaMalloc(&h->d_whier, hier_elems * sizeof(uint16_t)));
             // rows a >= d0 of the padded table are never written by the kernels but ARE compared by validate
             CU(cudaMemsetAsync(h->d_whier, 0, hier_elems * sizeof(uint16_t), h->stream));
         }
         if (!h->planes_valid) {
             int rc = ensure_bytes(h); if (rc) return rc;
-            const long long cells = (long long)h->R * h->d0 * We, rows = (long long)h->R * h->d0;
+            const long long cells = (long long)h->R * h->d0 * We;
             kmc_wide_pack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_status, h->d_planes, h->R, h->d0, h->d1);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            h->planes_valid = true; h->whier_valid = false;
+        }
+        if (!h->whier_valid) {
+            const long long rows = (long long)h->R * h->d0;
             kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p);
             CU(cudaGetLastError());
-            h->launches += 2;
-            h->planes_valid = true;
+            h->launches += 1;
+            h->whier_valid = true;
         }
         const size_t wbytes = wide_warp_bytes(h->d0);
         int wpb = h->warps_per_block > 0 ? h->warps_per_block : (h->R + 147) / 148;    // spread small batches over the SMs
@@ -871,6 +880,43 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
     p.any_flag = h->d_anyflag; p.draws = d_draws;
     p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
+    // Large lattices: the event runs on the bit-sliced lattice (noinc_planes_kernel.cuh) -- 64 sites per operation in
+    // the enumeration instead of 8.  (KMC_NOINC_PLANES=0/1 forces the choice.)
+    bool on_planes = !h->mm && h->n >= 65536 && wide_anchor_words(h->d1) <= 256;
+    if (const char *e = getenv("KMC_NOINC_PLANES")) on_planes = !h->mm && atoi(e) != 0 && wide_anchor_words(h->d1) <= 256;
+    if (on_planes) {
+        const int We = wide_row_words(h->d1);
+        const int chunks = planes_chunks(h->d1), rpb = 8 / chunks, nblk = (h->d0 + rpb - 1) / rpb;
+        if (!h->d_planes) CU(cudaMalloc(&h->d_planes, (size_t)h->R * N_TYPES * h->d0 * We * sizeof(unsigned long long)));
+        if (!h->d_prowc) {
+            CU(cudaMalloc(&h->d_prowc, (size_t)h->R * PRC_STRIDE * h->d0 * sizeof(uint32_t)));
+            CU(cudaMalloc(&h->d_pblk, (size_t)h->R * nblk * PRC_STRIDE * sizeof(uint32_t)));
+        }
+        if (!h->planes_valid) {
+            rc = ensure_bytes(h); if (rc) return rc;
+            const long long cells = (long long)h->R * h->d0 * We;
+            kmc_wide_pack_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, h->stream>>>(h->d_status, h->d_planes, h->R, h->d0, h->d1);
+            CU(cudaGetLastError());
+            h->launches += 1;
+            h->planes_valid = true;
+        }
+        NoincPlanesParams q;
+        q.base = p; q.planes = h->d_planes; q.rowc = h->d_prowc; q.blk = h->d_pblk; q.counts = h->d_counts;
+        q.nblk = nblk; q.rpb = rpb;
+        for (long long t = 0; t < nsteps; t++) {
+            // sim.py:114-115: initialize() -- a full re-enumeration -- before every event
+            kmc_planes_rowcount_kernel<<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
+                                                                                     h->R, h->d0, h->d1, chunks, nblk);
+            q.base.t = t;
+            kmc_noinc_planes_select_kernel<<<h->R, 256, 0, h->stream>>>(q);
+            CU(cudaGetLastError());
+            h->launches += 2;
+        }
+        h->swept = false; h->hier_valid = false; h->whier_valid = false;
+        h->bytes_stale = true;                     // the status bytes lag behind the planes until somebody asks for them
+        if (rs) CU(cudaMemcpyAsync(events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
+        return check_flags(h, false);
+    }
     // rows row-1 .. row+2 of the chosen row are staged in shared memory when they fit
     const size_t stage_bytes = 4 * (size_t)h->d1 <= (size_t)h->max_smem_optin - 4096 ? 4 * (size_t)h->d1 : 0;
     p.stage = stage_bytes ? 1 : 0;

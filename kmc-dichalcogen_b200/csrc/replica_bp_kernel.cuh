@@ -34,9 +34,16 @@ enum { T_Z = 0, T_D = 1, T_M1 = 2, T_M2 = 3, T_A4 = 4, T_A7 = 5, N_TYPES = 6 };
 enum { PL_Z = 0, PL_ZP = 1, PL_ZM = 2, PL_D = 3, PL_DP = 4, PL_DM = 5, PL_M1 = 6, PL_M2 = 7, PL_A4 = 8, PL_A7 = 9,
        N_PLANES = 10 };
 
+// plane stride in 64-bit words: rows of different planes at the same row index would otherwise share a bank
+// (a 64-row plane is 512 B), which makes the plane update (one lane per plane) and the direction masks
+// (different planes, neighbouring rows) serialise; KMC_BP_PAD extra words spread the planes over the banks
+#ifndef KMC_BP_PAD
+#define KMC_BP_PAD 3
+#endif
+#define BPS(d0) ((d0) + KMC_BP_PAD)
 __host__ __device__ inline size_t replica_bp_warp_bytes(int d0) {
     const size_t d0e = ((size_t)d0 + 1) & ~(size_t)1;
-    const size_t planes = (size_t)N_PLANES * d0 * 8;
+    const size_t planes = (size_t)N_PLANES * BPS(d0) * 8;
     const size_t rc = (NC * d0e * 2 + 15) & ~(size_t)15;
     return planes + rc;
 }
@@ -87,9 +94,9 @@ __device__ __forceinline__ DirConst dir_const(int k, int d0) {
     DirConst c;
     // column offset db -> plane: db = 0 -> base, +1 -> P (bit b = bit b+1), -1 -> M
     const int dbn = nib(NBR_DB, k), dbe = nib(NEAR_DB, k), dbf = nib(FAR_DB, k);
-    c.off_n = (PL_Z + (dbn > 0 ? 1 : dbn < 0 ? 2 : 0)) * d0;  c.da_n = nib(NBR_DA, k);
-    c.off_e = (PL_D + (dbe > 0 ? 1 : dbe < 0 ? 2 : 0)) * d0;  c.da_e = nib(NEAR_DA, k);
-    c.off_f = (PL_D + (dbf > 0 ? 1 : dbf < 0 ? 2 : 0)) * d0;  c.da_f = nib(FAR_DA, k);
+    c.off_n = (PL_Z + (dbn > 0 ? 1 : dbn < 0 ? 2 : 0)) * BPS(d0);  c.da_n = nib(NBR_DA, k);
+    c.off_e = (PL_D + (dbe > 0 ? 1 : dbe < 0 ? 2 : 0)) * BPS(d0);  c.da_e = nib(NEAR_DA, k);
+    c.off_f = (PL_D + (dbf > 0 ? 1 : dbf < 0 ? 2 : 0)) * BPS(d0);  c.da_f = nib(FAR_DA, k);
     return c;
 }
 
@@ -97,7 +104,7 @@ __device__ __forceinline__ DirConst dir_const(int k, int d0) {
 template <int TD0>
 __device__ __forceinline__ void dir_masks(const u64 *PL, int d0, int a, const DirConst &c,
                                           u64 &present, u64 &near, u64 &far) {
-    present = PL[PL_D * d0 + a] & PL[c.off_n + wrapT<TD0>(a + c.da_n, d0)];
+    present = PL[PL_D * BPS(d0) + a] & PL[c.off_n + wrapT<TD0>(a + c.da_n, d0)];
     near = PL[c.off_e + wrapT<TD0>(a + c.da_e, d0)];
     far = PL[c.off_f + wrapT<TD0>(a + c.da_f, d0)];
 }
@@ -115,8 +122,8 @@ __device__ __forceinline__ u64 kind_select(u64 present, u64 near, u64 far, int q
 // CreateTrefoil anchored in row `a`: Up / Down masks
 template <int TD0, int TD1>
 __device__ __forceinline__ void trefoil_masks(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, u64 &up, u64 &dn) {
-    const u64 Da = PL[PL_D * d0 + a];
-    const u64 Db = PL[PL_D * d0 + wrapT<TD0>(a + 2, d0)];
+    const u64 Da = PL[PL_D * BPS(d0) + a];
+    const u64 Db = PL[PL_D * BPS(d0) + wrapT<TD0>(a + 2, d0)];
     const u64 both = Da & Db;
     up = both & rb.rotl(Da, rb.amount(2));
     dn = both & rb.rotl(Db, rb.amount(-2));
@@ -125,9 +132,9 @@ __device__ __forceinline__ void trefoil_masks(const u64 *PL, int d0, int a, cons
 // all 13 class counts of row `a` (full enumeration of one row; used at launch start and by validate)
 template <int TD0, int TD1>
 __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
-    const uint32_t pz = __popcll(PL[PL_Z * d0 + a]), pd = __popcll(PL[PL_D * d0 + a]);
-    const uint32_t pm = __popcll(PL[PL_M1 * d0 + a] | PL[PL_M2 * d0 + a]);
-    const uint32_t pa = __popcll(PL[PL_A4 * d0 + a] | PL[PL_A7 * d0 + a]);
+    const uint32_t pz = __popcll(PL[PL_Z * BPS(d0) + a]), pd = __popcll(PL[PL_D * BPS(d0) + a]);
+    const uint32_t pm = __popcll(PL[PL_M1 * BPS(d0) + a] | PL[PL_M2 * BPS(d0) + a]);
+    const uint32_t pa = __popcll(PL[PL_A4 * BPS(d0) + a] | PL[PL_A7 * BPS(d0) + a]);
     out[C_CREATE_DIV] = pz; out[C_FILL_DIV] = pd; out[C_DESTROY_TREF] = pa;
     out[C_CMONO_FROM_DOUBLE] = 2 * pz; out[C_CMONO_MAKE_EMPTY] = pm; out[C_FMONO_MAKE_DOUBLE] = pm;
     out[C_FMONO_FROM_EMPTY] = 2 * pd; out[C_FLIP] = pm;
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
 
     extern __shared__ uint4 smem_raw[];
     u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_bp_warp_bytes(d0));
-    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + N_PLANES * d0);      // [NC][d0e]
+    uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + N_PLANES * BPS(d0));      // [NC][d0e]
     const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(rc16);
 
     // ---- load: status bytes -> bit planes (one row per lane at a time) --------------------------
@@ -251,12 +258,12 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
                 for (int q = 0; q < N_TYPES; q++) w[q] |= (u64)(pl == q) << b;
             }
         }
-        PL[PL_Z * d0 + a] = w[T_Z];   PL[PL_ZP * d0 + a] = rb.rotl(w[T_Z], rb.amount(1));
-        PL[PL_ZM * d0 + a] = rb.rotl(w[T_Z], rb.amount(-1));
-        PL[PL_D * d0 + a] = w[T_D];   PL[PL_DP * d0 + a] = rb.rotl(w[T_D], rb.amount(1));
-        PL[PL_DM * d0 + a] = rb.rotl(w[T_D], rb.amount(-1));
-        PL[PL_M1 * d0 + a] = w[T_M1]; PL[PL_M2 * d0 + a] = w[T_M2];
-        PL[PL_A4 * d0 + a] = w[T_A4]; PL[PL_A7 * d0 + a] = w[T_A7];
+        PL[PL_Z * BPS(d0) + a] = w[T_Z];   PL[PL_ZP * BPS(d0) + a] = rb.rotl(w[T_Z], rb.amount(1));
+        PL[PL_ZM * BPS(d0) + a] = rb.rotl(w[T_Z], rb.amount(-1));
+        PL[PL_D * BPS(d0) + a] = w[T_D];   PL[PL_DP * BPS(d0) + a] = rb.rotl(w[T_D], rb.amount(1));
+        PL[PL_DM * BPS(d0) + a] = rb.rotl(w[T_D], rb.amount(-1));
+        PL[PL_M1 * BPS(d0) + a] = w[T_M1]; PL[PL_M2 * BPS(d0) + a] = w[T_M2];
+        PL[PL_A4 * BPS(d0) + a] = w[T_A4]; PL[PL_A7 * BPS(d0) + a] = w[T_A7];
     }
     __syncwarp();
     // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
@@ -410,9 +417,9 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
                 case C_FMONO_FROM_EMPTY: pa = PL_D; pb = PL_D; break;
                 default: pa = PL_M1; break;
             }
-            u64 ma = PL[pa * d0 + row];
-            const u64 mb = pb >= 0 ? PL[pb * d0 + row] : 0ull;
-            if (csel == C_FLIP) ma |= PL[PL_M2 * d0 + row];
+            u64 ma = PL[pa * BPS(d0) + row];
+            const u64 mb = pb >= 0 ? PL[pb * BPS(d0) + row] : 0ull;
+            if (csel == C_FLIP) ma |= PL[PL_M2 * BPS(d0) + row];
             const uint32_t n1 = __popcll(ma);
             const bool second = r >= n1;
             const u64 m = second ? mb : ma;
@@ -425,7 +432,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
                 case C_DESTROY_TREF: s0 = second ? 7 : 4; break;
                 case C_CMONO_MAKE_EMPTY: s0 = second ? 1 : 2; break;
                 case C_FMONO_MAKE_DOUBLE: s0 = second ? 2 : 1; break;
-                default: s0 = ((PL[PL_M1 * d0 + row] >> col) & 1ull) ? 1 : 2; break;
+                default: s0 = ((PL[PL_M1 * BPS(d0) + row] >> col) & 1ull) ? 1 : 2; break;
             }
         }
         const int site = row * d1 + col;
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         // bit planes: lane q < 10 maintains plane q, as 32-bit halves (program order handles nodes
         // sharing a word): clear the site's bit, set it again if the new status belongs to this plane
         if (lane < N_PLANES) {
-            uint32_t *P32 = reinterpret_cast<uint32_t *>(PL + lane * d0);
+            uint32_t *P32 = reinterpret_cast<uint32_t *>(PL + lane * BPS(d0));
             {
                 const int c = wrapT<TD1>(col + my_cshift, d1);
                 uint32_t *wp = P32 + 2 * row + (c >> 5);
@@ -574,14 +581,14 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
 #pragma unroll
             for (int c = 0; c < NC; c++) bad |= (rc16[c * d0e + a] != (uint16_t)cnt[c]);
             // plane consistency: at most one type bit per site; rotated copies agree with their base
-            const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a];
-            const u64 types[N_TYPES] = {z, dv, PL[PL_M1 * d0 + a], PL[PL_M2 * d0 + a], PL[PL_A4 * d0 + a], PL[PL_A7 * d0 + a]};
+            const u64 z = PL[PL_Z * BPS(d0) + a], dv = PL[PL_D * BPS(d0) + a];
+            const u64 types[N_TYPES] = {z, dv, PL[PL_M1 * BPS(d0) + a], PL[PL_M2 * BPS(d0) + a], PL[PL_A4 * BPS(d0) + a], PL[PL_A7 * BPS(d0) + a]};
             u64 seen = 0, dup = 0;
 #pragma unroll
             for (int q = 0; q < N_TYPES; q++) { dup |= seen & types[q]; seen |= types[q]; }
             bad |= dup != 0;
-            bad |= PL[PL_ZP * d0 + a] != rb.rotl(z, rb.amount(1)) || PL[PL_ZM * d0 + a] != rb.rotl(z, rb.amount(-1));
-            bad |= PL[PL_DP * d0 + a] != rb.rotl(dv, rb.amount(1)) || PL[PL_DM * d0 + a] != rb.rotl(dv, rb.amount(-1));
+            bad |= PL[PL_ZP * BPS(d0) + a] != rb.rotl(z, rb.amount(1)) || PL[PL_ZM * BPS(d0) + a] != rb.rotl(z, rb.amount(-1));
+            bad |= PL[PL_DP * BPS(d0) + a] != rb.rotl(dv, rb.amount(1)) || PL[PL_DM * BPS(d0) + a] != rb.rotl(dv, rb.amount(-1));
         }
         if (lane < NC) {
             int fresh = 0;
@@ -593,8 +600,8 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     // bit planes -> status bytes.  Pass 1: every site from its own plane bit (non-anchor trefoil
     // members get a placeholder); pass 2: each anchor writes the codes of its two partners.
     for (int a = lane; a < d0; a += 32) {
-        const u64 z = PL[PL_Z * d0 + a], dv = PL[PL_D * d0 + a], m1 = PL[PL_M1 * d0 + a], m2 = PL[PL_M2 * d0 + a];
-        const u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        const u64 z = PL[PL_Z * BPS(d0) + a], dv = PL[PL_D * BPS(d0) + a], m1 = PL[PL_M1 * BPS(d0) + a], m2 = PL[PL_M2 * BPS(d0) + a];
+        const u64 a4 = PL[PL_A4 * BPS(d0) + a], a7 = PL[PL_A7 * BPS(d0) + a];
         auto code_at = [&](int b) -> uint32_t {
             return ((z >> b) & 1) ? 0u : ((dv >> b) & 1) ? 3u : ((m1 >> b) & 1) ? 1u : ((m2 >> b) & 1) ? 2u
                  : ((a4 >> b) & 1) ? 4u : ((a7 >> b) & 1) ? 7u : 5u;
@@ -611,7 +618,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     }
     __syncwarp();
     for (int a = lane; a < d0; a += 32) {
-        u64 a4 = PL[PL_A4 * d0 + a], a7 = PL[PL_A7 * d0 + a];
+        u64 a4 = PL[PL_A4 * BPS(d0) + a], a7 = PL[PL_A7 * BPS(d0) + a];
         const int a2 = wrap1(a + 2, d0);
         while (a4) {
             const int b = __ffsll((long long)a4) - 1; a4 &= a4 - 1;

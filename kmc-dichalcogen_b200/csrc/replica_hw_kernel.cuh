@@ -261,7 +261,6 @@ constexpr int HW_MAX_THREADS = 896;
 template <int TD0, int TD1, bool PLAIN = false, bool MM = false>
 __global__ void __launch_bounds__(HW_MAX_THREADS, 1) kmc_replica_hw_kernel(const ReplicaParams p)
 {
-    constexpr int NRC = MM ? HW_RC_MM : HW_RC;
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
     const int n = d0 * d1;

@@ -1045,3 +1045,82 @@ def test_move_monovacancy_incremental_equals_no_incremental_and_perform_given():
         a.perform_given(0, int(np.flatnonzero(o.status() == 0)[0]), 17)
     a.close()
     b.close()
+
+
+# ---- the no-incremental event on the bit-sliced lattice (noinc_planes_kernel.cuh) ---------------------------------
+@pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 120), ((7, 130), 150),
+                                        ((33, 2100), 60), ((5, 64), 100), ((130, 65), 100), ((512, 4096), 40)])
+def test_no_incremental_on_planes_matches_oracle(dim, nsteps, monkeypatch):
+    """Large lattices take the plane path by themselves (>= 65536 sites); KMC_NOINC_PLANES=1 forces it for the
+    small and ragged shapes too.  Trefoils present (evolved lattice), two replicas, two launches, hop counters,
+    stochastic clock and tracers on -- everything against the oracle; then the byte-lattice paths take over from
+    the planes (lazy unpack) and the two no-incremental paths agree with each other."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    big = dim[0] * dim[1] > 100000
+    st0 = iid_state(dim, 77, p=(0.80, 0.05, 0.05, 0.10)) if big else evolved_state(dim, 31, nsteps=300)
+    st1 = iid_state(dim, 78, p=(0.70, 0.05, 0.05, 0.20)) if big else exact_state(dim, 0.2, 0.1, 5)
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
+    eng.enable_clock("stochastic")
+    eng.enable_tracers()
+    eng.upload_state(np.stack([st0, st1]))
+    n1 = nsteps // 3
+    ev = np.concatenate([eng.run_noinc(n1, 9, replica0=3, log_mode=nat.LOG_FULL),
+                         eng.run_noinc(nsteps - n1, 9, replica0=3, log_mode=nat.LOG_FULL)], axis=1)
+    final, t, hops = eng.download_state(), eng.clock(), eng.hops()
+    sq, cnt = eng.msd()
+    for r, st in enumerate((st0, st1)):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st)
+        o.enable_tracers()
+        o.set_clock(2)
+        done, want = o.run_philox(9, 3 + r, 0, nsteps)
+        assert done == nsteps
+        assert_events_equal(ev[r], want, "planes noinc replica %d" % r)
+        assert (ev[r]["total_rate"].view(np.uint64) == want["total_naive"].view(np.uint64)).all()
+        assert (ev[r]["counts"][:, :13] == want["counts"][:, :13]).all()
+        assert (final[r] == o.status()).all()
+        assert t[r] == o.clock()
+        slots = want["slot"].astype(int)
+        assert (hops[r] == np.bincount(slots[(slots >= 7) & (slots < 13)] - 7, minlength=6)).all()
+        assert (int(sq[r]), int(cnt[r])) == o.msd()
+    # hand over to the incremental kernels and back
+    ev2 = eng.run(50, 9, replica0=3, log_mode=nat.LOG_COMPACT, validate=True)
+    monkeypatch.setenv("KMC_NOINC_PLANES", "0")
+    ev3 = eng.run_noinc(20, 9, replica0=3, log_mode=nat.LOG_COMPACT)
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    ev4 = eng.run_noinc(20, 9, replica0=3, log_mode=nat.LOG_COMPACT)
+    for r, st in enumerate((st0, st1)):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, st)
+        _, want = o.run_philox(9, 3 + r, 0, nsteps + 90)
+        assert_events_equal(np.concatenate([ev2[r], ev3[r], ev4[r]]), want[nsteps:], "hand-over %d" % r)
+        assert (eng.download_state()[r] == o.status()).all()
+    eng.close()
+
+
+@pytest.mark.parametrize("name", boundary_tie_names())
+def test_boundary_ties_on_the_plane_no_incremental_path(name, monkeypatch):
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    g = load(name)
+    m = g["meta"]
+    eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
+    eng.upload_state(g["status0"])
+    ev = eng.step_draws_noinc(g["draws"], log_mode=nat.LOG_FULL)[0]
+    assert_events_equal(ev, g["events"], name)
+    assert np.nonzero(ev["flags"] & 1)[0].tolist() == m["tie_steps"] and eng.ties() == m["n_ties"]
+    assert (eng.download_state()[0] == g["status1"]).all()
+    eng.close()
+
+
+def test_plane_no_incremental_path_stops_on_zero_rate(monkeypatch):
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    dim = (9, 70)
+    rates = [0.0] * 13
+    rates[1] = 5.0
+    a = np.zeros(630, np.uint8); a[[3, 417]] = 3
+    eng = Engine(dim, rates, [1])
+    eng.upload_state(a)
+    with pytest.raises(ValueError, match="total weight of zero"):
+        eng.run_noinc(6, 5, log_mode=nat.LOG_COMPACT)
+    ev = eng._last_events[0]
+    assert list(ev["cls"]) == [1, 1, 0xFF, 0xFF, 0xFF, 0xFF]
+    assert (eng.download_state() == 0).all() and eng.steps_done()[0] == 2
+    eng.close()
