@@ -18,6 +18,7 @@
 #include "replica_bp_kernel.cuh"
 #include "replica_hw_kernel.cuh"
 #include "replica_wide_kernel.cuh"
+#include "replica_wide2_kernel.cuh"
 #include "sweep_kernel.cuh"
 #include "stategen_kernel.cuh"
 #include "zobrist_kernel.cuh"
@@ -606,8 +607,20 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
         p.hier = nullptr; p.hier_valid = 0; p.lane16 = -1;
         q.planes = h->d_planes; q.hier = h->d_whier; q.Wa = Wa; q.d0p = d0p;
-        CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
+        // small batches (at most one replica per SM): a whole CTA per replica, warps
+        // split by role -- the latency build (replica_wide2_kernel.cuh); KMC_WIDE_CTA=0/1 forces the choice
+        int sms2 = 148;
+        cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, h->device);
+        bool cta_per_replica = h->R <= sms2 && h->warps_per_block == 0;       // (one CTA per SM; beyond that one warp per replica wins)
+        if (const char *e = getenv("KMC_WIDE_CTA")) cta_per_replica = atoi(e) != 0;
+        if (cta_per_replica && wide2_cta_bytes(h->d0) <= (size_t)h->max_smem_optin - 1024) {
+            const size_t smem2 = wide2_cta_bytes(h->d0);
+            CU(cudaFuncSetAttribute(kmc_replica_wide2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            kmc_replica_wide2_kernel<<<(unsigned)h->R, 256, smem2, h->stream>>>(q);
+        } else {
+            CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
+        }
         CU(cudaGetLastError());
         h->launches += 1;
         if (validate) {          // the incrementally maintained row table against a fresh one from the planes

@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
 {
     const NoincParams &p = q.base;
     __shared__ unsigned long long wsum[8];
-    __shared__ unsigned long long s_tot[16][17];
+    __shared__ uint32_t s_tot[8][PRC_STRIDE];               // per-warp class sums of the CTA records
+    __shared__ double s_u1, s_u2;
     __shared__ unsigned long long s_rank;
     __shared__ double s_total;
     __shared__ int s_csel, s_zero, s_tie, s_row, s_word, s_bit;
@@ -140,22 +141,36 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     const uint32_t *rowc = q.rowc + (size_t)rep * PRC_STRIDE * d0;
     const unsigned long long step = p.steps_done[rep];
 
-    // ---- class totals: sum of the CTA records (thread = class c x one of 16 strided parts) -------------------
-    {
-        const int c = tid & 15, part = tid >> 4;
-        unsigned long long s = 0;
-        for (int b = part; b < q.nblk; b += 16) s += blk[(size_t)b * PRC_STRIDE + c];
-        s_tot[c][part] = s;
+    // ---- class totals: every thread owns KB consecutive CTA records and keeps all 13 class sums of them in
+    // registers (one round of independent 16-byte loads); they serve the totals now and the row search below
+    constexpr int KB_MAX = 8;                               // nblk <= 2048 CTA records (d0 <= 16384 rows)
+    const int kb = (q.nblk + 255) / 256;
+    uint32_t mine_c[PRC_STRIDE];
+#pragma unroll
+    for (int c = 0; c < PRC_STRIDE; c++) mine_c[c] = 0;
+    for (int i = 0; i < kb; i++) {
+        const int b = tid * kb + i;
+        if (b < q.nblk) {
+            const uint4 *rec = reinterpret_cast<const uint4 *>(blk + (size_t)b * PRC_STRIDE);
+            const uint4 x0 = rec[0], x1 = rec[1], x2 = rec[2], x3 = rec[3];
+            mine_c[0] += x0.x; mine_c[1] += x0.y; mine_c[2] += x0.z; mine_c[3] += x0.w;
+            mine_c[4] += x1.x; mine_c[5] += x1.y; mine_c[6] += x1.z; mine_c[7] += x1.w;
+            mine_c[8] += x2.x; mine_c[9] += x2.y; mine_c[10] += x2.z; mine_c[11] += x2.w;
+            mine_c[12] += x3.x;
+        }
     }
-    if (tid < 6) s_slotcnt[tid] = 0;
-    __syncthreads();
-    if (tid < 32) {
-        long long tot = 0;
-        if (lane < NC) for (int i = 0; i < 16; i++) tot += (long long)s_tot[lane][i];
-        if (lane < NCA) q.counts[(size_t)rep * NCA + lane] = lane < NC ? (unsigned long long)tot : 0ull;
-        const int myc = lane < NC ? lane : 0;
-        const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-        const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    (void)KB_MAX;
+    {
+        uint32_t mysum = 0;                                 // lane c < 13 of each warp collects the warp's sum of class c
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const uint32_t sc = __reduce_add_sync(FULL, mine_c[c]);
+            if (lane == c) mysum = sc;
+        }
+        if (lane < PRC_STRIDE) s_tot[tid >> 5][lane] = lane < NC ? mysum : 0u;
+    }
+    // the draws do not depend on the lattice: warp 1 makes them while the sums settle
+    if (tid == 32) {
         double u1, u2;
         if (p.draws) {
             const double2 u = *reinterpret_cast<const double2 *>(p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)p.t) * 2);
@@ -163,6 +178,18 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
         } else {
             kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
         }
+        s_u1 = u1; s_u2 = u2;
+    }
+    if (tid < 6) s_slotcnt[tid] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        long long tot = 0;
+        if (lane < NC) for (int i = 0; i < 8; i++) tot += (long long)s_tot[i][lane];
+        if (lane < NCA) q.counts[(size_t)rep * NCA + lane] = lane < NC ? (unsigned long long)tot : 0ull;
+        const int myc = lane < NC ? lane : 0;
+        const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+        const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+        const double u1 = s_u1, u2 = s_u2;
         const double w = __dmul_rn((double)tot, rate);
         PickState pstate = pick_state_init_n<16>(lane);
         const ClassPick pick = pick_class<16>(w, pos, pstate, u1, lane);
@@ -197,26 +224,30 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
 
     // ---- row: CTA record, then the rows of that CTA --------------------------------------------------------
     {
-        const int kb = (q.nblk + 255) / 256;
         const int b0 = tid * kb, b1 = min(b0 + kb, q.nblk);
-        unsigned long long local = 0, total;
-        for (int b = b0; b < b1; b++) local += blk[(size_t)b * PRC_STRIDE + csel];
+        uint32_t mysel = mine_c[0];                        // this thread's records' sum of the chosen class (registers)
+#pragma unroll
+        for (int c = 1; c < NC; c++) mysel = csel == c ? mine_c[c] : mysel;
+        unsigned long long local = mysel, total;
         const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
         const unsigned long long rank = s_rank;
         if (rank >= excl && rank < excl + local) {
+            // the one thread that holds the rank: its <= kb records, then the <= 8 rows of the record
             unsigned long long r = rank - excl;
             int b = b0;
-            for (; b < b1; b++) {
+            for (; b < b1 - 1; b++) {
                 const unsigned long long v = blk[(size_t)b * PRC_STRIDE + csel];
                 if (r < v) break;
                 r -= v;
             }
-            int a = b * q.rpb;
-            for (int i = 0; i < q.rpb - 1; i++) {
-                const unsigned long long v = rowc[(size_t)csel * d0 + a];
-                if (r < v) break;
-                r -= v; a++;
-            }
+            const int a0 = b * q.rpb;
+            uint32_t rv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) rv[i] = (i < q.rpb && a0 + i < d0) ? rowc[(size_t)csel * d0 + a0 + i] : 0u;
+            int a = a0;
+#pragma unroll
+            for (int i = 0; i < 7; i++)
+                if (a == a0 + i && i < q.rpb - 1 && r >= rv[i]) { r -= rv[i]; a = a0 + i + 1; }
             s_row = a; s_rin = (uint32_t)r;
         }
     }

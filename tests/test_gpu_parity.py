@@ -201,9 +201,11 @@ def test_large_lattice_incremental_1024():
     eng.close()
 
 
+@pytest.mark.parametrize("cta", ["0", "1"])
 @pytest.mark.parametrize("dim", [(12, 128), (40, 192), (7, 320), (130, 128), (64, 2048), (5, 128), (1100, 128),
                                  (12, 130), (40, 200), (7, 70), (9, 65), (200, 200), (20, 2044), (5, 67), (33, 127)])
-def test_wide_bitplane_kernel_matches_oracle(dim):
+def test_wide_bitplane_kernel_matches_oracle(dim, cta, monkeypatch):
+    monkeypatch.setenv("KMC_WIDE_CTA", cta)        # 0: one warp per replica, 1: a CTA per replica (warps split by role)
     """Variant 5: bit planes of rows wider than one word kept in HBM, row table in shared memory."""
     nrep, nsteps, seed = 3, 5000, 4711
     st0 = np.stack([evolved_state(dim, 40 + r, nsteps=300) for r in range(nrep)])
@@ -224,7 +226,9 @@ def test_wide_bitplane_kernel_matches_oracle(dim):
     eng.close()
 
 
-def test_wide_kernel_interleaves_with_the_byte_paths():
+@pytest.mark.parametrize("cta", ["0", "1"])
+def test_wide_kernel_interleaves_with_the_byte_paths(cta, monkeypatch):
+    monkeypatch.setenv("KMC_WIDE_CTA", cta)
     """Planes are authoritative after a wide launch; every byte-side entry point must see the same lattice:
     wide run -> sweep -> perform_given -> byte-kernel run -> wide run -> injected draws."""
     dim, seed = (24, 128), 31
@@ -260,7 +264,9 @@ def test_wide_kernel_interleaves_with_the_byte_paths():
     eng.close()
 
 
-def test_wide_kernel_stops_on_zero_total_rate():
+@pytest.mark.parametrize("cta", ["0", "1"])
+def test_wide_kernel_stops_on_zero_total_rate(cta, monkeypatch):
+    monkeypatch.setenv("KMC_WIDE_CTA", cta)
     dim = (8, 128)
     rates = [0.0] * 13
     rates[1] = 5.0                                   # FillDivacancy only: runs out after the divacancies
