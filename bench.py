@@ -348,6 +348,11 @@ def main():
         # calls); `--e2e-in-flight 1` gives the strictly sequential figure.
         n_flight = max(1, min(2, args.e2e_in_flight))
         engines = [eng] + [Engine(DIM, rates, order, n_replicas=R, device=local) for _ in range(n_flight - 1)]
+        if n_flight == 2 and 1024 <= R < 4096:
+            # two handles in flight put 2 R replicas on the GPU at once: enough for the two-replicas-per-warp kernel,
+            # which one handle alone would not pick below 4096 replicas (measured at R = 2048: 1.58e9 vs 1.28e9 e2e)
+            for e in engines:
+                e.set_replica_kernel(4)
         hosts_in = [host] + [host.clone().pin_memory() for _ in range(n_flight - 1)]
         hosts_out = [host_out] + [torch.empty_like(host).pin_memory() for _ in range(n_flight - 1)]
         checks = [0] * n_flight
