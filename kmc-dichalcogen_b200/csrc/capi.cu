@@ -50,7 +50,9 @@ struct kmc_engine {
     uint8_t *d_status = nullptr;
     uint8_t *d_slots = nullptr;              // [R][17][n], allocated on first sweep
     uint8_t *d_slots_alt = nullptr; bool slots_double = false;   // measurement: alternate output buffers
-    uint32_t *d_rowcnt = nullptr;            // [R][d0][16]
+    uint32_t *d_rowcnt = nullptr;            // [R][d0][16] (general MoveMonovacancy sweep: [R][d0][32])
+    uint32_t *d_rowmm = nullptr;             // [R][d0][4] MoveMonovacancy row counts of the aligned two-kernel sweep
+    bool sweep_split = false;                // the last sweep left its row counts in d_rowcnt (stride 16) + d_rowmm
     unsigned long long *d_counts = nullptr;  // [R][13]
     unsigned long long *d_acc = nullptr;     // [R][16] running totals of the aligned sweep (zero between launches)
     unsigned int *d_ticket = nullptr;        // [R]
@@ -166,7 +168,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (!h) return KMC_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_counts);
+    cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_rowmm); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock); cudaFree(h->d_tracer);
     cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags); cudaFree(h->d_anyflag);
@@ -338,7 +340,14 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     const int rcs = h->mm ? RCG_STRIDE_MM : RCG_STRIDE, nsl = h->mm ? NSA : NS;
     if (!h->d_rowcnt) CU(cudaMalloc(&h->d_rowcnt, R * h->d0 * rcs * sizeof(uint32_t)));
     if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * nsl * h->n));
-    if (h->mm) {
+    // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas
+    const int cpr = h->d1 >> 4;
+    const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
+    // MoveMonovacancy live on an aligned shape (slot planes wanted): the 17-plane aligned kernel writes planes 0..16 of
+    // the 29-plane layout, its companion kmc_sweep_mm16_kernel planes 17..28 and the four MoveMonovacancy row counts
+    const bool mm_split = h->mm && aligned && with_slots;
+    h->sweep_split = mm_split;
+    if (h->mm && !mm_split) {
         // MoveMonovacancy live: the general enumeration kernel (all 9 rules, 29 slot planes, one thread per site)
         CU(cudaMemsetAsync(h->d_rowcnt, 0, R * h->d0 * rcs * sizeof(uint32_t), h->stream));
         SweepParams p;
@@ -358,9 +367,19 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * (h->mm ? NSA : NS) * h->n));
         std::swap(h->d_slots, h->d_slots_alt);
     }
-    // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas, one launch in total
-    const int cpr = h->d1 >> 4;
-    const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
+    if (mm_split) {
+        if (!h->d_rowmm) CU(cudaMalloc(&h->d_rowmm, R * h->d0 * 4 * sizeof(uint32_t)));
+        CU(cudaMemsetAsync(h->d_rowmm, 0, R * h->d0 * 4 * sizeof(uint32_t), h->stream));
+        SweepMMParams m;
+        m.d0 = h->d0; m.d1 = h->d1; m.n = h->n; m.n_replicas = h->R;
+        m.status = h->d_status; m.slots = h->d_slots; m.rowmm = h->d_rowmm;
+        const long long chunks = (long long)R * (h->n >> 4);
+        kmc_sweep_mm16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, h->stream>>>(m);
+        CU(cudaGetLastError());
+        kmc_reduce_rowmm_kernel<<<h->R, 256, 0, h->stream>>>(h->d_rowmm, h->d0, h->d_counts);
+        CU(cudaGetLastError());
+        h->launches += 2;
+    }
     if (aligned) {
         if (!h->d_acc) {
             CU(cudaMalloc(&h->d_acc, R * 16 * sizeof(unsigned long long)));
@@ -392,7 +411,7 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
             q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
             q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
             q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
-            q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc;
+            q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc; q.nplanes = nsl;
             if (with_slots) kmc_sweep_roll_kernel<true><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
             else kmc_sweep_roll_kernel<false><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
             CU(cudaGetLastError());
@@ -403,7 +422,7 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
         q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
         q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
-        q.ctas_per_replica = (h->n >> 4) / 256;
+        q.ctas_per_replica = (h->n >> 4) / 256; q.nplanes = nsl;
         const long long blocks = (long long)R * q.ctas_per_replica;
         if (h->sweep_variant == 2) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         else kmc_sweep16n_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
@@ -472,12 +491,15 @@ extern "C" int kmc_get_row_counts(kmc_engine *h, uint32_t *out)
     int rc = bind(h); if (rc) return rc;
     if (!out) return fail(KMC_ERR_ARG, "kmc_get_row_counts: null buffer");
     if (!h->swept) return fail(KMC_ERR_ARG, "kmc_get_row_counts: call kmc_sweep first");
-    const int rcs = h->mm ? RCG_STRIDE_MM : RCG_STRIDE, ncx = h->mm ? NCA : NC;
-    std::vector<uint32_t> tmp((size_t)h->R * h->d0 * rcs);
+    const bool split = h->sweep_split;
+    const int rcs = (h->mm && !split) ? RCG_STRIDE_MM : RCG_STRIDE, ncx = (h->mm && !split) ? NCA : NC;
+    std::vector<uint32_t> tmp((size_t)h->R * h->d0 * rcs), mmv(split ? (size_t)h->R * h->d0 * 4 : 0);
     CU(cudaMemcpyAsync(tmp.data(), h->d_rowcnt, tmp.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (split) CU(cudaMemcpyAsync(mmv.data(), h->d_rowmm, mmv.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < (size_t)h->R * h->d0; i++)
-        for (int c = 0; c < NCA; c++) out[i * NCA + c] = c < ncx ? tmp[i * rcs + c] : 0u;
+        for (int c = 0; c < NCA; c++)
+            out[i * NCA + c] = c < ncx ? tmp[i * rcs + c] : (split && c >= C_MOVE_MONO ? mmv[i * 4 + c - C_MOVE_MONO] : 0u);
     return KMC_OK;
 }
 

@@ -267,6 +267,7 @@ struct Sweep16Params {
     unsigned int *ticket;              // [R] CTAs finished, zero between launches
     unsigned long long *counts;        // [R][13] class totals (output)
     int ctas_per_replica;
+    int nplanes;                       // planes per replica in `slots`: 17, or 29 when the MoveMonovacancy planes follow
 };
 
 #ifdef __CUDACC__
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
         k.q[3] = zd_flags(q4.z).div; k.q[4] = zd_flags(q4.w).div;
     }
     ByteAcc acc = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + cl : nullptr;
     {
         uint32_t o0[9], o1[9], o2[9], o3[9];
         own_planes(k, 0, o0, acc); own_planes(k, 1, o1, acc); own_planes(k, 2, o2, acc); own_planes(k, 3, o3, acc);
@@ -688,7 +689,7 @@ __global__ void __launch_bounds__(256, KMC_SWEEP_OCC) kmc_sweep16n_kernel(const 
         k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
         k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
     }
-    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + cl : nullptr;
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + cl : nullptr;
     uint32_t pk[7];
     sweep_chunk_n(k, O, (size_t)cpl, pk);
     row_counts_epilogue(p, rows_sm, pk, tid, lane, cpr, rows_in_cta, row_local, rep, a);
@@ -728,6 +729,7 @@ struct SweepRollParams {
     unsigned int *ticket;
     unsigned long long *counts;
     int rows_per_cta, ctas_per_replica;
+    int nplanes;
 };
 constexpr int ROLL_MAX_ROWS = 16;
 
@@ -763,7 +765,7 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
         k.m[0] = rm.own0; k.m[1] = rm.own1; k.m[2] = rm.next;
         k.p[0] = rp.prev; k.p[1] = rp.own0; k.p[2] = rp.own1;
         k.q[0] = rq.prev.div; k.q[1] = rq.own0.div; k.q[2] = rq.own1.div;
-        uint4 *O = (STORE && p.slots) ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * NS * p.n) + ((size_t)a * cpr + ci) : nullptr;
+        uint4 *O = (STORE && p.slots) ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + ((size_t)a * cpr + ci) : nullptr;
         uint32_t pk[7];
         sweep_chunk_n<STORE>(k, O, (size_t)cpl, pk);
 #pragma unroll
@@ -930,6 +932,110 @@ __global__ void __launch_bounds__(256) kmc_sweep_kernel_mm(const SweepParams p)
         if (out[j] != 0xFF) atomicAdd(R + out[j], 1u);
     }
 }
+// ---- MoveMonovacancy planes for aligned shapes: the companion of the 17-plane aligned kernels ---------------------
+// One thread = 16 consecutive sites of a row (one 128-bit load per neighbour row, twelve 128-bit streaming stores:
+// planes 17 + 2k + (L - 1)).  Byte-parallel: a 32-bit word holds four sites; a (direction, layer) slot exists where the
+// site's layer set contains L (bit L-1 of a status <= 3) and the neighbour's layer set is defined and lacks L; the class
+// code is 13 + 2 * (site is a divacancy) + (neighbour is not pristine).  12 algorithmic bytes per site on top of the
+// 18 of the 17-plane sweep.  Row counts of the four classes go to their own table rowmm [R][d0][4] (zero on entry).
+struct SweepMMParams {
+    int d0, d1, n, n_replicas;
+    const uint8_t *status;
+    uint8_t *slots;                    // [R][29][n] (planes 17..28 are written here) or nullptr
+    uint32_t *rowmm;                   // [R][d0][4]
+};
+struct MMFlags { uint32_t l1, l2, div, def, nz; };        // per byte 0/1: layer 1 / 2 vacant, divacancy, defined, non-pristine
+__device__ __forceinline__ MMFlags mm_flags(uint32_t w) {
+    const uint32_t e0 = w & ONES, e1 = (w >> 1) & ONES, hi = ((w >> 2) | (w >> 3)) & ONES;
+    MMFlags f;
+    f.def = hi ^ ONES; f.l1 = e0 & f.def; f.l2 = e1 & f.def; f.div = e0 & e1 & f.def; f.nz = (e0 | e1) & f.def;
+    return f;
+}
+__global__ void __launch_bounds__(256) kmc_sweep_mm16_kernel(const SweepMMParams p)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cpr = p.d1 >> 4, cpl = p.n >> 4;
+    const long long g = (long long)blockIdx.x * 256 + tid;
+    const int rep = (int)(g / cpl);
+    if (rep >= p.n_replicas) return;
+    const int cl = (int)(g - (long long)rep * cpl);
+    const int a = cl / cpr, ci = cl - a * cpr;
+    const int d0 = p.d0;
+    const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1;
+    const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+    const uint8_t *S = p.status + (size_t)rep * p.n;
+    const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+    const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+    const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+    const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci);
+    // words of the three rows around the chunk: index 0 = the word before the chunk, 1..4 = the chunk, 5 = the word after
+    uint32_t cw[6], mw[6], pw[6];
+    cw[0] = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3); cw[1] = c4.x; cw[2] = c4.y; cw[3] = c4.z; cw[4] = c4.w;
+    cw[5] = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+    mw[0] = 0; mw[1] = m4.x; mw[2] = m4.y; mw[3] = m4.z; mw[4] = m4.w; mw[5] = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+    pw[0] = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3); pw[1] = p4.x; pw[2] = p4.y; pw[3] = p4.z; pw[4] = p4.w; pw[5] = 0;
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + ((size_t)rep * NSA + MM_SLOT0) * p.n) + cl : nullptr;
+    uint32_t n_nat = 0, n_mer = 0, n_spl = 0, n_swp = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        uint32_t o1[4], o2[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            // the neighbour word of direction k (neighbors_and_mutuals order: (-1,1) (0,-1) (1,0) (0,1) (-1,0) (1,-1))
+            uint32_t tw;
+            if (k == 0) tw = shr_sites(mw[j + 1], mw[j + 2], 1);
+            else if (k == 1) tw = shl_sites(cw[j], cw[j + 1], 1);
+            else if (k == 2) tw = pw[j + 1];
+            else if (k == 3) tw = shr_sites(cw[j + 1], cw[j + 2], 1);
+            else if (k == 4) tw = mw[j + 1];
+            else tw = shl_sites(pw[j], pw[j + 1], 1);
+            const MMFlags sf = mm_flags(cw[j + 1]), tf = mm_flags(tw);
+            const uint32_t ex1 = sf.l1 & tf.def & ~tf.l1, ex2 = sf.l2 & tf.def & ~tf.l2;
+            const uint32_t cls = 0x0D0D0D0Du + 2u * sf.div + tf.nz;          // 13 + 2 * divacancy + non-pristine, per byte
+            o1[j] = code(ex1, cls); o2[j] = code(ex2, cls);
+            const uint32_t ex = ex1 + ex2;                                     // 0, 1 or 2 per byte
+            const uint32_t d = sf.div * 3u, z = tf.nz * 3u;                    // 0 / 3 masks per byte for the 2-bit counts
+            n_nat += hsum(ex & ~d & ~z); n_mer += hsum(ex & ~d & z);
+            n_spl += hsum(ex & d & ~z);  n_swp += hsum(ex & d & z);
+        }
+        if (O) {
+            __stcs(O + (size_t)(2 * k) * cpl, make_uint4(o1[0], o1[1], o1[2], o1[3]));
+            __stcs(O + (size_t)(2 * k + 1) * cpl, make_uint4(o2[0], o2[1], o2[2], o2[3]));
+        }
+    }
+    // row counts: a warp lies inside one row when a row holds a multiple of 32 chunks; else every thread adds its own
+    uint32_t *R4 = p.rowmm + ((size_t)rep * d0 + a) * 4;
+    if ((cpr & 31) == 0) {
+        const uint32_t s01 = __reduce_add_sync(0xFFFFFFFFu, n_nat | (n_mer << 16));
+        const uint32_t s23 = __reduce_add_sync(0xFFFFFFFFu, n_spl | (n_swp << 16));
+        if (lane == 0) {
+            if (s01 & 0xFFFFu) atomicAdd(R4 + 0, s01 & 0xFFFFu);
+            if (s01 >> 16) atomicAdd(R4 + 1, s01 >> 16);
+            if (s23 & 0xFFFFu) atomicAdd(R4 + 2, s23 & 0xFFFFu);
+            if (s23 >> 16) atomicAdd(R4 + 3, s23 >> 16);
+        }
+    } else {
+        if (n_nat) atomicAdd(R4 + 0, n_nat);
+        if (n_mer) atomicAdd(R4 + 1, n_mer);
+        if (n_spl) atomicAdd(R4 + 2, n_spl);
+        if (n_swp) atomicAdd(R4 + 3, n_swp);
+    }
+}
+// class totals 13..16 per replica from rowmm
+__global__ void kmc_reduce_rowmm_kernel(const uint32_t *rowmm, int d0, unsigned long long *counts)
+{
+    const int rep = blockIdx.x;
+    __shared__ unsigned long long acc[4];
+    if (threadIdx.x < 4) acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int c = threadIdx.x & 3;
+    unsigned long long s = 0;
+    for (int a = threadIdx.x >> 2; a < d0; a += blockDim.x >> 2) s += rowmm[((size_t)rep * d0 + a) * 4 + c];
+    atomicAdd(&acc[c], s);
+    __syncthreads();
+    if (threadIdx.x < 4) counts[(size_t)rep * NCA + C_MOVE_MONO + threadIdx.x] = acc[threadIdx.x];
+}
+
 __global__ void kmc_reduce_counts_mm_kernel(const uint32_t *rowcnt, int d0, int n_replicas, unsigned long long *counts)
 {
     const int rep = blockIdx.x;

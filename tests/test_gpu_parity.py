@@ -408,7 +408,8 @@ def test_sweep_matches_oracle(dim, variant):
     eng.close()
 
 
-@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (7, 130), (128, 32), (300, 260), (37, 1024)])
+@pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (7, 130), (128, 32), (300, 260), (37, 1024),
+                                 (64, 1024), (16, 4096), (512, 512), (256, 16), (8, 8192)])
 def test_sweep_with_move_monovacancy_matches_oracle(dim):
     """All nine rules: 29 slot planes, 17 classes, per-row counts."""
     sts = [evolved_state(dim, 3, rates=MM_RATES, order=MM_ORDER) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3),
