@@ -564,11 +564,14 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         for (int i = 0; i < 8 && lane16 < 0; i++) if (h->order_pos[cand[i]] < 0) lane16 = cand[i];
     }
     const bool hw_mm_ok = h->mm && lane16 >= 0 && h->d1 <= 64 && 2 * replica_hw_bytes(h->d0, true) <= (size_t)h->max_smem_optin;
-    if (h->mm && (h->variant == 2 || h->variant == 5 || (h->variant == 4 && !hw_mm_ok)))
-        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: replica kernels 0 (auto), 1, 3 (byte lattice) and -- for rows of "
-                                 "<= 64 sites with at least one own-status class disabled -- 4 (half-warp) apply");
-    const bool wide_ok = !h->mm && h->d1 > 64 && h->d1 <= 2048 &&
-                         wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin;
+    // ... and the wide bit-plane kernel (variant 5) in its CTA-per-replica build (replica_wide2_kernel.cuh)
+    const bool wide_geom = h->d1 > 64 && h->d1 <= 2048;
+    const bool wide_mm_ok = h->mm && wide_geom && wide2_cta_bytes(h->d0, true) <= (size_t)h->max_smem_optin - 1024;
+    if (h->mm && (h->variant == 2 || (h->variant == 5 && !wide_mm_ok) || (h->variant == 4 && !hw_mm_ok)))
+        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: replica kernels 0 (auto), 1, 3 (byte lattice), 4 (half-warp; rows "
+                                 "of <= 64 sites, at least one own-status class disabled) and 5 (wide bit planes; 64 < dim1 <= "
+                                 "2048) apply");
+    const bool wide_ok = h->mm ? wide_mm_ok : (wide_geom && wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (h->variant == 5 && !wide_ok)
         return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs 64 < dim1 <= 2048 and dim0 <= ~8700");
     // auto: lattices whose byte form does not fit shared memory, and batches too large for all replicas to be
@@ -576,7 +579,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // SM: 1184 replicas of 256x256 take 11.9 us per event there, 4.7 us here)
     bool wide_auto = false;
     if (h->variant == 0 && wide_ok) {
-        const size_t bbytes = replica_warp_bytes(h->d0, h->d1);
+        const size_t bbytes = replica_warp_bytes(h->d0, h->d1, h->mm);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
         const long long per_sm = bbytes <= (size_t)h->max_smem_optin ? (long long)((size_t)h->max_smem_optin / bbytes) : 0;
@@ -587,7 +590,8 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (h->variant == 5 || wide_auto) {
         const int Wa = wide_anchor_words(h->d1), We = wide_row_words(h->d1), d0p = (h->d0 + 1) & ~1;
         const size_t plane_words = (size_t)h->R * N_TYPES * h->d0 * We;
-        const size_t hier_elems = (size_t)h->R * NC * d0p;
+        const int nct = wide_tables(h->mm);
+        const size_t hier_elems = (size_t)h->R * nct * d0p;
         if (!h->d_planes) CU(cudaMalloc(&h->d_planes, plane_words * sizeof(unsigned long long)));
         if (!h->d_whier) {
             CU(cudaMalloc(&h->d_whier, hier_elems * sizeof(uint16_t)));
@@ -604,9 +608,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         }
         if (!h->whier_valid) {
             const long long rows = (long long)h->R * h->d0;
-            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p);
+            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p, nct);
+            if (h->mm) kmc_wide_hier_mm_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier, h->R, h->d0, h->d1, d0p);
             CU(cudaGetLastError());
-            h->launches += 1;
+            h->launches += h->mm ? 2 : 1;
             h->whier_valid = true;
         }
         const size_t wbytes = wide_warp_bytes(h->d0);
@@ -635,10 +640,15 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, h->device);
         bool cta_per_replica = h->R <= sms2 && h->warps_per_block == 0;       // (one CTA per SM; beyond that one warp per replica wins)
         if (const char *e = getenv("KMC_WIDE_CTA")) cta_per_replica = atoi(e) != 0;
-        if (cta_per_replica && wide2_cta_bytes(h->d0) <= (size_t)h->max_smem_optin - 1024) {
+        if (h->mm) {
+            // MoveMonovacancy: only the CTA-per-replica build maintains its classes (any batch size)
+            const size_t smem2 = wide2_cta_bytes(h->d0, true);
+            CU(cudaFuncSetAttribute(kmc_replica_wide2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            kmc_replica_wide2_kernel<true><<<(unsigned)h->R, 256, smem2, h->stream>>>(q);
+        } else if (cta_per_replica && wide2_cta_bytes(h->d0) <= (size_t)h->max_smem_optin - 1024) {
             const size_t smem2 = wide2_cta_bytes(h->d0);
-            CU(cudaFuncSetAttribute(kmc_replica_wide2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            kmc_replica_wide2_kernel<<<(unsigned)h->R, 256, smem2, h->stream>>>(q);
+            CU(cudaFuncSetAttribute(kmc_replica_wide2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            kmc_replica_wide2_kernel<false><<<(unsigned)h->R, 256, smem2, h->stream>>>(q);
         } else {
             CU(cudaFuncSetAttribute(kmc_replica_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kmc_replica_wide_kernel<<<(unsigned)((h->R + wpb - 1) / wpb), wpb * 32, smem, h->stream>>>(q);
@@ -649,11 +659,12 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
             if (!h->d_whier_chk) CU(cudaMalloc(&h->d_whier_chk, hier_elems * sizeof(uint16_t)));
             const long long rows = (long long)h->R * h->d0;
             CU(cudaMemsetAsync(h->d_whier_chk, 0, hier_elems * sizeof(uint16_t), h->stream));
-            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier_chk, h->R, h->d0, h->d1, d0p);
+            kmc_wide_hier_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier_chk, h->R, h->d0, h->d1, d0p, nct);
+            if (h->mm) kmc_wide_hier_mm_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, h->stream>>>(h->d_planes, h->d_whier_chk, h->R, h->d0, h->d1, d0p);
             kmc_wide_compare_kernel<<<(unsigned)((hier_elems + 255) / 256), 256, 0, h->stream>>>(
-                h->d_whier, h->d_whier_chk, (long long)NC * d0p, h->R, h->d_flags);
+                h->d_whier, h->d_whier_chk, (long long)nct * d0p, h->R, h->d_flags);
             CU(cudaGetLastError());
-            h->launches += 2;
+            h->launches += h->mm ? 3 : 2;
         }
         h->swept = false; h->hier_valid = false;
         h->bytes_stale = true;

@@ -20,9 +20,52 @@
 
 namespace kmc {
 
-__host__ __device__ inline size_t wide2_cta_bytes(int d0) {
+// Row tables: one per class of the reference's own rules; with MoveMonovacancy (MM build) three more -- natural (13),
+// merge-divacancy (14), swap-divacancy (15th table, class 16); split-divacancy (class 15) has none: its row count
+// is twice the sum of the row's four MoveDivacancy counts (see replica_hw_kernel.cuh).
+constexpr int WIDE_NCT_MM = 16;
+__host__ __device__ inline int wide_tables(bool mm) { return mm ? WIDE_NCT_MM : NC; }
+__host__ __device__ inline size_t wide2_cta_bytes(int d0, bool mm = false) {
     const size_t d0p = ((size_t)d0 + 1) & ~(size_t)1;
-    return ((NC * d0p * 2 + 15) & ~(size_t)15) + NC * 32 * sizeof(uint32_t);      // row table + 32 block sums per class
+    const size_t nct = (size_t)wide_tables(mm);
+    return ((nct * d0p * 2 + 15) & ~(size_t)15) + nct * 32 * sizeof(uint32_t);    // row tables + 32 block sums per table
+}
+// table of a class in the MM build (-1: derived)
+__device__ __forceinline__ int wide_table_of(int c) { return c < C_MOVE_MONO + 2 ? c : (c == C_MOVE_MONO + 3 ? 15 : -1); }
+
+// MoveMonovacancy counts of the cell (row a, word w) in direction k: natural | merge << 16, and swap
+__device__ __forceinline__ void mm_cell_counts(const WGeom &G, int a, int w, int k, uint32_t &nm, uint32_t &sw) {
+    const u64 v = G.valid(w);
+    const u64 m1 = window_at(G.rowp(T_M1, a), w, 0) & v, m2 = window_at(G.rowp(T_M2, a), w, 0) & v;
+    const u64 dv = window_at(G.rowp(T_D, a), w, 0) & v;
+    const int an = wrap1(a + nib(NBR_DA, k), G.d0), db = nib(NBR_DB, k);
+    const u64 zn = window_at(G.rowp(T_Z, an), w, db), m1n = window_at(G.rowp(T_M1, an), w, db);
+    const u64 m2n = window_at(G.rowp(T_M2, an), w, db);
+    nm = (uint32_t)__popcll((m1 | m2) & zn) | ((uint32_t)__popcll((m1 & m2n) | (m2 & m1n)) << 16);
+    sw = (uint32_t)__popcll(dv & (m1n | m2n));
+}
+// the sites of MoveMonovacancy kind q (class 13 + q) in slot (direction k, layer L) of the cell
+__device__ __forceinline__ u64 mm_cell_mask(const WGeom &G, int a, int w, int k, int layer, int q) {
+    const u64 v = G.valid(w);
+    const int an = wrap1(a + nib(NBR_DA, k), G.d0), db = nib(NBR_DB, k);
+    const u64 src = window_at(G.rowp(q < 2 ? (layer == 1 ? T_M1 : T_M2) : T_D, a), w, 0) & v;
+    const u64 dst = window_at(G.rowp((q & 1) ? (layer == 1 ? T_M2 : T_M1) : T_Z, an), w, db);
+    return src & dst;
+}
+// row tables 13, 14, 15 of the MM build from the planes: one thread per (replica, row)
+__global__ void kmc_wide_hier_mm_kernel(const u64 *planes, uint16_t *hier, int R, int d0, int d1, int d0p)
+{
+    const int Wa = wide_anchor_words(d1), We = Wa + 1;
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (long long)R * d0) return;
+    const int a = (int)(g % d0);
+    const long long rep = g / d0;
+    WGeom G{planes + rep * N_TYPES * d0 * We, d0, d1, Wa, We};
+    uint32_t nm = 0, sw = 0;
+    for (int w = 0; w < Wa; w++)
+        for (int k = 0; k < 6; k++) { uint32_t x, y; mm_cell_counts(G, a, w, k, x, y); nm += x; sw += y; }
+    uint16_t *H = hier + rep * WIDE_NCT_MM * d0p;
+    H[13 * d0p + a] = (uint16_t)nm; H[14 * d0p + a] = (uint16_t)(nm >> 16); H[15 * d0p + a] = (uint16_t)sw;
 }
 
 // one refresh task with warp-uniform operand descriptors (decoded once, outside the event loop)
@@ -59,8 +102,12 @@ __device__ __forceinline__ void role_counts(const u64 *P, int d0, int We, int a,
     else c01 = __popcll(first & Bv) + __popcll(first & C);
 }
 
+template <bool MM = false>
 __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WideParams wp)
 {
+    constexpr int NCT = MM ? WIDE_NCT_MM : NC;             // row tables
+    constexpr int NCX = MM ? NCA : NC;                     // classes
+    constexpr int NL = MM ? 32 : 16;                       // weight lanes of the class choice
     const ReplicaParams &p = wp.base;
     const int d0 = p.d0, d1 = p.d1, Wa = wp.Wa, We = wp.Wa + 1, d0p = wp.d0p;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -69,22 +116,22 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
     extern __shared__ uint4 smem_raw[];
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(smem_raw);
     uint32_t *rc32 = reinterpret_cast<uint32_t *>(rc16);
-    uint32_t *bs = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(rc16) + ((NC * (size_t)d0p * 2 + 15) & ~(size_t)15));
+    uint32_t *bs = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(rc16) + ((NCT * (size_t)d0p * 2 + 15) & ~(size_t)15));
     __shared__ int s_csel, s_row, s_zero, s_tie, s_col, s_s0;
-    __shared__ uint32_t s_rin, s_slot_tot[8];
+    __shared__ uint32_t s_rin, s_slot_tot[12];
     __shared__ double s_total;
-    __shared__ int s_delta[16];                             // class total changes of the refresh (classes 2..6)
+    __shared__ int s_delta[20];                             // class total changes of the refresh (classes 2..6, 13..16)
 
     u64 *P = wp.planes + (size_t)rep * N_TYPES * d0 * We;
     WGeom G{P, d0, d1, Wa, We};
-    uint16_t *ghier = wp.hier + (size_t)rep * NC * d0p;
-    for (int i = tid; i < (NC * d0p) / 2; i += 256) rc32[i] = reinterpret_cast<const uint32_t *>(ghier)[i];
-    if (tid < 16) s_delta[tid] = 0;
+    uint16_t *ghier = wp.hier + (size_t)rep * NCT * d0p;
+    for (int i = tid; i < (NCT * d0p) / 2; i += 256) rc32[i] = reinterpret_cast<const uint32_t *>(ghier)[i];
+    if (tid < 20) s_delta[tid] = 0;
     __syncthreads();
     int bshift = 0;
     while ((32 << bshift) < d0) bshift++;
     const int B = 1 << bshift;
-    for (int c = warp; c < NC; c += 8) {
+    for (int c = warp; c < NCT; c += 8) {
         uint32_t sum = 0;
         for (int q = 0; q < B; q++) { const int a = lane * B + q; if (a < d0) sum += rc16[c * d0p + a]; }
         bs[c * 32 + lane] = sum;
@@ -92,14 +139,20 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
     __syncthreads();
 
     // warp 0: class state (lane c owns class c)
-    const int myc = lane < NC ? lane : 0;
-    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    const int myc = lane < NCX ? lane : 0;
+    const double rate = (lane < NCX && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (lane < NCX && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
     int tot = 0;
-    if (warp == 0 && lane < NC)
-        for (int i = 0; i < 32; i++) tot += (int)bs[lane * 32 + i];
+    if (warp == 0 && lane < NCX) {
+        if (MM && lane == C_MOVE_MONO + 2) {                // split-divacancy: twice the MoveDivacancy hops
+            for (int q = 0; q < 4; q++) for (int i = 0; i < 32; i++) tot += 2 * (int)bs[(C_MOVE_DIV + q) * 32 + i];
+        } else {
+            const int tb = MM ? wide_table_of(lane) : lane;
+            for (int i = 0; i < 32; i++) tot += (int)bs[tb * 32 + i];
+        }
+    }
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
-    PickState pstate = pick_state_init(lane);
+    PickState pstate = pick_state_init_n<NL>(lane);
     // warp 7: statistics
     unsigned long long hist = 0, hops = 0, n_ties = 0;
     double tclock = p.clock ? p.clock[rep] : 0.0;
@@ -131,11 +184,11 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             const double u1 = __shfl_sync(FULL, mu1, (int)(t & 31));
             const double u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
             const double w = __dmul_rn((double)tot, rate);
-            const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
+            const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
             if (p.log_mode == KMC_LOG_FULL && !pick.zero) {
                 kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                       ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-                if (lane < NCA) rec->counts[lane] = lane < NC ? (uint32_t)tot : 0u;
+                if (lane < NCA) rec->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
             }
             int row = 0;
             uint32_t r = 0;
@@ -145,17 +198,29 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                 long long rr = (long long)__dmul_rn(u2, (double)cnt);
                 if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
                 r = (uint32_t)rr;
+                // row count of the chosen class: its table, or (split-divacancy) twice the four MoveDivacancy tables
+                const bool split = MM && csel == C_MOVE_MONO + 2;
+                const int tb = MM ? (split ? C_MOVE_DIV : wide_table_of(csel)) : csel;
+                auto blocksum = [&](int i) -> uint32_t {
+                    return split ? 2u * (bs[C_MOVE_DIV * 32 + i] + bs[(C_MOVE_DIV + 1) * 32 + i] + bs[(C_MOVE_DIV + 2) * 32 + i] +
+                                         bs[(C_MOVE_DIV + 3) * 32 + i]) : bs[tb * 32 + i];
+                };
+                auto rowcount = [&](int a) -> uint32_t {
+                    return split ? 2u * ((uint32_t)rc16[C_MOVE_DIV * d0p + a] + rc16[(C_MOVE_DIV + 1) * d0p + a] +
+                                         rc16[(C_MOVE_DIV + 2) * d0p + a] + rc16[(C_MOVE_DIV + 3) * d0p + a])
+                                 : (uint32_t)rc16[tb * d0p + a];
+                };
                 int L = 0;
-                warp_rank_search(bs[csel * 32 + lane], r, L, lane);
+                warp_rank_search(blocksum(lane), r, L, lane);
                 const int a0 = (L << bshift) + lane * r2;
                 uint32_t sum = 0;
                 for (int q = 0; q < r2; q++)
-                    if (lane * r2 + q < B && a0 + q < d0) sum += rc16[csel * d0p + a0 + q];
+                    if (lane * r2 + q < B && a0 + q < d0) sum += rowcount(a0 + q);
                 int L2 = 0;
                 warp_rank_search(sum, r, L2, lane);
                 row = (L << bshift) + L2 * r2;
                 for (int q = 0; q < r2 - 1; q++) {
-                    const uint32_t v = rc16[csel * d0p + row];
+                    const uint32_t v = rowcount(row);
                     if (r < v) break;
                     r -= v; row++;
                 }
@@ -165,7 +230,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                 s_row = row; s_rin = r;
             }
         }
-        if (tid < 8) s_slot_tot[tid] = 0;
+        if (tid < 12) s_slot_tot[tid] = 0;
         __syncthreads();                                               // B1
         if (s_zero) {                                                  // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
@@ -190,8 +255,9 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
 
         // ================= phase 2: the class's slot masks of the chosen row, one role per warp ================
         // (warp 7 meanwhile starts the plane rows of the refresh moving: Z and D of rows row-3 .. row+3)
-        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
-        u64 m = 0;
+        const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 :
+                          ((MM && csel >= C_MOVE_MONO) ? 3 : 0));
+        u64 m = 0, m_l2 = 0;                                   // (MM group: the warp's direction, layers 1 and 2)
         if (warp == 7) {
             const int lines = (We * 8 + 127) >> 7;
             const int j = lane >> 2, pl = (lane >> 1) & 1, li = lane & 1;
@@ -207,6 +273,11 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                     u64 pr, ne, fa;
                     cell_dir_masks(nb, warp, pr, ne, fa);
                     m = kind_select(pr, ne, fa, csel - C_MOVE_DIV);
+                }
+            } else if (MM && group == 3) {
+                if (warp < 6) {
+                    m = mm_cell_mask(G, row, lane, warp, 1, csel - C_MOVE_MONO);
+                    m_l2 = mm_cell_mask(G, row, lane, warp, 2, csel - C_MOVE_MONO);
                 }
             } else if (group == 2) {
                 if (warp < 2) {
@@ -236,18 +307,26 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                 }
             }
         }
-        const uint32_t mcnt = __popcll(m);
+        uint32_t mcnt = __popcll(m);
+        const uint32_t mcnt2 = MM ? (uint32_t)__popcll(m_l2) : 0u;
         if (warp < 6) {
-            const uint32_t wt = __reduce_add_sync(FULL, mcnt);
-            if (lane == 0) s_slot_tot[warp] = wt;
+            if (MM && group == 3) {                                    // slots (direction, layer) = 2 * warp + (L - 1)
+                const uint32_t wt = __reduce_add_sync(FULL, mcnt | (mcnt2 << 16));
+                if (lane == 0) { s_slot_tot[2 * warp] = wt & 0xFFFFu; s_slot_tot[2 * warp + 1] = wt >> 16; }
+            } else {
+                const uint32_t wt = __reduce_add_sync(FULL, mcnt);
+                if (lane == 0) s_slot_tot[warp] = wt;
+            }
         }
         __syncthreads();                                               // B2
         uint32_t r = s_rin;
         int j = 0;
 #pragma unroll
-        for (int q = 0; q < 5; q++)
+        for (int q = 0; q < (MM ? 11 : 5); q++)
             if (j == q && r >= s_slot_tot[q]) { r -= s_slot_tot[q]; j = q + 1; }
-        if (warp == j) {
+        const int jwarp = (MM && group == 3) ? j >> 1 : j;
+        if (MM && group == 3 && (j & 1)) { m = m_l2; mcnt = mcnt2; }
+        if (warp == jwarp) {
             int L = 0;
             warp_rank_search(mcnt, r, L, lane);                        // r: rank inside word L of slot j
             const u64 mj = __shfl_sync(FULL, m, L);
@@ -255,7 +334,8 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             if (lane == 0) {
                 s_col = 64 * L + bit;
                 int s0v = S_DIVAC;
-                if (!group) switch (csel) {
+                if (MM && group == 3) { if (csel < C_MOVE_MONO + 2) s0v = (j & 1) + 1; }    // the hopping layer
+                else if (!group) switch (csel) {
                     case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0v = 0; break;
                     case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0v = 3; break;
                     case C_DESTROY_TREF: s0v = j ? 7 : 4; break;
@@ -288,6 +368,12 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             mv.b2 = wrap1(col + db2, d1);
             mv.ns1 = (int)((e.w1 >> 16) & 0xF); mv.ns2 = (int)((e.w1 >> 20) & 0xF);
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
+            if (MM && slot >= MM_SLOT0) {
+                const int layer = ((slot - MM_SLOT0) & 1) + 1;
+                const bool onto_mono = (csel - C_MOVE_MONO) & 1;
+                os1 = onto_mono ? 3 - layer : 0;
+                mv.ns1 = onto_mono ? 3 : layer;
+            }
         }
         const int na = mv.na;
         // words holding a column within 2 of a touched column (see replica_wide_kernel.cuh)
@@ -323,8 +409,11 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             ta = wrap1(wrap1(a, d0), d0);
             tact = lane < ntk;
         }
-        uint32_t b01 = 0, b23 = 0;
-        if (tact) role_counts(P, d0, We, ta, twd, warp, ops, G.valid(twd), b01, b23);
+        uint32_t b01 = 0, b23 = 0, bnm = 0, bsw = 0;
+        if (tact) {
+            role_counts(P, d0, We, ta, twd, warp, ops, G.valid(twd), b01, b23);
+            if (MM && warp < 6) mm_cell_counts(G, ta, twd, warp, bnm, bsw);
+        }
         if (warp == 7) {
             if (p.clock && lane == 0)
                 tclock = __dadd_rn(tclock, kmc_time_step(p.clock_mode, total, p.seed, p.replica0 + (uint32_t)rep,
@@ -343,7 +432,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                 }
             }
             if (lane == csel) hist++;
-            if (lane == slot - 7) hops++;
+            if (lane == slot - 7 && slot < 13) hops++;
             if (tie && lane == 0) n_ties++;
             if (tracer && lane == 31)
                 tracer_update(tracer, slot, na, site, mv.ns0, mv.a1 * d1 + mv.b1, mv.ns1, mv.a2 * d1 + mv.b2, mv.ns2, s0);
@@ -415,6 +504,28 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                     atomicAdd(&bs[C_CREATE_TREF * 32 + (ta >> bshift)], (uint32_t)dd[0]);
                 }
             }
+            if (MM && warp < 6) {
+                uint32_t anm = 0, asw = 0;
+                if (tact) {
+                    mm_cell_counts(G, ta, twd, warp, anm, asw);
+                    const int dm[3] = {(int)(anm & 0xFFFF) - (int)(bnm & 0xFFFF), (int)(anm >> 16) - (int)(bnm >> 16),
+                                       (int)asw - (int)bsw};
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        if (dm[q]) {
+                            atomicAdd(&rc32[((13 + q) * d0p + ta) >> 1], (uint32_t)dm[q] << (16 * (ta & 1)));
+                            atomicAdd(&bs[(13 + q) * 32 + (ta >> bshift)], (uint32_t)dm[q]);
+                        }
+                }
+                int n_lo, n_hi, s_lo, s_hi;
+                reduce_packed_diff(anm, bnm, n_lo, n_hi);
+                reduce_packed_diff(asw, bsw, s_lo, s_hi);
+                if (lane == 0) {
+                    if (n_lo) atomicAdd(&s_delta[C_MOVE_MONO], n_lo);
+                    if (n_hi) atomicAdd(&s_delta[C_MOVE_MONO + 1], n_hi);
+                    if (s_lo) atomicAdd(&s_delta[C_MOVE_MONO + 3], s_lo);
+                }
+            }
             int d_lo, d_hi, e_lo, e_hi;
             reduce_packed_diff(a01, b01, d_lo, d_hi);
             if (warp < 6) {
@@ -432,21 +543,35 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             }
         }
         __syncthreads();                                               // B6
-        if (warp == 0 && lane >= C_MOVE_DIV && lane <= C_CREATE_TREF) {
-            tot += s_delta[lane];
-            s_delta[lane] = 0;                    // (written again only after B5 of the next event)
+        if (warp == 0) {
+            int d = 0;
+            if (lane >= C_MOVE_DIV && lane <= C_CREATE_TREF) d = s_delta[lane];
+            if (MM && (lane == C_MOVE_MONO || lane == C_MOVE_MONO + 1 || lane == C_MOVE_MONO + 3)) d = s_delta[lane];
+            if (MM && lane == C_MOVE_MONO + 2)    // split-divacancy = 2 x MoveDivacancy hops
+                d = 2 * (s_delta[C_MOVE_DIV] + s_delta[C_MOVE_DIV + 1] + s_delta[C_MOVE_DIV + 2] + s_delta[C_MOVE_DIV + 3]);
+            tot += d;
+            __syncwarp();
+            if (lane < 20) s_delta[lane] = 0;     // (written again only after B5 of the next event)
         }
     }
 
     // ---- epilogue ---------------------------------------------------------------------------------------------
     __syncthreads();
     const long long done = t;
-    for (int i = tid; i < (NC * d0p) / 2; i += 256) reinterpret_cast<uint32_t *>(ghier)[i] = rc32[i];
+    for (int i = tid; i < (NCT * d0p) / 2; i += 256) reinterpret_cast<uint32_t *>(ghier)[i] = rc32[i];
     if (warp == 0) {
-        if (lane < NC) {
+        if (lane < NCX) {
             int fresh = 0, blocks = 0;
-            for (int a = 0; a < d0; a++) fresh += rc16[lane * d0p + a];
-            for (int i = 0; i < 32; i++) blocks += (int)bs[lane * 32 + i];
+            if (MM && lane == C_MOVE_MONO + 2) {
+                for (int q = 0; q < 4; q++) {
+                    for (int a = 0; a < d0; a++) fresh += 2 * rc16[(C_MOVE_DIV + q) * d0p + a];
+                    for (int i = 0; i < 32; i++) blocks += 2 * (int)bs[(C_MOVE_DIV + q) * 32 + i];
+                }
+            } else {
+                const int tb = MM ? wide_table_of(lane) : lane;
+                for (int a = 0; a < d0; a++) fresh += rc16[tb * d0p + a];
+                for (int i = 0; i < 32; i++) blocks += (int)bs[tb * 32 + i];
+            }
             if (fresh != tot || blocks != tot) flag |= FLAG_VALIDATE;      // totals and block sums vs the row table
         }
         flag = __reduce_or_sync(FULL, flag);
@@ -456,7 +581,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
         }
     }
     if (warp == 7) {
-        if (lane < NC) p.hist[(size_t)rep * NCA + lane] += hist;
+        if (lane < NCX) p.hist[(size_t)rep * NCA + lane] += hist;
         if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
         if (lane == 0) {
             if (p.clock) p.clock[rep] = tclock;

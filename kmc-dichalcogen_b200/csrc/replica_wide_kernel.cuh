@@ -182,7 +182,8 @@ __global__ void kmc_wide_unpack_kernel(const u64 *planes, uint8_t *status, int R
 }
 
 // row table from the planes: one thread per (replica, row)
-__global__ void kmc_wide_hier_kernel(const u64 *planes, uint16_t *hier, int R, int d0, int d1, int d0p)
+// nct = tables per replica in `hier` (13; 16 when the MoveMonovacancy tables follow, see replica_wide2_kernel.cuh)
+__global__ void kmc_wide_hier_kernel(const u64 *planes, uint16_t *hier, int R, int d0, int d1, int d0p, int nct = NC)
 {
     const int Wa = wide_anchor_words(d1), We = Wa + 1;
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,7 +203,7 @@ __global__ void kmc_wide_hier_kernel(const u64 *planes, uint16_t *hier, int R, i
         cell_counts(n, c01, c23, ct);
         k01 += c01; k23 += c23; tre += ct;
     }
-    uint16_t *H = hier + rep * NC * d0p;
+    uint16_t *H = hier + rep * nct * d0p;
     H[C_CREATE_DIV * d0p + a] = (uint16_t)pz; H[C_FILL_DIV * d0p + a] = (uint16_t)pd;
     H[C_MOVE_DIV * d0p + a] = (uint16_t)k01; H[(C_MOVE_DIV + 1) * d0p + a] = (uint16_t)(k01 >> 16);
     H[(C_MOVE_DIV + 2) * d0p + a] = (uint16_t)k23; H[(C_MOVE_DIV + 3) * d0p + a] = (uint16_t)(k23 >> 16);
