@@ -345,7 +345,7 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
     // MoveMonovacancy live on an aligned shape (slot planes wanted): the 17-plane aligned kernel writes planes 0..16 of
     // the 29-plane layout, its companion kmc_sweep_mm16_kernel planes 17..28 and the four MoveMonovacancy row counts
-    const bool mm_split = h->mm && aligned && with_slots;
+    const bool mm_split = h->mm && aligned;
     h->sweep_split = mm_split;
     if (h->mm && !mm_split) {
         // MoveMonovacancy live: the general enumeration kernel (all 9 rules, 29 slot planes, one thread per site)
@@ -372,7 +372,7 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         CU(cudaMemsetAsync(h->d_rowmm, 0, R * h->d0 * 4 * sizeof(uint32_t), h->stream));
         SweepMMParams m;
         m.d0 = h->d0; m.d1 = h->d1; m.n = h->n; m.n_replicas = h->R;
-        m.status = h->d_status; m.slots = h->d_slots; m.rowmm = h->d_rowmm;
+        m.status = h->d_status; m.slots = with_slots ? h->d_slots : nullptr; m.rowmm = h->d_rowmm;
         const long long chunks = (long long)R * (h->n >> 4);
         kmc_sweep_mm16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, h->stream>>>(m);
         CU(cudaGetLastError());
@@ -971,6 +971,7 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
     for (long long t = 0; t < nsteps; t++) {
         rc = sweep_launch(h, false); if (rc) return rc;        // sim.py:114-115: initialize() every step
         p.rowcnt = h->d_rowcnt; p.counts = h->d_counts; p.t = t;
+        p.rowmm = h->sweep_split ? h->d_rowmm : nullptr; p.rc_stride = (h->mm && !h->sweep_split) ? RCG_STRIDE_MM : RCG_STRIDE;
         kmc_noinc_select_apply_kernel<<<h->R, 256, stage_bytes, h->stream>>>(p);
         CU(cudaGetLastError());
         h->launches += 1;

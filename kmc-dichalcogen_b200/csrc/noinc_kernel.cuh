@@ -16,6 +16,7 @@ struct NoincParams {
     const uint32_t *rowcnt;              // [R][d0][rc_stride]
     const unsigned long long *counts;    // [R][NCA]
     int rc_stride;                       // 16 (aligned sweep kernels) or 32 (MoveMonovacancy-aware sweep)
+    const uint32_t *rowmm;               // [R][d0][4] MoveMonovacancy row counts of the aligned two-kernel sweep, or nullptr
     int mm;                              // MoveMonovacancy classes are live: 17 classes
     double rate[NCA];
     int order_pos[NCA];
@@ -140,13 +141,15 @@ __global__ void __launch_bounds__(256) kmc_noinc_select_apply_kernel(const Noinc
         const int kr = (d0 + 255) / 256;
         const int r0 = tid * kr, r1 = min(r0 + kr, d0);
         unsigned long long local = 0, total;
-        for (int a = r0; a < r1; a++) local += rcg[(size_t)a * rcs + csel];
+        const uint32_t *rmm = p.rowmm ? p.rowmm + (size_t)rep * d0 * 4 : nullptr;
+        const bool in_mm = rmm && csel >= C_MOVE_MONO;
+        for (int a = r0; a < r1; a++) local += in_mm ? rmm[(size_t)a * 4 + csel - C_MOVE_MONO] : rcg[(size_t)a * rcs + csel];
         const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
         if (rank >= excl && rank < excl + local) {
             unsigned long long r = rank - excl;
             int a = r0;
             for (; a < r1; a++) {
-                const unsigned long long v = rcg[(size_t)a * rcs + csel];
+                const unsigned long long v = in_mm ? rmm[(size_t)a * 4 + csel - C_MOVE_MONO] : rcg[(size_t)a * rcs + csel];
                 if (r < v) break;
                 r -= v;
             }

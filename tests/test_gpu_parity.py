@@ -1137,3 +1137,20 @@ def test_plane_no_incremental_path_stops_on_zero_rate(monkeypatch):
     assert list(ev["cls"]) == [1, 1, 0xFF, 0xFF, 0xFF, 0xFF]
     assert (eng.download_state() == 0).all() and eng.steps_done()[0] == 2
     eng.close()
+
+
+@pytest.mark.parametrize("dim", [(64, 64), (16, 4096), (128, 32)])
+def test_no_incremental_with_move_monovacancy_on_aligned_shapes(dim):
+    """Aligned shapes enumerate with the two-kernel sweep (17-plane kernel + MoveMonovacancy companion), whose
+    MoveMonovacancy row counts live in their own table: the no-incremental selection must read both."""
+    st0 = exact_state(dim, 0.15, 0.15, 8)
+    eng = Engine(dim, MM_RATES, MM_ORDER)
+    eng.upload_state(st0)
+    ev = eng.run_noinc(150, 21, log_mode=nat.LOG_FULL)[0]
+    o = ko.Oracle(dim, MM_RATES, MM_ORDER, st0)
+    _, want = o.run_philox(21, 0, 0, 150)
+    assert_events_equal(ev, want, "noinc mm")
+    assert (ev["counts"] == want["counts"]).all()
+    assert (eng.download_state()[0] == o.status()).all()
+    assert (ev["cls"] >= 13).sum() > 20
+    eng.close()
