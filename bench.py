@@ -39,16 +39,31 @@ KB_EV = 1.38064852e-23 * 6.24150913e18            # reference demo1/sim.py:27-29
 WSE2_BARRIERS = {2: 2.25, 3: 2.11199155, 4: 2.52009312, 5: 2.25, 6: 3.12293677, 7: 4.43051273,
                  8: 6.72584072, 9: 6.72584072, 12: 3.41217502}      # config/WSe2.yaml
 WSE2_ORDER = [8, 9, 12, 2, 3, 4, 5, 6, 7]
+# config/WSe2.yaml with EVERY rule it names: MoveMonovacancy (:8-13) is a stub in the reference (rules.py:295-296) and was
+# left out in round 1; it is built now, so the headline workload is the whole file
+WSE2_FULL_BARRIERS = dict(WSE2_BARRIERS, **{"13": 2.56175687, "14": 3.03662851, "15": 2.33673358, "16": 2.56175687})
+WSE2_FULL_BARRIERS = {int(k): v for k, v in WSE2_FULL_BARRIERS.items()}
+WSE2_FULL_ORDER = [8, 9, 12, 13, 14, 15, 16, 2, 3, 4, 5, 6, 7]
 SWEEP_DIM = (4096, 4096)
 SWEEP_BYTES_PER_SITE = 18                         # 1 B status read + 17 B slot codes written
+SWEEP_BYTES_PER_SITE_FULL = 30                    # + 12 B MoveMonovacancy slot codes
+
+
+def _rates(barriers):
+    import math
+    r = [0.0] * 17
+    for c, e in barriers.items():
+        r[c] = math.exp(-e / (TEMPERATURE * KB_EV))
+    return r
 
 
 def wse2_rates():
-    import math
-    r = [0.0] * 17
-    for c, e in WSE2_BARRIERS.items():
-        r[c] = math.exp(-e / (TEMPERATURE * KB_EV))
-    return r
+    """config/WSe2.yaml without MoveMonovacancy: the round-1 headline workload (kept for continuity and probes)."""
+    return _rates(WSE2_BARRIERS)
+
+
+def wse2_full_rates():
+    return _rates(WSE2_FULL_BARRIERS)
 
 
 def synthetic_lattices(n_replicas, replica0, dim=DIM, frac_div=0.05, frac_mono=0.05):
@@ -211,7 +226,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rates, order = wse2_rates(), WSE2_ORDER
+    rates, order = wse2_full_rates(), WSE2_FULL_ORDER
     n_threads = os.cpu_count() or 1
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import kmc_oracle as ko
@@ -234,14 +249,14 @@ def run_reference_arm(args):
         total += done
     dt = time.perf_counter() - t0
     value = total / dt
-    sample = "%d replicas x %d events per step (64x64 WSe2, 1500 K), %d host threads" % (n_rep, n_ev, n_threads)
+    sample = "%d replicas x %d events per step (64x64, config/WSe2.yaml all rules, 1500 K), %d host threads" % (n_rep, n_ev, n_threads)
     line = {
         "impl": "reference", "metric": "kmc_events_per_sec", "value": value, "unit": "events/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 lattice / f64 rates",
         "data": "synthetic",
-        "config": {"workload": "config/WSe2.yaml 64x64 lattice, independent replicas, CPU port of the "
-                               "reference hot path (oracle/kmc_oracle.c), bounded sample", "sample": sample},
+        "config": {"workload": "config/WSe2.yaml (every rule, MoveMonovacancy included) 64x64 lattice, independent replicas, "
+                               "CPU port of the reference hot path (oracle/kmc_oracle.c), bounded sample", "sample": sample},
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": n_threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -301,7 +316,8 @@ def main():
         parallel.barrier()
         torch.cuda.synchronize()
 
-    rates, order = wse2_rates(), WSE2_ORDER
+    rates, order = wse2_full_rates(), WSE2_FULL_ORDER          # the headline: config/WSe2.yaml, every rule
+    rates13, order13 = wse2_rates(), WSE2_ORDER                 # round-1 workload (MoveMonovacancy left out)
     E = args.events
 
     def measure_batch(R, sample_clocks):
@@ -420,7 +436,10 @@ def main():
     roofline = None
     if rank == 0 and not args.no_sweep:
         peak, peak_src = measured_peaks()
-        sw = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
+        # the 17-plane kernel (kmc_sweep_roll_kernel) is launched identically with and without MoveMonovacancy; it is
+        # timed alone on an engine without the rule, the whole 29-plane sweep (that kernel + its MoveMonovacancy
+        # companion) on an engine with the full rule set below
+        sw = Engine(SWEEP_DIM, rates13, order13, n_replicas=1, device=local)
         sw.upload_state(iid_lattice(SWEEP_DIM, SEED))
         for _ in range(3):
             sw.sweep()
@@ -446,6 +465,21 @@ def main():
         steady_ms = sw.timer_stop() / n_steady
         sweep_launches = sw.launch_count() - l0
         sw.close()
+        fs = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
+        fs.upload_state(iid_lattice(SWEEP_DIM, SEED))
+        for _ in range(3):
+            fs.sweep()
+        fs.sync()
+        l0 = fs.launch_count()
+        ms_full = []
+        for _ in range(args.sweep_iters):
+            fs.flush_l2()
+            fs.timer_start()
+            fs.sweep()
+            ms_full.append(fs.timer_stop())
+        sweep_launches += fs.launch_count() - l0
+        fs.close()
+        full_ms = float(np.mean(ms_full))
         avg_ms = float(np.mean(ms))
         nsites = SWEEP_DIM[0] * SWEEP_DIM[1]
         achieved = nsites * SWEEP_BYTES_PER_SITE / (avg_ms * 1e-3) / 1e9
@@ -458,6 +492,11 @@ def main():
                     "achieved_steady": nsites * SWEEP_BYTES_PER_SITE / (steady_ms * 1e-3) / 1e9,
                     "frac_steady": nsites * SWEEP_BYTES_PER_SITE / (steady_ms * 1e-3) / 1e9 / peak,
                     "steady_note": "%d back-to-back launches alternating two slot-plane buffers, one CUDA event pair, no flush" % n_steady,
+                    "full_rule_set": {"what": "config/WSe2.yaml with MoveMonovacancy: 29 slot planes = this kernel + "
+                                              "kmc_sweep_mm16_kernel (+ row-count memset and reduce), one CUDA event pair",
+                                      "bytes_per_site": SWEEP_BYTES_PER_SITE_FULL, "ms_per_sweep": full_ms,
+                                      "achieved": nsites * SWEEP_BYTES_PER_SITE_FULL / (full_ms * 1e-3) / 1e9,
+                                      "frac": nsites * SWEEP_BYTES_PER_SITE_FULL / (full_ms * 1e-3) / 1e9 / peak},
                     "note": "timed region = exactly one launch (slot planes + row counts + class totals in one kernel), CUDA events on the engine's stream, L2 flushed before each launch"}
         launches += sweep_launches
 
@@ -465,61 +504,47 @@ def main():
     other = None
     if rank == 0 and not args.no_other_configs:
         other = {}
-        # configs[1]: 64x64, ONE trajectory, incremental (latency-bound: one warp on one SM)
-        one = Engine(DIM, rates, order, n_replicas=1, device=local)
-        one.upload_state(synthetic_lattices(1, 0))
-        one.run(20000, SEED)
-        one.sync()
-        one.timer_start()
-        one.run(500000, SEED)
-        ms1 = one.timer_stop()
-        one.close()
-        other["64x64_single_trajectory_incremental"] = {"events_per_s": 500000 / (ms1 * 1e-3), "events": 500000}
-        # the headline batch with every implemented rule live (config/mixed_rates.yaml: 13 classes, the two halves
-        # of a warp mostly choose different classes -- the half-warp kernel's worst case for lockstep)
+        FULL, R1 = "config/WSe2.yaml, every rule (MoveMonovacancy live)", "config/WSe2.yaml without MoveMonovacancy (round-1 workload)"
+
+        def timed_batch(rts, odr, nrep, warm, nev, dim=DIM, lattices=None):
+            e = Engine(dim, rts, odr, n_replicas=nrep, device=local)
+            e.upload_state(lattices if lattices is not None else synthetic_lattices(nrep, 0))
+            e.run(warm, SEED)
+            e.sync()
+            e.timer_start()
+            e.run(nev, SEED)
+            ms_ = e.timer_stop()
+            e.check_status()
+            h_ = e.histogram()
+            e.close()
+            return nrep * nev / (ms_ * 1e-3), [int(x) for x in h_]
+
+        # the round-1 headline workload (the same batch without MoveMonovacancy), for continuity with BENCH_r01
+        v, hh = timed_batch(rates13, order13, R, 1000, E)
+        other["64x64_x%d_wse2_without_move_monovacancy" % R] = {"events_per_s": v, "replicas": R, "events_per_replica": E,
+                                                               "config": R1, "kernel": "kmc_replica_hw_kernel<64,64,PLAIN>",
+                                                               "event_histogram": hh}
+        # the headline batch with every implemented rule of the reference live at comparable rates
+        # (config/mixed_rates.yaml: 13 classes; the two halves of a warp mostly choose different classes)
         mx_rates = [10.0, 20.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 55.0]
         mx_order = [8, 9, 10, 11, 0, 2, 3, 4, 5, 6, 7, 12, 1]
-        mx = Engine(DIM, mx_rates, mx_order, n_replicas=R, device=local)
-        mx.upload_state(synthetic_lattices(R, 0))
-        mx.run(2000, SEED)
-        mx.sync()
-        mx.timer_start()
-        mx.run(E, SEED)
-        msx = mx.timer_stop()
-        mx.check_status()
-        mxh = mx.histogram()
-        mx.close()
-        other["64x64_x%d_mixed_rates" % R] = {"events_per_s": R * E / (msx * 1e-3), "replicas": R, "events_per_replica": E,
+        v, hh = timed_batch(mx_rates, mx_order, R, 2000, E)
+        other["64x64_x%d_mixed_rates" % R] = {"events_per_s": v, "replicas": R, "events_per_replica": E,
                                               "config": "kmc-dichalcogen_b200/config/mixed_rates.yaml (13 live classes)",
-                                              "event_histogram": [int(x) for x in mxh]}
-        # the reference's config/WSe2.yaml with EVERY rule it names, i.e. MoveMonovacancy live (a stub in the
-        # reference; extension with stated semantics): 13 classes, ~90 % of the events are monovacancy hops.  The
-        # MoveMonovacancy-aware build of the half-warp kernel (8 row tables, class 16 on a disabled class's lane).
-        fw_bar = dict(WSE2_BARRIERS)
-        fw_bar.update({13: 2.56175687, 14: 3.03662851, 15: 2.33673358, 16: 2.56175687})
-        import math as _m
-        fw_rates = [(_m.exp(-fw_bar[c] / (TEMPERATURE * KB_EV)) if c in fw_bar else 0.0) for c in range(17)]
-        fw_order = [8, 9, 12, 13, 14, 15, 16, 2, 3, 4, 5, 6, 7]
-        fw = Engine(DIM, fw_rates, fw_order, n_replicas=R, device=local)
-        fw.upload_state(synthetic_lattices(R, 0))
-        fw.run(1000, SEED)
-        fw.sync()
-        fw.timer_start()
-        fw.run(E, SEED)
-        msf = fw.timer_stop()
-        fw.check_status()
-        fwh = fw.histogram()
-        fw.close()
-        other["64x64_x%d_wse2_full_with_move_monovacancy" % R] = {
-            "events_per_s": R * E / (msf * 1e-3), "replicas": R, "events_per_replica": E,
-            "config": "kmc-dichalcogen_b200/config/wse2_full.yaml (= reference config/WSe2.yaml, all rules)",
-            "kernel": "kmc_replica_hw_kernel<64,64,PLAIN,MM>", "event_histogram": [int(x) for x in fwh]}
+                                              "event_histogram": hh}
+        # configs[1]: 64x64, ONE trajectory, incremental (latency-bound: one warp on one SM)
+        v, _ = timed_batch(rates, order, 1, 20000, 300000)
+        v13, _ = timed_batch(rates13, order13, 1, 20000, 500000)
+        other["64x64_single_trajectory_incremental"] = {"events_per_s": v, "config": FULL,
+                                                        "without_move_monovacancy_events_per_s": v13}
         # the same trajectory through the reference-facing API with the reference's JSON event log produced for
         # every event (KmcSim.iter_json_lines: kernel launches of 4096 events + host formatting), wall clock
         from demo1.sim import KmcSim, RuleSpec
         from demo1.state import State
         specs = [RuleSpec("CreateMonovacancy", {"from-double": 6.72584072, "make-empty": 6.72584072}, True),
                  RuleSpec("FlipMonovacancy", {"natural": 3.41217502}, True),
+                 RuleSpec("MoveMonovacancy", {"natural": 2.56175687, "merge-divacancy": 3.03662851,
+                                              "split-divacancy": 2.33673358, "swap-divacancy": 2.56175687}, True),
                  RuleSpec("MoveDivacancy", {"natural": 2.25, "missing-metal": 2.11199155, "missing-comb": 2.52009312,
                                             "missing-both": 2.25}, True),
                  RuleSpec("CreateTrefoil", {"natural": 3.12293677}, True),
@@ -531,47 +556,41 @@ def main():
             nchar += sum(map(len, lines))
         dt = time.perf_counter() - t0
         sim.close()
-        other["64x64_single_trajectory_json_event_log"] = {"events_per_s": nlog / dt, "events": nlog,
+        other["64x64_single_trajectory_json_event_log"] = {"events_per_s": nlog / dt, "events": nlog, "config": FULL,
                                                            "json_bytes_per_event": nchar / nlog}
         # configs[0]: the reference's own CPU-runnable case (`python3 -m demo1 test-cfg.yaml`: 200x200, pristine
         # start, test-cfg.yaml rates, one trajectory); the Python reference does ~2.5e3 events/s on it
         tc_rates = [10.0, 0.0, 12.0, 3.0, 7.0, 7.0, 5000.0, 400.0, 10.0, 300.0, 100.0, 100.0, 0.0]
         tc_order = [8, 9, 10, 11, 0, 2, 3, 4, 5, 6, 7]
-        tc = Engine((200, 200), tc_rates, tc_order, n_replicas=1, device=local)
-        tc.upload_state(np.zeros((1, 200 * 200), dtype=np.uint8))
-        tc.run(10000, SEED)
-        tc.sync()
-        tc.timer_start()
-        tc.run(200000, SEED)
-        mst = tc.timer_stop()
-        tc.close()
-        other["200x200_testcfg_single_trajectory"] = {"events_per_s": 200000 / (mst * 1e-3), "events": 200000}
-        # configs[3] end to end: one `--no-incremental` event on 4096^2 = count-only sweep + select + apply
-        big = Engine(SWEEP_DIM, rates, order, n_replicas=1, device=local)
-        big.upload_state(iid_lattice(SWEEP_DIM, SEED))
-        big.run_noinc(5, SEED)
-        big.sync()
-        big.timer_start()
-        big.run_noinc(40, SEED)
-        msn = big.timer_stop()
-        big.close()
-        other["4096x4096_no_incremental_event"] = {"events_per_s": 40 / (msn * 1e-3), "ms_per_event": msn / 40,
-                                                   "launches_per_event": 2}
-        # configs[4] shape: 1024x1024 lattices stay in HBM/L2, row hierarchy in shared memory
+        v, _ = timed_batch(tc_rates, tc_order, 1, 10000, 200000, dim=(200, 200), lattices=np.zeros((1, 200 * 200), dtype=np.uint8))
+        other["200x200_testcfg_single_trajectory"] = {"events_per_s": v, "events": 200000}
+        # configs[3] end to end: one `--no-incremental` event on 4096^2 = full re-enumeration + select + apply.
+        # Without MoveMonovacancy the event runs on the bit-sliced lattice (noinc_planes_kernel.cuh); with it on the byte
+        # lattice (count-only 17-class sweep + MoveMonovacancy companion + block-wide selection)
+        for key, rts, odr in (("4096x4096_no_incremental_event", rates, order),
+                              ("4096x4096_no_incremental_event_without_move_monovacancy", rates13, order13)):
+            big = Engine(SWEEP_DIM, rts, odr, n_replicas=1, device=local)
+            big.upload_state(iid_lattice(SWEEP_DIM, SEED))
+            big.run_noinc(5, SEED)
+            big.sync()
+            big.timer_start()
+            big.run_noinc(40, SEED)
+            msn = big.timer_stop()
+            big.close()
+            other[key] = {"events_per_s": 40 / (msn * 1e-3), "ms_per_event": msn / 40}
+        # configs[4] shape: 1024x1024 lattices stay in HBM/L2 as bit planes, row tables in shared memory, one CTA per
+        # replica (128 replicas = one GPU's share of the 1024 at 8 GPUs)
         nrep5, ev5 = 128, 4000
-        lat = Engine((1024, 1024), rates, order, n_replicas=nrep5, device=local)
         rng = np.random.Generator(np.random.Philox(SEED))
         base = rng.choice(np.arange(4, dtype=np.uint8), size=1024 * 1024, p=(0.90, 0.025, 0.025, 0.05)).astype(np.uint8)
-        lat.upload_state(np.tile(base, (nrep5, 1)))
-        lat.run(200, SEED)
-        lat.sync()
-        lat.timer_start()
-        lat.run(ev5, SEED)
-        ms5 = lat.timer_stop()
-        lat.close()
+        lat5 = np.tile(base, (nrep5, 1))
+        v, _ = timed_batch(rates, order, nrep5, 200, ev5, dim=(1024, 1024), lattices=lat5)
+        v13, _ = timed_batch(rates13, order13, nrep5, 200, ev5, dim=(1024, 1024), lattices=lat5)
+        del lat5
         other["1024x1024_x128_replicas_incremental"] = {
-            "events_per_s": nrep5 * ev5 / (ms5 * 1e-3), "replicas": nrep5, "events_per_replica": ev5,
-            "note": "bit planes + row table stay in HBM/L2 between launches (wide bit-plane kernel)"}
+            "events_per_s": v, "config": FULL, "replicas": nrep5, "events_per_replica": ev5,
+            "without_move_monovacancy_events_per_s": v13,
+            "note": "bit planes + row tables stay in HBM/L2 between launches (wide bit-plane kernel, CTA per replica)"}
         # the initial lattices generated on the device (reference gen_random_state 'exact' under
         # a Philox stream per replica) instead of uploaded
         gen = Engine(DIM, rates, order, n_replicas=R, device=local)
@@ -597,9 +616,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": max_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 lattice / f64 rates", "data": "synthetic",
-            "config": {"workload": "config/WSe2.yaml (MoveMonovacancy stub disabled) T=1500K, 64x64 lattice, "
+            "config": {"workload": "config/WSe2.yaml, every rule it names (MoveMonovacancy -- a stub in the reference -- "
+                                   "built as an extension with stated semantics), T=1500K, 64x64 lattice, "
                                    "5%% divacancy + 5%% monovacancy, %d independent replicas per GPU, "
-                                   "two replicas per warp (half-warp kernel)" % R,
+                                   "two replicas per warp (half-warp kernel, MoveMonovacancy-aware build); the round-1 "
+                                   "workload (same file without that rule) is other_configs.64x64_x%d_wse2_without_move_monovacancy" % (R, R),
                        "replicas_per_gpu": R, "events_per_replica_per_step": E,
                        "l2": "flushed (256 MiB read on the engine's stream, leaves clean lines) before every timed launch", "seed": SEED,
                        "parallelism": "replicas sharded by contiguous global index; one NCCL all-reduce of "

@@ -975,7 +975,16 @@ __global__ void __launch_bounds__(256) kmc_sweep_mm16_kernel(const SweepMMParams
     mw[0] = 0; mw[1] = m4.x; mw[2] = m4.y; mw[3] = m4.z; mw[4] = m4.w; mw[5] = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
     pw[0] = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3); pw[1] = p4.x; pw[2] = p4.y; pw[3] = p4.z; pw[4] = p4.w; pw[5] = 0;
     uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + ((size_t)rep * NSA + MM_SLOT0) * p.n) + cl : nullptr;
-    uint32_t n_nat = 0, n_mer = 0, n_spl = 0, n_swp = 0;
+    // source-site flags of the chunk's four words, hoisted out of the direction loop
+    uint32_t sl1[4], sl2[4], sd3[4], sbase[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const MMFlags sf = mm_flags(cw[j + 1]);
+        sl1[j] = sf.l1; sl2[j] = sf.l2; sd3[j] = sf.div * 3u;
+        sbase[j] = 0x0D0D0D0Du + 2u * sf.div;                       // 13 + 2 * divacancy per byte
+    }
+    // per-byte running sums of the four kinds (<= 2 per byte and step, 24 steps: no carries); one hsum each at the end
+    uint32_t a_nat = 0, a_mer = 0, a_spl = 0, a_swp = 0;
 #pragma unroll
     for (int k = 0; k < 6; k++) {
         uint32_t o1[4], o2[4];
@@ -989,20 +998,21 @@ __global__ void __launch_bounds__(256) kmc_sweep_mm16_kernel(const SweepMMParams
             else if (k == 3) tw = shr_sites(cw[j + 1], cw[j + 2], 1);
             else if (k == 4) tw = mw[j + 1];
             else tw = shl_sites(pw[j], pw[j + 1], 1);
-            const MMFlags sf = mm_flags(cw[j + 1]), tf = mm_flags(tw);
-            const uint32_t ex1 = sf.l1 & tf.def & ~tf.l1, ex2 = sf.l2 & tf.def & ~tf.l2;
-            const uint32_t cls = 0x0D0D0D0Du + 2u * sf.div + tf.nz;          // 13 + 2 * divacancy + non-pristine, per byte
+            const MMFlags tf = mm_flags(tw);
+            const uint32_t ex1 = sl1[j] & tf.def & ~tf.l1, ex2 = sl2[j] & tf.def & ~tf.l2;
+            const uint32_t cls = sbase[j] + tf.nz;                             // + (neighbour is not pristine)
             o1[j] = code(ex1, cls); o2[j] = code(ex2, cls);
             const uint32_t ex = ex1 + ex2;                                     // 0, 1 or 2 per byte
-            const uint32_t d = sf.div * 3u, z = tf.nz * 3u;                    // 0 / 3 masks per byte for the 2-bit counts
-            n_nat += hsum(ex & ~d & ~z); n_mer += hsum(ex & ~d & z);
-            n_spl += hsum(ex & d & ~z);  n_swp += hsum(ex & d & z);
+            const uint32_t z3 = tf.nz * 3u;
+            const uint32_t e_m = ex & ~sd3[j], e_d = ex & sd3[j];              // source monovacancy / divacancy
+            a_nat += e_m & ~z3; a_mer += e_m & z3; a_spl += e_d & ~z3; a_swp += e_d & z3;
         }
         if (O) {
             __stcs(O + (size_t)(2 * k) * cpl, make_uint4(o1[0], o1[1], o1[2], o1[3]));
             __stcs(O + (size_t)(2 * k + 1) * cpl, make_uint4(o2[0], o2[1], o2[2], o2[3]));
         }
     }
+    const uint32_t n_nat = hsum(a_nat), n_mer = hsum(a_mer), n_spl = hsum(a_spl), n_swp = hsum(a_swp);
     // row counts: a warp lies inside one row when a row holds a multiple of 32 chunks; else every thread adds its own
     uint32_t *R4 = p.rowmm + ((size_t)rep * d0 + a) * 4;
     if ((cpr & 31) == 0) {
