@@ -567,10 +567,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     // ... and the wide bit-plane kernel (variant 5) in its CTA-per-replica build (replica_wide2_kernel.cuh)
     const bool wide_geom = h->d1 > 64 && h->d1 <= 2048;
     const bool wide_mm_ok = h->mm && wide_geom && wide2_cta_bytes(h->d0, true) <= (size_t)h->max_smem_optin - 1024;
-    if (h->mm && (h->variant == 2 || (h->variant == 5 && !wide_mm_ok) || (h->variant == 4 && !hw_mm_ok)))
-        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: replica kernels 0 (auto), 1, 3 (byte lattice), 4 (half-warp; rows "
-                                 "of <= 64 sites, at least one own-status class disabled) and 5 (wide bit planes; 64 < dim1 <= "
-                                 "2048) apply");
+    if (h->mm && ((h->variant == 5 && !wide_mm_ok) || (h->variant == 4 && !hw_mm_ok)))
+        return fail(KMC_ERR_ARG, "MoveMonovacancy is enabled: of the bit-sliced kernels, 4 (half-warp) needs rows of <= 64 sites "
+                                 "and at least one own-status class disabled, 5 (wide bit planes) needs 64 < dim1 <= 2048");
     const bool wide_ok = h->mm ? wide_mm_ok : (wide_geom && wide_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (h->variant == 5 && !wide_ok)
         return fail(KMC_ERR_ARG, "the wide bit-plane kernel needs 64 < dim1 <= 2048 and dim0 <= ~8700");
@@ -674,7 +673,7 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     { int rc = ensure_bytes(h); if (rc) return rc; }
     long long hw_min = 4096;
     if (const char *e = getenv("KMC_HW_MIN_REPLICAS")) hw_min = atoll(e);              // tuning knob
-    const bool halfwarp = h->variant == 4 || (h->variant == 0 && hw_mm_ok) ||
+    const bool halfwarp = h->variant == 4 || (h->variant == 0 && hw_mm_ok && h->R >= hw_min) ||
                           (!h->mm && h->variant == 0 && h->d1 <= 64 && h->R >= hw_min &&
                            2 * replica_hw_bytes(h->d0) <= (size_t)h->max_smem_optin);
     if (halfwarp) {
@@ -737,10 +736,10 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         if (rs) CU(cudaMemcpyAsync(host_events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));
         return KMC_OK;
     }
-    const bool bitplanes = h->variant == 2 || (!h->mm && h->variant == 0 && h->d1 <= 64 &&
-                                               replica_bp_warp_bytes(h->d0) <= (size_t)h->max_smem_optin);
+    const bool bitplanes = h->variant == 2 || (h->variant == 0 && h->d1 <= 64 &&
+                                               replica_bp_warp_bytes(h->d0, h->mm) <= (size_t)h->max_smem_optin);
     if (bitplanes && h->d1 > 64) return fail(KMC_ERR_ARG, "the bit-plane replica kernel needs dim1 <= 64");
-    size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0) : replica_warp_bytes(h->d0, h->d1, h->mm);
+    size_t wbytes = bitplanes ? replica_bp_warp_bytes(h->d0, h->mm) : replica_warp_bytes(h->d0, h->d1, h->mm);
     // lattices that do not fit shared memory stay in HBM/L2; only the row-count hierarchy is staged
     const bool global_state = h->variant == 3 || (!bitplanes && wbytes > (size_t)h->max_smem_optin);
     if (global_state) {
@@ -788,7 +787,11 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
     if (bitplanes) {
         // small batches cannot use the occupancy the 64-register build is compiled for: latency build (96 registers)
         const bool lat = getenv("KMC_BP_LAT") ? atoi(getenv("KMC_BP_LAT")) != 0 : h->R <= 16 * 148;
-        if (h->d0 == 64 && h->d1 == 64) { if (lat) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, true>)); else KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>)); }
+        if (h->mm) {
+            if (h->d0 == 64 && h->d1 == 64) {
+                if (lat) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, true, true>)); else KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, false, true>));
+            } else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0, false, true>));
+        } else if (h->d0 == 64 && h->d1 == 64) { if (lat) KMC_LAUNCH((kmc_replica_bp_kernel<64, 64, true>)); else KMC_LAUNCH((kmc_replica_bp_kernel<64, 64>)); }
         else KMC_LAUNCH((kmc_replica_bp_kernel<0, 0>));
     } else if (global_state) {
         if (h->mm) KMC_LAUNCH((kmc_replica_kernel<0, 0, true, true>)); else KMC_LAUNCH((kmc_replica_kernel<0, 0, true>));

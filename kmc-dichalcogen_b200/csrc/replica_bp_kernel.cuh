@@ -41,12 +41,17 @@ enum { PL_Z = 0, PL_ZP = 1, PL_ZM = 2, PL_D = 3, PL_DP = 4, PL_DM = 5, PL_M1 = 6
 #define KMC_BP_PAD 3
 #endif
 #define BPS(d0) ((d0) + KMC_BP_PAD)
-__host__ __device__ inline size_t replica_bp_warp_bytes(int d0) {
+// Row tables: one per class of the reference's own rules (13); the MoveMonovacancy build keeps three more -- natural
+// (13), merge-divacancy (14), swap-divacancy (table 15 = class 16); split-divacancy (class 15) is derived: twice the sum
+// of the row's four MoveDivacancy counts.
+constexpr int BP_NCT_MM = 16;
+__host__ __device__ inline size_t replica_bp_warp_bytes(int d0, bool mm = false) {
     const size_t d0e = ((size_t)d0 + 1) & ~(size_t)1;
     const size_t planes = (size_t)N_PLANES * BPS(d0) * 8;
-    const size_t rc = (NC * d0e * 2 + 15) & ~(size_t)15;
+    const size_t rc = ((mm ? BP_NCT_MM : NC) * d0e * 2 + 15) & ~(size_t)15;
     return planes + rc;
 }
+__device__ __forceinline__ int bp_table_of(int c) { return c < C_MOVE_MONO + 2 ? c : (c == C_MOVE_MONO + 3 ? 15 : -1); }
 
 // neighbors_and_mutuals (reference state.py:443-459), direction k: (da, db) of nbr / near / far
 constexpr uint32_t NBR_DA = (uint32_t)pack_nibbles({-1, 0, 1, 0, -1, 1}),  NBR_DB = (uint32_t)pack_nibbles({1, -1, 0, 1, 0, -1});
@@ -129,9 +134,26 @@ __device__ __forceinline__ void trefoil_masks(const u64 *PL, int d0, int a, cons
     dn = both & rb.rotl(Db, rb.amount(-2));
 }
 
-// all 13 class counts of row `a` (full enumeration of one row; used at launch start and by validate)
+// MoveMonovacancy, row `a`, direction k: the neighbour row's Z comes from the pre-rotated plane, its M1 / M2 are rotated
+// on the fly.  own / nbr masks for the site search and the counts (natural | merge << 16, swap) for the tables.
+struct MMRow { u64 m1, m2, dv, zn, m1n, m2n; };
 template <int TD0, int TD1>
-__device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NC]) {
+__device__ __forceinline__ MMRow bp_mm_row(const u64 *PL, int d0, int a, int k, const RowBits<TD1> &rb) {
+    const int an = wrapT<TD0>(a + nib(NBR_DA, k), d0), db = nib(NBR_DB, k);
+    MMRow r;
+    r.m1 = PL[PL_M1 * BPS(d0) + a]; r.m2 = PL[PL_M2 * BPS(d0) + a]; r.dv = PL[PL_D * BPS(d0) + a];
+    r.zn = PL[(PL_Z + (db > 0 ? 1 : db < 0 ? 2 : 0)) * BPS(d0) + an];
+    r.m1n = rb.rotl(PL[PL_M1 * BPS(d0) + an], rb.amount(db));
+    r.m2n = rb.rotl(PL[PL_M2 * BPS(d0) + an], rb.amount(db));
+    return r;
+}
+__device__ __forceinline__ void bp_mm_counts(const MMRow &r, uint32_t &nm, uint32_t &sw) {
+    nm = (uint32_t)__popcll((r.m1 | r.m2) & r.zn) | ((uint32_t)__popcll((r.m1 & r.m2n) | (r.m2 & r.m1n)) << 16);
+    sw = (uint32_t)__popcll(r.dv & (r.m1n | r.m2n));
+}
+// all class counts of row `a` (full enumeration of one row; used at launch start and by validate)
+template <int TD0, int TD1, bool MM = false>
+__device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, const RowBits<TD1> &rb, uint32_t out[NCA]) {
     const uint32_t pz = __popcll(PL[PL_Z * BPS(d0) + a]), pd = __popcll(PL[PL_D * BPS(d0) + a]);
     const uint32_t pm = __popcll(PL[PL_M1 * BPS(d0) + a] | PL[PL_M2 * BPS(d0) + a]);
     const uint32_t pa = __popcll(PL[PL_A4 * BPS(d0) + a] | PL[PL_A7 * BPS(d0) + a]);
@@ -149,6 +171,16 @@ __device__ __forceinline__ void bp_row_counts(const u64 *PL, int d0, int a, cons
     out[C_MOVE_DIV + 2] = k23 & 0xFFFF; out[C_MOVE_DIV + 3] = k23 >> 16;
     u64 up, dn; trefoil_masks<TD0>(PL, d0, a, rb, up, dn);
     out[C_CREATE_TREF] = __popcll(up) + __popcll(dn);
+    if (MM) {
+        uint32_t nm = 0, sw = 0;
+        for (int k = 0; k < 6; k++) {
+            uint32_t x, y; bp_mm_counts(bp_mm_row<TD0>(PL, d0, a, k, rb), x, y);
+            nm += x; sw += y;
+        }
+        out[C_MOVE_MONO] = nm & 0xFFFF; out[C_MOVE_MONO + 1] = nm >> 16;
+        out[C_MOVE_MONO + 2] = 2 * ((k01 & 0xFFFF) + (k01 >> 16) + (k23 & 0xFFFF) + (k23 >> 16));
+        out[C_MOVE_MONO + 3] = sw;
+    }
 }
 
 // position of the (idx)-th set bit (0-based) of a row mask, found by 32 lanes in parallel:
@@ -218,9 +250,12 @@ __device__ __forceinline__ int nth_bit_small(uint32_t m, uint32_t n) {
 
 // LAT = true: the latency build for small batches and single trajectories -- same code, but the register
 // allocator is not held to 64 registers for occupancy that such launches cannot use
-template <int TD0, int TD1, bool LAT = false>
-__global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const ReplicaParams p)
+// MM = true: MoveMonovacancy's four classes as well (17 classes on 32 weight lanes, three more row tables).
+template <int TD0, int TD1, bool LAT = false, bool MM = false>
+__global__ void __launch_bounds__(256, LAT ? 2 : 4) kmc_replica_bp_kernel(const ReplicaParams p)
 {
+    constexpr int NCX = MM ? NCA : NC;                 // classes
+    constexpr int NL = MM ? 32 : 16;                   // weight lanes of the class choice
     const int d0 = TD0 ? TD0 : p.d0;
     const int d1 = TD1 ? TD1 : p.d1;
     const int n = d0 * d1;
@@ -232,7 +267,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     const RowBits<TD1> rb(d1);
 
     extern __shared__ uint4 smem_raw[];
-    u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_bp_warp_bytes(d0));
+    u64 *PL = reinterpret_cast<u64 *>(reinterpret_cast<uint8_t *>(smem_raw) + (size_t)warp * replica_bp_warp_bytes(d0, MM));
     uint16_t *rc16 = reinterpret_cast<uint16_t *>(PL + N_PLANES * BPS(d0));      // [NC][d0e]
     const uint32_t *rc32 = reinterpret_cast<const uint32_t *>(rc16);
 
@@ -268,24 +303,34 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
     __syncwarp();
     // ---- build the row hierarchy (full enumeration, as Rule.initialize_moves does) ---------------
     for (int a = lane; a < d0e; a += 32) {
-        uint32_t cnt[NC];
-        if (a < d0) bp_row_counts<TD0>(PL, d0, a, rb, cnt);
+        uint32_t cnt[NCA];
+        if (a < d0) bp_row_counts<TD0, TD1, MM>(PL, d0, a, rb, cnt);
 #pragma unroll
         for (int c = 0; c < NC; c++) rc16[c * d0e + a] = a < d0 ? (uint16_t)cnt[c] : (uint16_t)0;
+        if (MM) {
+            rc16[13 * d0e + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO] : (uint16_t)0;
+            rc16[14 * d0e + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO + 1] : (uint16_t)0;
+            rc16[15 * d0e + a] = a < d0 ? (uint16_t)cnt[C_MOVE_MONO + 3] : (uint16_t)0;
+        }
     }
     __syncwarp();
 
-    // per-lane class state: lane c < 13 owns class c; lanes 13..15 are permanent zero weights
-    const int myc = lane < NC ? lane : 0;
-    const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-    const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    // per-lane class state: lane c owns class c; the other weight lanes are permanent zero weights
+    const int myc = lane < NCX ? lane : 0;
+    const double rate = (lane < NCX && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+    const int pos = (lane < NCX && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+    const int my_tab = lane < NC ? lane : ((MM && lane < NCX) ? bp_table_of(lane) : -1);
     int tot = 0;
-    if (lane < NC)
-        for (int a = 0; a < d0; a++) tot += rc16[lane * d0e + a];
+    if (my_tab >= 0)
+        for (int a = 0; a < d0; a++) tot += rc16[my_tab * d0e + a];
+    else if (MM && lane == C_MOVE_MONO + 2)
+        for (int a = 0; a < d0; a++)
+            tot += 2 * (rc16[C_MOVE_DIV * d0e + a] + rc16[(C_MOVE_DIV + 1) * d0e + a] + rc16[(C_MOVE_DIV + 2) * d0e + a] +
+                        rc16[(C_MOVE_DIV + 3) * d0e + a]);
     // own-status classes: 2 bits per status = moves of my class a site of that status carries
     const uint32_t my_g1 = (lane < NC && !(lane >= C_MOVE_DIV && lane <= C_CREATE_TREF)) ? g1_const(lane) : 0u;
     unsigned long long hist = 0, hops = 0, n_ties = 0;
-    PickState pstate = pick_state_init(lane);
+    PickState pstate = pick_state_init_n<NL>(lane);
     double tclock = p.clock ? p.clock[rep] : 0.0;          // continues across launches in event order
     uint32_t *const tracer = p.tracer ? p.tracer + (size_t)rep * n : nullptr;
     // refresh roles: lane = 6*j + k -> (row slot j, direction k)
@@ -327,7 +372,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
 
         // ---- 1./2. weights and class choice (sim.py:120-122, kmc.py:21-54) ----------------------
         const double w = __dmul_rn((double)tot, rate);
-        const ClassPick pick = pick_class(w, pos, pstate, u1, lane);
+        const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
         if (pick.zero) {                                        // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && lane == 0) {
@@ -351,7 +396,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         if (p.log_mode == KMC_LOG_FULL) {
             kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                   ((size_t)rep * (size_t)p.nsteps + (size_t)t);
-            if (lane < NCA) rec->counts[lane] = lane < NC ? (uint32_t)tot : 0u;
+            if (lane < NCA) rec->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
         }
 
         // ---- 3. in-class pick: rank in (row, slot, column) order -----------------------------------
@@ -364,9 +409,14 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         }
         // 3a. row: two rows per lane per pass (one 32-bit load of two uint16 counts)
         int row = 0;
+        const bool split = MM && csel == C_MOVE_MONO + 2;
+        const int tab = MM ? (split ? C_MOVE_DIV : bp_table_of(csel)) : csel;
         for (int base = 0; base < d0; base += 64) {
             const int r0 = base + 2 * lane;
-            const uint32_t v01 = (r0 < d0) ? rc32[(csel * d0e + r0) >> 1] : 0u;
+            uint32_t v01 = (r0 < d0) ? rc32[(tab * d0e + r0) >> 1] : 0u;
+            if (split && r0 < d0)          // twice the four MoveDivacancy tables (packed pairs, no carries: <= 3072)
+                v01 = 2u * (v01 + rc32[((C_MOVE_DIV + 1) * d0e + r0) >> 1] + rc32[((C_MOVE_DIV + 2) * d0e + r0) >> 1] +
+                            rc32[((C_MOVE_DIV + 3) * d0e + r0) >> 1]);
             const uint32_t v0 = v01 & 0xFFFFu, v1 = v01 >> 16;
             int L;
             if (warp_rank_search(v0 + v1, r, L, lane)) {
@@ -378,7 +428,26 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         }
         // 3b/3c. slot, then site, within the row (canonical order: row, slot, column)
         int col, slot, s0;
-        if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
+        if (MM && csel >= C_MOVE_MONO) {
+            // lanes 0..11 hold the mask of slot 17 + lane = (direction lane >> 1, layer (lane & 1) + 1)
+            const MMRow mr = bp_mm_row<TD0>(PL, d0, row, lane < 12 ? lane >> 1 : 0, rb);
+            const bool l2 = lane & 1;
+            const int q = csel - C_MOVE_MONO;
+            const u64 src = q < 2 ? (l2 ? mr.m2 : mr.m1) : mr.dv;
+            const u64 dst = (q & 1) ? (l2 ? mr.m1n : mr.m2n) : mr.zn;
+            const u64 mine = lane < 12 ? (src & dst) : 0ull;
+            const uint32_t cntk = __popcll(mine);
+            uint32_t pre = cntk, t1;
+            t1 = __shfl_up_sync(FULL, pre, 1); if (lane >= 1) pre += t1;
+            t1 = __shfl_up_sync(FULL, pre, 2); if (lane >= 2) pre += t1;
+            t1 = __shfl_up_sync(FULL, pre, 4); if (lane >= 4) pre += t1;
+            t1 = __shfl_up_sync(FULL, pre, 8); if (lane >= 8) pre += t1;
+            const int ksel = __ffs(__ballot_sync(FULL, pre > r) & 0xFFFu) - 1;
+            const uint32_t rem = r - __shfl_sync(FULL, pre - cntk, ksel);
+            col = nth_set_bit(__shfl_sync(FULL, mine, ksel), rem, lane, my_low_lo, my_low_hi);
+            slot = MM_SLOT0 + ksel;
+            s0 = q < 2 ? (ksel & 1) + 1 : S_DIVAC;
+        } else if (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) {
             // lanes 0..5 hold their direction's kind mask for this row; a 6-lane prefix picks the direction
             u64 pr, ne, fa;
             dir_masks<TD0>(PL, d0, row, my_dir, pr, ne, fa);
@@ -452,7 +521,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             }
         }
         if (lane == csel) hist++;
-        if (lane == slot - 7) hops++;                          // lanes 0..5: divacancy hops per direction
+        if (lane == slot - 7 && slot < 13) hops++;             // lanes 0..5: divacancy hops per direction
         if (pick.tie && lane == 0) n_ties++;
 
         // ---- 4. the move (uniform): touched nodes, old and new status --------------------------------
@@ -469,10 +538,17 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             mv.b2 = wrapT<TD1>(col + (int)((e.w1 >> 12) & 0xF) - 2, d1);
             mv.ns1 = (int)((e.w1 >> 16) & 0xF); mv.ns2 = (int)((e.w1 >> 20) & 0xF);
             os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
+            if (MM && slot >= MM_SLOT0) {
+                // the target gains the layer: pristine -> L (natural, split), opposite monovacancy -> divacancy
+                const int layer = ((slot - MM_SLOT0) & 1) + 1;
+                const bool onto_mono = (csel - C_MOVE_MONO) & 1;
+                os1 = onto_mono ? 3 - layer : 0;
+                mv.ns1 = onto_mono ? 3 : layer;
+            }
         }
         const int na = mv.na;
         if (tracer && lane == 31)
-            tracer_update(tracer, slot, na, row * d1 + col, mv.ns0, mv.a1 * d1 + mv.b1, mv.ns1, mv.a2 * d1 + mv.b2, mv.ns2);
+            tracer_update(tracer, slot, na, row * d1 + col, mv.ns0, mv.a1 * d1 + mv.b1, mv.ns1, mv.a2 * d1 + mv.b2, mv.ns2, s0);
         // bit planes: lane q < 10 maintains plane q, as 32-bit halves (program order handles nodes
         // sharing a word): clear the site's bit, set it again if the new status belongs to this plane
         if (lane < N_PLANES) {
@@ -518,22 +594,29 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         // ---- 5b. MoveDivacancy: rows within +-1 of the touched rows, re-derived and replaced -------------
         // touched rows relative to `row`: 0 (always), da of the target (moves), +2 (trefoils)
         int lo = -1, hi = 1;
-        if (slot >= 13) hi = 3;
+        if (slot >= 13 && slot < MM_SLOT0) hi = 3;
         else if (slot >= 7) { lo += mv.da1 < 0 ? mv.da1 : 0; hi += mv.da1 > 0 ? mv.da1 : 0; }
         {
             const bool act = my_j <= hi - lo;
             const int ra = wrapT<TD0>(row + lo + my_j, d0);
-            uint32_t pk01 = 0, pk23 = 0;
+            uint32_t pk01 = 0, pk23 = 0, pknm = 0, pksw = 0;
             if (act) {
                 u64 pr, ne, fa;
                 dir_masks<TD0>(PL, d0, ra, my_dir, pr, ne, fa);
                 kind_counts(pr, ne, fa, pk01, pk23);
+                if (MM) bp_mm_counts(bp_mm_row<TD0>(PL, d0, ra, my_k, rb), pknm, pksw);
             }
             pk01 += __shfl_down_sync(FULL, pk01, 3);
             pk23 += __shfl_down_sync(FULL, pk23, 3);
             pk01 += __shfl_down_sync(FULL, pk01, 1) + __shfl_down_sync(FULL, pk01, 2);
             pk23 += __shfl_down_sync(FULL, pk23, 1) + __shfl_down_sync(FULL, pk23, 2);
-            uint32_t d01 = 0, d23 = 0;
+            if (MM) {
+                pknm += __shfl_down_sync(FULL, pknm, 3);
+                pksw += __shfl_down_sync(FULL, pksw, 3);
+                pknm += __shfl_down_sync(FULL, pknm, 1) + __shfl_down_sync(FULL, pknm, 2);
+                pksw += __shfl_down_sync(FULL, pksw, 1) + __shfl_down_sync(FULL, pksw, 2);
+            }
+            uint32_t d01 = 0, d23 = 0, dnm = 0, dsw = 0;
             if (act && my_k == 0) {
                 uint16_t *q = rc16 + C_MOVE_DIV * d0e + ra;
                 const uint32_t o0 = q[0], o1 = q[d0e], o2 = q[2 * d0e], o3 = q[3 * d0e];
@@ -542,14 +625,31 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
                 // signed 16-bit pair deltas as one integer each (hi*65536 + lo)
                 d01 = pk01 - (o0 | (o1 << 16));
                 d23 = pk23 - (o2 | (o3 << 16));
+                if (MM) {                                           // tables 13, 14, 15 = classes 13, 14, 16
+                    uint16_t *m = rc16 + 13 * d0e + ra;
+                    const uint32_t o5 = m[0], o6 = m[d0e], o7 = m[2 * d0e];
+                    m[0] = (uint16_t)pknm; m[d0e] = (uint16_t)(pknm >> 16); m[2 * d0e] = (uint16_t)pksw;
+                    dnm = pknm - (o5 | (o6 << 16));
+                    dsw = pksw - o7;
+                }
             }
             const int s01 = (int)__reduce_add_sync(FULL, d01);
             const int s23 = (int)__reduce_add_sync(FULL, d23);
             const int l01 = (int)(short)(s01 & 0xFFFF), l23 = (int)(short)(s23 & 0xFFFF);
+            const int h01 = (s01 - l01) >> 16, h23 = (s23 - l23) >> 16;
             if (lane == C_MOVE_DIV) tot += l01;
-            if (lane == C_MOVE_DIV + 1) tot += (s01 - l01) >> 16;
+            if (lane == C_MOVE_DIV + 1) tot += h01;
             if (lane == C_MOVE_DIV + 2) tot += l23;
-            if (lane == C_MOVE_DIV + 3) tot += (s23 - l23) >> 16;
+            if (lane == C_MOVE_DIV + 3) tot += h23;
+            if (MM) {
+                const int snm = (int)__reduce_add_sync(FULL, dnm);
+                const int ssw = (int)__reduce_add_sync(FULL, dsw);
+                const int lnm = (int)(short)(snm & 0xFFFF);
+                if (lane == C_MOVE_MONO) tot += lnm;
+                if (lane == C_MOVE_MONO + 1) tot += (snm - lnm) >> 16;
+                if (lane == C_MOVE_MONO + 2) tot += 2 * (l01 + h01 + l23 + h23);      // split = 2 x MoveDivacancy hops
+                if (lane == C_MOVE_MONO + 3) tot += ssw;
+            }
         }
         // ---- 5c. CreateTrefoil: anchor rows row-3 .. row+2 (covers t and t-2 of every touched row t) -----
         {
@@ -576,10 +676,15 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
         // KmcSim.validate (sim.py:159-168): incremental tables vs a fresh enumeration
         bool bad = false;
         for (int a = lane; a < d0; a += 32) {
-            uint32_t cnt[NC];
-            bp_row_counts<TD0>(PL, d0, a, rb, cnt);
+            uint32_t cnt[NCA];
+            bp_row_counts<TD0, TD1, MM>(PL, d0, a, rb, cnt);
 #pragma unroll
             for (int c = 0; c < NC; c++) bad |= (rc16[c * d0e + a] != (uint16_t)cnt[c]);
+            if (MM) {
+                bad |= rc16[13 * d0e + a] != (uint16_t)cnt[C_MOVE_MONO];
+                bad |= rc16[14 * d0e + a] != (uint16_t)cnt[C_MOVE_MONO + 1];
+                bad |= rc16[15 * d0e + a] != (uint16_t)cnt[C_MOVE_MONO + 3];
+            }
             // plane consistency: at most one type bit per site; rotated copies agree with their base
             const u64 z = PL[PL_Z * BPS(d0) + a], dv = PL[PL_D * BPS(d0) + a];
             const u64 types[N_TYPES] = {z, dv, PL[PL_M1 * BPS(d0) + a], PL[PL_M2 * BPS(d0) + a], PL[PL_A4 * BPS(d0) + a], PL[PL_A7 * BPS(d0) + a]};
@@ -590,9 +695,15 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             bad |= PL[PL_ZP * BPS(d0) + a] != rb.rotl(z, rb.amount(1)) || PL[PL_ZM * BPS(d0) + a] != rb.rotl(z, rb.amount(-1));
             bad |= PL[PL_DP * BPS(d0) + a] != rb.rotl(dv, rb.amount(1)) || PL[PL_DM * BPS(d0) + a] != rb.rotl(dv, rb.amount(-1));
         }
-        if (lane < NC) {
+        if (my_tab >= 0) {
             int fresh = 0;
-            for (int a = 0; a < d0; a++) fresh += rc16[lane * d0e + a];
+            for (int a = 0; a < d0; a++) fresh += rc16[my_tab * d0e + a];
+            bad |= (fresh != tot);
+        } else if (MM && lane == C_MOVE_MONO + 2) {
+            int fresh = 0;
+            for (int a = 0; a < d0; a++)
+                fresh += 2 * (rc16[C_MOVE_DIV * d0e + a] + rc16[(C_MOVE_DIV + 1) * d0e + a] + rc16[(C_MOVE_DIV + 2) * d0e + a] +
+                              rc16[(C_MOVE_DIV + 3) * d0e + a]);
             bad |= (fresh != tot);
         }
         if (__any_sync(FULL, bad)) flag |= FLAG_VALIDATE;
@@ -631,7 +742,7 @@ __global__ void __launch_bounds__(256, LAT ? 1 : 4) kmc_replica_bp_kernel(const 
             gst[a2 * d1 + wrap1(b - 2, d1)] = (uint8_t)(S_TREF + 5);
         }
     }
-    if (lane < NC) p.hist[(size_t)rep * NCA + lane] += hist;
+    if (lane < NCX) p.hist[(size_t)rep * NCA + lane] += hist;
     if (lane < 6) p.hops[(size_t)rep * 6 + lane] += hops;
     if (lane == 0) {
         p.steps_done[rep] = step_base + (unsigned long long)done;

@@ -902,7 +902,7 @@ MM_FIXTURES = ["wse2_full_16x16", "wse2_full_64x64", "wse2_full_hot_24x24", "all
                "allrules_mm_64x64", "allrules_mm_12x130"]
 
 
-@pytest.mark.parametrize("variant", [1, 3, 4, 5, "noinc", "draws"])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, "noinc", "draws"])
 @pytest.mark.parametrize("name", MM_FIXTURES)
 def test_move_monovacancy_fixtures_on_the_general_kernels(name, variant):
     """Fixtures made by the REFERENCE engine running oracle/move_monovacancy.py's rule class (all of
@@ -914,6 +914,8 @@ def test_move_monovacancy_fixtures_on_the_general_kernels(name, variant):
         pytest.skip("half-warp kernel: rows of <= 64 sites and at most 16 enabled classes")
     if variant == 5 and m["dim"][1] <= 64:
         pytest.skip("wide bit-plane kernel: rows wider than 64 sites")
+    if variant == 2 and m["dim"][1] > 64:
+        pytest.skip("warp-per-replica bit-plane kernel: rows of <= 64 sites")
     eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
     eng.upload_state(g["status0"])
     n = m["nsteps"] if variant != "noinc" else min(m["nsteps"], 400)
@@ -946,7 +948,7 @@ MM16_ORDER = [c for c in MM_ORDER if c != 1]
 MM16B_ORDER = [16, 15, 14, 13] + [c for c in range(13) if c != 9]          # another order, another lane for class 16
 
 
-@pytest.mark.parametrize("variant", [0, 1, 3, 4, 5])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("dim,rates,order", [((64, 64), MM_RATES, MM_ORDER), ((33, 47), MM_RATES, MM_ORDER),
                                              ((5, 5), MM_RATES, MM_ORDER), ((7, 130), MM_RATES, MM_ORDER),
                                              ((24, 200), MM_RATES, MM_ORDER), ((130, 128), wse2_full_rates(5000.0), WSE2_FULL_ORDER),
@@ -963,6 +965,8 @@ def test_move_monovacancy_replicas_match_oracle(dim, rates, order, variant):
         pytest.skip("half-warp kernel: rows of <= 64 sites and at most 16 enabled classes")
     if variant == 5 and dim[1] <= 64:
         pytest.skip("wide bit-plane kernel: rows wider than 64 sites")
+    if variant == 2 and dim[1] > 64:
+        pytest.skip("warp-per-replica bit-plane kernel: rows of <= 64 sites")
     st0 = np.stack([exact_state(dim, 0.12 + 0.03 * r, 0.10, 300 + r) for r in range(nrep)])
     eng = Engine(dim, rates, order, n_replicas=nrep)
     eng.set_replica_kernel(variant)
@@ -994,10 +998,11 @@ def test_move_monovacancy_replicas_match_oracle(dim, rates, order, variant):
 
 def test_kernels_that_cannot_take_move_monovacancy_decline():
     eng = Engine((64, 64), MM_RATES, MM_ORDER)             # all 17 classes: no free lane in the half-warp kernel
-    for variant in (2, 4):
-        eng.set_replica_kernel(variant)
-        with pytest.raises(RuntimeError, match="MoveMonovacancy is enabled"):
-            eng.run(10, 1)
+    eng.set_replica_kernel(4)
+    with pytest.raises(RuntimeError, match="MoveMonovacancy is enabled"):
+        eng.run(10, 1)
+    eng.set_replica_kernel(2)                              # (the warp-per-replica kernel has 32 weight lanes)
+    eng.run(10, 1, validate=True)
     eng.close()
     eng = Engine((8, 128), MM_RATES, MM16_ORDER)           # rows wider than 64 sites: not the half-warp kernel
     eng.set_replica_kernel(4)
