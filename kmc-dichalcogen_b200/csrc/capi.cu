@@ -931,8 +931,8 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         p.tracer = h->tracer_on ? h->d_tracer : nullptr;
     // Large lattices: the event runs on the bit-sliced lattice (noinc_planes_kernel.cuh) -- 64 sites per operation in
     // the enumeration instead of 8.  (KMC_NOINC_PLANES=0/1 forces the choice.)
-    bool on_planes = !h->mm && h->n >= 65536 && wide_anchor_words(h->d1) <= 256;
-    if (const char *e = getenv("KMC_NOINC_PLANES")) on_planes = !h->mm && atoi(e) != 0 && wide_anchor_words(h->d1) <= 256;
+    bool on_planes = h->n >= 65536 && wide_anchor_words(h->d1) <= 256;
+    if (const char *e = getenv("KMC_NOINC_PLANES")) on_planes = atoi(e) != 0 && wide_anchor_words(h->d1) <= 256;
     if (on_planes) {
         const int We = wide_row_words(h->d1);
         const int chunks = planes_chunks(h->d1), rpb = 8 / chunks, nblk = (h->d0 + rpb - 1) / rpb;
@@ -954,10 +954,16 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         q.nblk = nblk; q.rpb = rpb;
         for (long long t = 0; t < nsteps; t++) {
             // sim.py:114-115: initialize() -- a full re-enumeration -- before every event
-            kmc_planes_rowcount_kernel<<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
-                                                                                     h->R, h->d0, h->d1, chunks, nblk);
             q.base.t = t;
-            kmc_noinc_planes_select_kernel<<<h->R, 256, 0, h->stream>>>(q);
+            if (h->mm) {
+                kmc_planes_rowcount_kernel<true><<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
+                                                                                               h->R, h->d0, h->d1, chunks, nblk);
+                kmc_noinc_planes_select_kernel<true><<<h->R, 256, 0, h->stream>>>(q);
+            } else {
+                kmc_planes_rowcount_kernel<false><<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
+                                                                                                h->R, h->d0, h->d1, chunks, nblk);
+                kmc_noinc_planes_select_kernel<false><<<h->R, 256, 0, h->stream>>>(q);
+            }
             CU(cudaGetLastError());
             h->launches += 2;
         }

@@ -16,7 +16,7 @@
 // Results are bit-identical to the byte-lattice path (tests: both against the oracle).
 #pragma once
 #include "noinc_kernel.cuh"
-#include "replica_wide_kernel.cuh"
+#include "replica_wide2_kernel.cuh"
 
 namespace kmc {
 
@@ -32,10 +32,13 @@ __host__ __device__ inline int planes_chunks(int d1) {       // warps per row: p
 // Full enumeration from the planes.  CTA = 8 warps = 8 / chunks rows; warp = 32 consecutive cells of one row.
 //   rowc [R][16][d0]   class-major row counts (classes 0..12)
 //   blk  [R][nblk][16] per-CTA sums of the same, nblk = ceil(d0 / rows_per_cta)
+// MM: slots 13, 14, 15 of a record hold MoveMonovacancy natural, merge-divacancy, swap-divacancy (class 16); the
+// split-divacancy count (class 15) is twice the sum of slots 2..5 and is not stored.
+template <bool MM = false>
 __global__ void __launch_bounds__(256) kmc_planes_rowcount_kernel(const u64 *planes, uint32_t *rowc, uint32_t *blk,
                                                                  int R, int d0, int d1, int chunks, int nblk)
 {
-    __shared__ uint32_t part[8][5];
+    __shared__ uint32_t part[8][7];
     __shared__ uint32_t rowval[8][PRC_STRIDE];
     const int Wa = wide_anchor_words(d1), We = Wa + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -45,8 +48,10 @@ __global__ void __launch_bounds__(256) kmc_planes_rowcount_kernel(const u64 *pla
     const int a = b * rpb + rl, chunk = warp % chunks;
     const int w = chunk * 32 + lane;
     WGeom G{planes + (size_t)rep * N_TYPES * d0 * We, d0, d1, Wa, We};
-    uint32_t zd = 0, ma = 0, k01 = 0, k23 = 0, tre = 0;
+    uint32_t zd = 0, ma = 0, k01 = 0, k23 = 0, tre = 0, nm = 0, sw = 0;
     if (a < d0 && w < Wa) {
+        if (MM)
+            for (int k = 0; k < 6; k++) { uint32_t x, y; mm_cell_counts(G, a, w, k, x, y); nm += x; sw += y; }
         const u64 v = G.valid(w);
         zd = (uint32_t)__popcll(window_at(G.rowp(T_Z, a), w, 0) & v) |
              ((uint32_t)__popcll(window_at(G.rowp(T_D, a), w, 0) & v) << 16);
@@ -59,15 +64,20 @@ __global__ void __launch_bounds__(256) kmc_planes_rowcount_kernel(const u64 *pla
     // 16-bit fields: a warp covers 2048 sites with <= 6 moves per site and class (<= 12288 per field)
     zd = __reduce_add_sync(FULL, zd); ma = __reduce_add_sync(FULL, ma);
     k01 = __reduce_add_sync(FULL, k01); k23 = __reduce_add_sync(FULL, k23); tre = __reduce_add_sync(FULL, tre);
-    if (lane == 0) { part[warp][0] = zd; part[warp][1] = ma; part[warp][2] = k01; part[warp][3] = k23; part[warp][4] = tre; }
+    if (MM) { nm = __reduce_add_sync(FULL, nm); sw = __reduce_add_sync(FULL, sw); }
+    if (lane == 0) {
+        part[warp][0] = zd; part[warp][1] = ma; part[warp][2] = k01; part[warp][3] = k23; part[warp][4] = tre;
+        part[warp][5] = nm; part[warp][6] = sw;
+    }
     __syncthreads();
     // the leader warp of each row: lane c < 13 combines the row's chunks (fields unpacked first) and writes class c
     if (chunk == 0 && lane < PRC_STRIDE) {
-        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, tr = 0;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, tr = 0, nat = 0, mer = 0, swp = 0;
         for (int q = 0; q < chunks; q++) {
 #pragma unroll
             for (int f = 0; f < 4; f++) { const uint32_t x = part[warp + q][f]; lo[f] += x & 0xFFFFu; hi[f] += x >> 16; }
             tr += part[warp + q][4];
+            nat += part[warp + q][5] & 0xFFFFu; mer += part[warp + q][5] >> 16; swp += part[warp + q][6];
         }
         const uint32_t pz = lo[0], pd = hi[0], pm = lo[1], pa = hi[1];
         uint32_t val = 0;
@@ -83,17 +93,20 @@ __global__ void __launch_bounds__(256) kmc_planes_rowcount_kernel(const u64 *pla
             case C_CMONO_FROM_DOUBLE: val = 2 * pz; break;
             case C_FMONO_FROM_EMPTY: val = 2 * pd; break;
             case C_CMONO_MAKE_EMPTY: case C_FMONO_MAKE_DOUBLE: case C_FLIP: val = pm; break;   // one per monovacancy
+            case 13: val = MM ? nat : 0; break;
+            case 14: val = MM ? mer : 0; break;
+            case 15: val = MM ? swp : 0; break;
             default: val = 0; break;
         }
         if (a >= d0) val = 0;
-        if (a < d0 && lane < NC) rowc[((size_t)rep * PRC_STRIDE + lane) * d0 + a] = val;
+        if (a < d0 && lane < (MM ? PRC_STRIDE : NC)) rowc[((size_t)rep * PRC_STRIDE + lane) * d0 + a] = val;
         rowval[rl][lane] = val;
     }
     __syncthreads();
     if (warp == 0 && lane < PRC_STRIDE) {
         uint32_t s = 0;
         for (int q = 0; q < rpb; q++) s += rowval[q][lane];
-        blk[((size_t)rep * nblk + b) * PRC_STRIDE + lane] = s;
+        blk[((size_t)rep * nblk + b) * PRC_STRIDE + lane] = s;          // (lanes 13..15: MoveMonovacancy tables, 0 without MM)
     }
 }
 
@@ -107,8 +120,11 @@ struct NoincPlanesParams {
 };
 
 // One CTA (256 threads) per replica.
+template <bool MM = false>
 __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const NoincPlanesParams q)
 {
+    constexpr int NCX = MM ? NCA : NC;
+    constexpr int NL = MM ? 32 : 16;
     const NoincParams &p = q.base;
     __shared__ unsigned long long wsum[8];
     __shared__ uint32_t s_tot[8][PRC_STRIDE];               // per-warp class sums of the CTA records
@@ -116,7 +132,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     __shared__ unsigned long long s_rank;
     __shared__ double s_total;
     __shared__ int s_csel, s_zero, s_tie, s_row, s_word, s_bit;
-    __shared__ uint32_t s_rin, s_slotcnt[6];
+    __shared__ uint32_t s_rin, s_slotcnt[12];
     const int rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
     const int Wa = wide_anchor_words(d1), We = Wa + 1;
@@ -156,18 +172,18 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
             mine_c[0] += x0.x; mine_c[1] += x0.y; mine_c[2] += x0.z; mine_c[3] += x0.w;
             mine_c[4] += x1.x; mine_c[5] += x1.y; mine_c[6] += x1.z; mine_c[7] += x1.w;
             mine_c[8] += x2.x; mine_c[9] += x2.y; mine_c[10] += x2.z; mine_c[11] += x2.w;
-            mine_c[12] += x3.x;
+            mine_c[12] += x3.x; mine_c[13] += x3.y; mine_c[14] += x3.z; mine_c[15] += x3.w;
         }
     }
     (void)KB_MAX;
     {
         uint32_t mysum = 0;                                 // lane c < 13 of each warp collects the warp's sum of class c
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
+        for (int c = 0; c < (MM ? PRC_STRIDE : NC); c++) {
             const uint32_t sc = __reduce_add_sync(FULL, mine_c[c]);
             if (lane == c) mysum = sc;
         }
-        if (lane < PRC_STRIDE) s_tot[tid >> 5][lane] = lane < NC ? mysum : 0u;
+        if (lane < PRC_STRIDE) s_tot[tid >> 5][lane] = lane < (MM ? PRC_STRIDE : NC) ? mysum : 0u;
     }
     // the draws do not depend on the lattice: warp 1 makes them while the sums settle
     if (tid == 32) {
@@ -180,21 +196,29 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
         }
         s_u1 = u1; s_u2 = u2;
     }
-    if (tid < 6) s_slotcnt[tid] = 0;
+    if (tid < 12) s_slotcnt[tid] = 0;
     __syncthreads();
     if (tid < 32) {
+        // class totals: lane c reads the table of class c (MM: 13, 14 -> 13, 14; 16 -> 15; 15 = 2 x classes 2..5)
         long long tot = 0;
-        if (lane < NC) for (int i = 0; i < 8; i++) tot += (long long)s_tot[i][lane];
-        if (lane < NCA) q.counts[(size_t)rep * NCA + lane] = lane < NC ? (unsigned long long)tot : 0ull;
-        const int myc = lane < NC ? lane : 0;
-        const double rate = (lane < NC && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
-        const int pos = (lane < NC && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
+        if (lane < NCX) {
+            if (MM && lane == C_MOVE_MONO + 2) {
+                for (int c = C_MOVE_DIV; c < C_MOVE_DIV + 4; c++) for (int i = 0; i < 8; i++) tot += 2 * (long long)s_tot[i][c];
+            } else {
+                const int tb = (MM && lane == C_MOVE_MONO + 3) ? 15 : lane;
+                for (int i = 0; i < 8; i++) tot += (long long)s_tot[i][tb];
+            }
+        }
+        if (lane < NCA) q.counts[(size_t)rep * NCA + lane] = lane < NCX ? (unsigned long long)tot : 0ull;
+        const int myc = lane < NCX ? lane : 0;
+        const double rate = (lane < NCX && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
+        const int pos = (lane < NCX && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
         const double u1 = s_u1, u2 = s_u2;
         const double w = __dmul_rn((double)tot, rate);
-        PickState pstate = pick_state_init_n<16>(lane);
-        const ClassPick pick = pick_class<16>(w, pos, pstate, u1, lane);
+        PickState pstate = pick_state_init_n<NL>(lane);
+        const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
         if (p.log_mode == KMC_LOG_FULL && lane < NCA)
-            (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = lane < NC ? (uint32_t)tot : 0u;
+            (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
         const long long cnt = __shfl_sync(FULL, tot, pick.zero ? 0 : pick.csel);
         long long rr = (long long)__dmul_rn(u2, (double)cnt);
         if (rr > cnt - 1) rr = cnt - 1;
@@ -225,9 +249,21 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     // ---- row: CTA record, then the rows of that CTA --------------------------------------------------------
     {
         const int b0 = tid * kb, b1 = min(b0 + kb, q.nblk);
+        // table of the chosen class (MM: class 16 -> 15); split-divacancy is twice tables 2..5
+        const bool split = MM && csel == C_MOVE_MONO + 2;
+        const int tb = (MM && csel == C_MOVE_MONO + 3) ? 15 : csel;
         uint32_t mysel = mine_c[0];                        // this thread's records' sum of the chosen class (registers)
 #pragma unroll
-        for (int c = 1; c < NC; c++) mysel = csel == c ? mine_c[c] : mysel;
+        for (int c = 1; c < (MM ? PRC_STRIDE : NC); c++) mysel = tb == c ? mine_c[c] : mysel;
+        if (split) mysel = 2u * (mine_c[2] + mine_c[3] + mine_c[4] + mine_c[5]);
+        auto blkval = [&](int b) -> unsigned long long {
+            const uint32_t *rec = blk + (size_t)b * PRC_STRIDE;
+            return split ? 2ull * ((unsigned long long)rec[2] + rec[3] + rec[4] + rec[5]) : rec[tb];
+        };
+        auto rowval_of = [&](int a) -> uint32_t {
+            return split ? 2u * (rowc[(size_t)2 * d0 + a] + rowc[(size_t)3 * d0 + a] + rowc[(size_t)4 * d0 + a] + rowc[(size_t)5 * d0 + a])
+                         : rowc[(size_t)tb * d0 + a];
+        };
         unsigned long long local = mysel, total;
         const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
         const unsigned long long rank = s_rank;
@@ -236,14 +272,14 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
             unsigned long long r = rank - excl;
             int b = b0;
             for (; b < b1 - 1; b++) {
-                const unsigned long long v = blk[(size_t)b * PRC_STRIDE + csel];
+                const unsigned long long v = blkval(b);
                 if (r < v) break;
                 r -= v;
             }
             const int a0 = b * q.rpb;
             uint32_t rv[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) rv[i] = (i < q.rpb && a0 + i < d0) ? rowc[(size_t)csel * d0 + a0 + i] : 0u;
+            for (int i = 0; i < 8; i++) rv[i] = (i < q.rpb && a0 + i < d0) ? rowval_of(a0 + i) : 0u;
             int a = a0;
 #pragma unroll
             for (int i = 0; i < 7; i++)
@@ -255,10 +291,17 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     const int row = s_row;
 
     // ---- slot and site inside the row: one thread per 64-site cell (rows of <= 16384 sites) --------------------
-    u64 m[6] = {0, 0, 0, 0, 0, 0};                          // this thread's cell: sites of the class per slot
-    const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 : 0);
+    constexpr int NSL = MM ? 12 : 6;
+    u64 m[NSL];                                             // this thread's cell: sites of the class per slot
+#pragma unroll
+    for (int i = 0; i < NSL; i++) m[i] = 0;
+    const int group = (csel >= C_MOVE_DIV && csel < C_MOVE_DIV + 4) ? 1 : (csel == C_CREATE_TREF ? 2 :
+                      ((MM && csel >= C_MOVE_MONO) ? 3 : 0));
     if (tid < Wa) {
-        if (group == 1) {
+        if (MM && group == 3) {
+#pragma unroll
+            for (int i = 0; i < NSL; i++) m[i] = mm_cell_mask(G, row, tid, i >> 1, (i & 1) + 1, csel - C_MOVE_MONO);
+        } else if (group == 1) {
             Nbhd nb;
             load_nbhd<false>(G, row, tid, nb);
 #pragma unroll
@@ -292,28 +335,24 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
         }
     }
     {
-        uint32_t c01 = (uint32_t)__popcll(m[0]) | ((uint32_t)__popcll(m[1]) << 16);
-        uint32_t c23 = (uint32_t)__popcll(m[2]) | ((uint32_t)__popcll(m[3]) << 16);
-        uint32_t c45 = (uint32_t)__popcll(m[4]) | ((uint32_t)__popcll(m[5]) << 16);
-        c01 = __reduce_add_sync(FULL, c01); c23 = __reduce_add_sync(FULL, c23); c45 = __reduce_add_sync(FULL, c45);
-        if (lane == 0) {
-            if (c01 & 0xFFFFu) atomicAdd(&s_slotcnt[0], c01 & 0xFFFFu);
-            if (c01 >> 16) atomicAdd(&s_slotcnt[1], c01 >> 16);
-            if (c23 & 0xFFFFu) atomicAdd(&s_slotcnt[2], c23 & 0xFFFFu);
-            if (c23 >> 16) atomicAdd(&s_slotcnt[3], c23 >> 16);
-            if (c45 & 0xFFFFu) atomicAdd(&s_slotcnt[4], c45 & 0xFFFFu);
-            if (c45 >> 16) atomicAdd(&s_slotcnt[5], c45 >> 16);
+#pragma unroll
+        for (int i = 0; i < NSL; i += 2) {
+            const uint32_t c = __reduce_add_sync(FULL, (uint32_t)__popcll(m[i]) | ((uint32_t)__popcll(m[i + 1]) << 16));
+            if (lane == 0) {
+                if (c & 0xFFFFu) atomicAdd(&s_slotcnt[i], c & 0xFFFFu);
+                if (c >> 16) atomicAdd(&s_slotcnt[i + 1], c >> 16);
+            }
         }
     }
     __syncthreads();
     uint32_t r = s_rin;
     int j = 0;
 #pragma unroll
-    for (int i = 0; i < 5; i++)
+    for (int i = 0; i < NSL - 1; i++)
         if (j == i && r >= s_slotcnt[i]) { r -= s_slotcnt[i]; j = i + 1; }
     u64 mj = m[0];
 #pragma unroll
-    for (int i = 1; i < 6; i++) mj = j == i ? m[i] : mj;
+    for (int i = 1; i < NSL; i++) mj = j == i ? m[i] : mj;
     {
         const unsigned long long local = (unsigned long long)__popcll(mj);
         unsigned long long total;
@@ -326,7 +365,8 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     const int col = 64 * s_word + s_bit;
     const int slot = class_slot_base(csel) + j;
     int s0;
-    if (group) s0 = S_DIVAC;
+    if (MM && group == 3) s0 = csel < C_MOVE_MONO + 2 ? (j & 1) + 1 : S_DIVAC;
+    else if (group) s0 = S_DIVAC;
     else switch (csel) {
         case C_CREATE_DIV: case C_CMONO_FROM_DOUBLE: s0 = 0; break;
         case C_FILL_DIV: case C_FMONO_FROM_EMPTY: s0 = 3; break;
@@ -337,11 +377,17 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     }
     const int site = row * d1 + col;
     // ---- the move: thread (node i, plane pl) = tid < 18 rewrites its plane bit (+ halo copy) ---------------------
-    const MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
+    MoveNodes mv = move_nodes(row, col, slot, s0, d0, d1);
     int os1, os2;
     {
         const MoveEntry e = MOVE_TABLE[slot];
         os1 = (int)((e.w1 >> 24) & 0xF); os2 = (int)(e.w1 >> 28);
+        if (MM && slot >= MM_SLOT0) {
+            const int layer = ((slot - MM_SLOT0) & 1) + 1;
+            const bool onto_mono = (csel - C_MOVE_MONO) & 1;
+            os1 = onto_mono ? 3 - layer : 0;
+            mv.ns1 = onto_mono ? 3 : layer;
+        }
     }
     __syncthreads();                                       // every read of the planes above is done
     if (tid < 18) {
