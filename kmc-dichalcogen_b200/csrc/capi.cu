@@ -376,7 +376,9 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         const long long chunks = (long long)R * (h->n >> 4);
         kmc_sweep_mm16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, h->stream>>>(m);
         CU(cudaGetLastError());
-        kmc_reduce_rowmm_kernel<<<h->R, 256, 0, h->stream>>>(h->d_rowmm, h->d0, h->d_counts);
+        // (the four MoveMonovacancy totals of every replica start from zero: strided 32-byte memset)
+        CU(cudaMemset2DAsync(h->d_counts + C_MOVE_MONO, NCA * sizeof(unsigned long long), 0, 4 * sizeof(unsigned long long), R, h->stream));
+        kmc_reduce_rowmm_kernel<<<dim3((unsigned)((h->d0 + 255) / 256), (unsigned)h->R), 256, 0, h->stream>>>(h->d_rowmm, h->d0, h->d_counts);
         CU(cudaGetLastError());
         h->launches += 2;
     }

@@ -1031,19 +1031,23 @@ __global__ void __launch_bounds__(256) kmc_sweep_mm16_kernel(const SweepMMParams
         if (n_swp) atomicAdd(R4 + 3, n_swp);
     }
 }
-// class totals 13..16 per replica from rowmm
-__global__ void kmc_reduce_rowmm_kernel(const uint32_t *rowmm, int d0, unsigned long long *counts)
+// class totals 13..16 per replica from rowmm: one thread per row (one 128-bit load), warp sums, one atomic per warp and
+// class into counts (the four entries must be zero on entry).  grid = (ceil(d0 / 256), R)
+__global__ void __launch_bounds__(256) kmc_reduce_rowmm_kernel(const uint32_t *rowmm, int d0, unsigned long long *counts)
 {
-    const int rep = blockIdx.x;
-    __shared__ unsigned long long acc[4];
-    if (threadIdx.x < 4) acc[threadIdx.x] = 0;
-    __syncthreads();
-    const int c = threadIdx.x & 3;
-    unsigned long long s = 0;
-    for (int a = threadIdx.x >> 2; a < d0; a += blockDim.x >> 2) s += rowmm[((size_t)rep * d0 + a) * 4 + c];
-    atomicAdd(&acc[c], s);
-    __syncthreads();
-    if (threadIdx.x < 4) counts[(size_t)rep * NCA + C_MOVE_MONO + threadIdx.x] = acc[threadIdx.x];
+    const int rep = blockIdx.y;
+    const int a = blockIdx.x * 256 + threadIdx.x;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (a < d0) v = __ldg(reinterpret_cast<const uint4 *>(rowmm + ((size_t)rep * d0 + a) * 4));
+    const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, v.x), s1 = __reduce_add_sync(0xFFFFFFFFu, v.y);
+    const uint32_t s2 = __reduce_add_sync(0xFFFFFFFFu, v.z), s3 = __reduce_add_sync(0xFFFFFFFFu, v.w);
+    if ((threadIdx.x & 31) == 0) {
+        unsigned long long *c = counts + (size_t)rep * NCA + C_MOVE_MONO;
+        if (s0) atomicAdd(c + 0, (unsigned long long)s0);
+        if (s1) atomicAdd(c + 1, (unsigned long long)s1);
+        if (s2) atomicAdd(c + 2, (unsigned long long)s2);
+        if (s3) atomicAdd(c + 3, (unsigned long long)s3);
+    }
 }
 
 __global__ void kmc_reduce_counts_mm_kernel(const uint32_t *rowcnt, int d0, int n_replicas, unsigned long long *counts)
