@@ -14,7 +14,7 @@
 //   warp 0 also     class choice + row search (it owns the 13 class totals, lane c = class c)
 // Six block barriers per event order the phases (choose | site search | pick | before-counts | rewrite |
 // after-counts).  Same planes, same row table, same results as the one-warp kernel; selected automatically for
-// batches of at most 2 replicas per SM.
+// batches of at most one replica per SM (and for every MoveMonovacancy rule set).
 #pragma once
 #include "replica_wide_kernel.cuh"
 
