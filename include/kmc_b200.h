@@ -211,7 +211,8 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
  * row-count hierarchy in shared memory (chosen automatically when the lattice does not fit and variant 5
  * does not apply), 5 = bit planes of rows wider than 64 sites kept in HBM/L2 with the row table in shared
  * memory (64 < dim1 <= 2048; chosen automatically when the byte lattices of the batch cannot all be resident
- * in shared memory, e.g. 1024x1024 or a thousand 256x256 replicas).  All produce identical results. */
+ * in shared memory, e.g. 1024x1024 or a thousand 256x256 replicas; a whole CTA per replica when the batch has no
+ * more replicas than the device has SMs, else one warp per replica).  All produce identical results. */
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
 /* aligned-shape sweep kernel: 0 = automatic (rolling window over rows when a row fills a CTA, i.e. 4096
@@ -240,8 +241,9 @@ int kmc_set_sweep_double_buffer(kmc_engine *h, int on);
  *   14 MoveMonovacancy:merge-divacancy   config/WSe2.yaml:8-13)              the vacancy in layer L of `node` hops to nbr_k, whose
  *   15 MoveMonovacancy:split-divacancy                                       layer set must be defined and lack L;
  *   16 MoveMonovacancy:swap-divacancy                                        kind = 2*(node is a divacancy) + (nbr_k not pristine)
- * While any of classes 13..16 is enabled the engine runs its general kernels (byte lattice; one thread per site in
- * the sweep); the bit-sliced replica kernels and the aligned sweep kernels serve the reference's own 13 classes.
+ * While any of classes 13..16 is enabled the engine runs the MoveMonovacancy-aware build of the same kernels (17 class
+ * weights, 29 slot planes); rule sets without the rule run the 13-class builds.  The one-warp-per-replica form of
+ * variant 5 has no such build (the CTA-per-replica form serves those batches).
  * In-class order (the rank the in-class draw indexes): row ascending, then slot ascending, then column.
  */
 

@@ -9,6 +9,7 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <chrono>
 
 #include "../../include/kmc_b200.h"
 #include "kmc_common.cuh"
@@ -71,6 +72,7 @@ struct kmc_engine {
     bool planes_valid = false, bytes_stale = false;
     bool whier_valid = false;                // d_whier matches the planes (the no-incremental plane path does not maintain it)
     uint32_t *d_prowc = nullptr, *d_pblk = nullptr;   // no-incremental path on planes: class-major row counts, CTA sums
+    unsigned int *d_pticket = nullptr;                // and the per-replica ticket that elects the selecting CTA
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
     int variant = 0;                         // 0 auto, 1 byte lattice, 2 bit planes, 3 byte lattice kept in HBM
@@ -170,7 +172,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_rowmm); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock); cudaFree(h->d_tracer);
-    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk);
+    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk); cudaFree(h->d_pticket);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags); cudaFree(h->d_anyflag);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -937,11 +939,13 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
     if (const char *e = getenv("KMC_NOINC_PLANES")) on_planes = atoi(e) != 0 && wide_anchor_words(h->d1) <= 256;
     if (on_planes) {
         const int We = wide_row_words(h->d1);
-        const int chunks = planes_chunks(h->d1), rpb = 8 / chunks, nblk = (h->d0 + rpb - 1) / rpb;
+        const int chunks = planes_chunks(h->d1), rpb = planes_rows_per_cta(h->d1), nblk = (h->d0 + rpb - 1) / rpb;
         if (!h->d_planes) CU(cudaMalloc(&h->d_planes, (size_t)h->R * N_TYPES * h->d0 * We * sizeof(unsigned long long)));
         if (!h->d_prowc) {
             CU(cudaMalloc(&h->d_prowc, (size_t)h->R * PRC_STRIDE * h->d0 * sizeof(uint32_t)));
             CU(cudaMalloc(&h->d_pblk, (size_t)h->R * nblk * PRC_STRIDE * sizeof(uint32_t)));
+            CU(cudaMalloc(&h->d_pticket, (size_t)h->R * sizeof(unsigned int)));
+            CU(cudaMemsetAsync(h->d_pticket, 0, (size_t)h->R * sizeof(unsigned int), h->stream));
         }
         if (!h->planes_valid) {
             rc = ensure_bytes(h); if (rc) return rc;
@@ -953,22 +957,26 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         }
         NoincPlanesParams q;
         q.base = p; q.planes = h->d_planes; q.rowc = h->d_prowc; q.blk = h->d_pblk; q.counts = h->d_counts;
-        q.nblk = nblk; q.rpb = rpb;
+        q.ticket = h->d_pticket; q.nblk = nblk; q.rpb = rpb; q.chunks = chunks;
+        q.chunk_shift = 0; while ((1 << q.chunk_shift) < chunks) q.chunk_shift++;
+        q.base.stage = getenv("KMC_NOINC_DEBUG_SKIP") ? atoi(getenv("KMC_NOINC_DEBUG_SKIP")) : 0;
+        const bool pdl = !getenv("KMC_NOINC_NO_PDL");
+        const auto dbg_t0 = std::chrono::steady_clock::now();
         for (long long t = 0; t < nsteps; t++) {
-            // sim.py:114-115: initialize() -- a full re-enumeration -- before every event
+            // sim.py:114-115: initialize() -- a full re-enumeration -- before every event; one launch does both
             q.base.t = t;
-            if (h->mm) {
-                kmc_planes_rowcount_kernel<true><<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
-                                                                                               h->R, h->d0, h->d1, chunks, nblk);
-                kmc_noinc_planes_select_kernel<true><<<h->R, 256, 0, h->stream>>>(q);
-            } else {
-                kmc_planes_rowcount_kernel<false><<<(unsigned)(h->R * nblk), 256, 0, h->stream>>>(h->d_planes, h->d_prowc, h->d_pblk,
-                                                                                                h->R, h->d0, h->d1, chunks, nblk);
-                kmc_noinc_planes_select_kernel<false><<<h->R, 256, 0, h->stream>>>(q);
-            }
-            CU(cudaGetLastError());
-            h->launches += 2;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(h->R * nblk)); cfg.blockDim = dim3(256); cfg.stream = h->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+            if (h->mm) CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<true>, q));
+            else CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<false>, q));
+            h->launches += 1;
         }
+        if (getenv("KMC_NOINC_DEBUG_TIME"))
+            fprintf(stderr, "noinc enqueue: %.2f us per event\n", 1e6 * std::chrono::duration<double>(std::chrono::steady_clock::now() - dbg_t0).count() / (double)(nsteps ? nsteps : 1));
         h->swept = false; h->hier_valid = false; h->whier_valid = false;
         h->bytes_stale = true;                     // the status bytes lag behind the planes until somebody asks for them
         if (rs) CU(cudaMemcpyAsync(events, h->d_events, rs * (size_t)h->R * (size_t)nsteps, cudaMemcpyDeviceToHost, h->stream));

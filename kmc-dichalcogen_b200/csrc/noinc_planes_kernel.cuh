@@ -4,14 +4,17 @@
 // The byte-lattice version (sweep_kernel.cuh count-only + noinc_kernel.cuh) spends ~1.4 warp-instructions per site
 // on the enumeration (nibble-parallel, 8 sites per operation) and selects on one CTA from a strided row table:
 // 23 + 18 us per event at 4096^2.  Here the lattice lives as the six predicate planes of replica_wide_kernel.cuh
-// (Z, D, M1, M2, A4, A7; 0.75 B per site, two-column halo per row end), so
-//   * the full enumeration evaluates 64 sites per operation: one thread per 64-site cell builds the six
-//     MoveDivacancy direction masks and the trefoil masks of its cell from a 3 x 2 neighbourhood of plane words and
-//     popcounts them (~0.1 warp-instructions per site; the planes are 12.6 MB at 4096^2: HBM/L2-bound);
-//   * row counts leave the kernel class-major (coalesced for the row search) together with per-CTA partial sums
+// (Z, D, M1, M2, A4, A7; 0.75 B per site, two-column halo per row end), and ONE launch does the whole event:
+//   * enumeration: a warp owns PNR consecutive rows x 32 cells (a cell = 64 sites); a lane loads the plane words of
+//     rows a-1 .. a+PNR+1 of its cell once, builds every shifted window once (they are shared by the anchor rows
+//     and the six directions) and popcounts the MoveDivacancy / trefoil / MoveMonovacancy masks;
+//   * row counts leave the CTA class-major (coalesced for the row search) together with one record of per-CTA sums
 //     (a two-level hierarchy: CTA -> row), no atomics, nothing to zero;
-//   * the selection kernel scans the CTA sums, walks the <= 8 rows of the chosen CTA, searches the chosen row with
-//     one thread per cell and flips the touched bits of the planes (and their halo copies).
+//   * the CTA that finishes last (a ticket per replica) is the selector: it sums the records, chooses the class
+//     (same fp64 sequence as every other kernel), finds record -> row -> slot -> cell -> bit with three dependent
+//     rounds of loads, and flips the touched bits of the planes (and their halo copies) with atomics.
+// (History: two launches -- 1024 CTAs of one row x 64 cells, then a one-CTA selection kernel with ~10 dependent L2
+// round trips -- took 10.8 + 11.4 us.)
 // Status bytes are only materialised (kmc_wide_unpack_kernel) when somebody asks for them.
 // Results are bit-identical to the byte-lattice path (tests: both against the oracle).
 #pragma once
@@ -20,146 +23,238 @@
 
 namespace kmc {
 
-constexpr int PRC_STRIDE = 16;             // words per CTA partial-sum record / classes per row-count plane
+constexpr int PRC_STRIDE = 16;             // words per CTA record / classes per row-count plane
+constexpr int PNR = 2;                     // consecutive rows per warp in the enumeration
 
-__host__ __device__ inline int planes_chunks(int d1) {       // warps per row: power of two >= ceil(Wa / 32), <= 8
+__host__ __device__ inline int planes_chunks(int d1) {       // warps per row group: power of two >= ceil(Wa / 32), <= 8
     const int need = (wide_anchor_words(d1) + 31) >> 5;
     int c = 1;
     while (c < need) c <<= 1;
     return c;
 }
-
-// Full enumeration from the planes.  CTA = 8 warps = 8 / chunks rows; warp = 32 consecutive cells of one row.
-//   rowc [R][16][d0]   class-major row counts (classes 0..12)
-//   blk  [R][nblk][16] per-CTA sums of the same, nblk = ceil(d0 / rows_per_cta)
-// MM: slots 13, 14, 15 of a record hold MoveMonovacancy natural, merge-divacancy, swap-divacancy (class 16); the
-// split-divacancy count (class 15) is twice the sum of slots 2..5 and is not stored.
-template <bool MM = false>
-__global__ void __launch_bounds__(256) kmc_planes_rowcount_kernel(const u64 *planes, uint32_t *rowc, uint32_t *blk,
-                                                                 int R, int d0, int d1, int chunks, int nblk)
-{
-    __shared__ uint32_t part[8][7];
-    __shared__ uint32_t rowval[8][PRC_STRIDE];
-    const int Wa = wide_anchor_words(d1), We = Wa + 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int rpb = 8 / chunks;
-    const int rep = blockIdx.x / nblk, b = blockIdx.x - rep * nblk;
-    const int rl = warp / chunks;                                  // row slot inside the CTA
-    const int a = b * rpb + rl, chunk = warp % chunks;
-    const int w = chunk * 32 + lane;
-    WGeom G{planes + (size_t)rep * N_TYPES * d0 * We, d0, d1, Wa, We};
-    uint32_t zd = 0, ma = 0, k01 = 0, k23 = 0, tre = 0, nm = 0, sw = 0;
-    if (a < d0 && w < Wa) {
-        if (MM)
-            for (int k = 0; k < 6; k++) { uint32_t x, y; mm_cell_counts(G, a, w, k, x, y); nm += x; sw += y; }
-        const u64 v = G.valid(w);
-        zd = (uint32_t)__popcll(window_at(G.rowp(T_Z, a), w, 0) & v) |
-             ((uint32_t)__popcll(window_at(G.rowp(T_D, a), w, 0) & v) << 16);
-        ma = (uint32_t)__popcll((window_at(G.rowp(T_M1, a), w, 0) | window_at(G.rowp(T_M2, a), w, 0)) & v) |
-             ((uint32_t)__popcll((window_at(G.rowp(T_A4, a), w, 0) | window_at(G.rowp(T_A7, a), w, 0)) & v) << 16);
-        Nbhd n;
-        load_nbhd(G, a, w, n);
-        cell_counts(n, k01, k23, tre);
-    }
-    // 16-bit fields: a warp covers 2048 sites with <= 6 moves per site and class (<= 12288 per field)
-    zd = __reduce_add_sync(FULL, zd); ma = __reduce_add_sync(FULL, ma);
-    k01 = __reduce_add_sync(FULL, k01); k23 = __reduce_add_sync(FULL, k23); tre = __reduce_add_sync(FULL, tre);
-    if (MM) { nm = __reduce_add_sync(FULL, nm); sw = __reduce_add_sync(FULL, sw); }
-    if (lane == 0) {
-        part[warp][0] = zd; part[warp][1] = ma; part[warp][2] = k01; part[warp][3] = k23; part[warp][4] = tre;
-        part[warp][5] = nm; part[warp][6] = sw;
-    }
-    __syncthreads();
-    // the leader warp of each row: lane c < 13 combines the row's chunks (fields unpacked first) and writes class c
-    if (chunk == 0 && lane < PRC_STRIDE) {
-        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, tr = 0, nat = 0, mer = 0, swp = 0;
-        for (int q = 0; q < chunks; q++) {
-#pragma unroll
-            for (int f = 0; f < 4; f++) { const uint32_t x = part[warp + q][f]; lo[f] += x & 0xFFFFu; hi[f] += x >> 16; }
-            tr += part[warp + q][4];
-            nat += part[warp + q][5] & 0xFFFFu; mer += part[warp + q][5] >> 16; swp += part[warp + q][6];
-        }
-        const uint32_t pz = lo[0], pd = hi[0], pm = lo[1], pa = hi[1];
-        uint32_t val = 0;
-        switch (lane) {
-            case C_CREATE_DIV: val = pz; break;
-            case C_FILL_DIV: val = pd; break;
-            case C_MOVE_DIV: val = lo[2]; break;
-            case C_MOVE_DIV + 1: val = hi[2]; break;
-            case C_MOVE_DIV + 2: val = lo[3]; break;
-            case C_MOVE_DIV + 3: val = hi[3]; break;
-            case C_CREATE_TREF: val = tr; break;
-            case C_DESTROY_TREF: val = pa; break;
-            case C_CMONO_FROM_DOUBLE: val = 2 * pz; break;
-            case C_FMONO_FROM_EMPTY: val = 2 * pd; break;
-            case C_CMONO_MAKE_EMPTY: case C_FMONO_MAKE_DOUBLE: case C_FLIP: val = pm; break;   // one per monovacancy
-            case 13: val = MM ? nat : 0; break;
-            case 14: val = MM ? mer : 0; break;
-            case 15: val = MM ? swp : 0; break;
-            default: val = 0; break;
-        }
-        if (a >= d0) val = 0;
-        if (a < d0 && lane < (MM ? PRC_STRIDE : NC)) rowc[((size_t)rep * PRC_STRIDE + lane) * d0 + a] = val;
-        rowval[rl][lane] = val;
-    }
-    __syncthreads();
-    if (warp == 0 && lane < PRC_STRIDE) {
-        uint32_t s = 0;
-        for (int q = 0; q < rpb; q++) s += rowval[q][lane];
-        blk[((size_t)rep * nblk + b) * PRC_STRIDE + lane] = s;          // (lanes 13..15: MoveMonovacancy tables, 0 without MM)
-    }
-}
+__host__ __device__ inline int planes_rows_per_cta(int d1) { return (8 / planes_chunks(d1)) * PNR; }
 
 struct NoincPlanesParams {
     NoincParams base;                    // rate / order / draws / statistics pointers; status, rowcnt unused
     u64 *planes;                         // [R][6][d0][We]
-    const uint32_t *rowc;                // [R][16][d0]
-    const uint32_t *blk;                 // [R][nblk][16]
+    uint32_t *rowc;                      // [R][16][d0]   class-major row counts (classes 0..12; MM: 13, 14, 15)
+    uint32_t *blk;                       // [R][nblk][16] per-CTA sums of the same
     unsigned long long *counts;          // [R][NCA] class totals of this event's enumeration (out)
-    int nblk, rpb;
+    unsigned int *ticket;                // [R] zero between launches
+    int nblk, rpb, chunks, chunk_shift;
 };
 
-// One CTA (256 threads) per replica.
-template <bool MM = false>
-__global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const NoincPlanesParams q)
+// Word wc of a plane row and the low half of word wc + 1 (all that ever shifts into a window).  The neighbour lane
+// holds that word already: one shuffle instead of a second trip to L2; only the last lane of the warp (and the lane
+// of the row's last anchor word) loads it.  Called by all 32 lanes.
+__device__ __forceinline__ u64 plane_word_pair(const u64 *rp, int wc, bool own_next, uint32_t &x1) {
+    const u64 x0 = rp[wc];
+    x1 = __shfl_down_sync(FULL, (uint32_t)x0, 1);
+    if (own_next) x1 = reinterpret_cast<const uint32_t *>(rp + wc + 1)[0];
+    return x0;
+}
+
+// the count of class c (record slot c) from the unpacked field sums: lo/hi[0] = pristine / divacancy sites,
+// lo/hi[1] = monovacancies / trefoil anchors, lo/hi[2], lo/hi[3] = MoveDivacancy kinds, tr = trefoil sites
+template <bool MM>
+__device__ __forceinline__ uint32_t planes_class_value(int c, const uint32_t lo[4], const uint32_t hi[4], uint32_t tr,
+                                                       uint32_t nat, uint32_t mer, uint32_t swp) {
+    const uint32_t pz = lo[0], pd = hi[0], pm = lo[1], pa = hi[1];
+    switch (c) {
+        case C_CREATE_DIV: return pz;
+        case C_FILL_DIV: return pd;
+        case C_MOVE_DIV: return lo[2];
+        case C_MOVE_DIV + 1: return hi[2];
+        case C_MOVE_DIV + 2: return lo[3];
+        case C_MOVE_DIV + 3: return hi[3];
+        case C_CREATE_TREF: return tr;
+        case C_DESTROY_TREF: return pa;
+        case C_CMONO_FROM_DOUBLE: return 2 * pz;
+        case C_FMONO_FROM_EMPTY: return 2 * pd;
+        case C_CMONO_MAKE_EMPTY: case C_FMONO_MAKE_DOUBLE: case C_FLIP: return pm;      // one per monovacancy
+        case 13: return MM ? nat : 0;
+        case 14: return MM ? mer : 0;
+        case 15: return MM ? swp : 0;
+        default: return 0;
+    }
+}
+
+// ---- enumeration: the CTA's rows ---------------------------------------------------------------------------------
+// MM: slots 13, 14, 15 of a record hold MoveMonovacancy natural, merge-divacancy, swap-divacancy (class 16); the
+// split-divacancy count (class 15) is twice the sum of slots 2..5 and is not stored.
+template <bool MM>
+__device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int rep, int b,
+                                                 uint32_t (*part)[PNR][8])
+{
+    const int d0 = q.base.d0, d1 = q.base.d1;
+    const int Wa = wide_anchor_words(d1), We = Wa + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunks = q.chunks, groups = 8 / chunks;
+    const int g = warp >> q.chunk_shift, chunk = warp & (chunks - 1);     // chunks is a power of two
+    const int a0 = (b * groups + g) * PNR;                         // first row of this warp
+    const int w = chunk * 32 + lane;
+    uint32_t acc[PNR][7];
+#pragma unroll
+    for (int i = 0; i < PNR; i++)
+#pragma unroll
+        for (int f = 0; f < 7; f++) acc[i][f] = 0;
+    if (a0 < d0) {                                                 // (warp-uniform)
+        const u64 *P = q.planes + (size_t)rep * N_TYPES * d0 * We;
+        WGeom G{P, d0, d1, Wa, We};
+        // lanes beyond the row's last cell run along on its last cell with an empty `valid` mask (they take part in
+        // the shuffles of plane_word_pair)
+        const int wc = min(w, Wa - 1);
+        const bool own_next = lane == 31 || w >= Wa - 1;
+        const u64 valid = w < Wa ? G.valid(w) : 0ull;
+        // windows of rows a0-1 .. a0+PNR+1 (index r = offset + 1): Z and the monovacancy layers at db -1, 0, +1
+        // (index db + 1), D at db -2 .. +2 (index db + 2)
+        u64 Zw[PNR + 2][3], Dw[PNR + 3][5], M1w[MM ? PNR + 2 : 1][3], M2w[MM ? PNR + 2 : 1][3];
+#pragma unroll
+        for (int r = 0; r < PNR + 3; r++) {
+            const int ar = wrap1(a0 + r - 1, d0);                  // a0 < d0 and d0 >= 5: wraps at most once
+            uint32_t x1;
+            const u64 x0 = plane_word_pair(G.rowp(T_D, ar), wc, own_next, x1);
+#pragma unroll
+            for (int j = 0; j < 5; j++) Dw[r][j] = window(x0, (u64)x1, j - 2);
+            if (r < PNR + 2) {
+                uint32_t y1;
+                const u64 y0 = plane_word_pair(G.rowp(T_Z, ar), wc, own_next, y1);
+#pragma unroll
+                for (int j = 0; j < 3; j++) Zw[r][j] = window(y0, (u64)y1, j - 1);
+                if (MM) {
+                    uint32_t u1, v1;
+                    const u64 u0 = plane_word_pair(G.rowp(T_M1, ar), wc, own_next, u1), v0 = plane_word_pair(G.rowp(T_M2, ar), wc, own_next, v1);
+#pragma unroll
+                    for (int j = 0; j < 3; j++) { M1w[r][j] = window(u0, (u64)u1, j - 1); M2w[r][j] = window(v0, (u64)v1, j - 1); }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PNR; i++) {
+            if (a0 + i < d0) {
+                const int a = a0 + i;
+                const u64 dv = Dw[i + 1][2] & valid, zv = Zw[i + 1][1] & valid;
+                u64 mono, anch, m1 = 0, m2 = 0;
+                {
+                    uint32_t s1, t1;
+                    const u64 s0 = plane_word_pair(G.rowp(T_A4, a), wc, own_next, s1), t0 = plane_word_pair(G.rowp(T_A7, a), wc, own_next, t1);
+                    anch = window(s0 | t0, (u64)(s1 | t1), 0) & valid;
+                    if (MM) { m1 = M1w[i + 1][1] & valid; m2 = M2w[i + 1][1] & valid; mono = m1 | m2; }
+                    else {
+                        uint32_t u1, v1;
+                        const u64 u0 = plane_word_pair(G.rowp(T_M1, a), wc, own_next, u1), v0 = plane_word_pair(G.rowp(T_M2, a), wc, own_next, v1);
+                        mono = window(u0 | v0, (u64)(u1 | v1), 0) & valid;
+                    }
+                }
+                uint32_t nP = 0, nPN = 0, nPF = 0, nPNF = 0, nm = 0, sw = 0;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const int rn = i + 1 + nib(NBR_DA, k), re = i + 1 + nib(NEAR_DA, k), rf = i + 1 + nib(FAR_DA, k);
+                    const u64 zn = Zw[rn][nib(NBR_DB, k) + 1];
+                    // present, present & near, present & far, all three: the four kinds follow by inclusion-exclusion
+                    const u64 pr = dv & zn, pn = pr & Dw[re][nib(NEAR_DB, k) + 2], pf = pr & Dw[rf][nib(FAR_DB, k) + 2];
+                    nP += __popcll(pr); nPN += __popcll(pn); nPF += __popcll(pf);
+                    nPNF += __popcll(pn & pf);
+                    if (MM) {
+                        const u64 m1n = M1w[rn][nib(NBR_DB, k) + 1], m2n = M2w[rn][nib(NBR_DB, k) + 1];
+                        nm += (uint32_t)__popcll((m1 | m2) & zn) | ((uint32_t)__popcll((m1 & m2n) | (m2 & m1n)) << 16);
+                        sw += (uint32_t)__popcll(dv & (m1n | m2n));
+                    }
+                }
+                const u64 both = dv & Dw[i + 3][2];
+                acc[i][0] = (uint32_t)__popcll(zv) | ((uint32_t)__popcll(dv) << 16);
+                acc[i][1] = (uint32_t)__popcll(mono) | ((uint32_t)__popcll(anch) << 16);
+                acc[i][2] = (nP - nPN - nPF + nPNF) | ((nPN - nPNF) << 16);        // natural | missing-metal
+                acc[i][3] = (nPF - nPNF) | (nPNF << 16);                            // missing-comb | missing-both
+                acc[i][4] = (uint32_t)(__popcll(both & Dw[i + 1][4]) + __popcll(both & Dw[i + 3][0]));
+                acc[i][5] = nm; acc[i][6] = sw;
+            }
+        }
+    }
+    // 16-bit fields: a warp covers 2048 sites of a row with <= 6 moves per site and class (<= 12288 per field)
+#pragma unroll
+    for (int i = 0; i < PNR; i++)
+#pragma unroll
+        for (int f = 0; f < (MM ? 7 : 5); f++) {
+            const uint32_t s = __reduce_add_sync(FULL, acc[i][f]);
+            if (lane == 0) part[warp][i][f] = s;
+        }
+    __syncthreads();
+    // thread (row slot rs, class c) combines the row's chunks (fields unpacked first) and writes the row count
+    const int rpb = groups * PNR;
+    if (tid < rpb * PRC_STRIDE) {
+        const int rs = tid >> 4, c = tid & 15;
+        const int gg = rs / PNR, i = rs - gg * PNR;                   // (PNR is a constant power of two)
+        const int a = (b * groups + gg) * PNR + i;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, tr = 0, nat = 0, mer = 0, swp = 0;
+        for (int ch = 0; ch < chunks; ch++) {
+            const uint32_t *pw = part[gg * chunks + ch][i];
+#pragma unroll
+            for (int f = 0; f < 4; f++) { const uint32_t x = pw[f]; lo[f] += x & 0xFFFFu; hi[f] += x >> 16; }
+            tr += pw[4];
+            if (MM) { nat += pw[5] & 0xFFFFu; mer += pw[5] >> 16; swp += pw[6]; }
+        }
+        const uint32_t val = planes_class_value<MM>(c, lo, hi, tr, nat, mer, swp);
+        if (a < d0 && c < (MM ? PRC_STRIDE : NC)) q.rowc[((size_t)rep * PRC_STRIDE + c) * d0 + a] = val;
+    }
+    // the CTA record: lane c of the last warp sums class c over all of the CTA's warps and rows (rows beyond the
+    // lattice contributed zeros)
+    if (tid >= 224 && tid < 224 + PRC_STRIDE) {
+        const int c = tid - 224;
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0}, tr = 0, nat = 0, mer = 0, swp = 0;
+        for (int wq = 0; wq < 8; wq++)
+#pragma unroll
+            for (int i = 0; i < PNR; i++) {
+                const uint32_t *pw = part[wq][i];
+#pragma unroll
+                for (int f = 0; f < 4; f++) { const uint32_t x = pw[f]; lo[f] += x & 0xFFFFu; hi[f] += x >> 16; }
+                tr += pw[4];
+                if (MM) { nat += pw[5] & 0xFFFFu; mer += pw[5] >> 16; swp += pw[6]; }
+            }
+        q.blk[((size_t)rep * q.nblk + b) * PRC_STRIDE + c] = planes_class_value<MM>(c, lo, hi, tr, nat, mer, swp);
+    }
+}
+
+__device__ __forceinline__ void noinc_record_none(const NoincParams &p, size_t idx) {
+    if (p.log_mode == KMC_LOG_FULL) {
+        kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
+        rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
+        rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
+    } else if (p.log_mode == KMC_LOG_COMPACT) {
+        kmc_event_compact e; e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE;
+        e.flags = 0; e.total_rate = 0.0;
+        reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
+    }
+}
+
+// ---- selection + move: the 256 threads of the replica's last CTA ---------------------------------------------------
+template <bool MM>
+__device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int rep)
 {
     constexpr int NCX = MM ? NCA : NC;
     constexpr int NL = MM ? 32 : 16;
     const NoincParams &p = q.base;
-    __shared__ unsigned long long wsum[8];
     __shared__ uint32_t s_tot[8][PRC_STRIDE];               // per-warp class sums of the CTA records
     __shared__ double s_u1, s_u2;
     __shared__ unsigned long long s_rank;
     __shared__ double s_total;
-    __shared__ int s_csel, s_zero, s_tie, s_row, s_word, s_bit;
-    __shared__ uint32_t s_rin, s_slotcnt[12];
-    const int rep = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    __shared__ int s_csel, s_zero, s_tie, s_row, s_word, s_bit, s_layer1;
+    __shared__ uint32_t s_rin, s_wslot[8][12];
+    const int tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
     const int Wa = wide_anchor_words(d1), We = Wa + 1;
     const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
-    if (p.flags[rep] & FLAG_ZERO_RATE) {                // this replica already stopped (uniform): no event
-        if (tid == 0) {
-            if (p.log_mode == KMC_LOG_FULL) {
-                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
-                rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
-                rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
-            } else if (p.log_mode == KMC_LOG_COMPACT) {
-                kmc_event_compact e; e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE;
-                e.flags = 0; e.total_rate = 0.0;
-                reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
-            }
-        }
-        return;
-    }
+    // ---- round 1 of loads: everything that does not depend on the enumeration's outcome, and the CTA records -------
+    const uint32_t flag0 = p.flags[rep];
+    const unsigned long long step = p.steps_done[rep];
+    double clk = 0.0;
+    if (tid == 0 && p.clock) clk = p.clock[rep];
     u64 *P = q.planes + (size_t)rep * N_TYPES * d0 * We;
     WGeom G{P, d0, d1, Wa, We};
     const uint32_t *blk = q.blk + (size_t)rep * q.nblk * PRC_STRIDE;
     const uint32_t *rowc = q.rowc + (size_t)rep * PRC_STRIDE * d0;
-    const unsigned long long step = p.steps_done[rep];
-
-    // ---- class totals: every thread owns KB consecutive CTA records and keeps all 13 class sums of them in
-    // registers (one round of independent 16-byte loads); they serve the totals now and the row search below
-    constexpr int KB_MAX = 8;                               // nblk <= 2048 CTA records (d0 <= 16384 rows)
+    // every thread owns kb consecutive CTA records and keeps the class sums of them in registers: they serve the
+    // totals now and the search for the thread that holds the rank below
     const int kb = (q.nblk + 255) / 256;
     uint32_t mine_c[PRC_STRIDE];
 #pragma unroll
@@ -168,16 +263,19 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
         const int b = tid * kb + i;
         if (b < q.nblk) {
             const uint4 *rec = reinterpret_cast<const uint4 *>(blk + (size_t)b * PRC_STRIDE);
-            const uint4 x0 = rec[0], x1 = rec[1], x2 = rec[2], x3 = rec[3];
+            const uint4 x0 = __ldcg(rec), x1 = __ldcg(rec + 1), x2 = __ldcg(rec + 2), x3 = __ldcg(rec + 3);
             mine_c[0] += x0.x; mine_c[1] += x0.y; mine_c[2] += x0.z; mine_c[3] += x0.w;
             mine_c[4] += x1.x; mine_c[5] += x1.y; mine_c[6] += x1.z; mine_c[7] += x1.w;
             mine_c[8] += x2.x; mine_c[9] += x2.y; mine_c[10] += x2.z; mine_c[11] += x2.w;
             mine_c[12] += x3.x; mine_c[13] += x3.y; mine_c[14] += x3.z; mine_c[15] += x3.w;
         }
     }
-    (void)KB_MAX;
+    if (flag0 & FLAG_ZERO_RATE) {                        // this replica already stopped (uniform): no event
+        if (tid == 0) noinc_record_none(p, idx);
+        return;
+    }
     {
-        uint32_t mysum = 0;                                 // lane c < 13 of each warp collects the warp's sum of class c
+        uint32_t mysum = 0;                                 // lane c of each warp collects the warp's sum of class c
 #pragma unroll
         for (int c = 0; c < (MM ? PRC_STRIDE : NC); c++) {
             const uint32_t sc = __reduce_add_sync(FULL, mine_c[c]);
@@ -189,14 +287,13 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     if (tid == 32) {
         double u1, u2;
         if (p.draws) {
-            const double2 u = *reinterpret_cast<const double2 *>(p.draws + ((size_t)rep * (size_t)p.nsteps + (size_t)p.t) * 2);
+            const double2 u = *reinterpret_cast<const double2 *>(p.draws + idx * 2);
             u1 = u.x; u2 = u.y;
         } else {
             kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
         }
         s_u1 = u1; s_u2 = u2;
     }
-    if (tid < 12) s_slotcnt[tid] = 0;
     __syncthreads();
     if (tid < 32) {
         // class totals: lane c reads the table of class c (MM: 13, 14 -> 13, 14; 16 -> 15; 15 = 2 x classes 2..5)
@@ -230,25 +327,16 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
     __syncthreads();
     if (s_zero) {
         if (tid == 0) {
-            p.flags[rep] |= FLAG_ZERO_RATE;
+            p.flags[rep] = flag0 | FLAG_ZERO_RATE;
             atomicOr(p.any_flag, FLAG_ZERO_RATE);
-            if (p.log_mode == KMC_LOG_FULL) {
-                kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) + idx;
-                rec->site = 0xFFFFFFFFu; rec->cls = KMC_CLASS_NONE; rec->slot = KMC_SLOT_NONE;
-                rec->flags = 0; rec->total_rate = 0.0; rec->pad = 0;
-            } else if (p.log_mode == KMC_LOG_COMPACT) {
-                kmc_event_compact e; e.site = 0xFFFFFFFFu; e.cls = KMC_CLASS_NONE; e.slot = KMC_SLOT_NONE;
-                e.flags = 0; e.total_rate = 0.0;
-                reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
-            }
+            noinc_record_none(p, idx);
         }
         return;
     }
     const int csel = s_csel;
 
-    // ---- row: CTA record, then the rows of that CTA --------------------------------------------------------
+    // ---- row: the thread whose records hold the rank walks their rows (round 2 of loads) ------------------------------
     {
-        const int b0 = tid * kb, b1 = min(b0 + kb, q.nblk);
         // table of the chosen class (MM: class 16 -> 15); split-divacancy is twice tables 2..5
         const bool split = MM && csel == C_MOVE_MONO + 2;
         const int tb = (MM && csel == C_MOVE_MONO + 3) ? 15 : csel;
@@ -256,39 +344,47 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
 #pragma unroll
         for (int c = 1; c < (MM ? PRC_STRIDE : NC); c++) mysel = tb == c ? mine_c[c] : mysel;
         if (split) mysel = 2u * (mine_c[2] + mine_c[3] + mine_c[4] + mine_c[5]);
-        auto blkval = [&](int b) -> unsigned long long {
-            const uint32_t *rec = blk + (size_t)b * PRC_STRIDE;
-            return split ? 2ull * ((unsigned long long)rec[2] + rec[3] + rec[4] + rec[5]) : rec[tb];
-        };
         auto rowval_of = [&](int a) -> uint32_t {
-            return split ? 2u * (rowc[(size_t)2 * d0 + a] + rowc[(size_t)3 * d0 + a] + rowc[(size_t)4 * d0 + a] + rowc[(size_t)5 * d0 + a])
-                         : rowc[(size_t)tb * d0 + a];
+            return split ? 2u * (__ldcg(rowc + (size_t)2 * d0 + a) + __ldcg(rowc + (size_t)3 * d0 + a) +
+                                 __ldcg(rowc + (size_t)4 * d0 + a) + __ldcg(rowc + (size_t)5 * d0 + a))
+                         : __ldcg(rowc + (size_t)tb * d0 + a);
         };
-        unsigned long long local = mysel, total;
-        const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
+        // exclusive prefix of `mysel` over the CTA: the warps before this one from the per-warp class sums that made
+        // the totals (s_tot), the lanes before this one by a warp scan -- no barrier
+        unsigned long long excl = 0;
+        for (int wq = 0; wq < (tid >> 5); wq++)
+            excl += split ? 2ull * ((unsigned long long)s_tot[wq][2] + s_tot[wq][3] + s_tot[wq][4] + s_tot[wq][5])
+                          : (unsigned long long)s_tot[wq][tb];
+        const unsigned long long local = mysel;
+        {
+            uint32_t inc = mysel;                          // (a warp's records hold fewer than 2^32 moves of a class)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+            excl += inc - mysel;
+        }
         const unsigned long long rank = s_rank;
         if (rank >= excl && rank < excl + local) {
-            // the one thread that holds the rank: its <= kb records, then the <= 8 rows of the record
-            unsigned long long r = rank - excl;
-            int b = b0;
-            for (; b < b1 - 1; b++) {
-                const unsigned long long v = blkval(b);
-                if (r < v) break;
-                r -= v;
+            uint32_t r = (uint32_t)(rank - excl);
+            const int a_lo = tid * kb * q.rpb, a_hi = min((tid + 1) * kb * q.rpb, d0);
+            int row = a_hi - 1;
+            bool found = false;
+            for (int a = a_lo; a < a_hi && !found; a += 16) {
+                uint32_t rv[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) rv[i] = a + i < a_hi ? rowval_of(a + i) : 0u;    // independent loads
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    if (!found && a + i < a_hi) {
+                        if (r < rv[i]) { found = true; row = a + i; }
+                        else r -= rv[i];
+                    }
             }
-            const int a0 = b * q.rpb;
-            uint32_t rv[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) rv[i] = (i < q.rpb && a0 + i < d0) ? rowval_of(a0 + i) : 0u;
-            int a = a0;
-#pragma unroll
-            for (int i = 0; i < 7; i++)
-                if (a == a0 + i && i < q.rpb - 1 && r >= rv[i]) { r -= rv[i]; a = a0 + i + 1; }
-            s_row = a; s_rin = (uint32_t)r;
+            s_row = row; s_rin = r;
         }
     }
     __syncthreads();
     const int row = s_row;
+    u64 flip_m1 = 0;
 
     // ---- slot and site inside the row: one thread per 64-site cell (rows of <= 16384 sites) --------------------
     constexpr int NSL = MM ? 12 : 6;
@@ -330,35 +426,44 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
             }
             const u64 v = G.valid(tid);
             m[0] = window_at(G.rowp(pa, row), tid, 0) & v;
+            flip_m1 = m[0];
             if (csel == C_FLIP) m[0] |= window_at(G.rowp(T_M2, row), tid, 0) & v;
             if (pb >= 0) m[1] = window_at(G.rowp(pb, row), tid, 0) & v;
         }
     }
     {
+        // per-warp slot counts (plain stores: every warp writes its own line, nothing to zero)
 #pragma unroll
         for (int i = 0; i < NSL; i += 2) {
             const uint32_t c = __reduce_add_sync(FULL, (uint32_t)__popcll(m[i]) | ((uint32_t)__popcll(m[i + 1]) << 16));
-            if (lane == 0) {
-                if (c & 0xFFFFu) atomicAdd(&s_slotcnt[i], c & 0xFFFFu);
-                if (c >> 16) atomicAdd(&s_slotcnt[i + 1], c >> 16);
-            }
+            if (lane == 0) { s_wslot[tid >> 5][i] = c & 0xFFFFu; s_wslot[tid >> 5][i + 1] = c >> 16; }
         }
     }
     __syncthreads();
     uint32_t r = s_rin;
     int j = 0;
 #pragma unroll
-    for (int i = 0; i < NSL - 1; i++)
-        if (j == i && r >= s_slotcnt[i]) { r -= s_slotcnt[i]; j = i + 1; }
+    for (int i = 0; i < NSL - 1; i++) {
+        uint32_t tot = 0;
+#pragma unroll
+        for (int wq = 0; wq < 8; wq++) tot += s_wslot[wq][i];
+        if (j == i && r >= tot) { r -= tot; j = i + 1; }
+    }
     u64 mj = m[0];
 #pragma unroll
     for (int i = 1; i < NSL; i++) mj = j == i ? m[i] : mj;
     {
-        const unsigned long long local = (unsigned long long)__popcll(mj);
-        unsigned long long total;
-        const unsigned long long excl = block_exclusive_scan(local, wsum, tid, total);
-        if ((unsigned long long)r >= excl && (unsigned long long)r < excl + local) {
-            s_word = tid; s_bit = nth_bit64(mj, r - (uint32_t)excl);
+        // exclusive prefix of the cells' counts: warps before this one from s_wslot, lanes by a warp scan
+        const uint32_t local = (uint32_t)__popcll(mj);
+        uint32_t excl = 0;
+        for (int wq = 0; wq < (tid >> 5); wq++) excl += s_wslot[wq][j];
+        uint32_t inc = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        excl += inc - local;
+        if (r >= excl && r < excl + local) {
+            s_word = tid; s_bit = nth_bit64(mj, r - excl);
+            s_layer1 = (int)((flip_m1 >> s_bit) & 1ull);
         }
     }
     __syncthreads();
@@ -373,7 +478,7 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
         case C_DESTROY_TREF: s0 = j ? 7 : 4; break;
         case C_CMONO_MAKE_EMPTY: s0 = j ? 1 : 2; break;
         case C_FMONO_MAKE_DOUBLE: s0 = j ? 2 : 1; break;
-        default: s0 = ((window_at(G.rowp(T_M1, row), s_word, 0) >> s_bit) & 1ull) ? 1 : 2; break;
+        default: s0 = s_layer1 ? 1 : 2; break;             // FlipMonovacancy: the layer the vacancy is in
     }
     const int site = row * d1 + col;
     // ---- the move: thread (node i, plane pl) = tid < 18 rewrites its plane bit (+ halo copy) ---------------------
@@ -424,12 +529,41 @@ __global__ void __launch_bounds__(256) kmc_noinc_planes_select_kernel(const Noin
             reinterpret_cast<kmc_event_compact *>(p.events)[idx] = e;
         }
         p.steps_done[rep] = step + 1;
-        if (p.clock) p.clock[rep] = __dadd_rn(p.clock[rep], kmc_time_step(p.clock_mode, s_total, p.seed,
-                                                                          p.replica0 + (uint32_t)rep, step));
-        p.hist[(size_t)rep * NCA + csel] += 1;
-        if (slot >= 7 && slot < 13) p.hops[(size_t)rep * 6 + slot - 7] += 1;
-        if (s_tie) p.ties[rep] += 1;
+        if (p.clock) p.clock[rep] = __dadd_rn(clk, kmc_time_step(p.clock_mode, s_total, p.seed, p.replica0 + (uint32_t)rep, step));
+        // (statistics of one replica are only ever touched by its selector: fire-and-forget adds, no load round trips)
+        atomicAdd(p.hist + (size_t)rep * NCA + csel, 1ull);
+        if (slot >= 7 && slot < 13) atomicAdd(p.hops + (size_t)rep * 6 + slot - 7, 1ull);
+        if (s_tie) atomicAdd(p.ties + rep, 1ull);
     }
+}
+
+// One launch per event.  grid = R * nblk CTAs of 256 threads; CTA (rep, b) enumerates rows b * rpb .. of replica rep.
+template <bool MM = false>
+__global__ void __launch_bounds__(256) kmc_noinc_planes_event_kernel(const NoincPlanesParams q)
+{
+    __shared__ uint32_t part[8][PNR][8];
+    __shared__ int s_last;
+    const int rep = q.base.n_replicas == 1 ? 0 : blockIdx.x / q.nblk, b = blockIdx.x - rep * q.nblk;
+    // Programmatic dependent launch: the next event's CTAs may become resident while this grid runs (they hold at
+    // their own `wait` until this grid has completed and its writes are visible) -- hides the launch latency between
+    // the dependent launches of consecutive events.  Nothing the previous grid wrote is read above this line.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (q.base.stage == 3) return;
+    planes_enumerate<MM>(q, rep, b, part);
+    if (q.base.stage == 4) return;
+    // row counts and the record are written; the barrier orders them before thread 0's fence (fences are cumulative),
+    // the ticket after it: the CTA that draws the last ticket sees everything every CTA wrote
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(q.ticket + rep, 1u);
+        s_last = t == (unsigned)q.nblk - 1u;
+        if (s_last) { q.ticket[rep] = 0u; __threadfence(); }
+    }
+    __syncthreads();
+    if (!s_last || q.base.stage >= 2) return;
+    planes_select<MM>(q, rep);
 }
 
 }  // namespace kmc
