@@ -72,6 +72,7 @@ struct kmc_engine {
     bool planes_valid = false, bytes_stale = false;
     bool whier_valid = false;                // d_whier matches the planes (the no-incremental plane path does not maintain it)
     uint32_t *d_prowc = nullptr, *d_pblk = nullptr;   // no-incremental path on planes: class-major row counts, CTA sums
+    unsigned int *d_pepoch = nullptr;                 // persistent form: events completed in this call
     unsigned int *d_pticket = nullptr;                // and the per-replica ticket that elects the selecting CTA
     void *d_flush = nullptr; size_t flush_bytes = 0;   // L2-flush scratch (measurement helper)
     int warps_per_block = 0;
@@ -172,7 +173,7 @@ extern "C" int kmc_destroy(kmc_engine *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_slots); cudaFree(h->d_slots_alt); cudaFree(h->d_rowcnt); cudaFree(h->d_rowmm); cudaFree(h->d_counts);
     cudaFree(h->d_acc); cudaFree(h->d_ticket); cudaFree(h->d_flush); cudaFree(h->d_hier); cudaFree(h->d_clock); cudaFree(h->d_tracer);
-    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk); cudaFree(h->d_pticket);
+    cudaFree(h->d_planes); cudaFree(h->d_whier); cudaFree(h->d_whier_chk); cudaFree(h->d_prowc); cudaFree(h->d_pblk); cudaFree(h->d_pticket); cudaFree(h->d_pepoch);
     cudaFree(h->d_steps); cudaFree(h->d_hist); cudaFree(h->d_hops); cudaFree(h->d_ties); cudaFree(h->d_flags); cudaFree(h->d_anyflag);
     cudaFree(h->d_events); cudaFree(h->d_draws); cudaFree(h->d_result);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -532,6 +533,7 @@ static int check_flags(kmc_engine *h, bool check_validate)
     CU(cudaStreamSynchronize(h->stream));
     int zero = -1, bad = -1;
     for (int r = 0; r < h->R; r++) {
+        if (fl[r] & FLAG_STALL) return fail(KMC_ERR_CUDA, "no-incremental kernel: a CTA waited in vain for its replica's selector");
         if ((fl[r] & FLAG_VALIDATE) && bad < 0) bad = r;
         if ((fl[r] & FLAG_ZERO_RATE) && zero < 0) zero = r;
     }
@@ -945,6 +947,7 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
             CU(cudaMalloc(&h->d_prowc, (size_t)h->R * PRC_STRIDE * h->d0 * sizeof(uint32_t)));
             CU(cudaMalloc(&h->d_pblk, (size_t)h->R * nblk * PRC_STRIDE * sizeof(uint32_t)));
             CU(cudaMalloc(&h->d_pticket, (size_t)h->R * sizeof(unsigned int)));
+            CU(cudaMalloc(&h->d_pepoch, (size_t)h->R * sizeof(unsigned int)));
             CU(cudaMemsetAsync(h->d_pticket, 0, (size_t)h->R * sizeof(unsigned int), h->stream));
         }
         if (!h->planes_valid) {
@@ -957,22 +960,43 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         }
         NoincPlanesParams q;
         q.base = p; q.planes = h->d_planes; q.rowc = h->d_prowc; q.blk = h->d_pblk; q.counts = h->d_counts;
-        q.ticket = h->d_pticket; q.nblk = nblk; q.rpb = rpb; q.chunks = chunks;
+        q.ticket = h->d_pticket; q.epoch = h->d_pepoch; q.nblk = nblk; q.rpb = rpb; q.chunks = chunks;
         q.chunk_shift = 0; while ((1 << q.chunk_shift) < chunks) q.chunk_shift++;
         q.base.stage = getenv("KMC_NOINC_DEBUG_SKIP") ? atoi(getenv("KMC_NOINC_DEBUG_SKIP")) : 0;
         const bool pdl = !getenv("KMC_NOINC_NO_PDL");
         const auto dbg_t0 = std::chrono::steady_clock::now();
-        for (long long t = 0; t < nsteps; t++) {
+        // One cooperative launch for the whole call when every CTA can be resident at once (4096^2: 512 CTAs); else one
+        // launch per event, chained by programmatic dependent launch.
+        const unsigned grid = (unsigned)(h->R * nblk);
+        bool persist = nsteps >= 2 && !getenv("KMC_NOINC_NO_PERSIST") && q.base.stage == 0;
+        if (persist) {
+            int per_sm = 0, coop = 0;
+            if (h->mm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmc_noinc_planes_event_kernel<true, true>, 256, 0));
+            else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmc_noinc_planes_event_kernel<false, true>, 256, 0));
+            CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, h->device));
+            int sms = 0;
+            CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            if (!coop || (long long)per_sm * sms < (long long)grid) persist = false;
+        }
+        if (persist) {
+            CU(cudaMemsetAsync(h->d_pepoch, 0, (size_t)h->R * sizeof(unsigned int), h->stream));
+            long long t0 = 0, t1 = nsteps;
+            void *args[] = {(void *)&q, (void *)&t0, (void *)&t1};
+            const void *fn = h->mm ? (const void *)kmc_noinc_planes_event_kernel<true, true>
+                                   : (const void *)kmc_noinc_planes_event_kernel<false, true>;
+            CU(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(256), args, 0, h->stream));
+            h->launches += 1;
+        } else for (long long t = 0; t < nsteps; t++) {
             // sim.py:114-115: initialize() -- a full re-enumeration -- before every event; one launch does both
-            q.base.t = t;
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3((unsigned)(h->R * nblk)); cfg.blockDim = dim3(256); cfg.stream = h->stream;
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.stream = h->stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-            if (h->mm) CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<true>, q));
-            else CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<false>, q));
+            const long long t1 = t + 1;
+            if (h->mm) CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<true, false>, q, t, t1));
+            else CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<false, false>, q, t, t1));
             h->launches += 1;
         }
         if (getenv("KMC_NOINC_DEBUG_TIME"))

@@ -41,6 +41,7 @@ struct NoincPlanesParams {
     uint32_t *blk;                       // [R][nblk][16] per-CTA sums of the same
     unsigned long long *counts;          // [R][NCA] class totals of this event's enumeration (out)
     unsigned int *ticket;                // [R] zero between launches
+    unsigned int *epoch;                 // [R] persistent form: events of this call completed so far (zero on entry)
     int nblk, rpb, chunks, chunk_shift;
 };
 
@@ -153,8 +154,12 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
                     const u64 zn = Zw[rn][nib(NBR_DB, k) + 1];
                     // present, present & near, present & far, all three: the four kinds follow by inclusion-exclusion
                     const u64 pr = dv & zn, pn = pr & Dw[re][nib(NEAR_DB, k) + 2], pf = pr & Dw[rf][nib(FAR_DB, k) + 2];
+#ifdef KMC_ENUM_OLD
+                    { uint32_t c01, c23; kind_counts(pr, Dw[re][nib(NEAR_DB, k) + 2], Dw[rf][nib(FAR_DB, k) + 2], c01, c23); nP += c01; nPN += c23; }
+#else
                     nP += __popcll(pr); nPN += __popcll(pn); nPF += __popcll(pf);
                     nPNF += __popcll(pn & pf);
+#endif
                     if (MM) {
                         const u64 m1n = M1w[rn][nib(NBR_DB, k) + 1], m2n = M2w[rn][nib(NBR_DB, k) + 1];
                         nm += (uint32_t)__popcll((m1 | m2) & zn) | ((uint32_t)__popcll((m1 & m2n) | (m2 & m1n)) << 16);
@@ -164,8 +169,12 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
                 const u64 both = dv & Dw[i + 3][2];
                 acc[i][0] = (uint32_t)__popcll(zv) | ((uint32_t)__popcll(dv) << 16);
                 acc[i][1] = (uint32_t)__popcll(mono) | ((uint32_t)__popcll(anch) << 16);
+#ifdef KMC_ENUM_OLD
+                acc[i][2] = nP; acc[i][3] = nPN;
+#else
                 acc[i][2] = (nP - nPN - nPF + nPNF) | ((nPN - nPNF) << 16);        // natural | missing-metal
                 acc[i][3] = (nPF - nPNF) | (nPNF << 16);                            // missing-comb | missing-both
+#endif
                 acc[i][4] = (uint32_t)(__popcll(both & Dw[i + 1][4]) + __popcll(both & Dw[i + 3][0]));
                 acc[i][5] = nm; acc[i][6] = sw;
             }
@@ -229,7 +238,7 @@ __device__ __forceinline__ void noinc_record_none(const NoincParams &p, size_t i
 
 // ---- selection + move: the 256 threads of the replica's last CTA ---------------------------------------------------
 template <bool MM>
-__device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int rep)
+__device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int rep, long long t)
 {
     constexpr int NCX = MM ? NCA : NC;
     constexpr int NL = MM ? 32 : 16;
@@ -243,7 +252,7 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
     const int tid = threadIdx.x, lane = tid & 31;
     const int d0 = p.d0, d1 = p.d1;
     const int Wa = wide_anchor_words(d1), We = Wa + 1;
-    const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)p.t;
+    const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
     // ---- round 1 of loads: everything that does not depend on the enumeration's outcome, and the CTA records -------
     const uint32_t flag0 = p.flags[rep];
     const unsigned long long step = p.steps_done[rep];
@@ -537,33 +546,63 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
     }
 }
 
-// One launch per event.  grid = R * nblk CTAs of 256 threads; CTA (rep, b) enumerates rows b * rpb .. of replica rep.
-template <bool MM = false>
-__global__ void __launch_bounds__(256) kmc_noinc_planes_event_kernel(const NoincPlanesParams q)
+// grid = R * nblk CTAs of 256 threads; CTA (rep, b) enumerates rows b * rpb .. of replica rep.
+//  * PERSIST = false: one launch per event (local step index t0), chained by programmatic dependent launch;
+//  * PERSIST = true: ONE cooperative launch runs events t0 .. t1-1.  After its enumeration every CTA waits until the
+//    replica's selector has published the event (`epoch`, release / acquire through fences as in a grid barrier), so
+//    the ~4 us it costs to start a dependent grid are paid once per call instead of once per event.  All CTAs must be
+//    co-resident (the host checks the occupancy and uses the cooperative launch API); a bounded spin turns a
+//    missing selector into FLAG_STALL instead of a hang.
+constexpr uint32_t FLAG_STALL = 8u;
+template <bool MM = false, bool PERSIST = false>
+__global__ void __launch_bounds__(256, MM ? 2 : 4) kmc_noinc_planes_event_kernel(const NoincPlanesParams q, const long long t0, const long long t1)
 {
     __shared__ uint32_t part[8][PNR][8];
-    __shared__ int s_last;
+    __shared__ int s_last, s_abort;
     const int rep = q.base.n_replicas == 1 ? 0 : blockIdx.x / q.nblk, b = blockIdx.x - rep * q.nblk;
-    // Programmatic dependent launch: the next event's CTAs may become resident while this grid runs (they hold at
-    // their own `wait` until this grid has completed and its writes are visible) -- hides the launch latency between
-    // the dependent launches of consecutive events.  Nothing the previous grid wrote is read above this line.
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (q.base.stage == 3) return;
-    planes_enumerate<MM>(q, rep, b, part);
-    if (q.base.stage == 4) return;
-    // row counts and the record are written; the barrier orders them before thread 0's fence (fences are cumulative),
-    // the ticket after it: the CTA that draws the last ticket sees everything every CTA wrote
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int t = atomicAdd(q.ticket + rep, 1u);
-        s_last = t == (unsigned)q.nblk - 1u;
-        if (s_last) { q.ticket[rep] = 0u; __threadfence(); }
+    if (!PERSIST) {
+        // Programmatic dependent launch: the next event's CTAs may become resident while this grid runs (they hold at
+        // their own `wait` until this grid has completed and its writes are visible).  Nothing the previous grid
+        // wrote is read above this line.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    __syncthreads();
-    if (!s_last || q.base.stage >= 2) return;
-    planes_select<MM>(q, rep);
+    for (long long t = t0; t < t1; t++) {
+        planes_enumerate<MM>(q, rep, b, part);
+        // row counts and the record are written; the barrier orders them before thread 0's release (cumulative),
+        // the ticket with it: the CTA that draws the last ticket sees everything every CTA wrote
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int tk;                                // release our rows, acquire everybody else's
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(tk) : "l"(q.ticket + rep) : "memory");
+            s_last = tk == (unsigned)q.nblk - 1u;
+            if (s_last) q.ticket[rep] = 0u;
+        }
+        __syncthreads();
+        const bool last = s_last != 0;
+        if (last && q.base.stage < 2) planes_select<MM>(q, rep, t);
+        if (!PERSIST) return;
+        __syncthreads();                                    // the selector's threads are through
+        if (threadIdx.x == 0) {
+            int stalled = 0;
+            if (last) {                                     // the move, the statistics and the ticket reset, then the epoch
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(q.epoch + rep), "r"((unsigned)(t + 1)) : "memory");
+            } else {
+                unsigned int spins = 0, seen;
+                for (;;) {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(q.epoch + rep) : "memory");
+                    if (seen >= (unsigned)(t + 1)) break;
+                    if (++spins > (1u << 22)) { stalled = 1; break; }
+                }
+            }
+            s_abort = stalled;
+        }
+        __syncthreads();
+        if (s_abort) {
+            if (threadIdx.x == 0) { atomicOr(q.base.flags + rep, FLAG_STALL); atomicOr(q.base.any_flag, FLAG_STALL); }
+            return;
+        }
+    }
 }
 
 }  // namespace kmc

@@ -2,6 +2,9 @@
 import os, sys, time
 sys.path.insert(0, "kmc-dichalcogen_b200"); sys.path.insert(0, ".")
 import bench
+if os.environ.get("KMC_LIB"):
+    import demo1._native as _n
+    _n.LIB_PATH = os.path.abspath(os.environ["KMC_LIB"])
 from demo1.engine import Engine
 N = int(os.environ.get("NOINC_EVENTS", "2000"))
 big = Engine(bench.SWEEP_DIM, bench.wse2_rates(), bench.WSE2_ORDER, n_replicas=1)
