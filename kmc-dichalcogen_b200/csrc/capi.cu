@@ -8,6 +8,7 @@
 #include <string.h>
 #include <string>
 #include <utility>
+#include <algorithm>
 #include <vector>
 #include <chrono>
 
@@ -947,8 +948,8 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
             CU(cudaMalloc(&h->d_prowc, (size_t)h->R * PRC_STRIDE * h->d0 * sizeof(uint32_t)));
             CU(cudaMalloc(&h->d_pblk, (size_t)h->R * nblk * PRC_STRIDE * sizeof(uint32_t)));
             CU(cudaMalloc(&h->d_pticket, (size_t)h->R * sizeof(unsigned int)));
-            CU(cudaMalloc(&h->d_pepoch, (size_t)h->R * sizeof(unsigned int)));
             CU(cudaMemsetAsync(h->d_pticket, 0, (size_t)h->R * sizeof(unsigned int), h->stream));
+            CU(cudaMalloc(&h->d_pepoch, (size_t)h->R * sizeof(unsigned int)));
         }
         if (!h->planes_valid) {
             rc = ensure_bytes(h); if (rc) return rc;
@@ -980,6 +981,7 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         }
         if (persist) {
             CU(cudaMemsetAsync(h->d_pepoch, 0, (size_t)h->R * sizeof(unsigned int), h->stream));
+            CU(cudaMemsetAsync(h->d_pticket, 0, (size_t)h->R * sizeof(unsigned int), h->stream));   // (also after an aborted call)
             long long t0 = 0, t1 = nsteps;
             void *args[] = {(void *)&q, (void *)&t0, (void *)&t1};
             const void *fn = h->mm ? (const void *)kmc_noinc_planes_event_kernel<true, true>
@@ -999,6 +1001,18 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
             else CU(cudaLaunchKernelEx(&cfg, kmc_noinc_planes_event_kernel<false, false>, q, t, t1));
             h->launches += 1;
         }
+#ifdef KMC_NOINC_TRACE
+        {
+            long long tr[16];
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpyFromSymbol(tr, g_noinc_trace, sizeof tr));
+            fprintf(stderr, "noinc trace (cycles since the start of the event, mean of %lld events):", tr[15]);
+            for (int i = 0; i < 14; i++) fprintf(stderr, " %d:%.0f", i, (double)tr[i] / (double)(tr[15] ? tr[15] : 1));
+            fprintf(stderr, "\n");
+            memset(tr, 0, sizeof tr);
+            CU(cudaMemcpyToSymbol(g_noinc_trace, tr, sizeof tr));
+        }
+#endif
         if (getenv("KMC_NOINC_DEBUG_TIME"))
             fprintf(stderr, "noinc enqueue: %.2f us per event\n", 1e6 * std::chrono::duration<double>(std::chrono::steady_clock::now() - dbg_t0).count() / (double)(nsteps ? nsteps : 1));
         h->swept = false; h->hier_valid = false; h->whier_valid = false;

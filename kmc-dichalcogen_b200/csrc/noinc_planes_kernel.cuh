@@ -13,6 +13,9 @@
 //   * the CTA that finishes last (a ticket per replica) is the selector: it sums the records, chooses the class
 //     (same fp64 sequence as every other kernel), finds record -> row -> slot -> cell -> bit with three dependent
 //     rounds of loads, and flips the touched bits of the planes (and their halo copies) with atomics.
+// Tried and dropped (profiles/README.md): a fixed selector CTA per replica; relaxed polling with back-off; a rolled
+// row loop in the enumeration (smaller code, but the loads no longer overlap: 16.5 vs 15.4 us); an unrolled one-shot
+// class choice (1200 straight-line instructions run once by a lone warp cost ~20 cycles of instruction fetch each).
 // (History: two launches -- 1024 CTAs of one row x 64 cells, then a one-CTA selection kernel with ~10 dependent L2
 // round trips -- took 10.8 + 11.4 us.)
 // Status bytes are only materialised (kmc_wide_unpack_kernel) when somebody asks for them.
@@ -22,6 +25,13 @@
 #include "replica_wide2_kernel.cuh"
 
 namespace kmc {
+
+#ifdef KMC_NOINC_TRACE
+__device__ long long g_noinc_trace[16];
+#define NTRACE(i) do { if (threadIdx.x == 0) atomicAdd((unsigned long long *)&g_noinc_trace[i], (unsigned long long)(clock64() - tr0)); } while (0)
+#else
+#define NTRACE(i) do { } while (0)
+#endif
 
 constexpr int PRC_STRIDE = 16;             // words per CTA record / classes per row-count plane
 constexpr int PNR = 2;                     // consecutive rows per warp in the enumeration
@@ -40,7 +50,7 @@ struct NoincPlanesParams {
     uint32_t *rowc;                      // [R][16][d0]   class-major row counts (classes 0..12; MM: 13, 14, 15)
     uint32_t *blk;                       // [R][nblk][16] per-CTA sums of the same
     unsigned long long *counts;          // [R][NCA] class totals of this event's enumeration (out)
-    unsigned int *ticket;                // [R] zero between launches
+    unsigned int *ticket;                // [R] arrivals; zero between launches
     unsigned int *epoch;                 // [R] persistent form: events of this call completed so far (zero on entry)
     int nblk, rpb, chunks, chunk_shift;
 };
@@ -238,13 +248,14 @@ __device__ __forceinline__ void noinc_record_none(const NoincParams &p, size_t i
 
 // ---- selection + move: the 256 threads of the replica's last CTA ---------------------------------------------------
 template <bool MM>
-__device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int rep, long long t)
+__device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int rep, long long t, unsigned long long step,
+                                              const double *s_u, long long tr0)
 {
+    (void)tr0;
     constexpr int NCX = MM ? NCA : NC;
     constexpr int NL = MM ? 32 : 16;
     const NoincParams &p = q.base;
     __shared__ uint32_t s_tot[8][PRC_STRIDE];               // per-warp class sums of the CTA records
-    __shared__ double s_u1, s_u2;
     __shared__ unsigned long long s_rank;
     __shared__ double s_total;
     __shared__ int s_csel, s_zero, s_tie, s_row, s_word, s_bit, s_layer1;
@@ -255,7 +266,6 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
     const size_t idx = (size_t)rep * (size_t)p.nsteps + (size_t)t;
     // ---- round 1 of loads: everything that does not depend on the enumeration's outcome, and the CTA records -------
     const uint32_t flag0 = p.flags[rep];
-    const unsigned long long step = p.steps_done[rep];
     double clk = 0.0;
     if (tid == 0 && p.clock) clk = p.clock[rep];
     u64 *P = q.planes + (size_t)rep * N_TYPES * d0 * We;
@@ -292,18 +302,8 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
         }
         if (lane < PRC_STRIDE) s_tot[tid >> 5][lane] = lane < (MM ? PRC_STRIDE : NC) ? mysum : 0u;
     }
-    // the draws do not depend on the lattice: warp 1 makes them while the sums settle
-    if (tid == 32) {
-        double u1, u2;
-        if (p.draws) {
-            const double2 u = *reinterpret_cast<const double2 *>(p.draws + idx * 2);
-            u1 = u.x; u2 = u.y;
-        } else {
-            kmc_draw(p.seed, p.replica0 + (uint32_t)rep, step, u1, u2);
-        }
-        s_u1 = u1; s_u2 = u2;
-    }
     __syncthreads();
+    NTRACE(2);
     if (tid < 32) {
         // class totals: lane c reads the table of class c (MM: 13, 14 -> 13, 14; 16 -> 15; 15 = 2 x classes 2..5)
         long long tot = 0;
@@ -316,24 +316,29 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
             }
         }
         if (lane < NCA) q.counts[(size_t)rep * NCA + lane] = lane < NCX ? (unsigned long long)tot : 0ull;
+        NTRACE(8);
         const int myc = lane < NCX ? lane : 0;
         const double rate = (lane < NCX && p.order_pos[myc] >= 0) ? p.rate[myc] : 0.0;
         const int pos = (lane < NCX && p.order_pos[myc] >= 0) ? p.order_pos[myc] : 100 + lane;
-        const double u1 = s_u1, u2 = s_u2;
+        const double u1 = s_u[0], u2 = s_u[1];             // (made at the top of the event, see the kernel)
         const double w = __dmul_rn((double)tot, rate);
         PickState pstate = pick_state_init_n<NL>(lane);
+        NTRACE(9);
         const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
+        NTRACE(10);
         if (p.log_mode == KMC_LOG_FULL && lane < NCA)
             (reinterpret_cast<kmc_event_full *>(p.events) + idx)->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
         const long long cnt = __shfl_sync(FULL, tot, pick.zero ? 0 : pick.csel);
         long long rr = (long long)__dmul_rn(u2, (double)cnt);
         if (rr > cnt - 1) rr = cnt - 1;
+        NTRACE(11);
         if (lane == 0) {
             s_csel = pick.csel; s_zero = pick.zero; s_tie = pick.tie != 0; s_total = pick.total;
             s_rank = (unsigned long long)(rr < 0 ? 0 : rr);
         }
     }
     __syncthreads();
+    NTRACE(3);
     if (s_zero) {
         if (tid == 0) {
             p.flags[rep] = flag0 | FLAG_ZERO_RATE;
@@ -392,6 +397,7 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
         }
     }
     __syncthreads();
+    NTRACE(4);
     const int row = s_row;
     u64 flip_m1 = 0;
 
@@ -449,6 +455,7 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
         }
     }
     __syncthreads();
+    NTRACE(5);
     uint32_t r = s_rin;
     int j = 0;
 #pragma unroll
@@ -476,6 +483,7 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
         }
     }
     __syncthreads();
+    NTRACE(6);
     const int col = 64 * s_word + s_bit;
     const int slot = class_slot_base(csel) + j;
     int s0;
@@ -504,6 +512,7 @@ __device__ __forceinline__ void planes_select(const NoincPlanesParams &q, int re
         }
     }
     __syncthreads();                                       // every read of the planes above is done
+    NTRACE(7);
     if (tid < 18) {
         const int i = tid / 6, pl = tid % 6;
         const int as = i == 0 ? row : (i == 1 ? mv.a1 : mv.a2), bc = i == 0 ? col : (i == 1 ? mv.b1 : mv.b2);
@@ -559,6 +568,8 @@ __global__ void __launch_bounds__(256, MM ? 2 : 4) kmc_noinc_planes_event_kernel
 {
     __shared__ uint32_t part[8][PNR][8];
     __shared__ int s_last, s_abort;
+    __shared__ double s_u[2];
+    __shared__ uint32_t s_touch;
     const int rep = q.base.n_replicas == 1 ? 0 : blockIdx.x / q.nblk, b = blockIdx.x - rep * q.nblk;
     if (!PERSIST) {
         // Programmatic dependent launch: the next event's CTAs may become resident while this grid runs (they hold at
@@ -567,8 +578,31 @@ __global__ void __launch_bounds__(256, MM ? 2 : 4) kmc_noinc_planes_event_kernel
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
         asm volatile("griddepcontrol.wait;" ::: "memory");
     }
+    // the replica's event counter when this launch started (a stopped replica does not advance it, nor does it use it)
+    const unsigned long long step0 = q.base.steps_done[rep];
+    if (threadIdx.x == 64) s_touch = MOVE_TABLE[0].w1;      // the selector reads the move table late: have it in the constant cache
     for (long long t = t0; t < t1; t++) {
+        // the event's draws depend on nothing the enumeration makes: one thread has them ready for the selector
+        const unsigned long long step = step0 + (unsigned long long)(t - t0);
+#ifdef KMC_NOINC_TRACE
+        const long long tr0 = clock64();
+#else
+        const long long tr0 = 0;
+#endif
+        if (threadIdx.x == 32) {
+            double u1, u2;
+            if (q.base.draws) {
+                const double2 u = *reinterpret_cast<const double2 *>(q.base.draws + ((size_t)rep * (size_t)q.base.nsteps + (size_t)t) * 2);
+                u1 = u.x; u2 = u.y;
+            } else {
+                kmc_draw(q.base.seed, q.base.replica0 + (uint32_t)rep, step, u1, u2);
+            }
+            s_u[0] = u1; s_u[1] = u2;
+        }
         planes_enumerate<MM>(q, rep, b, part);
+#ifdef KMC_NOINC_TRACE
+        const long long c0 = clock64() - tr0;
+#endif
         // row counts and the record are written; the barrier orders them before thread 0's release (cumulative),
         // the ticket with it: the CTA that draws the last ticket sees everything every CTA wrote
         __syncthreads();
@@ -579,14 +613,25 @@ __global__ void __launch_bounds__(256, MM ? 2 : 4) kmc_noinc_planes_event_kernel
             if (s_last) q.ticket[rep] = 0u;
         }
         __syncthreads();
+        // (A fixed selector -- the replica's CTA 0 waiting for all arrivals, to keep the selection code warm in one SM's
+        // instruction caches -- was tried: no faster, and it cannot overlap the next grid's start without persistence.)
         const bool last = s_last != 0;
-        if (last && q.base.stage < 2) planes_select<MM>(q, rep, t);
+#ifdef KMC_NOINC_TRACE
+        if (last && threadIdx.x == 0) {
+            atomicAdd((unsigned long long *)&g_noinc_trace[0], (unsigned long long)c0);
+            atomicAdd((unsigned long long *)&g_noinc_trace[1], (unsigned long long)(clock64() - tr0));
+            atomicAdd((unsigned long long *)&g_noinc_trace[15], 1ull);
+        }
+#endif
+        if (last && q.base.stage < 2) planes_select<MM>(q, rep, t, step, s_u, tr0);
         if (!PERSIST) return;
         __syncthreads();                                    // the selector's threads are through
+        if (last) NTRACE(12);
         if (threadIdx.x == 0) {
             int stalled = 0;
             if (last) {                                     // the move, the statistics and the ticket reset, then the epoch
                 asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(q.epoch + rep), "r"((unsigned)(t + 1)) : "memory");
+                NTRACE(13);
             } else {
                 unsigned int spins = 0, seen;
                 for (;;) {
