@@ -56,7 +56,7 @@ struct kmc_engine {
     uint32_t *d_rowmm = nullptr;             // [R][d0][4] MoveMonovacancy row counts of the aligned two-kernel sweep
     bool sweep_split = false;                // the last sweep left its row counts in d_rowcnt (stride 16) + d_rowmm
     unsigned long long *d_counts = nullptr;  // [R][13]
-    unsigned long long *d_acc = nullptr;     // [R][16] running totals of the aligned sweep (zero between launches)
+    unsigned long long *d_acc = nullptr;     // [R][32] running totals of the aligned sweep (zero between launches)
     unsigned int *d_ticket = nullptr;        // [R]
     unsigned long long *d_steps = nullptr, *d_hist = nullptr, *d_ties = nullptr, *d_hops = nullptr;
     uint32_t *d_flags = nullptr;
@@ -371,8 +371,10 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * (h->mm ? NSA : NS) * h->n));
         std::swap(h->d_slots, h->d_slots_alt);
     }
-    if (mm_split) {
-        if (!h->d_rowmm) CU(cudaMalloc(&h->d_rowmm, R * h->d0 * 4 * sizeof(uint32_t)));
+    // rows that fill a CTA: the rolling-window kernel does all 29 planes in one pass
+    const bool mm_fused = mm_split && cpr == 256 && h->sweep_variant == 0 && !getenv("KMC_SWEEP_MM_SPLIT");
+    if (mm_split && !h->d_rowmm) CU(cudaMalloc(&h->d_rowmm, R * h->d0 * 4 * sizeof(uint32_t)));
+    if (mm_split && !mm_fused) {
         CU(cudaMemsetAsync(h->d_rowmm, 0, R * h->d0 * 4 * sizeof(uint32_t), h->stream));
         SweepMMParams m;
         m.d0 = h->d0; m.d1 = h->d1; m.n = h->n; m.n_replicas = h->R;
@@ -388,9 +390,9 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     }
     if (aligned) {
         if (!h->d_acc) {
-            CU(cudaMalloc(&h->d_acc, R * 16 * sizeof(unsigned long long)));
+            CU(cudaMalloc(&h->d_acc, R * ROLL_ACC_STRIDE * sizeof(unsigned long long)));
             CU(cudaMalloc(&h->d_ticket, R * sizeof(unsigned int)));
-            CU(cudaMemsetAsync(h->d_acc, 0, R * 16 * sizeof(unsigned long long), h->stream));
+            CU(cudaMemsetAsync(h->d_acc, 0, R * ROLL_ACC_STRIDE * sizeof(unsigned long long), h->stream));
             CU(cudaMemsetAsync(h->d_ticket, 0, R * sizeof(unsigned int), h->stream));
         }
         if (cpr == 256 && h->sweep_variant == 0) {
@@ -418,8 +420,13 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
             q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
             q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
             q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc; q.nplanes = nsl;
-            if (with_slots) kmc_sweep_roll_kernel<true><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
-            else kmc_sweep_roll_kernel<false><<<(unsigned)(R * q.ctas_per_replica), 256, 0, h->stream>>>(q);
+            q.rowmm = mm_fused ? h->d_rowmm : nullptr;
+            const unsigned grid = (unsigned)(R * q.ctas_per_replica);
+            if (mm_fused) {
+                if (with_slots) kmc_sweep_roll_kernel<true, true><<<grid, 256, 0, h->stream>>>(q);
+                else kmc_sweep_roll_kernel<false, true><<<grid, 256, 0, h->stream>>>(q);
+            } else if (with_slots) kmc_sweep_roll_kernel<true><<<grid, 256, 0, h->stream>>>(q);
+            else kmc_sweep_roll_kernel<false><<<grid, 256, 0, h->stream>>>(q);
             CU(cudaGetLastError());
             h->launches += 1;
             return KMC_OK;

@@ -696,6 +696,81 @@ __global__ void __launch_bounds__(256, KMC_SWEEP_OCC) kmc_sweep16n_kernel(const 
 }
 #endif  // __CUDACC__
 
+
+// ---- MoveMonovacancy planes on the nibble layout (fused into the rolling-window kernel) ----------------------------
+// Per site (nibble) three target-side flags travel together in one word T: bit 0 = its layer set is defined and lacks
+// layer 1, bit 1 = defined and lacks layer 2, bit 2 = defined and not pristine.  One funnel shift moves all three to
+// the neighbour's position.  With the source flags l1 (layer 1 vacant), l2 << 1 and the divacancy bit placed in the
+// free bit, one LOP3 per layer gives the PRMT selector: layer 1 index = exists + 2 divacancy + 4 non-pristine, layer 2
+// index = divacancy + 2 exists + 4 non-pristine; the table bytes are the class codes 13 + 2 divacancy + non-pristine.
+constexpr uint32_t TWOSN = 0x22222222u, FOURSN = 0x44444444u;
+__host__ __device__ __forceinline__ uint32_t mm_target_word(uint32_t n) {
+    const uint32_t e0 = n & ONESN, e1 = (n >> 1) & ONESN, hi = ((n >> 2) | (n >> 3)) & ONESN;
+    const uint32_t def = hi ^ ONESN;
+    return (def & ~e0) | ((def & ~e1) << 1) | ((def & (e0 | e1)) << 2);
+}
+struct MMTargets { uint32_t t[4]; };          // target words of a row around the chunk: prev, own0, own1, next
+struct MMNibAcc { uint32_t e1, e2, n1, n2; };  // per-nibble sums over the directions: exists (layer 1 | layer 2 at bit 1), same & non-pristine
+
+#ifdef __CUDACC__
+template <bool STORE>
+__device__ __forceinline__ void mm_emit(uint4 *O, size_t cpl, int k, const uint32_t T[2], const uint32_t m1[2], const uint32_t m2[2],
+                                        const uint32_t dv[2], MMNibAcc acc[2])
+{
+    uint32_t o1[4], o2[4];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t s1 = (T[j] & m1[j]) | (dv[j] << 1), s2 = (T[j] & m2[j]) | dv[j];
+        acc[j].e1 += s1 & ONESN; acc[j].e2 += s2 & TWOSN;
+        acc[j].n1 += s1 & (T[j] >> 2) & ONESN; acc[j].n2 += s2 & (T[j] >> 1) & TWOSN;
+        if (STORE) {
+            o1[2 * j] = prmt(0x0FFF0DFFu, 0x10FF0EFFu, s1); o1[2 * j + 1] = prmt(0x0FFF0DFFu, 0x10FF0EFFu, s1 >> 16);
+            o2[2 * j] = prmt(0x0F0DFFFFu, 0x100EFFFFu, s2); o2[2 * j + 1] = prmt(0x0F0DFFFFu, 0x100EFFFFu, s2 >> 16);
+        }
+    }
+    if (STORE && O) {
+        KMC_SLOT_STORE(O + (size_t)(MM_SLOT0 + 2 * k) * cpl, make_uint4(o1[0], o1[1], o1[2], o1[3]));
+        KMC_SLOT_STORE(O + (size_t)(MM_SLOT0 + 2 * k + 1) * cpl, make_uint4(o2[0], o2[1], o2[2], o2[3]));
+    }
+}
+// planes 17..28 of one 16-site chunk and its four MoveMonovacancy class counts (natural | merge << 16, split | swap << 16)
+// n0, n1: the chunk's own nibble words; rows a-1 (m), a (c), a+1 (p)
+template <bool STORE>
+__device__ __forceinline__ void sweep_chunk_mm(uint32_t n0, uint32_t n1, const MMTargets &m, const MMTargets &c, const MMTargets &p,
+                                               uint4 *O, size_t cpl, uint32_t &pk_nm, uint32_t &pk_ss)
+{
+    uint32_t m1[2], m2[2], dv[2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t n = j ? n1 : n0;
+        const uint32_t e0 = n & ONESN, e1 = (n >> 1) & ONESN, def = (((n >> 2) | (n >> 3)) & ONESN) ^ ONESN;
+        const uint32_t l1 = e0 & def, l2 = e1 & def;
+        m1[j] = l1 | FOURSN; m2[j] = (l2 << 1) | FOURSN; dv[j] = l1 & l2;
+    }
+    MMNibAcc acc[2] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    uint32_t T[2];
+    // neighbors_and_mutuals order: (-1,+1) (0,-1) (+1,0) (0,+1) (-1,0) (+1,-1); t[] = prev, own0, own1, next
+    T[0] = nshr(m.t[1], m.t[2], 1); T[1] = nshr(m.t[2], m.t[3], 1); mm_emit<STORE>(O, cpl, 0, T, m1, m2, dv, acc);
+    T[0] = nshl(c.t[0], c.t[1], 1); T[1] = nshl(c.t[1], c.t[2], 1); mm_emit<STORE>(O, cpl, 1, T, m1, m2, dv, acc);
+    T[0] = p.t[1];                  T[1] = p.t[2];                  mm_emit<STORE>(O, cpl, 2, T, m1, m2, dv, acc);
+    T[0] = nshr(c.t[1], c.t[2], 1); T[1] = nshr(c.t[2], c.t[3], 1); mm_emit<STORE>(O, cpl, 3, T, m1, m2, dv, acc);
+    T[0] = m.t[1];                  T[1] = m.t[2];                  mm_emit<STORE>(O, cpl, 4, T, m1, m2, dv, acc);
+    T[0] = nshl(p.t[0], p.t[1], 1); T[1] = nshl(p.t[1], p.t[2], 1); mm_emit<STORE>(O, cpl, 5, T, m1, m2, dv, acc);
+    // per nibble: X = moves of the site (<= 12), XN = those onto a non-pristine neighbour; split by the source kind
+    uint32_t sx = 0, sxn = 0, sxd = 0, sxnd = 0;
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t X = acc[j].e1 + (acc[j].e2 >> 1), XN = acc[j].n1 + (acc[j].n2 >> 1), dm = dv[j] * 15u;
+        const uint32_t Xd = X & dm, XNd = XN & dm;
+        sx += (X & 0x0F0F0F0Fu) + ((X >> 4) & 0x0F0F0F0Fu);      sxn += (XN & 0x0F0F0F0Fu) + ((XN >> 4) & 0x0F0F0F0Fu);
+        sxd += (Xd & 0x0F0F0F0Fu) + ((Xd >> 4) & 0x0F0F0F0Fu);   sxnd += (XNd & 0x0F0F0F0Fu) + ((XNd >> 4) & 0x0F0F0F0Fu);
+    }
+    const uint32_t tx = (sx * ONES) >> 24, txn = (sxn * ONES) >> 24, txd = (sxd * ONES) >> 24, txnd = (sxnd * ONES) >> 24;
+    pk_nm = (tx - txn - txd + txnd) | ((txn - txnd) << 16);       // natural | merge-divacancy
+    pk_ss = (txd - txnd) | (txnd << 16);                          // split-divacancy | swap-divacancy
+}
+#endif
+
 #ifdef __CUDACC__
 // ---- rolling window over rows -----------------------------------------------------------------------------
 // For rows that fill a whole CTA (d1 = 4096: 256 threads x 16 sites).  A CTA walks `rows_per_cta`
@@ -713,10 +788,14 @@ __device__ __forceinline__ RowRaw load_row_raw(const uint8_t *S, int d1, int a, 
     w.next = __ldg(reinterpret_cast<const uint32_t *>(r + cin));
     return w;
 }
-__device__ __forceinline__ RowRec make_row(const RowRaw &w) {
+// MM: also the row's MoveMonovacancy target words (see mm_target_word)
+template <bool MM>
+__device__ __forceinline__ RowRec make_row(const RowRaw &w, MMTargets &t) {
     RowRec r;
     r.n0 = pack_nib(w.own.x, w.own.y); r.n1 = pack_nib(w.own.z, w.own.w);
-    r.prev = nzd(pack_nib(0u, w.prev)); r.own0 = nzd(r.n0); r.own1 = nzd(r.n1); r.next = nzd(pack_nib(w.next, 0u));
+    const uint32_t np = pack_nib(0u, w.prev), nn = pack_nib(w.next, 0u);
+    r.prev = nzd(np); r.own0 = nzd(r.n0); r.own1 = nzd(r.n1); r.next = nzd(nn);
+    if (MM) { t.t[0] = mm_target_word(np); t.t[1] = mm_target_word(r.n0); t.t[2] = mm_target_word(r.n1); t.t[3] = mm_target_word(nn); }
     return r;
 }
 
@@ -725,21 +804,25 @@ struct SweepRollParams {
     const uint8_t *status;
     uint8_t *slots;
     uint32_t *rowcnt;
-    unsigned long long *acc;
+    unsigned long long *acc;            // [R][ROLL_ACC_STRIDE] running class totals, zero between launches
     unsigned int *ticket;
     unsigned long long *counts;
     int rows_per_cta, ctas_per_replica;
     int nplanes;
+    uint32_t *rowmm;                    // MM: [R][d0][4] row counts of the four MoveMonovacancy classes (plain stores)
 };
 constexpr int ROLL_MAX_ROWS = 16;
+constexpr int ROLL_ACC_STRIDE = 32;
 
 #ifndef KMC_ROLL_OCC
 #define KMC_ROLL_OCC 3
 #endif
-template <bool STORE>
-__global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const SweepRollParams p)
+// MM = true: every rule of config/WSe2.yaml in ONE pass -- the 17 planes and 13 classes above plus the twelve
+// MoveMonovacancy planes (17..28) and its four classes from the same registers (30 algorithmic bytes per site).
+template <bool STORE, bool MM = false>
+__global__ void __launch_bounds__(256, MM ? 2 : KMC_ROLL_OCC) kmc_sweep_roll_kernel(const SweepRollParams p)
 {
-    __shared__ uint32_t part[ROLL_MAX_ROWS][8][8];       // [row step][warp][7 count pairs]
+    __shared__ uint32_t part[ROLL_MAX_ROWS][8][MM ? 10 : 8];       // [row step][warp][7 (MM: 9) count pairs]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d0 = p.d0, d1 = p.d1;
     const int cpr = d1 >> 4;                              // == 256
@@ -751,10 +834,11 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
     const uint8_t *S = p.status + (size_t)rep * p.n;
     auto wrap = [d0](int a) { return a < 0 ? a + d0 : (a >= d0 ? a - d0 : a); };
 
-    RowRec rm = make_row(load_row_raw(S, d1, wrap(a0 - 1), ci, cim, cin));
-    RowRec rc = make_row(load_row_raw(S, d1, a0, ci, cim, cin));
-    RowRec rp = make_row(load_row_raw(S, d1, wrap(a0 + 1), ci, cim, cin));
-    RowRec rq = make_row(load_row_raw(S, d1, wrap(a0 + 2), ci, cim, cin));
+    MMTargets tm, tc, tp, tq;
+    RowRec rm = make_row<MM>(load_row_raw(S, d1, wrap(a0 - 1), ci, cim, cin), tm);
+    RowRec rc = make_row<MM>(load_row_raw(S, d1, a0, ci, cim, cin), tc);
+    RowRec rp = make_row<MM>(load_row_raw(S, d1, wrap(a0 + 1), ci, cim, cin), tp);
+    RowRec rq = make_row<MM>(load_row_raw(S, d1, wrap(a0 + 2), ci, cim, cin), tq);
     for (int i = 0; i < nrows; i++) {
         const int a = a0 + i;
         // prefetch the row that enters the window next
@@ -766,17 +850,20 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
         k.p[0] = rp.prev; k.p[1] = rp.own0; k.p[2] = rp.own1;
         k.q[0] = rq.prev.div; k.q[1] = rq.own0.div; k.q[2] = rq.own1.div;
         uint4 *O = (STORE && p.slots) ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + ((size_t)a * cpr + ci) : nullptr;
-        uint32_t pk[7];
+        uint32_t pk[MM ? 9 : 7];
         sweep_chunk_n<STORE>(k, O, (size_t)cpl, pk);
+        if (MM) sweep_chunk_mm<STORE>(rc.n0, rc.n1, tm, tc, tp, O, (size_t)cpl, pk[MM ? 7 : 0], pk[MM ? 8 : 0]);
 #pragma unroll
-        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
-        if (lane < 7) {
+        for (int j = 0; j < (MM ? 9 : 7); j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
+        if (lane < (MM ? 9 : 7)) {
             uint32_t v = pk[0];
 #pragma unroll
-            for (int j = 1; j < 7; j++) v = lane == j ? pk[j] : v;
+            for (int j = 1; j < (MM ? 9 : 7); j++) v = lane == j ? pk[j] : v;
             part[i][warp][lane] = v;
         }
-        rm = rc; rc = rp; rp = rq; rq = make_row(nxt);
+        rm = rc; rc = rp; rp = rq;
+        if (MM) { tm = tc; tc = tp; tp = tq; }
+        rq = make_row<MM>(nxt, tq);
     }
     __syncthreads();
     // row counts: thread (row step i, field f) sums the 8 warps' partials; plain stores
@@ -791,17 +878,27 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
         mine = sum;
     }
     // class totals of this CTA: reduce over its rows (threads with the same f), then running totals + ticket
-    __shared__ unsigned long long tot_sm[16];
-    if (tid < 16) tot_sm[tid] = 0;
+    __shared__ unsigned long long tot_sm[20];
+    if (tid < 20) tot_sm[tid] = 0;
     __syncthreads();
     if (tid < nrows * RCG_STRIDE && mine) atomicAdd(&tot_sm[tid & 15], mine);
+    if (MM && tid < nrows * 4) {
+        // the four MoveMonovacancy classes: their own row table (a 16-word row of `rowcnt` holds the other 13)
+        const int i = tid >> 2, f = tid & 3;
+        uint32_t sum = 0;
+        for (int w = 0; w < 8; w++) { const uint32_t v = part[i][w][7 + (f >> 1)]; sum += (f & 1) ? (v >> 16) : (v & 0xFFFFu); }
+        p.rowmm[((size_t)rep * d0 + a0 + i) * 4 + f] = sum;
+        if (sum) atomicAdd(&tot_sm[16 + f], (unsigned long long)sum);
+    }
     __syncthreads();
     if (tid < 32) {
-        const unsigned long long sum = tid < NC ? tot_sm[tid] : 0ull;
+        // lane c = class c (MM: classes 13..16 sit in tot_sm[16..19])
+        constexpr int NCX = MM ? NCA : NC;
+        const unsigned long long sum = tid < NC ? tot_sm[tid] : ((MM && tid < NCA) ? tot_sm[16 + tid - NC] : 0ull);
         if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NCA + tid] = sum;
+            if (tid < NCX) p.counts[(size_t)rep * NCA + tid] = sum;
         } else {
-            if (tid < NC && sum) atomicAdd(&p.acc[(size_t)rep * 16 + tid], sum);
+            if (tid < NCX && sum) atomicAdd(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], sum);
             __syncwarp();
             unsigned int last = 0;
             if (tid == 0) {
@@ -811,7 +908,7 @@ __global__ void __launch_bounds__(256, KMC_ROLL_OCC) kmc_sweep_roll_kernel(const
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NCX) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }

@@ -409,7 +409,7 @@ def test_sweep_matches_oracle(dim, variant):
 
 
 @pytest.mark.parametrize("dim", [(8, 8), (64, 64), (16, 20), (5, 7), (9, 11), (7, 130), (128, 32), (300, 260), (37, 1024),
-                                 (64, 1024), (16, 4096), (512, 512), (256, 16), (8, 8192)])
+                                 (64, 1024), (16, 4096), (37, 4096), (5, 4096), (512, 4096), (512, 512), (256, 16), (8, 8192)])
 def test_sweep_with_move_monovacancy_matches_oracle(dim):
     """All nine rules: 29 slot planes, 17 classes, per-row counts."""
     sts = [evolved_state(dim, 3, rates=MM_RATES, order=MM_ORDER) if dim[0] * dim[1] <= 4096 else iid_state(dim, 3),
@@ -441,6 +441,29 @@ def test_sweep_full_size_4096():
     slots = eng.slots()[0]
     assert (slots == ws).all()
     eng.close()
+
+
+def test_sweep_full_size_4096_every_rule():
+    """BASELINE config 4 with config/WSe2.yaml's full rule set: 29 planes, 17 classes in ONE pass of the rolling-window
+    kernel; the split form (17-plane kernel + MoveMonovacancy companion) must give the same bytes."""
+    import os
+    dim = (4096, 4096)
+    st = iid_state(dim, 20261020)
+    ws, wc, wr = ko.sweep(st, dim)
+    for split in (False, True):
+        if split:
+            os.environ["KMC_SWEEP_MM_SPLIT"] = "1"
+        try:
+            eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=1)
+            eng.upload_state(st)
+            eng.sweep()
+            eng.sweep()         # twice: the running totals / ticket return to zero between launches
+            assert (eng.counts()[0] == wc).all()
+            assert (eng.row_counts()[0] == wr).all()
+            assert (eng.slots()[0] == ws).all()
+            eng.close()
+        finally:
+            os.environ.pop("KMC_SWEEP_MM_SPLIT", None)
 
 
 @pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 60)])
