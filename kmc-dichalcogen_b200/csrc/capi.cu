@@ -668,6 +668,18 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         }
         CU(cudaGetLastError());
         h->launches += 1;
+#ifdef KMC_WIDE_TRACE
+        {
+            long long tr[16];
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaMemcpyFromSymbol(tr, g_wide_trace, sizeof tr));
+            fprintf(stderr, "wide2 trace (cycles since the start of the event, mean of %lld events of replica 0):", tr[15]);
+            for (int i = 1; i < 8; i++) fprintf(stderr, " %d:%.0f", i, (double)tr[i] / (double)(tr[15] ? tr[15] : 1));
+            fprintf(stderr, "\n");
+            memset(tr, 0, sizeof tr);
+            CU(cudaMemcpyToSymbol(g_wide_trace, tr, sizeof tr));
+        }
+#endif
         if (validate) {          // the incrementally maintained row table against a fresh one from the planes
             if (!h->d_whier_chk) CU(cudaMalloc(&h->d_whier_chk, hier_elems * sizeof(uint16_t)));
             const long long rows = (long long)h->R * h->d0;

@@ -20,6 +20,15 @@
 
 namespace kmc {
 
+// -DKMC_WIDE_TRACE: thread 0 of CTA 0 adds the cycles since the start of the event after each of the six barriers to
+// g_wide_trace (slot 15 counts the events); capi.cu prints the averages after a launch.
+#ifdef KMC_WIDE_TRACE
+__device__ long long g_wide_trace[16];
+#define WTRACE(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&g_wide_trace[i], (unsigned long long)(clock64() - wtr0)); } while (0)
+#else
+#define WTRACE(i) do { } while (0)
+#endif
+
 // Row tables: one per class of the reference's own rules; with MoveMonovacancy (MM build) three more -- natural (13),
 // merge-divacancy (14), swap-divacancy (15th table, class 16); split-divacancy (class 15) has none: its row count
 // is twice the sum of the row's four MoveDivacancy counts (see replica_hw_kernel.cuh).
@@ -167,6 +176,10 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
     uint32_t flag = 0;
 
     for (; t < p.nsteps; t++) {
+#ifdef KMC_WIDE_TRACE
+        const long long wtr0 = clock64();
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&g_wide_trace[15], 1ull);
+#endif
         // ================= phase 1 (warp 0): draws, class choice, row ===================================
         if (warp == 0) {
             if ((t & 31) == 0) {
@@ -185,6 +198,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             const double u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
             const double w = __dmul_rn((double)tot, rate);
             const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
+            WTRACE(7);
             if (p.log_mode == KMC_LOG_FULL && !pick.zero) {
                 kmc_event_full *rec = reinterpret_cast<kmc_event_full *>(p.events) +
                                       ((size_t)rep * (size_t)p.nsteps + (size_t)t);
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
         }
         if (tid < 12) s_slot_tot[tid] = 0;
         __syncthreads();                                               // B1
+        WTRACE(1);
         if (s_zero) {                                                  // kmc.py:31-32: nothing can happen
             flag |= FLAG_ZERO_RATE;
             if (p.log_mode != KMC_LOG_NONE && tid == 0) {
@@ -319,6 +334,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             }
         }
         __syncthreads();                                               // B2
+        WTRACE(2);
         uint32_t r = s_rin;
         int j = 0;
 #pragma unroll
@@ -347,6 +363,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             }
         }
         __syncthreads();                                               // B3
+        WTRACE(3);
         const int col = s_col, s0 = s_s0;
         const int slot = class_slot_base(csel) + j;
         const int site = row * d1 + col;
@@ -457,6 +474,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             tot += dsum;
         }
         __syncthreads();                                               // B4: every before-load has its data
+        WTRACE(4);
 
         // ================= phase 4 (warp 7): rewrite the planes; lane pl < 6 owns plane pl ===========================
         if (warp == 7 && lane < N_TYPES) {
@@ -483,6 +501,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             __threadfence_block();
         }
         __syncthreads();                                               // B5: the new planes are visible
+        WTRACE(5);
 
         // ================= phase 5: after-counts, differences to the row table and the class totals ================
         if (warp < 7) {
@@ -543,6 +562,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             }
         }
         __syncthreads();                                               // B6
+        WTRACE(6);
         if (warp == 0) {
             int d = 0;
             if (lane >= C_MOVE_DIV && lane <= C_CREATE_TREF) d = s_delta[lane];

@@ -4,6 +4,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "kmc-dichalcogen_b200"))
 import numpy as np
 import bench
+if os.environ.get("KMC_LIB"):
+    import demo1._native as _n
+    _n.LIB_PATH = os.path.abspath(os.environ["KMC_LIB"])
 from demo1.engine import Engine
 nrep, ev = 128, 1000
 lat = Engine((1024, 1024), bench.wse2_rates(), bench.WSE2_ORDER, n_replicas=nrep)
