@@ -145,7 +145,10 @@ int kmc_check_status(kmc_engine *h);
 int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot);
 
 /* The `--no-incremental` event (sim.py:114-143) on a lattice of any size held in HBM: full sweep,
- * class selection + hierarchical in-class rank search, apply.  Same draws and records as kmc_run. */
+ * class selection + hierarchical in-class rank search, apply.  Same draws and records as kmc_run.  At most 2^30
+ * events per call (KMC_ERR_ARG beyond that).  Lattices of 65536 sites and more run on bit planes, one kernel per
+ * event -- one cooperative launch for the whole call when all its CTAs can be resident; the status bytes are
+ * brought up to date when they are asked for. */
 int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
                   void *events);
 /* the same event with the caller's draws u[n_replicas][nsteps][2] (the kmc_step_draws seam on this path) */

@@ -940,6 +940,7 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
 {
     int rc;
     if (nsteps < 0) return fail(KMC_ERR_ARG, "nsteps must be >= 0");
+    if (nsteps > (1ll << 30)) return fail(KMC_ERR_ARG, "at most 2^30 no-incremental events per call: split the run");
     if (log_mode < 0 || log_mode > 2) return fail(KMC_ERR_ARG, "bad log_mode");
     if (log_mode != KMC_LOG_NONE && !events) return fail(KMC_ERR_ARG, "log_mode set but events buffer is null");
     const size_t rs = record_size(log_mode);
