@@ -53,3 +53,12 @@ soak((64, 64), 296, 1, 5, 10000, [0, 295], rates=MM_RATES, order=MM_ORDER)
 soak((200, 200), 148, 5, 10, 10000, [0, 147], env={"KMC_WIDE_CTA": "1"})
 soak((1024, 1024), 32, 5, 4, 10000, [0, 31], env={"KMC_WIDE_CTA": "1"})
 soak((300, 260), 4, 0, 4, 2000, [0, 3], env={"KMC_NOINC_PLANES": "1"}, noinc=True)
+# the one-kernel no-incremental event: cooperative launch per call, per-event launches, several replicas, every rule
+soak((512, 512), 3, 0, 3, 3000, [0, 2], env={"KMC_NOINC_PLANES": "1"}, noinc=True)
+soak((512, 512), 3, 0, 2, 2000, [0, 2], env={"KMC_NOINC_PLANES": "1", "KMC_NOINC_NO_PERSIST": "1"}, noinc=True)
+os.environ.pop("KMC_NOINC_NO_PERSIST", None)
+soak((300, 260), 5, 0, 3, 2000, [0, 4], rates=MM_RATES, order=MM_ORDER, env={"KMC_NOINC_PLANES": "1"}, noinc=True)
+soak((1024, 1100), 2, 0, 2, 1500, [0, 1], rates=wse2_full_rates(1500.0), order=WSE2_FULL_ORDER, noinc=True)
+# MoveMonovacancy on the warp-per-replica bit-plane kernel and on the CTA-per-replica wide kernel
+soak((64, 64), 1024, 2, 10, 10000, [0, 1023], rates=MM_RATES, order=MM_ORDER)
+soak((200, 200), 64, 5, 10, 10000, [0, 63], rates=MM_RATES, order=MM_ORDER)
