@@ -1140,6 +1140,32 @@ def test_no_incremental_on_planes_matches_oracle(dim, nsteps, rules, monkeypatch
     eng.close()
 
 
+@pytest.mark.parametrize("launch", ["cooperative", "per_event_pdl", "per_event_plain"])
+@pytest.mark.parametrize("dim", [(300, 260), (512, 4096)])
+def test_plane_no_incremental_launch_forms_agree(dim, launch, monkeypatch):
+    """The same event kernel runs as one cooperative launch per call (epoch hand-over between events) or as one launch
+    per event, with or without programmatic dependent launch: same records, same lattices, three replicas."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    if launch != "cooperative":
+        monkeypatch.setenv("KMC_NOINC_NO_PERSIST", "1")
+    if launch == "per_event_plain":
+        monkeypatch.setenv("KMC_NOINC_NO_PDL", "1")
+    nsteps = 60
+    sts = np.stack([iid_state(dim, 40 + r, p=(0.80, 0.05, 0.05, 0.10)) for r in range(3)])
+    eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=3)
+    eng.upload_state(sts)
+    ev = np.concatenate([eng.run_noinc(1, 13, log_mode=nat.LOG_COMPACT),          # (a one-event call is never cooperative)
+                         eng.run_noinc(nsteps - 1, 13, log_mode=nat.LOG_COMPACT)], axis=1)
+    final = eng.download_state()
+    for r in range(3):
+        o = ko.Oracle(dim, MM_RATES, MM_ORDER, sts[r])
+        _, want = o.run_philox(13, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "%s replica %d" % (launch, r))
+        assert (final[r] == o.status()).all()
+    assert (eng.steps_done() == nsteps).all()
+    eng.close()
+
+
 @pytest.mark.parametrize("name", boundary_tie_names())
 def test_boundary_ties_on_the_plane_no_incremental_path(name, monkeypatch):
     monkeypatch.setenv("KMC_NOINC_PLANES", "1")
