@@ -983,13 +983,14 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
         q.base = p; q.planes = h->d_planes; q.rowc = h->d_prowc; q.blk = h->d_pblk; q.counts = h->d_counts;
         q.ticket = h->d_pticket; q.epoch = h->d_pepoch; q.nblk = nblk; q.rpb = rpb; q.chunks = chunks;
         q.chunk_shift = 0; while ((1 << q.chunk_shift) < chunks) q.chunk_shift++;
-        q.base.stage = getenv("KMC_NOINC_DEBUG_SKIP") ? atoi(getenv("KMC_NOINC_DEBUG_SKIP")) : 0;
+        q.base.stage = 0;
+        q.skip_select = getenv("KMC_NOINC_DEBUG_SKIP") ? 1 : 0;
         const bool pdl = !getenv("KMC_NOINC_NO_PDL");
         const auto dbg_t0 = std::chrono::steady_clock::now();
         // One cooperative launch for the whole call when every CTA can be resident at once (4096^2: 512 CTAs); else one
         // launch per event, chained by programmatic dependent launch.
         const unsigned grid = (unsigned)(h->R * nblk);
-        bool persist = nsteps >= 2 && !getenv("KMC_NOINC_NO_PERSIST") && q.base.stage == 0;
+        bool persist = nsteps >= 2 && !getenv("KMC_NOINC_NO_PERSIST") && !q.skip_select;
         if (persist) {
             int per_sm = 0, coop = 0;
             if (h->mm) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kmc_noinc_planes_event_kernel<true, true>, 256, 0));

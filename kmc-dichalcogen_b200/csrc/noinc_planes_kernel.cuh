@@ -53,6 +53,7 @@ struct NoincPlanesParams {
     unsigned int *ticket;                // [R] arrivals; zero between launches
     unsigned int *epoch;                 // [R] persistent form: events of this call completed so far (zero on entry)
     int nblk, rpb, chunks, chunk_shift;
+    int skip_select;                     // measurement only (KMC_NOINC_DEBUG_SKIP): enumerate, elect, do not select
 };
 
 // Word wc of a plane row and the low half of word wc + 1 (all that ever shifts into a window).  The neighbour lane
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(256, MM ? 2 : 4) kmc_noinc_planes_event_kernel
             atomicAdd((unsigned long long *)&g_noinc_trace[15], 1ull);
         }
 #endif
-        if (last && q.base.stage < 2) planes_select<MM>(q, rep, t, step, s_u, tr0);
+        if (last && !q.skip_select) planes_select<MM>(q, rep, t, step, s_u, tr0);
         if (!PERSIST) return;
         __syncthreads();                                    // the selector's threads are through
         if (last) NTRACE(12);
