@@ -347,8 +347,8 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas
     const int cpr = h->d1 >> 4;
     const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
-    // MoveMonovacancy live on an aligned shape (slot planes wanted): the 17-plane aligned kernel writes planes 0..16 of
-    // the 29-plane layout, its companion kmc_sweep_mm16_kernel planes 17..28 and the four MoveMonovacancy row counts
+    // MoveMonovacancy live on an aligned shape: the MoveMonovacancy builds of the nibble kernels write all 29 planes;
+    // the row counts are split over two tables, d_rowcnt [..][16] (classes 0..12) and d_rowmm [..][4] (classes 13..16)
     const bool mm_split = h->mm && aligned;
     h->sweep_split = mm_split;
     if (h->mm && !mm_split) {
@@ -371,23 +371,9 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         if (!h->d_slots_alt) CU(cudaMalloc(&h->d_slots_alt, R * (h->mm ? NSA : NS) * h->n));
         std::swap(h->d_slots, h->d_slots_alt);
     }
-    // rows that fill a CTA: the rolling-window kernel does all 29 planes in one pass
-    const bool mm_fused = mm_split && cpr == 256 && h->sweep_variant == 0 && !getenv("KMC_SWEEP_MM_SPLIT");
+    // (aligned shapes: the nibble kernels do all 29 planes in one pass; the four MoveMonovacancy row counts have their
+    // own table)
     if (mm_split && !h->d_rowmm) CU(cudaMalloc(&h->d_rowmm, R * h->d0 * 4 * sizeof(uint32_t)));
-    if (mm_split && !mm_fused) {
-        CU(cudaMemsetAsync(h->d_rowmm, 0, R * h->d0 * 4 * sizeof(uint32_t), h->stream));
-        SweepMMParams m;
-        m.d0 = h->d0; m.d1 = h->d1; m.n = h->n; m.n_replicas = h->R;
-        m.status = h->d_status; m.slots = with_slots ? h->d_slots : nullptr; m.rowmm = h->d_rowmm;
-        const long long chunks = (long long)R * (h->n >> 4);
-        kmc_sweep_mm16_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, h->stream>>>(m);
-        CU(cudaGetLastError());
-        // (the four MoveMonovacancy totals of every replica start from zero: strided 32-byte memset)
-        CU(cudaMemset2DAsync(h->d_counts + C_MOVE_MONO, NCA * sizeof(unsigned long long), 0, 4 * sizeof(unsigned long long), R, h->stream));
-        kmc_reduce_rowmm_kernel<<<dim3((unsigned)((h->d0 + 255) / 256), (unsigned)h->R), 256, 0, h->stream>>>(h->d_rowmm, h->d0, h->d_counts);
-        CU(cudaGetLastError());
-        h->launches += 2;
-    }
     if (aligned) {
         if (!h->d_acc) {
             CU(cudaMalloc(&h->d_acc, R * ROLL_ACC_STRIDE * sizeof(unsigned long long)));
@@ -420,9 +406,9 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
             q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
             q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
             q.rows_per_cta = rpc; q.ctas_per_replica = (h->d0 + rpc - 1) / rpc; q.nplanes = nsl;
-            q.rowmm = mm_fused ? h->d_rowmm : nullptr;
+            q.rowmm = mm_split ? h->d_rowmm : nullptr;
             const unsigned grid = (unsigned)(R * q.ctas_per_replica);
-            if (mm_fused) {
+            if (mm_split) {
                 if (with_slots) kmc_sweep_roll_kernel<true, true><<<grid, 256, 0, h->stream>>>(q);
                 else kmc_sweep_roll_kernel<false, true><<<grid, 256, 0, h->stream>>>(q);
             } else if (with_slots) kmc_sweep_roll_kernel<true><<<grid, 256, 0, h->stream>>>(q);
@@ -435,10 +421,11 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
         q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
         q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
-        q.ctas_per_replica = (h->n >> 4) / 256; q.nplanes = nsl;
+        q.ctas_per_replica = (h->n >> 4) / 256; q.nplanes = nsl; q.rowmm = mm_split ? h->d_rowmm : nullptr;
         const long long blocks = (long long)R * q.ctas_per_replica;
-        if (h->sweep_variant == 2) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
-        else kmc_sweep16n_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        if (mm_split) kmc_sweep16n_kernel<true><<<(unsigned)blocks, 256, 0, h->stream>>>(q);     // (variant 2 has no MoveMonovacancy build)
+        else if (h->sweep_variant == 2) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        else kmc_sweep16n_kernel<false><<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         CU(cudaGetLastError());
         h->launches += 1;
         return KMC_OK;

@@ -20,6 +20,7 @@
 namespace kmc {
 
 constexpr int RCG_STRIDE = 16;            // uint32 per row in the global row-count table
+constexpr int ROLL_ACC_STRIDE = 32;       // uint64 per replica in the running class totals of the aligned kernels
 constexpr uint32_t ONES = 0x01010101u;
 
 // per-byte flags (0x01 / 0x00) of a word of four status bytes (status < 16)
@@ -263,11 +264,12 @@ struct Sweep16Params {
     const uint8_t *status;             // [R][n]
     uint8_t *slots;                    // [R][17][n] or nullptr
     uint32_t *rowcnt;                  // [R][d0][16]
-    unsigned long long *acc;           // [R][16] running class totals, zero between launches
+    unsigned long long *acc;           // [R][ROLL_ACC_STRIDE] running class totals, zero between launches
     unsigned int *ticket;              // [R] CTAs finished, zero between launches
     unsigned long long *counts;        // [R][13] class totals (output)
     int ctas_per_replica;
     int nplanes;                       // planes per replica in `slots`: 17, or 29 when the MoveMonovacancy planes follow
+    uint32_t *rowmm;                   // MM build: [R][d0][4] row counts of the four MoveMonovacancy classes
 };
 
 #ifdef __CUDACC__
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
         if (p.ctas_per_replica == 1) {
             if (tid < NC) p.counts[(size_t)rep * NCA + tid] = s;
         } else {
-            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], s);
             __syncwarp();
             unsigned int last = 0;
             if (tid == 0) {
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }
@@ -404,38 +406,49 @@ __global__ void __launch_bounds__(256, 3) kmc_sweep16_kernel(const Sweep16Params
 #ifdef __CUDACC__
 // K2 epilogue shared by the aligned kernels: per-row class counts from each thread's 16-bit count
 // pairs, plain row stores, class totals via running totals + ticket (last CTA of a replica publishes).
-__device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint32_t *rows_sm, uint32_t pk[7],
+template <int NP>
+__device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint32_t *rows_sm, uint32_t *rows_mm, uint32_t pk[NP],
                                                     int tid, int lane, int cpr, int rows_in_cta, int row_local,
                                                     int rep, int a)
 {
+    constexpr bool MM = NP > 7;
+    constexpr int SCR = MM ? 12 : 8;                                        // scratch words per warp
     if (cpr >= 32) {
         // every warp lies inside one row: warp sums go to per-warp slots, no zeroing, no atomics
 #pragma unroll
-        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
-        if (lane < 7) {
+        for (int j = 0; j < NP; j++) pk[j] = __reduce_add_sync(0xFFFFFFFFu, pk[j]);
+        if (lane < NP) {
             uint32_t v = pk[0];
 #pragma unroll
-            for (int j = 1; j < 7; j++) v = lane == j ? pk[j] : v;
-            rows_sm[256 * RCG_STRIDE / 2 + (tid >> 5) * 8 + lane] = v;     // scratch in the upper half
+            for (int j = 1; j < NP; j++) v = lane == j ? pk[j] : v;
+            rows_sm[256 * RCG_STRIDE / 2 + (tid >> 5) * SCR + lane] = v;   // scratch in the upper half
         }
         __syncthreads();
         const int wpr = cpr >> 5;                                          // warps per row
+        uint32_t s = 0, s_mm = 0;
         if (tid < rows_in_cta * RCG_STRIDE) {
             const int r = tid >> 4, f = tid & 15;
-            uint32_t s = 0;
             if (f < 2 * 7)
                 for (int w = 0; w < wpr; w++) {
-                    const uint32_t v = rows_sm[256 * RCG_STRIDE / 2 + (r * wpr + w) * 8 + (f >> 1)];
+                    const uint32_t v = rows_sm[256 * RCG_STRIDE / 2 + (r * wpr + w) * SCR + (f >> 1)];
                     s += (f & 1) ? (v >> 16) : (v & 0xFFFFu);
                 }
-            rows_sm[tid] = f < NC ? s : 0u;
         }
+        if (MM && tid < rows_in_cta * 4) {
+            const int r = tid >> 2, f = tid & 3;
+            for (int w = 0; w < wpr; w++) {
+                const uint32_t v = rows_sm[256 * RCG_STRIDE / 2 + (r * wpr + w) * SCR + 7 + (f >> 1)];
+                s_mm += (f & 1) ? (v >> 16) : (v & 0xFFFFu);
+            }
+        }
+        if (tid < rows_in_cta * RCG_STRIDE) rows_sm[tid] = (tid & 15) < NC ? s : 0u;   // (rows_in_cta <= 8 here: below the scratch)
+        if (MM && tid < rows_in_cta * 4) rows_mm[tid] = s_mm;
         __syncthreads();
     } else {
         const uint32_t mask = __match_any_sync(0xFFFFFFFFu, row_local);
 #pragma unroll
-        for (int j = 0; j < 7; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
-        __syncthreads();                                                   // rows_sm zeroed by everyone
+        for (int j = 0; j < NP; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
+        __syncthreads();                                                   // rows_sm / rows_mm zeroed by everyone
         if ((__ffs(mask) - 1) == lane) {
             uint32_t *R = rows_sm + row_local * RCG_STRIDE;
 #pragma unroll
@@ -444,6 +457,15 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
                 if (lo) atomicAdd(R + 2 * j, lo);
                 if (hi) atomicAdd(R + 2 * j + 1, hi);
             }
+            if (MM) {
+                uint32_t *R4 = rows_mm + row_local * 4;
+#pragma unroll
+                for (int j = 7; j < NP; j++) {
+                    const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
+                    if (lo) atomicAdd(R4 + 2 * (j - 7), lo);
+                    if (hi) atomicAdd(R4 + 2 * (j - 7) + 1, hi);
+                }
+            }
         }
         __syncthreads();
     }
@@ -451,15 +473,22 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
         const int first_row = a - row_local;
         uint32_t *G = p.rowcnt + ((size_t)rep * p.d0 + first_row) * RCG_STRIDE;
         for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
+        if (MM) {
+            uint32_t *G4 = p.rowmm + ((size_t)rep * p.d0 + first_row) * 4;
+            for (int i = tid; i < rows_in_cta * 4; i += 256) G4[i] = rows_mm[i];
+        }
     }
     if (tid < 32) {
+        constexpr int NCX = MM ? NCA : NC;
         unsigned long long s = 0;
         if (tid < NC)
             for (int r = 0; r < rows_in_cta; r++) s += rows_sm[r * RCG_STRIDE + tid];
+        else if (MM && tid < NCA)
+            for (int r = 0; r < rows_in_cta; r++) s += rows_mm[r * 4 + tid - NC];
         if (p.ctas_per_replica == 1) {
-            if (tid < NC) p.counts[(size_t)rep * NCA + tid] = s;
+            if (tid < NCX) p.counts[(size_t)rep * NCA + tid] = s;
         } else {
-            if (tid < NC && s) atomicAdd(&p.acc[(size_t)rep * 16 + tid], s);
+            if (tid < NCX && s) atomicAdd(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], s);
             __syncwarp();
             unsigned int last = 0;
             if (tid == 0) {
@@ -469,7 +498,7 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
             }
             last = __shfl_sync(0xFFFFFFFFu, last, 0);
             if (last) {
-                if (tid < NC) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * 16 + tid], 0ull);
+                if (tid < NCX) p.counts[(size_t)rep * NCA + tid] = atomicExch(&p.acc[(size_t)rep * ROLL_ACC_STRIDE + tid], 0ull);
                 if (tid == 0) p.ticket[rep] = 0u;
             }
         }
@@ -647,56 +676,6 @@ __device__ __forceinline__ void sweep_chunk_n(const Chunk16N &k, uint4 *O, size_
     }
 }
 
-#ifndef KMC_SWEEP_OCC
-#define KMC_SWEEP_OCC 4
-#endif
-__global__ void __launch_bounds__(256, KMC_SWEEP_OCC) kmc_sweep16n_kernel(const Sweep16Params p)
-{
-    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
-    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
-    const int rows_in_cta = 256 / cpr;
-    const long long g = (long long)blockIdx.x * 256 + tid;
-    const int rep = (int)(g / cpl);
-    const int cl = (int)(g - (long long)rep * cpl);
-    const int a = cl / cpr, ci = cl - a * cpr;
-    const int row_local = tid / cpr;
-    const int d0 = p.d0;
-
-    Chunk16N k;
-    {
-        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
-        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
-        const uint8_t *S = p.status + (size_t)rep * p.n;
-        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
-        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
-        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
-        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
-        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
-        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
-        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
-        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
-        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
-        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
-        if (cpr < 32)
-            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
-        k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
-        k.c[0] = nzd(pack_nib(0u, c_prev)); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]);
-        k.c[3] = nzd(pack_nib(c_next, 0u));
-        k.m[0] = nzd(pack_nib(m4.x, m4.y)); k.m[1] = nzd(pack_nib(m4.z, m4.w)); k.m[2] = nzd(pack_nib(m_next, 0u));
-        k.p[0] = nzd(pack_nib(0u, p_prev)); k.p[1] = nzd(pack_nib(p4.x, p4.y)); k.p[2] = nzd(pack_nib(p4.z, p4.w));
-        k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
-        k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
-    }
-    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + cl : nullptr;
-    uint32_t pk[7];
-    sweep_chunk_n(k, O, (size_t)cpl, pk);
-    row_counts_epilogue(p, rows_sm, pk, tid, lane, cpr, rows_in_cta, row_local, rep, a);
-}
-#endif  // __CUDACC__
-
-
 // ---- MoveMonovacancy planes on the nibble layout (fused into the rolling-window kernel) ----------------------------
 // Per site (nibble) three target-side flags travel together in one word T: bit 0 = its layer set is defined and lacks
 // layer 1, bit 1 = defined and lacks layer 2, bit 2 = defined and not pristine.  One funnel shift moves all three to
@@ -771,6 +750,71 @@ __device__ __forceinline__ void sweep_chunk_mm(uint32_t n0, uint32_t n1, const M
 }
 #endif
 
+
+#ifndef KMC_SWEEP_OCC
+#define KMC_SWEEP_OCC 4
+#endif
+template <bool MM = false>
+__global__ void __launch_bounds__(256, MM ? 2 : KMC_SWEEP_OCC) kmc_sweep16n_kernel(const Sweep16Params p)
+{
+    __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
+    __shared__ uint32_t rows_mm[MM ? 256 * 4 : 1];          // MM: [rows_in_cta][4]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cpr = p.d1 >> 4;                  // 16-site chunks per row (divides 256)
+    const int cpl = p.n >> 4;                   // chunks per lattice (multiple of 256)
+    const int rows_in_cta = 256 / cpr;
+    const long long g = (long long)blockIdx.x * 256 + tid;
+    const int rep = (int)(g / cpl);
+    const int cl = (int)(g - (long long)rep * cpl);
+    const int a = cl / cpr, ci = cl - a * cpr;
+    const int row_local = tid / cpr;
+    const int d0 = p.d0;
+
+    Chunk16N k;
+    MMTargets tm, tc, tp;
+    {
+        const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1, ap2 = ap + 1 == d0 ? 0 : ap + 1;
+        const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
+        const uint8_t *S = p.status + (size_t)rep * p.n;
+        const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
+        const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
+        const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
+        const uint4 *rq = reinterpret_cast<const uint4 *>(S + (size_t)ap2 * p.d1);
+        const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci), q4 = __ldg(rq + ci);
+        const uint32_t c_prev = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3);
+        const uint32_t c_next = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
+        const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
+        const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
+        const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
+        if (cpr < 32) {
+            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
+            if (MM) for (int i = tid; i < rows_in_cta * 4; i += 256) rows_mm[i] = 0;
+        }
+        const uint32_t ncp = pack_nib(0u, c_prev), ncn = pack_nib(c_next, 0u);
+        const uint32_t nm0 = pack_nib(m4.x, m4.y), nm1 = pack_nib(m4.z, m4.w), nmn = pack_nib(m_next, 0u);
+        const uint32_t npp = pack_nib(0u, p_prev), np0 = pack_nib(p4.x, p4.y), np1 = pack_nib(p4.z, p4.w);
+        k.cn[0] = pack_nib(c4.x, c4.y); k.cn[1] = pack_nib(c4.z, c4.w);
+        k.c[0] = nzd(ncp); k.c[1] = nzd(k.cn[0]); k.c[2] = nzd(k.cn[1]); k.c[3] = nzd(ncn);
+        k.m[0] = nzd(nm0); k.m[1] = nzd(nm1); k.m[2] = nzd(nmn);
+        k.p[0] = nzd(npp); k.p[1] = nzd(np0); k.p[2] = nzd(np1);
+        k.q[0] = nzd(pack_nib(0u, q_prev)).div; k.q[1] = nzd(pack_nib(q4.x, q4.y)).div;
+        k.q[2] = nzd(pack_nib(q4.z, q4.w)).div;
+        if (MM) {
+            // MoveMonovacancy target words of rows a-1, a, a+1 (prev, own0, own1, next; the unused ends stay 0)
+            tm.t[0] = 0; tm.t[1] = mm_target_word(nm0); tm.t[2] = mm_target_word(nm1); tm.t[3] = mm_target_word(nmn);
+            tc.t[0] = mm_target_word(ncp); tc.t[1] = mm_target_word(k.cn[0]); tc.t[2] = mm_target_word(k.cn[1]); tc.t[3] = mm_target_word(ncn);
+            tp.t[0] = mm_target_word(npp); tp.t[1] = mm_target_word(np0); tp.t[2] = mm_target_word(np1); tp.t[3] = 0;
+        }
+    }
+    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + (size_t)rep * p.nplanes * p.n) + cl : nullptr;
+    uint32_t pk[MM ? 9 : 7];
+    sweep_chunk_n(k, O, (size_t)cpl, pk);
+    if (MM) sweep_chunk_mm<true>(k.cn[0], k.cn[1], tm, tc, tp, O, (size_t)cpl, pk[MM ? 7 : 0], pk[MM ? 8 : 0]);
+    row_counts_epilogue<MM ? 9 : 7>(p, rows_sm, rows_mm, pk, tid, lane, cpr, rows_in_cta, row_local, rep, a);
+}
+#endif  // __CUDACC__
+
+
 #ifdef __CUDACC__
 // ---- rolling window over rows -----------------------------------------------------------------------------
 // For rows that fill a whole CTA (d1 = 4096: 256 threads x 16 sites).  A CTA walks `rows_per_cta`
@@ -812,7 +856,6 @@ struct SweepRollParams {
     uint32_t *rowmm;                    // MM: [R][d0][4] row counts of the four MoveMonovacancy classes (plain stores)
 };
 constexpr int ROLL_MAX_ROWS = 16;
-constexpr int ROLL_ACC_STRIDE = 32;
 
 #ifndef KMC_ROLL_OCC
 #define KMC_ROLL_OCC 3
@@ -1029,124 +1072,6 @@ __global__ void __launch_bounds__(256) kmc_sweep_kernel_mm(const SweepParams p)
         if (out[j] != 0xFF) atomicAdd(R + out[j], 1u);
     }
 }
-// ---- MoveMonovacancy planes for aligned shapes: the companion of the 17-plane aligned kernels ---------------------
-// One thread = 16 consecutive sites of a row (one 128-bit load per neighbour row, twelve 128-bit streaming stores:
-// planes 17 + 2k + (L - 1)).  Byte-parallel: a 32-bit word holds four sites; a (direction, layer) slot exists where the
-// site's layer set contains L (bit L-1 of a status <= 3) and the neighbour's layer set is defined and lacks L; the class
-// code is 13 + 2 * (site is a divacancy) + (neighbour is not pristine).  12 algorithmic bytes per site on top of the
-// 18 of the 17-plane sweep.  Row counts of the four classes go to their own table rowmm [R][d0][4] (zero on entry).
-struct SweepMMParams {
-    int d0, d1, n, n_replicas;
-    const uint8_t *status;
-    uint8_t *slots;                    // [R][29][n] (planes 17..28 are written here) or nullptr
-    uint32_t *rowmm;                   // [R][d0][4]
-};
-struct MMFlags { uint32_t l1, l2, div, def, nz; };        // per byte 0/1: layer 1 / 2 vacant, divacancy, defined, non-pristine
-__device__ __forceinline__ MMFlags mm_flags(uint32_t w) {
-    const uint32_t e0 = w & ONES, e1 = (w >> 1) & ONES, hi = ((w >> 2) | (w >> 3)) & ONES;
-    MMFlags f;
-    f.def = hi ^ ONES; f.l1 = e0 & f.def; f.l2 = e1 & f.def; f.div = e0 & e1 & f.def; f.nz = (e0 | e1) & f.def;
-    return f;
-}
-__global__ void __launch_bounds__(256) kmc_sweep_mm16_kernel(const SweepMMParams p)
-{
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int cpr = p.d1 >> 4, cpl = p.n >> 4;
-    const long long g = (long long)blockIdx.x * 256 + tid;
-    const int rep = (int)(g / cpl);
-    if (rep >= p.n_replicas) return;
-    const int cl = (int)(g - (long long)rep * cpl);
-    const int a = cl / cpr, ci = cl - a * cpr;
-    const int d0 = p.d0;
-    const int am = a == 0 ? d0 - 1 : a - 1, ap = a + 1 == d0 ? 0 : a + 1;
-    const int cim = ci == 0 ? cpr - 1 : ci - 1, cin = ci + 1 == cpr ? 0 : ci + 1;
-    const uint8_t *S = p.status + (size_t)rep * p.n;
-    const uint4 *rm = reinterpret_cast<const uint4 *>(S + (size_t)am * p.d1);
-    const uint4 *r0 = reinterpret_cast<const uint4 *>(S + (size_t)a * p.d1);
-    const uint4 *rp = reinterpret_cast<const uint4 *>(S + (size_t)ap * p.d1);
-    const uint4 c4 = __ldg(r0 + ci), m4 = __ldg(rm + ci), p4 = __ldg(rp + ci);
-    // words of the three rows around the chunk: index 0 = the word before the chunk, 1..4 = the chunk, 5 = the word after
-    uint32_t cw[6], mw[6], pw[6];
-    cw[0] = __ldg(reinterpret_cast<const uint32_t *>(r0 + cim) + 3); cw[1] = c4.x; cw[2] = c4.y; cw[3] = c4.z; cw[4] = c4.w;
-    cw[5] = __ldg(reinterpret_cast<const uint32_t *>(r0 + cin));
-    mw[0] = 0; mw[1] = m4.x; mw[2] = m4.y; mw[3] = m4.z; mw[4] = m4.w; mw[5] = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
-    pw[0] = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3); pw[1] = p4.x; pw[2] = p4.y; pw[3] = p4.z; pw[4] = p4.w; pw[5] = 0;
-    uint4 *O = p.slots ? reinterpret_cast<uint4 *>(p.slots + ((size_t)rep * NSA + MM_SLOT0) * p.n) + cl : nullptr;
-    // source-site flags of the chunk's four words, hoisted out of the direction loop
-    uint32_t sl1[4], sl2[4], sd3[4], sbase[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const MMFlags sf = mm_flags(cw[j + 1]);
-        sl1[j] = sf.l1; sl2[j] = sf.l2; sd3[j] = sf.div * 3u;
-        sbase[j] = 0x0D0D0D0Du + 2u * sf.div;                       // 13 + 2 * divacancy per byte
-    }
-    // per-byte running sums of the four kinds (<= 2 per byte and step, 24 steps: no carries); one hsum each at the end
-    uint32_t a_nat = 0, a_mer = 0, a_spl = 0, a_swp = 0;
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        uint32_t o1[4], o2[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            // the neighbour word of direction k (neighbors_and_mutuals order: (-1,1) (0,-1) (1,0) (0,1) (-1,0) (1,-1))
-            uint32_t tw;
-            if (k == 0) tw = shr_sites(mw[j + 1], mw[j + 2], 1);
-            else if (k == 1) tw = shl_sites(cw[j], cw[j + 1], 1);
-            else if (k == 2) tw = pw[j + 1];
-            else if (k == 3) tw = shr_sites(cw[j + 1], cw[j + 2], 1);
-            else if (k == 4) tw = mw[j + 1];
-            else tw = shl_sites(pw[j], pw[j + 1], 1);
-            const MMFlags tf = mm_flags(tw);
-            const uint32_t ex1 = sl1[j] & tf.def & ~tf.l1, ex2 = sl2[j] & tf.def & ~tf.l2;
-            const uint32_t cls = sbase[j] + tf.nz;                             // + (neighbour is not pristine)
-            o1[j] = code(ex1, cls); o2[j] = code(ex2, cls);
-            const uint32_t ex = ex1 + ex2;                                     // 0, 1 or 2 per byte
-            const uint32_t z3 = tf.nz * 3u;
-            const uint32_t e_m = ex & ~sd3[j], e_d = ex & sd3[j];              // source monovacancy / divacancy
-            a_nat += e_m & ~z3; a_mer += e_m & z3; a_spl += e_d & ~z3; a_swp += e_d & z3;
-        }
-        if (O) {
-            __stcs(O + (size_t)(2 * k) * cpl, make_uint4(o1[0], o1[1], o1[2], o1[3]));
-            __stcs(O + (size_t)(2 * k + 1) * cpl, make_uint4(o2[0], o2[1], o2[2], o2[3]));
-        }
-    }
-    const uint32_t n_nat = hsum(a_nat), n_mer = hsum(a_mer), n_spl = hsum(a_spl), n_swp = hsum(a_swp);
-    // row counts: a warp lies inside one row when a row holds a multiple of 32 chunks; else every thread adds its own
-    uint32_t *R4 = p.rowmm + ((size_t)rep * d0 + a) * 4;
-    if ((cpr & 31) == 0) {
-        const uint32_t s01 = __reduce_add_sync(0xFFFFFFFFu, n_nat | (n_mer << 16));
-        const uint32_t s23 = __reduce_add_sync(0xFFFFFFFFu, n_spl | (n_swp << 16));
-        if (lane == 0) {
-            if (s01 & 0xFFFFu) atomicAdd(R4 + 0, s01 & 0xFFFFu);
-            if (s01 >> 16) atomicAdd(R4 + 1, s01 >> 16);
-            if (s23 & 0xFFFFu) atomicAdd(R4 + 2, s23 & 0xFFFFu);
-            if (s23 >> 16) atomicAdd(R4 + 3, s23 >> 16);
-        }
-    } else {
-        if (n_nat) atomicAdd(R4 + 0, n_nat);
-        if (n_mer) atomicAdd(R4 + 1, n_mer);
-        if (n_spl) atomicAdd(R4 + 2, n_spl);
-        if (n_swp) atomicAdd(R4 + 3, n_swp);
-    }
-}
-// class totals 13..16 per replica from rowmm: one thread per row (one 128-bit load), warp sums, one atomic per warp and
-// class into counts (the four entries must be zero on entry).  grid = (ceil(d0 / 256), R)
-__global__ void __launch_bounds__(256) kmc_reduce_rowmm_kernel(const uint32_t *rowmm, int d0, unsigned long long *counts)
-{
-    const int rep = blockIdx.y;
-    const int a = blockIdx.x * 256 + threadIdx.x;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (a < d0) v = __ldg(reinterpret_cast<const uint4 *>(rowmm + ((size_t)rep * d0 + a) * 4));
-    const uint32_t s0 = __reduce_add_sync(0xFFFFFFFFu, v.x), s1 = __reduce_add_sync(0xFFFFFFFFu, v.y);
-    const uint32_t s2 = __reduce_add_sync(0xFFFFFFFFu, v.z), s3 = __reduce_add_sync(0xFFFFFFFFu, v.w);
-    if ((threadIdx.x & 31) == 0) {
-        unsigned long long *c = counts + (size_t)rep * NCA + C_MOVE_MONO;
-        if (s0) atomicAdd(c + 0, (unsigned long long)s0);
-        if (s1) atomicAdd(c + 1, (unsigned long long)s1);
-        if (s2) atomicAdd(c + 2, (unsigned long long)s2);
-        if (s3) atomicAdd(c + 3, (unsigned long long)s3);
-    }
-}
-
 __global__ void kmc_reduce_counts_mm_kernel(const uint32_t *rowcnt, int d0, int n_replicas, unsigned long long *counts)
 {
     const int rep = blockIdx.x;

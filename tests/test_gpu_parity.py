@@ -444,26 +444,21 @@ def test_sweep_full_size_4096():
 
 
 def test_sweep_full_size_4096_every_rule():
-    """BASELINE config 4 with config/WSe2.yaml's full rule set: 29 planes, 17 classes in ONE pass of the rolling-window
-    kernel; the split form (17-plane kernel + MoveMonovacancy companion) must give the same bytes."""
-    import os
+    """BASELINE config 4 with config/WSe2.yaml's full rule set: 29 planes, 17 classes in ONE pass -- the rolling-window
+    kernel (automatic) and the one-row-per-CTA nibble kernel (sweep variant 1) must both give the oracle's bytes."""
     dim = (4096, 4096)
     st = iid_state(dim, 20261020)
     ws, wc, wr = ko.sweep(st, dim)
-    for split in (False, True):
-        if split:
-            os.environ["KMC_SWEEP_MM_SPLIT"] = "1"
-        try:
-            eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=1)
-            eng.upload_state(st)
-            eng.sweep()
-            eng.sweep()         # twice: the running totals / ticket return to zero between launches
-            assert (eng.counts()[0] == wc).all()
-            assert (eng.row_counts()[0] == wr).all()
-            assert (eng.slots()[0] == ws).all()
-            eng.close()
-        finally:
-            os.environ.pop("KMC_SWEEP_MM_SPLIT", None)
+    for variant in (0, 1):
+        eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=1)
+        eng.set_sweep_kernel(variant)
+        eng.upload_state(st)
+        eng.sweep()
+        eng.sweep()         # twice: the running totals / ticket return to zero between launches
+        assert (eng.counts()[0] == wc).all()
+        assert (eng.row_counts()[0] == wr).all()
+        assert (eng.slots()[0] == ws).all()
+        eng.close()
 
 
 @pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 60)])
@@ -1198,8 +1193,8 @@ def test_plane_no_incremental_path_stops_on_zero_rate(monkeypatch):
 
 @pytest.mark.parametrize("dim", [(64, 64), (16, 4096), (128, 32)])
 def test_no_incremental_with_move_monovacancy_on_aligned_shapes(dim):
-    """Aligned shapes enumerate with the two-kernel sweep (17-plane kernel + MoveMonovacancy companion), whose
-    MoveMonovacancy row counts live in their own table: the no-incremental selection must read both."""
+    """Aligned shapes enumerate with the MoveMonovacancy builds of the nibble sweep kernels, whose MoveMonovacancy row
+    counts live in their own table: the no-incremental selection must read both."""
     st0 = exact_state(dim, 0.15, 0.15, 8)
     eng = Engine(dim, MM_RATES, MM_ORDER)
     eng.upload_state(st0)
