@@ -755,7 +755,7 @@ __device__ __forceinline__ void sweep_chunk_mm(uint32_t n0, uint32_t n1, const M
 #define KMC_SWEEP_OCC 4
 #endif
 template <bool MM = false>
-__global__ void __launch_bounds__(256, MM ? 2 : KMC_SWEEP_OCC) kmc_sweep16n_kernel(const Sweep16Params p)
+__global__ void __launch_bounds__(256, MM ? 4 : KMC_SWEEP_OCC) kmc_sweep16n_kernel(const Sweep16Params p)
 {
     __shared__ uint32_t rows_sm[256 * RCG_STRIDE];          // [rows_in_cta][16], rows_in_cta <= 256
     __shared__ uint32_t rows_mm[MM ? 256 * 4 : 1];          // MM: [rows_in_cta][4]
