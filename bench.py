@@ -573,20 +573,21 @@ def main():
         tc_order = [8, 9, 10, 11, 0, 2, 3, 4, 5, 6, 7]
         v, _ = timed_batch(tc_rates, tc_order, 1, 10000, 200000, dim=(200, 200), lattices=np.zeros((1, 200 * 200), dtype=np.uint8))
         other["200x200_testcfg_single_trajectory"] = {"events_per_s": v, "events": 200000}
-        # configs[3] end to end: one `--no-incremental` event on 4096^2 = full re-enumeration + select + apply.
-        # Without MoveMonovacancy the event runs on the bit-sliced lattice (noinc_planes_kernel.cuh); with it on the byte
-        # lattice (count-only 17-class sweep + MoveMonovacancy companion + block-wide selection)
+        # configs[3] end to end: one `--no-incremental` event on 4096^2 = full re-enumeration + select + apply, on the
+        # bit-sliced lattice (noinc_planes_kernel.cuh): one kernel per event; without MoveMonovacancy all CTAs fit on
+        # the device at once and the whole call is one cooperative launch
         for key, rts, odr in (("4096x4096_no_incremental_event", rates, order),
                               ("4096x4096_no_incremental_event_without_move_monovacancy", rates13, order13)):
             big = Engine(SWEEP_DIM, rts, odr, n_replicas=1, device=local)
             big.upload_state(iid_lattice(SWEEP_DIM, SEED))
             big.run_noinc(5, SEED)
             big.sync()
+            nev = 400
             big.timer_start()
-            big.run_noinc(40, SEED)
+            big.run_noinc(nev, SEED)
             msn = big.timer_stop()
             big.close()
-            other[key] = {"events_per_s": 40 / (msn * 1e-3), "ms_per_event": msn / 40}
+            other[key] = {"events_per_s": nev / (msn * 1e-3), "ms_per_event": msn / nev, "events": nev}
         # configs[4] shape: 1024x1024 lattices stay in HBM/L2 as bit planes, row tables in shared memory, one CTA per
         # replica (128 replicas = one GPU's share of the 1024 at 8 GPUs)
         nrep5, ev5 = 128, 4000
