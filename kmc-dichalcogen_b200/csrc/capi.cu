@@ -585,7 +585,9 @@ static int replica_launch(kmc_engine *h, long long nsteps, uint64_t seed, uint32
         const long long per_sm = bbytes <= (size_t)h->max_smem_optin ? (long long)((size_t)h->max_smem_optin / bbytes) : 0;
         // (and from about 215 x 215 sites even a single trajectory is faster here: the byte kernel's searches grow
         // with the row length, 3.1 / 3.5 / 4.0 / 5.1 us per event at 128 / 192 / 256 / 448 squared, this one stays at 3.7)
-        wide_auto = per_sm == 0 || (long long)h->R > per_sm * sms || h->n > 46000;
+        // (round 2, CTA-per-replica build, `profiles/probe_200.py`: the byte kernel's in-row search grows with the row
+        // length -- 3.3 / 3.5 / 3.65 / 3.9 us per event at 128 / 160 / 192 / 200 columns -- this one stays at 3.5-3.7 us)
+        wide_auto = per_sm == 0 || (long long)h->R > per_sm * sms || h->n > 46000 || (h->R <= sms && h->d1 >= 196);
     }
     if (h->variant == 5 || wide_auto) {
         const int Wa = wide_anchor_words(h->d1), We = wide_row_words(h->d1), d0p = (h->d0 + 1) & ~1;
