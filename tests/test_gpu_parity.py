@@ -443,6 +443,24 @@ def test_sweep_full_size_4096():
     eng.close()
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("dim", [(64, 64), (16, 4096), (128, 32), (256, 16), (8, 2048)])
+def test_sweep_with_move_monovacancy_on_the_forced_aligned_kernels(dim, variant):
+    """Sweep variants 1 and 2 with MoveMonovacancy enabled both run the MoveMonovacancy build of the 16-sites-per-thread
+    nibble kernel (the byte-parallel variant has none); three replicas, two launches."""
+    sts = [iid_state(dim, 11 + r, p=(0.6, 0.15, 0.15, 0.1)) for r in range(3)]
+    eng = Engine(dim, MM_RATES, MM_ORDER, n_replicas=3)
+    eng.set_sweep_kernel(variant)
+    eng.upload_state(np.stack(sts))
+    eng.sweep()
+    eng.sweep()
+    slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
+    for r in range(3):
+        ws, wc, wr = ko.sweep(sts[r], dim)
+        assert (slots[r] == ws).all() and (counts[r] == wc).all() and (rows[r] == wr).all()
+    eng.close()
+
+
 def test_sweep_full_size_4096_every_rule():
     """BASELINE config 4 with config/WSe2.yaml's full rule set: 29 planes, 17 classes in ONE pass -- the rolling-window
     kernel (automatic) and the one-row-per-CTA nibble kernel (sweep variant 1) must both give the oracle's bytes."""
