@@ -130,6 +130,13 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
     __shared__ uint32_t s_rin, s_slot_tot[12];
     __shared__ double s_total;
     __shared__ int s_delta[20];                             // class total changes of the refresh (classes 2..6, 13..16)
+    // speculative row search: warp 0 publishes the class totals and the in-class draw before it starts choosing the
+    // class; warps 1..6 each search the row of one candidate class (the six enabled classes with the highest rates)
+    // meanwhile.  If the chosen class is a candidate -- with DFT rates practically always -- its row is there when the
+    // class choice ends; otherwise warp 0 searches as before.
+    __shared__ int s_pub_tot[NCA], s_hit, s_spec_row[8];
+    __shared__ uint32_t s_spec_rin[8];
+    __shared__ double s_pub_u2;
 
     u64 *P = wp.planes + (size_t)rep * N_TYPES * d0 * We;
     WGeom G{P, d0, d1, Wa, We};
@@ -170,17 +177,65 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
     const TaskOps ops = task_ops(warp < 7 ? warp : 6);
     const int r2 = B > 32 ? B >> 5 : 1;
 
+    int my_cand = -1;                                      // warps 1..6: the class whose row this warp searches ahead
+    int cand_warp_of_my_class = -1;                        // warp 0, lane c: the warp that searches class c (or -1)
+    {
+        auto live = [&](int c) { return p.order_pos[c] >= 0 && p.rate[c] > 0.0; };
+        auto rate_rank = [&](int c) {                       // number of enabled classes that come before c by rate
+            int rk = 0;
+            for (int o = 0; o < NCX; o++)
+                if (o != c && live(o) && (p.rate[o] > p.rate[c] || (p.rate[o] == p.rate[c] && o < c))) rk++;
+            return rk;
+        };
+        for (int c = 0; c < NCX; c++)
+            if (live(c) && warp >= 1 && warp <= 6 && rate_rank(c) == warp - 1) my_cand = c;
+        if (lane < NCX && live(lane)) { const int rk = rate_rank(lane); if (rk < 6) cand_warp_of_my_class = rk + 1; }
+    }
     const unsigned long long step_base = p.steps_done[rep];
     double mu1 = 0.0, mu2 = 0.0;
     long long t = 0;
     uint32_t flag = 0;
 
+    // row and rank inside the row of the in-class draw u2 among the `cnt` moves of class c: one warp, two rank searches
+    // over the class's block sums and row counts in shared memory
+    auto row_search = [&](int c, int cnt, double u2v, int &row, uint32_t &r) {
+        long long rr = (long long)__dmul_rn(u2v, (double)cnt);
+        if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
+        r = (uint32_t)rr;
+        // row count of the class: its table, or (split-divacancy) twice the four MoveDivacancy tables
+        const bool split = MM && c == C_MOVE_MONO + 2;
+        const int tb = MM ? (split ? C_MOVE_DIV : wide_table_of(c)) : c;
+        auto blocksum = [&](int i) -> uint32_t {
+            return split ? 2u * (bs[C_MOVE_DIV * 32 + i] + bs[(C_MOVE_DIV + 1) * 32 + i] + bs[(C_MOVE_DIV + 2) * 32 + i] +
+                                 bs[(C_MOVE_DIV + 3) * 32 + i]) : bs[tb * 32 + i];
+        };
+        auto rowcount = [&](int a) -> uint32_t {
+            return split ? 2u * ((uint32_t)rc16[C_MOVE_DIV * d0p + a] + rc16[(C_MOVE_DIV + 1) * d0p + a] +
+                                 rc16[(C_MOVE_DIV + 2) * d0p + a] + rc16[(C_MOVE_DIV + 3) * d0p + a])
+                         : (uint32_t)rc16[tb * d0p + a];
+        };
+        int L = 0;
+        warp_rank_search(blocksum(lane), r, L, lane);
+        const int a0 = (L << bshift) + lane * r2;
+        uint32_t sum = 0;
+        for (int q = 0; q < r2; q++)
+            if (lane * r2 + q < B && a0 + q < d0) sum += rowcount(a0 + q);
+        int L2 = 0;
+        warp_rank_search(sum, r, L2, lane);
+        row = (L << bshift) + L2 * r2;
+        for (int q = 0; q < r2 - 1; q++) {
+            const uint32_t v = rowcount(row);
+            if (r < v) break;
+            r -= v; row++;
+        }
+    };
     for (; t < p.nsteps; t++) {
 #ifdef KMC_WIDE_TRACE
         const long long wtr0 = clock64();
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&g_wide_trace[15], 1ull);
 #endif
-        // ================= phase 1 (warp 0): draws, class choice, row ===================================
+        // ================= phase 1: draws and class choice (warp 0), row search (ahead: warps 1..6) =======
+        double u1 = 0.0, u2 = 0.0;
         if (warp == 0) {
             if ((t & 31) == 0) {
                 const long long tt = t + lane;
@@ -194,8 +249,16 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                     }
                 }
             }
-            const double u1 = __shfl_sync(FULL, mu1, (int)(t & 31));
-            const double u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
+            u1 = __shfl_sync(FULL, mu1, (int)(t & 31));
+            u2 = __shfl_sync(FULL, mu2, (int)(t & 31));
+            if (lane < NCX) s_pub_tot[lane] = tot;
+            if (lane == 0) s_pub_u2 = u2;
+        }
+        if (tid < 12) s_slot_tot[tid] = 0;
+        // B0 (warps 0..6 only: warp 7 is still writing the previous event's record and statistics, which overlaps the
+        // class choice): totals and the in-class draw are public
+        if (warp < 7) asm volatile("bar.sync 1, 224;" ::: "memory");
+        if (warp == 0) {
             const double w = __dmul_rn((double)tot, rate);
             const ClassPick pick = pick_class<NL>(w, pos, pstate, u1, lane);
             WTRACE(7);
@@ -204,47 +267,23 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
                                       ((size_t)rep * (size_t)p.nsteps + (size_t)t);
                 if (lane < NCA) rec->counts[lane] = lane < NCX ? (uint32_t)tot : 0u;
             }
-            int row = 0;
+            int row = 0, hit = -1;
             uint32_t r = 0;
             if (!pick.zero) {
-                const int csel = pick.csel;
-                const int cnt = __shfl_sync(FULL, tot, csel);
-                long long rr = (long long)__dmul_rn(u2, (double)cnt);
-                if (rr > (long long)cnt - 1) rr = (long long)cnt - 1;
-                r = (uint32_t)rr;
-                // row count of the chosen class: its table, or (split-divacancy) twice the four MoveDivacancy tables
-                const bool split = MM && csel == C_MOVE_MONO + 2;
-                const int tb = MM ? (split ? C_MOVE_DIV : wide_table_of(csel)) : csel;
-                auto blocksum = [&](int i) -> uint32_t {
-                    return split ? 2u * (bs[C_MOVE_DIV * 32 + i] + bs[(C_MOVE_DIV + 1) * 32 + i] + bs[(C_MOVE_DIV + 2) * 32 + i] +
-                                         bs[(C_MOVE_DIV + 3) * 32 + i]) : bs[tb * 32 + i];
-                };
-                auto rowcount = [&](int a) -> uint32_t {
-                    return split ? 2u * ((uint32_t)rc16[C_MOVE_DIV * d0p + a] + rc16[(C_MOVE_DIV + 1) * d0p + a] +
-                                         rc16[(C_MOVE_DIV + 2) * d0p + a] + rc16[(C_MOVE_DIV + 3) * d0p + a])
-                                 : (uint32_t)rc16[tb * d0p + a];
-                };
-                int L = 0;
-                warp_rank_search(blocksum(lane), r, L, lane);
-                const int a0 = (L << bshift) + lane * r2;
-                uint32_t sum = 0;
-                for (int q = 0; q < r2; q++)
-                    if (lane * r2 + q < B && a0 + q < d0) sum += rowcount(a0 + q);
-                int L2 = 0;
-                warp_rank_search(sum, r, L2, lane);
-                row = (L << bshift) + L2 * r2;
-                for (int q = 0; q < r2 - 1; q++) {
-                    const uint32_t v = rowcount(row);
-                    if (r < v) break;
-                    r -= v; row++;
-                }
+                hit = __shfl_sync(FULL, cand_warp_of_my_class, pick.csel);     // the warp that searched this class ahead
+                if (hit < 0) row_search(pick.csel, __shfl_sync(FULL, tot, pick.csel), u2, row, r);
             }
             if (lane == 0) {
                 s_csel = pick.csel; s_zero = pick.zero; s_tie = pick.tie != 0; s_total = pick.total;
-                s_row = row; s_rin = r;
+                s_row = row; s_rin = r; s_hit = hit;
             }
+        } else if (my_cand >= 0) {
+            const int cnt = s_pub_tot[my_cand];
+            int row = 0;
+            uint32_t r = 0;
+            if (cnt > 0) row_search(my_cand, cnt, s_pub_u2, row, r);
+            if (lane == 0) { s_spec_row[warp] = row; s_spec_rin[warp] = r; }
         }
-        if (tid < 12) s_slot_tot[tid] = 0;
         __syncthreads();                                               // B1
         WTRACE(1);
         if (s_zero) {                                                  // kmc.py:31-32: nothing can happen
@@ -264,7 +303,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
             }
             break;
         }
-        const int csel = s_csel, row = s_row;
+        const int csel = s_csel, row = s_hit >= 0 ? s_spec_row[s_hit] : s_row;
         const double total = s_total;
         const int tie = s_tie;
 
@@ -335,7 +374,7 @@ __global__ void __launch_bounds__(256, 1) kmc_replica_wide2_kernel(const WidePar
         }
         __syncthreads();                                               // B2
         WTRACE(2);
-        uint32_t r = s_rin;
+        uint32_t r = s_hit >= 0 ? s_spec_rin[s_hit] : s_rin;
         int j = 0;
 #pragma unroll
         for (int q = 0; q < (MM ? 11 : 5); q++)
