@@ -1104,7 +1104,8 @@ def test_move_monovacancy_incremental_equals_no_incremental_and_perform_given():
 # ---- the no-incremental event on the bit-sliced lattice (noinc_planes_kernel.cuh) ---------------------------------
 @pytest.mark.parametrize("rules", ["reference", "with_move_monovacancy"])
 @pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 120), ((7, 130), 150),
-                                        ((33, 2100), 60), ((5, 64), 100), ((130, 65), 100), ((512, 4096), 40)])
+                                        ((33, 2100), 60), ((5, 64), 100), ((130, 65), 100), ((512, 4096), 40),
+                                        ((7, 8192), 40), ((5, 16384), 40)])
 def test_no_incremental_on_planes_matches_oracle(dim, nsteps, rules, monkeypatch):
     """Large lattices take the plane path by themselves (>= 65536 sites); KMC_NOINC_PLANES=1 forces it for the
     small and ragged shapes too.  Trefoils present (evolved lattice), two replicas, two launches, hop counters,
@@ -1176,6 +1177,26 @@ def test_plane_no_incremental_launch_forms_agree(dim, launch, monkeypatch):
         assert_events_equal(ev[r], want, "%s replica %d" % (launch, r))
         assert (final[r] == o.status()).all()
     assert (eng.steps_done() == nsteps).all()
+    eng.close()
+
+
+def test_plane_no_incremental_batch_too_large_for_one_cooperative_launch(monkeypatch):
+    """48 replicas of 300 x 260 are 1824 CTAs -- more than fit on the device at once -- so the call falls back to one
+    launch per event by itself; a sample of replicas against the oracle."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "1")
+    dim, nrep, nsteps = (300, 260), 48, 40
+    sts = np.stack([iid_state(dim, 900 + r, p=(0.80, 0.05, 0.05, 0.10)) for r in range(nrep)])
+    eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=nrep)
+    eng.upload_state(sts)
+    l0 = eng.launch_count()
+    ev = eng.run_noinc(nsteps, 17, log_mode=nat.LOG_COMPACT)
+    assert eng.launch_count() - l0 >= nsteps            # (one kernel per event, plus the pack of the planes)
+    final = eng.download_state()
+    for r in (0, 1, 23, 47):
+        o = ko.Oracle(dim, TEST_RATES, ALL_ORDER, sts[r])
+        _, want = o.run_philox(17, r, 0, nsteps)
+        assert_events_equal(ev[r], want, "replica %d" % r)
+        assert (final[r] == o.status()).all()
     eng.close()
 
 
