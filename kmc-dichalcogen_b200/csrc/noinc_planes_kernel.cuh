@@ -165,12 +165,8 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
                     const u64 zn = Zw[rn][nib(NBR_DB, k) + 1];
                     // present, present & near, present & far, all three: the four kinds follow by inclusion-exclusion
                     const u64 pr = dv & zn, pn = pr & Dw[re][nib(NEAR_DB, k) + 2], pf = pr & Dw[rf][nib(FAR_DB, k) + 2];
-#ifdef KMC_ENUM_OLD
-                    { uint32_t c01, c23; kind_counts(pr, Dw[re][nib(NEAR_DB, k) + 2], Dw[rf][nib(FAR_DB, k) + 2], c01, c23); nP += c01; nPN += c23; }
-#else
                     nP += __popcll(pr); nPN += __popcll(pn); nPF += __popcll(pf);
                     nPNF += __popcll(pn & pf);
-#endif
                     if (MM) {
                         const u64 m1n = M1w[rn][nib(NBR_DB, k) + 1], m2n = M2w[rn][nib(NBR_DB, k) + 1];
                         nm += (uint32_t)__popcll((m1 | m2) & zn) | ((uint32_t)__popcll((m1 & m2n) | (m2 & m1n)) << 16);
@@ -180,12 +176,8 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
                 const u64 both = dv & Dw[i + 3][2];
                 acc[i][0] = (uint32_t)__popcll(zv) | ((uint32_t)__popcll(dv) << 16);
                 acc[i][1] = (uint32_t)__popcll(mono) | ((uint32_t)__popcll(anch) << 16);
-#ifdef KMC_ENUM_OLD
-                acc[i][2] = nP; acc[i][3] = nPN;
-#else
                 acc[i][2] = (nP - nPN - nPF + nPNF) | ((nPN - nPNF) << 16);        // natural | missing-metal
                 acc[i][3] = (nPF - nPNF) | (nPNF << 16);                            // missing-comb | missing-both
-#endif
                 acc[i][4] = (uint32_t)(__popcll(both & Dw[i + 1][4]) + __popcll(both & Dw[i + 3][0]));
                 acc[i][5] = nm; acc[i][6] = sw;
             }
