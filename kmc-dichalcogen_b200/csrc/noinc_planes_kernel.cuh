@@ -14,7 +14,7 @@
 //     (same fp64 sequence as every other kernel), finds record -> row -> slot -> cell -> bit with three dependent
 //     rounds of loads, and flips the touched bits of the planes (and their halo copies) with atomics.
 // Tried and dropped (profiles/README.md): a fixed selector CTA per replica; relaxed polling with back-off; a rolled
-// row loop in the enumeration (smaller code, but the loads no longer overlap: 16.5 vs 15.4 us); an unrolled one-shot
+// row loop in the enumeration (smaller code, no faster); an unrolled one-shot
 // class choice (1200 straight-line instructions run once by a lone warp cost ~20 cycles of instruction fetch each).
 // (History: two launches -- 1024 CTAs of one row x 64 cells, then a one-CTA selection kernel with ~10 dependent L2
 // round trips -- took 10.8 + 11.4 us.)
