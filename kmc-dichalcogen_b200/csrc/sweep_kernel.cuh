@@ -445,26 +445,24 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
         if (MM && tid < rows_in_cta * 4) rows_mm[tid] = s_mm;
         __syncthreads();
     } else {
-        const uint32_t mask = __match_any_sync(0xFFFFFFFFu, row_local);
+        // rows shorter than a warp: a row is cpr consecutive lanes (cpr is a power of two), summed by xor shuffles inside
+        // the group; its first lane stores the row's record (every row of the CTA has exactly one owner: no zeroing, no
+        // atomics).  16-bit fields: a row of < 512 sites holds < 6144 moves of a class.
 #pragma unroll
-        for (int j = 0; j < NP; j++) pk[j] = __reduce_add_sync(mask, pk[j]);
-        __syncthreads();                                                   // rows_sm / rows_mm zeroed by everyone
-        if ((__ffs(mask) - 1) == lane) {
+        for (int j = 0; j < NP; j++)
+            for (int o = cpr >> 1; o >= 1; o >>= 1) pk[j] += __shfl_xor_sync(0xFFFFFFFFu, pk[j], o);
+        if ((lane & (cpr - 1)) == 0) {
             uint32_t *R = rows_sm + row_local * RCG_STRIDE;
 #pragma unroll
             for (int j = 0; j < 7; j++) {
-                const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
-                if (lo) atomicAdd(R + 2 * j, lo);
-                if (hi) atomicAdd(R + 2 * j + 1, hi);
+                R[2 * j] = pk[j] & 0xFFFFu;
+                R[2 * j + 1] = 2 * j + 1 < NC ? pk[j] >> 16 : 0u;
             }
+            R[14] = 0; R[15] = 0;
             if (MM) {
                 uint32_t *R4 = rows_mm + row_local * 4;
 #pragma unroll
-                for (int j = 7; j < NP; j++) {
-                    const uint32_t lo = pk[j] & 0xFFFFu, hi = pk[j] >> 16;
-                    if (lo) atomicAdd(R4 + 2 * (j - 7), lo);
-                    if (hi) atomicAdd(R4 + 2 * (j - 7) + 1, hi);
-                }
+                for (int j = 7; j < NP; j++) { R4[2 * (j - 7)] = pk[j] & 0xFFFFu; R4[2 * (j - 7) + 1] = pk[j] >> 16; }
             }
         }
         __syncthreads();
@@ -786,10 +784,6 @@ __global__ void __launch_bounds__(256, MM ? 4 : KMC_SWEEP_OCC) kmc_sweep16n_kern
         const uint32_t m_next = __ldg(reinterpret_cast<const uint32_t *>(rm + cin));
         const uint32_t p_prev = __ldg(reinterpret_cast<const uint32_t *>(rp + cim) + 3);
         const uint32_t q_prev = __ldg(reinterpret_cast<const uint32_t *>(rq + cim) + 3);
-        if (cpr < 32) {
-            for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) rows_sm[i] = 0;
-            if (MM) for (int i = tid; i < rows_in_cta * 4; i += 256) rows_mm[i] = 0;
-        }
         const uint32_t ncp = pack_nib(0u, c_prev), ncn = pack_nib(c_next, 0u);
         const uint32_t nm0 = pack_nib(m4.x, m4.y), nm1 = pack_nib(m4.z, m4.w), nmn = pack_nib(m_next, 0u);
         const uint32_t npp = pack_nib(0u, p_prev), np0 = pack_nib(p4.x, p4.y), np1 = pack_nib(p4.z, p4.w);
