@@ -146,8 +146,8 @@ int kmc_perform_given(kmc_engine *h, int replica, uint32_t site, int slot);
 
 /* The `--no-incremental` event (sim.py:114-143) on a lattice of any size held in HBM: full sweep,
  * class selection + hierarchical in-class rank search, apply.  Same draws and records as kmc_run.  At most 2^30
- * events per call (KMC_ERR_ARG beyond that).  Lattices of 65536 sites and more run on bit planes, one kernel per
- * event -- one cooperative launch for the whole call when all its CTAs can be resident; the status bytes are
+ * events per call (KMC_ERR_ARG beyond that).  Lattices with rows of at most 16384 sites run on bit planes, one kernel
+ * per event -- one cooperative launch for the whole call when all its CTAs can be resident; the status bytes are
  * brought up to date when they are asked for. */
 int kmc_run_noinc(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t replica0, int log_mode,
                   void *events);

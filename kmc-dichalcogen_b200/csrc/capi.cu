@@ -944,10 +944,12 @@ static int noinc_launch(kmc_engine *h, int64_t nsteps, uint64_t seed, uint32_t r
     p.steps_done = h->d_steps; p.hist = h->d_hist; p.hops = h->d_hops; p.ties = h->d_ties; p.flags = h->d_flags;
     p.any_flag = h->d_anyflag; p.draws = d_draws;
     p.clock = h->clock_mode ? h->d_clock : nullptr; p.clock_mode = h->clock_mode;
-        p.tracer = h->tracer_on ? h->d_tracer : nullptr;
-    // Large lattices: the event runs on the bit-sliced lattice (noinc_planes_kernel.cuh) -- 64 sites per operation in
-    // the enumeration instead of 8.  (KMC_NOINC_PLANES=0/1 forces the choice.)
-    bool on_planes = h->n >= 65536 && wide_anchor_words(h->d1) <= 256;
+    p.tracer = h->tracer_on ? h->d_tracer : nullptr;
+    // The event runs on the bit-sliced lattice (noinc_planes_kernel.cuh) -- 64 sites per operation in the enumeration
+    // instead of 8, one kernel per event -- for every lattice with rows of at most 16384 sites: 9.7 us per event from
+    // 64 x 64 to 1024 x 1024 (byte path 15-30 us), 14.5 us at 4096 x 4096 (`profiles/probe_noinc_small.py`).
+    // (KMC_NOINC_PLANES=0/1 forces the choice.)
+    bool on_planes = wide_anchor_words(h->d1) <= 256;
     if (const char *e = getenv("KMC_NOINC_PLANES")) on_planes = atoi(e) != 0 && wide_anchor_words(h->d1) <= 256;
     if (on_planes) {
         const int We = wide_row_words(h->d1);

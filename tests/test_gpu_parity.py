@@ -98,7 +98,7 @@ def test_golden_trajectory_injected_draws(name):
 
 @pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, "noinc"])
 @pytest.mark.parametrize("name", boundary_tie_names())
-def test_boundary_ties_on_every_kernel(name, variant):
+def test_boundary_ties_on_every_kernel(name, variant, monkeypatch):
     """north star: "trajectories that diverge only at a cumulative-rate boundary tie are reported and counted".
     The fixtures (made from the unmodified reference, oracle/make_golden.py:boundary_tie_trajectory) place a
     third of the class draws EXACTLY on a cumulative weight, where the reference's bisect_left (kmc.py:50) takes
@@ -112,6 +112,7 @@ def test_boundary_ties_on_every_kernel(name, variant):
     eng = Engine(m["dim"], g["rates"], m["class_order"], n_replicas=1)
     eng.upload_state(g["status0"])
     if variant == "noinc":
+        monkeypatch.setenv("KMC_NOINC_PLANES", "0")      # the byte-lattice path (the plane path has its own tie test)
         ev = eng.step_draws_noinc(g["draws"], log_mode=nat.LOG_FULL)[0]
     else:
         eng.set_replica_kernel(variant)
@@ -480,7 +481,9 @@ def test_sweep_full_size_4096_every_rule():
 
 
 @pytest.mark.parametrize("dim,nsteps", [((64, 64), 300), ((50, 36), 200), ((9, 11), 200), ((300, 260), 60)])
-def test_no_incremental_path_matches_oracle(dim, nsteps):
+def test_no_incremental_path_matches_oracle(dim, nsteps, monkeypatch):
+    """The byte-lattice path (count-only sweep + one-CTA selection); the bit-plane path has its own tests below."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "0")
     st0 = exact_state(dim, 0.1, 0.1, 77)
     eng = Engine(dim, TEST_RATES, ALL_ORDER, n_replicas=2)
     eng.upload_state(np.stack([st0, st0]))
@@ -556,9 +559,10 @@ def test_statistics_only_launch_reports_a_stop_through_check_status(variant):
     eng.close()
 
 
-def test_no_incremental_path_after_a_stop_on_an_earlier_lattice():
+def test_no_incremental_path_after_a_stop_on_an_earlier_lattice(monkeypatch):
     """kmc_noinc_select_apply_kernel returns at entry when the replica's zero-rate flag is set; the
     flag must be cleared with the lattice, and records of steps that never ran must read CLASS_NONE."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "0")          # the byte-lattice path (the plane path: see below)
     dim = (9, 11)
     rates = [0.0] * 13
     rates[1] = 5.0
@@ -1231,9 +1235,10 @@ def test_plane_no_incremental_path_stops_on_zero_rate(monkeypatch):
 
 
 @pytest.mark.parametrize("dim", [(64, 64), (16, 4096), (128, 32)])
-def test_no_incremental_with_move_monovacancy_on_aligned_shapes(dim):
-    """Aligned shapes enumerate with the MoveMonovacancy builds of the nibble sweep kernels, whose MoveMonovacancy row
-    counts live in their own table: the no-incremental selection must read both."""
+def test_no_incremental_with_move_monovacancy_on_aligned_shapes(dim, monkeypatch):
+    """Byte-lattice path: aligned shapes enumerate with the MoveMonovacancy builds of the nibble sweep kernels, whose
+    MoveMonovacancy row counts live in their own table: the no-incremental selection must read both."""
+    monkeypatch.setenv("KMC_NOINC_PLANES", "0")
     st0 = exact_state(dim, 0.15, 0.15, 8)
     eng = Engine(dim, MM_RATES, MM_ORDER)
     eng.upload_state(st0)
