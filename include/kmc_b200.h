@@ -219,7 +219,8 @@ int kmc_get_device_pointers(kmc_engine *h, void **status, void **slots, void **r
 int kmc_set_warps_per_block(kmc_engine *h, int warps);
 int kmc_set_replica_kernel(kmc_engine *h, int variant);
 /* aligned-shape sweep kernel: 0 = automatic (rolling window over rows when a row fills a CTA, i.e. 4096
- * sites; else nibble-parallel + PRMT tables), 1 = nibble-parallel + PRMT, 2 = byte-parallel.  Same results. */
+ * sites; else nibble-parallel + PRMT tables), 1 = nibble-parallel + PRMT, 2 = byte-parallel (with MoveMonovacancy
+ * enabled: the same kernel as 1; the byte-parallel kernel has no build for that rule).  Same results. */
 int kmc_set_sweep_kernel(kmc_engine *h, int variant);
 /* measurement helper: successive kmc_sweep calls write two alternating slot-plane buffers (steady-state
  * bandwidth: no launch rewrites lines its predecessor left dirty in L2).  Getters read the latest one. */
