@@ -346,7 +346,11 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
     if (with_slots && !h->d_slots) CU(cudaMalloc(&h->d_slots, R * nsl * h->n));
     // aligned fast path: 16 sites per thread, CTAs aligned to rows and replicas
     const int cpr = h->d1 >> 4;
-    const bool aligned = (h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && ((h->n >> 4) % 256) == 0;
+    const int cpl_all = h->n >> 4;                     // 16-site chunks per lattice
+    // (lattices of fewer than 4096 sites: a CTA of the 16-sites-per-thread kernel holds several whole replicas)
+    const bool aligned_small = (h->d1 & 15) == 0 && cpr >= 1 && (256 % cpr) == 0 && (h->n & 15) == 0 && cpl_all < 256 &&
+                               (256 % cpl_all) == 0 && ((long long)h->R * cpl_all) % 256 == 0;
+    const bool aligned = ((h->d1 & 15) == 0 && cpr <= 256 && (256 % cpr) == 0 && (cpl_all % 256) == 0) || aligned_small;
     // MoveMonovacancy live on an aligned shape: the MoveMonovacancy builds of the nibble kernels write all 29 planes;
     // the row counts are split over two tables, d_rowcnt [..][16] (classes 0..12) and d_rowmm [..][4] (classes 13..16)
     const bool mm_split = h->mm && aligned;
@@ -421,10 +425,10 @@ static int sweep_launch(kmc_engine *h, bool with_slots)
         q.d0 = h->d0; q.d1 = h->d1; q.n = h->n; q.n_replicas = h->R;
         q.status = h->d_status; q.slots = with_slots ? h->d_slots : nullptr; q.rowcnt = h->d_rowcnt;
         q.acc = h->d_acc; q.ticket = h->d_ticket; q.counts = h->d_counts;
-        q.ctas_per_replica = (h->n >> 4) / 256; q.nplanes = nsl; q.rowmm = mm_split ? h->d_rowmm : nullptr;
-        const long long blocks = (long long)R * q.ctas_per_replica;
+        q.ctas_per_replica = (h->n >> 4) / 256; q.nplanes = nsl; q.rowmm = mm_split ? h->d_rowmm : nullptr;      // (0: several replicas per CTA)
+        const long long blocks = aligned_small ? ((long long)R * cpl_all) / 256 : (long long)R * q.ctas_per_replica;
         if (mm_split) kmc_sweep16n_kernel<true><<<(unsigned)blocks, 256, 0, h->stream>>>(q);     // (variant 2 has no MoveMonovacancy build)
-        else if (h->sweep_variant == 2) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
+        else if (h->sweep_variant == 2 && !aligned_small) kmc_sweep16_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         else kmc_sweep16n_kernel<false><<<(unsigned)blocks, 256, 0, h->stream>>>(q);
         CU(cudaGetLastError());
         h->launches += 1;

@@ -468,13 +468,29 @@ __device__ __forceinline__ void row_counts_epilogue(const Sweep16Params &p, uint
         __syncthreads();
     }
     {
-        const int first_row = a - row_local;
-        uint32_t *G = p.rowcnt + ((size_t)rep * p.d0 + first_row) * RCG_STRIDE;
+        // (the CTA's rows are consecutive in the [replica][row] tables, also when it spans several small replicas)
+        const size_t first_row = (size_t)blockIdx.x * rows_in_cta;
+        (void)a; (void)row_local;
+        uint32_t *G = p.rowcnt + first_row * RCG_STRIDE;
         for (int i = tid; i < rows_in_cta * RCG_STRIDE; i += 256) G[i] = rows_sm[i];
         if (MM) {
-            uint32_t *G4 = p.rowmm + ((size_t)rep * p.d0 + first_row) * 4;
+            uint32_t *G4 = p.rowmm + first_row * 4;
             for (int i = tid; i < rows_in_cta * 4; i += 256) G4[i] = rows_mm[i];
         }
+    }
+    if (p.ctas_per_replica == 0) {
+        // lattices of fewer than 4096 sites: the CTA holds 256 / (chunks per lattice) whole replicas; thread (local
+        // replica, class) sums the replica's rows and publishes its total directly
+        constexpr int NCX = MM ? NCA : NC;
+        const int cpl = p.n >> 4, reps_in_cta = 256 / cpl, d0 = p.d0;
+        for (int idx = tid; idx < reps_in_cta * NCX; idx += 256) {
+            const int lr = idx / NCX, c = idx - lr * NCX;
+            unsigned long long s = 0;
+            for (int r = 0; r < d0; r++)
+                s += c < NC ? rows_sm[(lr * d0 + r) * RCG_STRIDE + c] : rows_mm[(lr * d0 + r) * 4 + c - NC];
+            p.counts[((size_t)blockIdx.x * reps_in_cta + lr) * NCA + c] = s;
+        }
+        return;
     }
     if (tid < 32) {
         constexpr int NCX = MM ? NCA : NC;

@@ -462,6 +462,27 @@ def test_sweep_with_move_monovacancy_on_the_forced_aligned_kernels(dim, variant)
     eng.close()
 
 
+@pytest.mark.parametrize("rules", ["reference", "with_move_monovacancy"])
+@pytest.mark.parametrize("dim,nrep", [((16, 64), 8), ((64, 16), 4), ((32, 32), 12), ((8, 16), 64), ((16, 16), 48), ((8, 128), 6),
+                                      ((32, 64), 2), ((16, 64), 3)])
+def test_sweep_of_small_lattices_several_replicas_per_cta(dim, nrep, rules):
+    """Lattices of fewer than 4096 sites whose 16-site chunks divide a CTA: one CTA of the nibble kernel holds several
+    whole replicas (the last case does not fill whole CTAs and takes the general kernels)."""
+    RATES, ORDER = (MM_RATES, MM_ORDER) if rules == "with_move_monovacancy" else (TEST_RATES, ALL_ORDER)
+    sts = [iid_state(dim, 70 + r, p=(0.6, 0.15, 0.15, 0.1)) for r in range(nrep)]
+    eng = Engine(dim, RATES, ORDER, n_replicas=nrep)
+    eng.upload_state(np.stack(sts))
+    eng.sweep()
+    eng.sweep()
+    slots, counts, rows = eng.slots(), eng.counts(), eng.row_counts()
+    for r in range(nrep):
+        ws, wc, wr = ko.sweep(sts[r], dim)
+        if rules == "reference":
+            ws, wc, wr = reference_rules_only(ws, wc, wr)
+        assert (slots[r] == ws).all() and (counts[r] == wc).all() and (rows[r] == wr).all(), r
+    eng.close()
+
+
 def test_sweep_full_size_4096_every_rule():
     """BASELINE config 4 with config/WSe2.yaml's full rule set: 29 planes, 17 classes in ONE pass -- the rolling-window
     kernel (automatic) and the one-row-per-CTA nibble kernel (sweep variant 1) must both give the oracle's bytes."""
