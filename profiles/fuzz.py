@@ -14,7 +14,8 @@ stats = {"variant_runs": 0, "declined": 0, "zero_rate_cases": 0, "events": 0, "m
 while time.time() < deadline:
     ncase += 1
     d0 = int(rng.choice([5, 7, 8, 9, 13, 16, 31, 32, 33, 64, 65, 100, 128]))
-    d1 = int(rng.choice([5, 7, 8, 15, 16, 17, 32, 48, 63, 64, 65, 96, 128, 130, 200, 256]))
+    d1 = int(rng.choice([5, 7, 8, 15, 16, 17, 32, 48, 63, 64, 65, 96, 128, 130, 200, 256] +
+                        ([320, 512, 1000, 1024, 2048] if os.environ.get("FUZZ_WIDE") else [])))
     if d0 == 6 or d1 == 6:
         continue
     dim = (d0, d1)
