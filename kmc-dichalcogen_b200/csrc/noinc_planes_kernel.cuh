@@ -56,14 +56,12 @@ struct NoincPlanesParams {
     int skip_select;                     // measurement only (KMC_NOINC_DEBUG_SKIP): enumerate, elect, do not select
 };
 
-// Word wc of a plane row and the low half of word wc + 1 (all that ever shifts into a window).  The neighbour lane
-// holds that word already: one shuffle instead of a second trip to L2; only the last lane of the warp (and the lane
-// of the row's last anchor word) loads it.  Called by all 32 lanes.
-__device__ __forceinline__ u64 plane_word_pair(const u64 *rp, int wc, bool own_next, uint32_t &x1) {
-    const u64 x0 = rp[wc];
-    x1 = __shfl_down_sync(FULL, (uint32_t)x0, 1);
-    if (own_next) x1 = reinterpret_cast<const uint32_t *>(rp + wc + 1)[0];
-    return x0;
+// Word wc of a plane row and the low half of word wc + 1 (all that ever shifts into a window): two independent loads.
+// (Taking the second from the neighbour lane by shuffle saves the load but makes every window wait for a shuffle:
+// 14.5 instead of 14.0 us per 4096^2 event.)
+__device__ __forceinline__ u64 plane_word_pair(const u64 *rp, int wc, uint32_t &x1) {
+    x1 = reinterpret_cast<const uint32_t *>(rp + wc + 1)[0];
+    return rp[wc];
 }
 
 // the count of class c (record slot c) from the unpacked field sums: lo/hi[0] = pristine / divacancy sites,
@@ -113,10 +111,8 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
     if (a0 < d0) {                                                 // (warp-uniform)
         const u64 *P = q.planes + (size_t)rep * N_TYPES * d0 * We;
         WGeom G{P, d0, d1, Wa, We};
-        // lanes beyond the row's last cell run along on its last cell with an empty `valid` mask (they take part in
-        // the shuffles of plane_word_pair)
+        // lanes beyond the row's last cell run along on its last cell with an empty `valid` mask
         const int wc = min(w, Wa - 1);
-        const bool own_next = lane == 31 || w >= Wa - 1;
         const u64 valid = w < Wa ? G.valid(w) : 0ull;
         // windows of rows a0-1 .. a0+PNR+1 (index r = offset + 1): Z and the monovacancy layers at db -1, 0, +1
         // (index db + 1), D at db -2 .. +2 (index db + 2)
@@ -125,17 +121,17 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
         for (int r = 0; r < PNR + 3; r++) {
             const int ar = wrap1(a0 + r - 1, d0);                  // a0 < d0 and d0 >= 5: wraps at most once
             uint32_t x1;
-            const u64 x0 = plane_word_pair(G.rowp(T_D, ar), wc, own_next, x1);
+            const u64 x0 = plane_word_pair(G.rowp(T_D, ar), wc, x1);
 #pragma unroll
             for (int j = 0; j < 5; j++) Dw[r][j] = window(x0, (u64)x1, j - 2);
             if (r < PNR + 2) {
                 uint32_t y1;
-                const u64 y0 = plane_word_pair(G.rowp(T_Z, ar), wc, own_next, y1);
+                const u64 y0 = plane_word_pair(G.rowp(T_Z, ar), wc, y1);
 #pragma unroll
                 for (int j = 0; j < 3; j++) Zw[r][j] = window(y0, (u64)y1, j - 1);
                 if (MM) {
                     uint32_t u1, v1;
-                    const u64 u0 = plane_word_pair(G.rowp(T_M1, ar), wc, own_next, u1), v0 = plane_word_pair(G.rowp(T_M2, ar), wc, own_next, v1);
+                    const u64 u0 = plane_word_pair(G.rowp(T_M1, ar), wc, u1), v0 = plane_word_pair(G.rowp(T_M2, ar), wc, v1);
 #pragma unroll
                     for (int j = 0; j < 3; j++) { M1w[r][j] = window(u0, (u64)u1, j - 1); M2w[r][j] = window(v0, (u64)v1, j - 1); }
                 }
@@ -149,12 +145,12 @@ __device__ __forceinline__ void planes_enumerate(const NoincPlanesParams &q, int
                 u64 mono, anch, m1 = 0, m2 = 0;
                 {
                     uint32_t s1, t1;
-                    const u64 s0 = plane_word_pair(G.rowp(T_A4, a), wc, own_next, s1), t0 = plane_word_pair(G.rowp(T_A7, a), wc, own_next, t1);
+                    const u64 s0 = plane_word_pair(G.rowp(T_A4, a), wc, s1), t0 = plane_word_pair(G.rowp(T_A7, a), wc, t1);
                     anch = window(s0 | t0, (u64)(s1 | t1), 0) & valid;
                     if (MM) { m1 = M1w[i + 1][1] & valid; m2 = M2w[i + 1][1] & valid; mono = m1 | m2; }
                     else {
                         uint32_t u1, v1;
-                        const u64 u0 = plane_word_pair(G.rowp(T_M1, a), wc, own_next, u1), v0 = plane_word_pair(G.rowp(T_M2, a), wc, own_next, v1);
+                        const u64 u0 = plane_word_pair(G.rowp(T_M1, a), wc, u1), v0 = plane_word_pair(G.rowp(T_M2, a), wc, v1);
                         mono = window(u0 | v0, (u64)(u1 | v1), 0) & valid;
                     }
                 }
